@@ -1,0 +1,86 @@
+"""ctypes loader for libh2agg.so (the C ABI declared in include/h2agg.h).
+
+The product path has no CPU fallback: if the shared library is missing, or no B200 is present,
+loading / context creation raises.  PyTorch is not needed to use the library; bench.py and the
+multi-GPU host layer use it only for pinned buffers, events and torch.distributed.
+"""
+import ctypes
+import os
+import re
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libh2agg.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "h2agg.h")
+
+c_u64p = ctypes.POINTER(ctypes.c_uint64)
+c_vp = ctypes.c_void_p
+
+
+class H2aggError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def declared_symbols():
+    """Every function name include/h2agg.h declares (used by the CPU-side export test)."""
+    text = open(HEADER_PATH).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(h2agg_[a-z0-9_]+)\s*\(", text)))
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise H2aggError(
+            "libh2agg.so is not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'`. "
+            "There is no CPU fallback for the product path." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    sz, u32, u64, ci = ctypes.c_size_t, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_int
+    sig = {
+        "h2agg_init": (ci, [ci, ctypes.POINTER(c_vp)]),
+        "h2agg_destroy": (None, [c_vp]),
+        "h2agg_last_error": (ctypes.c_char_p, [c_vp]),
+        "h2agg_version": (ctypes.c_char_p, []),
+        "h2agg_set_stream": (ci, [c_vp, c_vp]),
+        "h2agg_synchronize": (ci, [c_vp]),
+        "h2agg_launch_count": (u64, [c_vp]),
+        "h2agg_host_register": (ci, [c_vp, c_vp, sz]),
+        "h2agg_host_unregister": (ci, [c_vp, c_vp]),
+        "h2agg_set_msm_window": (ci, [c_vp, ci]),
+        "h2agg_msm_config": (ci, [c_vp, sz, ctypes.POINTER(ci), ctypes.POINTER(ci)]),
+        "h2agg_srs_register": (ci, [c_vp, c_vp, sz, ctypes.POINTER(u64)]),
+        "h2agg_srs_register_dev": (ci, [c_vp, c_vp, sz, ctypes.POINTER(u64)]),
+        "h2agg_srs_release": (ci, [c_vp, u64]),
+        "h2agg_msm_g1": (ci, [c_vp, u64, c_vp, c_vp, sz, c_vp]),
+        "h2agg_msm_g1_batch": (ci, [c_vp, u64, ctypes.POINTER(c_vp), sz, sz, c_vp]),
+        "h2agg_msm_g1_dev": (ci, [c_vp, u64, c_vp, c_vp, sz, c_vp]),
+        "h2agg_msm_g1_windows": (ci, [c_vp, u64, c_vp, c_vp, sz, ci, ci, c_vp]),
+        "h2agg_msm_g1_windows_dev": (ci, [c_vp, u64, c_vp, c_vp, sz, ci, ci, c_vp]),
+        "h2agg_g1_sum": (ci, [c_vp, c_vp, sz, c_vp]),
+        "h2agg_ntt_fr": (ci, [c_vp, c_vp, c_vp, u32]),
+        "h2agg_intt_fr": (ci, [c_vp, c_vp, c_vp, c_vp, u32]),
+        "h2agg_ntt_fr_dev": (ci, [c_vp, c_vp, c_vp, c_vp, u32]),
+        "h2agg_coeff_to_extended": (ci, [c_vp, c_vp, u32, u32, c_vp, c_vp, c_vp]),
+        "h2agg_extended_to_coeff": (ci, [c_vp, c_vp, u32, c_vp, c_vp, c_vp, sz]),
+        "h2agg_coeff_to_extended_dev": (ci, [c_vp, c_vp, u32, u32, c_vp, c_vp, c_vp]),
+        "h2agg_extended_to_coeff_dev": (ci, [c_vp, c_vp, u32, c_vp, c_vp, c_vp, sz]),
+        "h2agg_field_mul": (ci, [c_vp, ci, c_vp, c_vp, c_vp, sz]),
+        "h2agg_field_op": (ci, [c_vp, ci, ci, c_vp, c_vp, c_vp, sz]),
+        "h2agg_dev_alloc": (ci, [c_vp, sz, ctypes.POINTER(c_vp)]),
+        "h2agg_dev_free": (ci, [c_vp, c_vp]),
+        "h2agg_memcpy_h2d": (ci, [c_vp, c_vp, c_vp, sz]),
+        "h2agg_memcpy_d2h": (ci, [c_vp, c_vp, c_vp, sz]),
+        "h2agg_synth_scalars_dev": (ci, [c_vp, u64, ci, u64, u64, c_vp]),
+        "h2agg_synth_bases_dev": (ci, [c_vp, u64, u64, u64, c_vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)  # AttributeError here = header and library out of sync
+        fn.restype = res
+        fn.argtypes = args
+    lib._h2agg_signatures = sig
+    _lib = lib
+    return lib

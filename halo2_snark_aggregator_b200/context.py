@@ -1,0 +1,167 @@
+"""Context = one GPU, one stream, resident SRS and twiddle tables (h2agg_ctx)."""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import H2aggError, c_vp
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return c_vp(a)
+    assert isinstance(a, np.ndarray) and a.dtype == np.uint64 and a.flags["C_CONTIGUOUS"], "need contiguous uint64 ndarray"
+    return c_vp(a.ctypes.data)
+
+
+class Context:
+    """Owns an h2agg_ctx. Raises H2aggError if the library or a B200 is missing (no CPU fallback)."""
+
+    def __init__(self, device=0):
+        self.lib = _lib.load()
+        h = c_vp()
+        rc = self.lib.h2agg_init(int(device), ctypes.byref(h))
+        if rc != 0:
+            raise H2aggError("h2agg_init failed (%d): %s" % (rc, self.lib.h2agg_last_error(None).decode()))
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.h2agg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc):
+        if rc != 0:
+            raise H2aggError("h2agg error %d: %s" % (rc, self.lib.h2agg_last_error(self.h).decode()))
+
+    # -- plumbing
+    def set_stream(self, cuda_stream_ptr):
+        self.check(self.lib.h2agg_set_stream(self.h, c_vp(cuda_stream_ptr)))
+
+    def synchronize(self):
+        self.check(self.lib.h2agg_synchronize(self.h))
+
+    def launch_count(self):
+        return int(self.lib.h2agg_launch_count(self.h))
+
+    def set_msm_window(self, c):
+        self.check(self.lib.h2agg_set_msm_window(self.h, int(c)))
+
+    def msm_config(self, n):
+        c, w = ctypes.c_int(), ctypes.c_int()
+        self.check(self.lib.h2agg_msm_config(self.h, n, ctypes.byref(c), ctypes.byref(w)))
+        return c.value, w.value
+
+    def dev_alloc(self, nbytes):
+        p = c_vp()
+        self.check(self.lib.h2agg_dev_alloc(self.h, nbytes, ctypes.byref(p)))
+        return p.value
+
+    def dev_free(self, p):
+        self.check(self.lib.h2agg_dev_free(self.h, c_vp(p)))
+
+    def h2d(self, d_dst, arr):
+        self.check(self.lib.h2agg_memcpy_h2d(self.h, c_vp(d_dst), _ptr(arr), arr.nbytes))
+
+    def d2h(self, d_src, n_u64):
+        out = np.empty(n_u64, dtype=np.uint64)
+        self.check(self.lib.h2agg_memcpy_d2h(self.h, _ptr(out), c_vp(d_src), out.nbytes))
+        return out
+
+    def synth_scalars_dev(self, seed, kind, first, n, d_out):
+        self.check(self.lib.h2agg_synth_scalars_dev(self.h, seed, kind, first, n, c_vp(d_out)))
+
+    def synth_bases_dev(self, seed, first, n, d_out):
+        self.check(self.lib.h2agg_synth_bases_dev(self.h, seed, first, n, c_vp(d_out)))
+
+    # -- SRS
+    def srs_register(self, bases):
+        sid = ctypes.c_uint64()
+        self.check(self.lib.h2agg_srs_register(self.h, _ptr(bases), bases.size // 8, ctypes.byref(sid)))
+        return sid.value
+
+    def srs_register_dev(self, d_bases, n):
+        sid = ctypes.c_uint64()
+        self.check(self.lib.h2agg_srs_register_dev(self.h, c_vp(d_bases), n, ctypes.byref(sid)))
+        return sid.value
+
+    def srs_release(self, sid):
+        self.check(self.lib.h2agg_srs_release(self.h, sid))
+
+    # -- K1
+    def msm_g1(self, scalars, bases=None, srs_id=0, n=None, windows=None):
+        n = scalars.size // 4 if n is None else n
+        out = np.zeros(12, dtype=np.uint64)
+        if windows is None:
+            self.check(self.lib.h2agg_msm_g1(self.h, srs_id, _ptr(bases), _ptr(scalars), n, _ptr(out)))
+        else:
+            self.check(self.lib.h2agg_msm_g1_windows(self.h, srs_id, _ptr(bases), _ptr(scalars), n, windows[0], windows[1], _ptr(out)))
+        return out
+
+    def msm_g1_dev(self, d_scalars, n, d_out160, d_bases=0, srs_id=0, windows=None):
+        if windows is None:
+            self.check(self.lib.h2agg_msm_g1_dev(self.h, srs_id, c_vp(d_bases), c_vp(d_scalars), n, c_vp(d_out160)))
+        else:
+            self.check(self.lib.h2agg_msm_g1_windows_dev(self.h, srs_id, c_vp(d_bases), c_vp(d_scalars), n, windows[0], windows[1], c_vp(d_out160)))
+
+    def msm_g1_batch(self, srs_id, cols, n=None):
+        n = cols[0].size // 4 if n is None else n
+        arr = (c_vp * len(cols))(*[c.ctypes.data if isinstance(c, np.ndarray) else c for c in cols])
+        out = np.zeros(8 * len(cols), dtype=np.uint64)
+        self.check(self.lib.h2agg_msm_g1_batch(self.h, srs_id, arr, len(cols), n, _ptr(out)))
+        return out.reshape(len(cols), 8)
+
+    def g1_sum(self, points_jac):
+        out = np.zeros(12, dtype=np.uint64)
+        self.check(self.lib.h2agg_g1_sum(self.h, _ptr(points_jac), points_jac.size // 12, _ptr(out)))
+        return out
+
+    # -- K2 / K3 (host pointers, in place like the reference)
+    def ntt_fr(self, a, omega, log_n):
+        self.check(self.lib.h2agg_ntt_fr(self.h, _ptr(a), _ptr(omega), log_n))
+
+    def intt_fr(self, a, omega_inv, n_inv, log_n):
+        self.check(self.lib.h2agg_intt_fr(self.h, _ptr(a), _ptr(omega_inv), _ptr(n_inv), log_n))
+
+    def ntt_fr_dev(self, d_a, omega, log_n, scale=None):
+        self.check(self.lib.h2agg_ntt_fr_dev(self.h, c_vp(d_a), _ptr(omega), _ptr(scale), log_n))
+
+    def coeff_to_extended(self, coeffs, k, ext_k, zeta, omega_ext):
+        out = np.empty(4 << ext_k, dtype=np.uint64)
+        self.check(self.lib.h2agg_coeff_to_extended(self.h, _ptr(coeffs), k, ext_k, _ptr(zeta), _ptr(omega_ext), _ptr(out)))
+        return out
+
+    def extended_to_coeff(self, a, ext_k, omega_ext_inv, ext_n_inv, zeta, out_len):
+        self.check(self.lib.h2agg_extended_to_coeff(self.h, _ptr(a), ext_k, _ptr(omega_ext_inv), _ptr(ext_n_inv), _ptr(zeta), out_len))
+        return a[: 4 * out_len]
+
+    def coeff_to_extended_dev(self, d_coeffs, k, ext_k, zeta, omega_ext, d_out):
+        self.check(self.lib.h2agg_coeff_to_extended_dev(self.h, c_vp(d_coeffs), k, ext_k, _ptr(zeta), _ptr(omega_ext), c_vp(d_out)))
+
+    def extended_to_coeff_dev(self, d_a, ext_k, omega_ext_inv, ext_n_inv, zeta, out_len):
+        self.check(self.lib.h2agg_extended_to_coeff_dev(self.h, c_vp(d_a), ext_k, _ptr(omega_ext_inv), _ptr(ext_n_inv), _ptr(zeta), out_len))
+
+    # -- field helpers (device)
+    def field_op(self, field, op, a, b=None):
+        out = np.empty_like(a)
+        self.check(self.lib.h2agg_field_op(self.h, field, op, _ptr(a), _ptr(b), _ptr(out), a.size // 4))
+        return out
+
+
+_default = None
+
+
+def default_context():
+    global _default
+    if _default is None:
+        _default = Context(0)
+    return _default

@@ -1,0 +1,493 @@
+// C ABI (include/h2agg.h) over the CUDA path.  No CPU fallback lives here: every entry point
+// either runs the sm_100a kernels or returns an error.
+#include "../../include/h2agg.h"
+#include "bn254_g1.cuh"
+#include "ctx.hpp"
+#include <cstring>
+#include <new>
+
+using namespace h2agg;
+
+static thread_local std::string g_init_error;
+
+#define LOCK(ctx) std::lock_guard<std::recursive_mutex> lock_((ctx)->mu)
+#define CHECK_ARG(ctx, cond, msg) \
+  do {                            \
+    if (!(cond)) {                \
+      (ctx)->last_error = (msg);  \
+      return 1;                   \
+    }                             \
+  } while (0)
+
+extern "C" {
+
+const char* h2agg_version(void) { return "h2agg-b200 0.1 (sm_100a)"; }
+
+int h2agg_init(int device_id, h2agg_ctx** out) {
+  if (!out) return 1;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_init_error = std::string("h2agg_init: no CUDA device (") + cudaGetErrorString(e) + ")";
+    cudaGetLastError();
+    return 3;
+  }
+  if (device_id < 0 || device_id >= ndev) {
+    g_init_error = "h2agg_init: device id out of range";
+    return 1;
+  }
+  if ((e = cudaSetDevice(device_id)) != cudaSuccess) {
+    g_init_error = std::string("h2agg_init: cudaSetDevice: ") + cudaGetErrorString(e);
+    return 2;
+  }
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device_id)) != cudaSuccess) {
+    g_init_error = std::string("h2agg_init: ") + cudaGetErrorString(e);
+    return 2;
+  }
+  if (prop.major != 10) {
+    g_init_error = "h2agg_init: this library is built for sm_100a (Blackwell B200) only; found sm_" +
+                   std::to_string(prop.major) + std::to_string(prop.minor);
+    return 3;
+  }
+  h2agg_ctx* ctx = new (std::nothrow) h2agg_ctx();
+  if (!ctx) return 2;
+  ctx->device = device_id;
+  ctx->sm_count = prop.multiProcessorCount;
+  if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    g_init_error = std::string("h2agg_init: cudaStreamCreate: ") + cudaGetErrorString(e);
+    delete ctx;
+    return 2;
+  }
+  ctx->own_stream = true;
+  ctx->pinned_cap = 1 << 16;
+  if ((e = cudaMallocHost(&ctx->pinned, ctx->pinned_cap)) != cudaSuccess) {
+    g_init_error = std::string("h2agg_init: cudaMallocHost: ") + cudaGetErrorString(e);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return 2;
+  }
+  if (ensure(ctx, ctx->small, 1 << 16)) {
+    g_init_error = ctx->last_error;
+    h2agg_destroy(ctx);
+    return 2;
+  }
+  *out = ctx;
+  return 0;
+}
+
+void h2agg_destroy(h2agg_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& t : ctx->tw) {
+    cudaFree(t.lo);
+    cudaFree(t.hi);
+  }
+  for (auto& kv : ctx->srs)
+    if (kv.second.owned) cudaFree(const_cast<void*>(kv.second.d_bases));
+  cudaFree(ctx->ntt_tmp.p);
+  cudaFree(ctx->io_a.p);
+  cudaFree(ctx->io_b.p);
+  cudaFree(ctx->msm_ws.p);
+  cudaFree(ctx->small.p);
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* h2agg_last_error(h2agg_ctx* ctx) { return ctx ? ctx->last_error.c_str() : g_init_error.c_str(); }
+
+int h2agg_set_stream(h2agg_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return 1;
+  LOCK(ctx);
+  H2AGG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->own_stream) {
+    cudaStreamDestroy(ctx->stream);
+    ctx->own_stream = false;
+  }
+  ctx->stream = (cudaStream_t)cuda_stream;
+  return 0;
+}
+
+int h2agg_synchronize(h2agg_ctx* ctx) {
+  if (!ctx) return 1;
+  LOCK(ctx);
+  H2AGG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+uint64_t h2agg_launch_count(h2agg_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int h2agg_host_register(h2agg_ctx* ctx, const void* p, size_t bytes) {
+  if (!ctx) return 1;
+  LOCK(ctx);
+  H2AGG_CUDA(ctx, cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterDefault));
+  return 0;
+}
+int h2agg_host_unregister(h2agg_ctx* ctx, const void* p) {
+  if (!ctx) return 1;
+  LOCK(ctx);
+  H2AGG_CUDA(ctx, cudaHostUnregister(const_cast<void*>(p)));
+  return 0;
+}
+
+int h2agg_set_msm_window(h2agg_ctx* ctx, int c_bits) {
+  if (!ctx) return 1;
+  LOCK(ctx);
+  CHECK_ARG(ctx, c_bits == 0 || (c_bits >= 2 && c_bits <= 20), "msm window must be 0 or in [2, 20]");
+  ctx->msm_window_bits = c_bits;
+  return 0;
+}
+
+int h2agg_msm_config(h2agg_ctx* ctx, size_t n, int* c_bits, int* n_windows) {
+  if (!ctx || !c_bits || !n_windows) return 1;
+  LOCK(ctx);
+  return msm_window_config(n ? n : 1, ctx->msm_window_bits, c_bits, n_windows);
+}
+
+// ---- SRS ----------------------------------------------------------------------------------------
+int h2agg_srs_register(h2agg_ctx* ctx, const uint64_t* bases, size_t n, uint64_t* out_id) {
+  if (!ctx) return 1;
+  LOCK(ctx);
+  CHECK_ARG(ctx, bases && out_id && n > 0, "srs_register: null argument or n == 0");
+  H2AGG_CUDA(ctx, cudaSetDevice(ctx->device));
+  void* d = nullptr;
+  H2AGG_CUDA(ctx, cudaMalloc(&d, n * 64));
+  cudaError_t e = cudaMemcpyAsync(d, bases, n * 64, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) {
+    cudaFree(d);
+    ctx->last_error = std::string("srs_register: ") + cudaGetErrorString(e);
+    return 2;
+  }
+  Srs s;
+  s.d_bases = d;
+  s.n = n;
+  s.owned = true;
+  *out_id = ctx->next_srs++;
+  ctx->srs[*out_id] = s;
+  return 0;
+}
+
+int h2agg_srs_register_dev(h2agg_ctx* ctx, const void* d_bases, size_t n, uint64_t* out_id) {
+  if (!ctx) return 1;
+  LOCK(ctx);
+  CHECK_ARG(ctx, d_bases && out_id && n > 0, "srs_register_dev: null argument or n == 0");
+  Srs s;
+  s.d_bases = d_bases;
+  s.n = n;
+  s.owned = false;
+  *out_id = ctx->next_srs++;
+  ctx->srs[*out_id] = s;
+  return 0;
+}
+
+int h2agg_srs_release(h2agg_ctx* ctx, uint64_t id) {
+  if (!ctx) return 1;
+  LOCK(ctx);
+  auto it = ctx->srs.find(id);
+  CHECK_ARG(ctx, it != ctx->srs.end(), "srs_release: unknown srs id");
+  H2AGG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (it->second.owned) cudaFree(const_cast<void*>(it->second.d_bases));
+  ctx->srs.erase(it);
+  return 0;
+}
+
+// resolve the device pointer of the bases for an MSM of n pairs (uploads host bases to io_b if needed)
+static int resolve_bases(h2agg_ctx* ctx, uint64_t srs_id, const void* host_bases, const void* dev_bases, size_t n,
+                         const void** out) {
+  if (srs_id) {
+    auto it = ctx->srs.find(srs_id);
+    CHECK_ARG(ctx, it != ctx->srs.end(), "msm: unknown srs id");
+    CHECK_ARG(ctx, it->second.n >= n, "msm: more scalars than registered bases");
+    *out = it->second.d_bases;
+    return 0;
+  }
+  if (dev_bases) {
+    *out = dev_bases;
+    return 0;
+  }
+  CHECK_ARG(ctx, host_bases || n == 0, "msm: no bases given (srs_id == 0 and bases == NULL)");
+  int rc = ensure(ctx, ctx->io_b, n * 64 + 64);
+  if (rc) return rc;
+  if (n) H2AGG_CUDA(ctx, cudaMemcpyAsync(ctx->io_b.p, host_bases, n * 64, cudaMemcpyHostToDevice, ctx->stream));
+  *out = ctx->io_b.p;
+  return 0;
+}
+
+// ---- MSM ----------------------------------------------------------------------------------------
+int h2agg_msm_g1_windows(h2agg_ctx* ctx, uint64_t srs_id, const uint64_t* bases, const uint64_t* scalars, size_t n,
+                         int win_begin, int win_end, uint64_t out_jacobian[12]) {
+  if (!ctx) return 1;
+  LOCK(ctx);
+  CHECK_ARG(ctx, out_jacobian, "msm: out is NULL");
+  CHECK_ARG(ctx, scalars || n == 0, "msm: scalars is NULL");
+  H2AGG_CUDA(ctx, cudaSetDevice(ctx->device));
+  const void* d_bases;
+  int rc = resolve_bases(ctx, srs_id, bases, nullptr, n, &d_bases);
+  if (rc) return rc;
+  rc = ensure(ctx, ctx->io_a, n * 32 + 64);
+  if (rc) return rc;
+  if (n) H2AGG_CUDA(ctx, cudaMemcpyAsync(ctx->io_a.p, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  rc = msm_run(ctx, d_bases, ctx->io_a.p, n, ctx->small.p, win_begin, win_end);
+  if (rc) return rc;
+  H2AGG_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, ctx->small.p, 160, cudaMemcpyDeviceToHost, ctx->stream));
+  H2AGG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  memcpy(out_jacobian, (uint8_t*)ctx->pinned + 64, 96);
+  return 0;
+}
+
+int h2agg_msm_g1(h2agg_ctx* ctx, uint64_t srs_id, const uint64_t* bases, const uint64_t* scalars, size_t n,
+                 uint64_t out_jacobian[12]) {
+  return h2agg_msm_g1_windows(ctx, srs_id, bases, scalars, n, 0, -1, out_jacobian);
+}
+
+int h2agg_msm_g1_windows_dev(h2agg_ctx* ctx, uint64_t srs_id, const void* d_bases_in, const void* d_scalars, size_t n,
+                             int win_begin, int win_end, void* d_out160) {
+  if (!ctx) return 1;
+  LOCK(ctx);
+  CHECK_ARG(ctx, d_out160 && (d_scalars || n == 0), "msm_dev: null argument");
+  CHECK_ARG(ctx, srs_id || d_bases_in || n == 0, "msm_dev: no bases");
+  H2AGG_CUDA(ctx, cudaSetDevice(ctx->device));
+  const void* d_bases;
+  int rc = resolve_bases(ctx, srs_id, nullptr, d_bases_in, n, &d_bases);
+  if (rc) return rc;
+  return msm_run(ctx, d_bases, d_scalars, n, d_out160, win_begin, win_end);
+}
+
+int h2agg_msm_g1_dev(h2agg_ctx* ctx, uint64_t srs_id, const void* d_bases, const void* d_scalars, size_t n,
+                     void* d_out160) {
+  return h2agg_msm_g1_windows_dev(ctx, srs_id, d_bases, d_scalars, n, 0, -1, d_out160);
+}
+
+int h2agg_msm_g1_batch(h2agg_ctx* ctx, uint64_t srs_id, const uint64_t* const* cols, size_t n_cols, size_t n,
+                       uint64_t* out_affine) {
+  if (!ctx) return 1;
+  LOCK(ctx);
+  CHECK_ARG(ctx, srs_id != 0, "msm_batch: needs a registered srs");
+  CHECK_ARG(ctx, cols && out_affine, "msm_batch: null argument");
+  CHECK_ARG(ctx, n_cols * 160 <= ctx->small.cap && n_cols * 160 <= ctx->pinned_cap, "msm_batch: too many columns");
+  H2AGG_CUDA(ctx, cudaSetDevice(ctx->device));
+  const void* d_bases;
+  int rc = resolve_bases(ctx, srs_id, nullptr, nullptr, n, &d_bases);
+  if (rc) return rc;
+  // double-buffered upload: column i+1 crosses PCIe while column i is in the bucket kernels
+  rc = ensure(ctx, ctx->io_a, n * 32 + 64);
+  if (rc) return rc;
+  rc = ensure(ctx, ctx->io_b, n * 32 + 64);
+  if (rc) return rc;
+  for (size_t i = 0; i < n_cols; i++) {
+    CHECK_ARG(ctx, cols[i], "msm_batch: null column");
+    void* buf = (i & 1) ? ctx->io_b.p : ctx->io_a.p;
+    if (n) H2AGG_CUDA(ctx, cudaMemcpyAsync(buf, cols[i], n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    rc = msm_run(ctx, d_bases, buf, n, (uint8_t*)ctx->small.p + i * 160, 0, -1);
+    if (rc) return rc;
+  }
+  H2AGG_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, ctx->small.p, n_cols * 160, cudaMemcpyDeviceToHost, ctx->stream));
+  H2AGG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (size_t i = 0; i < n_cols; i++) memcpy(out_affine + i * 8, (uint8_t*)ctx->pinned + i * 160, 64);
+  return 0;
+}
+
+int h2agg_g1_sum(h2agg_ctx* ctx, const uint64_t* pts, size_t m, uint64_t out_jacobian[12]) {
+  if (!ctx) return 1;
+  LOCK(ctx);
+  CHECK_ARG(ctx, pts && out_jacobian && m > 0 && m * 96 + 256 <= ctx->small.cap, "g1_sum: bad argument");
+  H2AGG_CUDA(ctx, cudaSetDevice(ctx->device));
+  uint8_t* d_in = (uint8_t*)ctx->small.p + 256;
+  H2AGG_CUDA(ctx, cudaMemcpyAsync(d_in, pts, m * 96, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = g1_sum_jacobian(ctx, d_in, m, ctx->small.p);
+  if (rc) return rc;
+  H2AGG_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, ctx->small.p, 160, cudaMemcpyDeviceToHost, ctx->stream));
+  H2AGG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  memcpy(out_jacobian, (uint8_t*)ctx->pinned + 64, 96);
+  return 0;
+}
+
+// ---- NTT ----------------------------------------------------------------------------------------
+static int ntt_host(h2agg_ctx* ctx, const uint64_t* src, size_t src_n, uint64_t* dst, size_t dst_n, NttOpts o) {
+  H2AGG_CUDA(ctx, cudaSetDevice(ctx->device));
+  size_t N = (size_t)1 << o.log_n;
+  int rc = ensure(ctx, ctx->io_a, N * 32);
+  if (rc) return rc;
+  H2AGG_CUDA(ctx, cudaMemcpyAsync(ctx->io_a.p, src, src_n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  o.src_n = src_n;
+  o.dst_n = dst_n;
+  rc = ntt_run(ctx, ctx->io_a.p, ctx->io_a.p, o);
+  if (rc) return rc;
+  H2AGG_CUDA(ctx, cudaMemcpyAsync(dst, ctx->io_a.p, dst_n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  H2AGG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int h2agg_ntt_fr(h2agg_ctx* ctx, uint64_t* a, const uint64_t omega[4], uint32_t log_n) {
+  if (!ctx) return 1;
+  LOCK(ctx);
+  CHECK_ARG(ctx, a && omega, "ntt: null argument");
+  CHECK_ARG(ctx, log_n <= 28, "ntt: log_n > 28");
+  NttOpts o{omega, log_n, 0, 0, nullptr, nullptr};
+  size_t N = (size_t)1 << log_n;
+  return ntt_host(ctx, a, N, a, N, o);
+}
+
+int h2agg_intt_fr(h2agg_ctx* ctx, uint64_t* a, const uint64_t omega_inv[4], const uint64_t n_inv[4], uint32_t log_n) {
+  if (!ctx) return 1;
+  LOCK(ctx);
+  CHECK_ARG(ctx, a && omega_inv && n_inv, "intt: null argument");
+  CHECK_ARG(ctx, log_n >= 1 && log_n <= 28, "intt: log_n out of range");
+  uint64_t s3[12];
+  for (int i = 0; i < 3; i++) memcpy(s3 + 4 * i, n_inv, 32);
+  NttOpts o{omega_inv, log_n, 0, 0, nullptr, s3};
+  size_t N = (size_t)1 << log_n;
+  return ntt_host(ctx, a, N, a, N, o);
+}
+
+int h2agg_ntt_fr_dev(h2agg_ctx* ctx, void* d_a, const uint64_t omega[4], const uint64_t* scale, uint32_t log_n) {
+  if (!ctx) return 1;
+  LOCK(ctx);
+  CHECK_ARG(ctx, d_a && omega, "ntt_dev: null argument");
+  CHECK_ARG(ctx, log_n <= 28 && (log_n >= 1 || !scale), "ntt_dev: log_n out of range");
+  H2AGG_CUDA(ctx, cudaSetDevice(ctx->device));
+  uint64_t s3[12];
+  if (scale)
+    for (int i = 0; i < 3; i++) memcpy(s3 + 4 * i, scale, 32);
+  size_t N = (size_t)1 << log_n;
+  NttOpts o{omega, log_n, N, N, nullptr, scale ? s3 : nullptr};
+  return ntt_run(ctx, d_a, d_a, o);
+}
+
+// Montgomery products of a handful of field elements on the device (zeta powers etc.)
+__global__ void coset_consts_kernel(Fr zeta, Fr scale, int inverse, Fr* out3) {
+  if (threadIdx.x || blockIdx.x) return;
+  Fr z2 = zeta * zeta;
+  if (!inverse) {
+    Fr::one().store(out3);
+    zeta.store(out3 + 1);
+    z2.store(out3 + 2);
+  } else {  // scale * zeta^-(i mod 3); zeta^-1 = zeta^2
+    scale.store(out3);
+    (scale * z2).store(out3 + 1);
+    (scale * zeta).store(out3 + 2);
+  }
+}
+
+static int coset_consts(h2agg_ctx* ctx, const uint64_t zeta[4], const uint64_t* scale, int inverse, uint64_t out3[12]) {
+  Fr z, s;
+  memcpy(z.v, zeta, 32);
+  if (scale) memcpy(s.v, scale, 32); else memset(s.v, 0, 32);
+  Fr* d = (Fr*)((uint8_t*)ctx->small.p + 4096);
+  coset_consts_kernel<<<1, 32, 0, ctx->stream>>>(z, s, inverse, d);
+  ctx->launches++;
+  H2AGG_CUDA(ctx, cudaGetLastError());
+  H2AGG_CUDA(ctx, cudaMemcpyAsync((uint8_t*)ctx->pinned + 4096, d, 96, cudaMemcpyDeviceToHost, ctx->stream));
+  H2AGG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  memcpy(out3, (uint8_t*)ctx->pinned + 4096, 96);
+  return 0;
+}
+
+int h2agg_coeff_to_extended_dev(h2agg_ctx* ctx, const void* d_coeffs, uint32_t k, uint32_t ext_k,
+                                const uint64_t zeta[4], const uint64_t omega_ext[4], void* d_out) {
+  if (!ctx) return 1;
+  LOCK(ctx);
+  CHECK_ARG(ctx, d_coeffs && d_out && zeta && omega_ext, "coeff_to_extended: null argument");
+  CHECK_ARG(ctx, ext_k >= k && ext_k >= 1 && ext_k <= 28, "coeff_to_extended: bad k / ext_k");
+  H2AGG_CUDA(ctx, cudaSetDevice(ctx->device));
+  uint64_t in3[12];
+  int rc = coset_consts(ctx, zeta, nullptr, 0, in3);
+  if (rc) return rc;
+  NttOpts o{omega_ext, ext_k, (size_t)1 << k, (size_t)1 << ext_k, in3, nullptr};
+  return ntt_run(ctx, d_coeffs, d_out, o);
+}
+
+int h2agg_coeff_to_extended(h2agg_ctx* ctx, const uint64_t* coeffs, uint32_t k, uint32_t ext_k, const uint64_t zeta[4],
+                            const uint64_t omega_ext[4], uint64_t* out) {
+  if (!ctx) return 1;
+  LOCK(ctx);
+  CHECK_ARG(ctx, coeffs && out && zeta && omega_ext, "coeff_to_extended: null argument");
+  CHECK_ARG(ctx, ext_k >= k && ext_k >= 1 && ext_k <= 28, "coeff_to_extended: bad k / ext_k");
+  H2AGG_CUDA(ctx, cudaSetDevice(ctx->device));
+  uint64_t in3[12];
+  int rc = coset_consts(ctx, zeta, nullptr, 0, in3);
+  if (rc) return rc;
+  NttOpts o{omega_ext, ext_k, 0, 0, in3, nullptr};
+  return ntt_host(ctx, coeffs, (size_t)1 << k, out, (size_t)1 << ext_k, o);
+}
+
+int h2agg_extended_to_coeff_dev(h2agg_ctx* ctx, void* d_a, uint32_t ext_k, const uint64_t omega_ext_inv[4],
+                                const uint64_t ext_n_inv[4], const uint64_t zeta[4], size_t out_len) {
+  if (!ctx) return 1;
+  LOCK(ctx);
+  CHECK_ARG(ctx, d_a && omega_ext_inv && ext_n_inv && zeta, "extended_to_coeff: null argument");
+  CHECK_ARG(ctx, ext_k >= 1 && ext_k <= 28 && out_len <= ((size_t)1 << ext_k), "extended_to_coeff: bad size");
+  H2AGG_CUDA(ctx, cudaSetDevice(ctx->device));
+  uint64_t out3[12];
+  int rc = coset_consts(ctx, zeta, ext_n_inv, 1, out3);
+  if (rc) return rc;
+  NttOpts o{omega_ext_inv, ext_k, (size_t)1 << ext_k, out_len, nullptr, out3};
+  return ntt_run(ctx, d_a, d_a, o);
+}
+
+int h2agg_extended_to_coeff(h2agg_ctx* ctx, uint64_t* a, uint32_t ext_k, const uint64_t omega_ext_inv[4],
+                            const uint64_t ext_n_inv[4], const uint64_t zeta[4], size_t out_len) {
+  if (!ctx) return 1;
+  LOCK(ctx);
+  CHECK_ARG(ctx, a && omega_ext_inv && ext_n_inv && zeta, "extended_to_coeff: null argument");
+  CHECK_ARG(ctx, ext_k >= 1 && ext_k <= 28 && out_len <= ((size_t)1 << ext_k), "extended_to_coeff: bad size");
+  H2AGG_CUDA(ctx, cudaSetDevice(ctx->device));
+  uint64_t out3[12];
+  int rc = coset_consts(ctx, zeta, ext_n_inv, 1, out3);
+  if (rc) return rc;
+  NttOpts o{omega_ext_inv, ext_k, 0, 0, nullptr, out3};
+  return ntt_host(ctx, a, (size_t)1 << ext_k, a, out_len, o);
+}
+
+}  // extern "C"
+
+// ---- field helpers (tests) ----------------------------------------------------------------------
+template <class F>
+__global__ void field_op_kernel(int op, const F* a, const F* b, F* out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  F x = F::load(a + i);
+  F r;
+  if (op == 2) r = fp_inv(x);
+  else {
+    F y = F::load(b + i);
+    r = (op == 0) ? x + y : (op == 1) ? x - y : x * y;
+  }
+  r.store(out + i);
+}
+
+extern "C" {
+
+int h2agg_field_op(h2agg_ctx* ctx, int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
+  if (!ctx) return 1;
+  LOCK(ctx);
+  CHECK_ARG(ctx, a && out && (b || op == 2) && (field == 0 || field == 1) && op >= 0 && op <= 3, "field_op: bad argument");
+  if (n == 0) return 0;
+  H2AGG_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc = ensure(ctx, ctx->io_a, n * 32);
+  if (rc) return rc;
+  rc = ensure(ctx, ctx->io_b, n * 32);
+  if (rc) return rc;
+  H2AGG_CUDA(ctx, cudaMemcpyAsync(ctx->io_a.p, a, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  if (b) H2AGG_CUDA(ctx, cudaMemcpyAsync(ctx->io_b.p, b, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  unsigned grid = (unsigned)((n + 127) / 128);
+  if (field == 0)
+    field_op_kernel<Fr><<<grid, 128, 0, ctx->stream>>>(op, (const Fr*)ctx->io_a.p, (const Fr*)ctx->io_b.p, (Fr*)ctx->io_a.p, n);
+  else
+    field_op_kernel<Fq><<<grid, 128, 0, ctx->stream>>>(op, (const Fq*)ctx->io_a.p, (const Fq*)ctx->io_b.p, (Fq*)ctx->io_a.p, n);
+  ctx->launches++;
+  H2AGG_CUDA(ctx, cudaGetLastError());
+  H2AGG_CUDA(ctx, cudaMemcpyAsync(out, ctx->io_a.p, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  H2AGG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int h2agg_field_mul(h2agg_ctx* ctx, int field, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
+  return h2agg_field_op(ctx, field, 3, a, b, out, n);
+}
+
+}  // extern "C"

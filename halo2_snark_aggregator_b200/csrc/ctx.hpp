@@ -1,0 +1,115 @@
+// Library context: device, stream, scratch arenas, cached twiddle tables, registered SRS.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+namespace h2agg {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+struct TwiddleTable {
+  uint64_t omega[4];
+  uint32_t log_n;
+  uint32_t lo_bits;  // T_lo has 2^lo_bits entries (omega^i), T_hi has 2^(log_n-lo_bits) (omega^(i<<lo_bits))
+  void* lo = nullptr;
+  void* hi = nullptr;
+  uint64_t last_use = 0;
+};
+
+struct Srs {
+  const void* d_bases = nullptr;  // n x 64 B affine, Montgomery
+  size_t n = 0;
+  bool owned = false;
+};
+
+struct Error {
+  int code;
+  std::string msg;
+};
+
+}  // namespace h2agg
+
+struct h2agg_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::recursive_mutex mu;  // the reference calls best_fft from rayon workers: serialise entry
+  std::string last_error;
+  // scratch
+  h2agg::DevBuf ntt_tmp;      // ping-pong buffer for multi-pass NTT
+  h2agg::DevBuf io_a, io_b;   // staging for host-pointer entry points
+  h2agg::DevBuf msm_ws;       // MSM workspace (digits, sort, buckets)
+  h2agg::DevBuf small;        // small constants / results
+  void* pinned = nullptr;     // pinned host bounce buffer for tiny results
+  size_t pinned_cap = 0;
+  std::vector<h2agg::TwiddleTable> tw;
+  uint64_t tick = 0;
+  std::unordered_map<uint64_t, h2agg::Srs> srs;
+  uint64_t next_srs = 1;
+  int sm_count = 148;
+  // counters (claimed in bench.py as gpu_launches)
+  uint64_t launches = 0;
+  // MSM tuning (0 = auto)
+  int msm_window_bits = 0;
+};
+
+namespace h2agg {
+
+#define H2AGG_CUDA(ctx, call)                                                                 \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess) {                                                                  \
+      (ctx)->last_error = std::string(#call) + ": " + cudaGetErrorString(e_) + " @" __FILE__ ":" + \
+                          std::to_string(__LINE__);                                           \
+      return 2;                                                                               \
+    }                                                                                         \
+  } while (0)
+
+inline int ensure(h2agg_ctx* ctx, DevBuf& b, size_t bytes) {
+  if (b.cap >= bytes) return 0;
+  if (b.p) {
+    H2AGG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    H2AGG_CUDA(ctx, cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+  }
+  size_t want = bytes + (bytes >> 3);  // slack so growing sweeps do not realloc every size
+  if (cudaMalloc(&b.p, want) != cudaSuccess) {
+    cudaGetLastError();
+    want = bytes;
+    H2AGG_CUDA(ctx, cudaMalloc(&b.p, want));
+  }
+  b.cap = want;
+  return 0;
+}
+
+// ---- internal device-pointer API (all asynchronous on ctx->stream) -------------------------
+// NTT over Fr. `src` has src_n valid elements (rest of the 2^log_n domain is implicit zero),
+// result lands in `dst` (may equal src), first dst_n elements written.
+struct NttOpts {
+  const uint64_t* omega;            // host, 4 limbs, Montgomery
+  uint32_t log_n;
+  size_t src_n, dst_n;
+  const uint64_t* in_coset3;        // host, 3x4 limbs: multiply input i by in_coset3[i%3]   (or null)
+  const uint64_t* out_scale3;       // host, 3x4 limbs: multiply output i by out_scale3[i%3] (or null)
+};
+int ntt_run(h2agg_ctx* ctx, const void* d_src, void* d_dst, const NttOpts& o);
+
+// MSM over G1: d_scalars n x 32 B (Montgomery Fr), d_bases n x 64 B affine.
+// Writes affine (64 B) + jacobian (96 B, z = 1 or 0) to d_out (160 B, device).
+// Windows [win_begin, win_end) only (pass 0, -1 for all): partial = sum_w 2^(c w) B_w.
+int msm_run(h2agg_ctx* ctx, const void* d_bases, const void* d_scalars, size_t n, void* d_out160,
+            int win_begin, int win_end);
+// sum of m affine-or-jacobian(96 B) points -> d_out160
+int g1_sum_jacobian(h2agg_ctx* ctx, const void* d_points96, size_t m, void* d_out160);
+int msm_window_config(size_t n, int forced_c, int* c, int* nwin);
+
+}  // namespace h2agg

@@ -1,0 +1,348 @@
+// K2/K3: NTT / iNTT / coset transforms over BN254 Fr for sm_100a.
+//
+// Replaces halo2_proofs `best_fft` and `EvaluationDomain::{ifft, coeff_to_extended,
+// extended_to_coeff}` (external crate, restated in SURVEY.md App. B2-B3) as reached from the
+// reference's `create_proof` call at halo2-snark-aggregator-circuit/src/verify_circuit.rs:986
+// and `keygen_pk` at :974.  Natural order in, natural order out, like the CPU function.
+//
+// Decomposition: N = R_1 * R_2 * ... * R_T (T <= 4, each R_t = 2^s_t, s_t <= 8, or one pass of
+// up to 2^11).  Pass t transforms digit n_t -> k_t on shared-memory tiles and multiplies by the
+// inter-pass twiddle w_N^(P_t * j * k_t); layout between passes is [k_1]..[k_t][n_{t+1}]..[n_T]
+// so every pass but the last reads and writes the same positions (in-place safe) in runs of
+// C x 32 B, and the last pass stores transposed (k_1 fastest) in runs of G x 32 B.
+// One HBM round trip per pass; the coset scaling (zeta^(i mod 3)), the zero padding n -> 4n and
+// the 1/n of the inverse transform are fused into the first load / last store (K3).
+// Twiddles are never streamed from HBM: a two-level table (2 x 2^(k/2) entries, L2-resident)
+// gives w^e with at most one extra multiplication, stage twiddles sit in shared memory.
+#include "bn254_field.cuh"
+#include "ctx.hpp"
+#include <cstring>
+
+namespace h2agg {
+
+static constexpr int NTT_THREADS = 256;
+static constexpr uint32_t NTT_TILE_LOG = 11;  // 2048 elements = 64 KiB of shared memory per CTA
+
+struct NttPassArgs {
+  const uint4* src;
+  uint4* dst;
+  const Fr* t_lo;
+  const Fr* t_hi;
+  unsigned long long src_n, dst_n;
+  uint32_t log_n, lo_bits;
+  uint32_t s;       // log2 radix of this pass
+  uint32_t log_l;   // log2 of product of later radices
+  uint32_t log_p;   // log2 of product of earlier radices
+  uint32_t cbits;   // log2 columns per tile
+  uint32_t log_r1;  // log2 radix of pass 1 (last pass only)
+  uint32_t nmid;    // number of middle passes (last pass only)
+  uint32_t mid_log[2];
+  uint32_t npass;
+  uint32_t has_in, has_out;
+  Fr in3[3];
+  Fr out3[3];
+};
+
+__device__ __forceinline__ Fr get_tw(const Fr* __restrict__ t_lo, const Fr* __restrict__ t_hi, uint32_t lo_bits,
+                                     uint32_t e) {
+  uint32_t lo = e & ((1u << lo_bits) - 1), hi = e >> lo_bits;
+  if (hi == 0) return Fr::load_nc(t_lo + lo);
+  if (lo == 0) return Fr::load_nc(t_hi + hi);
+  return Fr::load_nc(t_lo + lo) * Fr::load_nc(t_hi + hi);
+}
+
+__global__ void ntt_gen_tables(Fr omega, uint32_t lo_bits, uint32_t hi_bits, Fr* t_lo, Fr* t_hi) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t nlo = 1u << lo_bits, nhi = 1u << hi_bits;
+  if (i < nlo) {
+    fp_pow_u64(omega, i).store(t_lo + i);
+  } else if (i < nlo + nhi) {
+    uint32_t j = i - nlo;
+    fp_pow_u64(omega, (uint64_t)j << lo_bits).store(t_hi + j);
+  }
+}
+
+template <bool LAST>
+__global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(const __grid_constant__ NttPassArgs p) {
+  extern __shared__ uint4 smem[];
+  const uint32_t s = p.s, R = 1u << s, cbits = p.cbits, C = 1u << cbits, E = R << cbits;
+  const uint32_t rs = LAST ? 1u : C;
+  const uint32_t cs = LAST ? (R + 1) : 1u;
+  const uint32_t plane = LAST ? C * (R + 1) : E;
+  uint4* xl = smem;
+  uint4* xh = smem + plane;
+  uint4* twl = smem + 2 * plane;  // stage twiddles w_R^m, m < R/2 (two 16-byte planes)
+  uint4* twh = twl + (R >> 1);
+  const uint32_t tid = threadIdx.x;
+  const unsigned long long tile = blockIdx.x;
+
+  // ---- stage twiddles: w_R^m = w_N^(m * N/R)
+  for (uint32_t m = tid; m < (R >> 1); m += NTT_THREADS) {
+    Fr w = get_tw(p.t_lo, p.t_hi, p.lo_bits, m << (p.log_n - s));
+    twl[m] = w.lo4();
+    twh[m] = w.hi4();
+  }
+
+  // ---- tile coordinates
+  unsigned long long base;  // position of (row 0, col 0)
+  uint32_t j0 = 0;          // first column index j (non-last) / first k_1 (last)
+  uint32_t log_q = 0, rest = 0;
+  if (!LAST) {
+    uint32_t tiles_per_a = 1u << (p.log_l - cbits);
+    unsigned long long a = tile >> (p.log_l - cbits);
+    j0 = (uint32_t)(tile & (tiles_per_a - 1)) << cbits;
+    base = (a << (s + p.log_l)) + j0;
+  } else {
+    // A = k_1 * Q + rest, Q = P_T / R_1; tile -> (k1 group, rest)
+    log_q = p.log_p - p.log_r1;
+    rest = (uint32_t)(tile & ((1ull << log_q) - 1));
+    j0 = (uint32_t)(tile >> log_q) << cbits;
+    base = 0;
+  }
+
+  // ---- load (bit-reversed rows so that the DIT stages below end in natural order)
+  for (uint32_t idx = tid; idx < E; idx += NTT_THREADS) {
+    uint32_t r, c;
+    unsigned long long pos;
+    if (!LAST) {
+      c = idx & (C - 1);
+      r = idx >> cbits;
+      pos = base + ((unsigned long long)r << p.log_l) + c;
+    } else {
+      r = idx & (R - 1);
+      c = idx >> s;
+      pos = (((((unsigned long long)(j0 + c)) << log_q) + rest) << s) + r;
+    }
+    Fr v;
+    if (pos < p.src_n) {
+      v = Fr::from_halves(p.src[2 * pos], p.src[2 * pos + 1]);
+      if (p.has_in) {
+        uint32_t m3 = (uint32_t)(pos % 3);
+        if (m3) v = v * p.in3[m3];
+      }
+    } else {
+      v = Fr::zero();
+    }
+    uint32_t rr = __brev(r) >> (32 - s);
+    if (s == 0) rr = 0;
+    uint32_t si = rr * rs + c * cs;
+    xl[si] = v.lo4();
+    xh[si] = v.hi4();
+  }
+
+  // ---- radix-2 DIT stages in shared memory
+  for (uint32_t lh = 0; lh < s; lh++) {
+    __syncthreads();
+    const uint32_t h = 1u << lh;
+    for (uint32_t b = tid; b < (E >> 1); b += NTT_THREADS) {
+      uint32_t q, c;
+      if (!LAST) {
+        c = b & (C - 1);
+        q = b >> cbits;
+      } else {
+        q = b & ((R >> 1) - 1);
+        c = b >> (s - 1);
+      }
+      uint32_t j = q & (h - 1);
+      uint32_t i = ((q >> lh) << (lh + 1)) + j;
+      uint32_t i0 = i * rs + c * cs, i1 = (i + h) * rs + c * cs;
+      Fr x0 = Fr::from_halves(xl[i0], xh[i0]);
+      Fr x1 = Fr::from_halves(xl[i1], xh[i1]);
+      if (j) {
+        uint32_t m = j << (s - 1 - lh);
+        x1 = x1 * Fr::from_halves(twl[m], twh[m]);
+      }
+      Fr y0 = x0 + x1, y1 = x0 - x1;
+      xl[i0] = y0.lo4(); xh[i0] = y0.hi4();
+      xl[i1] = y1.lo4(); xh[i1] = y1.hi4();
+    }
+  }
+  __syncthreads();
+
+  // ---- store
+  if (!LAST) {
+    for (uint32_t idx = tid; idx < E; idx += NTT_THREADS) {
+      uint32_t c = idx & (C - 1), k = idx >> cbits;
+      unsigned long long pos = base + ((unsigned long long)k << p.log_l) + c;
+      uint32_t si = k * rs + c * cs;
+      Fr v = Fr::from_halves(xl[si], xh[si]);
+      uint32_t jj = j0 + c;
+      if (k && jj) {
+        // w_N^(P_t * j * k_t); j*k_t < M_t so the exponent is < N
+        uint32_t e = (uint32_t)(((unsigned long long)jj * k) << p.log_p);
+        v = v * get_tw(p.t_lo, p.t_hi, p.lo_bits, e);
+      }
+      p.dst[2 * pos] = v.lo4();
+      p.dst[2 * pos + 1] = v.hi4();
+    }
+  } else {
+    // revmix of the middle digits of `rest`
+    uint32_t mid = 0;
+    {
+      uint32_t consumed = 0, outshift = 0;
+      for (uint32_t i = 0; i < p.nmid; i++) consumed += p.mid_log[i];
+      for (uint32_t i = 0; i < p.nmid; i++) {
+        consumed -= p.mid_log[i];
+        uint32_t d = (rest >> consumed) & ((1u << p.mid_log[i]) - 1);
+        mid |= d << outshift;
+        outshift += p.mid_log[i];
+      }
+    }
+    unsigned long long obase = (p.npass == 1) ? 0ull : ((unsigned long long)j0 + ((unsigned long long)mid << p.log_r1));
+    for (uint32_t idx = tid; idx < E; idx += NTT_THREADS) {
+      uint32_t c = idx & (C - 1), k = idx >> cbits;
+      unsigned long long pos = obase + c + ((unsigned long long)k << p.log_p);
+      if (pos >= p.dst_n) continue;
+      uint32_t si = k * rs + c * cs;
+      Fr v = Fr::from_halves(xl[si], xh[si]);
+      if (p.has_out) v = v * p.out3[(uint32_t)(pos % 3)];
+      p.dst[2 * pos] = v.lo4();
+      p.dst[2 * pos + 1] = v.hi4();
+    }
+  }
+}
+
+static int get_tables(h2agg_ctx* ctx, const uint64_t* omega, uint32_t log_n, TwiddleTable** out) {
+  ctx->tick++;
+  for (auto& t : ctx->tw) {
+    if (t.log_n == log_n && memcmp(t.omega, omega, 32) == 0) {
+      t.last_use = ctx->tick;
+      *out = &t;
+      return 0;
+    }
+  }
+  if (ctx->tw.size() >= 24) {  // evict least recently used
+    size_t v = 0;
+    for (size_t i = 1; i < ctx->tw.size(); i++)
+      if (ctx->tw[i].last_use < ctx->tw[v].last_use) v = i;
+    H2AGG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->tw[v].lo);
+    cudaFree(ctx->tw[v].hi);
+    ctx->tw.erase(ctx->tw.begin() + v);
+  }
+  TwiddleTable t;
+  memcpy(t.omega, omega, 32);
+  t.log_n = log_n;
+  t.lo_bits = (log_n + 1) / 2;
+  uint32_t hi_bits = log_n - t.lo_bits;
+  H2AGG_CUDA(ctx, cudaMalloc(&t.lo, sizeof(Fr) << t.lo_bits));
+  H2AGG_CUDA(ctx, cudaMalloc(&t.hi, sizeof(Fr) << hi_bits));
+  Fr w;
+  memcpy(w.v, omega, 32);
+  uint32_t total = (1u << t.lo_bits) + (1u << hi_bits);
+  ntt_gen_tables<<<(total + 127) / 128, 128, 0, ctx->stream>>>(w, t.lo_bits, hi_bits, (Fr*)t.lo, (Fr*)t.hi);
+  ctx->launches++;
+  H2AGG_CUDA(ctx, cudaGetLastError());
+  t.last_use = ctx->tick;
+  ctx->tw.push_back(t);
+  *out = &ctx->tw.back();
+  return 0;
+}
+
+// split log_n into pass radices
+static int plan_passes(uint32_t log_n, uint32_t* s) {
+  if (log_n <= NTT_TILE_LOG) {
+    s[0] = log_n;
+    return 1;
+  }
+  int T = (log_n + 7) / 8;
+  uint32_t base = log_n / T, extra = log_n % T;
+  for (int t = 0; t < T; t++) s[t] = base + (t < (int)extra ? 1 : 0);
+  return T;
+}
+
+int ntt_run(h2agg_ctx* ctx, const void* d_src, void* d_dst, const NttOpts& o) {
+  if (o.log_n > 28) {
+    ctx->last_error = "ntt: log_n exceeds the 2-adicity of BN254 Fr (28)";
+    return 1;
+  }
+  const size_t N = (size_t)1 << o.log_n;
+  if (o.src_n > N || o.dst_n > N) {
+    ctx->last_error = "ntt: src_n/dst_n exceed the domain";
+    return 1;
+  }
+  if (o.log_n == 0) {
+    if (d_src != d_dst && o.dst_n) H2AGG_CUDA(ctx, cudaMemcpyAsync(d_dst, d_src, 32, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (o.out_scale3 || o.in_coset3) {
+      // a 1-point transform is the identity; scaling a single element is not needed by any caller
+      if (o.out_scale3) {
+        ctx->last_error = "ntt: log_n = 0 with scaling is not supported";
+        return 1;
+      }
+    }
+    return 0;
+  }
+  TwiddleTable* tw;
+  int rc = get_tables(ctx, o.omega, o.log_n, &tw);
+  if (rc) return rc;
+
+  uint32_t s[4];
+  int T = plan_passes(o.log_n, s);
+  const void* cur = d_src;
+  void* tmp = nullptr;
+  if (T > 1) {
+    rc = ensure(ctx, ctx->ntt_tmp, N * 32);
+    if (rc) return rc;
+    tmp = ctx->ntt_tmp.p;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    H2AGG_CUDA(ctx, cudaFuncSetAttribute(ntt_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    H2AGG_CUDA(ctx, cudaFuncSetAttribute(ntt_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr_set = true;
+  }
+
+  uint32_t log_p = 0;
+  for (int t = 0; t < T; t++) {
+    NttPassArgs a;
+    memset(&a, 0, sizeof(a));
+    bool last = (t == T - 1);
+    a.src = (const uint4*)cur;
+    a.dst = (uint4*)(last ? d_dst : tmp);
+    a.t_lo = (const Fr*)tw->lo;
+    a.t_hi = (const Fr*)tw->hi;
+    a.log_n = o.log_n;
+    a.lo_bits = tw->lo_bits;
+    a.s = s[t];
+    a.log_p = log_p;
+    a.log_l = o.log_n - log_p - s[t];
+    a.npass = T;
+    a.src_n = (t == 0) ? o.src_n : N;
+    a.dst_n = last ? o.dst_n : N;
+    if (t == 0 && o.in_coset3) {
+      a.has_in = 1;
+      memcpy(a.in3, o.in_coset3, 96);
+    }
+    if (last && o.out_scale3) {
+      a.has_out = 1;
+      memcpy(a.out3, o.out_scale3, 96);
+    }
+    uint32_t cb = NTT_TILE_LOG - s[t];
+    size_t smem;
+    unsigned long long tiles;
+    if (!last) {
+      if (cb > a.log_l) cb = a.log_l;
+      a.cbits = cb;
+      tiles = (unsigned long long)N >> (s[t] + cb);
+      smem = ((size_t)2 << (s[t] + cb)) * 16 + ((size_t)1 << s[t]) * 16;
+      ntt_pass_kernel<false><<<(unsigned)tiles, NTT_THREADS, smem, ctx->stream>>>(a);
+    } else {
+      a.log_r1 = (T == 1) ? 0 : s[0];
+      if (cb > a.log_r1) cb = a.log_r1;
+      if (T == 1) cb = 0;
+      a.cbits = cb;
+      a.nmid = (T >= 2) ? (uint32_t)(T - 2) : 0;
+      for (uint32_t i = 0; i < a.nmid; i++) a.mid_log[i] = s[1 + i];
+      tiles = (unsigned long long)N >> (s[t] + cb);
+      smem = ((size_t)2 << cb) * (((size_t)1 << s[t]) + 1) * 16 + ((size_t)1 << s[t]) * 16;
+      ntt_pass_kernel<true><<<(unsigned)tiles, NTT_THREADS, smem, ctx->stream>>>(a);
+    }
+    ctx->launches++;
+    H2AGG_CUDA(ctx, cudaGetLastError());
+    log_p += s[t];
+    cur = tmp;
+  }
+  return 0;
+}
+
+}  // namespace h2agg

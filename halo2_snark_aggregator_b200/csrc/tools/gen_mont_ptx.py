@@ -1,0 +1,193 @@
+#!/usr/bin/env python3
+"""Generate the inline-PTX Montgomery multiplication bodies for BN254 Fr / Fq.
+
+The product is computed over 8 x 32-bit limbs with the "even/odd column" schedule:
+products a[j]*b_i with even j accumulate into an `even` limb array, odd j into an
+`odd` array that is offset by one limb, so every (lo,hi) pair of a 32x32 product lands
+on an aligned register pair and ptxas fuses `mad.lo.cc` + `madc.hi.cc` into a single
+IMAD.WIDE.U32(.X).  That is 16 wide MADs per row, 128 per multiplication, plus 8
+`mul.lo` for the Montgomery quotient digits -- the minimum for 256-bit CIOS.
+
+The modulus limbs and -p^-1 mod 2^32 are emitted as immediates (they are compile-time
+constants of the curve), so a multiplication needs only its 16 input registers.
+
+Before writing the .inc files the script *executes* the generated PTX with a tiny
+interpreter (Python big ints, explicit carry flag) on random and edge-case operands and
+checks  r == a*b*R^-1 (mod p), r < 2p  -- so a typo in the schedule can never reach
+the GPU.  Run:  python gen_mont_ptx.py   (writes ../gen/mont_mul_bn254.inc)
+"""
+import os
+import random
+import re
+
+FR = 0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001
+FQ = 0x30644e72e131a029b85045b68181585d97816a916871ca8d3c208c16d87cfd47
+N = 8
+M32 = 0xFFFFFFFF
+
+
+class Gen:
+    def __init__(self, P):
+        self.P = P
+        self.p = [(P >> (32 * i)) & M32 for i in range(N)]
+        self.inv = (-pow(P, -1, 1 << 32)) & M32
+        self.lines = []
+        self.ntemps = 0
+
+    def new(self):
+        self.ntemps += 1
+        return "t%d" % (self.ntemps - 1)
+
+    def emit(self, s):
+        self.lines.append(s)
+
+    @staticmethod
+    def imm(v):
+        return "0x%08x" % v
+
+    # acc[0..7] (+)= x[0,2,4,6] * y with one carry chain through the four aligned pairs
+    def cmad(self, acc, xs, y):
+        for k in range(4):
+            lo = "mad.lo.cc.u32" if k == 0 else "madc.lo.cc.u32"
+            self.emit("%s %s, %s, %s, %s;" % (lo, acc[2 * k], y, xs[k], acc[2 * k]))
+            self.emit("madc.hi.cc.u32 %s, %s, %s, %s;" % (acc[2 * k + 1], y, xs[k], acc[2 * k + 1]))
+
+    def redc(self, even, odd):
+        mi = self.new()
+        self.emit("mul.lo.u32 %s, %s, %s;" % (mi, even[0], self.imm(self.inv)))
+        self.cmad(odd, [self.imm(self.p[j]) for j in (1, 3, 5, 7)], mi)
+        self.cmad(even, [self.imm(self.p[j]) for j in (0, 2, 4, 6)], mi)
+        self.emit("addc.u32 %s, %s, 0;" % (odd[7], odd[7]))
+
+    def row(self, even, odd, A, bi, first):
+        """One CIOS row; returns the (even, odd) register-name lists after the row."""
+        if first:
+            for k in range(4):
+                odd[2 * k], odd[2 * k + 1] = self.new(), self.new()
+                self.emit("mul.lo.u32 %s, %s, %s;" % (odd[2 * k], A[2 * k + 1], bi))
+                self.emit("mul.hi.u32 %s, %s, %s;" % (odd[2 * k + 1], A[2 * k + 1], bi))
+            for k in range(4):
+                even[2 * k], even[2 * k + 1] = self.new(), self.new()
+                self.emit("mul.lo.u32 %s, %s, %s;" % (even[2 * k], A[2 * k], bi))
+                self.emit("mul.hi.u32 %s, %s, %s;" % (even[2 * k + 1], A[2 * k], bi))
+        else:
+            # the limb that fell to position 0 after the previous row's /2^32
+            self.emit("add.cc.u32 %s, %s, %s;" % (even[0], even[0], odd[1]))
+            nodd = [None] * 8
+            for k in range(3):  # shift the odd array down two limbs while accumulating
+                nodd[2 * k], nodd[2 * k + 1] = self.new(), self.new()
+                self.emit("madc.lo.cc.u32 %s, %s, %s, %s;" % (nodd[2 * k], A[2 * k + 1], bi, odd[2 * k + 2]))
+                self.emit("madc.hi.cc.u32 %s, %s, %s, %s;" % (nodd[2 * k + 1], A[2 * k + 1], bi, odd[2 * k + 3]))
+            nodd[6], nodd[7] = self.new(), self.new()
+            self.emit("madc.lo.cc.u32 %s, %s, %s, 0;" % (nodd[6], A[7], bi))
+            self.emit("madc.hi.u32 %s, %s, %s, 0;" % (nodd[7], A[7], bi))
+            odd[:] = nodd
+            self.cmad(even, [A[j] for j in (0, 2, 4, 6)], bi)
+            self.emit("addc.u32 %s, %s, 0;" % (odd[7], odd[7]))
+        self.redc(even, odd)
+
+    def mont_mul(self):
+        A = ["%%%d" % (8 + i) for i in range(8)]
+        B = ["%%%d" % (16 + i) for i in range(8)]
+        even, odd = [None] * 8, [None] * 8
+        for i in range(0, 8, 2):
+            self.row(even, odd, A, B[i], i == 0)
+            self.row(odd, even, A, B[i + 1], False)
+        # merge: result[j] = even[j] + odd[j+1]
+        self.emit("add.cc.u32 %s, %s, %s;" % (even[0], even[0], odd[1]))
+        for j in range(1, 7):
+            self.emit("addc.cc.u32 %s, %s, %s;" % (even[j], even[j], odd[j + 1]))
+        self.emit("addc.u32 %s, %s, 0;" % (even[7], even[7]))
+        for j in range(8):
+            self.emit("mov.u32 %%%d, %s;" % (j, even[j]))
+        return self.lines
+
+
+def run_ptx(lines, a, b):
+    """Minimal interpreter for exactly the instruction forms emitted above."""
+    regs = {}
+    for i in range(8):
+        regs["%%%d" % (8 + i)] = (a >> (32 * i)) & M32
+        regs["%%%d" % (16 + i)] = (b >> (32 * i)) & M32
+    cc = 0
+
+    def val(x):
+        x = x.strip()
+        if x.startswith("0x"):
+            return int(x, 16)
+        if x.isdigit():
+            return int(x)
+        return regs[x]
+
+    for ln in lines:
+        m = re.match(r"([a-z0-9.]+)\s+(.*);", ln)
+        op, args = m.group(1), [s.strip() for s in m.group(2).split(",")]
+        d = args[0]
+        if op == "mov.u32":
+            regs[d] = val(args[1])
+        elif op == "mul.lo.u32":
+            regs[d] = (val(args[1]) * val(args[2])) & M32
+        elif op == "mul.hi.u32":
+            regs[d] = ((val(args[1]) * val(args[2])) >> 32) & M32
+        elif op.startswith("mad"):
+            base, part = op.split(".")[0], op.split(".")[1]
+            prod = val(args[1]) * val(args[2])
+            prod = (prod & M32) if part == "lo" else (prod >> 32)
+            s = prod + val(args[3]) + (cc if base == "madc" else 0)
+            regs[d] = s & M32
+            if ".cc." in op:
+                cc = s >> 32
+        elif op.startswith("add"):
+            base = op.split(".")[0]
+            s = val(args[1]) + val(args[2]) + (cc if base == "addc" else 0)
+            regs[d] = s & M32
+            if ".cc." in op:
+                cc = s >> 32
+        else:
+            raise ValueError(op)
+        assert cc in (0, 1)
+    return sum(regs["%%%d" % i] << (32 * i) for i in range(8))
+
+
+def selfcheck(P, lines, rounds=400):
+    rinv = pow(1 << 256, -1, P)
+    rng = random.Random(0xB200 ^ (P & 0xFFFF))
+    cases = [(0, 0), (1, 1), (P - 1, P - 1), (P - 1, 1), (0, P - 1), ((1 << 256) % P, (1 << 256) % P)]
+    cases += [(rng.randrange(P), rng.randrange(P)) for _ in range(rounds)]
+    for a, b in cases:
+        r = run_ptx(lines, a, b)
+        assert r < 2 * P, "row bound violated"
+        assert r % P == (a * b * rinv) % P, (hex(a), hex(b), hex(r))
+
+
+def c_body(name, lines, ntemps):
+    out = []
+    out.append("// GENERATED by tools/gen_mont_ptx.py -- do not edit. %s: r = a*b*2^-256 mod p, r in [0,2p)" % name)
+    out.append("#define H2AGG_MONT_MUL_%s(r, a, b) \\" % name)
+    out.append('  asm("{\\n\\t.reg .u32 t<%d>;\\n\\t" \\' % ntemps)
+    for ln in lines:
+        out.append('      "%s\\n\\t" \\' % ln)
+    out.append('      "}" \\')
+    out.append('      : "=r"((r)[0]), "=r"((r)[1]), "=r"((r)[2]), "=r"((r)[3]), "=r"((r)[4]), "=r"((r)[5]), "=r"((r)[6]), "=r"((r)[7]) \\')
+    out.append('      : "r"((a)[0]), "r"((a)[1]), "r"((a)[2]), "r"((a)[3]), "r"((a)[4]), "r"((a)[5]), "r"((a)[6]), "r"((a)[7]), \\')
+    out.append('        "r"((b)[0]), "r"((b)[1]), "r"((b)[2]), "r"((b)[3]), "r"((b)[4]), "r"((b)[5]), "r"((b)[6]), "r"((b)[7]))')
+    return "\n".join(out) + "\n"
+
+
+def main():
+    here = os.path.dirname(os.path.abspath(__file__))
+    dst = os.path.join(here, "..", "gen", "mont_mul_bn254.inc")
+    text = "#pragma once\n"
+    for name, P in (("FR", FR), ("FQ", FQ)):
+        g = Gen(P)
+        lines = g.mont_mul()
+        selfcheck(P, lines)
+        text += c_body(name, lines, g.ntemps) + "\n"
+        print("%s: %d PTX instructions, %d temps, self-check ok" % (name, len(lines), g.ntemps))
+    with open(dst, "w") as f:
+        f.write(text)
+    print("wrote", os.path.normpath(dst))
+
+
+if __name__ == "__main__":
+    main()

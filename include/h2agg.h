@@ -1,0 +1,134 @@
+/* h2agg.h -- C ABI of the B200-native prover backend for the halo2 aggregation circuit.
+ *
+ * This is the drop-in boundary.  The reference
+ * (scroll-tech/halo2-snark-aggregator) has no FFI today; its hot path enters the external
+ * crate halo2_proofs at
+ *     halo2-snark-aggregator-circuit/src/verify_circuit.rs:986-994   create_proof(...)
+ *     halo2-snark-aggregator-circuit/src/verify_circuit.rs:974-979   keygen_pk(...)
+ *     halo2-snark-aggregator-circuit/src/verify_circuit.rs:760-761   keygen_vk(...)
+ *     halo2-snark-aggregator-circuit/src/sample_circuit.rs:75-83     create_proof(...) (inner proofs)
+ * and from there reaches the free functions this library replaces (halo2_proofs is swapped
+ * with a Cargo [patch], precedent: /root/reference/Cargo.toml:10-11; the Rust binding is in
+ * INTEGRATION.md and rust/h2agg-sys/).
+ *
+ * Data layout everywhere = the Rust in-memory layout of halo2curves 0.2.1:
+ *   Fr, Fq      4 x u64 little-endian limbs, Montgomery form (R = 2^256), fully reduced
+ *   G1Affine    {x: Fq, y: Fq}            64 bytes, identity = (0, 0)
+ *   G1          {x: Fq, y: Fq, z: Fq}     96 bytes Jacobian, identity z = 0
+ * so a Rust slice can be passed as a pointer without conversion.
+ *
+ * Every function returns 0 on success; 1 = invalid argument, 2 = CUDA failure, 3 = no device.
+ * h2agg_last_error() gives the message.  There is no CPU fallback inside this library: with no
+ * usable GPU h2agg_init fails and nothing else can be called.
+ *
+ * Threading: a context serialises its entry points internally (best_fft is entered from rayon
+ * workers in the reference, halo2-snark-aggregator-sdk/src/lib.rs:52-55).  Host-pointer entry
+ * points return when the result is in host memory; *_dev entry points enqueue on the context's
+ * stream and return immediately.
+ */
+#ifndef H2AGG_H
+#define H2AGG_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct h2agg_ctx h2agg_ctx;
+
+/* ---- life cycle ------------------------------------------------------------------------- */
+/* One context per process per GPU (one process per GPU is the multi-GPU model). */
+int h2agg_init(int device_id, h2agg_ctx** out);
+void h2agg_destroy(h2agg_ctx* ctx);
+const char* h2agg_last_error(h2agg_ctx* ctx); /* ctx may be NULL: error of the last failed init */
+const char* h2agg_version(void);
+/* Run on a caller-owned CUDA stream (cudaStream_t) instead of the context's own. */
+int h2agg_set_stream(h2agg_ctx* ctx, void* cuda_stream);
+int h2agg_synchronize(h2agg_ctx* ctx);
+/* Number of kernels this context has launched so far (evidence counter for bench.py). */
+uint64_t h2agg_launch_count(h2agg_ctx* ctx);
+/* Pin / unpin a host range so H2D copies run at PCIe speed (the SRS, witness columns). */
+int h2agg_host_register(h2agg_ctx* ctx, const void* p, size_t bytes);
+int h2agg_host_unregister(h2agg_ctx* ctx, const void* p);
+/* MSM window width c in bits (0 = automatic). Exposed for sweeps and tests. */
+int h2agg_set_msm_window(h2agg_ctx* ctx, int c_bits);
+/* The (c, number of windows) the MSM uses for n pairs. */
+int h2agg_msm_config(h2agg_ctx* ctx, size_t n, int* c_bits, int* n_windows);
+
+/* ---- SRS residency -------------------------------------------------------------------------
+ * ParamsKZG { g, g_lagrange } are immutable for the life of the params
+ * (verify_circuit.rs:701-731 get_params_cached); register them once, keep them in HBM. */
+int h2agg_srs_register(h2agg_ctx* ctx, const uint64_t* bases_affine /* n*8 */, size_t n, uint64_t* out_srs_id);
+int h2agg_srs_register_dev(h2agg_ctx* ctx, const void* d_bases_affine, size_t n, uint64_t* out_srs_id); /* borrowed */
+int h2agg_srs_release(h2agg_ctx* ctx, uint64_t srs_id);
+
+/* ---- K1: multi-scalar multiplication  (replaces halo2_proofs::arithmetic::best_multiexp,
+ *      reached via ParamsKZG::commit_lagrange / commit from create_proof, verify_circuit.rs:986)
+ * result = sum_i scalars[i] * bases[i].  Bases come from srs_id (first n points) or, when
+ * srs_id == 0, from bases_affine.  out_jacobian receives the NORMALISED point (x, y, 1), or
+ * (0, 1, 0) for the identity, so that its first 64 bytes are the affine coordinates the
+ * transcript writes (halo2-snark-aggregator-api/src/transcript/sha.rs:156-173). */
+int h2agg_msm_g1(h2agg_ctx* ctx, uint64_t srs_id, const uint64_t* bases_affine /* n*8 or NULL */,
+                 const uint64_t* scalars /* n*4 */, size_t n, uint64_t out_jacobian[12]);
+/* One commit round: n_cols columns of n scalars against the same bases -> n_cols affine points. */
+int h2agg_msm_g1_batch(h2agg_ctx* ctx, uint64_t srs_id, const uint64_t* const* scalar_cols, size_t n_cols, size_t n,
+                       uint64_t* out_affine /* n_cols*8 */);
+/* Device-resident variant: d_scalars (n*32 B) and bases already in HBM; d_out160 receives
+ * affine (64 B) followed by the normalised Jacobian (96 B).  Asynchronous. */
+int h2agg_msm_g1_dev(h2agg_ctx* ctx, uint64_t srs_id, const void* d_bases_affine, const void* d_scalars, size_t n,
+                     void* d_out160);
+/* Window-sharded MSM: only windows [win_begin, win_end) of the signed-digit
+ * decomposition; the partial results of all shards add up to the full MSM. Host pointers. */
+int h2agg_msm_g1_windows(h2agg_ctx* ctx, uint64_t srs_id, const uint64_t* bases_affine, const uint64_t* scalars,
+                         size_t n, int win_begin, int win_end, uint64_t out_jacobian[12]);
+int h2agg_msm_g1_windows_dev(h2agg_ctx* ctx, uint64_t srs_id, const void* d_bases_affine, const void* d_scalars,
+                             size_t n, int win_begin, int win_end, void* d_out160);
+/* Sum of m Jacobian points (96 B each; the all-gathered shard partials) -> normalised Jacobian. */
+int h2agg_g1_sum(h2agg_ctx* ctx, const uint64_t* points_jacobian /* m*12 */, size_t m, uint64_t out_jacobian[12]);
+
+/* ---- K2: NTT  (replaces halo2_proofs::arithmetic::best_fft(a, omega, log_n)) -----------------
+ * In place, natural order in and out. log_n <= 28. */
+int h2agg_ntt_fr(h2agg_ctx* ctx, uint64_t* a /* 2^log_n * 4 */, const uint64_t omega[4], uint32_t log_n);
+/* EvaluationDomain::ifft / lagrange_to_coeff: best_fft(a, omega_inv) then * n_inv (= ifft_divisor). */
+int h2agg_intt_fr(h2agg_ctx* ctx, uint64_t* a, const uint64_t omega_inv[4], const uint64_t n_inv[4], uint32_t log_n);
+/* Device-resident, asynchronous; scale may be NULL. d_a in place. */
+int h2agg_ntt_fr_dev(h2agg_ctx* ctx, void* d_a, const uint64_t omega[4], const uint64_t* scale /* 4 or NULL */,
+                     uint32_t log_n);
+
+/* ---- K3: coset transforms of EvaluationDomain ----------------------------------------------------
+ * coeff_to_extended: out[i] = NTT_{2^ext_k}( zeta^(i mod 3) * coeffs[i], zero padded )   (n = 2^k inputs)
+ * extended_to_coeff: a = iNTT_{2^ext_k}(a) * ext_n_inv, then a[i] *= zeta^-(i mod 3); the first
+ *                    out_len elements are the result (halo2 truncates to n*(j-1)). */
+int h2agg_coeff_to_extended(h2agg_ctx* ctx, const uint64_t* coeffs /* 2^k * 4 */, uint32_t k, uint32_t ext_k,
+                            const uint64_t zeta[4], const uint64_t omega_ext[4], uint64_t* out /* 2^ext_k * 4 */);
+int h2agg_extended_to_coeff(h2agg_ctx* ctx, uint64_t* a /* 2^ext_k * 4, in place */, uint32_t ext_k,
+                            const uint64_t omega_ext_inv[4], const uint64_t ext_n_inv[4], const uint64_t zeta[4],
+                            size_t out_len);
+int h2agg_coeff_to_extended_dev(h2agg_ctx* ctx, const void* d_coeffs, uint32_t k, uint32_t ext_k,
+                                const uint64_t zeta[4], const uint64_t omega_ext[4], void* d_out);
+int h2agg_extended_to_coeff_dev(h2agg_ctx* ctx, void* d_a, uint32_t ext_k, const uint64_t omega_ext_inv[4],
+                                const uint64_t ext_n_inv[4], const uint64_t zeta[4], size_t out_len);
+
+/* ---- small helpers used by tests and the host layer (run on the device) ---------------------- */
+/* out[i] = a[i] * b[i] in Fr (field = 0) or Fq (field = 1); host pointers; Montgomery form. */
+int h2agg_field_mul(h2agg_ctx* ctx, int field, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n);
+/* out[i] = a[i] + b[i] (op 0), a[i] - b[i] (op 1), a[i]^-1 (op 2, b ignored) */
+int h2agg_field_op(h2agg_ctx* ctx, int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n);
+
+/* ---- device memory + synthetic inputs (bench / test plumbing; not part of the reference surface) ---
+ * Deterministic, counter-based inputs of SURVEY.md 8d generated straight into HBM; bit-identical to
+ * oracle_gen_scalars / oracle_gen_bases.  kind: 0 uniform Fr, 1 witness-like a0..a3
+ * (70% 17-bit, 10% {0,1}, 20% zero), 2 witness-like a4 (50% 68-bit, 20% full, 30% zero), 3 uniform 17-bit. */
+int h2agg_dev_alloc(h2agg_ctx* ctx, size_t bytes, void** out);
+int h2agg_dev_free(h2agg_ctx* ctx, void* p);
+int h2agg_memcpy_h2d(h2agg_ctx* ctx, void* d_dst, const void* src, size_t bytes);
+int h2agg_memcpy_d2h(h2agg_ctx* ctx, void* dst, const void* d_src, size_t bytes);
+int h2agg_synth_scalars_dev(h2agg_ctx* ctx, uint64_t seed, int kind, uint64_t first, uint64_t n, void* d_out);
+int h2agg_synth_bases_dev(h2agg_ctx* ctx, uint64_t seed, uint64_t first, uint64_t n, void* d_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* H2AGG_H */

@@ -1,0 +1,141 @@
+"""ctypes binding of the CPU oracle (oracle/cpu_halo2.cpp).  TEST INFRASTRUCTURE: imported only by
+tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs."""
+import ctypes
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+ORACLE_SO = os.path.join(ORACLE_DIR, "liboracle_h2.so")
+sys.path.insert(0, os.path.join(ORACLE_DIR, "py"))
+
+c_vp = ctypes.c_void_p
+
+
+def build_oracle(force=False):
+    src = os.path.join(ORACLE_DIR, "cpu_halo2.cpp")
+    if force or not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "-B", "liboracle_h2.so"], stdout=subprocess.DEVNULL)
+    return ORACLE_SO
+
+
+_o = None
+
+
+def oracle():
+    global _o
+    if _o is None:
+        lib = ctypes.CDLL(build_oracle())
+        try:  # a .so built on another CPU generation may not run here: rebuild once
+            lib.oracle_hw_threads()
+        except Exception:
+            lib = ctypes.CDLL(build_oracle(force=True))
+        u64, sz, u32, ui, ci = ctypes.c_uint64, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_uint, ctypes.c_int
+        lib.oracle_gen_scalars.argtypes = [u64, ci, sz, sz, c_vp, ui]
+        lib.oracle_gen_bases.argtypes = [u64, sz, sz, c_vp, ui]
+        lib.oracle_field_op.argtypes = [ci, ci, c_vp, c_vp, c_vp, sz]
+        lib.oracle_to_mont.argtypes = [ci, c_vp, c_vp, sz]
+        lib.oracle_from_mont.argtypes = [ci, c_vp, c_vp, sz]
+        lib.oracle_best_multiexp.argtypes = [c_vp, c_vp, sz, ui, c_vp]
+        lib.oracle_msm_naive.argtypes = [c_vp, c_vp, sz, c_vp]
+        lib.oracle_g1_sum.argtypes = [c_vp, sz, c_vp]
+        lib.oracle_g1_on_curve.argtypes = [c_vp]
+        lib.oracle_g1_on_curve.restype = ci
+        lib.oracle_best_fft.argtypes = [c_vp, c_vp, u32, ui]
+        lib.oracle_dft_naive.argtypes = [c_vp, c_vp, u32, c_vp]
+        lib.oracle_ifft.argtypes = [c_vp, c_vp, c_vp, u32, ui]
+        lib.oracle_coeff_to_extended.argtypes = [c_vp, u32, u32, c_vp, c_vp, c_vp, ui]
+        lib.oracle_extended_to_coeff.argtypes = [c_vp, u32, c_vp, c_vp, c_vp, ui]
+        lib.oracle_hw_threads.restype = ui
+        _o = lib
+    return _o
+
+
+def P(a):
+    return c_vp(a.ctypes.data) if a is not None else None
+
+
+def threads():
+    return int(oracle().oracle_hw_threads())
+
+
+def gen_scalars(seed, kind, n, first=0):
+    out = np.empty(4 * n, dtype=np.uint64)
+    oracle().oracle_gen_scalars(seed, kind, first, n, P(out), threads())
+    return out
+
+
+def gen_bases(seed, n, first=0):
+    out = np.empty(8 * n, dtype=np.uint64)
+    oracle().oracle_gen_bases(seed, first, n, P(out), threads())
+    return out
+
+
+def field_op(field, op, a, b=None):
+    out = np.empty_like(a)
+    oracle().oracle_field_op(field, op, P(a), P(b), P(out), a.size // 4)
+    return out
+
+
+def to_mont(field, canon):
+    out = np.empty_like(canon)
+    oracle().oracle_to_mont(field, P(canon), P(out), canon.size // 4)
+    return out
+
+
+def from_mont(field, mont):
+    out = np.empty_like(mont)
+    oracle().oracle_from_mont(field, P(mont), P(out), mont.size // 4)
+    return out
+
+
+def best_multiexp(scalars, bases, nthreads=None):
+    out = np.zeros(12, dtype=np.uint64)
+    oracle().oracle_best_multiexp(P(scalars), P(bases), scalars.size // 4, nthreads or threads(), P(out))
+    return out
+
+
+def msm_naive(scalars, bases):
+    out = np.zeros(12, dtype=np.uint64)
+    oracle().oracle_msm_naive(P(scalars), P(bases), scalars.size // 4, P(out))
+    return out
+
+
+def g1_sum(points12):
+    out = np.zeros(12, dtype=np.uint64)
+    oracle().oracle_g1_sum(P(points12), points12.size // 12, P(out))
+    return out
+
+
+def on_curve(aff8):
+    return bool(oracle().oracle_g1_on_curve(P(np.ascontiguousarray(aff8))))
+
+
+def best_fft(a, omega, log_n, nthreads=None):
+    oracle().oracle_best_fft(P(a), P(omega), log_n, nthreads or threads())
+    return a
+
+
+def dft_naive(a, omega, log_n):
+    out = np.empty_like(a)
+    oracle().oracle_dft_naive(P(a), P(omega), log_n, P(out))
+    return out
+
+
+def ifft(a, omega_inv, divisor, log_n, nthreads=None):
+    oracle().oracle_ifft(P(a), P(omega_inv), P(divisor), log_n, nthreads or threads())
+    return a
+
+
+def coeff_to_extended(coeffs, k, ext_k, zeta, omega_ext, nthreads=None):
+    out = np.empty(4 << ext_k, dtype=np.uint64)
+    oracle().oracle_coeff_to_extended(P(coeffs), k, ext_k, P(zeta), P(omega_ext), P(out), nthreads or threads())
+    return out
+
+
+def extended_to_coeff(a, ext_k, omega_ext_inv, ext_n_inv, zeta, out_len, nthreads=None):
+    oracle().oracle_extended_to_coeff(P(a), ext_k, P(omega_ext_inv), P(ext_n_inv), P(zeta), nthreads or threads())
+    return a[: 4 * out_len]

@@ -1,0 +1,229 @@
+"""GPU parity suite (-m gpu): every call goes through the C ABI (ctypes -> libh2agg.so -> sm_100a
+kernels) and is compared bit-for-bit with the CPU oracle / the committed golden vectors."""
+import numpy as np
+import pytest
+
+import oracle_binding as ob
+from util import affine_of, arr, domain_consts, fr_limbs, golden, omega
+
+pytestmark = pytest.mark.gpu
+
+
+# ---------------------------------------------------------------- field arithmetic (PTX schedule)
+def test_field_golden(ctx):
+    for case in golden("field.json"):
+        f = case["field"]
+        a, b = arr(case["a"]), arr(case["b"])
+        assert np.array_equal(ctx.field_op(f, 0, a, b), arr(case["add"]))
+        assert np.array_equal(ctx.field_op(f, 1, a, b), arr(case["sub"]))
+        assert np.array_equal(ctx.field_op(f, 3, a, b), arr(case["mul"]))
+        assert np.array_equal(ctx.field_op(f, 2, a), arr(case["inv"]))
+
+
+@pytest.mark.parametrize("field", [0, 1])
+def test_field_random_vs_oracle(ctx, field):
+    n = 20000
+    a = ob.gen_scalars(11 + field, 0, n)  # canonical-range values are valid Montgomery residues of either field
+    b = ob.gen_scalars(13 + field, 0, n)
+    for op in (0, 1, 3):
+        assert np.array_equal(ctx.field_op(field, op, a, b), ob.field_op(field, op, a, b)), op
+    assert np.array_equal(ctx.field_op(field, 2, a[:4000]), ob.field_op(field, 2, a[:4000]))
+
+
+# ---------------------------------------------------------------- synthetic generators
+def test_synth_matches_oracle(ctx):
+    n = 3000
+    d = ctx.dev_alloc(n * 64)
+    try:
+        for kind in range(4):
+            ctx.synth_scalars_dev(0xABC + kind, kind, 5, n, d)
+            assert np.array_equal(ctx.d2h(d, 4 * n), ob.gen_scalars(0xABC + kind, kind, n, first=5))
+        ctx.synth_bases_dev(0x53525300, 9, n, d)
+        assert np.array_equal(ctx.d2h(d, 8 * n), ob.gen_bases(0x53525300, n, first=9))
+    finally:
+        ctx.dev_free(d)
+
+
+# ---------------------------------------------------------------- K2 / K3
+@pytest.mark.parametrize("case", golden("ntt.json"), ids=lambda c: c["name"])
+def test_ntt_golden(ctx, case):
+    a, want = arr(case["input"]), arr(case["output"])
+    name = case["name"]
+    if name.startswith("fft"):
+        got = a.copy()
+        ctx.ntt_fr(got, arr(case["omega"]), case["k"])
+    elif name.startswith("ifft"):
+        got = a.copy()
+        ctx.intt_fr(got, arr(case["omega_inv"]), arr(case["n_inv"]), case["k"])
+    elif name.startswith("coeff_to_extended"):
+        got = ctx.coeff_to_extended(a, case["k"], case["ext_k"], arr(case["zeta"]), arr(case["omega_ext"]))
+    else:
+        got = ctx.extended_to_coeff(a.copy(), case["ext_k"], arr(case["omega_ext_inv"]), arr(case["ext_n_inv"]), arr(case["zeta"]), case["out_len"])
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("k", list(range(1, 21)))
+def test_ntt_vs_oracle(ctx, k):
+    a = ob.gen_scalars(0xF00 + k, 0, 1 << k)
+    w = fr_limbs(omega(k))
+    want = ob.best_fft(a.copy(), w, k)
+    got = a.copy()
+    ctx.ntt_fr(got, w, k)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("k", [1, 5, 11, 12, 16, 17, 18, 20])
+def test_domain_transforms_vs_oracle(ctx, k):
+    d = domain_consts(k)
+    a = ob.gen_scalars(0xD0 + k, 0, 1 << k)
+    got = a.copy()
+    ctx.intt_fr(got, d["omega_inv"], d["n_inv"], k)
+    assert np.array_equal(got, ob.ifft(a.copy(), d["omega_inv"], d["n_inv"], k))
+    ext = ctx.coeff_to_extended(a, k, k + 2, d["zeta"], d["omega_ext"])
+    assert np.array_equal(ext, ob.coeff_to_extended(a, k, k + 2, d["zeta"], d["omega_ext"]))
+    back = ctx.extended_to_coeff(ext.copy(), k + 2, d["omega_ext_inv"], d["ext_n_inv"], d["zeta"], 3 << k)
+    assert np.array_equal(back, ob.extended_to_coeff(ext.copy(), k + 2, d["omega_ext_inv"], d["ext_n_inv"], d["zeta"], 3 << k))
+    assert np.array_equal(back[: 4 << k], a) and not back[4 << k:].any()
+
+
+@pytest.mark.parametrize("k", [22, 24])
+def test_ntt_full_size_properties(ctx, k):
+    """BASELINE sizes (n = 2^22 and the 4n extended domain): round trip + linearity + a spot DFT row."""
+    n = 1 << k
+    w = omega(k)
+    from util import R_MOD
+    w_l, wi_l, ni_l = fr_limbs(w), fr_limbs(pow(w, -1, R_MOD)), fr_limbs(pow(n, -1, R_MOD))
+    a = ob.gen_scalars(0xBEEF + k, 0, n)
+    b = ob.gen_scalars(0xCAFE + k, 0, n)
+    fa, fb, fab = a.copy(), b.copy(), ob.field_op(0, 0, a, b)
+    ctx.ntt_fr(fa, w_l, k)
+    ctx.ntt_fr(fb, w_l, k)
+    ctx.ntt_fr(fab, w_l, k)
+    assert np.array_equal(fab, ob.field_op(0, 0, fa, fb))  # linearity
+    # X[0] = sum of inputs, checked through the oracle's adds
+    acc = a.reshape(-1, 4)
+    while acc.shape[0] > 1:
+        h = acc.shape[0] // 2
+        acc = ob.field_op(0, 0, np.ascontiguousarray(acc[:h]).ravel(), np.ascontiguousarray(acc[h:]).ravel()).reshape(-1, 4)
+    assert np.array_equal(fa[:4], acc.ravel())
+    ctx.intt_fr(fa, wi_l, ni_l, k)
+    assert np.array_equal(fa, a)  # round trip
+
+
+# ---------------------------------------------------------------- K1 / K4
+@pytest.mark.parametrize("case", golden("msm.json"), ids=lambda c: c["name"])
+def test_msm_golden(ctx, case):
+    s, b = arr(case["scalars"]), arr(case["bases"])
+    got = ctx.msm_g1(s, b)
+    assert np.array_equal(affine_of(got), arr(case["affine"]))
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 17, 64, 255, 1024, 4097, 1 << 14, 1 << 16])
+@pytest.mark.parametrize("kind", [0, 1, 2])
+def test_msm_vs_oracle(ctx, n, kind):
+    s = ob.gen_scalars(0xA660000 + n, kind, n)
+    b = ob.gen_bases(0x53525300, n)
+    assert np.array_equal(ctx.msm_g1(s, b), ob.best_multiexp(s, b))
+
+
+@pytest.mark.parametrize("c", [2, 3, 5, 8, 11, 13, 16])
+def test_msm_every_window_width(ctx, c):
+    n = 5000
+    s = ob.gen_scalars(77, 0, n)
+    s[:4] = np.array([0xFFFFFFFFFFFFFFFF, 0xFFFFFFFFFFFFFFFF, 0xFFFFFFFFFFFFFFFF, 0x0FFFFFFFFFFFFFFF], dtype=np.uint64)  # arbitrary residue
+    s[:4] = ob.field_op(0, 0, s[:4], s[4:8])  # normalise into range
+    b = ob.gen_bases(78, n)
+    want = ob.best_multiexp(s, b)
+    ctx.set_msm_window(c)
+    try:
+        assert np.array_equal(ctx.msm_g1(s, b), want)
+    finally:
+        ctx.set_msm_window(0)
+
+
+def test_msm_edge_cases(ctx):
+    n = 2048
+    b = ob.gen_bases(5, n)
+    zero = np.zeros(4 * n, dtype=np.uint64)
+    ident = np.array([0, 0, 0, 0] + list(ob.to_mont(1, np.array([1, 0, 0, 0], dtype=np.uint64))) + [0, 0, 0, 0], dtype=np.uint64)
+    assert np.array_equal(ctx.msm_g1(zero, b), ident)  # all-zero scalars -> identity (0, 1, 0)
+    assert np.array_equal(ctx.msm_g1(zero[:0], b[:0]), ident)  # empty input
+    minus1 = ob.field_op(0, 1, zero, np.tile(fr_limbs(1), n))  # all r-1
+    assert np.array_equal(ctx.msm_g1(minus1, b), ob.best_multiexp(minus1, b))
+    same = np.tile(b[:8], n)  # every base the same point: constant doubling inside buckets
+    s = ob.gen_scalars(6, 0, n)
+    assert np.array_equal(ctx.msm_g1(s, same), ob.best_multiexp(s, same))
+    ones = np.tile(fr_limbs(1), n)  # one hot bucket (digit 1 of window 0) holding every point
+    assert np.array_equal(ctx.msm_g1(ones, b), ob.best_multiexp(ones, b))
+    assert np.array_equal(ctx.msm_g1(ones, same), ob.best_multiexp(ones, same))
+    holes = b.copy()
+    holes.reshape(-1, 8)[::3] = 0  # identity bases
+    assert np.array_equal(ctx.msm_g1(s, holes), ob.best_multiexp(s, holes))
+    # P and -P pairs cancel exactly
+    pm = b.copy().reshape(-1, 8)
+    negy = ob.field_op(1, 1, np.zeros(4 * (n // 2), dtype=np.uint64), np.ascontiguousarray(pm[: n // 2, 4:]).ravel()).reshape(-1, 4)
+    pm[n // 2:, :4] = pm[: n // 2, :4]
+    pm[n // 2:, 4:] = negy
+    s2 = np.concatenate([s[: 4 * (n // 2)], s[: 4 * (n // 2)]])
+    assert np.array_equal(ctx.msm_g1(s2, np.ascontiguousarray(pm).ravel()), ident)
+
+
+def test_msm_hot_bucket_large(ctx):
+    """Witness-like worst case: 2^18 booleans -> one bucket with ~131k points (task split + CTA fold)."""
+    n = 1 << 18
+    s = ob.gen_scalars(99, 1, n)
+    b = ob.gen_bases(0x53525300, n)
+    assert np.array_equal(ctx.msm_g1(s, b), ob.best_multiexp(s, b))
+
+
+def test_msm_srs_resident_batch_and_windows(ctx):
+    n = 1 << 13
+    b = ob.gen_bases(0x53525300, n)
+    sid = ctx.srs_register(b)
+    try:
+        cols = [ob.gen_scalars(200 + i, i % 3, n) for i in range(5)]
+        want = [ob.best_multiexp(c, b) for c in cols]
+        for c, w in zip(cols, want):
+            assert np.array_equal(ctx.msm_g1(c, srs_id=sid), w)
+        got = ctx.msm_g1_batch(sid, cols)
+        for i in range(5):
+            assert np.array_equal(got[i], affine_of(want[i]))
+        # window sharding: partials over disjoint window ranges add up to the full result
+        cbits, nwin = ctx.msm_config(n)
+        for shards in (2, 3, 8):
+            edges = [nwin * i // shards for i in range(shards + 1)]
+            parts = [ctx.msm_g1(cols[0], srs_id=sid, windows=(edges[i], edges[i + 1])) for i in range(shards)]
+            assert np.array_equal(ctx.g1_sum(np.concatenate(parts)), want[0])
+            assert np.array_equal(ob.g1_sum(np.concatenate(parts)), want[0])
+    finally:
+        ctx.srs_release(sid)
+
+
+def test_msm_full_size_properties(ctx):
+    """n = 2^22 (BASELINE k): additivity under concatenation and MSM(s, [P,P,...]) = (sum s) P,
+    checked against oracle results at sizes it finishes in seconds."""
+    n = 1 << 22
+    d_b = ctx.dev_alloc(n * 64)
+    d_s = ctx.dev_alloc(n * 32)
+    d_o = ctx.dev_alloc(4 * 160)
+    try:
+        ctx.synth_bases_dev(0x53525300 + 22, 0, n, d_b)
+        ctx.synth_scalars_dev(0xA660000 + 22, 0, 0, n, d_s)
+        ctx.msm_g1_dev(d_s, n, d_o, d_bases=d_b)
+        h = n // 2
+        ctx.msm_g1_dev(d_s, h, d_o + 160, d_bases=d_b)
+        ctx.msm_g1_dev(d_s + h * 32, h, d_o + 320, d_bases=d_b + h * 64)
+        ctx.synchronize()
+        out = ctx.d2h(d_o, 60).reshape(3, 20)
+        whole, lo, hi = out[0, 8:], out[1, 8:], out[2, 8:]
+        assert np.array_equal(ob.g1_sum(np.concatenate([lo, hi])), whole)
+        # first 2^16 pairs against the oracle directly
+        m = 1 << 16
+        ctx.msm_g1_dev(d_s, m, d_o + 480, d_bases=d_b)
+        ctx.synchronize()
+        got = ctx.d2h(d_o + 480, 20)[8:]
+        assert np.array_equal(got, ob.best_multiexp(ob.gen_scalars(0xA660000 + 22, 0, m), ob.gen_bases(0x53525300 + 22, m)))
+    finally:
+        ctx.dev_free(d_b)
+        ctx.dev_free(d_s)
+        ctx.dev_free(d_o)

@@ -1,0 +1,100 @@
+"""CPU suite: the C++ oracle against the Python big-int golden vectors and against itself
+(bucket method vs double-and-add, radix-2 recursion vs O(n^2) DFT), plus generator agreement."""
+import numpy as np
+import pytest
+
+import bn254_ref as ref
+import oracle_binding as ob
+from util import affine_of, arr, domain_consts, fr_limbs, golden, omega
+
+
+def test_field_golden():
+    for case in golden("field.json"):
+        f = case["field"]
+        a, b = arr(case["a"]), arr(case["b"])
+        assert np.array_equal(ob.field_op(f, 0, a, b), arr(case["add"]))
+        assert np.array_equal(ob.field_op(f, 1, a, b), arr(case["sub"]))
+        assert np.array_equal(ob.field_op(f, 3, a, b), arr(case["mul"]))
+        assert np.array_equal(ob.field_op(f, 2, a), arr(case["inv"]))
+
+
+@pytest.mark.parametrize("case", golden("msm.json"), ids=lambda c: c["name"])
+def test_msm_golden(case):
+    s, b = arr(case["scalars"]), arr(case["bases"])
+    want = arr(case["affine"])
+    for nthreads in (1, 3):
+        assert np.array_equal(affine_of(ob.best_multiexp(s, b, nthreads)), want)
+    assert np.array_equal(affine_of(ob.msm_naive(s, b)), want)
+
+
+@pytest.mark.parametrize("case", golden("ntt.json"), ids=lambda c: c["name"])
+def test_ntt_golden(case):
+    a, want = arr(case["input"]), arr(case["output"])
+    name = case["name"]
+    if name.startswith("fft"):
+        got = ob.best_fft(a.copy(), arr(case["omega"]), case["k"], 1)
+        assert np.array_equal(got, want)
+        assert np.array_equal(ob.best_fft(a.copy(), arr(case["omega"]), case["k"], 4), want)
+    elif name.startswith("ifft"):
+        assert np.array_equal(ob.ifft(a.copy(), arr(case["omega_inv"]), arr(case["n_inv"]), case["k"]), want)
+    elif name.startswith("coeff_to_extended"):
+        assert np.array_equal(ob.coeff_to_extended(a, case["k"], case["ext_k"], arr(case["zeta"]), arr(case["omega_ext"])), want)
+    else:
+        got = ob.extended_to_coeff(a.copy(), case["ext_k"], arr(case["omega_ext_inv"]), arr(case["ext_n_inv"]), arr(case["zeta"]), case["out_len"])
+        assert np.array_equal(got, want)
+
+
+def test_generators_match_python():
+    for kind in range(4):
+        got = ob.gen_scalars(0x1234 + kind, kind, 40, first=7)
+        want = np.array(ref.pack_fr([ref.gen_scalar(0x1234 + kind, kind, 7 + i) for i in range(40)]), dtype=np.uint64)
+        assert np.array_equal(got, want)
+    got = ob.gen_bases(0x5352_5300, 12, first=3)
+    pts = [ref.gen_base(0x5352_5300, 3 + i) for i in range(12)]
+    assert all(ref.on_curve(p) for p in pts)
+    assert np.array_equal(got, np.array(ref.pack_points(pts), dtype=np.uint64))
+    for i in range(12):
+        assert ob.on_curve(got[8 * i:8 * i + 8])
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 31, 32, 33, 100, 1000])
+@pytest.mark.parametrize("kind", [0, 1, 2])
+def test_best_multiexp_vs_naive(n, kind):
+    s = ob.gen_scalars(0xA660000 + n, kind, n)
+    b = ob.gen_bases(0x53525300, n)
+    want = ob.msm_naive(s, b)
+    for nthreads in (1, 2, 8):
+        assert np.array_equal(ob.best_multiexp(s, b, nthreads), want)
+
+
+@pytest.mark.parametrize("k", range(0, 11))
+def test_best_fft_vs_dft(k):
+    a = ob.gen_scalars(0xF00 + k, 0, 1 << k)
+    w = fr_limbs(omega(k))
+    want = ob.dft_naive(a, w, k)
+    for nthreads in (1, 4, 8):
+        assert np.array_equal(ob.best_fft(a.copy(), w, k, nthreads), want)
+
+
+@pytest.mark.parametrize("k", [3, 8, 12, 15])
+def test_domain_round_trips(k):
+    d = domain_consts(k)
+    a = ob.gen_scalars(0xD0 + k, 0, 1 << k)
+    f = ob.best_fft(a.copy(), d["omega"], k)
+    assert np.array_equal(ob.ifft(f, d["omega_inv"], d["n_inv"], k), a)
+    ext = ob.coeff_to_extended(a, k, k + 2, d["zeta"], d["omega_ext"])
+    back = ob.extended_to_coeff(ext, k + 2, d["omega_ext_inv"], d["ext_n_inv"], d["zeta"], 3 << k)
+    assert np.array_equal(back[: 4 << k], a)
+    assert not back[4 << k:].any()
+
+
+def test_msm_linearity_and_concatenation():
+    n = 300
+    s1, s2 = ob.gen_scalars(1, 0, n), ob.gen_scalars(2, 0, n)
+    b = ob.gen_bases(3, n)
+    lhs = ob.best_multiexp(ob.field_op(0, 0, s1, s2), b)
+    rhs = ob.g1_sum(np.concatenate([ob.best_multiexp(s1, b), ob.best_multiexp(s2, b)]))
+    assert np.array_equal(lhs, rhs)
+    whole = ob.best_multiexp(s1, b)
+    parts = ob.g1_sum(np.concatenate([ob.best_multiexp(s1[: 4 * 100], b[: 8 * 100]), ob.best_multiexp(s1[4 * 100:], b[8 * 100:])]))
+    assert np.array_equal(whole, parts)
