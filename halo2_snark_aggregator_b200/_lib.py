@@ -48,6 +48,8 @@ def load():
         "h2agg_set_stream": (ci, [c_vp, c_vp]),
         "h2agg_synchronize": (ci, [c_vp]),
         "h2agg_launch_count": (u64, [c_vp]),
+        "h2agg_kernel_timing": (ci, [c_vp, ci]),
+        "h2agg_kernel_times": (ci, [c_vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(u64), ci]),
         "h2agg_host_register": (ci, [c_vp, c_vp, sz]),
         "h2agg_host_unregister": (ci, [c_vp, c_vp]),
         "h2agg_set_msm_window": (ci, [c_vp, ci]),

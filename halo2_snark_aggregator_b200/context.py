@@ -53,6 +53,24 @@ class Context:
     def launch_count(self):
         return int(self.lib.h2agg_launch_count(self.h))
 
+    KERNEL_CLASSES = ("msm_accumulate", "msm_digits_sort", "msm_reduce", "ntt_pass", "msm_total")
+
+    def kernel_timing(self, enable):
+        self.check(self.lib.h2agg_kernel_timing(self.h, 1 if enable else 0))
+
+    def kernel_times(self):
+        """{class: (total_ms, launches)} since the last call (synchronises)."""
+        ms = (ctypes.c_double * 5)()
+        cnt = (ctypes.c_uint64 * 5)()
+        self.check(self.lib.h2agg_kernel_times(self.h, ms, cnt, 5))
+        return {k: (ms[i], int(cnt[i])) for i, k in enumerate(self.KERNEL_CLASSES)}
+
+    def host_register(self, arr):
+        self.check(self.lib.h2agg_host_register(self.h, _ptr(arr), arr.nbytes))
+
+    def host_unregister(self, arr):
+        self.check(self.lib.h2agg_host_unregister(self.h, _ptr(arr)))
+
     def set_msm_window(self, c):
         self.check(self.lib.h2agg_set_msm_window(self.h, int(c)))
 

@@ -120,6 +120,34 @@ int h2agg_synchronize(h2agg_ctx* ctx) {
 
 uint64_t h2agg_launch_count(h2agg_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+int h2agg_kernel_timing(h2agg_ctx* ctx, int enable) {
+  if (!ctx) return 1;
+  LOCK(ctx);
+  H2AGG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (auto& t : ctx->timed) { ctx->ev_pool.push_back(t.a); ctx->ev_pool.push_back(t.b); }
+  ctx->timed.clear();
+  ctx->timing = enable != 0;
+  return 0;
+}
+
+int h2agg_kernel_times(h2agg_ctx* ctx, double* ms_per_class, uint64_t* count_per_class, int n_classes) {
+  if (!ctx) return 1;
+  LOCK(ctx);
+  CHECK_ARG(ctx, ms_per_class && count_per_class && n_classes >= KC_COUNT, "kernel_times: need >= 5 classes");
+  H2AGG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < n_classes; i++) { ms_per_class[i] = 0; count_per_class[i] = 0; }
+  for (auto& t : ctx->timed) {
+    float ms = 0;
+    H2AGG_CUDA(ctx, cudaEventElapsedTime(&ms, t.a, t.b));
+    ms_per_class[t.cls] += ms;
+    count_per_class[t.cls]++;
+    ctx->ev_pool.push_back(t.a);
+    ctx->ev_pool.push_back(t.b);
+  }
+  ctx->timed.clear();
+  return 0;
+}
+
 int h2agg_host_register(h2agg_ctx* ctx, const void* p, size_t bytes) {
   if (!ctx) return 1;
   LOCK(ctx);

@@ -59,6 +59,11 @@ struct h2agg_ctx {
   uint64_t launches = 0;
   // MSM tuning (0 = auto)
   int msm_window_bits = 0;
+  // per-kernel-class device timing (CUDA events on ctx->stream), enabled by h2agg_kernel_timing
+  bool timing = false;
+  struct Timed { cudaEvent_t a, b; int cls; };
+  std::vector<Timed> timed;
+  std::vector<cudaEvent_t> ev_pool;
 };
 
 namespace h2agg {
@@ -90,6 +95,31 @@ inline int ensure(h2agg_ctx* ctx, DevBuf& b, size_t bytes) {
   b.cap = want;
   return 0;
 }
+
+// kernel classes for the timing hook
+enum KernelClass { KC_MSM_ACCUMULATE = 0, KC_MSM_DIGITS = 1, KC_MSM_REDUCE = 2, KC_NTT_PASS = 3, KC_MSM_TOTAL = 4, KC_COUNT = 5 };
+
+struct ScopedKernelTimer {
+  h2agg_ctx* ctx;
+  h2agg_ctx::Timed t;
+  bool on;
+  ScopedKernelTimer(h2agg_ctx* c, int cls) : ctx(c), on(c->timing) {
+    if (!on) return;
+    auto get = [&]() {
+      cudaEvent_t e;
+      if (!ctx->ev_pool.empty()) { e = ctx->ev_pool.back(); ctx->ev_pool.pop_back(); }
+      else cudaEventCreate(&e);
+      return e;
+    };
+    t.a = get(); t.b = get(); t.cls = cls;
+    cudaEventRecord(t.a, ctx->stream);
+  }
+  ~ScopedKernelTimer() {
+    if (!on) return;
+    cudaEventRecord(t.b, ctx->stream);
+    ctx->timed.push_back(t);
+  }
+};
 
 // ---- internal device-pointer API (all asynchronous on ctx->stream) -------------------------
 // NTT over Fr. `src` has src_n valid elements (rest of the 2^log_n domain is implicit zero),

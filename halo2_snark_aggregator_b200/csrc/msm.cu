@@ -405,10 +405,12 @@ int msm_run(h2agg_ctx* ctx, const void* d_bases, const void* d_scalars, size_t n
   uint8_t* buckets = ws + o_buckets;
 
   cudaStream_t st = ctx->stream;
+  ScopedKernelTimer t_total(ctx, KC_MSM_TOTAL);
   H2AGG_CUDA(ctx, cudaMemsetAsync(counts, 0, (size_t)(g.nb + 1) * 4, st));
   H2AGG_CUDA(ctx, cudaMemsetAsync(hot_count, 0, 256, st));
   if (n) {
     uint32_t grid = (uint32_t)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 8);
+    ScopedKernelTimer tk(ctx, KC_MSM_DIGITS);
     msm_digits<false><<<grid, 256, 0, st>>>((const uint4*)d_scalars, g, counts, nullptr);
     ctx->launches++;
   }
@@ -418,12 +420,17 @@ int msm_run(h2agg_ctx* ctx, const void* d_bases, const void* d_scalars, size_t n
   ctx->launches += 3;
   if (n) {
     uint32_t grid = (uint32_t)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 8);
-    msm_digits<true><<<grid, 256, 0, st>>>((const uint4*)d_scalars, g, cursor, entries);
-    ctx->launches++;
+    {
+      ScopedKernelTimer tk(ctx, KC_MSM_DIGITS);
+      msm_digits<true><<<grid, 256, 0, st>>>((const uint4*)d_scalars, g, cursor, entries);
+      ctx->launches++;
+    }
+    ScopedKernelTimer tk(ctx, KC_MSM_ACCUMULATE);
     msm_accumulate<<<(uint32_t)((max_tasks + MSM_THREADS - 1) / MSM_THREADS), MSM_THREADS, 0, st>>>(
         (const uint8_t*)d_bases, entries, offsets, task_off, g, partials, buckets);
     ctx->launches++;
   }
+  ScopedKernelTimer t_red(ctx, KC_MSM_REDUCE);
   msm_fold<<<(g.nb + MSM_THREADS - 1) / MSM_THREADS, MSM_THREADS, 0, st>>>(task_off, g, partials, buckets, hot_count,
                                                                             hot_list);
   msm_fold_hot<<<ctx->sm_count * 2, 256, 0, st>>>(task_off, partials, buckets, hot_count, hot_list);

@@ -317,6 +317,7 @@ int ntt_run(h2agg_ctx* ctx, const void* d_src, void* d_dst, const NttOpts& o) {
       a.has_out = 1;
       memcpy(a.out3, o.out_scale3, 96);
     }
+    ScopedKernelTimer tk(ctx, KC_NTT_PASS);
     uint32_t cb = NTT_TILE_LOG - s[t];
     size_t smem;
     unsigned long long tiles;

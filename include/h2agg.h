@@ -49,6 +49,11 @@ int h2agg_set_stream(h2agg_ctx* ctx, void* cuda_stream);
 int h2agg_synchronize(h2agg_ctx* ctx);
 /* Number of kernels this context has launched so far (evidence counter for bench.py). */
 uint64_t h2agg_launch_count(h2agg_ctx* ctx);
+/* Per-kernel-class device timing with CUDA events on the context's stream (bench.py roofline).
+ * classes: 0 msm_accumulate, 1 msm digit/sort kernels, 2 msm bucket+window reduction, 3 ntt pass,
+ * 4 whole MSM.  h2agg_kernel_times synchronises, returns the sums since the last call and resets. */
+int h2agg_kernel_timing(h2agg_ctx* ctx, int enable);
+int h2agg_kernel_times(h2agg_ctx* ctx, double* ms_per_class, uint64_t* count_per_class, int n_classes);
 /* Pin / unpin a host range so H2D copies run at PCIe speed (the SRS, witness columns). */
 int h2agg_host_register(h2agg_ctx* ctx, const void* p, size_t bytes);
 int h2agg_host_unregister(h2agg_ctx* ctx, const void* p);
