@@ -243,14 +243,21 @@ def main():
     def step_device():
         c = 0
         for r in rounds:
-            sent = 0
-            for i, u in mine:
-                if u[0] != r:
-                    continue
+            mine_r = [(i, u) for i, u in mine if u[0] == r]
+            msm_ids = [i for i, u in mine_r if u[1] == "msm"]
+            first_msm = True
+            for i, u in mine_r:
                 what = u[1]
                 if what == "msm":
-                    ctx.msm_g1_dev(t_cols[i].data_ptr(), n, t_out.data_ptr() + i * 160, srs_id=srs)
-                    sent += 1
+                    # the round's commitments are independent: one batched call per contiguous group
+                    # (rounds 0-2, 4: one group; round 3: random poly before, h pieces after the NTTs)
+                    group = [j for j in msm_ids if (j < 64) == (i < 64)] if r == 3 else msm_ids
+                    if group and group[0] == i:
+                        if contiguous_out(group):
+                            ctx.msm_g1_batch_dev([t_cols[j].data_ptr() for j in group], n, t_out.data_ptr() + group[0] * 160, srs_id=srs)
+                        else:
+                            for j in group:
+                                ctx.msm_g1_dev(t_cols[j].data_ptr(), n, t_out.data_ptr() + j * 160, srs_id=srs)
                 elif what == "intt":
                     dom.lagrange_to_coeff_dev(t_ntt[c % n_ntt_bufs].data_ptr())
                 elif what == "coset":
@@ -261,11 +268,13 @@ def main():
             if world > 1:
                 # every rank needs every commitment of the round to drive the transcript:
                 # one all-gather of <= 14 x 160 B per commit round (EC points are not an NCCL reduce op)
-                mine_r = [i for i, u in mine if u[0] == r and u[1] == "msm"]
                 send = torch.zeros(per_round_max * 160, dtype=torch.uint8, device=dev)
-                for slot, i in enumerate(mine_r):
+                for slot, i in enumerate(msm_ids):
                     send[slot * 160:(slot + 1) * 160] = t_out[i * 160:(i + 1) * 160]
                 dist.all_gather_into_tensor(t_gather, send)
+
+    def contiguous_out(group):
+        return all(b - a == 1 for a, b in zip(group, group[1:]))
 
     def barrier():
         torch.cuda.synchronize()
@@ -316,7 +325,7 @@ def main():
         h2d = d2h = 0
         for i, u in mine:
             if u[1] == "msm":
-                h2d += n * 32; d2h += 96
+                h2d += n * 32; d2h += 160
             elif u[1] == "intt":
                 h2d += n * 32; d2h += n * 32
             elif u[1] == "coset":
@@ -327,18 +336,23 @@ def main():
         def step_host():
             c = 0
             outs = []
-            for i, u in mine:
-                what = u[1]
-                if what == "msm":
-                    outs.append(ctx.msm_g1(h_cols[i], srs_id=srs, n=n))
-                elif what == "intt":
-                    ctx.intt_fr(h_ntt[c % 2], dom.omega_inv, dom.ifft_divisor, k)
-                elif what == "coset":
-                    ctx.lib.h2agg_coeff_to_extended(ctx.h, h_ntt[c % 2].ctypes.data, k, k + 2, dom.g_coset.ctypes.data,
-                                                    dom.extended_omega.ctypes.data, h_ext.ctypes.data)
-                else:
-                    ctx.extended_to_coeff(h_ext, k + 2, dom.extended_omega_inv, dom.extended_ifft_divisor, dom.g_coset, 3 * n)
-                c += 1
+            for r in rounds:
+                mine_r = [(i, u) for i, u in mine if u[0] == r]
+                msm_ids = [i for i, u in mine_r if u[1] == "msm"]
+                for i, u in mine_r:
+                    what = u[1]
+                    if what == "msm":
+                        group = [j for j in msm_ids if (j < 64) == (i < 64)] if r == 3 else msm_ids
+                        if group and group[0] == i:  # one commit round = one batched call (H2D of column i+1 overlaps MSM i)
+                            outs.append(ctx.msm_g1_batch(srs, [h_cols[j] for j in group], n))
+                    elif what == "intt":
+                        ctx.intt_fr(h_ntt[c % 2], dom.omega_inv, dom.ifft_divisor, k)
+                    elif what == "coset":
+                        ctx.lib.h2agg_coeff_to_extended(ctx.h, h_ntt[c % 2].ctypes.data, k, k + 2, dom.g_coset.ctypes.data,
+                                                        dom.extended_omega.ctypes.data, h_ext.ctypes.data)
+                    else:
+                        ctx.extended_to_coeff(h_ext, k + 2, dom.extended_omega_inv, dom.extended_ifft_divisor, dom.g_coset, 3 * n)
+                    c += 1
             return outs
 
         step_host()

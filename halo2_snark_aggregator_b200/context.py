@@ -138,6 +138,10 @@ class Context:
         self.check(self.lib.h2agg_msm_g1_batch(self.h, srs_id, arr, len(cols), n, _ptr(out)))
         return out.reshape(len(cols), 8)
 
+    def msm_g1_batch_dev(self, d_cols, n, d_out160s, d_bases=0, srs_id=0):
+        arr = (c_vp * len(d_cols))(*d_cols)
+        self.check(self.lib.h2agg_msm_g1_batch_dev(self.h, srs_id, c_vp(d_bases), arr, len(d_cols), n, c_vp(d_out160s)))
+
     def g1_sum(self, points_jac):
         out = np.zeros(12, dtype=np.uint64)
         self.check(self.lib.h2agg_g1_sum(self.h, _ptr(points_jac), points_jac.size // 12, _ptr(out)))

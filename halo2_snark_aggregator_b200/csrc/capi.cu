@@ -91,6 +91,14 @@ void h2agg_destroy(h2agg_ctx* ctx) {
   cudaFree(ctx->io_a.p);
   cudaFree(ctx->io_b.p);
   cudaFree(ctx->msm_ws.p);
+  for (int i = 0; i < N_LANES; i++) {
+    if (ctx->lanes[i].st) cudaStreamSynchronize(ctx->lanes[i].st);
+    cudaFree(ctx->lanes[i].ws.p);
+    cudaFree(ctx->lanes[i].io.p);
+    if (ctx->lanes[i].done) cudaEventDestroy(ctx->lanes[i].done);
+    if (ctx->lanes[i].st) cudaStreamDestroy(ctx->lanes[i].st);
+  }
+  if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
   cudaFree(ctx->small.p);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -259,7 +267,7 @@ int h2agg_msm_g1_windows(h2agg_ctx* ctx, uint64_t srs_id, const uint64_t* bases,
   rc = ensure(ctx, ctx->io_a, n * 32 + 64);
   if (rc) return rc;
   if (n) H2AGG_CUDA(ctx, cudaMemcpyAsync(ctx->io_a.p, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-  rc = msm_run(ctx, d_bases, ctx->io_a.p, n, ctx->small.p, win_begin, win_end);
+  rc = msm_run(ctx, ctx->stream, ctx->msm_ws, d_bases, ctx->io_a.p, n, ctx->small.p, win_begin, win_end);
   if (rc) return rc;
   H2AGG_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, ctx->small.p, 160, cudaMemcpyDeviceToHost, ctx->stream));
   H2AGG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -282,7 +290,7 @@ int h2agg_msm_g1_windows_dev(h2agg_ctx* ctx, uint64_t srs_id, const void* d_base
   const void* d_bases;
   int rc = resolve_bases(ctx, srs_id, nullptr, d_bases_in, n, &d_bases);
   if (rc) return rc;
-  return msm_run(ctx, d_bases, d_scalars, n, d_out160, win_begin, win_end);
+  return msm_run(ctx, ctx->stream, ctx->msm_ws, d_bases, d_scalars, n, d_out160, win_begin, win_end);
 }
 
 int h2agg_msm_g1_dev(h2agg_ctx* ctx, uint64_t srs_id, const void* d_bases, const void* d_scalars, size_t n,
@@ -301,22 +309,26 @@ int h2agg_msm_g1_batch(h2agg_ctx* ctx, uint64_t srs_id, const uint64_t* const* c
   const void* d_bases;
   int rc = resolve_bases(ctx, srs_id, nullptr, nullptr, n, &d_bases);
   if (rc) return rc;
-  // double-buffered upload: column i+1 crosses PCIe while column i is in the bucket kernels
-  rc = ensure(ctx, ctx->io_a, n * 32 + 64);
+  // lanes: column i+1 crosses PCIe while column i is in the bucket kernels
+  for (size_t i = 0; i < n_cols; i++) CHECK_ARG(ctx, cols[i], "msm_batch: null column");
+  rc = msm_run_batch(ctx, d_bases, (const void* const*)cols, n_cols, n, (uint8_t*)ctx->small.p, true);
   if (rc) return rc;
-  rc = ensure(ctx, ctx->io_b, n * 32 + 64);
-  if (rc) return rc;
-  for (size_t i = 0; i < n_cols; i++) {
-    CHECK_ARG(ctx, cols[i], "msm_batch: null column");
-    void* buf = (i & 1) ? ctx->io_b.p : ctx->io_a.p;
-    if (n) H2AGG_CUDA(ctx, cudaMemcpyAsync(buf, cols[i], n * 32, cudaMemcpyHostToDevice, ctx->stream));
-    rc = msm_run(ctx, d_bases, buf, n, (uint8_t*)ctx->small.p + i * 160, 0, -1);
-    if (rc) return rc;
-  }
   H2AGG_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, ctx->small.p, n_cols * 160, cudaMemcpyDeviceToHost, ctx->stream));
   H2AGG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   for (size_t i = 0; i < n_cols; i++) memcpy(out_affine + i * 8, (uint8_t*)ctx->pinned + i * 160, 64);
   return 0;
+}
+
+int h2agg_msm_g1_batch_dev(h2agg_ctx* ctx, uint64_t srs_id, const void* d_bases_in, const void* const* d_cols,
+                           size_t n_cols, size_t n, void* d_out160s) {
+  if (!ctx) return 1;
+  LOCK(ctx);
+  CHECK_ARG(ctx, d_cols && d_out160s, "msm_batch_dev: null argument");
+  H2AGG_CUDA(ctx, cudaSetDevice(ctx->device));
+  const void* d_bases;
+  int rc = resolve_bases(ctx, srs_id, nullptr, d_bases_in, n, &d_bases);
+  if (rc) return rc;
+  return msm_run_batch(ctx, d_bases, d_cols, n_cols, n, (uint8_t*)d_out160s, false);
 }
 
 int h2agg_g1_sum(h2agg_ctx* ctx, const uint64_t* pts, size_t m, uint64_t out_jacobian[12]) {

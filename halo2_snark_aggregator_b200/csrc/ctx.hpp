@@ -30,10 +30,16 @@ struct Srs {
   bool owned = false;
 };
 
-struct Error {
-  int code;
-  std::string msg;
+// A lane = one auxiliary stream with its own MSM workspace and staging buffer.  Batches alternate
+// lanes so the latency-bound tail of MSM i (window sums, Horner, inversion) and the H2D copy of
+// column i+1 overlap with the IMAD-bound bucket accumulation of its neighbour.
+struct Lane {
+  cudaStream_t st = nullptr;
+  DevBuf ws;        // MSM workspace
+  DevBuf io;        // staging for host-pointer batches
+  cudaEvent_t done = nullptr;
 };
+static constexpr int N_LANES = 2;
 
 }  // namespace h2agg
 
@@ -46,7 +52,9 @@ struct h2agg_ctx {
   // scratch
   h2agg::DevBuf ntt_tmp;      // ping-pong buffer for multi-pass NTT
   h2agg::DevBuf io_a, io_b;   // staging for host-pointer entry points
-  h2agg::DevBuf msm_ws;       // MSM workspace (digits, sort, buckets)
+  h2agg::DevBuf msm_ws;       // MSM workspace (digits, sort, buckets) of the main stream
+  h2agg::Lane lanes[h2agg::N_LANES];
+  cudaEvent_t fork_ev = nullptr;
   h2agg::DevBuf small;        // small constants / results
   void* pinned = nullptr;     // pinned host bounce buffer for tiny results
   size_t pinned_cap = 0;
@@ -81,7 +89,7 @@ namespace h2agg {
 inline int ensure(h2agg_ctx* ctx, DevBuf& b, size_t bytes) {
   if (b.cap >= bytes) return 0;
   if (b.p) {
-    H2AGG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    H2AGG_CUDA(ctx, cudaDeviceSynchronize());
     H2AGG_CUDA(ctx, cudaFree(b.p));
     b.p = nullptr;
     b.cap = 0;
@@ -103,7 +111,8 @@ struct ScopedKernelTimer {
   h2agg_ctx* ctx;
   h2agg_ctx::Timed t;
   bool on;
-  ScopedKernelTimer(h2agg_ctx* c, int cls) : ctx(c), on(c->timing) {
+  cudaStream_t st;
+  ScopedKernelTimer(h2agg_ctx* c, int cls, cudaStream_t s = nullptr) : ctx(c), on(c->timing), st(s ? s : c->stream) {
     if (!on) return;
     auto get = [&]() {
       cudaEvent_t e;
@@ -112,11 +121,11 @@ struct ScopedKernelTimer {
       return e;
     };
     t.a = get(); t.b = get(); t.cls = cls;
-    cudaEventRecord(t.a, ctx->stream);
+    cudaEventRecord(t.a, st);
   }
   ~ScopedKernelTimer() {
     if (!on) return;
-    cudaEventRecord(t.b, ctx->stream);
+    cudaEventRecord(t.b, st);
     ctx->timed.push_back(t);
   }
 };
@@ -136,8 +145,13 @@ int ntt_run(h2agg_ctx* ctx, const void* d_src, void* d_dst, const NttOpts& o);
 // MSM over G1: d_scalars n x 32 B (Montgomery Fr), d_bases n x 64 B affine.
 // Writes affine (64 B) + jacobian (96 B, z = 1 or 0) to d_out (160 B, device).
 // Windows [win_begin, win_end) only (pass 0, -1 for all): partial = sum_w 2^(c w) B_w.
-int msm_run(h2agg_ctx* ctx, const void* d_bases, const void* d_scalars, size_t n, void* d_out160,
-            int win_begin, int win_end);
+int msm_run(h2agg_ctx* ctx, cudaStream_t st, DevBuf& ws, const void* d_bases, const void* d_scalars, size_t n,
+            void* d_out160, int win_begin, int win_end);
+// n_cols MSMs against the same bases, alternating lanes; joins back into ctx->stream.
+// Columns are device pointers, or host pointers when `host_cols` (then staged through the lanes).
+int msm_run_batch(h2agg_ctx* ctx, const void* d_bases, const void* const* cols, size_t n_cols, size_t n,
+                  uint8_t* d_out160s, bool host_cols);
+int lanes_init(h2agg_ctx* ctx);
 // sum of m affine-or-jacobian(96 B) points -> d_out160
 int g1_sum_jacobian(h2agg_ctx* ctx, const void* d_points96, size_t m, void* d_out160);
 int msm_window_config(size_t n, int forced_c, int* c, int* nwin);

@@ -344,8 +344,43 @@ int g1_sum_jacobian(h2agg_ctx* ctx, const void* d_points96, size_t m, void* d_ou
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-int msm_run(h2agg_ctx* ctx, const void* d_bases, const void* d_scalars, size_t n, void* d_out160, int win_begin,
-            int win_end) {
+int lanes_init(h2agg_ctx* ctx) {
+  if (ctx->fork_ev) return 0;
+  H2AGG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
+  for (int i = 0; i < N_LANES; i++) {
+    H2AGG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->lanes[i].st, cudaStreamNonBlocking));
+    H2AGG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->lanes[i].done, cudaEventDisableTiming));
+  }
+  return 0;
+}
+
+int msm_run_batch(h2agg_ctx* ctx, const void* d_bases, const void* const* cols, size_t n_cols, size_t n,
+                  uint8_t* d_out160s, bool host_cols) {
+  if (n_cols == 0) return 0;
+  int rc;
+  if (n_cols == 1 && !host_cols) return msm_run(ctx, ctx->stream, ctx->msm_ws, d_bases, cols[0], n, d_out160s, 0, -1);
+  if ((rc = lanes_init(ctx))) return rc;
+  H2AGG_CUDA(ctx, cudaEventRecord(ctx->fork_ev, ctx->stream));
+  for (int l = 0; l < N_LANES; l++) H2AGG_CUDA(ctx, cudaStreamWaitEvent(ctx->lanes[l].st, ctx->fork_ev, 0));
+  for (size_t i = 0; i < n_cols; i++) {
+    Lane& ln = ctx->lanes[i % N_LANES];
+    const void* d_col = cols[i];
+    if (host_cols) {
+      if ((rc = ensure(ctx, ln.io, n * 32 + 64))) return rc;
+      if (n) H2AGG_CUDA(ctx, cudaMemcpyAsync(ln.io.p, cols[i], n * 32, cudaMemcpyHostToDevice, ln.st));
+      d_col = ln.io.p;
+    }
+    if ((rc = msm_run(ctx, ln.st, ln.ws, d_bases, d_col, n, d_out160s + i * 160, 0, -1))) return rc;
+  }
+  for (int l = 0; l < N_LANES; l++) {
+    H2AGG_CUDA(ctx, cudaEventRecord(ctx->lanes[l].done, ctx->lanes[l].st));
+    H2AGG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->lanes[l].done, 0));
+  }
+  return 0;
+}
+
+int msm_run(h2agg_ctx* ctx, cudaStream_t st, DevBuf& wsbuf, const void* d_bases, const void* d_scalars, size_t n,
+            void* d_out160, int win_begin, int win_end) {
   if (n >= (1ull << 31)) {
     ctx->last_error = "msm: n must be < 2^31";
     return 1;
@@ -390,9 +425,9 @@ int msm_run(h2agg_ctx* ctx, const void* d_bases, const void* d_scalars, size_t n
   size_t lvl_items = (size_t)g.nwin * ((g.bpw + WSUM_L - 1) / WSUM_L);
   size_t o_lvl_s0 = carve(lvl_items * 128), o_lvl_c0 = carve(lvl_items * 128);
   size_t o_lvl_s1 = carve(lvl_items * 128), o_lvl_c1 = carve(lvl_items * 128);
-  int rc = ensure(ctx, ctx->msm_ws, off);
+  int rc = ensure(ctx, wsbuf, off);
   if (rc) return rc;
-  uint8_t* ws = (uint8_t*)ctx->msm_ws.p;
+  uint8_t* ws = (uint8_t*)wsbuf.p;
   uint32_t* counts = (uint32_t*)(ws + o_counts);
   uint32_t* offsets = (uint32_t*)(ws + o_offsets);
   uint32_t* cursor = (uint32_t*)(ws + o_cursor);
@@ -404,13 +439,12 @@ int msm_run(h2agg_ctx* ctx, const void* d_bases, const void* d_scalars, size_t n
   uint8_t* partials = ws + o_partials;
   uint8_t* buckets = ws + o_buckets;
 
-  cudaStream_t st = ctx->stream;
-  ScopedKernelTimer t_total(ctx, KC_MSM_TOTAL);
+  ScopedKernelTimer t_total(ctx, KC_MSM_TOTAL, st);
   H2AGG_CUDA(ctx, cudaMemsetAsync(counts, 0, (size_t)(g.nb + 1) * 4, st));
   H2AGG_CUDA(ctx, cudaMemsetAsync(hot_count, 0, 256, st));
   if (n) {
     uint32_t grid = (uint32_t)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 8);
-    ScopedKernelTimer tk(ctx, KC_MSM_DIGITS);
+    ScopedKernelTimer tk(ctx, KC_MSM_DIGITS, st);
     msm_digits<false><<<grid, 256, 0, st>>>((const uint4*)d_scalars, g, counts, nullptr);
     ctx->launches++;
   }
@@ -421,16 +455,16 @@ int msm_run(h2agg_ctx* ctx, const void* d_bases, const void* d_scalars, size_t n
   if (n) {
     uint32_t grid = (uint32_t)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 8);
     {
-      ScopedKernelTimer tk(ctx, KC_MSM_DIGITS);
+      ScopedKernelTimer tk(ctx, KC_MSM_DIGITS, st);
       msm_digits<true><<<grid, 256, 0, st>>>((const uint4*)d_scalars, g, cursor, entries);
       ctx->launches++;
     }
-    ScopedKernelTimer tk(ctx, KC_MSM_ACCUMULATE);
+    ScopedKernelTimer tk(ctx, KC_MSM_ACCUMULATE, st);
     msm_accumulate<<<(uint32_t)((max_tasks + MSM_THREADS - 1) / MSM_THREADS), MSM_THREADS, 0, st>>>(
         (const uint8_t*)d_bases, entries, offsets, task_off, g, partials, buckets);
     ctx->launches++;
   }
-  ScopedKernelTimer t_red(ctx, KC_MSM_REDUCE);
+  ScopedKernelTimer t_red(ctx, KC_MSM_REDUCE, st);
   msm_fold<<<(g.nb + MSM_THREADS - 1) / MSM_THREADS, MSM_THREADS, 0, st>>>(task_off, g, partials, buckets, hot_count,
                                                                             hot_list);
   msm_fold_hot<<<ctx->sm_count * 2, 256, 0, st>>>(task_off, partials, buckets, hot_count, hot_list);

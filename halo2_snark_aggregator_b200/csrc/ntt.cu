@@ -20,7 +20,7 @@
 
 namespace h2agg {
 
-static constexpr int NTT_THREADS = 256;
+static constexpr int NTT_THREADS = 512;
 static constexpr uint32_t NTT_TILE_LOG = 11;  // 2048 elements = 64 KiB of shared memory per CTA
 
 struct NttPassArgs {
@@ -39,6 +39,7 @@ struct NttPassArgs {
   uint32_t mid_log[2];
   uint32_t npass;
   uint32_t has_in, has_out;
+  uint32_t zskip;   // top `zskip` bits of the row index are zero for every non-zero input row (first pass)
   Fr in3[3];
   Fr out3[3];
 };
@@ -100,8 +101,13 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(const __grid_cons
     base = 0;
   }
 
-  // ---- load (bit-reversed rows so that the DIT stages below end in natural order)
-  for (uint32_t idx = tid; idx < E; idx += NTT_THREADS) {
+  // ---- load.  Non-last passes: rows land bit-reversed and DIT stages follow (natural order out).
+  // Last pass: rows land in natural order (contiguous, conflict-free) and DIF stages follow; the
+  // store then reads row brev(k).  Rows r >= R >> zskip are known to be zero (zero-padded coset
+  // input): they are neither loaded nor computed -- after the bit reversal the first `zskip` DIT
+  // stages degenerate to copies, so each loaded value is replicated 2^zskip times instead.
+  const uint32_t zs = LAST ? 0u : p.zskip;
+  for (uint32_t idx = tid; idx < (E >> zs); idx += NTT_THREADS) {
     uint32_t r, c;
     unsigned long long pos;
     if (!LAST) {
@@ -123,36 +129,53 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(const __grid_cons
     } else {
       v = Fr::zero();
     }
-    uint32_t rr = __brev(r) >> (32 - s);
-    if (s == 0) rr = 0;
-    uint32_t si = rr * rs + c * cs;
-    xl[si] = v.lo4();
-    xh[si] = v.hi4();
+    if (!LAST) {
+      uint32_t rr = __brev(r) >> (32 - s);
+      for (uint32_t t = 0; t < (1u << zs); t++) {
+        uint32_t si = (rr + t) * rs + c * cs;
+        xl[si] = v.lo4();
+        xh[si] = v.hi4();
+      }
+    } else {
+      uint32_t si = r * rs + c * cs;
+      xl[si] = v.lo4();
+      xh[si] = v.hi4();
+    }
   }
 
-  // ---- radix-2 DIT stages in shared memory
-  for (uint32_t lh = 0; lh < s; lh++) {
+  // ---- radix-2 stages in shared memory.  Thread -> (j, g, c) with c fastest and the twiddle
+  // index j slowest, so a warp shares one twiddle and the w = 1 butterflies (j == 0: a whole
+  // stage's worth plus half, a quarter, ... of the others) skip the multiplication warp-uniformly.
+  for (uint32_t st = zs; st < s; st++) {
     __syncthreads();
+    const uint32_t lh = LAST ? (s - 1 - st) : st;  // DIF runs the strides downwards
     const uint32_t h = 1u << lh;
+    const uint32_t gbits = s - 1 - lh;             // log2 of the number of groups R / 2h
     for (uint32_t b = tid; b < (E >> 1); b += NTT_THREADS) {
-      uint32_t q, c;
-      if (!LAST) {
-        c = b & (C - 1);
-        q = b >> cbits;
-      } else {
-        q = b & ((R >> 1) - 1);
-        c = b >> (s - 1);
-      }
-      uint32_t j = q & (h - 1);
-      uint32_t i = ((q >> lh) << (lh + 1)) + j;
+      uint32_t c = b & (C - 1);
+      uint32_t q = b >> cbits;
+      uint32_t g = q & ((1u << gbits) - 1);
+      uint32_t j = q >> gbits;
+      uint32_t i = (g << (lh + 1)) + j;
       uint32_t i0 = i * rs + c * cs, i1 = (i + h) * rs + c * cs;
       Fr x0 = Fr::from_halves(xl[i0], xh[i0]);
       Fr x1 = Fr::from_halves(xl[i1], xh[i1]);
-      if (j) {
-        uint32_t m = j << (s - 1 - lh);
-        x1 = x1 * Fr::from_halves(twl[m], twh[m]);
+      Fr y0, y1;
+      if (!LAST) {
+        if (j) {
+          uint32_t m = j << gbits;
+          x1 = x1 * Fr::from_halves(twl[m], twh[m]);
+        }
+        y0 = x0 + x1;
+        y1 = x0 - x1;
+      } else {
+        y0 = x0 + x1;
+        y1 = x0 - x1;
+        if (j) {
+          uint32_t m = j << gbits;
+          y1 = y1 * Fr::from_halves(twl[m], twh[m]);
+        }
       }
-      Fr y0 = x0 + x1, y1 = x0 - x1;
       xl[i0] = y0.lo4(); xh[i0] = y0.hi4();
       xl[i1] = y1.lo4(); xh[i1] = y1.hi4();
     }
@@ -193,7 +216,7 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(const __grid_cons
       uint32_t c = idx & (C - 1), k = idx >> cbits;
       unsigned long long pos = obase + c + ((unsigned long long)k << p.log_p);
       if (pos >= p.dst_n) continue;
-      uint32_t si = k * rs + c * cs;
+      uint32_t si = (__brev(k) >> (32 - s)) * rs + c * cs;
       Fr v = Fr::from_halves(xl[si], xh[si]);
       if (p.has_out) v = v * p.out3[(uint32_t)(pos % 3)];
       p.dst[2 * pos] = v.lo4();
@@ -309,6 +332,11 @@ int ntt_run(h2agg_ctx* ctx, const void* d_src, void* d_dst, const NttOpts& o) {
     a.npass = T;
     a.src_n = (t == 0) ? o.src_n : N;
     a.dst_n = last ? o.dst_n : N;
+    if (t == 0 && !last) {
+      uint32_t z = 0;
+      while (z < s[0] && (o.src_n << (z + 1)) <= N) z++;
+      a.zskip = z;
+    }
     if (t == 0 && o.in_coset3) {
       a.has_in = 1;
       memcpy(a.in3, o.in_coset3, 96);

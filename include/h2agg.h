@@ -80,6 +80,11 @@ int h2agg_msm_g1(h2agg_ctx* ctx, uint64_t srs_id, const uint64_t* bases_affine /
 /* One commit round: n_cols columns of n scalars against the same bases -> n_cols affine points. */
 int h2agg_msm_g1_batch(h2agg_ctx* ctx, uint64_t srs_id, const uint64_t* const* scalar_cols, size_t n_cols, size_t n,
                        uint64_t* out_affine /* n_cols*8 */);
+/* Same with device-resident columns; d_out160s receives n_cols x (affine 64 B + Jacobian 96 B).
+ * Internally alternates two streams so the latency-bound tail of one MSM overlaps the bucket
+ * accumulation of the next; joined back into the context's stream before returning. */
+int h2agg_msm_g1_batch_dev(h2agg_ctx* ctx, uint64_t srs_id, const void* d_bases_affine, const void* const* d_scalar_cols,
+                           size_t n_cols, size_t n, void* d_out160s);
 /* Device-resident variant: d_scalars (n*32 B) and bases already in HBM; d_out160 receives
  * affine (64 B) followed by the normalised Jacobian (96 B).  Asynchronous. */
 int h2agg_msm_g1_dev(h2agg_ctx* ctx, uint64_t srs_id, const void* d_bases_affine, const void* d_scalars, size_t n,

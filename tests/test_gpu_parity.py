@@ -227,3 +227,26 @@ def test_msm_full_size_properties(ctx):
         ctx.dev_free(d_b)
         ctx.dev_free(d_s)
         ctx.dev_free(d_o)
+
+
+def test_msm_batch_dev_lanes(ctx):
+    """Device-resident batch (two alternating streams) == per-column results == oracle."""
+    n = 1 << 14
+    ncols = 7
+    d_b = ctx.dev_alloc(n * 64)
+    d_cols = [ctx.dev_alloc(n * 32) for _ in range(ncols)]
+    d_o = ctx.dev_alloc(ncols * 160)
+    try:
+        ctx.synth_bases_dev(0x53525300, 0, n, d_b)
+        for i, d in enumerate(d_cols):
+            ctx.synth_scalars_dev(900 + i, i % 4, 0, n, d)
+        for _ in range(3):  # repeated to shake out cross-stream workspace reuse
+            ctx.msm_g1_batch_dev(d_cols, n, d_o, d_bases=d_b)
+            ctx.synchronize()
+            got = ctx.d2h(d_o, 20 * ncols).reshape(ncols, 20)
+            b = ob.gen_bases(0x53525300, n)
+            for i in range(ncols):
+                assert np.array_equal(got[i, 8:], ob.best_multiexp(ob.gen_scalars(900 + i, i % 4, n), b)), i
+    finally:
+        for d in d_cols + [d_b, d_o]:
+            ctx.dev_free(d)
