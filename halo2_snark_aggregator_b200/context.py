@@ -74,6 +74,15 @@ class Context:
     def set_msm_window(self, c):
         self.check(self.lib.h2agg_set_msm_window(self.h, int(c)))
 
+    def set_srs_precompute(self, enable):
+        self.check(self.lib.h2agg_set_srs_precompute(self.h, 1 if enable else 0))
+
+    def srs_config(self, sid):
+        """(table_mode, c, n_windows) for MSMs against a registered SRS."""
+        t, c, w = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        self.check(self.lib.h2agg_srs_config(self.h, sid, ctypes.byref(t), ctypes.byref(c), ctypes.byref(w)))
+        return bool(t.value), c.value, w.value
+
     def msm_config(self, n):
         c, w = ctypes.c_int(), ctypes.c_int()
         self.check(self.lib.h2agg_msm_config(self.h, n, ctypes.byref(c), ctypes.byref(w)))

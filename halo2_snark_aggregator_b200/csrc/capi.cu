@@ -85,8 +85,10 @@ void h2agg_destroy(h2agg_ctx* ctx) {
     cudaFree(t.lo);
     cudaFree(t.hi);
   }
-  for (auto& kv : ctx->srs)
+  for (auto& kv : ctx->srs) {
     if (kv.second.owned) cudaFree(const_cast<void*>(kv.second.d_bases));
+    if (kv.second.d_table) cudaFree(kv.second.d_table);
+  }
   cudaFree(ctx->ntt_tmp.p);
   cudaFree(ctx->io_a.p);
   cudaFree(ctx->io_b.p);
@@ -177,6 +179,28 @@ int h2agg_set_msm_window(h2agg_ctx* ctx, int c_bits) {
   return 0;
 }
 
+int h2agg_set_srs_precompute(h2agg_ctx* ctx, int enable) {
+  if (!ctx) return 1;
+  LOCK(ctx);
+  ctx->srs_precompute = enable != 0;
+  return 0;
+}
+
+int h2agg_srs_config(h2agg_ctx* ctx, uint64_t srs_id, int* table_mode, int* c_bits, int* n_windows) {
+  if (!ctx || !table_mode || !c_bits || !n_windows) return 1;
+  LOCK(ctx);
+  auto it = ctx->srs.find(srs_id);
+  CHECK_ARG(ctx, it != ctx->srs.end(), "srs_config: unknown srs id");
+  const bool table = it->second.d_table != nullptr && ctx->msm_window_bits == 0;
+  *table_mode = table ? 1 : 0;
+  if (table) {
+    *c_bits = it->second.table_c;
+    *n_windows = it->second.table_nwin;
+    return 0;
+  }
+  return msm_window_config(it->second.n, ctx->msm_window_bits, c_bits, n_windows);
+}
+
 int h2agg_msm_config(h2agg_ctx* ctx, size_t n, int* c_bits, int* n_windows) {
   if (!ctx || !c_bits || !n_windows) return 1;
   LOCK(ctx);
@@ -202,6 +226,10 @@ int h2agg_srs_register(h2agg_ctx* ctx, const uint64_t* bases, size_t n, uint64_t
   s.d_bases = d;
   s.n = n;
   s.owned = true;
+  if (ctx->srs_precompute) {
+    int rc = msm_build_srs_table(ctx, s);
+    if (rc) { cudaFree(d); return rc; }
+  }
   *out_id = ctx->next_srs++;
   ctx->srs[*out_id] = s;
   return 0;
@@ -215,6 +243,11 @@ int h2agg_srs_register_dev(h2agg_ctx* ctx, const void* d_bases, size_t n, uint64
   s.d_bases = d_bases;
   s.n = n;
   s.owned = false;
+  H2AGG_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (ctx->srs_precompute) {
+    int rc = msm_build_srs_table(ctx, s);
+    if (rc) return rc;
+  }
   *out_id = ctx->next_srs++;
   ctx->srs[*out_id] = s;
   return 0;
@@ -227,29 +260,36 @@ int h2agg_srs_release(h2agg_ctx* ctx, uint64_t id) {
   CHECK_ARG(ctx, it != ctx->srs.end(), "srs_release: unknown srs id");
   H2AGG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   if (it->second.owned) cudaFree(const_cast<void*>(it->second.d_bases));
+  if (it->second.d_table) cudaFree(it->second.d_table);
   ctx->srs.erase(it);
   return 0;
 }
 
-// resolve the device pointer of the bases for an MSM of n pairs (uploads host bases to io_b if needed)
+// resolve what an MSM of n pairs runs against (uploads host bases to io_b if needed)
 static int resolve_bases(h2agg_ctx* ctx, uint64_t srs_id, const void* host_bases, const void* dev_bases, size_t n,
-                         const void** out) {
+                         MsmBases* out) {
+  *out = MsmBases();
   if (srs_id) {
     auto it = ctx->srs.find(srs_id);
     CHECK_ARG(ctx, it != ctx->srs.end(), "msm: unknown srs id");
     CHECK_ARG(ctx, it->second.n >= n, "msm: more scalars than registered bases");
-    *out = it->second.d_bases;
+    out->d_bases = it->second.d_bases;
+    out->d_table = it->second.d_table;
+    out->table_c = it->second.table_c;
+    out->table_nwin = it->second.table_nwin;
+    out->srs_n = it->second.n;
     return 0;
   }
+  out->srs_n = n;
   if (dev_bases) {
-    *out = dev_bases;
+    out->d_bases = dev_bases;
     return 0;
   }
   CHECK_ARG(ctx, host_bases || n == 0, "msm: no bases given (srs_id == 0 and bases == NULL)");
   int rc = ensure(ctx, ctx->io_b, n * 64 + 64);
   if (rc) return rc;
   if (n) H2AGG_CUDA(ctx, cudaMemcpyAsync(ctx->io_b.p, host_bases, n * 64, cudaMemcpyHostToDevice, ctx->stream));
-  *out = ctx->io_b.p;
+  out->d_bases = ctx->io_b.p;
   return 0;
 }
 
@@ -261,7 +301,7 @@ int h2agg_msm_g1_windows(h2agg_ctx* ctx, uint64_t srs_id, const uint64_t* bases,
   CHECK_ARG(ctx, out_jacobian, "msm: out is NULL");
   CHECK_ARG(ctx, scalars || n == 0, "msm: scalars is NULL");
   H2AGG_CUDA(ctx, cudaSetDevice(ctx->device));
-  const void* d_bases;
+  MsmBases d_bases;
   int rc = resolve_bases(ctx, srs_id, bases, nullptr, n, &d_bases);
   if (rc) return rc;
   rc = ensure(ctx, ctx->io_a, n * 32 + 64);
@@ -287,7 +327,7 @@ int h2agg_msm_g1_windows_dev(h2agg_ctx* ctx, uint64_t srs_id, const void* d_base
   CHECK_ARG(ctx, d_out160 && (d_scalars || n == 0), "msm_dev: null argument");
   CHECK_ARG(ctx, srs_id || d_bases_in || n == 0, "msm_dev: no bases");
   H2AGG_CUDA(ctx, cudaSetDevice(ctx->device));
-  const void* d_bases;
+  MsmBases d_bases;
   int rc = resolve_bases(ctx, srs_id, nullptr, d_bases_in, n, &d_bases);
   if (rc) return rc;
   return msm_run(ctx, ctx->stream, ctx->msm_ws, d_bases, d_scalars, n, d_out160, win_begin, win_end);
@@ -306,7 +346,7 @@ int h2agg_msm_g1_batch(h2agg_ctx* ctx, uint64_t srs_id, const uint64_t* const* c
   CHECK_ARG(ctx, cols && out_affine, "msm_batch: null argument");
   CHECK_ARG(ctx, n_cols * 160 <= ctx->small.cap && n_cols * 160 <= ctx->pinned_cap, "msm_batch: too many columns");
   H2AGG_CUDA(ctx, cudaSetDevice(ctx->device));
-  const void* d_bases;
+  MsmBases d_bases;
   int rc = resolve_bases(ctx, srs_id, nullptr, nullptr, n, &d_bases);
   if (rc) return rc;
   // lanes: column i+1 crosses PCIe while column i is in the bucket kernels
@@ -325,7 +365,7 @@ int h2agg_msm_g1_batch_dev(h2agg_ctx* ctx, uint64_t srs_id, const void* d_bases_
   LOCK(ctx);
   CHECK_ARG(ctx, d_cols && d_out160s, "msm_batch_dev: null argument");
   H2AGG_CUDA(ctx, cudaSetDevice(ctx->device));
-  const void* d_bases;
+  MsmBases d_bases;
   int rc = resolve_bases(ctx, srs_id, nullptr, d_bases_in, n, &d_bases);
   if (rc) return rc;
   return msm_run_batch(ctx, d_bases, d_cols, n_cols, n, (uint8_t*)d_out160s, false);

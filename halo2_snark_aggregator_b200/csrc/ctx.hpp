@@ -28,6 +28,16 @@ struct Srs {
   const void* d_bases = nullptr;  // n x 64 B affine, Montgomery
   size_t n = 0;
   bool owned = false;
+  void* d_table = nullptr;        // table mode: table_nwin rows of n affine points, row w = 2^(c w) * bases
+  int table_c = 0, table_nwin = 0;
+};
+
+// what an MSM call runs against
+struct MsmBases {
+  const void* d_bases = nullptr;
+  const void* d_table = nullptr;
+  int table_c = 0, table_nwin = 0;
+  size_t srs_n = 0;
 };
 
 // A lane = one auxiliary stream with its own MSM workspace and staging buffer.  Batches alternate
@@ -65,8 +75,9 @@ struct h2agg_ctx {
   int sm_count = 148;
   // counters (claimed in bench.py as gpu_launches)
   uint64_t launches = 0;
-  // MSM tuning (0 = auto)
+  // MSM tuning (0 = auto; a forced width also forces plain mode)
   int msm_window_bits = 0;
+  bool srs_precompute = true;  // build the 2^(c w) P table when an SRS is registered
   // per-kernel-class device timing (CUDA events on ctx->stream), enabled by h2agg_kernel_timing
   bool timing = false;
   struct Timed { cudaEvent_t a, b; int cls; };
@@ -145,11 +156,13 @@ int ntt_run(h2agg_ctx* ctx, const void* d_src, void* d_dst, const NttOpts& o);
 // MSM over G1: d_scalars n x 32 B (Montgomery Fr), d_bases n x 64 B affine.
 // Writes affine (64 B) + jacobian (96 B, z = 1 or 0) to d_out (160 B, device).
 // Windows [win_begin, win_end) only (pass 0, -1 for all): partial = sum_w 2^(c w) B_w.
-int msm_run(h2agg_ctx* ctx, cudaStream_t st, DevBuf& ws, const void* d_bases, const void* d_scalars, size_t n,
+int msm_run(h2agg_ctx* ctx, cudaStream_t st, DevBuf& ws, const MsmBases& bases, const void* d_scalars, size_t n,
             void* d_out160, int win_begin, int win_end);
+int msm_build_srs_table(h2agg_ctx* ctx, Srs& s);
+int msm_table_config(size_t srs_n, int* c, int* nwin);
 // n_cols MSMs against the same bases, alternating lanes; joins back into ctx->stream.
 // Columns are device pointers, or host pointers when `host_cols` (then staged through the lanes).
-int msm_run_batch(h2agg_ctx* ctx, const void* d_bases, const void* const* cols, size_t n_cols, size_t n,
+int msm_run_batch(h2agg_ctx* ctx, const MsmBases& bases, const void* const* cols, size_t n_cols, size_t n,
                   uint8_t* d_out160s, bool host_cols);
 int lanes_init(h2agg_ctx* ctx);
 // sum of m affine-or-jacobian(96 B) points -> d_out160

@@ -6,35 +6,48 @@
 // `keygen_vk` at :760-761.  The result Sum_i s_i * P_i is a unique group element, so any
 // correct schedule is bit-exact after normalisation to affine.
 //
-// Pipeline (all on one stream, no host synchronisation inside):
-//   K4 msm_count    Montgomery -> canonical scalar, signed c-bit digits, bucket histogram
-//      scan         bucket offsets + per-bucket task counts (buckets longer than T points are
-//                   split into T-point tasks so one hot bucket -- witness columns are full of
-//                   0/1/17-bit values -- cannot serialise the kernel)
-//   K4 msm_scatter  counting sort of (point index | sign) by bucket
-//   K1 msm_accumulate  one thread per task: gather 64-byte affine bases as 4 x uint4,
-//                   XYZZ mixed additions (8M + 2S), exact handling of P+P / P-P / identity
-//      msm_fold / msm_fold_hot   combine the tasks of split buckets (CTA tree for hot ones)
-//      msm_wsum     sum_d d * B_d per window by a 4-ary (S, C) reduction tree
-//      msm_final    Horner over windows, one inversion, affine + Jacobian(z=1) out
+// Two modes share every kernel:
+//   plain  bases given per call: W = ceil(255/c) windows x 2^(c-1) signed-digit buckets each,
+//          Horner over windows at the end.
+//   table  bases registered as an SRS (ParamsKZG::g / g_lagrange are immutable, so the 180 GB of
+//          HBM buy arithmetic): 2^(c w) P_i is precomputed for every window w, all W digits of a
+//          scalar fall into ONE set of 2^(c-1) buckets, c grows to 20 (13 windows instead of 16),
+//          the per-window reductions and the 240-doubling Horner chain disappear.
+//
+// Pipeline (one stream, no host synchronisation inside):
+//   K4 msm_digits<count>   Montgomery -> canonical scalar, signed c-bit digits, bucket histogram
+//      msm_scan1/2/3       exclusive scan -> bucket offsets
+//   K4 msm_digits<scatter> counting sort of (base index | sign) by bucket
+//   K1 msm_accumulate      the sorted list is cut into chunks of exactly T entries, one thread per
+//                          chunk, whatever bucket boundaries fall inside: every lane of a warp does
+//                          the same number of XYZZ mixed additions (8M+2S) and a hot bucket
+//                          (witness columns are full of 0/1/17-bit values) is split across threads
+//                          by construction.  Bases are gathered as 4 x 16-byte read-only loads.
+//      msm_fold / msm_fold_hot  stitch the pieces of buckets that straddle chunks (CTA tree for hot ones)
+//      msm_wsum            sum_d d * B_d by a 4-ary (S, C) reduction tree
+//      msm_final           Horner over windows (plain mode), one inversion, affine + Jacobian(z=1) out
 #include "bn254_g1.cuh"
 #include "ctx.hpp"
+#include <algorithm>
 #include <cstring>
 
 namespace h2agg {
 
 static constexpr int MSM_THREADS = 128;
-static constexpr uint32_t HOT_TASKS = 8;   // buckets with more tasks than this get a whole CTA
+static constexpr uint32_t HOT_PIECES = 8;  // buckets cut into more pieces than this get a whole CTA
 static constexpr uint32_t WSUM_L = 4;      // arity of the window-sum tree
 
 struct MsmGeom {
-  uint32_t n;
-  uint32_t c;         // window bits
-  uint32_t nwin;      // ceil(255 / c)
-  uint32_t bpw;       // buckets per window = 2^(c-1)
-  uint32_t nb;        // nwin * bpw
-  uint32_t task_len;  // T
+  uint32_t n;          // scalars in this MSM
+  uint32_t c;          // window bits
+  uint32_t nwin;       // ceil(255 / c) digit positions
+  uint32_t bpw;        // buckets per window = 2^(c-1)
+  uint32_t nsets;      // bucket sets: nwin (plain) or 1 (table)
+  uint32_t nb;         // nsets * bpw
+  uint32_t chunk;      // T
   uint32_t win_begin, win_end;
+  uint32_t table;      // 1: entries index the precomputed table [w][srs_n]
+  uint32_t srs_n;      // row length of the table
 };
 
 int msm_window_config(size_t n, int forced_c, int* c_out, int* nwin_out) {
@@ -55,7 +68,18 @@ int msm_window_config(size_t n, int forced_c, int* c_out, int* nwin_out) {
   return 0;
 }
 
-// signed digit of window w (canonical scalar in v[8]); returns carry for the next window
+int msm_table_config(size_t srs_n, int* c_out, int* nwin_out) {
+  int lg = 0;
+  while (((size_t)1 << (lg + 1)) <= srs_n) lg++;
+  int c = lg - 2;
+  if (c > 20) c = 20;
+  if (c < 4) c = 4;
+  *c_out = c;
+  *nwin_out = (255 + c - 1) / c;
+  return 0;
+}
+
+// signed digit of window w (canonical scalar in v[8]); carry feeds the next window
 __device__ __forceinline__ int32_t take_digit(const uint32_t* v, uint32_t w, uint32_t c, uint32_t& carry) {
   uint32_t bit = w * c;
   uint32_t limb = bit >> 5, sh = bit & 31;
@@ -87,10 +111,11 @@ __global__ void __launch_bounds__(256) msm_digits(const uint4* __restrict__ scal
       int32_t d = take_digit(v, w, g.c, carry);
       if (d == 0 || w < g.win_begin || w >= g.win_end) continue;
       uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
-      uint32_t key = w * g.bpw + (mag - 1);
+      uint32_t key = (g.table ? 0u : w * g.bpw) + (mag - 1);
       if (SCATTER) {
         uint32_t pos = atomicAdd(counts_or_cursor + key, 1u);
-        entries[pos] = i | (d < 0 ? 0x80000000u : 0u);
+        uint32_t idx = g.table ? (w * g.srs_n + i) : i;
+        entries[pos] = idx | (d < 0 ? 0x80000000u : 0u);
       } else {
         atomicAdd(counts_or_cursor + key, 1u);
       }
@@ -98,152 +123,162 @@ __global__ void __launch_bounds__(256) msm_digits(const uint4* __restrict__ scal
   }
 }
 
-// ---- exclusive scan of (count, ceil(count/T)) pairs over nb buckets, 2048 per block -------------
+// ---- exclusive scan of the bucket histogram, 2048 per block -------------------------------------------
 static constexpr uint32_t SCAN_ITEMS = 8, SCAN_THREADS = 256, SCAN_BLOCK = SCAN_ITEMS * SCAN_THREADS;
 
-__device__ __forceinline__ uint2 add2(uint2 a, uint2 b) { return make_uint2(a.x + b.x, a.y + b.y); }
-
-__device__ uint2 block_exclusive_scan(uint2 v, uint2* total, uint2* sh /*[SCAN_THREADS/32]*/) {
+__device__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total, uint32_t* sh /*[SCAN_THREADS/32]*/) {
   uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  uint2 inc = v;
+  uint32_t inc = v;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    uint32_t x = __shfl_up_sync(0xffffffffu, inc.x, o), y = __shfl_up_sync(0xffffffffu, inc.y, o);
-    if (lane >= (uint32_t)o) { inc.x += x; inc.y += y; }
+    uint32_t x = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= (uint32_t)o) inc += x;
   }
   if (lane == 31) sh[wid] = inc;
   __syncthreads();
-  uint2 woff = make_uint2(0, 0), tot = make_uint2(0, 0);
+  uint32_t woff = 0, tot = 0;
   for (uint32_t k = 0; k < SCAN_THREADS / 32; k++) {
-    if (k < wid) woff = add2(woff, sh[k]);
-    tot = add2(tot, sh[k]);
+    if (k < wid) woff += sh[k];
+    tot += sh[k];
   }
   __syncthreads();
   *total = tot;
-  return make_uint2(woff.x + inc.x - v.x, woff.y + inc.y - v.y);
+  return woff + inc - v;
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS) msm_scan1(const uint32_t* __restrict__ counts, uint32_t nb,
-                                                           uint32_t task_len, uint2* block_sums) {
-  __shared__ uint2 sh[SCAN_THREADS / 32];
+                                                           uint32_t* block_sums) {
+  __shared__ uint32_t sh[SCAN_THREADS / 32];
   uint32_t base = blockIdx.x * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS;
-  uint2 acc = make_uint2(0, 0);
+  uint32_t acc = 0;
 #pragma unroll
-  for (uint32_t k = 0; k < SCAN_ITEMS; k++) {
-    uint32_t cnt = (base + k < nb) ? counts[base + k] : 0;
-    acc.x += cnt;
-    acc.y += (cnt + task_len - 1) / task_len;
-  }
-  uint2 tot;
+  for (uint32_t k = 0; k < SCAN_ITEMS; k++) acc += (base + k < nb) ? counts[base + k] : 0;
+  uint32_t tot;
   block_exclusive_scan(acc, &tot, sh);
   if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) msm_scan2(uint2* block_sums, uint32_t nblocks) {
-  __shared__ uint2 sh[SCAN_THREADS / 32];
+__global__ void __launch_bounds__(SCAN_THREADS) msm_scan2(uint32_t* block_sums, uint32_t nblocks) {
+  __shared__ uint32_t sh[SCAN_THREADS / 32];
   uint32_t base = threadIdx.x * SCAN_ITEMS;
-  uint2 loc[SCAN_ITEMS];
-  uint2 acc = make_uint2(0, 0);
+  uint32_t loc[SCAN_ITEMS];
+  uint32_t acc = 0;
 #pragma unroll
   for (uint32_t k = 0; k < SCAN_ITEMS; k++) {
-    loc[k] = (base + k < nblocks) ? block_sums[base + k] : make_uint2(0, 0);
-    acc = add2(acc, loc[k]);
+    loc[k] = (base + k < nblocks) ? block_sums[base + k] : 0;
+    acc += loc[k];
   }
-  uint2 tot;
-  uint2 off = block_exclusive_scan(acc, &tot, sh);
+  uint32_t tot;
+  uint32_t off = block_exclusive_scan(acc, &tot, sh);
 #pragma unroll
   for (uint32_t k = 0; k < SCAN_ITEMS; k++) {
     if (base + k < nblocks) block_sums[base + k] = off;
-    off = add2(off, loc[k]);
+    off += loc[k];
   }
 }
 
-// offsets[nb+1], cursor[nb] (= offsets, consumed by the scatter), task_off[nb+1]
+// offsets[nb+1] and cursor[nb] (= offsets, consumed by the scatter)
 __global__ void __launch_bounds__(SCAN_THREADS) msm_scan3(const uint32_t* __restrict__ counts, uint32_t nb,
-                                                           uint32_t task_len, const uint2* __restrict__ block_sums,
-                                                           uint32_t* offsets, uint32_t* cursor, uint32_t* task_off) {
-  __shared__ uint2 sh[SCAN_THREADS / 32];
+                                                           const uint32_t* __restrict__ block_sums, uint32_t* offsets,
+                                                           uint32_t* cursor) {
+  __shared__ uint32_t sh[SCAN_THREADS / 32];
   uint32_t base = blockIdx.x * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS;
   uint32_t cnt[SCAN_ITEMS];
-  uint2 acc = make_uint2(0, 0);
+  uint32_t acc = 0;
 #pragma unroll
   for (uint32_t k = 0; k < SCAN_ITEMS; k++) {
     cnt[k] = (base + k < nb) ? counts[base + k] : 0;
-    acc.x += cnt[k];
-    acc.y += (cnt[k] + task_len - 1) / task_len;
+    acc += cnt[k];
   }
-  uint2 tot;
-  uint2 off = add2(block_exclusive_scan(acc, &tot, sh), block_sums[blockIdx.x]);
+  uint32_t tot;
+  uint32_t off = block_exclusive_scan(acc, &tot, sh) + block_sums[blockIdx.x];
 #pragma unroll
   for (uint32_t k = 0; k < SCAN_ITEMS; k++) {
     if (base + k <= nb) {  // also writes the closing element [nb]
-      offsets[base + k] = off.x;
-      task_off[base + k] = off.y;
-      if (base + k < nb) cursor[base + k] = off.x;
+      offsets[base + k] = off;
+      if (base + k < nb) cursor[base + k] = off;
     }
-    off.x += cnt[k];
-    off.y += (cnt[k] + task_len - 1) / task_len;
+    off += cnt[k];
   }
 }
 
-// ---- K1: bucket accumulation --------------------------------------------------------------------
+// ---- K1: bucket accumulation over fixed-size chunks of the sorted entry list ---------------------------
+// Piece bookkeeping for a bucket [beg, end) cut by chunk boundaries (chunk t = [tT, (t+1)T)):
+//   entirely inside one chunk           -> written straight to bucket_sums[b]
+//   first piece (bucket starts in t)    -> tail_part[t]
+//   every later piece (chunks t+1..)    -> head_part[t']
 __global__ void __launch_bounds__(MSM_THREADS) msm_accumulate(const uint8_t* __restrict__ bases,
                                                                const uint32_t* __restrict__ entries,
-                                                               const uint32_t* __restrict__ offsets,
-                                                               const uint32_t* __restrict__ task_off, MsmGeom g,
-                                                               uint8_t* __restrict__ partials,
+                                                               const uint32_t* __restrict__ offsets, MsmGeom g,
+                                                               uint8_t* __restrict__ head_part,
+                                                               uint8_t* __restrict__ tail_part,
                                                                uint8_t* __restrict__ bucket_sums) {
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t ntasks = task_off[g.nb];
-  if (t >= ntasks) return;
-  // largest b with task_off[b] <= t  (buckets without tasks have task_off[b] == task_off[b+1])
-  uint32_t lo = 0, hi = g.nb;  // invariant: task_off[lo] <= t < task_off[hi]
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t total = __ldg(offsets + g.nb);
+  const unsigned long long start64 = (unsigned long long)t * g.chunk;
+  if (start64 >= total) return;
+  const uint32_t start = (uint32_t)start64;
+  const uint32_t end = (uint32_t)min((unsigned long long)total, start64 + g.chunk);
+  // largest b with offsets[b] <= start: the (non-empty) bucket that owns slot `start`
+  uint32_t lo = 0, hi = g.nb;  // offsets[lo] <= start < offsets[hi]
   while (hi - lo > 1) {
     uint32_t mid = (lo + hi) >> 1;
-    if (__ldg(task_off + mid) <= t) lo = mid; else hi = mid;
+    if (__ldg(offsets + mid) <= start) lo = mid; else hi = mid;
   }
   uint32_t b = lo;
-  uint32_t t0 = __ldg(task_off + b), t1 = __ldg(task_off + b + 1);
-  uint32_t beg = __ldg(offsets + b), end = __ldg(offsets + b + 1);
-  uint32_t start = beg + (t - t0) * g.task_len;
-  uint32_t stop = min(start + g.task_len, end);
-
+  uint32_t bbeg = __ldg(offsets + b), bend = __ldg(offsets + b + 1);
   G1Xyzz acc = G1Xyzz::identity();
-  for (uint32_t k = start; k < stop; k++) {
+  // ONE flat loop over the chunk: the bucket switch is a short predicated side branch, so the
+  // lanes of a warp stay converged on the expensive mixed addition (a nested per-bucket loop
+  // would make every lane wait for the longest segment of its neighbours).
+  for (uint32_t k = start; k < end; k++) {
+    if (k == bend) {
+      // bucket b is finished inside this chunk (it cannot continue past `end` here)
+      if (bbeg < start) acc.store(head_part + (size_t)t * 128);
+      else acc.store(bucket_sums + (size_t)b * 128);
+      acc = G1Xyzz::identity();
+      b++;
+      while (__ldg(offsets + b + 1) <= k) b++;  // skip empty buckets; k < total so this terminates
+      bbeg = __ldg(offsets + b);
+      bend = __ldg(offsets + b + 1);
+    }
     uint32_t e = __ldg(entries + k);
     G1Affine q = G1Affine::load_nc(bases + (size_t)(e & 0x7fffffffu) * 64);
     if (e >> 31) q.y = fp_neg(q.y);
     xyzz_madd(acc, q);
   }
-  if (t1 - t0 == 1) acc.store(bucket_sums + (size_t)b * 128);
-  else acc.store(partials + (size_t)t * 128);
+  if (bbeg < start) acc.store(head_part + (size_t)t * 128);
+  else if (bend > end) acc.store(tail_part + (size_t)t * 128);
+  else acc.store(bucket_sums + (size_t)b * 128);
 }
 
-// buckets with 0 or 2..HOT tasks; hot ones are queued
-__global__ void __launch_bounds__(MSM_THREADS) msm_fold(const uint32_t* __restrict__ task_off, MsmGeom g,
-                                                         const uint8_t* __restrict__ partials,
+// stitch buckets that straddle chunk boundaries; empty buckets -> identity; hot ones are queued
+__global__ void __launch_bounds__(MSM_THREADS) msm_fold(const uint32_t* __restrict__ offsets, MsmGeom g,
+                                                         const uint8_t* __restrict__ head_part,
+                                                         const uint8_t* __restrict__ tail_part,
                                                          uint8_t* __restrict__ bucket_sums, uint32_t* hot_count,
                                                          uint32_t* hot_list) {
   uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= g.nb) return;
-  uint32_t t0 = task_off[b], t1 = task_off[b + 1];
-  uint32_t nt = t1 - t0;
-  if (nt == 1) return;
-  if (nt == 0) {
+  uint32_t beg = offsets[b], end = offsets[b + 1];
+  if (beg == end) {
     G1Xyzz::identity().store(bucket_sums + (size_t)b * 128);
     return;
   }
-  if (nt > HOT_TASKS) {
+  uint32_t t0 = beg / g.chunk, t1 = (end - 1) / g.chunk;
+  if (t0 == t1) return;  // complete, already written by its chunk
+  if (t1 - t0 + 1 > HOT_PIECES) {
     hot_list[atomicAdd(hot_count, 1u)] = b;
     return;
   }
-  G1Xyzz acc = G1Xyzz::load(partials + (size_t)t0 * 128);
-  for (uint32_t t = t0 + 1; t < t1; t++) xyzz_add(acc, G1Xyzz::load(partials + (size_t)t * 128));
+  G1Xyzz acc = G1Xyzz::load(tail_part + (size_t)t0 * 128);
+  for (uint32_t t = t0 + 1; t <= t1; t++) xyzz_add(acc, G1Xyzz::load(head_part + (size_t)t * 128));
   acc.store(bucket_sums + (size_t)b * 128);
 }
 
-__global__ void __launch_bounds__(256) msm_fold_hot(const uint32_t* __restrict__ task_off,
-                                                     const uint8_t* __restrict__ partials,
+__global__ void __launch_bounds__(256) msm_fold_hot(const uint32_t* __restrict__ offsets, MsmGeom g,
+                                                     const uint8_t* __restrict__ head_part,
+                                                     const uint8_t* __restrict__ tail_part,
                                                      uint8_t* __restrict__ bucket_sums,
                                                      const uint32_t* __restrict__ hot_count,
                                                      const uint32_t* __restrict__ hot_list) {
@@ -251,9 +286,11 @@ __global__ void __launch_bounds__(256) msm_fold_hot(const uint32_t* __restrict__
   uint32_t nhot = *hot_count;
   for (uint32_t h = blockIdx.x; h < nhot; h += gridDim.x) {
     uint32_t b = hot_list[h];
-    uint32_t t0 = task_off[b], t1 = task_off[b + 1];
+    uint32_t beg = offsets[b], end = offsets[b + 1];
+    uint32_t t0 = beg / g.chunk, t1 = (end - 1) / g.chunk;
     G1Xyzz acc = G1Xyzz::identity();
-    for (uint32_t t = t0 + threadIdx.x; t < t1; t += blockDim.x) xyzz_add(acc, G1Xyzz::load(partials + (size_t)t * 128));
+    if (threadIdx.x == 0) acc = G1Xyzz::load(tail_part + (size_t)t0 * 128);
+    for (uint32_t t = t0 + 1 + threadIdx.x; t <= t1; t += blockDim.x) xyzz_add(acc, G1Xyzz::load(head_part + (size_t)t * 128));
     acc.store(sh + threadIdx.x * 8);
     __syncthreads();
     for (uint32_t o = 128; o > 0; o >>= 1) {
@@ -270,14 +307,14 @@ __global__ void __launch_bounds__(256) msm_fold_hot(const uint32_t* __restrict__
 }
 
 // ---- window sums: sum_idx (idx * S_idx + C_idx) by an L-ary tree -------------------------------------
-// level input: per window m items (S, C); output ceil(m/L) items.  At level 0, C aliases S
+// level input: per bucket set m items (S, C); output ceil(m/L) items.  At level 0, C aliases S
 // (bucket idx holds digit idx+1).
 __global__ void __launch_bounds__(MSM_THREADS) msm_wsum(const uint8_t* __restrict__ s_in, const uint8_t* __restrict__ c_in,
-                                                         uint32_t nwin, uint32_t m, uint8_t* __restrict__ s_out,
+                                                         uint32_t nsets, uint32_t m, uint8_t* __restrict__ s_out,
                                                          uint8_t* __restrict__ c_out) {
   uint32_t mo = (m + WSUM_L - 1) / WSUM_L;
   uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= nwin * mo) return;
+  if (gid >= nsets * mo) return;
   uint32_t w = gid / mo, t = gid % mo;
   uint32_t first = t * WSUM_L;
   uint32_t cnt = min(WSUM_L, m - first);
@@ -295,24 +332,32 @@ __global__ void __launch_bounds__(MSM_THREADS) msm_wsum(const uint8_t* __restric
   acc.store(c_out + ob);
 }
 
-// Horner over windows [wb, we), times 2^(c*wb); affine + jacobian out
-__global__ void msm_final(const uint8_t* __restrict__ wsum_c, MsmGeom g, uint8_t* out160) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  G1Xyzz acc = G1Xyzz::identity();
-  for (int w = (int)g.win_end - 1; w >= (int)g.win_begin; w--) {
-    if (!acc.is_identity())
-      for (uint32_t k = 0; k < g.c; k++) acc = xyzz_dbl(acc);
-    xyzz_add(acc, G1Xyzz::load(wsum_c + (size_t)w * 128));
-  }
-  if (!acc.is_identity())
-    for (uint32_t k = 0; k < g.c * g.win_begin; k++) acc = xyzz_dbl(acc);
+__device__ __forceinline__ void write_out160(const G1Xyzz& acc, uint8_t* out160) {
   G1Affine a = xyzz_to_affine(acc);
+  bool id = acc.is_identity();
   a.x.store(out160);
   a.y.store(out160 + 32);
-  bool id = acc.is_identity();
   a.x.store(out160 + 64);
   (id ? Fq::one() : a.y).store(out160 + 96);
   (id ? Fq::zero() : Fq::one()).store(out160 + 128);
+}
+
+// plain mode: Horner over windows [wb, we), times 2^(c*wb); table mode: the single set is the answer
+__global__ void msm_final(const uint8_t* __restrict__ wsum_c, MsmGeom g, uint8_t* out160) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  G1Xyzz acc = G1Xyzz::identity();
+  if (g.table) {
+    acc = G1Xyzz::load(wsum_c);
+  } else {
+    for (int w = (int)g.win_end - 1; w >= (int)g.win_begin; w--) {
+      if (!acc.is_identity())
+        for (uint32_t k = 0; k < g.c; k++) acc = xyzz_dbl(acc);
+      xyzz_add(acc, G1Xyzz::load(wsum_c + (size_t)w * 128));
+    }
+    if (!acc.is_identity())
+      for (uint32_t k = 0; k < g.c * g.win_begin; k++) acc = xyzz_dbl(acc);
+  }
+  write_out160(acc, out160);
 }
 
 __global__ void g1_sum_kernel(const uint8_t* __restrict__ pts96, uint32_t m, uint8_t* out160) {
@@ -326,13 +371,7 @@ __global__ void g1_sum_kernel(const uint8_t* __restrict__ pts96, uint32_t m, uin
     p.x = x; p.y = y; p.zz = fp_sqr(z); p.zzz = p.zz * z;
     xyzz_add(acc, p);
   }
-  G1Affine a = xyzz_to_affine(acc);
-  bool id = acc.is_identity();
-  a.x.store(out160);
-  a.y.store(out160 + 32);
-  a.x.store(out160 + 64);
-  (id ? Fq::one() : a.y).store(out160 + 96);
-  (id ? Fq::zero() : Fq::one()).store(out160 + 128);
+  write_out160(acc, out160);
 }
 
 int g1_sum_jacobian(h2agg_ctx* ctx, const void* d_points96, size_t m, void* d_out160) {
@@ -342,7 +381,78 @@ int g1_sum_jacobian(h2agg_ctx* ctx, const void* d_points96, size_t m, void* d_ou
   return 0;
 }
 
-static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+// ---- SRS table: rows w = 0..W-1 of 2^(c w) P_i in affine form ---------------------------------------------
+// One thread per point: Jacobian doubling chain, Z's batch-inverted per thread (Montgomery's trick).
+static constexpr int MAX_TABLE_ROWS = 64;
+
+__global__ void __launch_bounds__(128) msm_build_table(const uint8_t* __restrict__ bases, uint32_t n, uint32_t c,
+                                                        uint32_t nwin, uint8_t* __restrict__ table) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  G1Affine p = G1Affine::load_nc(bases + (size_t)i * 64);
+  const size_t row = (size_t)n * 64;
+  p.x.store(table + (size_t)i * 64);
+  p.y.store(table + (size_t)i * 64 + 32);
+  if (p.is_identity()) {
+    for (uint32_t w = 1; w < nwin; w++) {
+      p.x.store(table + w * row + (size_t)i * 64);
+      p.y.store(table + w * row + (size_t)i * 64 + 32);
+    }
+    return;
+  }
+  // Jacobian chain; X, Y parked in the table slot, Z prefix products in local memory
+  Fq X = p.x, Y = p.y, Z = Fq::one();
+  Fq prefix[MAX_TABLE_ROWS];
+  Fq zs[MAX_TABLE_ROWS];
+  Fq run = Fq::one();
+  for (uint32_t w = 1; w < nwin; w++) {
+    for (uint32_t k = 0; k < c; k++) {  // dbl-2009-l (a = 0); BN254 G1 has no 2-torsion so Y != 0
+      Fq A = fp_sqr(X), B = fp_sqr(Y), C = fp_sqr(B);
+      Fq t = X + B;
+      Fq D = fp_dbl(fp_sqr(t) - A - C);
+      Fq E = fp_dbl(A) + A, F = fp_sqr(E);
+      Fq Z3 = fp_dbl(Y * Z);
+      X = F - fp_dbl(D);
+      Y = E * (D - X) - fp_dbl(fp_dbl(fp_dbl(C)));
+      Z = Z3;
+    }
+    X.store(table + w * row + (size_t)i * 64);
+    Y.store(table + w * row + (size_t)i * 64 + 32);
+    zs[w] = Z;
+    prefix[w] = run;  // product of Z_1 .. Z_{w-1}
+    run = run * Z;
+  }
+  Fq inv = fp_inv(run);
+  for (uint32_t w = nwin - 1; w >= 1; w--) {
+    Fq zi = inv * prefix[w];  // 1 / Z_w
+    inv = inv * zs[w];
+    Fq zi2 = fp_sqr(zi);
+    Fq x = Fq::load(table + w * row + (size_t)i * 64) * zi2;
+    Fq y = Fq::load(table + w * row + (size_t)i * 64 + 32) * zi2 * zi;
+    x.store(table + w * row + (size_t)i * 64);
+    y.store(table + w * row + (size_t)i * 64 + 32);
+  }
+}
+
+int msm_build_srs_table(h2agg_ctx* ctx, Srs& s) {
+  int c, nwin;
+  msm_table_config(s.n, &c, &nwin);
+  if (nwin > MAX_TABLE_ROWS || (size_t)nwin * s.n >= (1ull << 31)) return 0;  // stay in plain mode
+  void* t = nullptr;
+  if (cudaMalloc(&t, (size_t)nwin * s.n * 64) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;  // not enough memory for the table: plain mode still works
+  }
+  msm_build_table<<<(unsigned)((s.n + 127) / 128), 128, 0, ctx->stream>>>((const uint8_t*)s.d_bases, (uint32_t)s.n,
+                                                                          (uint32_t)c, (uint32_t)nwin, (uint8_t*)t);
+  ctx->launches++;
+  H2AGG_CUDA(ctx, cudaGetLastError());
+  H2AGG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  s.d_table = t;
+  s.table_c = c;
+  s.table_nwin = nwin;
+  return 0;
+}
 
 int lanes_init(h2agg_ctx* ctx) {
   if (ctx->fork_ev) return 0;
@@ -354,11 +464,11 @@ int lanes_init(h2agg_ctx* ctx) {
   return 0;
 }
 
-int msm_run_batch(h2agg_ctx* ctx, const void* d_bases, const void* const* cols, size_t n_cols, size_t n,
+int msm_run_batch(h2agg_ctx* ctx, const MsmBases& bases, const void* const* cols, size_t n_cols, size_t n,
                   uint8_t* d_out160s, bool host_cols) {
   if (n_cols == 0) return 0;
   int rc;
-  if (n_cols == 1 && !host_cols) return msm_run(ctx, ctx->stream, ctx->msm_ws, d_bases, cols[0], n, d_out160s, 0, -1);
+  if (n_cols == 1 && !host_cols) return msm_run(ctx, ctx->stream, ctx->msm_ws, bases, cols[0], n, d_out160s, 0, -1);
   if ((rc = lanes_init(ctx))) return rc;
   H2AGG_CUDA(ctx, cudaEventRecord(ctx->fork_ev, ctx->stream));
   for (int l = 0; l < N_LANES; l++) H2AGG_CUDA(ctx, cudaStreamWaitEvent(ctx->lanes[l].st, ctx->fork_ev, 0));
@@ -370,7 +480,7 @@ int msm_run_batch(h2agg_ctx* ctx, const void* d_bases, const void* const* cols, 
       if (n) H2AGG_CUDA(ctx, cudaMemcpyAsync(ln.io.p, cols[i], n * 32, cudaMemcpyHostToDevice, ln.st));
       d_col = ln.io.p;
     }
-    if ((rc = msm_run(ctx, ln.st, ln.ws, d_bases, d_col, n, d_out160s + i * 160, 0, -1))) return rc;
+    if ((rc = msm_run(ctx, ln.st, ln.ws, bases, d_col, n, d_out160s + i * 160, 0, -1))) return rc;
   }
   for (int l = 0; l < N_LANES; l++) {
     H2AGG_CUDA(ctx, cudaEventRecord(ctx->lanes[l].done, ctx->lanes[l].st));
@@ -379,7 +489,9 @@ int msm_run_batch(h2agg_ctx* ctx, const void* d_bases, const void* const* cols, 
   return 0;
 }
 
-int msm_run(h2agg_ctx* ctx, cudaStream_t st, DevBuf& wsbuf, const void* d_bases, const void* d_scalars, size_t n,
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+int msm_run(h2agg_ctx* ctx, cudaStream_t st, DevBuf& wsbuf, const MsmBases& bases, const void* d_scalars, size_t n,
             void* d_out160, int win_begin, int win_end) {
   if (n >= (1ull << 31)) {
     ctx->last_error = "msm: n must be < 2^31";
@@ -387,23 +499,32 @@ int msm_run(h2agg_ctx* ctx, cudaStream_t st, DevBuf& wsbuf, const void* d_bases,
   }
   MsmGeom g;
   int c, nwin;
-  msm_window_config(n ? n : 1, ctx->msm_window_bits, &c, &nwin);
+  const bool table = bases.d_table != nullptr && ctx->msm_window_bits == 0;
+  if (table) {
+    c = bases.table_c;
+    nwin = bases.table_nwin;
+  } else {
+    msm_window_config(n ? n : 1, ctx->msm_window_bits, &c, &nwin);
+  }
   g.n = (uint32_t)n;
   g.c = (uint32_t)c;
   g.nwin = (uint32_t)nwin;
   g.bpw = 1u << (c - 1);
-  g.nb = g.nwin * g.bpw;
+  g.nsets = table ? 1u : g.nwin;
+  g.nb = g.nsets * g.bpw;
+  g.table = table ? 1u : 0u;
+  g.srs_n = (uint32_t)bases.srs_n;
   g.win_begin = win_begin < 0 ? 0 : (uint32_t)win_begin;
   g.win_end = (win_end < 0 || win_end > nwin) ? (uint32_t)nwin : (uint32_t)win_end;
   if (g.win_begin > g.win_end) g.win_begin = g.win_end;
-  {
-    size_t avg = n / g.bpw;
-    uint32_t T = 32;
-    while (T < 2 * avg && T < 512) T <<= 1;
-    g.task_len = T;
-  }
+  g.chunk = 128;
+  const uint8_t* d_points = (const uint8_t*)(table ? bases.d_table : bases.d_bases);
   const size_t max_entries = (size_t)n * (g.win_end - g.win_begin);
-  const size_t max_tasks = max_entries / g.task_len + g.nb + 1;
+  if (max_entries >= (1ull << 32) - 1) {
+    ctx->last_error = "msm: n * windows exceeds the 32-bit entry index";
+    return 1;
+  }
+  const size_t max_chunks = max_entries / g.chunk + 1;
   const uint32_t scan_blocks = (g.nb + 1 + SCAN_BLOCK - 1) / SCAN_BLOCK;
   if (scan_blocks > SCAN_BLOCK) {
     ctx->last_error = "msm: too many buckets for the scan";
@@ -416,13 +537,13 @@ int msm_run(h2agg_ctx* ctx, cudaStream_t st, DevBuf& wsbuf, const void* d_bases,
   size_t o_counts = carve((size_t)(g.nb + 1) * 4);
   size_t o_offsets = carve((size_t)(g.nb + 1) * 4);
   size_t o_cursor = carve((size_t)(g.nb + 1) * 4);
-  size_t o_taskoff = carve((size_t)(g.nb + 1) * 4);
-  size_t o_bsums = carve((size_t)scan_blocks * 8);
+  size_t o_bsums = carve((size_t)scan_blocks * 4);
   size_t o_hot = carve((size_t)(g.nb + 1) * 4 + 256);
   size_t o_entries = carve((max_entries + 1) * 4);
-  size_t o_partials = carve(max_tasks * 128);
+  size_t o_head = carve(max_chunks * 128);
+  size_t o_tail = carve(max_chunks * 128);
   size_t o_buckets = carve((size_t)g.nb * 128);
-  size_t lvl_items = (size_t)g.nwin * ((g.bpw + WSUM_L - 1) / WSUM_L);
+  size_t lvl_items = (size_t)g.nsets * ((g.bpw + WSUM_L - 1) / WSUM_L);
   size_t o_lvl_s0 = carve(lvl_items * 128), o_lvl_c0 = carve(lvl_items * 128);
   size_t o_lvl_s1 = carve(lvl_items * 128), o_lvl_c1 = carve(lvl_items * 128);
   int rc = ensure(ctx, wsbuf, off);
@@ -431,43 +552,42 @@ int msm_run(h2agg_ctx* ctx, cudaStream_t st, DevBuf& wsbuf, const void* d_bases,
   uint32_t* counts = (uint32_t*)(ws + o_counts);
   uint32_t* offsets = (uint32_t*)(ws + o_offsets);
   uint32_t* cursor = (uint32_t*)(ws + o_cursor);
-  uint32_t* task_off = (uint32_t*)(ws + o_taskoff);
-  uint2* bsums = (uint2*)(ws + o_bsums);
+  uint32_t* bsums = (uint32_t*)(ws + o_bsums);
   uint32_t* hot_count = (uint32_t*)(ws + o_hot);
   uint32_t* hot_list = hot_count + 64;
   uint32_t* entries = (uint32_t*)(ws + o_entries);
-  uint8_t* partials = ws + o_partials;
+  uint8_t* head_part = ws + o_head;
+  uint8_t* tail_part = ws + o_tail;
   uint8_t* buckets = ws + o_buckets;
 
   ScopedKernelTimer t_total(ctx, KC_MSM_TOTAL, st);
   H2AGG_CUDA(ctx, cudaMemsetAsync(counts, 0, (size_t)(g.nb + 1) * 4, st));
   H2AGG_CUDA(ctx, cudaMemsetAsync(hot_count, 0, 256, st));
+  const uint32_t dgrid = (uint32_t)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 8);
   if (n) {
-    uint32_t grid = (uint32_t)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 8);
     ScopedKernelTimer tk(ctx, KC_MSM_DIGITS, st);
-    msm_digits<false><<<grid, 256, 0, st>>>((const uint4*)d_scalars, g, counts, nullptr);
+    msm_digits<false><<<dgrid, 256, 0, st>>>((const uint4*)d_scalars, g, counts, nullptr);
     ctx->launches++;
   }
-  msm_scan1<<<scan_blocks, SCAN_THREADS, 0, st>>>(counts, g.nb, g.task_len, bsums);
+  msm_scan1<<<scan_blocks, SCAN_THREADS, 0, st>>>(counts, g.nb, bsums);
   msm_scan2<<<1, SCAN_THREADS, 0, st>>>(bsums, scan_blocks);
-  msm_scan3<<<scan_blocks, SCAN_THREADS, 0, st>>>(counts, g.nb, g.task_len, bsums, offsets, cursor, task_off);
+  msm_scan3<<<scan_blocks, SCAN_THREADS, 0, st>>>(counts, g.nb, bsums, offsets, cursor);
   ctx->launches += 3;
   if (n) {
-    uint32_t grid = (uint32_t)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 8);
     {
       ScopedKernelTimer tk(ctx, KC_MSM_DIGITS, st);
-      msm_digits<true><<<grid, 256, 0, st>>>((const uint4*)d_scalars, g, cursor, entries);
+      msm_digits<true><<<dgrid, 256, 0, st>>>((const uint4*)d_scalars, g, cursor, entries);
       ctx->launches++;
     }
     ScopedKernelTimer tk(ctx, KC_MSM_ACCUMULATE, st);
-    msm_accumulate<<<(uint32_t)((max_tasks + MSM_THREADS - 1) / MSM_THREADS), MSM_THREADS, 0, st>>>(
-        (const uint8_t*)d_bases, entries, offsets, task_off, g, partials, buckets);
+    msm_accumulate<<<(uint32_t)((max_chunks + MSM_THREADS - 1) / MSM_THREADS), MSM_THREADS, 0, st>>>(
+        d_points, entries, offsets, g, head_part, tail_part, buckets);
     ctx->launches++;
   }
   ScopedKernelTimer t_red(ctx, KC_MSM_REDUCE, st);
-  msm_fold<<<(g.nb + MSM_THREADS - 1) / MSM_THREADS, MSM_THREADS, 0, st>>>(task_off, g, partials, buckets, hot_count,
-                                                                            hot_list);
-  msm_fold_hot<<<ctx->sm_count * 2, 256, 0, st>>>(task_off, partials, buckets, hot_count, hot_list);
+  msm_fold<<<(g.nb + MSM_THREADS - 1) / MSM_THREADS, MSM_THREADS, 0, st>>>(offsets, g, head_part, tail_part, buckets,
+                                                                            hot_count, hot_list);
+  msm_fold_hot<<<ctx->sm_count * 2, 256, 0, st>>>(offsets, g, head_part, tail_part, buckets, hot_count, hot_list);
   ctx->launches += 2;
   H2AGG_CUDA(ctx, cudaGetLastError());
 
@@ -477,11 +597,10 @@ int msm_run(h2agg_ctx* ctx, cudaStream_t st, DevBuf& wsbuf, const void* d_bases,
   uint8_t* lvl_c[2] = {ws + o_lvl_c0, ws + o_lvl_c1};
   uint32_t m = g.bpw;
   int flip = 0;
-  // at least one level so that the final C holds sum (idx+1) * B_idx
-  do {
+  do {  // at least one level so that the final C holds sum (idx+1) * B_idx
     uint32_t mo = (m + WSUM_L - 1) / WSUM_L;
-    uint32_t total = g.nwin * mo;
-    msm_wsum<<<(total + MSM_THREADS - 1) / MSM_THREADS, MSM_THREADS, 0, st>>>(s_in, c_in, g.nwin, m, lvl_s[flip],
+    uint32_t total = g.nsets * mo;
+    msm_wsum<<<(total + MSM_THREADS - 1) / MSM_THREADS, MSM_THREADS, 0, st>>>(s_in, c_in, g.nsets, m, lvl_s[flip],
                                                                               lvl_c[flip]);
     ctx->launches++;
     s_in = lvl_s[flip];

@@ -59,7 +59,12 @@ int h2agg_host_register(h2agg_ctx* ctx, const void* p, size_t bytes);
 int h2agg_host_unregister(h2agg_ctx* ctx, const void* p);
 /* MSM window width c in bits (0 = automatic). Exposed for sweeps and tests. */
 int h2agg_set_msm_window(h2agg_ctx* ctx, int c_bits);
-/* The (c, number of windows) the MSM uses for n pairs. */
+/* Fixed-base tables: when an SRS is registered, precompute 2^(c w) P_i for every window w
+ * (W x the SRS size in HBM, c up to 20) so all windows share one bucket set.  Default on. */
+int h2agg_set_srs_precompute(h2agg_ctx* ctx, int enable);
+/* (table_mode, c, number of windows) MSMs against this SRS use. */
+int h2agg_srs_config(h2agg_ctx* ctx, uint64_t srs_id, int* table_mode, int* c_bits, int* n_windows);
+/* The (c, number of windows) the MSM uses for n pairs with per-call bases (plain mode). */
 int h2agg_msm_config(h2agg_ctx* ctx, size_t n, int* c_bits, int* n_windows);
 
 /* ---- SRS residency -------------------------------------------------------------------------

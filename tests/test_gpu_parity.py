@@ -176,27 +176,57 @@ def test_msm_hot_bucket_large(ctx):
     assert np.array_equal(ctx.msm_g1(s, b), ob.best_multiexp(s, b))
 
 
-def test_msm_srs_resident_batch_and_windows(ctx):
+@pytest.mark.parametrize("precompute", [True, False])
+def test_msm_srs_resident_batch_and_windows(ctx, precompute):
+    """Registered SRS in table mode (fixed-base 2^(cw) P tables) and in plain mode."""
     n = 1 << 13
     b = ob.gen_bases(0x53525300, n)
+    b.reshape(-1, 8)[5] = 0  # an identity base inside the SRS
+    ctx.set_srs_precompute(precompute)
     sid = ctx.srs_register(b)
+    ctx.set_srs_precompute(True)
     try:
-        cols = [ob.gen_scalars(200 + i, i % 3, n) for i in range(5)]
+        table, cbits, nwin = ctx.srs_config(sid)
+        assert table == precompute
+        cols = [ob.gen_scalars(200 + i, i % 4, n) for i in range(5)]
         want = [ob.best_multiexp(c, b) for c in cols]
         for c, w in zip(cols, want):
             assert np.array_equal(ctx.msm_g1(c, srs_id=sid), w)
         got = ctx.msm_g1_batch(sid, cols)
         for i in range(5):
             assert np.array_equal(got[i], affine_of(want[i]))
+        # commit() of a shorter polynomial uses a prefix of the SRS
+        m = 3000
+        assert np.array_equal(ctx.msm_g1(cols[0][: 4 * m], srs_id=sid, n=m), ob.best_multiexp(cols[0][: 4 * m], b[: 8 * m]))
         # window sharding: partials over disjoint window ranges add up to the full result
-        cbits, nwin = ctx.msm_config(n)
         for shards in (2, 3, 8):
             edges = [nwin * i // shards for i in range(shards + 1)]
             parts = [ctx.msm_g1(cols[0], srs_id=sid, windows=(edges[i], edges[i + 1])) for i in range(shards)]
             assert np.array_equal(ctx.g1_sum(np.concatenate(parts)), want[0])
             assert np.array_equal(ob.g1_sum(np.concatenate(parts)), want[0])
+        # a forced window width falls back to plain mode on the same SRS
+        ctx.set_msm_window(9)
+        try:
+            assert np.array_equal(ctx.msm_g1(cols[2], srs_id=sid), want[2])
+        finally:
+            ctx.set_msm_window(0)
     finally:
         ctx.srs_release(sid)
+
+
+def test_msm_table_mode_edge_cases(ctx):
+    n = 4096
+    b = ob.gen_bases(5, n)
+    same = np.tile(b[:8], n)
+    for bases in (b, same):
+        sid = ctx.srs_register(bases)
+        try:
+            assert ctx.srs_config(sid)[0]
+            for s in (np.tile(fr_limbs(1), n), ob.field_op(0, 1, np.zeros(4 * n, dtype=np.uint64), np.tile(fr_limbs(1), n)),
+                      ob.gen_scalars(6, 0, n), ob.gen_scalars(7, 1, n), np.zeros(4 * n, dtype=np.uint64)):
+                assert np.array_equal(ctx.msm_g1(s, srs_id=sid), ob.best_multiexp(s, bases))
+        finally:
+            ctx.srs_release(sid)
 
 
 def test_msm_full_size_properties(ctx):
@@ -205,11 +235,18 @@ def test_msm_full_size_properties(ctx):
     n = 1 << 22
     d_b = ctx.dev_alloc(n * 64)
     d_s = ctx.dev_alloc(n * 32)
-    d_o = ctx.dev_alloc(4 * 160)
+    d_o = ctx.dev_alloc(5 * 160)
     try:
         ctx.synth_bases_dev(0x53525300 + 22, 0, n, d_b)
         ctx.synth_scalars_dev(0xA660000 + 22, 0, 0, n, d_s)
         ctx.msm_g1_dev(d_s, n, d_o, d_bases=d_b)
+        sid = ctx.srs_register_dev(d_b, n)  # table mode at full size: 13 x 256 MiB
+        assert ctx.srs_config(sid) == (True, 20, 13)
+        ctx.msm_g1_dev(d_s, n, d_o + 640, srs_id=sid)
+        ctx.synchronize()
+        both = ctx.d2h(d_o, 100).reshape(5, 20)
+        assert np.array_equal(both[0], both[4])  # table mode == plain mode, bit for bit
+        ctx.srs_release(sid)
         h = n // 2
         ctx.msm_g1_dev(d_s, h, d_o + 160, d_bases=d_b)
         ctx.msm_g1_dev(d_s + h * 32, h, d_o + 320, d_bases=d_b + h * 64)

@@ -11,6 +11,7 @@ from halo2_snark_aggregator_b200.domain import EvaluationDomain
 
 k = int(sys.argv[1]) if len(sys.argv) > 1 else 22
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+warm = True
 n = 1 << k
 ctx = h2.Context(0)
 dom = EvaluationDomain(5, k, ctx)
@@ -22,7 +23,16 @@ ctx.synth_bases_dev(0x53525300 + k, 0, n, d_b)
 for i, kind in enumerate((0, 1, 2)):
     ctx.synth_scalars_dev(0x1000 + i, kind, 0, n, d_s[i])
 ctx.synchronize()
+sid = ctx.srs_register_dev(d_b, n) if os.environ.get("TABLE", "1") == "1" else 0
+print("srs config", ctx.srs_config(sid) if sid else None)
 ctx.kernel_timing(True)
+if sid:
+    for i in range(3):
+        t0 = time.perf_counter()
+        ctx.msm_g1_dev(d_s[i], n, d_o + 160 * i, srs_id=sid)
+        ctx.synchronize()
+        print("table-mode msm kind", i, "ms", (time.perf_counter() - t0) * 1e3)
+    print(ctx.kernel_times())
 for r in range(reps):
     for i in range(3):
         t0 = time.perf_counter()
