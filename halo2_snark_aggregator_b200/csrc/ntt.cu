@@ -225,6 +225,8 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(const __grid_cons
   }
 }
 
+int plan_passes(uint32_t log_n, uint32_t* s);
+
 static int get_tables(h2agg_ctx* ctx, const uint64_t* omega, uint32_t log_n, TwiddleTable** out) {
   ctx->tick++;
   for (auto& t : ctx->tw) {
@@ -246,7 +248,13 @@ static int get_tables(h2agg_ctx* ctx, const uint64_t* omega, uint32_t log_n, Twi
   TwiddleTable t;
   memcpy(t.omega, omega, 32);
   t.log_n = log_n;
-  t.lo_bits = (log_n + 1) / 2;
+  // lo_bits = log2(R_1): every pass after the first needs w^(P_t x) with P_t a multiple of R_1,
+  // i.e. a direct T_hi hit; only the first pass pays one multiplication to combine T_lo * T_hi.
+  {
+    uint32_t sp[4];
+    int T = plan_passes(log_n, sp);
+    t.lo_bits = (T == 1) ? (log_n + 1) / 2 : sp[0];
+  }
   uint32_t hi_bits = log_n - t.lo_bits;
   H2AGG_CUDA(ctx, cudaMalloc(&t.lo, sizeof(Fr) << t.lo_bits));
   H2AGG_CUDA(ctx, cudaMalloc(&t.hi, sizeof(Fr) << hi_bits));
@@ -263,7 +271,7 @@ static int get_tables(h2agg_ctx* ctx, const uint64_t* omega, uint32_t log_n, Twi
 }
 
 // split log_n into pass radices
-static int plan_passes(uint32_t log_n, uint32_t* s) {
+int plan_passes(uint32_t log_n, uint32_t* s) {
   if (log_n <= NTT_TILE_LOG) {
     s[0] = log_n;
     return 1;
