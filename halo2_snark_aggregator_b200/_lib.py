@@ -73,6 +73,24 @@ def load():
         "h2agg_extended_to_coeff": (ci, [c_vp, c_vp, u32, c_vp, c_vp, c_vp, sz]),
         "h2agg_coeff_to_extended_dev": (ci, [c_vp, c_vp, u32, u32, c_vp, c_vp, c_vp]),
         "h2agg_extended_to_coeff_dev": (ci, [c_vp, c_vp, u32, c_vp, c_vp, c_vp, sz]),
+        "h2agg_wit_new": (c_vp, []),
+        "h2agg_wit_free": (None, [c_vp]),
+        "h2agg_wit_error": (ctypes.c_char_p, [c_vp]),
+        "h2agg_wit_rows": (u64, [c_vp]),
+        "h2agg_wit_ops": (u64, [c_vp]),
+        "h2agg_wit_assign_point": (ctypes.c_int64, [c_vp, c_vp]),
+        "h2agg_wit_assign_constant_point": (ctypes.c_int64, [c_vp, c_vp]),
+        "h2agg_wit_assign_scalar": (ctypes.c_int64, [c_vp, c_vp]),
+        "h2agg_wit_ecc_add": (ctypes.c_int64, [c_vp, ctypes.c_int64, ctypes.c_int64]),
+        "h2agg_wit_ecc_sub": (ctypes.c_int64, [c_vp, ctypes.c_int64, ctypes.c_int64]),
+        "h2agg_wit_ecc_double": (ctypes.c_int64, [c_vp, ctypes.c_int64]),
+        "h2agg_wit_ecc_reduce": (ctypes.c_int64, [c_vp, ctypes.c_int64]),
+        "h2agg_wit_ecc_mul": (ctypes.c_int64, [c_vp, ctypes.c_int64, ctypes.c_int64]),
+        "h2agg_wit_ecc_shamir": (ctypes.c_int64, [c_vp, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64), sz]),
+        "h2agg_wit_ecc_constant_mul": (ctypes.c_int64, [c_vp, c_vp, ctypes.c_int64]),
+        "h2agg_wit_point_value": (ci, [c_vp, ctypes.c_int64, c_vp, ctypes.POINTER(ci)]),
+        "h2agg_witness_expand": (ci, [c_vp, c_vp, ctypes.POINTER(c_vp), sz]),
+        "h2agg_witness_expand_dev": (ci, [c_vp, c_vp, ctypes.POINTER(c_vp), sz]),
         "h2agg_field_mul": (ci, [c_vp, ci, c_vp, c_vp, c_vp, sz]),
         "h2agg_field_op": (ci, [c_vp, ci, ci, c_vp, c_vp, c_vp, sz]),
         "h2agg_dev_alloc": (ci, [c_vp, sz, ctypes.POINTER(c_vp)]),

@@ -53,16 +53,16 @@ class Context:
     def launch_count(self):
         return int(self.lib.h2agg_launch_count(self.h))
 
-    KERNEL_CLASSES = ("msm_accumulate", "msm_digits_sort", "msm_reduce", "ntt_pass", "msm_total")
+    KERNEL_CLASSES = ("msm_accumulate", "msm_digits_sort", "msm_reduce", "ntt_pass", "msm_total", "witness_expand")
 
     def kernel_timing(self, enable):
         self.check(self.lib.h2agg_kernel_timing(self.h, 1 if enable else 0))
 
     def kernel_times(self):
         """{class: (total_ms, launches)} since the last call (synchronises)."""
-        ms = (ctypes.c_double * 5)()
-        cnt = (ctypes.c_uint64 * 5)()
-        self.check(self.lib.h2agg_kernel_times(self.h, ms, cnt, 5))
+        ms = (ctypes.c_double * 6)()
+        cnt = (ctypes.c_uint64 * 6)()
+        self.check(self.lib.h2agg_kernel_times(self.h, ms, cnt, 6))
         return {k: (ms[i], int(cnt[i])) for i, k in enumerate(self.KERNEL_CLASSES)}
 
     def host_register(self, arr):

@@ -143,7 +143,7 @@ int h2agg_kernel_timing(h2agg_ctx* ctx, int enable) {
 int h2agg_kernel_times(h2agg_ctx* ctx, double* ms_per_class, uint64_t* count_per_class, int n_classes) {
   if (!ctx) return 1;
   LOCK(ctx);
-  CHECK_ARG(ctx, ms_per_class && count_per_class && n_classes >= KC_COUNT, "kernel_times: need >= 5 classes");
+  CHECK_ARG(ctx, ms_per_class && count_per_class && n_classes >= KC_COUNT, "kernel_times: need >= 6 classes");
   H2AGG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   for (int i = 0; i < n_classes; i++) { ms_per_class[i] = 0; count_per_class[i] = 0; }
   for (auto& t : ctx->timed) {

@@ -116,7 +116,7 @@ inline int ensure(h2agg_ctx* ctx, DevBuf& b, size_t bytes) {
 }
 
 // kernel classes for the timing hook
-enum KernelClass { KC_MSM_ACCUMULATE = 0, KC_MSM_DIGITS = 1, KC_MSM_REDUCE = 2, KC_NTT_PASS = 3, KC_MSM_TOTAL = 4, KC_COUNT = 5 };
+enum KernelClass { KC_MSM_ACCUMULATE = 0, KC_MSM_DIGITS = 1, KC_MSM_REDUCE = 2, KC_NTT_PASS = 3, KC_MSM_TOTAL = 4, KC_WITNESS = 5, KC_COUNT = 6 };
 
 struct ScopedKernelTimer {
   h2agg_ctx* ctx;
@@ -160,6 +160,7 @@ int msm_run(h2agg_ctx* ctx, cudaStream_t st, DevBuf& ws, const MsmBases& bases, 
             void* d_out160, int win_begin, int win_end);
 int msm_build_srs_table(h2agg_ctx* ctx, Srs& s);
 int msm_table_config(size_t srs_n, int* c, int* nwin);
+int witness_expand_dev(h2agg_ctx* ctx, const void* d_ops, size_t n_ops, void* const d_cols[5], size_t n_rows);
 // n_cols MSMs against the same bases, alternating lanes; joins back into ctx->stream.
 // Columns are device pointers, or host pointers when `host_cols` (then staged through the lanes).
 int msm_run_batch(h2agg_ctx* ctx, const MsmBases& bases, const void* const* cols, size_t n_cols, size_t n,

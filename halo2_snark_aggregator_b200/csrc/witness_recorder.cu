@@ -1,0 +1,984 @@
+// Host side of the witness path: a *recording* implementation of the reference's chip surface.
+//
+// The reference already has three implementations of its plugin traits ArithCommonChip /
+// ArithEccChip / ArithFieldChip (halo2-snark-aggregator-api/src/arith/{common,ecc,field}.rs): Mock,
+// Circuit (halo2-snark-aggregator-circuit/src/chips/ecc_chip.rs:28-133) and Solidity (a recording
+// context, halo2-snark-aggregator-solidity/src/lib.rs:194,293).  This is the fourth: it walks the
+// same strictly sequential chip-op chain as EccChipOps / FiveColumnIntegerChip
+// (halo2-ecc-circuit-lib/src/chips/ecc_chip.rs, five/integer_chip.rs), but instead of pushing
+// ~150 cells per integer op through `dyn Region` it
+//   * keeps only the skeleton needed to continue the chain: limb values (small integers), the
+//     value mod p, `overflows`, the native/curvature caches and the row offset -- so the row
+//     layout (including the state-dependent `reduce`s, :583-593) is reproduced exactly;
+//   * appends one 256-byte record per row recipe; the B200 kernel (witness.cu) computes the
+//     quotients, carries, range chunks, natives and inverses and writes the 5 advice columns.
+// No 256-bit division, no inversion except the one `div` needs natively, happens on the host.
+#include "../../include/h2agg.h"
+#include "ctx.hpp"
+#include "witness_ops.h"
+#include <cstring>
+#include <stdexcept>
+#include <vector>
+
+typedef unsigned __int128 u128;
+typedef uint64_t u64;
+
+namespace h2agg {
+namespace wit {
+
+// ---- host Fq (4 x 64 Montgomery) -------------------------------------------------------------
+struct Fq {
+  u64 v[4];
+};
+static const u64 QP[4] = {0x3c208c16d87cfd47ULL, 0x97816a916871ca8dULL, 0xb85045b68181585dULL, 0x30644e72e131a029ULL};
+static const u64 QR2[4] = {0xf32cfc5b538afa89ULL, 0xb5e71911d44501fbULL, 0x47ab1eff0a417ff6ULL, 0x06d89f71cab8351fULL};
+static const u64 QINV = 0x87d20782e4866389ULL;
+
+static inline bool q_geq(const u64* a) {
+  for (int i = 3; i >= 0; i--) {
+    if (a[i] > QP[i]) return true;
+    if (a[i] < QP[i]) return false;
+  }
+  return true;
+}
+static inline void q_subp(u64* a) {
+  u64 b = 0;
+  for (int i = 0; i < 4; i++) {
+    u128 d = (u128)a[i] - QP[i] - b;
+    a[i] = (u64)d;
+    b = (u64)(d >> 64) & 1;
+  }
+}
+static inline Fq q_add(const Fq& a, const Fq& b) {
+  Fq r;
+  u128 c = 0;
+  for (int i = 0; i < 4; i++) {
+    c += (u128)a.v[i] + b.v[i];
+    r.v[i] = (u64)c;
+    c >>= 64;
+  }
+  if (q_geq(r.v)) q_subp(r.v);
+  return r;
+}
+static inline Fq q_sub(const Fq& a, const Fq& b) {
+  Fq r;
+  u64 bo = 0;
+  for (int i = 0; i < 4; i++) {
+    u128 d = (u128)a.v[i] - b.v[i] - bo;
+    r.v[i] = (u64)d;
+    bo = (u64)(d >> 64) & 1;
+  }
+  if (bo) {
+    u128 c = 0;
+    for (int i = 0; i < 4; i++) {
+      c += (u128)r.v[i] + QP[i];
+      r.v[i] = (u64)c;
+      c >>= 64;
+    }
+  }
+  return r;
+}
+static inline Fq q_mul(const Fq& a, const Fq& b) {
+  u64 t[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < 4; i++) {
+    u128 c = 0;
+    for (int j = 0; j < 4; j++) {
+      c += (u128)a.v[j] * b.v[i] + t[j];
+      t[j] = (u64)c;
+      c >>= 64;
+    }
+    c += t[4];
+    t[4] = (u64)c;
+    t[5] = (u64)(c >> 64);
+    u64 m = t[0] * QINV;
+    c = ((u128)m * QP[0] + t[0]) >> 64;
+    for (int j = 1; j < 4; j++) {
+      c += (u128)m * QP[j] + t[j];
+      t[j - 1] = (u64)c;
+      c >>= 64;
+    }
+    c += t[4];
+    t[3] = (u64)c;
+    t[4] = t[5] + (u64)(c >> 64);
+  }
+  Fq r{{t[0], t[1], t[2], t[3]}};
+  if (t[4] || q_geq(r.v)) q_subp(r.v);
+  return r;
+}
+static inline Fq q_zero() { return Fq{{0, 0, 0, 0}}; }
+static inline bool q_is_zero(const Fq& a) { return (a.v[0] | a.v[1] | a.v[2] | a.v[3]) == 0; }
+static inline Fq q_from_canon(const u64* c) {
+  Fq a{{c[0], c[1], c[2], c[3]}};
+  Fq r2{{QR2[0], QR2[1], QR2[2], QR2[3]}};
+  return q_mul(a, r2);
+}
+static inline void q_to_canon(const Fq& a, u64* c) {
+  Fq one{{1, 0, 0, 0}};
+  Fq r = q_mul(a, one);
+  memcpy(c, r.v, 32);
+}
+static inline Fq q_small(u64 x) {
+  u64 c[4] = {x, 0, 0, 0};
+  return q_from_canon(c);
+}
+static Fq q_inv(const Fq& a) {  // a^(p-2); 0 -> 0
+  u64 e[4] = {QP[0] - 2, QP[1], QP[2], QP[3]};
+  Fq r = q_small(1);
+  for (int i = 255; i >= 0; i--) {
+    r = q_mul(r, r);
+    if ((e[i >> 6] >> (i & 63)) & 1) r = q_mul(r, a);
+  }
+  return r;
+}
+
+// ---- assigned objects (value semantics: a C++ copy is a Rust `.clone()`) ---------------------------
+struct Cell {
+  uint32_t row = 0;
+  uint8_t col = 0;
+};
+struct HInt {  // AssignedInteger, chips/integer_chip.rs:12-48
+  u128 limb[4];
+  Cell cell[4];
+  uint32_t overflows = 0;
+  bool native_cached = false;
+  Fq w;  // value mod p (Montgomery)
+};
+struct HCond {  // AssignedCondition / small AssignedValue
+  u64 value = 0;
+  Cell cell;
+};
+struct HCurv {
+  HInt v;
+  HCond z;
+};
+struct HPoint {  // AssignedPoint, chips/ecc_chip.rs:23-58
+  HInt x, y;
+  HCond z;
+  bool has_curv = false;
+  HCurv curv;
+};
+struct HScalar {  // AssignedValue<Fr>: canonical 256-bit
+  u64 v[4];
+  Cell cell;
+};
+
+static const u128 LIMB_MASK = (((u128)1) << 68) - 1;
+static const int OVERFLOW_LIMIT = 64, OVERFLOW_THRESHOLD = 32;
+
+struct Recorder {
+  std::vector<WitnessOp> ops;
+  uint32_t offset = 0;
+  // pending RAW128 record
+  bool raw_open = false;
+  WitnessOp raw;
+  // constants
+  u128 p_limbs[4];
+  std::vector<HPoint> points;
+  std::vector<HScalar> scalars;
+
+  Recorder() {
+    // limbs of p
+    u64 c[4] = {QP[0], QP[1], QP[2], QP[3]};
+    canon_to_limbs(c, p_limbs);
+  }
+
+  static void canon_to_limbs(const u64* c, u128* out) {
+    // 256-bit little-endian -> four 68-bit limbs
+    u128 lo = (u128)c[0] | ((u128)c[1] << 64);
+    u128 hi = (u128)c[2] | ((u128)c[3] << 64);
+    out[0] = lo & LIMB_MASK;
+    out[1] = ((lo >> 68) | (hi << 60)) & LIMB_MASK;
+    out[2] = (hi >> 8) & LIMB_MASK;
+    out[3] = hi >> 76;
+  }
+
+  // ---- record emission -----------------------------------------------------------------------
+  void flush_raw() {
+    if (raw_open) {
+      ops.push_back(raw);
+      raw_open = false;
+    }
+  }
+  uint32_t raw_row(const u128 c[5]) {  // one advice row of small values
+    if (raw_open && raw.aux == 3) flush_raw();
+    if (!raw_open) {
+      memset(&raw, 0, sizeof(raw));
+      raw.opcode = WOP_RAW128;
+      raw.row = offset;
+      raw_open = true;
+    }
+    uint32_t r = raw.aux++;
+    for (int k = 0; k < 5; k++) {
+      raw.v[10 * r + 2 * k] = (u64)c[k];
+      raw.v[10 * r + 2 * k + 1] = (u64)(c[k] >> 64);
+    }
+    return offset++;
+  }
+  uint32_t row5(u128 a0, u128 a1 = 0, u128 a2 = 0, u128 a3 = 0, u128 a4 = 0) {
+    u128 c[5] = {a0, a1, a2, a3, a4};
+    return raw_row(c);
+  }
+  uint32_t raw256_row(const u64 cells[5][4]) {
+    flush_raw();
+    WitnessOp op;
+    memset(&op, 0, sizeof(op));
+    op.opcode = WOP_RAW256;
+    op.row = offset;
+    for (int c = 0; c < 5; c++) memcpy(op.v + 4 * c, cells[c], 32);
+    ops.push_back(op);
+    return offset++;
+  }
+  static void put_limbs(u64* dst, const HInt& a) {
+    for (int i = 0; i < 4; i++) {
+      dst[2 * i] = (u64)a.limb[i];
+      dst[2 * i + 1] = (u64)(a.limb[i] >> 64);
+    }
+  }
+
+  // ---- base gate (gates/base_gate.rs, five/base_gate.rs) ----------------------------------------
+  HCond bg_assign_constant(u64 v) {
+    HCond c;
+    c.value = v;
+    c.cell = Cell{row5(v), 0};
+    return c;
+  }
+  HCond bg_mul(const HCond& a, const HCond& b) {  // :302-324 -> cells[2]
+    HCond c;
+    c.value = a.value * b.value;
+    c.cell = Cell{row5(a.value, b.value, c.value), 2};
+    return c;
+  }
+  HCond bg_not(const HCond& a) {  // sum_with_constant([(a,-1)], 1) -> [1-a, a]
+    HCond c;
+    c.value = 1 - a.value;
+    c.cell = Cell{row5(c.value, a.value), 0};
+    return c;
+  }
+  HCond bg_or(const HCond& a, const HCond& b) {
+    HCond c;
+    c.value = a.value | b.value;
+    c.cell = Cell{row5(a.value, b.value, c.value), 2};
+    return c;
+  }
+  HCond bg_xnor(const HCond& a, const HCond& b) {
+    HCond c;
+    c.value = (a.value == b.value) ? 1 : 0;
+    c.cell = Cell{row5(a.value, b.value, c.value), 2};
+    return c;
+  }
+  HCond bg_bisec(const HCond& cond, const HCond& a, const HCond& b) {  // five/base_gate.rs:82-108 -> cells[4]
+    HCond c;
+    c.value = cond.value ? a.value : b.value;
+    c.cell = Cell{row5(cond.value, a.value, cond.value, b.value, c.value), 4};
+    return c;
+  }
+  void bg_assert_constant(const HCond& a) { row5(a.value); }
+  void bg_assert_bit(u64 a) { row5(a, a); }
+
+  // ---- integer chip (five/integer_chip.rs) ---------------------------------------------------------
+  static u64 chunk(u128 l, int i) { return (u64)(l >> (17 * i)) & 0x1ffff; }
+  uint32_t limb_row(u128 n, int nchunks) {  // assign_{nonleading, *_leading}_limb: [c_top..c0, 0.., n]
+    u128 c[5] = {0, 0, 0, 0, n};
+    for (int k = 0; k < nchunks; k++) c[k] = chunk(n, nchunks - 1 - k);
+    return raw_row(c);
+  }
+  HInt assign_w_limbs(const u128 limbs[4], const Fq& w) {  // :447-464, most significant limb first
+    HInt a;
+    a.w = w;
+    a.overflows = 0;
+    a.native_cached = false;
+    const int nch[4] = {4, 4, 4, 3};
+    for (int i = 3; i >= 0; i--) {
+      a.limb[i] = limbs[i];
+      a.cell[i] = Cell{limb_row(limbs[i], nch[i]), 4};
+    }
+    return a;
+  }
+  HInt assign_w(const Fq& w) {
+    u64 c[4];
+    q_to_canon(w, c);
+    u128 l[4];
+    canon_to_limbs(c, l);
+    return assign_w_limbs(l, w);
+  }
+  HInt int_assign_constant(const Fq& w) {  // :784-794
+    u64 c[4];
+    q_to_canon(w, c);
+    HInt a;
+    canon_to_limbs(c, a.limb);
+    a.w = w;
+    for (int i = 0; i < 4; i++) a.cell[i] = Cell{row5(a.limb[i]), 0};
+    return a;
+  }
+  void native(HInt& a) {  // :595-621
+    if (a.native_cached) return;
+    flush_raw();
+    WitnessOp op;
+    memset(&op, 0, sizeof(op));
+    op.opcode = WOP_NATIVE;
+    op.row = offset;
+    put_limbs(op.v, a);
+    ops.push_back(op);
+    offset += 1;
+    a.native_cached = true;
+  }
+  void find_w_modulus_ceil(const HInt& a, u128 out[4]) {  // :31-51
+    // smallest multiple of p that is >= (overflows + 1) * 2^254, re-limbed with borrowed headroom
+    // n = ceil(((ov+1) << 254) / p): p > 2^253 so n is in [ov+1, 2(ov+1)]
+    u64 k = a.overflows + 1;
+    // compute n*p for candidates with 320-bit arithmetic (5 x u64)
+    auto mul_small = [&](u64 n, u64* out5) {
+      u128 c = 0;
+      for (int i = 0; i < 4; i++) {
+        c += (u128)QP[i] * n;
+        out5[i] = (u64)c;
+        c >>= 64;
+      }
+      out5[4] = (u64)c;
+    };
+    u64 target[5] = {0, 0, 0, k << 62, k >> 2};  // k * 2^254
+    u64 n = k, up[5];
+    for (;; n++) {
+      mul_small(n, up);
+      bool ge = true;
+      for (int i = 4; i >= 0; i--) {
+        if (up[i] > target[i]) break;
+        if (up[i] < target[i]) { ge = false; break; }
+      }
+      if (ge) break;
+    }
+    // limbs[i] = upper mod 2^68 + k * 2^68 ; upper = (upper - limbs[i]) / 2^68
+    // work on a signed-free representation: upper as 5 x u64, subtraction never underflows overall
+    auto low68 = [&](const u64* x) { return ((u128)x[0] | ((u128)x[1] << 64)) & LIMB_MASK; };
+    auto shr68 = [&](u64* x) {
+      for (int i = 0; i < 5; i++) {
+        u128 lo = (i + 1 < 5) ? x[i + 1] : 0, hi = (i + 2 < 5) ? x[i + 2] : 0;
+        u128 v = (lo >> 4) | (hi << 60);
+        x[i] = (u64)v;
+      }
+    };
+    for (int i = 0; i < 3; i++) {
+      u128 rem = low68(up) + (u128)k * (((u128)1) << 68);
+      // upper = (upper - rem) / 2^68  = (upper >> 68) - k   (the low 68 bits cancel)
+      shr68(up);
+      u128 borrow = k;
+      for (int j = 0; j < 5 && borrow; j++) {
+        u128 d = (u128)up[j] - (u64)borrow;
+        up[j] = (u64)d;
+        borrow = (d >> 64) & 1;
+      }
+      out[i] = rem;
+    }
+    out[3] = (u128)up[0] | ((u128)up[1] << 64);
+  }
+  void reduce(HInt& a) {  // :483-581
+    if (a.overflows == 0) return;
+    if (a.overflows >= (uint32_t)OVERFLOW_LIMIT) throw std::runtime_error("integer overflow limit exceeded");
+    flush_raw();
+    u64 c[4];
+    q_to_canon(a.w, c);
+    u128 rl[4];
+    canon_to_limbs(c, rl);
+    WitnessOp op;
+    memset(&op, 0, sizeof(op));
+    op.opcode = WOP_REDUCE;
+    op.row = offset;
+    op.flags = a.native_cached ? 1u : 0u;
+    put_limbs(op.v, a);
+    HInt rem;
+    rem.w = a.w;
+    for (int i = 0; i < 4; i++) rem.limb[i] = rl[i];
+    put_limbs(op.v + 8, rem);
+    ops.push_back(op);
+    const uint32_t r0 = offset;
+    // rows: assign_w(rem) 4 (limb 3 at r0 .. limb 0 at r0+3), [d,v], native(rem), [native(a)], 2 checks
+    for (int i = 0; i < 4; i++) rem.cell[i] = Cell{r0 + (uint32_t)(3 - i), 4};
+    offset += 4 + 1 + 1 + (a.native_cached ? 0 : 1) + 2;
+    rem.overflows = 0;
+    rem.native_cached = true;
+    a = rem;
+  }
+  void conditionally_reduce(HInt& a) {
+    if (a.overflows >= (uint32_t)OVERFLOW_THRESHOLD) reduce(a);
+  }
+  HInt int_add(const HInt& a, const HInt& b) {  // :641-658 rows [s, a_i, b_i]
+    HInt r;
+    for (int i = 0; i < 4; i++) {
+      r.limb[i] = a.limb[i] + b.limb[i];
+      r.cell[i] = Cell{row5(r.limb[i], a.limb[i], b.limb[i]), 0};
+    }
+    r.overflows = a.overflows + b.overflows + 1;
+    r.w = q_add(a.w, b.w);
+    conditionally_reduce(r);
+    return r;
+  }
+  HInt int_sub(const HInt& a, const HInt& b) {  // :660-683
+    u128 up[4];
+    find_w_modulus_ceil(b, up);
+    HInt r;
+    for (int i = 0; i < 4; i++) {
+      r.limb[i] = a.limb[i] + up[i] - b.limb[i];
+      r.cell[i] = Cell{row5(r.limb[i], a.limb[i], b.limb[i]), 0};
+    }
+    r.overflows = a.overflows + (b.overflows + 1) + 1;
+    r.w = q_sub(a.w, b.w);
+    conditionally_reduce(r);
+    return r;
+  }
+  HInt int_neg(const HInt& a) {  // :685-707
+    u128 up[4];
+    find_w_modulus_ceil(a, up);
+    HInt r;
+    for (int i = 0; i < 4; i++) {
+      r.limb[i] = up[i] - a.limb[i];
+      r.cell[i] = Cell{row5(r.limb[i], a.limb[i]), 0};
+    }
+    r.overflows = a.overflows + 1;
+    r.w = q_sub(q_zero(), a.w);
+    conditionally_reduce(r);
+    return r;
+  }
+  HInt int_mul_small_constant(HInt& a, u64 b) {  // :808-835
+    if (a.overflows * b >= (u64)OVERFLOW_LIMIT) reduce(a);
+    HInt r;
+    for (int i = 0; i < 4; i++) {
+      r.limb[i] = a.limb[i] * b;
+      r.cell[i] = Cell{row5(r.limb[i], a.limb[i]), 0};
+    }
+    r.overflows = a.overflows * (uint32_t)b;
+    r.w = q_mul(a.w, q_small(b));
+    conditionally_reduce(r);
+    return r;
+  }
+  HInt int_bisec(const HCond& cond, const HInt& a, const HInt& b) {  // :845-866
+    HInt r;
+    for (int i = 0; i < 4; i++) {
+      r.limb[i] = cond.value ? a.limb[i] : b.limb[i];
+      r.cell[i] = Cell{row5(cond.value, a.limb[i], cond.value, b.limb[i], r.limb[i]), 4};
+    }
+    r.overflows = a.overflows > b.overflows ? a.overflows : b.overflows;
+    r.w = cond.value ? a.w : b.w;
+    return r;
+  }
+  // x * y = d * p + z with `fresh` (y or z) assign_w'd here; sets the native caches like the
+  // reference's &mut borrows do                                                          :104-320
+  void mul_eq(HInt& x, HInt* y /*null = square*/, HInt& z, bool fresh_is_y) {
+    flush_raw();
+    WitnessOp op;
+    memset(&op, 0, sizeof(op));
+    op.opcode = WOP_MULEQ;
+    op.row = offset;
+    const bool sq = (y == nullptr);
+    op.flags = (x.native_cached ? 1u : 0u) | ((!sq && y->native_cached) ? 2u : 0u) | (z.native_cached ? 4u : 0u) |
+               (sq ? 8u : 0u) | (fresh_is_y ? 16u : 0u);
+    put_limbs(op.v, x);
+    if (!sq) put_limbs(op.v + 8, *y);
+    put_limbs(op.v + 16, z);
+    ops.push_back(op);
+    HInt& fresh = fresh_is_y ? *y : z;
+    for (int i = 0; i < 4; i++) fresh.cell[i] = Cell{offset + (uint32_t)(3 - i), 4};
+    uint32_t rows = 4 + 4 + 10 + 4 + 4;
+    rows += x.native_cached ? 0 : 1;
+    if (!sq) rows += y->native_cached ? 0 : 1;
+    rows += 1;
+    rows += z.native_cached ? 0 : 1;
+    rows += 1;
+    offset += rows;
+    x.native_cached = true;
+    if (!sq) y->native_cached = true;
+    z.native_cached = true;
+  }
+  HInt fresh_int(const Fq& w) {  // canonical limbs, rows assigned by the following mul_eq
+    HInt a;
+    u64 c[4];
+    q_to_canon(w, c);
+    canon_to_limbs(c, a.limb);
+    a.w = w;
+    a.overflows = 0;
+    a.native_cached = false;
+    return a;
+  }
+  HInt int_mul(HInt& a, HInt& b) {  // :709-726
+    if (a.overflows >= (uint32_t)OVERFLOW_LIMIT || b.overflows >= (uint32_t)OVERFLOW_LIMIT) throw std::runtime_error("mul: overflow");
+    HInt rem = fresh_int(q_mul(a.w, b.w));
+    if (&a == &b) mul_eq(a, nullptr, rem, false);
+    else mul_eq(a, &b, rem, false);
+    return rem;
+  }
+  HInt int_square(HInt& a) {  // :728-743
+    HInt rem = fresh_int(q_mul(a.w, a.w));
+    mul_eq(a, nullptr, rem, false);
+    return rem;
+  }
+  HCond int_is_zero(HInt& a) {  // :796-806
+    reduce(a);
+    flush_raw();
+    WitnessOp op;
+    memset(&op, 0, sizeof(op));
+    op.opcode = WOP_ISZERO;
+    op.row = offset;
+    op.flags = a.native_cached ? 1u : 0u;
+    put_limbs(op.v, a);
+    ops.push_back(op);
+    uint32_t rows = 1 + 2 + (a.native_cached ? 0 : 1) + 1 + 2 + 1 + 2 + 1 + 1;
+    offset += rows;
+    a.native_cached = true;
+    HCond c;
+    c.value = q_is_zero(a.w) ? 1 : 0;  // a reduced value is canonical, so "== p" never holds
+    c.cell = Cell{offset - 1, 2};
+    return c;
+  }
+  HCond int_is_equal(HInt& a, HInt& b) {
+    HInt diff = int_sub(a, b);
+    return int_is_zero(diff);
+  }
+  HCond int_div(HInt& a, HInt& b, HInt* out_c) {  // :745-782
+    HCond is_b_zero = int_is_zero(b);
+    HCond a_coeff = bg_not(is_b_zero);
+    reduce(a);
+    HInt a2;
+    for (int i = 0; i < 4; i++) {
+      a2.limb[i] = a_coeff.value ? a.limb[i] : 0;
+      a2.cell[i] = Cell{row5(a.limb[i], a_coeff.value, a2.limb[i]), 2};
+    }
+    a2.overflows = a.overflows;
+    a2.native_cached = false;
+    a2.w = a_coeff.value ? a.w : q_zero();
+    Fq c = q_is_zero(b.w) ? q_zero() : q_mul(q_inv(b.w), a2.w);
+    HInt ci = fresh_int(c);
+    mul_eq(b, &ci, a2, true);
+    *out_c = ci;
+    return is_b_zero;
+  }
+
+  // ---- ecc chip (chips/ecc_chip.rs) ------------------------------------------------------------------
+  HCurv& curvature(HPoint& a) {  // :280-307
+    if (!a.has_curv) {
+      HInt x_square = int_square(a.x);
+      HInt numerator = int_mul_small_constant(x_square, 3);
+      HInt denominator = int_mul_small_constant(a.y, 2);
+      HCurv c;
+      c.z = int_div(numerator, denominator, &c.v);
+      a.curv = c;
+      a.has_curv = true;
+    }
+    return a.curv;
+  }
+  HCurv bisec_curvature(const HCond& cond, const HCurv& a, const HCurv& b) {
+    HCurv r;
+    r.v = int_bisec(cond, a.v, b.v);
+    r.z = bg_bisec(cond, a.z, b.z);
+    return r;
+  }
+  HPoint bisec_point(const HCond& cond, const HPoint& a, const HPoint& b) {
+    HPoint r;
+    r.x = int_bisec(cond, a.x, b.x);
+    r.y = int_bisec(cond, a.y, b.y);
+    r.z = bg_bisec(cond, a.z, b.z);
+    return r;
+  }
+  HPoint bisec_point_with_curvature(const HCond& cond, HPoint& a, HPoint& b) {
+    HPoint r;
+    r.x = int_bisec(cond, a.x, b.x);
+    r.y = int_bisec(cond, a.y, b.y);
+    r.z = bg_bisec(cond, a.z, b.z);
+    HCurv& ca = curvature(a);
+    HCurv& cb = curvature(b);
+    r.curv = bisec_curvature(cond, ca, cb);
+    r.has_curv = true;
+    return r;
+  }
+  HPoint lambda_to_point(HCurv& lambda, const HPoint& a, const HPoint& b) {  // :356-382
+    HInt& l = lambda.v;
+    HInt l_square = int_square(l);
+    HInt t = int_sub(l_square, a.x);
+    HInt cx = int_sub(t, b.x);
+    HInt t2 = int_sub(a.x, cx);
+    HInt t3 = int_mul(t2, l);
+    HInt cy = int_sub(t3, a.y);
+    HPoint p;
+    p.x = cx; p.y = cy; p.z = lambda.z;
+    return p;
+  }
+  HPoint ecc_add(HPoint& a, const HPoint& b) {  // :383-408
+    HInt diff_x = int_sub(a.x, b.x);
+    HInt diff_y = int_sub(a.y, b.y);
+    HCurv tangent;
+    HCond x_eq = int_div(diff_y, diff_x, &tangent.v);
+    HCond y_eq = int_is_zero(diff_y);
+    HCond eq = bg_mul(x_eq, y_eq);
+    tangent.z = x_eq;
+    HCurv& curv = curvature(a);
+    HCurv lambda = bisec_curvature(eq, curv, tangent);
+    HPoint p = lambda_to_point(lambda, a, b);
+    p = bisec_point(a.z, b, p);
+    p = bisec_point(b.z, a, p);
+    return p;
+  }
+  HPoint ecc_double(HPoint& a) {  // :409-419
+    HCurv c = curvature(a);  // clone
+    HPoint p = lambda_to_point(c, a, a);
+    p.z = bg_bisec(a.z, a.z, p.z);
+    return p;
+  }
+  HPoint assign_identity() {  // :517-527
+    HInt zero = int_assign_constant(q_zero());
+    HCond one = bg_assign_constant(1);
+    HPoint p;
+    p.x = zero; p.y = zero; p.z = one;
+    p.curv.v = zero; p.curv.z = one;
+    p.has_curv = true;
+    return p;
+  }
+  HPoint assign_constant_point_with_curvature(bool identity, const Fq& x, const Fq& y) {  // :438-472
+    Fq xv = identity ? q_zero() : x, yv = identity ? q_zero() : y;
+    HPoint p;
+    p.curv.v = int_assign_constant(q_is_zero(xv) ? q_zero() : q_mul(yv, q_inv(xv)));
+    p.curv.z = bg_assign_constant(q_is_zero(xv) ? 1 : 0);
+    p.x = int_assign_constant(xv);
+    p.y = int_assign_constant(yv);
+    p.z = bg_assign_constant(identity ? 1 : 0);
+    p.has_curv = true;
+    return p;
+  }
+  HPoint assign_constant_point(bool identity, const Fq& x, const Fq& y) {  // :420-437
+    HPoint p;
+    p.x = int_assign_constant(identity ? q_zero() : x);
+    p.y = int_assign_constant(identity ? q_zero() : y);
+    p.z = bg_assign_constant(identity ? 1 : 0);
+    return p;
+  }
+  HPoint assign_point(bool identity, const Fq& x, const Fq& y) {  // :473-500 (on-curve check)
+    HPoint p;
+    p.x = assign_w(identity ? q_zero() : x);
+    p.y = assign_w(identity ? q_zero() : y);
+    HCond z;
+    z.value = identity ? 1 : 0;
+    z.cell = Cell{row5(z.value), 0};  // base_gate.assign
+    p.z = z;
+    HInt b = int_assign_constant(q_small(3));
+    HInt y2 = int_square(p.y);
+    HInt x2 = int_square(p.x);
+    HInt x3 = int_mul(x2, p.x);
+    HInt right = int_add(x3, b);
+    HCond eq = int_is_equal(y2, right);
+    HCond eq_or_identity = bg_or(eq, z);
+    if (!eq_or_identity.value) throw std::runtime_error("assign_point: point is not on the curve");
+    bg_assert_constant(eq_or_identity);
+    return p;
+  }
+  HPoint ecc_neg(const HPoint& a) {
+    HPoint r;
+    r.x = a.x;
+    r.y = int_neg(a.y);
+    r.z = a.z;
+    return r;
+  }
+  HPoint ecc_sub(HPoint& a, const HPoint& b) {
+    HPoint nb = ecc_neg(b);
+    return ecc_add(a, nb);
+  }
+  HPoint ecc_reduce(HPoint& a) {  // :569-580
+    reduce(a.x);
+    reduce(a.y);
+    HPoint id = assign_identity();
+    return bisec_point(a.z, id, a);
+  }
+  // NativeEccChip::decompose_scalar, chips/native_ecc_chip.rs:42-132 -> windows big-endian, bits little-endian
+  std::vector<std::vector<HCond>> decompose_scalar(const HScalar& s, int window) {
+    const int windows = (254 - 1 + window) / window;
+    std::vector<std::vector<HCond>> ret;
+    u64 cur[4] = {s.v[0], s.v[1], s.v[2], s.v[3]};
+    for (int w = 0; w < windows; w++) {
+      u64 cells[5][4];
+      memset(cells, 0, sizeof(cells));
+      std::vector<HCond> bits(window);
+      for (int i = 0; i < window; i++) {
+        bits[i].value = (cur[0] >> i) & 1;
+        cells[i][0] = bits[i].value;
+      }
+      memcpy(cells[4], cur, 32);
+      uint32_t row = raw256_row(cells);
+      for (int i = 0; i < window; i++) bits[i].cell = Cell{row, (uint8_t)i};
+      ret.push_back(bits);
+      // cur >>= window
+      for (int k = 0; k < 4; k++) cur[k] = (cur[k] >> window) | (k + 1 < 4 ? cur[k + 1] << (64 - window) : 0);
+    }
+    std::vector<std::vector<HCond>> be(ret.rbegin(), ret.rend());
+    for (auto& win : be)
+      for (auto& bit : win) bg_assert_bit(bit.value);
+    return be;
+  }
+  HPoint pick_candidate(const std::vector<HPoint>& candidates, const std::vector<HCond>& bits_le) {
+    std::vector<HPoint> curr = candidates;  // clone
+    for (const HCond& bit : bits_le) {
+      std::vector<HPoint> next;
+      for (size_t k = 0; k + 1 < curr.size(); k += 2) next.push_back(bisec_point_with_curvature(bit, curr[k + 1], curr[k]));
+      curr.swap(next);
+    }
+    return curr[0];
+  }
+  HPoint ecc_mul(HPoint& a, const HScalar& s) {  // :86-138
+    auto windows = decompose_scalar(s, 4);
+    std::vector<HPoint> cands;
+    cands.push_back(assign_identity());
+    cands.push_back(a);
+    for (int i = 2; i < 16; i++) {
+      HPoint ai = ecc_add(cands[i - 1], a);
+      cands.push_back(ai);
+    }
+    HPoint acc = pick_candidate(cands, windows[0]);
+    for (size_t w = 1; w < windows.size(); w++) {
+      for (int k = 0; k < 4; k++) acc = ecc_double(acc);
+      HPoint curr = pick_candidate(cands, windows[w]);
+      acc = ecc_add(curr, acc);
+    }
+    return acc;
+  }
+  HPoint ecc_shamir(std::vector<HPoint>& pts, const std::vector<HScalar>& scalars) {  // :139-244
+    std::vector<std::vector<std::vector<HCond>>> windows;
+    for (auto& s : scalars) windows.push_back(decompose_scalar(s, 4));
+    HPoint identity = assign_identity();
+    std::vector<std::vector<HPoint>> pc;
+    for (auto& a : pts) {
+      std::vector<HPoint> cands;
+      cands.push_back(identity);
+      cands.push_back(a);
+      for (int i = 2; i < 16; i++) {
+        HPoint ai = ecc_add(cands[i - 1], a);
+        curvature(ai);
+        cands.push_back(ai);
+      }
+      pc.push_back(cands);
+    }
+    bool have_acc = false;
+    HPoint acc;
+    for (size_t wi = 0; wi < windows[0].size(); wi++) {
+      bool have_inner = false;
+      HPoint inner;
+      for (size_t pi = 0; pi < pts.size(); pi++) {
+        HPoint ci = pick_candidate(pc[pi], windows[pi][wi]);
+        if (!have_inner) { inner = ci; have_inner = true; }
+        else inner = ecc_add(ci, inner);
+      }
+      if (!have_acc) { acc = inner; have_acc = true; }
+      else {
+        for (int k = 0; k < 4; k++) acc = ecc_double(acc);
+        acc = ecc_add(inner, acc);
+      }
+    }
+    return acc;
+  }
+};
+
+// native affine group law for constant_mul's table of constants (host, Fq Montgomery)
+struct Aff {
+  Fq x, y;
+  bool inf;
+};
+static Aff aff_add(const Aff& p, const Aff& q) {
+  if (p.inf) return q;
+  if (q.inf) return p;
+  Fq lam;
+  if (memcmp(p.x.v, q.x.v, 32) == 0) {
+    Fq s = q_add(p.y, q.y);
+    if (q_is_zero(s)) return Aff{q_zero(), q_zero(), true};
+    Fq xx = q_mul(p.x, p.x);
+    lam = q_mul(q_add(q_add(xx, xx), xx), q_inv(q_add(p.y, p.y)));
+  } else {
+    lam = q_mul(q_sub(q.y, p.y), q_inv(q_sub(q.x, p.x)));
+  }
+  Fq x3 = q_sub(q_sub(q_mul(lam, lam), p.x), q.x);
+  Fq y3 = q_sub(q_mul(lam, q_sub(p.x, x3)), p.y);
+  return Aff{x3, y3, false};
+}
+
+}  // namespace wit
+}  // namespace h2agg
+
+using namespace h2agg;
+using namespace h2agg::wit;
+
+struct h2agg_witness {
+  Recorder rec;
+  std::string err;
+};
+
+static bool is_identity_affine(const uint64_t* xy) {
+  for (int i = 0; i < 8; i++)
+    if (xy[i]) return false;
+  return true;
+}
+static Fq fq_from_mont_words(const uint64_t* w) { return Fq{{w[0], w[1], w[2], w[3]}}; }
+
+#define WIT_TRY(w, ...)               \
+  try {                               \
+    __VA_ARGS__;                      \
+  } catch (const std::exception& e) { \
+    (w)->err = e.what();              \
+    return -1;                        \
+  }
+
+extern "C" {
+
+h2agg_witness* h2agg_wit_new(void) { return new h2agg_witness(); }
+void h2agg_wit_free(h2agg_witness* w) { delete w; }
+const char* h2agg_wit_error(h2agg_witness* w) { return w ? w->err.c_str() : ""; }
+uint64_t h2agg_wit_rows(h2agg_witness* w) { return w->rec.offset; }
+uint64_t h2agg_wit_ops(h2agg_witness* w) { w->rec.flush_raw(); return w->rec.ops.size(); }
+
+// points are affine Montgomery (x, y), (0,0) = identity; returns a point handle
+int64_t h2agg_wit_assign_point(h2agg_witness* w, const uint64_t xy[8]) {
+  WIT_TRY(w, {
+    w->rec.points.push_back(w->rec.assign_point(is_identity_affine(xy), fq_from_mont_words(xy), fq_from_mont_words(xy + 4)));
+  });
+  return (int64_t)w->rec.points.size() - 1;
+}
+int64_t h2agg_wit_assign_constant_point(h2agg_witness* w, const uint64_t xy[8]) {
+  WIT_TRY(w, {
+    w->rec.points.push_back(w->rec.assign_constant_point(is_identity_affine(xy), fq_from_mont_words(xy), fq_from_mont_words(xy + 4)));
+  });
+  return (int64_t)w->rec.points.size() - 1;
+}
+// scalar: Montgomery Fr (4 limbs) as the chips hold it; assigned with BaseGateOps::assign (1 row)
+int64_t h2agg_wit_assign_scalar(h2agg_witness* w, const uint64_t s_canonical[4]) {
+  HScalar s;
+  memcpy(s.v, s_canonical, 32);
+  uint64_t cells[5][4];
+  memset(cells, 0, sizeof(cells));
+  memcpy(cells[0], s_canonical, 32);
+  s.cell = Cell{w->rec.raw256_row(cells), 0};
+  w->rec.scalars.push_back(s);
+  return (int64_t)w->rec.scalars.size() - 1;
+}
+int64_t h2agg_wit_ecc_add(h2agg_witness* w, int64_t a, int64_t b) {
+  WIT_TRY(w, {
+    HPoint bb = w->rec.points.at(b);
+    HPoint r = w->rec.ecc_add(w->rec.points.at(a), bb);
+    w->rec.points.push_back(r);
+  });
+  return (int64_t)w->rec.points.size() - 1;
+}
+int64_t h2agg_wit_ecc_sub(h2agg_witness* w, int64_t a, int64_t b) {
+  WIT_TRY(w, {
+    HPoint bb = w->rec.points.at(b);
+    HPoint r = w->rec.ecc_sub(w->rec.points.at(a), bb);
+    w->rec.points.push_back(r);
+  });
+  return (int64_t)w->rec.points.size() - 1;
+}
+int64_t h2agg_wit_ecc_double(h2agg_witness* w, int64_t a) {
+  WIT_TRY(w, {
+    HPoint r = w->rec.ecc_double(w->rec.points.at(a));
+    w->rec.points.push_back(r);
+  });
+  return (int64_t)w->rec.points.size() - 1;
+}
+int64_t h2agg_wit_ecc_reduce(h2agg_witness* w, int64_t a) {
+  WIT_TRY(w, {
+    HPoint r = w->rec.ecc_reduce(w->rec.points.at(a));
+    w->rec.points.push_back(r);
+  });
+  return (int64_t)w->rec.points.size() - 1;
+}
+// ArithEccChip::scalar_mul -> EccChipOps::mul
+int64_t h2agg_wit_ecc_mul(h2agg_witness* w, int64_t a, int64_t s) {
+  WIT_TRY(w, {
+    HPoint r = w->rec.ecc_mul(w->rec.points.at(a), w->rec.scalars.at(s));
+    w->rec.points.push_back(r);
+  });
+  return (int64_t)w->rec.points.size() - 1;
+}
+// ArithEccChip::multi_exp -> EccChipOps::shamir (halo2-snark-aggregator-circuit/src/chips/ecc_chip.rs:125-132)
+int64_t h2agg_wit_ecc_shamir(h2agg_witness* w, const int64_t* pts, const int64_t* scalars, size_t n) {
+  WIT_TRY(w, {
+    std::vector<HPoint> p;
+    std::vector<HScalar> s;
+    for (size_t i = 0; i < n; i++) {
+      p.push_back(w->rec.points.at(pts[i]));
+      s.push_back(w->rec.scalars.at(scalars[i]));
+    }
+    HPoint r = w->rec.ecc_shamir(p, s);
+    w->rec.points.push_back(r);
+  });
+  return (int64_t)w->rec.points.size() - 1;
+}
+// ArithEccChip::scalar_mul_constant -> EccChipOps::constant_mul (2-bit windows over constant multiples)
+int64_t h2agg_wit_ecc_constant_mul(h2agg_witness* w, const uint64_t base_xy[8], int64_t s) {
+  WIT_TRY(w, {
+    Recorder& r = w->rec;
+    auto bits_be = r.decompose_scalar(r.scalars.at(s), 2);
+    HPoint identity = r.assign_constant_point_with_curvature(true, q_zero(), q_zero());
+    Aff base{fq_from_mont_words(base_xy), fq_from_mont_words(base_xy + 4), is_identity_affine(base_xy)};
+    bool have = false;
+    HPoint acc;
+    for (auto it = bits_be.rbegin(); it != bits_be.rend(); ++it) {
+      Aff b2 = aff_add(base, base), b3 = aff_add(b2, base);
+      HPoint c01 = r.assign_constant_point_with_curvature(b2.inf, b2.x, b2.y);
+      HPoint c10 = r.assign_constant_point_with_curvature(base.inf, base.x, base.y);
+      HPoint c11 = r.assign_constant_point_with_curvature(b3.inf, b3.x, b3.y);
+      HPoint c0 = r.bisec_point_with_curvature((*it)[0], c10, identity);
+      HPoint c1 = r.bisec_point_with_curvature((*it)[0], c11, c01);
+      HPoint slot = r.bisec_point_with_curvature((*it)[1], c1, c0);
+      if (!have) { acc = slot; have = true; }
+      else acc = r.ecc_add(slot, acc);
+      base = aff_add(b3, base);
+    }
+    r.points.push_back(acc);
+  });
+  return (int64_t)w->rec.points.size() - 1;
+}
+// value of a point handle: canonical affine (x mod p, y mod p) as Montgomery limbs + identity flag
+int h2agg_wit_point_value(h2agg_witness* w, int64_t h, uint64_t out_xy[8], int* is_identity) {
+  if (h < 0 || (size_t)h >= w->rec.points.size()) return -1;
+  const HPoint& p = w->rec.points[h];
+  memcpy(out_xy, p.x.w.v, 32);
+  memcpy(out_xy + 4, p.y.w.v, 32);
+  *is_identity = (int)p.z.value;
+  return 0;
+}
+
+// Run the expansion kernel over everything recorded so far: 5 advice columns of n_rows Fr each
+// (host pointers; rows beyond the recorded offset stay zero like unassigned halo2 cells).
+int h2agg_witness_expand(h2agg_ctx* ctx, h2agg_witness* w, uint64_t* const advice_cols[5], size_t n_rows) {
+  if (!ctx || !w) return 1;
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+  w->rec.flush_raw();
+  if (n_rows < w->rec.offset) {
+    ctx->last_error = "witness_expand: n_rows is smaller than the recorded layout";
+    return 1;
+  }
+  H2AGG_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t n_ops = w->rec.ops.size();
+  int rc = ensure(ctx, ctx->io_a, n_ops * sizeof(WitnessOp) + 256);
+  if (rc) return rc;
+  rc = ensure(ctx, ctx->io_b, n_rows * 32 * 5);
+  if (rc) return rc;
+  if (n_ops) H2AGG_CUDA(ctx, cudaMemcpyAsync(ctx->io_a.p, w->rec.ops.data(), n_ops * sizeof(WitnessOp), cudaMemcpyHostToDevice, ctx->stream));
+  void* cols[5];
+  for (int c = 0; c < 5; c++) cols[c] = (uint8_t*)ctx->io_b.p + (size_t)c * n_rows * 32;
+  rc = witness_expand_dev(ctx, ctx->io_a.p, n_ops, cols, n_rows);
+  if (rc) return rc;
+  for (int c = 0; c < 5; c++) H2AGG_CUDA(ctx, cudaMemcpyAsync(advice_cols[c], cols[c], n_rows * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  H2AGG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// Same, leaving the columns in HBM (they feed commit_lagrange directly): d_cols = 5 device pointers.
+int h2agg_witness_expand_dev(h2agg_ctx* ctx, h2agg_witness* w, void* const d_cols[5], size_t n_rows) {
+  if (!ctx || !w) return 1;
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+  w->rec.flush_raw();
+  if (n_rows < w->rec.offset) {
+    ctx->last_error = "witness_expand: n_rows is smaller than the recorded layout";
+    return 1;
+  }
+  H2AGG_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t n_ops = w->rec.ops.size();
+  int rc = ensure(ctx, ctx->io_a, n_ops * sizeof(WitnessOp) + 256);
+  if (rc) return rc;
+  if (n_ops) H2AGG_CUDA(ctx, cudaMemcpyAsync(ctx->io_a.p, w->rec.ops.data(), n_ops * sizeof(WitnessOp), cudaMemcpyHostToDevice, ctx->stream));
+  return witness_expand_dev(ctx, ctx->io_a.p, n_ops, d_cols, n_rows);
+}
+
+}  // extern "C"

@@ -126,6 +126,37 @@ int h2agg_coeff_to_extended_dev(h2agg_ctx* ctx, const void* d_coeffs, uint32_t k
 int h2agg_extended_to_coeff_dev(h2agg_ctx* ctx, void* d_a, uint32_t ext_k, const uint64_t omega_ext_inv[4],
                                 const uint64_t ext_n_inv[4], const uint64_t zeta[4], size_t out_len);
 
+/* ---- W1-W5: witness synthesis of halo2-ecc-circuit-lib ---------------------------
+ * A recording implementation of the reference's chip surface -- ArithEccChip::{add, sub, scalar_mul,
+ * scalar_mul_constant, multi_exp, assign_var, assign_const, normalize}
+ * (halo2-snark-aggregator-api/src/arith/ecc.rs:5-61, common.rs:3-42) as bound to
+ * EccChipOps::{add, sub, mul, constant_mul, shamir, assign_point, assign_constant_point, reduce}
+ * by halo2-snark-aggregator-circuit/src/chips/ecc_chip.rs:28-133.  The host walks the sequential op
+ * chain and reproduces the exact row layout; the kernel expands every integer op into its advice
+ * rows.  Handles are indices; negative return = error (h2agg_wit_error).  Points are affine
+ * Montgomery Fq pairs, (0,0) = identity; scalars are CANONICAL 256-bit integers < r. */
+typedef struct h2agg_witness h2agg_witness;
+h2agg_witness* h2agg_wit_new(void);
+void h2agg_wit_free(h2agg_witness* w);
+const char* h2agg_wit_error(h2agg_witness* w);
+uint64_t h2agg_wit_rows(h2agg_witness* w); /* current row offset = rows the layout occupies */
+uint64_t h2agg_wit_ops(h2agg_witness* w);  /* op records queued for the kernel */
+int64_t h2agg_wit_assign_point(h2agg_witness* w, const uint64_t xy[8]);          /* assign_point (on-curve check rows) */
+int64_t h2agg_wit_assign_constant_point(h2agg_witness* w, const uint64_t xy[8]); /* assign_constant_point */
+int64_t h2agg_wit_assign_scalar(h2agg_witness* w, const uint64_t s_canonical[4]);
+int64_t h2agg_wit_ecc_add(h2agg_witness* w, int64_t a, int64_t b);
+int64_t h2agg_wit_ecc_sub(h2agg_witness* w, int64_t a, int64_t b);
+int64_t h2agg_wit_ecc_double(h2agg_witness* w, int64_t a);
+int64_t h2agg_wit_ecc_reduce(h2agg_witness* w, int64_t a);                        /* normalize */
+int64_t h2agg_wit_ecc_mul(h2agg_witness* w, int64_t a, int64_t s);                /* scalar_mul */
+int64_t h2agg_wit_ecc_shamir(h2agg_witness* w, const int64_t* pts, const int64_t* scalars, size_t n); /* multi_exp */
+int64_t h2agg_wit_ecc_constant_mul(h2agg_witness* w, const uint64_t base_xy[8], int64_t s); /* scalar_mul_constant */
+int h2agg_wit_point_value(h2agg_witness* w, int64_t h, uint64_t out_xy[8], int* is_identity); /* to_value */
+/* Expand everything recorded into the 5 advice columns (n_rows Fr each, Montgomery; rows past the
+ * recorded offset are zero like unassigned halo2 cells).  Host pointers / device pointers. */
+int h2agg_witness_expand(h2agg_ctx* ctx, h2agg_witness* w, uint64_t* const advice_cols[5], size_t n_rows);
+int h2agg_witness_expand_dev(h2agg_ctx* ctx, h2agg_witness* w, void* const d_cols[5], size_t n_rows);
+
 /* ---- small helpers used by tests and the host layer (run on the device) ---------------------- */
 /* out[i] = a[i] * b[i] in Fr (field = 0) or Fq (field = 1); host pointers; Montgomery form. */
 int h2agg_field_mul(h2agg_ctx* ctx, int field, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n);

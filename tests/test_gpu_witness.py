@@ -1,0 +1,65 @@
+"""GPU parity for the witness path (W1-W5): the 5 advice columns produced by the recorder + the
+B200 expansion kernel (through the C ABI) equal, bit for bit, the advice cells of the Python
+restatement of halo2-ecc-circuit-lib -- whose rows are themselves MockProver-checked."""
+import numpy as np
+import pytest
+
+import ecc_chip_ref as E
+import halo2_snark_aggregator_b200 as h2
+import witness_scenarios as ws
+
+pytestmark = pytest.mark.gpu
+
+
+def _compare(b, cols):
+    want = E.advice_columns(b.ctx)
+    n = b.ctx.offset
+    assert cols.shape[1] >= n
+    for c in range(5):
+        w = ws.fr_mont_rows(want[c])
+        got = cols[c, :n]
+        if not np.array_equal(got, w):
+            bad = np.nonzero((got != w).any(axis=1))[0]
+            raise AssertionError("advice column %d differs at %d rows, first row %d" % (c, bad.size, bad[0]))
+    assert not cols[:, n:].any()  # rows past the layout stay zero
+
+
+@pytest.mark.parametrize("name", ws.SCENARIOS)
+def test_advice_columns_match_reference_restatement(ctx, name):
+    chip = h2.B200EccChip()
+    b, res = ws.run(name, chip)
+    E.check(b.ctx)  # the oracle's rows satisfy gate + lookups + copy constraints
+    assert chip.rows() == b.ctx.offset
+    cols = chip.expand(ctx, n_rows=b.ctx.offset + 17)
+    _compare(b, cols)
+    chip.close()
+
+
+def test_expand_dev_feeds_commit_without_leaving_hbm(ctx):
+    """Witness columns stay in HBM and go straight into the MSM (commit_lagrange of an advice column)."""
+    import oracle_binding as ob
+
+    chip = h2.B200EccChip()
+    b, _ = ws.run("multi_exp_1", chip)
+    n = 1 << 17
+    assert chip.rows() <= n
+    d_cols = [ctx.dev_alloc(n * 32) for _ in range(5)]
+    d_b = ctx.dev_alloc(n * 64)
+    d_o = ctx.dev_alloc(5 * 160)
+    try:
+        chip.expand_dev(ctx, d_cols, n)
+        ctx.synth_bases_dev(0x53525300, 0, n, d_b)
+        ctx.msm_g1_batch_dev(d_cols, n, d_o, d_bases=d_b)
+        ctx.synchronize()
+        got = ctx.d2h(d_o, 100).reshape(5, 20)
+        bases = ob.gen_bases(0x53525300, n)
+        want_cols = E.advice_columns(b.ctx)
+        for c in (0, 4):
+            col = np.zeros((n, 4), dtype=np.uint64)
+            col[: b.ctx.offset] = ws.fr_mont_rows(want_cols[c])
+            assert np.array_equal(ctx.d2h(d_cols[c], 4 * n).reshape(n, 4), col)
+            assert np.array_equal(got[c, 8:], ob.best_multiexp(np.ascontiguousarray(col).ravel(), bases))
+    finally:
+        for d in d_cols + [d_b, d_o]:
+            ctx.dev_free(d)
+        chip.close()

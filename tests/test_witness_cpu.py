@@ -1,0 +1,122 @@
+"""CPU suite for the witness path: (1) the Python oracle is a faithful chip restatement -- its rows
+satisfy the gate polynomial, range lookups and copy constraints (mini-MockProver), its results equal
+native G1 arithmetic and its row counts reproduce SURVEY.md App. G / the reference's estimator;
+(2) the product's host recorder reproduces the oracle's row layout op for op (no GPU needed for
+that); (3) kernel constants."""
+import os
+import random
+import re
+
+import numpy as np
+import pytest
+
+import bn254_ref as ref
+import ecc_chip_ref as E
+import halo2_snark_aggregator_b200 as h2
+import witness_scenarios as ws
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_integer_chip_vs_native_fq_and_row_counts():
+    rng = random.Random(3)
+    ctx = E.Context()
+    counts = {}
+    for _ in range(6):
+        x, y = rng.randrange(E.P), rng.randrange(E.P)
+        a, b = E.assign_w(ctx, x), E.assign_w(ctx, y)
+        o = ctx.offset; r = E.int_mul(ctx, a, b); counts["mul"] = ctx.offset - o
+        assert r.w() == x * y % E.P
+        a = E.assign_w(ctx, x); o = ctx.offset; r = E.int_square(ctx, a); counts["square"] = ctx.offset - o
+        assert r.w() == x * x % E.P
+        a, b = E.assign_w(ctx, x), E.assign_w(ctx, y)
+        o = ctx.offset; z, c = E.int_div(ctx, a, b); counts["div"] = ctx.offset - o
+        assert c.w() * y % E.P == x and z.value == 0
+        a, b = E.assign_w(ctx, x), E.assign_w(ctx, y)
+        s = E.int_add(ctx, a, b); assert s.w() == (x + y) % E.P
+        d = E.int_sub(ctx, a, b); assert d.w() == (x - y) % E.P
+        n = E.int_neg(ctx, a); assert n.w() == (-x) % E.P
+        o = ctx.offset; E.reduce(ctx, s); counts["reduce"] = ctx.offset - o
+        assert s.w() == (x + y) % E.P and s.overflows == 0
+        a = E.assign_w(ctx, x); o = ctx.offset; z = E.int_is_zero(ctx, a); counts["is_zero"] = ctx.offset - o
+        assert z.value == 0
+    z0 = E.assign_w(ctx, 0)
+    assert E.int_is_zero(ctx, z0).value == 1
+    a, b = E.assign_w(ctx, 5), E.assign_w(ctx, 0)  # division by zero: c = 0, flag set (:745-782)
+    zf, c = E.int_div(ctx, a, b)
+    assert zf.value == 1 and c.w() == 0
+    a = E.assign_w(ctx, 12345); bit = E.int_get_last_bit(ctx, a); assert bit.value == 1
+    big = E.assign_w(ctx, E.P - 1)
+    acc = big
+    for _ in range(40):  # drive overflows past the threshold: conditional reduce must kick in
+        acc = E.int_add(ctx, acc, big)
+        assert acc.overflows < E.OVERFLOW_LIMIT
+    assert acc.w() == 41 * (E.P - 1) % E.P
+    assert counts == {"mul": 31, "square": 30, "div": 47, "reduce": 9, "is_zero": 12}
+    E.check(ctx)
+
+
+@pytest.mark.parametrize("name", ws.SCENARIOS)
+def test_oracle_scenarios_mockprover_and_native_results(name):
+    b, res = ws.run(name)
+    for handle, want in res:
+        assert b.value(handle) == want
+    E.check(b.ctx)
+
+
+def test_oracle_row_counts_match_reference_estimator():
+    """shamir with 1 / 2 points = 73 463 / 110 064 rows, i.e. the marginal cost per
+    point brackets the reference's hard-coded ecmul_rows = 32196 (evaluation.rs:132)."""
+    rows = {}
+    for n in (1, 2):
+        rng = random.Random(n)
+        ctx = E.Context()
+        pts = [E.assign_point(ctx, ref.g1_mul(rng.randrange(1, ref.R), ref.G1_GEN)) for _ in range(n)]
+        sc = [E.bg_assign(ctx, rng.randrange(ref.R)) for _ in range(n)]
+        o = ctx.offset
+        E.ecc_shamir(ctx, pts, sc)
+        rows[n] = ctx.offset - o
+    assert rows == {1: 73463, 2: 110064}
+    assert 30000 < rows[2] - rows[1] < 40000
+
+
+@pytest.mark.parametrize("name", ws.SCENARIOS)
+def test_recorder_reproduces_oracle_layout_and_values(name):
+    chip = h2.B200EccChip()
+    b, res = ws.run(name, chip)
+    assert chip.rows() == b.ctx.offset, "row layout diverged from the reference restatement"
+    for (o, h), want in res:
+        xy, ident = chip.to_value(h)
+        if want is None:
+            assert ident
+        else:
+            assert not ident and np.array_equal(xy, ws.xy_mont(want))
+    assert chip.ops() > 0
+    chip.close()
+
+
+def test_recorder_rejects_point_off_curve():
+    chip = h2.B200EccChip()
+    with pytest.raises(h2.H2aggError):
+        chip.assign_var(ws.xy_mont((1, 3)))
+    chip.close()
+
+
+def test_kernel_constants():
+    src = open(os.path.join(ROOT, "halo2_snark_aggregator_b200", "csrc", "witness.cu")).read()
+
+    def words(name):
+        m = re.search(name + r"\[[^=]*=\s*\{(.*?)\};", src, re.S)
+        vals = [int(x, 16) for x in re.findall(r"0x[0-9a-f]+", m.group(1))]
+        return vals
+
+    def val(ws_):
+        return sum(w << (32 * i) for i, w in enumerate(ws_))
+
+    assert val(words("W_PINV288")) == pow(E.P, -1, 1 << 288)
+    negw = words("W_NEGW")
+    want = E.Helper.bn_to_limb_le(E.Helper.integer_modulus - E.P)
+    assert [val(negw[3 * i:3 * i + 3]) for i in range(4)] == want
+    assert val(words("W_P_LIMB0")) == E.P % (1 << 68)
+    assert val(words("W_NATIVE")) == E.P % E.R
+    assert val(words("W_INV_2_136")) == pow(1 << 136, -1, E.R)
