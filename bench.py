@@ -180,6 +180,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--msm-window", type=int, default=0)
+    ap.add_argument("--parallelism", default="columns", choices=["columns", "windows"])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -214,8 +215,9 @@ def main():
     dom = EvaluationDomain(5, k, ctx)  # cs.degree() = 5 for the aggregation circuit -> extended_k = k + 2
     ext_n = dom.extended_len()
     units = schedule()
-    mine = [(i, u) for i, u in enumerate(units) if i % world == rank]  # column-parallel sharding
     rounds = sorted(set(u[0] for u in units))
+    mode = args.parallelism if world > 1 else "columns"
+    from halo2_snark_aggregator_b200 import parallel as par
 
     def dbuf(nbytes):
         return torch.empty(nbytes, dtype=torch.uint8, device=dev)
@@ -223,7 +225,14 @@ def main():
     t_bases = dbuf(n * 64)
     ctx.synth_bases_dev(SEED_BASES + k, 0, n, t_bases.data_ptr())
     srs = ctx.srs_register_dev(t_bases.data_ptr(), n)
-    msm_units = [(i, u) for i, u in mine if u[1] == "msm"]
+    table_mode, cbits, nwin = ctx.srs_config(srs)
+    win = par.window_shards(nwin, world)[rank] if mode == "windows" else None
+    # which units this rank executes
+    all_msm = [i for i, u in enumerate(units) if u[1] == "msm"]
+    my_msm = all_msm if mode == "windows" else [i for i in all_msm if i % world == rank]
+    my_ntt = [i for i, u in enumerate(units) if u[1] != "msm" and i % world == rank]
+    mine = sorted(my_msm + my_ntt)
+    msm_units = [(i, units[i]) for i in my_msm]
     t_cols = {}
     for i, u in msm_units:
         t_cols[i] = dbuf(n * 32)
@@ -235,29 +244,44 @@ def main():
     t_ext = [dbuf(ext_n * 32) for _ in range(2)]
     ctx.synth_scalars_dev(SEED_SCALARS + 99, 0, 0, ext_n, t_ext[0].data_ptr())
     ctx.synth_scalars_dev(SEED_SCALARS + 98, 0, 0, ext_n, t_ext[1].data_ptr())
-    t_out = torch.zeros(len(units) * 160, dtype=torch.uint8, device=dev)
-    per_round_max = max(sum(1 for u in units if u[0] == r and u[1] == "msm") for r in rounds)
-    t_gather = torch.zeros(world * per_round_max * 160, dtype=torch.uint8, device=dev) if world > 1 else None
+    # commit groups: the MSMs of a round that are issued together (round 3: random poly, then h pieces)
+    groups = []
+    for r in rounds:
+        ids = [i for i in my_msm if units[i][0] == r]
+        if r == 3:
+            for part in ([i for i in ids if i < 64], [i for i in ids if i >= 64]):
+                if part:
+                    groups.append((r, part))
+        elif ids:
+            groups.append((r, ids))
+    slot = {}
+    for _, ids in groups:
+        for i in ids:
+            slot[i] = len(slot)
+    t_mine = torch.zeros(max(len(slot), 1) * 160, dtype=torch.uint8, device=dev)     # my results / partials
+    per_round = {r: [i for i in all_msm if units[i][0] == r] for r in rounds}
+    per_round_max = max(max(len([i for i in v if (mode == "windows" or i % world == rr)]) for rr in range(world)) for v in per_round.values())
+    t_send = torch.zeros(per_round_max * 160, dtype=torch.uint8, device=dev)
+    t_gather = torch.zeros(world * per_round_max * 160, dtype=torch.uint8, device=dev)
+    t_final = torch.zeros(len(units) * 160, dtype=torch.uint8, device=dev)          # windows mode: combined points
     ctx.synchronize()
 
     def step_device():
         c = 0
+        issued = set()
         for r in rounds:
-            mine_r = [(i, u) for i, u in mine if u[0] == r]
-            msm_ids = [i for i, u in mine_r if u[1] == "msm"]
-            first_msm = True
-            for i, u in mine_r:
+            for i in mine:
+                u = units[i]
+                if u[0] != r:
+                    continue
                 what = u[1]
                 if what == "msm":
-                    # the round's commitments are independent: one batched call per contiguous group
-                    # (rounds 0-2, 4: one group; round 3: random poly before, h pieces after the NTTs)
-                    group = [j for j in msm_ids if (j < 64) == (i < 64)] if r == 3 else msm_ids
-                    if group and group[0] == i:
-                        if contiguous_out(group):
-                            ctx.msm_g1_batch_dev([t_cols[j].data_ptr() for j in group], n, t_out.data_ptr() + group[0] * 160, srs_id=srs)
-                        else:
-                            for j in group:
-                                ctx.msm_g1_dev(t_cols[j].data_ptr(), n, t_out.data_ptr() + j * 160, srs_id=srs)
+                    if i in issued:
+                        continue
+                    ids = next(g for rr, g in groups if i in g)
+                    issued.update(ids)
+                    ctx.msm_g1_batch_dev([t_cols[j].data_ptr() for j in ids], n, t_mine.data_ptr() + slot[ids[0]] * 160,
+                                         srs_id=srs, windows=win)
                 elif what == "intt":
                     dom.lagrange_to_coeff_dev(t_ntt[c % n_ntt_bufs].data_ptr())
                 elif what == "coset":
@@ -266,15 +290,14 @@ def main():
                     dom.extended_to_coeff_dev(t_ext[c % 2].data_ptr())
                 c += 1
             if world > 1:
-                # every rank needs every commitment of the round to drive the transcript:
-                # one all-gather of <= 14 x 160 B per commit round (EC points are not an NCCL reduce op)
-                send = torch.zeros(per_round_max * 160, dtype=torch.uint8, device=dev)
-                for slot, i in enumerate(msm_ids):
-                    send[slot * 160:(slot + 1) * 160] = t_out[i * 160:(i + 1) * 160]
-                dist.all_gather_into_tensor(t_gather, send)
-
-    def contiguous_out(group):
-        return all(b - a == 1 for a, b in zip(group, group[1:]))
+                # every rank needs every commitment of the round to drive the transcript: ONE all-gather of
+                # <= 14 x 160 B per commit round (EC points are not an NCCL reduce op -> gather + local add)
+                ids = [i for i in per_round[r] if i in slot]
+                if ids:
+                    t_send[: len(ids) * 160] = t_mine[slot[ids[0]] * 160:(slot[ids[-1]] + 1) * 160]
+                dist.all_gather_into_tensor(t_gather, t_send)
+                if mode == "windows" and ids:
+                    ctx.g1_sum_dev(t_gather.data_ptr() + 64, world, per_round_max * 160, len(ids), t_final.data_ptr() + ids[0] * 160)
 
     def barrier():
         torch.cuda.synchronize()
@@ -313,8 +336,10 @@ def main():
         def pinned(nbytes):
             return torch.empty(nbytes // 8, dtype=torch.int64).pin_memory().numpy().view(np.uint64)
 
+        e_msm = [i for i in all_msm if i % world == rank]  # e2e is always column-parallel
+        e_units = sorted(e_msm + my_ntt)
         h_cols = {}
-        for i, u in msm_units:
+        for i in e_msm:
             h_cols[i] = pinned(n * 32)
             h_cols[i][:] = ctx.d2h(t_cols[i].data_ptr(), 4 * n)
         h_ntt = [pinned(n * 32) for _ in range(2)]
@@ -323,7 +348,8 @@ def main():
         h_ext = pinned(ext_n * 32)
         h_ext[:] = ctx.d2h(t_ext[0].data_ptr(), 4 * ext_n)
         h2d = d2h = 0
-        for i, u in mine:
+        for i in e_units:
+            u = units[i]
             if u[1] == "msm":
                 h2d += n * 32; d2h += 160
             elif u[1] == "intt":
@@ -337,7 +363,7 @@ def main():
             c = 0
             outs = []
             for r in rounds:
-                mine_r = [(i, u) for i, u in mine if u[0] == r]
+                mine_r = [(i, units[i]) for i in e_units if units[i][0] == r]
                 msm_ids = [i for i, u in mine_r if u[1] == "msm"]
                 for i, u in mine_r:
                     what = u[1]
@@ -385,14 +411,15 @@ def main():
         first_of_kind = {}
         for i, u in msm_units:
             first_of_kind.setdefault(u[2], i)
-        gpu_pts = ctx.d2h(t_out.data_ptr(), 20 * len(units)).reshape(len(units), 20)
+        gpu_pts_all = ctx.d2h(t_mine.data_ptr(), 20 * len(slot)).reshape(len(slot), 20)
+        gpu_pts = {i: gpu_pts_all[slot[i]] for i in slot}
         parity = True
         for kind, i in sorted(first_of_kind.items()):
             s = ctx.d2h(t_cols[i].data_ptr(), 4 * n)
             t0 = time.perf_counter()
             want = ob.best_multiexp(s, h_bases, cores)
             per["msm%d" % kind] = time.perf_counter() - t0
-            parity = parity and bool(np.array_equal(want, gpu_pts[i, 8:]))
+            parity = parity and bool(np.array_equal(want, gpu_pts[i][8:]))
         a = ob.gen_scalars(SEED_SCALARS + 77, 0, n)
         t0 = time.perf_counter(); ob.ifft(a, d["omega_inv"], d["n_inv"], k, cores); per["intt"] = time.perf_counter() - t0
         t0 = time.perf_counter(); e = ob.coeff_to_extended(a, k, k + 2, d["zeta"], d["omega_ext"], cores); per["coset"] = time.perf_counter() - t0
@@ -415,7 +442,6 @@ def main():
         acc_ms, acc_n = ktimes["msm_accumulate"]
         ntt_ms, ntt_n = ktimes["ntt_pass"]
         msm_ms, msm_n = ktimes["msm_total"]
-        cbits, nwin = ctx.msm_config(n)
         msm_bytes = 96 * n + 96
         achieved = (msm_bytes / (acc_ms / acc_n * 1e-3) / 1e9) if acc_n else None
         sched_bytes = algorithmic_bytes(k)
@@ -427,7 +453,8 @@ def main():
             "dtype": "u256-mod-p (8x32-bit Montgomery limbs, integer)", "data": "synthetic",
             "config": {"workload": "aggregation-circuit prover schedule (SURVEY.md App. C), k=%d: 38 MSM(2^%d) + 29 iNTT(2^%d) + 29 coset-NTT(2^%d->2^%d) + 1 iNTT(2^%d)" % (k, k, k, k, k + 2, k + 2),
                        "k": k, "scalars": "witness-like mixture (SURVEY.md 8d): 5x kind1, 1x kind2, 14x 17-bit, 18x uniform Fr",
-                       "parallelism": "column-parallel over %d GPU(s), one all-gather of commitments per commit round" % world,
+                       "parallelism": ("%s over %d GPU(s), one all-gather of commitments per commit round" % ("window-sharded MSM + column-parallel NTT" if mode == "windows" else "column-parallel", world)),
+                       "msm_mode": "fixed-base table (2^(c w) P rows resident in HBM)" if table_mode else "plain",
                        "msm_window_bits": cbits, "msm_windows": nwin,
                        "l2": "inputs larger than L2 (each column is 2^%d x 32 B; SRS 2^%d x 64 B), no flush needed" % (k, k)},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clock_info,

@@ -147,9 +147,16 @@ class Context:
         self.check(self.lib.h2agg_msm_g1_batch(self.h, srs_id, arr, len(cols), n, _ptr(out)))
         return out.reshape(len(cols), 8)
 
-    def msm_g1_batch_dev(self, d_cols, n, d_out160s, d_bases=0, srs_id=0):
+    def msm_g1_batch_dev(self, d_cols, n, d_out160s, d_bases=0, srs_id=0, windows=None):
         arr = (c_vp * len(d_cols))(*d_cols)
-        self.check(self.lib.h2agg_msm_g1_batch_dev(self.h, srs_id, c_vp(d_bases), arr, len(d_cols), n, c_vp(d_out160s)))
+        if windows is None:
+            self.check(self.lib.h2agg_msm_g1_batch_dev(self.h, srs_id, c_vp(d_bases), arr, len(d_cols), n, c_vp(d_out160s)))
+        else:
+            self.check(self.lib.h2agg_msm_g1_batch_windows_dev(self.h, srs_id, c_vp(d_bases), arr, len(d_cols), n, windows[0], windows[1], c_vp(d_out160s)))
+
+    def g1_sum_dev(self, d_points, m, stride_bytes, n_out, d_out160s):
+        """out[j] = sum_i Jacobian point at d_points + i*stride + j*160 (device; combines gathered window shards)."""
+        self.check(self.lib.h2agg_g1_sum_dev(self.h, c_vp(d_points), m, stride_bytes, n_out, c_vp(d_out160s)))
 
     def g1_sum(self, points_jac):
         out = np.zeros(12, dtype=np.uint64)

@@ -371,6 +371,26 @@ int h2agg_msm_g1_batch_dev(h2agg_ctx* ctx, uint64_t srs_id, const void* d_bases_
   return msm_run_batch(ctx, d_bases, d_cols, n_cols, n, (uint8_t*)d_out160s, false);
 }
 
+int h2agg_msm_g1_batch_windows_dev(h2agg_ctx* ctx, uint64_t srs_id, const void* d_bases_in, const void* const* d_cols,
+                                   size_t n_cols, size_t n, int win_begin, int win_end, void* d_out160s) {
+  if (!ctx) return 1;
+  LOCK(ctx);
+  CHECK_ARG(ctx, d_cols && d_out160s, "msm_batch_windows_dev: null argument");
+  H2AGG_CUDA(ctx, cudaSetDevice(ctx->device));
+  MsmBases d_bases;
+  int rc = resolve_bases(ctx, srs_id, nullptr, d_bases_in, n, &d_bases);
+  if (rc) return rc;
+  return msm_run_batch(ctx, d_bases, d_cols, n_cols, n, (uint8_t*)d_out160s, false, win_begin, win_end);
+}
+
+int h2agg_g1_sum_dev(h2agg_ctx* ctx, const void* d_points, size_t m, size_t stride_bytes, size_t n_out, void* d_out160s) {
+  if (!ctx) return 1;
+  LOCK(ctx);
+  CHECK_ARG(ctx, d_points && d_out160s && m > 0 && n_out > 0, "g1_sum_dev: bad argument");
+  H2AGG_CUDA(ctx, cudaSetDevice(ctx->device));
+  return g1_sum_jacobian(ctx, d_points, m, d_out160s, stride_bytes, n_out);
+}
+
 int h2agg_g1_sum(h2agg_ctx* ctx, const uint64_t* pts, size_t m, uint64_t out_jacobian[12]) {
   if (!ctx) return 1;
   LOCK(ctx);

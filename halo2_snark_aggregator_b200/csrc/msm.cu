@@ -360,12 +360,16 @@ __global__ void msm_final(const uint8_t* __restrict__ wsum_c, MsmGeom g, uint8_t
   write_out160(acc, out160);
 }
 
-__global__ void g1_sum_kernel(const uint8_t* __restrict__ pts96, uint32_t m, uint8_t* out160) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// one thread per output: out[j] = sum_i point(i, j); point(i, j) at pts + i * stride + j * 160 (Jacobian, 96 B)
+__global__ void g1_sum_kernel(const uint8_t* __restrict__ pts, uint32_t m, size_t stride, uint32_t n_out, uint8_t* out160) {
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_out) return;
+  const uint8_t* pts96 = pts + (size_t)j * 160;
+  out160 += (size_t)j * 160;
   G1Xyzz acc = G1Xyzz::identity();
   for (uint32_t i = 0; i < m; i++) {
-    Fq x = Fq::load(pts96 + (size_t)i * 96), y = Fq::load(pts96 + (size_t)i * 96 + 32),
-       z = Fq::load(pts96 + (size_t)i * 96 + 64);
+    Fq x = Fq::load(pts96 + (size_t)i * stride), y = Fq::load(pts96 + (size_t)i * stride + 32),
+       z = Fq::load(pts96 + (size_t)i * stride + 64);
     if (z.is_zero()) continue;
     G1Xyzz p;  // general Jacobian -> XYZZ: (X, Y, Z^2, Z^3)
     p.x = x; p.y = y; p.zz = fp_sqr(z); p.zzz = p.zz * z;
@@ -374,8 +378,9 @@ __global__ void g1_sum_kernel(const uint8_t* __restrict__ pts96, uint32_t m, uin
   write_out160(acc, out160);
 }
 
-int g1_sum_jacobian(h2agg_ctx* ctx, const void* d_points96, size_t m, void* d_out160) {
-  g1_sum_kernel<<<1, 32, 0, ctx->stream>>>((const uint8_t*)d_points96, (uint32_t)m, (uint8_t*)d_out160);
+int g1_sum_jacobian(h2agg_ctx* ctx, const void* d_points96, size_t m, void* d_out160, size_t stride, size_t n_out) {
+  g1_sum_kernel<<<(unsigned)((n_out + 31) / 32), 32, 0, ctx->stream>>>((const uint8_t*)d_points96, (uint32_t)m, stride,
+                                                                     (uint32_t)n_out, (uint8_t*)d_out160);
   ctx->launches++;
   H2AGG_CUDA(ctx, cudaGetLastError());
   return 0;
@@ -465,10 +470,11 @@ int lanes_init(h2agg_ctx* ctx) {
 }
 
 int msm_run_batch(h2agg_ctx* ctx, const MsmBases& bases, const void* const* cols, size_t n_cols, size_t n,
-                  uint8_t* d_out160s, bool host_cols) {
+                  uint8_t* d_out160s, bool host_cols, int win_begin, int win_end) {
   if (n_cols == 0) return 0;
   int rc;
-  if (n_cols == 1 && !host_cols) return msm_run(ctx, ctx->stream, ctx->msm_ws, bases, cols[0], n, d_out160s, 0, -1);
+  if (n_cols == 1 && !host_cols)
+    return msm_run(ctx, ctx->stream, ctx->msm_ws, bases, cols[0], n, d_out160s, win_begin, win_end);
   if ((rc = lanes_init(ctx))) return rc;
   H2AGG_CUDA(ctx, cudaEventRecord(ctx->fork_ev, ctx->stream));
   for (int l = 0; l < N_LANES; l++) H2AGG_CUDA(ctx, cudaStreamWaitEvent(ctx->lanes[l].st, ctx->fork_ev, 0));
@@ -480,7 +486,7 @@ int msm_run_batch(h2agg_ctx* ctx, const MsmBases& bases, const void* const* cols
       if (n) H2AGG_CUDA(ctx, cudaMemcpyAsync(ln.io.p, cols[i], n * 32, cudaMemcpyHostToDevice, ln.st));
       d_col = ln.io.p;
     }
-    if ((rc = msm_run(ctx, ln.st, ln.ws, bases, d_col, n, d_out160s + i * 160, 0, -1))) return rc;
+    if ((rc = msm_run(ctx, ln.st, ln.ws, bases, d_col, n, d_out160s + i * 160, win_begin, win_end))) return rc;
   }
   for (int l = 0; l < N_LANES; l++) {
     H2AGG_CUDA(ctx, cudaEventRecord(ctx->lanes[l].done, ctx->lanes[l].st));

@@ -1,0 +1,44 @@
+"""Multi-GPU host logic: one process per GPU, torch.distributed for the plumbing.
+
+The path shards without a data-path exchange; the only collective is an all-gather of the
+commitments (64-byte affine + 96-byte Jacobian = 160 B each) per commit round so every rank can
+drive the Fiat-Shamir transcript.  EC addition is not an NCCL reduction operator, so combining
+window-sharded partial MSMs is all-gather + a local add (`h2agg_g1_sum`), never all-reduce."""
+
+
+def shard_units(n_units, world, rank):
+    """Column-parallel sharding (8e-1): unit i belongs to rank i % world."""
+    return [i for i in range(n_units) if i % world == rank]
+
+
+def window_shards(n_windows, world):
+    """Window-sharded MSM (8e-2): contiguous window ranges [begin, end) per rank, covering all windows."""
+    return [(n_windows * g // world, n_windows * (g + 1) // world) for g in range(world)]
+
+
+def gather_round(dist, torch, local, slots, world, device):
+    """All-gather one commit round.
+
+    local: {unit index -> uint8 tensor of 160 bytes (on `device`)} computed by this rank;
+    slots: the maximum number of units any rank owns in this round.
+    Returns {unit index -> 160-byte tensor} for ALL units of the round, identical on every rank.
+    Message layout per rank: slots x (8-byte little-endian unit index + 1, 160-byte point)."""
+    rec = 168
+    send = torch.zeros(slots * rec, dtype=torch.uint8, device=device)
+    for slot, (idx, pt) in enumerate(sorted(local.items())):
+        tag = torch.tensor([(idx + 1 >> (8 * b)) & 0xFF for b in range(8)], dtype=torch.uint8, device=device)
+        send[slot * rec:slot * rec + 8] = tag
+        send[slot * rec + 8:(slot + 1) * rec] = pt
+    if world == 1:
+        recv = send
+    else:
+        recv = torch.empty(world * slots * rec, dtype=torch.uint8, device=device)
+        dist.all_gather_into_tensor(recv, send)
+    out = {}
+    flat = recv.cpu()
+    for k in range(world * slots):
+        chunk = flat[k * rec:(k + 1) * rec]
+        tag = int.from_bytes(bytes(chunk[:8].tolist()), "little")
+        if tag:
+            out[tag - 1] = chunk[8:]
+    return out

@@ -100,6 +100,12 @@ int h2agg_msm_g1_windows(h2agg_ctx* ctx, uint64_t srs_id, const uint64_t* bases_
                          size_t n, int win_begin, int win_end, uint64_t out_jacobian[12]);
 int h2agg_msm_g1_windows_dev(h2agg_ctx* ctx, uint64_t srs_id, const void* d_bases_affine, const void* d_scalars,
                              size_t n, int win_begin, int win_end, void* d_out160);
+int h2agg_msm_g1_batch_windows_dev(h2agg_ctx* ctx, uint64_t srs_id, const void* d_bases_affine,
+                                   const void* const* d_scalar_cols, size_t n_cols, size_t n, int win_begin, int win_end,
+                                   void* d_out160s);
+/* Device-side combine of all-gathered partials: out[j] = sum_{i<m} P(i, j), the Jacobian point P(i, j)
+ * living at d_points + i * stride_bytes + j * 160; writes n_out x 160 B (affine + Jacobian). */
+int h2agg_g1_sum_dev(h2agg_ctx* ctx, const void* d_points, size_t m, size_t stride_bytes, size_t n_out, void* d_out160s);
 /* Sum of m Jacobian points (96 B each; the all-gathered shard partials) -> normalised Jacobian. */
 int h2agg_g1_sum(h2agg_ctx* ctx, const uint64_t* points_jacobian /* m*12 */, size_t m, uint64_t out_jacobian[12]);
 
