@@ -170,6 +170,15 @@ class Context:
     def intt_fr(self, a, omega_inv, n_inv, log_n):
         self.check(self.lib.h2agg_intt_fr(self.h, _ptr(a), _ptr(omega_inv), _ptr(n_inv), log_n))
 
+    def intt_fr_batch(self, cols, omega_inv, n_inv, log_n):
+        arr = (c_vp * len(cols))(*[c.ctypes.data for c in cols])
+        self.check(self.lib.h2agg_intt_fr_batch(self.h, arr, len(cols), _ptr(omega_inv), _ptr(n_inv), log_n))
+
+    def coeff_to_extended_batch(self, coeff_cols, out_cols, k, ext_k, zeta, omega_ext):
+        a = (c_vp * len(coeff_cols))(*[c.ctypes.data for c in coeff_cols])
+        b = (c_vp * len(out_cols))(*[c.ctypes.data for c in out_cols])
+        self.check(self.lib.h2agg_coeff_to_extended_batch(self.h, a, b, len(coeff_cols), k, ext_k, _ptr(zeta), _ptr(omega_ext)))
+
     def ntt_fr_dev(self, d_a, omega, log_n, scale=None):
         self.check(self.lib.h2agg_ntt_fr_dev(self.h, c_vp(d_a), _ptr(omega), _ptr(scale), log_n))
 

@@ -97,6 +97,8 @@ void h2agg_destroy(h2agg_ctx* ctx) {
     if (ctx->lanes[i].st) cudaStreamSynchronize(ctx->lanes[i].st);
     cudaFree(ctx->lanes[i].ws.p);
     cudaFree(ctx->lanes[i].io.p);
+    cudaFree(ctx->lanes[i].io_out.p);
+    cudaFree(ctx->lanes[i].ntt_tmp.p);
     if (ctx->lanes[i].done) cudaEventDestroy(ctx->lanes[i].done);
     if (ctx->lanes[i].st) cudaStreamDestroy(ctx->lanes[i].st);
   }
@@ -458,6 +460,60 @@ int h2agg_ntt_fr_dev(h2agg_ctx* ctx, void* d_a, const uint64_t omega[4], const u
   return ntt_run(ctx, d_a, d_a, o);
 }
 
+// Batched host-pointer transforms: column i runs on lane i % N_LANES, so the H2D copy of column i+1,
+// the passes of column i and the D2H copy of column i-1 overlap (PCIe is full duplex).
+// in_n / out_n elements per column; src/dst host pointers (dst may equal src).
+static int ntt_host_batch(h2agg_ctx* ctx, const uint64_t* const* src, uint64_t* const* dst, size_t n_cols, size_t in_n,
+                          size_t out_n, NttOpts o) {
+  H2AGG_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc = lanes_init(ctx);
+  if (rc) return rc;
+  const size_t N = (size_t)1 << o.log_n;
+  // twiddle tables are created on the main stream before the lanes fork
+  o.src_n = in_n;
+  o.dst_n = out_n;
+  H2AGG_CUDA(ctx, cudaEventRecord(ctx->fork_ev, ctx->stream));
+  for (int l = 0; l < N_LANES; l++) H2AGG_CUDA(ctx, cudaStreamWaitEvent(ctx->lanes[l].st, ctx->fork_ev, 0));
+  bool tables_ready = false;
+  for (size_t i = 0; i < n_cols; i++) {
+    Lane& ln = ctx->lanes[i % N_LANES];
+    if ((rc = ensure(ctx, ln.io, in_n * 32))) return rc;
+    if ((rc = ensure(ctx, ln.io_out, N * 32))) return rc;
+    H2AGG_CUDA(ctx, cudaMemcpyAsync(ln.io.p, src[i], in_n * 32, cudaMemcpyHostToDevice, ln.st));
+    if (!tables_ready) {
+      // first column: run on the main stream so the (cached) table generation is ordered before every lane
+      H2AGG_CUDA(ctx, cudaEventRecord(ln.done, ln.st));
+      H2AGG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ln.done, 0));
+      if ((rc = ntt_run(ctx, ln.io.p, ln.io_out.p, o, ctx->stream, &ln.ntt_tmp))) return rc;
+      H2AGG_CUDA(ctx, cudaEventRecord(ctx->fork_ev, ctx->stream));
+      for (int l = 0; l < N_LANES; l++) H2AGG_CUDA(ctx, cudaStreamWaitEvent(ctx->lanes[l].st, ctx->fork_ev, 0));
+      tables_ready = true;
+    } else {
+      if ((rc = ntt_run(ctx, ln.io.p, ln.io_out.p, o, ln.st, &ln.ntt_tmp))) return rc;
+    }
+    H2AGG_CUDA(ctx, cudaMemcpyAsync(dst[i], ln.io_out.p, out_n * 32, cudaMemcpyDeviceToHost, ln.st));
+  }
+  for (int l = 0; l < N_LANES; l++) {
+    H2AGG_CUDA(ctx, cudaEventRecord(ctx->lanes[l].done, ctx->lanes[l].st));
+    H2AGG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->lanes[l].done, 0));
+  }
+  H2AGG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int h2agg_intt_fr_batch(h2agg_ctx* ctx, uint64_t* const* cols, size_t n_cols, const uint64_t omega_inv[4],
+                        const uint64_t n_inv[4], uint32_t log_n) {
+  if (!ctx) return 1;
+  LOCK(ctx);
+  CHECK_ARG(ctx, cols && omega_inv && n_inv, "intt_batch: null argument");
+  CHECK_ARG(ctx, log_n >= 1 && log_n <= 28, "intt_batch: log_n out of range");
+  uint64_t s3[12];
+  for (int i = 0; i < 3; i++) memcpy(s3 + 4 * i, n_inv, 32);
+  NttOpts o{omega_inv, log_n, 0, 0, nullptr, s3};
+  size_t N = (size_t)1 << log_n;
+  return ntt_host_batch(ctx, (const uint64_t* const*)cols, cols, n_cols, N, N, o);
+}
+
 // Montgomery products of a handful of field elements on the device (zeta powers etc.)
 __global__ void coset_consts_kernel(Fr zeta, Fr scale, int inverse, Fr* out3) {
   if (threadIdx.x || blockIdx.x) return;
@@ -513,6 +569,21 @@ int h2agg_coeff_to_extended(h2agg_ctx* ctx, const uint64_t* coeffs, uint32_t k, 
   if (rc) return rc;
   NttOpts o{omega_ext, ext_k, 0, 0, in3, nullptr};
   return ntt_host(ctx, coeffs, (size_t)1 << k, out, (size_t)1 << ext_k, o);
+}
+
+int h2agg_coeff_to_extended_batch(h2agg_ctx* ctx, const uint64_t* const* coeff_cols, uint64_t* const* out_cols,
+                                  size_t n_cols, uint32_t k, uint32_t ext_k, const uint64_t zeta[4],
+                                  const uint64_t omega_ext[4]) {
+  if (!ctx) return 1;
+  LOCK(ctx);
+  CHECK_ARG(ctx, coeff_cols && out_cols && zeta && omega_ext, "coeff_to_extended_batch: null argument");
+  CHECK_ARG(ctx, ext_k >= k && ext_k >= 1 && ext_k <= 28, "coeff_to_extended_batch: bad k / ext_k");
+  H2AGG_CUDA(ctx, cudaSetDevice(ctx->device));
+  uint64_t in3[12];
+  int rc = coset_consts(ctx, zeta, nullptr, 0, in3);
+  if (rc) return rc;
+  NttOpts o{omega_ext, ext_k, 0, 0, in3, nullptr};
+  return ntt_host_batch(ctx, coeff_cols, out_cols, n_cols, (size_t)1 << k, (size_t)1 << ext_k, o);
 }
 
 int h2agg_extended_to_coeff_dev(h2agg_ctx* ctx, void* d_a, uint32_t ext_k, const uint64_t omega_ext_inv[4],

@@ -47,9 +47,11 @@ struct Lane {
   cudaStream_t st = nullptr;
   DevBuf ws;        // MSM workspace
   DevBuf io;        // staging for host-pointer batches
+  DevBuf io_out;    // NTT batches: result staging (coset transforms are out of place)
+  DevBuf ntt_tmp;   // NTT ping-pong buffer of this lane
   cudaEvent_t done = nullptr;
 };
-static constexpr int N_LANES = 2;
+static constexpr int N_LANES = 3;
 
 }  // namespace h2agg
 
@@ -151,7 +153,8 @@ struct NttOpts {
   const uint64_t* in_coset3;        // host, 3x4 limbs: multiply input i by in_coset3[i%3]   (or null)
   const uint64_t* out_scale3;       // host, 3x4 limbs: multiply output i by out_scale3[i%3] (or null)
 };
-int ntt_run(h2agg_ctx* ctx, const void* d_src, void* d_dst, const NttOpts& o);
+int ntt_run(h2agg_ctx* ctx, const void* d_src, void* d_dst, const NttOpts& o, cudaStream_t st = nullptr,
+            DevBuf* tmp = nullptr);
 
 // MSM over G1: d_scalars n x 32 B (Montgomery Fr), d_bases n x 64 B affine.
 // Writes affine (64 B) + jacobian (96 B, z = 1 or 0) to d_out (160 B, device).

@@ -95,6 +95,10 @@ __device__ __forceinline__ int32_t take_digit(const uint32_t* v, uint32_t w, uin
   return (int32_t)raw;
 }
 
+// Digits are produced in groups of DG windows: all DG atomics of a group are issued before any of
+// their results is consumed, so a thread keeps DG L2 round trips in flight instead of one.
+static constexpr int DG = 8;
+
 template <bool SCATTER>
 __global__ void __launch_bounds__(256) msm_digits(const uint4* __restrict__ scalars, MsmGeom g,
                                                    uint32_t* __restrict__ counts_or_cursor,
@@ -107,17 +111,28 @@ __global__ void __launch_bounds__(256) msm_digits(const uint4* __restrict__ scal
 #pragma unroll
     for (int k = 0; k < 8; k++) v[k] = s.v[k];
     uint32_t carry = 0;
-    for (uint32_t w = 0; w < g.nwin; w++) {
-      int32_t d = take_digit(v, w, g.c, carry);
-      if (d == 0 || w < g.win_begin || w >= g.win_end) continue;
-      uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
-      uint32_t key = (g.table ? 0u : w * g.bpw) + (mag - 1);
+    for (uint32_t w0 = 0; w0 < g.nwin; w0 += DG) {
+      uint32_t key[DG], val[DG], pos[DG];
+#pragma unroll
+      for (int j = 0; j < DG; j++) {
+        uint32_t w = w0 + j;
+        key[j] = 0xffffffffu;
+        if (w < g.nwin) {
+          int32_t d = take_digit(v, w, g.c, carry);
+          if (d != 0 && w >= g.win_begin && w < g.win_end) {
+            uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+            key[j] = (g.table ? 0u : w * g.bpw) + (mag - 1);
+            val[j] = (g.table ? (w * g.srs_n + i) : i) | (d < 0 ? 0x80000000u : 0u);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < DG; j++)
+        if (key[j] != 0xffffffffu) pos[j] = atomicAdd(counts_or_cursor + key[j], 1u);
       if (SCATTER) {
-        uint32_t pos = atomicAdd(counts_or_cursor + key, 1u);
-        uint32_t idx = g.table ? (w * g.srs_n + i) : i;
-        entries[pos] = idx | (d < 0 ? 0x80000000u : 0u);
-      } else {
-        atomicAdd(counts_or_cursor + key, 1u);
+#pragma unroll
+        for (int j = 0; j < DG; j++)
+          if (key[j] != 0xffffffffu) entries[pos[j]] = val[j];
       }
     }
   }

@@ -282,7 +282,9 @@ int plan_passes(uint32_t log_n, uint32_t* s) {
   return T;
 }
 
-int ntt_run(h2agg_ctx* ctx, const void* d_src, void* d_dst, const NttOpts& o) {
+int ntt_run(h2agg_ctx* ctx, const void* d_src, void* d_dst, const NttOpts& o, cudaStream_t st_in, DevBuf* tmpbuf_in) {
+  cudaStream_t st = st_in ? st_in : ctx->stream;
+  DevBuf& tmpbuf = tmpbuf_in ? *tmpbuf_in : ctx->ntt_tmp;
   if (o.log_n > 28) {
     ctx->last_error = "ntt: log_n exceeds the 2-adicity of BN254 Fr (28)";
     return 1;
@@ -293,7 +295,7 @@ int ntt_run(h2agg_ctx* ctx, const void* d_src, void* d_dst, const NttOpts& o) {
     return 1;
   }
   if (o.log_n == 0) {
-    if (d_src != d_dst && o.dst_n) H2AGG_CUDA(ctx, cudaMemcpyAsync(d_dst, d_src, 32, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (d_src != d_dst && o.dst_n) H2AGG_CUDA(ctx, cudaMemcpyAsync(d_dst, d_src, 32, cudaMemcpyDeviceToDevice, st));
     if (o.out_scale3 || o.in_coset3) {
       // a 1-point transform is the identity; scaling a single element is not needed by any caller
       if (o.out_scale3) {
@@ -312,9 +314,9 @@ int ntt_run(h2agg_ctx* ctx, const void* d_src, void* d_dst, const NttOpts& o) {
   const void* cur = d_src;
   void* tmp = nullptr;
   if (T > 1) {
-    rc = ensure(ctx, ctx->ntt_tmp, N * 32);
+    rc = ensure(ctx, tmpbuf, N * 32);
     if (rc) return rc;
-    tmp = ctx->ntt_tmp.p;
+    tmp = tmpbuf.p;
   }
   static bool attr_set = false;
   if (!attr_set) {
@@ -353,7 +355,7 @@ int ntt_run(h2agg_ctx* ctx, const void* d_src, void* d_dst, const NttOpts& o) {
       a.has_out = 1;
       memcpy(a.out3, o.out_scale3, 96);
     }
-    ScopedKernelTimer tk(ctx, KC_NTT_PASS);
+    ScopedKernelTimer tk(ctx, KC_NTT_PASS, st);
     uint32_t cb = NTT_TILE_LOG - s[t];
     size_t smem;
     unsigned long long tiles;
@@ -362,7 +364,7 @@ int ntt_run(h2agg_ctx* ctx, const void* d_src, void* d_dst, const NttOpts& o) {
       a.cbits = cb;
       tiles = (unsigned long long)N >> (s[t] + cb);
       smem = ((size_t)2 << (s[t] + cb)) * 16 + ((size_t)1 << s[t]) * 16;
-      ntt_pass_kernel<false><<<(unsigned)tiles, NTT_THREADS, smem, ctx->stream>>>(a);
+      ntt_pass_kernel<false><<<(unsigned)tiles, NTT_THREADS, smem, st>>>(a);
     } else {
       a.log_r1 = (T == 1) ? 0 : s[0];
       if (cb > a.log_r1) cb = a.log_r1;
@@ -372,7 +374,7 @@ int ntt_run(h2agg_ctx* ctx, const void* d_src, void* d_dst, const NttOpts& o) {
       for (uint32_t i = 0; i < a.nmid; i++) a.mid_log[i] = s[1 + i];
       tiles = (unsigned long long)N >> (s[t] + cb);
       smem = ((size_t)2 << cb) * (((size_t)1 << s[t]) + 1) * 16 + ((size_t)1 << s[t]) * 16;
-      ntt_pass_kernel<true><<<(unsigned)tiles, NTT_THREADS, smem, ctx->stream>>>(a);
+      ntt_pass_kernel<true><<<(unsigned)tiles, NTT_THREADS, smem, st>>>(a);
     }
     ctx->launches++;
     H2AGG_CUDA(ctx, cudaGetLastError());

@@ -56,6 +56,13 @@ class EvaluationDomain:
         return self.ctx.extended_to_coeff(a, self.extended_k, self.extended_omega_inv, self.extended_ifft_divisor,
                                           self.g_coset, self.n * self.quotient_poly_degree)
 
+    # a whole round at once (pipelined over the context's lanes)
+    def lagrange_to_coeff_many(self, cols):
+        self.ctx.intt_fr_batch(cols, self.omega_inv, self.ifft_divisor, self.k)
+
+    def coeff_to_extended_many(self, cols, outs):
+        self.ctx.coeff_to_extended_batch(cols, outs, self.k, self.extended_k, self.g_coset, self.extended_omega)
+
     # device-resident forms (asynchronous on the context's stream)
     def lagrange_to_coeff_dev(self, d_a):
         self.ctx.ntt_fr_dev(d_a, self.omega_inv, self.k, scale=self.ifft_divisor)

@@ -114,6 +114,10 @@ int h2agg_g1_sum(h2agg_ctx* ctx, const uint64_t* points_jacobian /* m*12 */, siz
 int h2agg_ntt_fr(h2agg_ctx* ctx, uint64_t* a /* 2^log_n * 4 */, const uint64_t omega[4], uint32_t log_n);
 /* EvaluationDomain::ifft / lagrange_to_coeff: best_fft(a, omega_inv) then * n_inv (= ifft_divisor). */
 int h2agg_intt_fr(h2agg_ctx* ctx, uint64_t* a, const uint64_t omega_inv[4], const uint64_t n_inv[4], uint32_t log_n);
+/* A round of inverse transforms (one per committed column), in place, pipelined over the context's
+ * lanes: H2D of column i+1, the passes of column i and D2H of column i-1 overlap. */
+int h2agg_intt_fr_batch(h2agg_ctx* ctx, uint64_t* const* cols, size_t n_cols, const uint64_t omega_inv[4],
+                        const uint64_t n_inv[4], uint32_t log_n);
 /* Device-resident, asynchronous; scale may be NULL. d_a in place. */
 int h2agg_ntt_fr_dev(h2agg_ctx* ctx, void* d_a, const uint64_t omega[4], const uint64_t* scale /* 4 or NULL */,
                      uint32_t log_n);
@@ -127,6 +131,9 @@ int h2agg_coeff_to_extended(h2agg_ctx* ctx, const uint64_t* coeffs /* 2^k * 4 */
 int h2agg_extended_to_coeff(h2agg_ctx* ctx, uint64_t* a /* 2^ext_k * 4, in place */, uint32_t ext_k,
                             const uint64_t omega_ext_inv[4], const uint64_t ext_n_inv[4], const uint64_t zeta[4],
                             size_t out_len);
+int h2agg_coeff_to_extended_batch(h2agg_ctx* ctx, const uint64_t* const* coeff_cols, uint64_t* const* out_cols,
+                                  size_t n_cols, uint32_t k, uint32_t ext_k, const uint64_t zeta[4],
+                                  const uint64_t omega_ext[4]);
 int h2agg_coeff_to_extended_dev(h2agg_ctx* ctx, const void* d_coeffs, uint32_t k, uint32_t ext_k,
                                 const uint64_t zeta[4], const uint64_t omega_ext[4], void* d_out);
 int h2agg_extended_to_coeff_dev(h2agg_ctx* ctx, void* d_a, uint32_t ext_k, const uint64_t omega_ext_inv[4],

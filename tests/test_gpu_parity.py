@@ -287,3 +287,20 @@ def test_msm_batch_dev_lanes(ctx):
     finally:
         for d in d_cols + [d_b, d_o]:
             ctx.dev_free(d)
+
+
+def test_ntt_host_batches_pipelined(ctx):
+    """h2agg_intt_fr_batch / h2agg_coeff_to_extended_batch (lanes) == per-column calls == oracle."""
+    k = 14
+    d = domain_consts(k)
+    cols = [ob.gen_scalars(700 + i, 0, 1 << k) for i in range(7)]
+    want = [ob.ifft(c.copy(), d["omega_inv"], d["n_inv"], k) for c in cols]
+    for _ in range(2):
+        work = [c.copy() for c in cols]
+        ctx.intt_fr_batch(work, d["omega_inv"], d["n_inv"], k)
+        for w, x in zip(want, work):
+            assert np.array_equal(w, x)
+    outs = [np.empty(4 << (k + 2), dtype=np.uint64) for _ in cols]
+    ctx.coeff_to_extended_batch(want, outs, k, k + 2, d["zeta"], d["omega_ext"])
+    for c, o in zip(want, outs):
+        assert np.array_equal(o, ob.coeff_to_extended(c, k, k + 2, d["zeta"], d["omega_ext"]))
