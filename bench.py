@@ -181,7 +181,7 @@ def main():
     ap.add_argument("--no-witness", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--msm-window", type=int, default=0)
-    ap.add_argument("--parallelism", default="columns", choices=["columns", "windows"])
+    ap.add_argument("--parallelism", default="auto", choices=["auto", "columns", "windows"])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -216,8 +216,8 @@ def main():
     dom = EvaluationDomain(5, k, ctx)  # cs.degree() = 5 for the aggregation circuit -> extended_k = k + 2
     ext_n = dom.extended_len()
     units = schedule()
-    rounds = sorted(set(u[0] for u in units))
     mode = args.parallelism if world > 1 else "columns"
+    rounds = sorted(set(u[0] for u in schedule()))
     from halo2_snark_aggregator_b200 import parallel as par
 
     def dbuf(nbytes):
@@ -227,13 +227,36 @@ def main():
     ctx.synth_bases_dev(SEED_BASES + k, 0, n, t_bases.data_ptr())
     srs = ctx.srs_register_dev(t_bases.data_ptr(), n)
     table_mode, cbits, nwin = ctx.srs_config(srs)
-    win = par.window_shards(nwin, world)[rank] if mode == "windows" else None
-    # which units this rank executes
-    all_msm = [i for i, u in enumerate(units) if u[1] == "msm"]
-    my_msm = all_msm if mode == "windows" else [i for i in all_msm if i % world == rank]
-    my_ntt = [i for i, u in enumerate(units) if u[1] != "msm" and i % world == rank]
-    mine = sorted(my_msm + my_ntt)
+
+    # ---- phases: groups of independent units; commitments are gathered after every phase that has MSMs.
+    # Round 3 has internal dependencies: (random poly commit + 29 coset NTTs) -> iNTT(4n) -> 4 h-piece commits.
+    phases = []
+    for r in sorted(set(u[0] for u in units)):
+        ids = [i for i, u in enumerate(units) if u[0] == r]
+        if r == 3:
+            phases.append([i for i in ids if units[i][1] == "coset" or (units[i][1] == "msm" and i < 64)])
+            phases.append([i for i in ids if units[i][1] == "ext_intt"])
+            phases.append([i for i in ids if units[i][1] == "msm" and i >= 64])
+        else:
+            phases.append(ids)
+    # measured single-GPU costs (ms) drive the balance
+    COST = {("msm", 0): 12.5, ("msm", 1): 2.6, ("msm", 2): 6.0, ("msm", 3): 2.6, ("intt", 0): 1.1, ("coset", 0): 4.0, ("ext_intt", 0): 4.4}
+    plan = []  # per phase: [(unit, rank, windows)]
+    for ids in phases:
+        mc = {i: COST[(units[i][1], units[i][2])] for i in ids if units[i][1] == "msm"}
+        oc = {i: COST[(units[i][1], units[i][2])] for i in ids if units[i][1] != "msm"}
+        if mode == "auto":
+            plan.append(par.plan_phase(mc, oc, world, nwin))
+        elif mode == "windows":
+            shards = par.window_shards(nwin, world)
+            plan.append([(i, rk, shards[rk]) for i in mc for rk in range(world) if shards[rk][1] > shards[rk][0]] +
+                        [(i, i % world, None) for i in oc])
+        else:
+            plan.append([(i, i % world, None) for i in ids])
+    my_msm = sorted(set(u for ph in plan for (u, rk, w) in ph if rk == rank and units[u][1] == "msm"))
     msm_units = [(i, units[i]) for i in my_msm]
+    all_msm = [i for i, u in enumerate(units) if u[1] == "msm"]
+    my_ntt = sorted(set(u for ph in plan for (u, rk, w) in ph if rk == rank and units[u][1] != "msm"))
     t_cols = {}
     for i, u in msm_units:
         t_cols[i] = dbuf(n * 32)
@@ -245,60 +268,64 @@ def main():
     t_ext = [dbuf(ext_n * 32) for _ in range(2)]
     ctx.synth_scalars_dev(SEED_SCALARS + 99, 0, 0, ext_n, t_ext[0].data_ptr())
     ctx.synth_scalars_dev(SEED_SCALARS + 98, 0, 0, ext_n, t_ext[1].data_ptr())
-    # commit groups: the MSMs of a round that are issued together (round 3: random poly, then h pieces)
-    groups = []
-    for r in rounds:
-        ids = [i for i in my_msm if units[i][0] == r]
-        if r == 3:
-            for part in ([i for i in ids if i < 64], [i for i in ids if i >= 64]):
-                if part:
-                    groups.append((r, part))
-        elif ids:
-            groups.append((r, ids))
-    slot = {}
-    for _, ids in groups:
-        for i in ids:
-            slot[i] = len(slot)
-    t_mine = torch.zeros(max(len(slot), 1) * 160, dtype=torch.uint8, device=dev)     # my results / partials
-    per_round = {r: [i for i in all_msm if units[i][0] == r] for r in rounds}
-    per_round_max = max(max(len([i for i in v if (mode == "windows" or i % world == rr)]) for rr in range(world)) for v in per_round.values())
-    t_send = torch.zeros(per_round_max * 160, dtype=torch.uint8, device=dev)
-    t_gather = torch.zeros(world * per_round_max * 160, dtype=torch.uint8, device=dev)
-    t_final = torch.zeros(len(units) * 160, dtype=torch.uint8, device=dev)          # windows mode: combined points
+    # per phase: my MSM calls grouped by window range (one batched call each) + the slot every MSM owns in the gather
+    phase_msms = [[i for i in ids if units[i][1] == "msm"] for ids in phases]
+    slots_max = max(len(x) for x in phase_msms)
+    t_send = torch.zeros(slots_max * 160, dtype=torch.uint8, device=dev)
+    t_gather = torch.zeros(world * slots_max * 160, dtype=torch.uint8, device=dev)
+    t_final = torch.zeros(len(units) * 160, dtype=torch.uint8, device=dev)   # every commitment, on every rank
+    t_stage = torch.zeros(slots_max * 160, dtype=torch.uint8, device=dev)
+    my_calls = []
+    for p_i, ph in enumerate(plan):
+        by_win = {}
+        for (u, rk, w) in ph:
+            if rk == rank and units[u][1] == "msm":
+                by_win.setdefault(w, []).append(u)
+        calls = []
+        for w, us in sorted(by_win.items(), key=lambda kv: (kv[0] is not None, kv[0] or (0, 0))):
+            us = sorted(us)
+            idx = torch.tensor([phase_msms[p_i].index(u) for u in us], dtype=torch.long, device=dev)
+            calls.append((w, us, idx))
+        my_calls.append(calls)
     ctx.synchronize()
 
     def step_device():
         c = 0
-        issued = set()
-        for r in rounds:
-            for i in mine:
-                u = units[i]
-                if u[0] != r:
+        for p_i, ph in enumerate(plan):
+            nm = len(phase_msms[p_i])
+            if nm and world > 1:
+                t_send.zero_()
+            for (w, us, idx) in my_calls[p_i]:
+                dst = t_final.data_ptr() + us[0] * 160 if (world == 1 and all(b - a == 1 for a, b in zip(us, us[1:]))) else t_stage.data_ptr()
+                ctx.msm_g1_batch_dev([t_cols[j].data_ptr() for j in us], n, dst, srs_id=srs, windows=w)
+                if world > 1:
+                    t_send.view(-1, 160)[idx] = t_stage.view(-1, 160)[: len(us)]
+                elif dst == t_stage.data_ptr():
+                    for q, j in enumerate(us):
+                        t_final[j * 160:(j + 1) * 160] = t_stage[q * 160:(q + 1) * 160]
+            for (u, rk, w) in ph:
+                if rk != rank or units[u][1] == "msm":
                     continue
-                what = u[1]
-                if what == "msm":
-                    if i in issued:
-                        continue
-                    ids = next(g for rr, g in groups if i in g)
-                    issued.update(ids)
-                    ctx.msm_g1_batch_dev([t_cols[j].data_ptr() for j in ids], n, t_mine.data_ptr() + slot[ids[0]] * 160,
-                                         srs_id=srs, windows=win)
-                elif what == "intt":
+                what = units[u][1]
+                if what == "intt":
                     dom.lagrange_to_coeff_dev(t_ntt[c % n_ntt_bufs].data_ptr())
                 elif what == "coset":
                     dom.coeff_to_extended_dev(t_ntt[c % n_ntt_bufs].data_ptr(), t_ext[c % 2].data_ptr())
                 else:
                     dom.extended_to_coeff_dev(t_ext[c % 2].data_ptr())
                 c += 1
-            if world > 1:
-                # every rank needs every commitment of the round to drive the transcript: ONE all-gather of
-                # <= 14 x 160 B per commit round (EC points are not an NCCL reduce op -> gather + local add)
-                ids = [i for i in per_round[r] if i in slot]
-                if ids:
-                    t_send[: len(ids) * 160] = t_mine[slot[ids[0]] * 160:(slot[ids[-1]] + 1) * 160]
+            if nm and world > 1:
+                # every rank needs every commitment of the phase to drive the transcript: ONE all-gather of
+                # <= 14 x 160 B, then a local add over ranks (whole results and window-shard partials alike;
+                # EC points are not an NCCL reduce op, hence gather + add, never all-reduce)
                 dist.all_gather_into_tensor(t_gather, t_send)
-                if mode == "windows" and ids:
-                    ctx.g1_sum_dev(t_gather.data_ptr() + 64, world, per_round_max * 160, len(ids), t_final.data_ptr() + ids[0] * 160)
+                first = phase_msms[p_i][0]
+                ctx.g1_sum_dev(t_gather.data_ptr() + 64, world, slots_max * 160, nm, t_stage.data_ptr())
+                if all(b - a == 1 for a, b in zip(phase_msms[p_i], phase_msms[p_i][1:])):
+                    t_final[first * 160:(first + nm) * 160] = t_stage[: nm * 160]
+                else:
+                    for q, j in enumerate(phase_msms[p_i]):
+                        t_final[j * 160:(j + 1) * 160] = t_stage[q * 160:(q + 1) * 160]
 
     def barrier():
         torch.cuda.synchronize()
@@ -456,8 +483,8 @@ def main():
         first_of_kind = {}
         for i, u in msm_units:
             first_of_kind.setdefault(u[2], i)
-        gpu_pts_all = ctx.d2h(t_mine.data_ptr(), 20 * len(slot)).reshape(len(slot), 20)
-        gpu_pts = {i: gpu_pts_all[slot[i]] for i in slot}
+        gpu_pts_all = ctx.d2h(t_final.data_ptr(), 20 * len(units)).reshape(len(units), 20)
+        gpu_pts = {i: gpu_pts_all[i] for i in all_msm}
         parity = True
         for kind, i in sorted(first_of_kind.items()):
             s = ctx.d2h(t_cols[i].data_ptr(), 4 * n)
@@ -498,7 +525,7 @@ def main():
             "dtype": "u256-mod-p (8x32-bit Montgomery limbs, integer)", "data": "synthetic",
             "config": {"workload": "aggregation-circuit prover schedule (SURVEY.md App. C), k=%d: 38 MSM(2^%d) + 29 iNTT(2^%d) + 29 coset-NTT(2^%d->2^%d) + 1 iNTT(2^%d)" % (k, k, k, k, k + 2, k + 2),
                        "k": k, "scalars": "witness-like mixture (SURVEY.md 8d): 5x kind1, 1x kind2, 14x 17-bit, 18x uniform Fr",
-                       "parallelism": ("%s over %d GPU(s), one all-gather of commitments per commit round" % ("window-sharded MSM + column-parallel NTT" if mode == "windows" else "column-parallel", world)),
+                       "parallelism": ("%s over %d GPU(s), one all-gather of commitments per commit phase" % ({"windows": "window-sharded MSM + column-parallel NTT", "columns": "column-parallel (round-robin)", "auto": "cost-balanced column-parallel, leftover MSMs window-sharded"}[mode], world)),
                        "msm_mode": "fixed-base table (2^(c w) P rows resident in HBM)" if table_mode else "plain",
                        "msm_window_bits": cbits, "msm_windows": nwin,
                        "l2": "inputs larger than L2 (each column is 2^%d x 32 B; SRS 2^%d x 64 B), no flush needed" % (k, k)},

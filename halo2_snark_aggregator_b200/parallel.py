@@ -42,3 +42,41 @@ def gather_round(dist, torch, local, slots, world, device):
         if tag:
             out[tag - 1] = chunk[8:]
     return out
+
+
+def plan_phase(msm_costs, other_costs, world, n_windows):
+    """Balance one phase of a commit round over `world` ranks (hybrid of 8e-1 and 8e-2).
+
+    msm_costs / other_costs: {unit -> estimated cost}.  Whole MSMs are dealt longest-first to the least
+    loaded rank while at least `world` of them remain; the remainder (fewer MSMs than ranks) is
+    window-sharded, each over a contiguous group of world // remainder ranks, so no rank idles while
+    a neighbour runs a whole 2^k-point MSM.  NTT-like units then fill the least loaded ranks.
+    Returns [(unit, rank, None | (win_begin, win_end))]."""
+    load = [0.0] * world
+    plan = []
+    msms = sorted(msm_costs, key=lambda u: (-msm_costs[u], u))
+    n_whole = (len(msms) // world) * world
+    for u in msms[:n_whole]:
+        r = min(range(world), key=lambda k: (load[k], k))
+        plan.append((u, r, None))
+        load[r] += msm_costs[u]
+    rest = msms[n_whole:]
+    if rest:
+        g = max(1, world // len(rest))
+        order = sorted(range(world), key=lambda k: (load[k], k))
+        for j, u in enumerate(rest):
+            ranks = order[j * g:(j + 1) * g] if g > 1 else [order[j % world]]
+            if len(ranks) == 1:
+                plan.append((u, ranks[0], None))
+                load[ranks[0]] += msm_costs[u]
+                continue
+            shards = window_shards(n_windows, len(ranks))
+            for r, (lo, hi) in zip(ranks, shards):
+                if hi > lo:
+                    plan.append((u, r, (lo, hi)))
+                    load[r] += msm_costs[u] * (hi - lo) / n_windows
+    for u in sorted(other_costs, key=lambda x: (-other_costs[x], x)):
+        r = min(range(world), key=lambda k: (load[k], k))
+        plan.append((u, r, None))
+        load[r] += other_costs[u]
+    return plan

@@ -86,3 +86,26 @@ def test_shard_helpers_cover_everything_once():
         for nwin in (13, 16, 24):
             sh = par.window_shards(nwin, world)
             assert sh[0][0] == 0 and sh[-1][1] == nwin and all(a[1] == b[0] for a, b in zip(sh, sh[1:]))
+
+
+def test_plan_phase_is_complete_and_balanced():
+    from halo2_snark_aggregator_b200 import parallel as par
+
+    nwin = 13
+    for world in (1, 2, 4, 8):
+        for n_msm in (1, 4, 6, 9, 14):
+            mc = {i: 12.5 for i in range(n_msm)}
+            oc = {100 + i: 1.1 for i in range(n_msm)}
+            plan = par.plan_phase(mc, oc, world, nwin)
+            # every MSM is covered exactly once over all windows, every other unit exactly once
+            for u in mc:
+                parts = sorted((w if w else (0, nwin)) for (x, rk, w) in plan if x == u)
+                assert parts[0][0] == 0 and parts[-1][1] == nwin and all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+                assert len(set(rk for (x, rk, w) in plan if x == u)) == len(parts)
+            for u in oc:
+                assert sum(1 for (x, rk, w) in plan if x == u) == 1
+            load = [0.0] * world
+            for (x, rk, w) in plan:
+                load[rk] += (mc[x] * ((w[1] - w[0]) / nwin if w else 1.0)) if x in mc else oc[x]
+            ideal = (sum(mc.values()) + sum(oc.values())) / world
+            assert max(load) <= ideal + 12.5 * (2.0 / nwin) + 12.5 * (0 if n_msm % world == 0 or world // max(n_msm % world, 1) > 1 else 1) + 1.2
