@@ -364,7 +364,13 @@ def main():
         def pinned(nbytes):
             return torch.empty(nbytes // 8, dtype=torch.int64).pin_memory().numpy().view(np.uint64)
 
-        e_msm = [i for i in all_msm if i % world == rank]  # e2e is always column-parallel
+        # e2e is column-parallel over whole columns: a window-sharded MSM is done whole by its lowest rank
+        owner = {}
+        for ph in plan:
+            for (u, rk, w) in ph:
+                if units[u][1] == "msm":
+                    owner[u] = min(owner.get(u, rk), rk)
+        e_msm = sorted(u for u, rk in owner.items() if rk == rank)
         e_units = sorted(e_msm + my_ntt)
         h_cols = {}
         for i in e_msm:
