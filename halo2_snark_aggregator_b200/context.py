@@ -74,6 +74,9 @@ class Context:
     def set_msm_window(self, c):
         self.check(self.lib.h2agg_set_msm_window(self.h, int(c)))
 
+    def set_msm_pair_rounds(self, rounds):
+        self.check(self.lib.h2agg_set_msm_pair_rounds(self.h, int(rounds)))
+
     def set_srs_precompute(self, enable):
         self.check(self.lib.h2agg_set_srs_precompute(self.h, 1 if enable else 0))
 

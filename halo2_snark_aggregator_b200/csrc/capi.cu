@@ -181,6 +181,14 @@ int h2agg_set_msm_window(h2agg_ctx* ctx, int c_bits) {
   return 0;
 }
 
+int h2agg_set_msm_pair_rounds(h2agg_ctx* ctx, int rounds) {
+  if (!ctx) return 1;
+  LOCK(ctx);
+  CHECK_ARG(ctx, rounds >= -1 && rounds <= 3, "msm pair rounds must be -1 (auto) or 0..3");
+  ctx->msm_pair_rounds = rounds;
+  return 0;
+}
+
 int h2agg_set_srs_precompute(h2agg_ctx* ctx, int enable) {
   if (!ctx) return 1;
   LOCK(ctx);

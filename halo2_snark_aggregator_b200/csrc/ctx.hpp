@@ -79,6 +79,7 @@ struct h2agg_ctx {
   uint64_t launches = 0;
   // MSM tuning (0 = auto; a forced width also forces plain mode)
   int msm_window_bits = 0;
+  int msm_pair_rounds = -1;    // batched-affine halving rounds before the XYZZ accumulation (-1 = auto)
   bool srs_precompute = true;  // build the 2^(c w) P table when an SRS is registered
   // per-kernel-class device timing (CUDA events on ctx->stream), enabled by h2agg_kernel_timing
   bool timing = false;

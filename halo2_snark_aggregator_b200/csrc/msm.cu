@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(MSM_THREADS) msm_accumulate(const uint8_t* __r
       bbeg = __ldg(offsets + b);
       bend = __ldg(offsets + b + 1);
     }
-    uint32_t e = __ldg(entries + k);
+    uint32_t e = entries ? __ldg(entries + k) : k;  // no entry list: the points are already in bucket order
     G1Affine q = G1Affine::load_nc(bases + (size_t)(e & 0x7fffffffu) * 64);
     if (e >> 31) q.y = fp_neg(q.y);
     xyzz_madd(acc, q);
@@ -265,6 +265,120 @@ __global__ void __launch_bounds__(MSM_THREADS) msm_accumulate(const uint8_t* __r
   if (bbeg < start) acc.store(head_part + (size_t)t * 128);
   else if (bend > end) acc.store(tail_part + (size_t)t * 128);
   else acc.store(bucket_sums + (size_t)b * 128);
+}
+
+// ---- batched-affine pair rounds ------------------------------------------------------------------------
+// Before the XYZZ accumulation the sorted list is halved a few times: in every bucket, neighbours
+// (2j, 2j+1) are added in AFFINE coordinates with one shared inversion per PAIR_B additions per thread
+// (Montgomery's trick: a forward pass of running denominator products, one inversion, a backward pass).
+// An affine addition then costs 5M + 1S instead of the 8M + 2S of an XYZZ mixed addition, which is what
+// matters on a part whose 256-bit multiplier (the fmaheavy pipe) is the bound.  P = Q, P = -Q and the
+// identity are handled exactly; an odd leftover of a bucket is copied through.
+static constexpr uint32_t PAIR_B = 256;
+
+__global__ void msm_half_counts(const uint32_t* __restrict__ off_in, uint32_t nb, uint32_t* __restrict__ counts) {
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < nb) counts[b] = (off_in[b + 1] - off_in[b] + 1) >> 1;
+  if (b == nb) counts[b] = 0;
+}
+
+struct PairIn {
+  G1Affine p, q;
+  bool pair;
+};
+
+__device__ __forceinline__ G1Affine pair_load(const uint8_t* __restrict__ points, const uint32_t* __restrict__ entries,
+                                              uint32_t i) {
+  uint32_t e = entries ? __ldg(entries + i) : i;
+  G1Affine a = G1Affine::load_nc(points + (size_t)(e & 0x7fffffffu) * 64);
+  if (e >> 31) a.y = fp_neg(a.y);
+  return a;
+}
+
+// classification shared by both passes: 0 copy p, 1 copy q, 2 identity, 3 double, 4 general
+__device__ __forceinline__ int pair_denominator(const PairIn& in, Fq& d) {
+  d = Fq::one();
+  if (!in.pair || in.q.is_identity()) return 0;
+  if (in.p.is_identity()) return 1;
+  if (in.p.x == in.q.x) {
+    if (in.p.y == in.q.y && !in.p.y.is_zero()) {
+      d = fp_dbl(in.p.y);
+      return 3;
+    }
+    return 2;
+  }
+  d = in.q.x - in.p.x;
+  return 4;
+}
+
+__global__ void __launch_bounds__(MSM_THREADS) msm_pair_round(const uint8_t* __restrict__ points,
+                                                               const uint32_t* __restrict__ entries,
+                                                               const uint32_t* __restrict__ off_in,
+                                                               const uint32_t* __restrict__ off_out, uint32_t nb,
+                                                               uint8_t* __restrict__ out, uint8_t* __restrict__ scratch,
+                                                               uint32_t nthreads) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t total = __ldg(off_out + nb);
+  const unsigned long long start64 = (unsigned long long)t * PAIR_B;
+  if (start64 >= total) return;
+  const uint32_t start = (uint32_t)start64;
+  const uint32_t end = (uint32_t)min((unsigned long long)total, start64 + PAIR_B);
+  uint32_t lo = 0, hi = nb;  // off_out[lo] <= start < off_out[hi]
+  while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (__ldg(off_out + mid) <= start) lo = mid; else hi = mid;
+  }
+  uint32_t b = lo;
+  Fq run = Fq::one();
+  // forward: running products of the denominators
+  for (uint32_t o = start; o < end; o++) {
+    while (__ldg(off_out + b + 1) <= o) b++;
+    const uint32_t i0 = __ldg(off_in + b) + 2 * (o - __ldg(off_out + b));
+    PairIn in;
+    in.pair = i0 + 1 < __ldg(off_in + b + 1);
+    in.p = pair_load(points, entries, i0);
+    if (in.pair) in.q = pair_load(points, entries, i0 + 1);
+    Fq d;
+    pair_denominator(in, d);
+    run.store(scratch + ((size_t)(o - start) * nthreads + t) * 32);
+    run = run * d;
+  }
+  Fq inv = fp_inv(run);
+  // backward: peel the individual inverses off and finish the additions
+  for (uint32_t o = end; o-- > start;) {
+    while (__ldg(off_out + b) > o) b--;
+    const uint32_t i0 = __ldg(off_in + b) + 2 * (o - __ldg(off_out + b));
+    PairIn in;
+    in.pair = i0 + 1 < __ldg(off_in + b + 1);
+    in.p = pair_load(points, entries, i0);
+    if (in.pair) in.q = pair_load(points, entries, i0 + 1);
+    Fq d;
+    const int kind = pair_denominator(in, d);
+    Fq dinv = inv * Fq::load(scratch + ((size_t)(o - start) * nthreads + t) * 32);
+    inv = inv * d;
+    G1Affine r;
+    if (kind == 4 || kind == 3) {
+      Fq lam;
+      if (kind == 4) {
+        lam = (in.q.y - in.p.y) * dinv;
+      } else {
+        Fq xx = fp_sqr(in.p.x);
+        lam = (fp_dbl(xx) + xx) * dinv;
+      }
+      const Fq& x2 = (kind == 4) ? in.q.x : in.p.x;
+      r.x = fp_sqr(lam) - in.p.x - x2;
+      r.y = lam * (in.p.x - r.x) - in.p.y;
+    } else if (kind == 0) {
+      r = in.p;
+    } else if (kind == 1) {
+      r = in.q;
+    } else {
+      r.x = Fq::zero();
+      r.y = Fq::zero();
+    }
+    r.x.store(out + (size_t)o * 64);
+    r.y.store(out + (size_t)o * 64 + 32);
+  }
 }
 
 // stitch buckets that straddle chunk boundaries; empty buckets -> identity; hot ones are queued
@@ -561,6 +675,23 @@ int msm_run(h2agg_ctx* ctx, cudaStream_t st, DevBuf& wsbuf, const MsmBases& base
   size_t o_bsums = carve((size_t)scan_blocks * 4);
   size_t o_hot = carve((size_t)(g.nb + 1) * 4 + 256);
   size_t o_entries = carve((max_entries + 1) * 4);
+  // batched-affine pair rounds (large MSMs only)
+  // Measured on B200 (round 1): with per-thread Fermat inversions and re-gathered operands the rounds are
+  // latency-bound and lose to the XYZZ path (uniform 2^22 column: 17.5 ms vs 12.6 ms), so "auto" keeps them off;
+  // they stay selectable (h2agg_set_msm_pair_rounds) and parity-tested as the base for next round's work.
+  const int pair_rounds = (ctx->msm_pair_rounds >= 0) ? ctx->msm_pair_rounds : 0;
+  size_t pr_max[4] = {max_entries, 0, 0, 0};
+  size_t o_pr_pts[4] = {0, 0, 0, 0}, o_pr_off[4] = {0, 0, 0, 0};
+  size_t o_pr_scratch = 0, pr_threads = 0;
+  for (int r = 1; r <= pair_rounds; r++) {
+    pr_max[r] = (pr_max[r - 1] + g.nb) / 2 + 1;
+    o_pr_pts[r] = carve(pr_max[r] * 64);
+    o_pr_off[r] = carve((size_t)(g.nb + 1) * 4);
+  }
+  if (pair_rounds > 0) {
+    pr_threads = align_up((pr_max[1] + PAIR_B - 1) / PAIR_B, MSM_THREADS);
+    o_pr_scratch = carve(pr_threads * PAIR_B * 32);
+  }
   size_t o_head = carve(max_chunks * 128);
   size_t o_tail = carve(max_chunks * 128);
   size_t o_buckets = carve((size_t)g.nb * 128);
@@ -601,8 +732,25 @@ int msm_run(h2agg_ctx* ctx, cudaStream_t st, DevBuf& wsbuf, const MsmBases& base
       ctx->launches++;
     }
     ScopedKernelTimer tk(ctx, KC_MSM_ACCUMULATE, st);
-    msm_accumulate<<<(uint32_t)((max_chunks + MSM_THREADS - 1) / MSM_THREADS), MSM_THREADS, 0, st>>>(
-        d_points, entries, offsets, g, head_part, tail_part, buckets);
+    const uint8_t* cur_pts = d_points;
+    const uint32_t* cur_entries = entries;
+    for (int r = 1; r <= pair_rounds; r++) {
+      uint32_t* off_r = (uint32_t*)(ws + o_pr_off[r]);
+      msm_half_counts<<<(g.nb + 1 + 255) / 256, 256, 0, st>>>(offsets, g.nb, counts);
+      msm_scan1<<<scan_blocks, SCAN_THREADS, 0, st>>>(counts, g.nb, bsums);
+      msm_scan2<<<1, SCAN_THREADS, 0, st>>>(bsums, scan_blocks);
+      msm_scan3<<<scan_blocks, SCAN_THREADS, 0, st>>>(counts, g.nb, bsums, off_r, cursor);
+      const uint32_t nthr = (uint32_t)align_up((pr_max[r] + PAIR_B - 1) / PAIR_B, MSM_THREADS);
+      msm_pair_round<<<nthr / MSM_THREADS, MSM_THREADS, 0, st>>>(cur_pts, cur_entries, offsets, off_r, g.nb, ws + o_pr_pts[r],
+                                                                ws + o_pr_scratch, nthr);
+      ctx->launches += 5;
+      cur_pts = ws + o_pr_pts[r];
+      cur_entries = nullptr;
+      offsets = off_r;
+    }
+    const size_t acc_chunks = (pair_rounds ? pr_max[pair_rounds] : max_entries) / g.chunk + 1;
+    msm_accumulate<<<(uint32_t)((acc_chunks + MSM_THREADS - 1) / MSM_THREADS), MSM_THREADS, 0, st>>>(
+        cur_pts, cur_entries, offsets, g, head_part, tail_part, buckets);
     ctx->launches++;
   }
   ScopedKernelTimer t_red(ctx, KC_MSM_REDUCE, st);

@@ -304,3 +304,47 @@ def test_ntt_host_batches_pipelined(ctx):
     ctx.coeff_to_extended_batch(want, outs, k, k + 2, d["zeta"], d["omega_ext"])
     for c, o in zip(want, outs):
         assert np.array_equal(o, ob.coeff_to_extended(c, k, k + 2, d["zeta"], d["omega_ext"]))
+
+
+@pytest.mark.parametrize("rounds", [1, 2, 3])
+def test_msm_batched_affine_pair_rounds(ctx, rounds):
+    """Force the batched-affine halving rounds on small inputs, including every special case of the
+    affine group law (P+P, P-P, identity operands, hot buckets, odd leftovers)."""
+    ctx.set_msm_pair_rounds(rounds)
+    try:
+        n = 3000
+        b = ob.gen_bases(5, n)
+        same = np.tile(b[:8], n)
+        holes = b.copy()
+        holes.reshape(-1, 8)[::3] = 0
+        pm = b.copy().reshape(-1, 8)
+        h = n // 2
+        pm[h:2 * h, :4] = pm[:h, :4]
+        pm[h:2 * h, 4:] = ob.field_op(1, 1, np.zeros(4 * h, dtype=np.uint64), np.ascontiguousarray(pm[:h, 4:]).ravel()).reshape(-1, 4)
+        pm = np.ascontiguousarray(pm).ravel()
+        ones = np.tile(fr_limbs(1), n)
+        for kind in (0, 1, 2, 3):
+            s = ob.gen_scalars(40 + kind, kind, n)
+            for bases in (b, same, holes, pm):
+                assert np.array_equal(ctx.msm_g1(s, bases), ob.best_multiexp(s, bases)), (kind,)
+        for bases in (b, same, holes, pm):
+            assert np.array_equal(ctx.msm_g1(ones, bases), ob.best_multiexp(ones, bases))
+        for c in (3, 7, 12):
+            ctx.set_msm_window(c)
+            s = ob.gen_scalars(77, 0, n)
+            assert np.array_equal(ctx.msm_g1(s, same), ob.best_multiexp(s, same))
+            ctx.set_msm_window(0)
+        sid = ctx.srs_register(b)  # table mode + pair rounds
+        try:
+            for kind in (0, 1):
+                s = ob.gen_scalars(50 + kind, kind, n)
+                assert np.array_equal(ctx.msm_g1(s, srs_id=sid), ob.best_multiexp(s, b))
+        finally:
+            ctx.srs_release(sid)
+        for m in (1, 2, 3, 255, 1 << 14):
+            s = ob.gen_scalars(60, 0, m)
+            bb = ob.gen_bases(61, m)
+            assert np.array_equal(ctx.msm_g1(s, bb), ob.best_multiexp(s, bb))
+    finally:
+        ctx.set_msm_pair_rounds(-1)
+        ctx.set_msm_window(0)
