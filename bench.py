@@ -537,7 +537,8 @@ def main():
                        "l2": "inputs larger than L2 (each column is 2^%d x 32 B; SRS 2^%d x 64 B), no flush needed" % (k, k)},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clock_info,
             "roofline": {"kernel": "msm_accumulate", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                         "frac": (achieved / peak) if achieved else None, "traffic": 7353400000, "peak_source": peak_src,
+                         "traffic_note": "dram__bytes_read+write of one msm_accumulate launch on a uniform 2^22 column in table mode (profiles/r01_ncu_summary.md): the gather of 54.5 M precomputed 64-byte points is by design",
                          "algorithmic_bytes_per_launch": msm_bytes, "avg_launch_ms": (acc_ms / acc_n) if acc_n else None,
                          "launches_timed": acc_n,
                          "note": "MSM is bound by the INT32 IMAD pipe, not HBM (SURVEY.md 8d); HBM fraction reported as the metric demands"},
