@@ -103,6 +103,8 @@ void h2agg_destroy(h2agg_ctx* ctx) {
     if (ctx->lanes[i].st) cudaStreamDestroy(ctx->lanes[i].st);
   }
   if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
+  for (auto& t : ctx->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+  for (auto e : ctx->ev_pool) cudaEventDestroy(e);
   cudaFree(ctx->small.p);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);

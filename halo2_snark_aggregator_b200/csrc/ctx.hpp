@@ -75,6 +75,7 @@ struct h2agg_ctx {
   std::unordered_map<uint64_t, h2agg::Srs> srs;
   uint64_t next_srs = 1;
   int sm_count = 148;
+  bool ntt_attr_set = false;  // dynamic shared-memory opt-in done for this device
   // counters (claimed in bench.py as gpu_launches)
   uint64_t launches = 0;
   // MSM tuning (0 = auto; a forced width also forces plain mode)

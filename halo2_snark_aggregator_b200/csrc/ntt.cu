@@ -107,6 +107,7 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(const __grid_cons
   // input): they are neither loaded nor computed -- after the bit reversal the first `zskip` DIT
   // stages degenerate to copies, so each loaded value is replicated 2^zskip times instead.
   const uint32_t zs = LAST ? 0u : p.zskip;
+#pragma unroll 4
   for (uint32_t idx = tid; idx < (E >> zs); idx += NTT_THREADS) {
     uint32_t r, c;
     unsigned long long pos;
@@ -151,6 +152,7 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(const __grid_cons
     const uint32_t lh = LAST ? (s - 1 - st) : st;  // DIF runs the strides downwards
     const uint32_t h = 1u << lh;
     const uint32_t gbits = s - 1 - lh;             // log2 of the number of groups R / 2h
+#pragma unroll 2
     for (uint32_t b = tid; b < (E >> 1); b += NTT_THREADS) {
       uint32_t c = b & (C - 1);
       uint32_t q = b >> cbits;
@@ -318,11 +320,10 @@ int ntt_run(h2agg_ctx* ctx, const void* d_src, void* d_dst, const NttOpts& o, cu
     if (rc) return rc;
     tmp = tmpbuf.p;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!ctx->ntt_attr_set) {
     H2AGG_CUDA(ctx, cudaFuncSetAttribute(ntt_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     H2AGG_CUDA(ctx, cudaFuncSetAttribute(ntt_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    attr_set = true;
+    ctx->ntt_attr_set = true;
   }
 
   uint32_t log_p = 0;
