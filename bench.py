@@ -475,6 +475,31 @@ def main():
         chip.close()
         del d_cols
 
+    # ---- N2 (next row): evaluation + Kate division of a 2^k coefficient vector, device resident
+    n2 = None
+    if rank == 0 and not args.no_witness:
+        pt = ctx.d2h(t_ntt[1].data_ptr(), 4)
+        d_q = dbuf(n * 32)
+        d_e = dbuf(64)
+        for _ in range(2):
+            ctx.eval_polynomial_dev(t_ntt[0].data_ptr(), n, pt, d_e.data_ptr())
+            ctx.kate_division_dev(t_ntt[0].data_ptr(), n, pt, d_q.data_ptr())
+        ea, eb, ec = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        torch.cuda.synchronize()
+        ea.record(stream)
+        for _ in range(10):
+            ctx.eval_polynomial_dev(t_ntt[0].data_ptr(), n, pt, d_e.data_ptr())
+        eb.record(stream)
+        for _ in range(10):
+            ctx.kate_division_dev(t_ntt[0].data_ptr(), n, pt, d_q.data_ptr())
+        ec.record(stream)
+        torch.cuda.synchronize()
+        t_ev, t_kd = ea.elapsed_time(eb) / 10, eb.elapsed_time(ec) / 10
+        n2 = {"eval_polynomial_ms": t_ev, "eval_hbm_gbs": 32.0 * n / (t_ev * 1e-3) / 1e9, "kate_division_ms": t_kd,
+              "kate_hbm_gbs": 96.0 * n / (t_kd * 1e-3) / 1e9, "n": n,
+              "note": "algorithmic bytes: eval reads 32 n; division reads 32 n twice and writes 32 n; one Fr product per coefficient per sweep"}
+        del d_q
+
     # ---- CPU baseline: the oracle port on this box's host cores, bounded sample (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -544,6 +569,7 @@ def main():
                          "note": "MSM is bound by the INT32 IMAD pipe, not HBM (SURVEY.md 8d); HBM fraction reported as the metric demands"},
             "cpu_baseline": cpu,
             "witness": witness,
+            "next_rows": {"N2_eval_and_kate_division": n2},
             "extra": {
                 "schedule_algorithmic_bytes": sched_bytes, "schedule_hbm_gbs": sched_bytes / (ms * 1e-3) / 1e9,
                 "schedule_hbm_frac": sched_bytes / (ms * 1e-3) / 1e9 / peak,

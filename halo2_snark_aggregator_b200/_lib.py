@@ -78,6 +78,10 @@ def load():
         "h2agg_extended_to_coeff": (ci, [c_vp, c_vp, u32, c_vp, c_vp, c_vp, sz]),
         "h2agg_coeff_to_extended_dev": (ci, [c_vp, c_vp, u32, u32, c_vp, c_vp, c_vp]),
         "h2agg_extended_to_coeff_dev": (ci, [c_vp, c_vp, u32, c_vp, c_vp, c_vp, sz]),
+        "h2agg_eval_polynomial": (ci, [c_vp, c_vp, sz, c_vp, c_vp]),
+        "h2agg_eval_polynomial_dev": (ci, [c_vp, c_vp, sz, c_vp, c_vp]),
+        "h2agg_kate_division": (ci, [c_vp, c_vp, sz, c_vp, c_vp]),
+        "h2agg_kate_division_dev": (ci, [c_vp, c_vp, sz, c_vp, c_vp]),
         "h2agg_wit_new": (c_vp, []),
         "h2agg_wit_free": (None, [c_vp]),
         "h2agg_wit_error": (ctypes.c_char_p, [c_vp]),

@@ -24,3 +24,15 @@ def best_fft(a, omega, log_n, ctx=None):
     assert a.dtype == np.uint64 and a.size == 4 << log_n, "best_fft: a.len() != 1 << log_n"
     ctx = ctx or default_context()
     ctx.ntt_fr(a, np.ascontiguousarray(omega, dtype=np.uint64), log_n)
+
+
+def eval_polynomial(poly, point, ctx=None):
+    """halo2_proofs::arithmetic::eval_polynomial(poly: &[F], point: F) -> F"""
+    ctx = ctx or default_context()
+    return ctx.eval_polynomial(poly, np.ascontiguousarray(point, dtype=np.uint64))
+
+
+def kate_division(a, b, ctx=None):
+    """halo2_proofs::arithmetic::kate_division(a, b) -> Vec<F> of len a.len() - 1"""
+    ctx = ctx or default_context()
+    return ctx.kate_division(a, np.ascontiguousarray(b, dtype=np.uint64))

@@ -200,6 +200,24 @@ class Context:
     def extended_to_coeff_dev(self, d_a, ext_k, omega_ext_inv, ext_n_inv, zeta, out_len):
         self.check(self.lib.h2agg_extended_to_coeff_dev(self.h, c_vp(d_a), ext_k, _ptr(omega_ext_inv), _ptr(ext_n_inv), _ptr(zeta), out_len))
 
+    # -- N2: evaluation / Kate division
+    def eval_polynomial(self, poly, point):
+        out = np.zeros(4, dtype=np.uint64)
+        self.check(self.lib.h2agg_eval_polynomial(self.h, _ptr(poly), poly.size // 4, _ptr(point), _ptr(out)))
+        return out
+
+    def eval_polynomial_dev(self, d_poly, n, point, d_out32):
+        self.check(self.lib.h2agg_eval_polynomial_dev(self.h, c_vp(d_poly), n, _ptr(point), c_vp(d_out32)))
+
+    def kate_division(self, a, b):
+        n = a.size // 4
+        q = np.zeros(4 * max(n - 1, 0), dtype=np.uint64)
+        self.check(self.lib.h2agg_kate_division(self.h, _ptr(a), n, _ptr(b), _ptr(q) if q.size else c_vp(a.ctypes.data)))
+        return q
+
+    def kate_division_dev(self, d_a, n, b, d_q):
+        self.check(self.lib.h2agg_kate_division_dev(self.h, c_vp(d_a), n, _ptr(b), c_vp(d_q)))
+
     # -- field helpers (device)
     def field_op(self, field, op, a, b=None):
         out = np.empty_like(a)

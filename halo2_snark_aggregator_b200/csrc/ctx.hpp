@@ -68,6 +68,7 @@ struct h2agg_ctx {
   h2agg::Lane lanes[h2agg::N_LANES];
   cudaEvent_t fork_ev = nullptr;
   h2agg::DevBuf small;        // small constants / results
+  h2agg::DevBuf poly_ws;      // recursion levels of eval_polynomial / kate_division
   void* pinned = nullptr;     // pinned host bounce buffer for tiny results
   size_t pinned_cap = 0;
   std::vector<h2agg::TwiddleTable> tw;

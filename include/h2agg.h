@@ -142,6 +142,16 @@ int h2agg_coeff_to_extended_dev(h2agg_ctx* ctx, const void* d_coeffs, uint32_t k
 int h2agg_extended_to_coeff_dev(h2agg_ctx* ctx, void* d_a, uint32_t ext_k, const uint64_t omega_ext_inv[4],
                                 const uint64_t ext_n_inv[4], const uint64_t zeta[4], size_t out_len);
 
+/* ---- N2 (first "next" row): evaluation round + GWC quotients on the device -------
+ * eval_polynomial(poly, point) = sum_i poly[i] * point^i   (halo2_proofs::arithmetic::eval_polynomial)
+ * kate_division(a, b): quotient of a(X) by (X - b), n - 1 coefficients, remainder dropped
+ *                      (halo2_proofs::arithmetic::kate_division).  The _dev form writes n entries
+ *                      (the last one is zero). */
+int h2agg_eval_polynomial(h2agg_ctx* ctx, const uint64_t* poly /* n*4 */, size_t n, const uint64_t point[4], uint64_t out[4]);
+int h2agg_eval_polynomial_dev(h2agg_ctx* ctx, const void* d_poly, size_t n, const uint64_t point[4], void* d_out32);
+int h2agg_kate_division(h2agg_ctx* ctx, const uint64_t* a /* n*4 */, size_t n, const uint64_t b[4], uint64_t* q /* (n-1)*4 */);
+int h2agg_kate_division_dev(h2agg_ctx* ctx, const void* d_a, size_t n, const uint64_t b[4], void* d_q /* n*32 B */);
+
 /* ---- W1-W5: witness synthesis of halo2-ecc-circuit-lib ---------------------------
  * A recording implementation of the reference's chip surface -- ArithEccChip::{add, sub, scalar_mul,
  * scalar_mul_constant, multi_exp, assign_var, assign_const, normalize}

@@ -661,6 +661,36 @@ void oracle_extended_to_coeff(uint64_t* a, uint32_t ext_k, const uint64_t* omega
   distribute_powers_zeta(p, en, z, false, threads);
 }
 
+// halo2_proofs::arithmetic::eval_polynomial (Horner; the parallel version splits into chunks and
+// recombines with powers of the point -- same value)
+void oracle_eval_polynomial(const uint64_t* poly, size_t n, const uint64_t* point, uint64_t* out) {
+  Fr x, acc = Fr::zero();
+  memcpy(x.v, point, 32);
+  for (size_t i = n; i-- > 0;) {
+    Fr c;
+    memcpy(c.v, poly + 4 * i, 32);
+    acc = add(mul(acc, x), c);
+  }
+  memcpy(out, acc.v, 32);
+}
+// halo2_proofs::arithmetic::kate_division: b = -b; tmp = 0; for (q, r) in q.rev().zip(a.rev()):
+//   lead = r - tmp; q = lead; tmp = lead * b      -> q has a.len() - 1 entries
+void oracle_kate_division(const uint64_t* a, size_t n, const uint64_t* b_in, uint64_t* q) {
+  if (n < 2) return;
+  Fr b;
+  memcpy(b.v, b_in, 32);
+  b = neg(b);
+  Fr tmp = Fr::zero();
+  for (size_t k = 0; k + 1 < n; k++) {
+    size_t qi = n - 2 - k, ai = n - 1 - k;
+    Fr lead;
+    memcpy(lead.v, a + 4 * ai, 32);
+    lead = sub(lead, tmp);
+    memcpy(q + 4 * qi, lead.v, 32);
+    tmp = mul(lead, b);
+  }
+}
+
 unsigned oracle_hw_threads(void) {
   unsigned t = std::thread::hardware_concurrency();
   return t ? t : 1;

@@ -49,6 +49,8 @@ def oracle():
         lib.oracle_ifft.argtypes = [c_vp, c_vp, c_vp, u32, ui]
         lib.oracle_coeff_to_extended.argtypes = [c_vp, u32, u32, c_vp, c_vp, c_vp, ui]
         lib.oracle_extended_to_coeff.argtypes = [c_vp, u32, c_vp, c_vp, c_vp, ui]
+        lib.oracle_eval_polynomial.argtypes = [c_vp, sz, c_vp, c_vp]
+        lib.oracle_kate_division.argtypes = [c_vp, sz, c_vp, c_vp]
         lib.oracle_hw_threads.restype = ui
         _o = lib
     return _o
@@ -139,3 +141,17 @@ def coeff_to_extended(coeffs, k, ext_k, zeta, omega_ext, nthreads=None):
 def extended_to_coeff(a, ext_k, omega_ext_inv, ext_n_inv, zeta, out_len, nthreads=None):
     oracle().oracle_extended_to_coeff(P(a), ext_k, P(omega_ext_inv), P(ext_n_inv), P(zeta), nthreads or threads())
     return a[: 4 * out_len]
+
+
+def eval_polynomial(poly, point):
+    out = np.zeros(4, dtype=np.uint64)
+    oracle().oracle_eval_polynomial(P(poly), poly.size // 4, P(point), P(out))
+    return out
+
+
+def kate_division(a, b):
+    n = a.size // 4
+    q = np.zeros(4 * max(n - 1, 0), dtype=np.uint64)
+    if n >= 2:
+        oracle().oracle_kate_division(P(a), n, P(b), P(q))
+    return q

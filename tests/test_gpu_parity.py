@@ -348,3 +348,38 @@ def test_msm_batched_affine_pair_rounds(ctx, rounds):
     finally:
         ctx.set_msm_pair_rounds(-1)
         ctx.set_msm_window(0)
+
+
+# ---------------------------------------------------------------- N2: evaluation round / GWC quotients
+@pytest.mark.parametrize("n", [1, 2, 63, 64, 65, 4095, 4096, 4097, (1 << 16) + 3, 1 << 20])
+def test_eval_polynomial_and_kate_division_vs_oracle(ctx, n):
+    a = ob.gen_scalars(0xE0 + n % 251, 0, n)
+    b = ob.gen_scalars(0xE1, 0, 1, first=n)
+    assert np.array_equal(ctx.eval_polynomial(a, b), ob.eval_polynomial(a, b))
+    assert np.array_equal(ctx.kate_division(a, b), ob.kate_division(a, b))
+
+
+def test_kate_division_full_size_identity(ctx):
+    """n = 2^22: a(z) == q(z) (z - b) + a(b) at a random z (Schwartz-Zippel), all on the device."""
+    n = 1 << 22
+    d_a, d_q, d_o = ctx.dev_alloc(n * 32), ctx.dev_alloc(n * 32), ctx.dev_alloc(128)
+    try:
+        ctx.synth_scalars_dev(0xE5, 0, 0, n, d_a)
+        b = ob.gen_scalars(0xE6, 0, 1)
+        z = ob.gen_scalars(0xE7, 0, 1)
+        ctx.kate_division_dev(d_a, n, b, d_q)
+        ctx.eval_polynomial_dev(d_a, n, z, d_o)
+        ctx.eval_polynomial_dev(d_a, n, b, d_o + 32)
+        ctx.eval_polynomial_dev(d_q, n, z, d_o + 64)
+        ctx.synchronize()
+        r = ctx.d2h(d_o, 12)
+        az, ab, qz = r[0:4], r[4:8], r[8:12]
+        rhs = ob.field_op(0, 0, ob.field_op(0, 3, qz, ob.field_op(0, 1, z, b)), ab)
+        assert np.array_equal(az, rhs)
+        # and the first 2^16 coefficients of a against the oracle's evaluation of the same prefix
+        m = 1 << 16
+        pre = ctx.d2h(d_a, 4 * m)
+        assert np.array_equal(ctx.eval_polynomial(pre, z), ob.eval_polynomial(pre, z))
+    finally:
+        for d in (d_a, d_q, d_o):
+            ctx.dev_free(d)

@@ -98,3 +98,25 @@ def test_msm_linearity_and_concatenation():
     whole = ob.best_multiexp(s1, b)
     parts = ob.g1_sum(np.concatenate([ob.best_multiexp(s1[: 4 * 100], b[: 8 * 100]), ob.best_multiexp(s1[4 * 100:], b[8 * 100:])]))
     assert np.array_equal(whole, parts)
+
+
+def test_eval_and_kate_division_vs_python_bigint():
+    import random
+
+    from util import R_MOD, fr_limbs
+
+    rng = random.Random(5)
+    for n in (1, 2, 3, 17, 64, 65, 200):
+        coeffs = [rng.randrange(R_MOD) for _ in range(n)]
+        b = rng.randrange(R_MOD)
+        a = np.array(ref.pack_fr(coeffs), dtype=np.uint64)
+        want_eval = sum(c * pow(b, i, R_MOD) for i, c in enumerate(coeffs)) % R_MOD
+        assert ref.unpack_fr(list(ob.eval_polynomial(a, fr_limbs(b)))) == [want_eval]
+        q = ref.unpack_fr(list(ob.kate_division(a, fr_limbs(b))))
+        # a(X) = q(X) (X - b) + a(b): compare coefficients
+        prod = [0] * n
+        for i, qi in enumerate(q):
+            prod[i + 1] = (prod[i + 1] + qi) % R_MOD
+            prod[i] = (prod[i] - qi * b) % R_MOD
+        prod[0] = (prod[0] + want_eval) % R_MOD
+        assert prod == coeffs
