@@ -289,10 +289,29 @@ def main():
         my_calls.append(calls)
     ctx.synchronize()
 
+    s_ntt = torch.cuda.Stream(device=dev)  # the phase's NTTs run beside its MSM batch (independent columns)
+    ev_fork, ev_join = torch.cuda.Event(), torch.cuda.Event()
+
     def step_device():
         c = 0
         for p_i, ph in enumerate(plan):
             nm = len(phase_msms[p_i])
+            ntt_here = [(u, rk, w) for (u, rk, w) in ph if rk == rank and units[u][1] != "msm"]
+            if ntt_here:
+                ev_fork.record(stream)
+                s_ntt.wait_event(ev_fork)
+                ctx.set_stream(s_ntt.cuda_stream)
+                for (u, rk, w) in ntt_here:
+                    what = units[u][1]
+                    if what == "intt":
+                        dom.lagrange_to_coeff_dev(t_ntt[c % n_ntt_bufs].data_ptr())
+                    elif what == "coset":
+                        dom.coeff_to_extended_dev(t_ntt[c % n_ntt_bufs].data_ptr(), t_ext[c % 2].data_ptr())
+                    else:
+                        dom.extended_to_coeff_dev(t_ext[c % 2].data_ptr())
+                    c += 1
+                ev_join.record(s_ntt)
+                ctx.set_stream(stream.cuda_stream)
             if nm and world > 1:
                 t_send.zero_()
             for (w, us, idx) in my_calls[p_i]:
@@ -303,17 +322,8 @@ def main():
                 elif dst == t_stage.data_ptr():
                     for q, j in enumerate(us):
                         t_final[j * 160:(j + 1) * 160] = t_stage[q * 160:(q + 1) * 160]
-            for (u, rk, w) in ph:
-                if rk != rank or units[u][1] == "msm":
-                    continue
-                what = units[u][1]
-                if what == "intt":
-                    dom.lagrange_to_coeff_dev(t_ntt[c % n_ntt_bufs].data_ptr())
-                elif what == "coset":
-                    dom.coeff_to_extended_dev(t_ntt[c % n_ntt_bufs].data_ptr(), t_ext[c % 2].data_ptr())
-                else:
-                    dom.extended_to_coeff_dev(t_ext[c % 2].data_ptr())
-                c += 1
+            if ntt_here:
+                stream.wait_event(ev_join)
             if nm and world > 1:
                 # every rank needs every commitment of the phase to drive the transcript: ONE all-gather of
                 # <= 14 x 160 B, then a local add over ranks (whole results and window-shard partials alike;

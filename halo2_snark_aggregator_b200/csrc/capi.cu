@@ -117,8 +117,10 @@ const char* h2agg_last_error(h2agg_ctx* ctx) { return ctx ? ctx->last_error.c_st
 int h2agg_set_stream(h2agg_ctx* ctx, void* cuda_stream) {
   if (!ctx) return 1;
   LOCK(ctx);
-  H2AGG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  // No synchronisation: like any CUDA stream switch, ordering between the old and the new stream is the
+  // caller's business (events).  The context's own stream is drained once before it is dropped.
   if (ctx->own_stream) {
+    H2AGG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     cudaStreamDestroy(ctx->stream);
     ctx->own_stream = false;
   }

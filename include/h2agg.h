@@ -44,7 +44,10 @@ int h2agg_init(int device_id, h2agg_ctx** out);
 void h2agg_destroy(h2agg_ctx* ctx);
 const char* h2agg_last_error(h2agg_ctx* ctx); /* ctx may be NULL: error of the last failed init */
 const char* h2agg_version(void);
-/* Run on a caller-owned CUDA stream (cudaStream_t) instead of the context's own. */
+/* Run on a caller-owned CUDA stream (cudaStream_t) instead of the context's own.  Switching streams
+ * does not synchronise: order them with events, as with any CUDA work.  MSM batches (lanes + their own
+ * workspaces) and NTTs (the context's ping-pong buffer) share no scratch, so a caller may run one
+ * NTT stream concurrently with MSM batches issued on another stream. */
 int h2agg_set_stream(h2agg_ctx* ctx, void* cuda_stream);
 int h2agg_synchronize(h2agg_ctx* ctx);
 /* Number of kernels this context has launched so far (evidence counter for bench.py). */
