@@ -179,6 +179,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-witness", action="store_true")
+    ap.add_argument("--overlap-ntt", action="store_true", help="run a phase's NTTs on a second stream beside its MSM batch (measured: no gain, the step is multiplier-bound)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--msm-window", type=int, default=0)
     ap.add_argument("--parallelism", default="auto", choices=["auto", "columns", "windows"])
@@ -298,9 +299,10 @@ def main():
             nm = len(phase_msms[p_i])
             ntt_here = [(u, rk, w) for (u, rk, w) in ph if rk == rank and units[u][1] != "msm"]
             if ntt_here:
-                ev_fork.record(stream)
-                s_ntt.wait_event(ev_fork)
-                ctx.set_stream(s_ntt.cuda_stream)
+                if args.overlap_ntt:
+                    ev_fork.record(stream)
+                    s_ntt.wait_event(ev_fork)
+                    ctx.set_stream(s_ntt.cuda_stream)
                 for (u, rk, w) in ntt_here:
                     what = units[u][1]
                     if what == "intt":
@@ -310,8 +312,9 @@ def main():
                     else:
                         dom.extended_to_coeff_dev(t_ext[c % 2].data_ptr())
                     c += 1
-                ev_join.record(s_ntt)
-                ctx.set_stream(stream.cuda_stream)
+                if args.overlap_ntt:
+                    ev_join.record(s_ntt)
+                    ctx.set_stream(stream.cuda_stream)
             if nm and world > 1:
                 t_send.zero_()
             for (w, us, idx) in my_calls[p_i]:
@@ -322,7 +325,7 @@ def main():
                 elif dst == t_stage.data_ptr():
                     for q, j in enumerate(us):
                         t_final[j * 160:(j + 1) * 160] = t_stage[q * 160:(q + 1) * 160]
-            if ntt_here:
+            if ntt_here and args.overlap_ntt:
                 stream.wait_event(ev_join)
             if nm and world > 1:
                 # every rank needs every commitment of the phase to drive the transcript: ONE all-gather of

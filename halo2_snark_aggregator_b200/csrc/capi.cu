@@ -84,6 +84,7 @@ void h2agg_destroy(h2agg_ctx* ctx) {
   for (auto& t : ctx->tw) {
     cudaFree(t.lo);
     cudaFree(t.hi);
+    cudaFree(t.full);
   }
   for (auto& kv : ctx->srs) {
     if (kv.second.owned) cudaFree(const_cast<void*>(kv.second.d_bases));

@@ -21,6 +21,7 @@ struct TwiddleTable {
   uint32_t lo_bits;  // T_lo has 2^lo_bits entries (omega^i), T_hi has 2^(log_n-lo_bits) (omega^(i<<lo_bits))
   void* lo = nullptr;
   void* hi = nullptr;
+  void* full = nullptr;  // omega^e, e < 2^log_n (first-pass twiddles), optional
   uint64_t last_use = 0;
 };
 
@@ -76,7 +77,8 @@ struct h2agg_ctx {
   std::unordered_map<uint64_t, h2agg::Srs> srs;
   uint64_t next_srs = 1;
   int sm_count = 148;
-  bool ntt_attr_set = false;  // dynamic shared-memory opt-in done for this device
+  bool ntt_attr_set = false;
+  bool ntt_full_tables = true;  // trade N x 32 B of HBM per (omega, k) for one product per element in the first pass  // dynamic shared-memory opt-in done for this device
   // counters (claimed in bench.py as gpu_launches)
   uint64_t launches = 0;
   // MSM tuning (0 = auto; a forced width also forces plain mode)

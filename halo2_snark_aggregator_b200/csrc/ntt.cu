@@ -20,7 +20,7 @@
 
 namespace h2agg {
 
-static constexpr int NTT_THREADS = 512;
+static constexpr int NTT_THREADS = 256;
 static constexpr uint32_t NTT_TILE_LOG = 11;  // 2048 elements = 64 KiB of shared memory per CTA
 
 struct NttPassArgs {
@@ -28,6 +28,7 @@ struct NttPassArgs {
   uint4* dst;
   const Fr* t_lo;
   const Fr* t_hi;
+  const Fr* t_full;  // w^e for every e < N (first pass only; may be null)
   unsigned long long src_n, dst_n;
   uint32_t log_n, lo_bits;
   uint32_t s;       // log2 radix of this pass
@@ -52,6 +53,13 @@ __device__ __forceinline__ Fr get_tw(const Fr* __restrict__ t_lo, const Fr* __re
   return Fr::load_nc(t_lo + lo) * Fr::load_nc(t_hi + hi);
 }
 
+__global__ void ntt_gen_full_table(const Fr* __restrict__ t_lo, const Fr* __restrict__ t_hi, uint32_t lo_bits, uint32_t log_n,
+                                   Fr* __restrict__ full) {
+  uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (1u << log_n)) return;
+  get_tw(t_lo, t_hi, lo_bits, e).store(full + e);
+}
+
 __global__ void ntt_gen_tables(Fr omega, uint32_t lo_bits, uint32_t hi_bits, Fr* t_lo, Fr* t_hi) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t nlo = 1u << lo_bits, nhi = 1u << hi_bits;
@@ -64,7 +72,7 @@ __global__ void ntt_gen_tables(Fr omega, uint32_t lo_bits, uint32_t hi_bits, Fr*
 }
 
 template <bool LAST>
-__global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(const __grid_constant__ NttPassArgs p) {
+__global__ void __launch_bounds__(NTT_THREADS, 3) ntt_pass_kernel(const __grid_constant__ NttPassArgs p) {
   extern __shared__ uint4 smem[];
   const uint32_t s = p.s, R = 1u << s, cbits = p.cbits, C = 1u << cbits, E = R << cbits;
   const uint32_t rs = LAST ? 1u : C;
@@ -144,18 +152,21 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(const __grid_cons
     }
   }
 
-  // ---- radix-2 stages in shared memory.  Thread -> (j, g, c) with c fastest and the twiddle
-  // index j slowest, so a warp shares one twiddle and the w = 1 butterflies (j == 0: a whole
-  // stage's worth plus half, a quarter, ... of the others) skip the multiplication warp-uniformly.
-  for (uint32_t st = zs; st < s; st++) {
+  // ---- butterfly stages in shared memory, two at a time (radix-4 in registers): a thread owns the
+  // four rows {i, i+h, i+2h, i+3h} of one column, so every second shared-memory round trip and
+  // __syncthreads() disappears and four independent products are in flight per thread.
+  // Thread -> (j, g, c) with c fastest and the twiddle index j slowest: a warp shares its twiddles and the
+  // w = 1 cases (j == 0) skip their products warp-uniformly.  An odd leftover stage runs radix-2.
+  uint32_t st = zs;
+  if ((s - zs) & 1) {  // single radix-2 stage first
     __syncthreads();
-    const uint32_t lh = LAST ? (s - 1 - st) : st;  // DIF runs the strides downwards
+    const uint32_t lh = LAST ? (s - 1 - st) : st;
     const uint32_t h = 1u << lh;
-    const uint32_t gbits = s - 1 - lh;             // log2 of the number of groups R / 2h
+    const uint32_t gbits = s - 1 - lh;
 #pragma unroll 2
-    for (uint32_t b = tid; b < (E >> 1); b += NTT_THREADS) {
-      uint32_t c = b & (C - 1);
-      uint32_t q = b >> cbits;
+    for (uint32_t bb = tid; bb < (E >> 1); bb += NTT_THREADS) {
+      uint32_t c = bb & (C - 1);
+      uint32_t q = bb >> cbits;
       uint32_t g = q & ((1u << gbits) - 1);
       uint32_t j = q >> gbits;
       uint32_t i = (g << (lh + 1)) + j;
@@ -181,6 +192,56 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(const __grid_cons
       xl[i0] = y0.lo4(); xh[i0] = y0.hi4();
       xl[i1] = y1.lo4(); xh[i1] = y1.hi4();
     }
+    st++;
+  }
+  for (; st < s; st += 2) {
+    __syncthreads();
+    // DIT: strides h then 2h with lh = st; DIF (last pass): strides 2h then h with lh = s - 2 - st
+    const uint32_t lh = LAST ? (s - 2 - st) : st;
+    const uint32_t h = 1u << lh;
+    const uint32_t gbits = s - 2 - lh;  // log2 of the number of groups R / 4h
+    for (uint32_t bb = tid; bb < (E >> 2); bb += NTT_THREADS) {
+      const uint32_t c = bb & (C - 1);
+      const uint32_t q = bb >> cbits;
+      const uint32_t g = q & ((1u << gbits) - 1);
+      const uint32_t j = q >> gbits;  // < h
+      const uint32_t i = (g << (lh + 2)) + j;
+      const uint32_t i0 = i * rs + c * cs, i1 = (i + h) * rs + c * cs, i2 = (i + 2 * h) * rs + c * cs,
+                     i3 = (i + 3 * h) * rs + c * cs;
+      Fr x0 = Fr::from_halves(xl[i0], xh[i0]);
+      Fr x1 = Fr::from_halves(xl[i1], xh[i1]);
+      Fr x2 = Fr::from_halves(xl[i2], xh[i2]);
+      Fr x3 = Fr::from_halves(xl[i3], xh[i3]);
+      // twiddles: w1 = w_R^(j R/2h) (stride h), w2 = w_R^(j R/4h), w3 = w_R^((j+h) R/4h) (stride 2h)
+      const uint32_t m1 = j << (gbits + 1), m2 = j << gbits, m3 = (j + h) << gbits;
+      const Fr w3 = Fr::from_halves(twl[m3], twh[m3]);
+      Fr y0, y1, y2, y3;
+      if (!LAST) {
+        if (j) {
+          const Fr w1 = Fr::from_halves(twl[m1], twh[m1]);
+          x1 = x1 * w1;
+          x3 = x3 * w1;
+        }
+        Fr a0 = x0 + x1, a1 = x0 - x1, a2 = x2 + x3, a3 = x2 - x3;
+        if (j) a2 = a2 * Fr::from_halves(twl[m2], twh[m2]);
+        a3 = a3 * w3;
+        y0 = a0 + a2; y2 = a0 - a2; y1 = a1 + a3; y3 = a1 - a3;
+      } else {
+        Fr b0 = x0 + x2, b2 = x0 - x2, b1 = x1 + x3, b3 = x1 - x3;
+        if (j) b2 = b2 * Fr::from_halves(twl[m2], twh[m2]);
+        b3 = b3 * w3;
+        y0 = b0 + b1; y1 = b0 - b1; y2 = b2 + b3; y3 = b2 - b3;
+        if (j) {
+          const Fr w1 = Fr::from_halves(twl[m1], twh[m1]);
+          y1 = y1 * w1;
+          y3 = y3 * w1;
+        }
+      }
+      xl[i0] = y0.lo4(); xh[i0] = y0.hi4();
+      xl[i1] = y1.lo4(); xh[i1] = y1.hi4();
+      xl[i2] = y2.lo4(); xh[i2] = y2.hi4();
+      xl[i3] = y3.lo4(); xh[i3] = y3.hi4();
+    }
   }
   __syncthreads();
 
@@ -195,7 +256,9 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(const __grid_cons
       if (k && jj) {
         // w_N^(P_t * j * k_t); j*k_t < M_t so the exponent is < N
         uint32_t e = (uint32_t)(((unsigned long long)jj * k) << p.log_p);
-        v = v * get_tw(p.t_lo, p.t_hi, p.lo_bits, e);
+        // first pass: e ranges over the whole domain -> one 32-byte gather from the full table instead of
+        // T_lo * T_hi (HBM bytes are cheap here, multiplier cycles are not); later passes hit T_hi directly
+        v = v * (p.t_full ? Fr::load_nc(p.t_full + e) : get_tw(p.t_lo, p.t_hi, p.lo_bits, e));
       }
       p.dst[2 * pos] = v.lo4();
       p.dst[2 * pos + 1] = v.hi4();
@@ -238,13 +301,14 @@ static int get_tables(h2agg_ctx* ctx, const uint64_t* omega, uint32_t log_n, Twi
       return 0;
     }
   }
-  if (ctx->tw.size() >= 24) {  // evict least recently used
+  if (ctx->tw.size() >= 12) {  // evict least recently used
     size_t v = 0;
     for (size_t i = 1; i < ctx->tw.size(); i++)
       if (ctx->tw[i].last_use < ctx->tw[v].last_use) v = i;
     H2AGG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     cudaFree(ctx->tw[v].lo);
     cudaFree(ctx->tw[v].hi);
+    cudaFree(ctx->tw[v].full);
     ctx->tw.erase(ctx->tw.begin() + v);
   }
   TwiddleTable t;
@@ -266,6 +330,18 @@ static int get_tables(h2agg_ctx* ctx, const uint64_t* omega, uint32_t log_n, Twi
   ntt_gen_tables<<<(total + 127) / 128, 128, 0, ctx->stream>>>(w, t.lo_bits, hi_bits, (Fr*)t.lo, (Fr*)t.hi);
   ctx->launches++;
   H2AGG_CUDA(ctx, cudaGetLastError());
+  // full table for the first pass of multi-pass transforms (N x 32 B: 128 MiB at 2^22, 512 MiB at 2^24)
+  t.full = nullptr;
+  if (log_n > NTT_TILE_LOG && log_n <= 26 && ctx->ntt_full_tables) {
+    if (cudaMalloc(&t.full, sizeof(Fr) << log_n) == cudaSuccess) {
+      ntt_gen_full_table<<<(1u << log_n) / 256, 256, 0, ctx->stream>>>((const Fr*)t.lo, (const Fr*)t.hi, t.lo_bits, log_n, (Fr*)t.full);
+      ctx->launches++;
+      H2AGG_CUDA(ctx, cudaGetLastError());
+    } else {
+      cudaGetLastError();
+      t.full = nullptr;  // out of memory: the two-level tables still work
+    }
+  }
   t.last_use = ctx->tick;
   ctx->tw.push_back(t);
   *out = &ctx->tw.back();
@@ -335,6 +411,7 @@ int ntt_run(h2agg_ctx* ctx, const void* d_src, void* d_dst, const NttOpts& o, cu
     a.dst = (uint4*)(last ? d_dst : tmp);
     a.t_lo = (const Fr*)tw->lo;
     a.t_hi = (const Fr*)tw->hi;
+    a.t_full = (t == 0 && !last) ? (const Fr*)tw->full : nullptr;
     a.log_n = o.log_n;
     a.lo_bits = tw->lo_bits;
     a.s = s[t];
