@@ -489,7 +489,7 @@ def main():
         del d_cols
 
     # ---- N2 (next row): evaluation + Kate division of a 2^k coefficient vector, device resident
-    n2 = None
+    n2 = n3 = None
     if rank == 0 and not args.no_witness:
         pt = ctx.d2h(t_ntt[1].data_ptr(), 4)
         d_q = dbuf(n * 32)
@@ -511,7 +511,19 @@ def main():
         n2 = {"eval_polynomial_ms": t_ev, "eval_hbm_gbs": 32.0 * n / (t_ev * 1e-3) / 1e9, "kate_division_ms": t_kd,
               "kate_hbm_gbs": 96.0 * n / (t_kd * 1e-3) / 1e9, "n": n,
               "note": "algorithmic bytes: eval reads 32 n; division reads 32 n twice and writes 32 n; one Fr product per coefficient per sweep"}
-        del d_q
+        # N3: running-product column of 2^k rows (batch inversion + product scan)
+        d_z = dbuf(n * 32)
+        for _ in range(2):
+            ctx.grand_product_dev(t_ntt[0].data_ptr(), t_ntt[1].data_ptr(), n, d_z.data_ptr())
+        ea.record(stream)
+        for _ in range(10):
+            ctx.grand_product_dev(t_ntt[0].data_ptr(), t_ntt[1].data_ptr(), n, d_z.data_ptr())
+        eb.record(stream)
+        torch.cuda.synchronize()
+        t_gp = ea.elapsed_time(eb) / 10
+        n3 = {"grand_product_ms": t_gp, "hbm_gbs": 96.0 * n / (t_gp * 1e-3) / 1e9, "n": n,
+              "note": "algorithmic bytes: numerators + denominators read, running products written; ~6 Fr products per row"}
+        del d_q, d_z
 
     # ---- CPU baseline: the oracle port on this box's host cores, bounded sample (rank 0, N=1 only)
     cpu = None
@@ -582,7 +594,7 @@ def main():
                          "note": "MSM is bound by the INT32 IMAD pipe, not HBM (SURVEY.md 8d); HBM fraction reported as the metric demands"},
             "cpu_baseline": cpu,
             "witness": witness,
-            "next_rows": {"N2_eval_and_kate_division": n2},
+            "next_rows": {"N2_eval_and_kate_division": n2, "N3_grand_product": n3},
             "extra": {
                 "schedule_algorithmic_bytes": sched_bytes, "schedule_hbm_gbs": sched_bytes / (ms * 1e-3) / 1e9,
                 "schedule_hbm_frac": sched_bytes / (ms * 1e-3) / 1e9 / peak,

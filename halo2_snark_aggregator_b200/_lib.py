@@ -82,6 +82,10 @@ def load():
         "h2agg_eval_polynomial_dev": (ci, [c_vp, c_vp, sz, c_vp, c_vp]),
         "h2agg_kate_division": (ci, [c_vp, c_vp, sz, c_vp, c_vp]),
         "h2agg_kate_division_dev": (ci, [c_vp, c_vp, sz, c_vp, c_vp]),
+        "h2agg_batch_invert": (ci, [c_vp, c_vp, sz]),
+        "h2agg_batch_invert_dev": (ci, [c_vp, c_vp, sz]),
+        "h2agg_grand_product": (ci, [c_vp, c_vp, c_vp, sz, c_vp]),
+        "h2agg_grand_product_dev": (ci, [c_vp, c_vp, c_vp, sz, c_vp]),
         "h2agg_wit_new": (c_vp, []),
         "h2agg_wit_free": (None, [c_vp]),
         "h2agg_wit_error": (ctypes.c_char_p, [c_vp]),

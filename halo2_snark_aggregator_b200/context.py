@@ -218,6 +218,20 @@ class Context:
     def kate_division_dev(self, d_a, n, b, d_q):
         self.check(self.lib.h2agg_kate_division_dev(self.h, c_vp(d_a), n, _ptr(b), c_vp(d_q)))
 
+    # -- N3: grand-product scans
+    def batch_invert(self, a):
+        out = a.copy()
+        self.check(self.lib.h2agg_batch_invert(self.h, _ptr(out), out.size // 4))
+        return out
+
+    def grand_product(self, num, den):
+        z = np.zeros_like(num)
+        self.check(self.lib.h2agg_grand_product(self.h, _ptr(num), _ptr(den), num.size // 4, _ptr(z)))
+        return z
+
+    def grand_product_dev(self, d_num, d_den, n, d_z):
+        self.check(self.lib.h2agg_grand_product_dev(self.h, c_vp(d_num), c_vp(d_den), n, c_vp(d_z)))
+
     # -- field helpers (device)
     def field_op(self, field, op, a, b=None):
         out = np.empty_like(a)

@@ -108,6 +108,7 @@ void h2agg_destroy(h2agg_ctx* ctx) {
   for (auto e : ctx->ev_pool) cudaEventDestroy(e);
   cudaFree(ctx->small.p);
   cudaFree(ctx->poly_ws.p);
+  cudaFree(ctx->scan_ws.p);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;

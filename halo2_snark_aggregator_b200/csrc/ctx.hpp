@@ -70,6 +70,7 @@ struct h2agg_ctx {
   cudaEvent_t fork_ev = nullptr;
   h2agg::DevBuf small;        // small constants / results
   h2agg::DevBuf poly_ws;      // recursion levels of eval_polynomial / kate_division
+  h2agg::DevBuf scan_ws;      // batch_invert / grand_product scratch
   void* pinned = nullptr;     // pinned host bounce buffer for tiny results
   size_t pinned_cap = 0;
   std::vector<h2agg::TwiddleTable> tw;

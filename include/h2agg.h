@@ -155,6 +155,14 @@ int h2agg_eval_polynomial_dev(h2agg_ctx* ctx, const void* d_poly, size_t n, cons
 int h2agg_kate_division(h2agg_ctx* ctx, const uint64_t* a /* n*4 */, size_t n, const uint64_t b[4], uint64_t* q /* (n-1)*4 */);
 int h2agg_kate_division_dev(h2agg_ctx* ctx, const void* d_a, size_t n, const uint64_t b[4], void* d_q /* n*32 B */);
 
+/* ---- N3 (next row): the scan primitives of the permutation / lookup grand products ----------------
+ * batch_invert: a[i] <- 1/a[i] in place, zeros stay zero (halo2_proofs BatchInvert semantics).
+ * grand_product: z[0] = 1, z[i+1] = z[i] * num[i] / den[i]  (n outputs; the running product columns). */
+int h2agg_batch_invert(h2agg_ctx* ctx, uint64_t* a /* n*4, in place */, size_t n);
+int h2agg_batch_invert_dev(h2agg_ctx* ctx, void* d_a, size_t n);
+int h2agg_grand_product(h2agg_ctx* ctx, const uint64_t* num, const uint64_t* den, size_t n, uint64_t* z /* n*4 */);
+int h2agg_grand_product_dev(h2agg_ctx* ctx, const void* d_num, const void* d_den, size_t n, void* d_z);
+
 /* ---- W1-W5: witness synthesis of halo2-ecc-circuit-lib ---------------------------
  * A recording implementation of the reference's chip surface -- ArithEccChip::{add, sub, scalar_mul,
  * scalar_mul_constant, multi_exp, assign_var, assign_const, normalize}

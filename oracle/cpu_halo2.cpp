@@ -691,6 +691,37 @@ void oracle_kate_division(const uint64_t* a, size_t n, const uint64_t* b_in, uin
   }
 }
 
+// halo2_proofs BatchInvert: zeros are skipped (stay zero), everything else is inverted
+void oracle_batch_invert(uint64_t* a, size_t n) {
+  std::vector<Fr> pre(n);
+  Fr run = Fr::one();
+  Fr* p = (Fr*)a;
+  for (size_t i = 0; i < n; i++) {
+    pre[i] = run;
+    if (!p[i].is_zero()) run = mul(run, p[i]);
+  }
+  Fr iv = inv(run);
+  for (size_t i = n; i-- > 0;) {
+    if (p[i].is_zero()) continue;
+    Fr v = p[i];
+    p[i] = mul(iv, pre[i]);
+    iv = mul(iv, v);
+  }
+}
+// running product column: z[0] = 1, z[i+1] = z[i] * num[i] / den[i]
+void oracle_grand_product(const uint64_t* num, const uint64_t* den, size_t n, uint64_t* z) {
+  std::vector<uint64_t> d(den, den + 4 * n);
+  oracle_batch_invert(d.data(), n);
+  Fr run = Fr::one();
+  for (size_t i = 0; i < n; i++) {
+    memcpy(z + 4 * i, run.v, 32);
+    Fr a, b;
+    memcpy(a.v, num + 4 * i, 32);
+    memcpy(b.v, d.data() + 4 * i, 32);
+    run = mul(run, mul(a, b));
+  }
+}
+
 unsigned oracle_hw_threads(void) {
   unsigned t = std::thread::hardware_concurrency();
   return t ? t : 1;

@@ -51,6 +51,8 @@ def oracle():
         lib.oracle_extended_to_coeff.argtypes = [c_vp, u32, c_vp, c_vp, c_vp, ui]
         lib.oracle_eval_polynomial.argtypes = [c_vp, sz, c_vp, c_vp]
         lib.oracle_kate_division.argtypes = [c_vp, sz, c_vp, c_vp]
+        lib.oracle_batch_invert.argtypes = [c_vp, sz]
+        lib.oracle_grand_product.argtypes = [c_vp, c_vp, sz, c_vp]
         lib.oracle_hw_threads.restype = ui
         _o = lib
     return _o
@@ -155,3 +157,15 @@ def kate_division(a, b):
     if n >= 2:
         oracle().oracle_kate_division(P(a), n, P(b), P(q))
     return q
+
+
+def batch_invert(a):
+    out = a.copy()
+    oracle().oracle_batch_invert(P(out), out.size // 4)
+    return out
+
+
+def grand_product(num, den):
+    z = np.zeros_like(num)
+    oracle().oracle_grand_product(P(num), P(den), num.size // 4, P(z))
+    return z

@@ -383,3 +383,34 @@ def test_kate_division_full_size_identity(ctx):
     finally:
         for d in (d_a, d_q, d_o):
             ctx.dev_free(d)
+
+
+# ---------------------------------------------------------------- N3: grand-product scans
+@pytest.mark.parametrize("n", [1, 2, 63, 64, 65, 4096, 4097, (1 << 16) + 5, 1 << 20])
+def test_batch_invert_and_grand_product_vs_oracle(ctx, n):
+    a = ob.gen_scalars(0xB0 + n % 97, 0, n)
+    if n > 70:
+        a.reshape(-1, 4)[[3, 64, 69]] = 0  # zeros are skipped, not poisoning the batch
+    assert np.array_equal(ctx.batch_invert(a), ob.batch_invert(a))
+    num = ob.gen_scalars(0xB1, 0, n)
+    den = ob.gen_scalars(0xB2, 1 if n > 1000 else 0, n)  # witness-like denominators contain zeros
+    assert np.array_equal(ctx.grand_product(num, den), ob.grand_product(num, den))
+
+
+def test_grand_product_full_size_telescopes(ctx):
+    """n = 2^22: with num = den shifted by one row the running product telescopes to den[0] / den[i]."""
+    n = 1 << 22
+    d_den, d_num, d_z = ctx.dev_alloc(n * 32), ctx.dev_alloc(n * 32 + 32), ctx.dev_alloc(n * 32)
+    try:
+        ctx.synth_scalars_dev(0xB5, 0, 0, n + 1, d_num)  # num[i] = v[i], den[i] = v[i+1]
+        ctx.grand_product_dev(d_num, d_num + 32, n, d_z)
+        ctx.synchronize()
+        v = ctx.d2h(d_num, 4 * (n + 1)).reshape(-1, 4)
+        z = ctx.d2h(d_z, 4 * n).reshape(-1, 4)
+        idx = np.array([1, 2, 63, 64, 65, 4097, n // 2 + 3, n - 1])
+        # z[i] * v[i] == v[0]
+        lhs = ob.field_op(0, 3, np.ascontiguousarray(z[idx]).ravel(), np.ascontiguousarray(v[idx]).ravel())
+        assert np.array_equal(lhs.reshape(-1, 4), np.tile(v[0], (len(idx), 1)))
+    finally:
+        for d in (d_den, d_num, d_z):
+            ctx.dev_free(d)

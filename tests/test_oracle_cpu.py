@@ -120,3 +120,25 @@ def test_eval_and_kate_division_vs_python_bigint():
             prod[i] = (prod[i] - qi * b) % R_MOD
         prod[0] = (prod[0] + want_eval) % R_MOD
         assert prod == coeffs
+
+
+def test_batch_invert_and_grand_product_vs_python_bigint():
+    import random
+
+    from util import R_MOD
+
+    rng = random.Random(9)
+    n = 150
+    vals = [rng.randrange(R_MOD) for _ in range(n)]
+    vals[7] = vals[64] = 0  # BatchInvert leaves zeros alone
+    a = np.array(ref.pack_fr(vals), dtype=np.uint64)
+    got = ref.unpack_fr(list(ob.batch_invert(a)))
+    assert got == [pow(v, -1, R_MOD) if v else 0 for v in vals]
+    num = [rng.randrange(R_MOD) for _ in range(n)]
+    den = [rng.randrange(1, R_MOD) for _ in range(n)]
+    z = ref.unpack_fr(list(ob.grand_product(np.array(ref.pack_fr(num), dtype=np.uint64), np.array(ref.pack_fr(den), dtype=np.uint64))))
+    run, want = 1, []
+    for x, y in zip(num, den):
+        want.append(run)
+        run = run * x * pow(y, -1, R_MOD) % R_MOD
+    assert z == want
