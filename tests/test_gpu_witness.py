@@ -63,3 +63,21 @@ def test_expand_dev_feeds_commit_without_leaving_hbm(ctx):
         for d in d_cols + [d_b, d_o]:
             ctx.dev_free(d)
         chip.close()
+
+
+def test_multi_exp_22_points_realistic_w_g(ctx):
+    """The size of one proof's `w_g` multi_exp in the reference's own example:
+    22 points -> 711 724 rows, every advice cell bit-exact, result = native MSM."""
+    import random
+
+    chip = h2.B200EccChip()
+    b = ws.Both(chip)
+    res, want, rows = ws.scenario_multi_exp_n(b, random.Random(22), 22)
+    assert rows == 711724  # SURVEY.md App. G row model
+    assert b.value(res) == want
+    xy, ident = chip.to_value(res[1])
+    assert not ident and np.array_equal(xy, ws.xy_mont(want))
+    assert chip.rows() == b.ctx.offset
+    cols = chip.expand(ctx)
+    _compare(b, cols)
+    chip.close()

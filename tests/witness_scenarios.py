@@ -138,3 +138,14 @@ def run(name, chip=None, seed=7):
     b = Both(chip)
     res = scenario(name, b, random.Random(seed))
     return b, res
+
+
+def scenario_multi_exp_n(b, rng, npts):
+    G = ref.G1_GEN
+    pts = [ref.g1_mul(rng.randrange(1, ref.R), G) for _ in range(npts)]
+    scs = [rng.randrange(ref.R) for _ in range(npts)]
+    hp = [b.assign_var(p) for p in pts]
+    hs = [b.assign_scalar(s) for s in scs]
+    start = b.ctx.offset
+    res = b.multi_exp(hp, hs)
+    return res, ref.msm(scs, pts), b.ctx.offset - start
