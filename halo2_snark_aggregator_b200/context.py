@@ -74,8 +74,10 @@ class Context:
     def set_msm_window(self, c):
         self.check(self.lib.h2agg_set_msm_window(self.h, int(c)))
 
-    def set_msm_pair_rounds(self, rounds):
+    def set_msm_pair_rounds(self, rounds, gate=None):
         self.check(self.lib.h2agg_set_msm_pair_rounds(self.h, int(rounds)))
+        if gate is not None:
+            self.check(self.lib.h2agg_set_msm_pair_gate(self.h, int(gate)))
 
     def set_srs_precompute(self, enable):
         self.check(self.lib.h2agg_set_srs_precompute(self.h, 1 if enable else 0))

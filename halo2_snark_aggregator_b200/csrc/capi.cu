@@ -196,6 +196,13 @@ int h2agg_set_msm_pair_rounds(h2agg_ctx* ctx, int rounds) {
   return 0;
 }
 
+int h2agg_set_msm_pair_gate(h2agg_ctx* ctx, uint32_t min_entries) {
+  if (!ctx) return 1;
+  LOCK(ctx);
+  ctx->msm_pair_gate = min_entries;
+  return 0;
+}
+
 int h2agg_set_srs_precompute(h2agg_ctx* ctx, int enable) {
   if (!ctx) return 1;
   LOCK(ctx);

@@ -85,6 +85,7 @@ struct h2agg_ctx {
   // MSM tuning (0 = auto; a forced width also forces plain mode)
   int msm_window_bits = 0;
   int msm_pair_rounds = -1;    // batched-affine halving rounds before the XYZZ accumulation (-1 = auto)
+  uint32_t msm_pair_gate = 1u << 23;  // ... run only when the (padded) entry count reaches this (device-side)
   bool srs_precompute = true;  // build the 2^(c w) P table when an SRS is registered
   // per-kernel-class device timing (CUDA events on ctx->stream), enabled by h2agg_kernel_timing
   bool timing = false;

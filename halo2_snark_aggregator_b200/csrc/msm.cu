@@ -36,6 +36,7 @@ namespace h2agg {
 static constexpr int MSM_THREADS = 128;
 static constexpr uint32_t HOT_PIECES = 8;  // buckets cut into more pieces than this get a whole CTA
 static constexpr uint32_t WSUM_L = 4;      // arity of the window-sum tree
+static constexpr uint32_t ENTRY_DUMMY = 0xffffffffu;  // padding slot of the sorted entry list
 
 struct MsmGeom {
   uint32_t n;          // scalars in this MSM
@@ -48,6 +49,8 @@ struct MsmGeom {
   uint32_t win_begin, win_end;
   uint32_t table;      // 1: entries index the precomputed table [w][srs_n]
   uint32_t srs_n;      // row length of the table
+  uint32_t pair_rounds;  // batched-affine halving rounds compiled into this launch sequence (0..3)
+  uint32_t pair_gate;    // ... which only run when the padded entry count reaches this
 };
 
 int msm_window_config(size_t n, int forced_c, int* c_out, int* nwin_out) {
@@ -161,13 +164,13 @@ __device__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total, uint32_t* 
   return woff + inc - v;
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) msm_scan1(const uint32_t* __restrict__ counts, uint32_t nb,
+__global__ void __launch_bounds__(SCAN_THREADS) msm_scan1(const uint32_t* __restrict__ counts, uint32_t nb, uint32_t pad,
                                                            uint32_t* block_sums) {
   __shared__ uint32_t sh[SCAN_THREADS / 32];
   uint32_t base = blockIdx.x * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS;
   uint32_t acc = 0;
 #pragma unroll
-  for (uint32_t k = 0; k < SCAN_ITEMS; k++) acc += (base + k < nb) ? counts[base + k] : 0;
+  for (uint32_t k = 0; k < SCAN_ITEMS; k++) acc += (base + k < nb) ? ((counts[base + k] + pad) & ~pad) : 0;
   uint32_t tot;
   block_exclusive_scan(acc, &tot, sh);
   if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
@@ -193,7 +196,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) msm_scan2(uint32_t* block_sums, 
 }
 
 // offsets[nb+1] and cursor[nb] (= offsets, consumed by the scatter)
-__global__ void __launch_bounds__(SCAN_THREADS) msm_scan3(const uint32_t* __restrict__ counts, uint32_t nb,
+__global__ void __launch_bounds__(SCAN_THREADS) msm_scan3(const uint32_t* __restrict__ counts, uint32_t nb, uint32_t pad,
                                                            const uint32_t* __restrict__ block_sums, uint32_t* offsets,
                                                            uint32_t* cursor) {
   __shared__ uint32_t sh[SCAN_THREADS / 32];
@@ -202,7 +205,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) msm_scan3(const uint32_t* __rest
   uint32_t acc = 0;
 #pragma unroll
   for (uint32_t k = 0; k < SCAN_ITEMS; k++) {
-    cnt[k] = (base + k < nb) ? counts[base + k] : 0;
+    cnt[k] = (base + k < nb) ? ((counts[base + k] + pad) & ~pad) : 0;
     acc += cnt[k];
   }
   uint32_t tot;
@@ -222,14 +225,21 @@ __global__ void __launch_bounds__(SCAN_THREADS) msm_scan3(const uint32_t* __rest
 //   entirely inside one chunk           -> written straight to bucket_sums[b]
 //   first piece (bucket starts in t)    -> tail_part[t]
 //   every later piece (chunks t+1..)    -> head_part[t']
-__global__ void __launch_bounds__(MSM_THREADS) msm_accumulate(const uint8_t* __restrict__ bases,
-                                                               const uint32_t* __restrict__ entries,
+__global__ void __launch_bounds__(MSM_THREADS) msm_accumulate(const uint8_t* __restrict__ bases_in,
+                                                               const uint32_t* __restrict__ entries_in,
+                                                               const uint8_t* __restrict__ paired_pts,
                                                                const uint32_t* __restrict__ offsets, MsmGeom g,
                                                                uint8_t* __restrict__ head_part,
                                                                uint8_t* __restrict__ tail_part,
                                                                uint8_t* __restrict__ bucket_sums) {
+  // after `pair_rounds` halving rounds (if the device-side gate let them run) the points are already in
+  // bucket order in `paired_pts` and every offset is divided by 2^rounds
+  const bool paired = g.pair_rounds && __ldg(offsets + g.nb) >= g.pair_gate;
+  const uint32_t sh = paired ? g.pair_rounds : 0;
+  const uint8_t* __restrict__ bases = paired ? paired_pts : bases_in;
+  const uint32_t* __restrict__ entries = paired ? nullptr : entries_in;
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t total = __ldg(offsets + g.nb);
+  const uint32_t total = __ldg(offsets + g.nb) >> sh;
   const unsigned long long start64 = (unsigned long long)t * g.chunk;
   if (start64 >= total) return;
   const uint32_t start = (uint32_t)start64;
@@ -238,10 +248,10 @@ __global__ void __launch_bounds__(MSM_THREADS) msm_accumulate(const uint8_t* __r
   uint32_t lo = 0, hi = g.nb;  // offsets[lo] <= start < offsets[hi]
   while (hi - lo > 1) {
     uint32_t mid = (lo + hi) >> 1;
-    if (__ldg(offsets + mid) <= start) lo = mid; else hi = mid;
+    if ((__ldg(offsets + mid) >> sh) <= start) lo = mid; else hi = mid;
   }
   uint32_t b = lo;
-  uint32_t bbeg = __ldg(offsets + b), bend = __ldg(offsets + b + 1);
+  uint32_t bbeg = __ldg(offsets + b) >> sh, bend = __ldg(offsets + b + 1) >> sh;
   G1Xyzz acc = G1Xyzz::identity();
   // ONE flat loop over the chunk: the bucket switch is a short predicated side branch, so the
   // lanes of a warp stay converged on the expensive mixed addition (a nested per-bucket loop
@@ -253,11 +263,12 @@ __global__ void __launch_bounds__(MSM_THREADS) msm_accumulate(const uint8_t* __r
       else acc.store(bucket_sums + (size_t)b * 128);
       acc = G1Xyzz::identity();
       b++;
-      while (__ldg(offsets + b + 1) <= k) b++;  // skip empty buckets; k < total so this terminates
-      bbeg = __ldg(offsets + b);
-      bend = __ldg(offsets + b + 1);
+      while ((__ldg(offsets + b + 1) >> sh) <= k) b++;  // skip empty buckets; k < total so this terminates
+      bbeg = __ldg(offsets + b) >> sh;
+      bend = __ldg(offsets + b + 1) >> sh;
     }
     uint32_t e = entries ? __ldg(entries + k) : k;  // no entry list: the points are already in bucket order
+    if (e == ENTRY_DUMMY) continue;                 // padding slot
     G1Affine q = G1Affine::load_nc(bases + (size_t)(e & 0x7fffffffu) * 64);
     if (e >> 31) q.y = fp_neg(q.y);
     xyzz_madd(acc, q);
@@ -268,110 +279,133 @@ __global__ void __launch_bounds__(MSM_THREADS) msm_accumulate(const uint8_t* __r
 }
 
 // ---- batched-affine pair rounds ------------------------------------------------------------------------
-// Before the XYZZ accumulation the sorted list is halved a few times: in every bucket, neighbours
-// (2j, 2j+1) are added in AFFINE coordinates with one shared inversion per PAIR_B additions per thread
-// (Montgomery's trick: a forward pass of running denominator products, one inversion, a backward pass).
-// An affine addition then costs 5M + 1S instead of the 8M + 2S of an XYZZ mixed addition, which is what
-// matters on a part whose 256-bit multiplier (the fmaheavy pipe) is the bound.  P = Q, P = -Q and the
-// identity are handled exactly; an odd leftover of a bucket is copied through.
+// Before the XYZZ accumulation the sorted list can be halved a few times: neighbours (2k, 2k+1) are added
+// in AFFINE coordinates with a shared inversion (Montgomery's trick: a forward pass of running denominator
+// products, one inversion, a backward pass): 5M + 1S per addition instead of the 8M + 2S of an XYZZ mixed
+// addition, which is what matters on a part whose 256-bit multiplier (the fmaheavy pipe) is the bound.
+// Every bucket's slice of the sorted list is padded to a multiple of 2^rounds with dummy (identity) entries,
+// so pairs never straddle buckets, the bucket offsets simply halve, and a round is a plain map over pairs.
+// The inversion is shared by a whole CTA (prefix/suffix product scans in shared memory, one Fermat inversion
+// per 128 x PAIR_B additions).  P = Q, P = -Q and identities are handled exactly.
+// The rounds are gated ON THE DEVICE by the number of entries (small-scalar witness columns have few and would
+// only pay the extra latency): every kernel evaluates the same predicate on offsets[nb].
 static constexpr uint32_t PAIR_B = 256;
-
-__global__ void msm_half_counts(const uint32_t* __restrict__ off_in, uint32_t nb, uint32_t* __restrict__ counts) {
-  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < nb) counts[b] = (off_in[b + 1] - off_in[b] + 1) >> 1;
-  if (b == nb) counts[b] = 0;
-}
-
-struct PairIn {
-  G1Affine p, q;
-  bool pair;
-};
 
 __device__ __forceinline__ G1Affine pair_load(const uint8_t* __restrict__ points, const uint32_t* __restrict__ entries,
                                               uint32_t i) {
-  uint32_t e = entries ? __ldg(entries + i) : i;
-  G1Affine a = G1Affine::load_nc(points + (size_t)(e & 0x7fffffffu) * 64);
-  if (e >> 31) a.y = fp_neg(a.y);
-  return a;
+  G1Affine a;
+  if (entries) {
+    uint32_t e = __ldg(entries + i);
+    if (e == ENTRY_DUMMY) {
+      a.x = Fq::zero();
+      a.y = Fq::zero();
+      return a;
+    }
+    a = G1Affine::load_nc(points + (size_t)(e & 0x7fffffffu) * 64);
+    if (e >> 31) a.y = fp_neg(a.y);
+    return a;
+  }
+  return G1Affine::load_nc(points + (size_t)i * 64);
 }
 
 // classification shared by both passes: 0 copy p, 1 copy q, 2 identity, 3 double, 4 general
-__device__ __forceinline__ int pair_denominator(const PairIn& in, Fq& d) {
+__device__ __forceinline__ int pair_denominator(const G1Affine& p, const G1Affine& q, Fq& d) {
   d = Fq::one();
-  if (!in.pair || in.q.is_identity()) return 0;
-  if (in.p.is_identity()) return 1;
-  if (in.p.x == in.q.x) {
-    if (in.p.y == in.q.y && !in.p.y.is_zero()) {
-      d = fp_dbl(in.p.y);
+  if (q.is_identity()) return 0;
+  if (p.is_identity()) return 1;
+  if (p.x == q.x) {
+    if (p.y == q.y && !p.y.is_zero()) {
+      d = fp_dbl(p.y);
       return 3;
     }
     return 2;
   }
-  d = in.q.x - in.p.x;
+  d = q.x - p.x;
   return 4;
+}
+
+// 1 / run for every thread of the CTA with ONE inversion: inclusive prefix and suffix product scans
+__device__ __forceinline__ Fq block_shared_inverse(const Fq& run, uint4* sh /* 2 * MSM_THREADS * 2 uint4 */) {
+  const uint32_t t = threadIdx.x;
+  uint4* pre = sh;
+  uint4* suf = sh + 2 * MSM_THREADS;
+  Fq p = run, q = run;
+  for (uint32_t off = 1; off < MSM_THREADS; off <<= 1) {
+    pre[2 * t] = p.lo4(); pre[2 * t + 1] = p.hi4();
+    suf[2 * t] = q.lo4(); suf[2 * t + 1] = q.hi4();
+    __syncthreads();
+    if (t >= off) p = p * Fq::from_halves(pre[2 * (t - off)], pre[2 * (t - off) + 1]);
+    if (t + off < MSM_THREADS) q = q * Fq::from_halves(suf[2 * (t + off)], suf[2 * (t + off) + 1]);
+    __syncthreads();
+  }
+  pre[2 * t] = p.lo4(); pre[2 * t + 1] = p.hi4();
+  suf[2 * t] = q.lo4(); suf[2 * t + 1] = q.hi4();
+  __syncthreads();
+  __shared__ uint4 inv_total[2];
+  if (t == 0) {
+    Fq it = fp_inv(Fq::from_halves(pre[2 * (MSM_THREADS - 1)], pre[2 * (MSM_THREADS - 1) + 1]));
+    inv_total[0] = it.lo4();
+    inv_total[1] = it.hi4();
+  }
+  __syncthreads();
+  Fq r = Fq::from_halves(inv_total[0], inv_total[1]);
+  if (t > 0) r = r * Fq::from_halves(pre[2 * (t - 1)], pre[2 * (t - 1) + 1]);
+  if (t + 1 < MSM_THREADS) r = r * Fq::from_halves(suf[2 * (t + 1)], suf[2 * (t + 1) + 1]);
+  __syncthreads();
+  return r;
 }
 
 __global__ void __launch_bounds__(MSM_THREADS) msm_pair_round(const uint8_t* __restrict__ points,
                                                                const uint32_t* __restrict__ entries,
-                                                               const uint32_t* __restrict__ off_in,
-                                                               const uint32_t* __restrict__ off_out, uint32_t nb,
-                                                               uint8_t* __restrict__ out, uint8_t* __restrict__ scratch,
-                                                               uint32_t nthreads) {
+                                                               const uint32_t* __restrict__ offsets, uint32_t nb,
+                                                               uint32_t shift_in, uint32_t gate, uint8_t* __restrict__ out,
+                                                               uint8_t* __restrict__ scratch, uint32_t nthreads) {
+  __shared__ uint4 sh[4 * MSM_THREADS];
+  const uint32_t padded_total = __ldg(offsets + nb);
+  if (padded_total < gate) return;  // grid-uniform
+  const uint32_t total_out = (padded_total >> shift_in) >> 1;
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t total = __ldg(off_out + nb);
   const unsigned long long start64 = (unsigned long long)t * PAIR_B;
-  if (start64 >= total) return;
-  const uint32_t start = (uint32_t)start64;
-  const uint32_t end = (uint32_t)min((unsigned long long)total, start64 + PAIR_B);
-  uint32_t lo = 0, hi = nb;  // off_out[lo] <= start < off_out[hi]
-  while (hi - lo > 1) {
-    uint32_t mid = (lo + hi) >> 1;
-    if (__ldg(off_out + mid) <= start) lo = mid; else hi = mid;
-  }
-  uint32_t b = lo;
+  const bool active = start64 < total_out;
+  const uint32_t start = active ? (uint32_t)start64 : 0;
+  const uint32_t end = active ? (uint32_t)min((unsigned long long)total_out, start64 + PAIR_B) : 0;
+  if ((unsigned long long)blockIdx.x * blockDim.x * PAIR_B >= total_out) return;  // whole CTA idle
   Fq run = Fq::one();
   // forward: running products of the denominators
+#pragma unroll 2
   for (uint32_t o = start; o < end; o++) {
-    while (__ldg(off_out + b + 1) <= o) b++;
-    const uint32_t i0 = __ldg(off_in + b) + 2 * (o - __ldg(off_out + b));
-    PairIn in;
-    in.pair = i0 + 1 < __ldg(off_in + b + 1);
-    in.p = pair_load(points, entries, i0);
-    if (in.pair) in.q = pair_load(points, entries, i0 + 1);
+    G1Affine p = pair_load(points, entries, 2 * o);
+    G1Affine q = pair_load(points, entries, 2 * o + 1);
     Fq d;
-    pair_denominator(in, d);
+    pair_denominator(p, q, d);
     run.store(scratch + ((size_t)(o - start) * nthreads + t) * 32);
     run = run * d;
   }
-  Fq inv = fp_inv(run);
+  Fq inv = block_shared_inverse(run, sh);
   // backward: peel the individual inverses off and finish the additions
+#pragma unroll 2
   for (uint32_t o = end; o-- > start;) {
-    while (__ldg(off_out + b) > o) b--;
-    const uint32_t i0 = __ldg(off_in + b) + 2 * (o - __ldg(off_out + b));
-    PairIn in;
-    in.pair = i0 + 1 < __ldg(off_in + b + 1);
-    in.p = pair_load(points, entries, i0);
-    if (in.pair) in.q = pair_load(points, entries, i0 + 1);
+    G1Affine p = pair_load(points, entries, 2 * o);
+    G1Affine q = pair_load(points, entries, 2 * o + 1);
     Fq d;
-    const int kind = pair_denominator(in, d);
+    const int kind = pair_denominator(p, q, d);
     Fq dinv = inv * Fq::load(scratch + ((size_t)(o - start) * nthreads + t) * 32);
     inv = inv * d;
     G1Affine r;
-    if (kind == 4 || kind == 3) {
+    if (kind >= 3) {
       Fq lam;
       if (kind == 4) {
-        lam = (in.q.y - in.p.y) * dinv;
+        lam = (q.y - p.y) * dinv;
       } else {
-        Fq xx = fp_sqr(in.p.x);
+        Fq xx = fp_sqr(p.x);
         lam = (fp_dbl(xx) + xx) * dinv;
       }
-      const Fq& x2 = (kind == 4) ? in.q.x : in.p.x;
-      r.x = fp_sqr(lam) - in.p.x - x2;
-      r.y = lam * (in.p.x - r.x) - in.p.y;
+      r.x = fp_sqr(lam) - p.x - q.x;  // q.x == p.x when doubling
+      r.y = lam * (p.x - r.x) - p.y;
     } else if (kind == 0) {
-      r = in.p;
+      r = p;
     } else if (kind == 1) {
-      r = in.q;
+      r = q;
     } else {
       r.x = Fq::zero();
       r.y = Fq::zero();
@@ -389,7 +423,8 @@ __global__ void __launch_bounds__(MSM_THREADS) msm_fold(const uint32_t* __restri
                                                          uint32_t* hot_list) {
   uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= g.nb) return;
-  uint32_t beg = offsets[b], end = offsets[b + 1];
+  const uint32_t sh = (g.pair_rounds && offsets[g.nb] >= g.pair_gate) ? g.pair_rounds : 0;
+  uint32_t beg = offsets[b] >> sh, end = offsets[b + 1] >> sh;
   if (beg == end) {
     G1Xyzz::identity().store(bucket_sums + (size_t)b * 128);
     return;
@@ -413,9 +448,10 @@ __global__ void __launch_bounds__(256) msm_fold_hot(const uint32_t* __restrict__
                                                      const uint32_t* __restrict__ hot_list) {
   __shared__ uint4 sh[256 * 8];  // one XYZZ point (128 B) per thread
   uint32_t nhot = *hot_count;
+  const uint32_t sh2 = (g.pair_rounds && offsets[g.nb] >= g.pair_gate) ? g.pair_rounds : 0;
   for (uint32_t h = blockIdx.x; h < nhot; h += gridDim.x) {
     uint32_t b = hot_list[h];
-    uint32_t beg = offsets[b], end = offsets[b + 1];
+    uint32_t beg = offsets[b] >> sh2, end = offsets[b + 1] >> sh2;
     uint32_t t0 = beg / g.chunk, t1 = (end - 1) / g.chunk;
     G1Xyzz acc = G1Xyzz::identity();
     if (threadIdx.x == 0) acc = G1Xyzz::load(tail_part + (size_t)t0 * 128);
@@ -654,7 +690,14 @@ int msm_run(h2agg_ctx* ctx, cudaStream_t st, DevBuf& wsbuf, const MsmBases& base
   if (g.win_begin > g.win_end) g.win_begin = g.win_end;
   g.chunk = 128;
   const uint8_t* d_points = (const uint8_t*)(table ? bases.d_table : bases.d_bases);
-  const size_t max_entries = (size_t)n * (g.win_end - g.win_begin);
+  // "auto" (-1) keeps the batched-affine rounds off: measured on B200 they do not beat the XYZZ path yet
+  // (DESIGN.md 7b); 1..3 turns them on, gated on the device by the number of entries.
+  const int pair_rounds = (ctx->msm_pair_rounds >= 0) ? ctx->msm_pair_rounds : 0;
+  const uint32_t pad = pair_rounds ? ((1u << pair_rounds) - 1) : 0;
+  g.pair_rounds = (uint32_t)pair_rounds;
+  g.pair_gate = ctx->msm_pair_gate;
+  // every non-empty bucket is padded to a multiple of 2^pair_rounds
+  const size_t max_entries = (size_t)n * (g.win_end - g.win_begin) + (size_t)pad * g.nb;
   if (max_entries >= (1ull << 32) - 1) {
     ctx->last_error = "msm: n * windows exceeds the 32-bit entry index";
     return 1;
@@ -675,21 +718,12 @@ int msm_run(h2agg_ctx* ctx, cudaStream_t st, DevBuf& wsbuf, const MsmBases& base
   size_t o_bsums = carve((size_t)scan_blocks * 4);
   size_t o_hot = carve((size_t)(g.nb + 1) * 4 + 256);
   size_t o_entries = carve((max_entries + 1) * 4);
-  // batched-affine pair rounds (large MSMs only)
-  // Measured on B200 (round 1): with per-thread Fermat inversions and re-gathered operands the rounds are
-  // latency-bound and lose to the XYZZ path (uniform 2^22 column: 17.5 ms vs 12.6 ms), so "auto" keeps them off;
-  // they stay selectable (h2agg_set_msm_pair_rounds) and parity-tested as the base for next round's work.
-  const int pair_rounds = (ctx->msm_pair_rounds >= 0) ? ctx->msm_pair_rounds : 0;
-  size_t pr_max[4] = {max_entries, 0, 0, 0};
-  size_t o_pr_pts[4] = {0, 0, 0, 0}, o_pr_off[4] = {0, 0, 0, 0};
+  // batched-affine pair rounds: outputs of the rounds + prefix-product scratch
+  size_t o_pr_pts[4] = {0, 0, 0, 0};
   size_t o_pr_scratch = 0, pr_threads = 0;
-  for (int r = 1; r <= pair_rounds; r++) {
-    pr_max[r] = (pr_max[r - 1] + g.nb) / 2 + 1;
-    o_pr_pts[r] = carve(pr_max[r] * 64);
-    o_pr_off[r] = carve((size_t)(g.nb + 1) * 4);
-  }
+  for (int r = 1; r <= pair_rounds; r++) o_pr_pts[r] = carve(((max_entries >> r) + 1) * 64);
   if (pair_rounds > 0) {
-    pr_threads = align_up((pr_max[1] + PAIR_B - 1) / PAIR_B, MSM_THREADS);
+    pr_threads = align_up(((max_entries >> 1) + PAIR_B - 1) / PAIR_B, MSM_THREADS);
     o_pr_scratch = carve(pr_threads * PAIR_B * 32);
   }
   size_t o_head = carve(max_chunks * 128);
@@ -721,10 +755,11 @@ int msm_run(h2agg_ctx* ctx, cudaStream_t st, DevBuf& wsbuf, const MsmBases& base
     msm_digits<false><<<dgrid, 256, 0, st>>>((const uint4*)d_scalars, g, counts, nullptr);
     ctx->launches++;
   }
-  msm_scan1<<<scan_blocks, SCAN_THREADS, 0, st>>>(counts, g.nb, bsums);
+  msm_scan1<<<scan_blocks, SCAN_THREADS, 0, st>>>(counts, g.nb, pad, bsums);
   msm_scan2<<<1, SCAN_THREADS, 0, st>>>(bsums, scan_blocks);
-  msm_scan3<<<scan_blocks, SCAN_THREADS, 0, st>>>(counts, g.nb, bsums, offsets, cursor);
+  msm_scan3<<<scan_blocks, SCAN_THREADS, 0, st>>>(counts, g.nb, pad, bsums, offsets, cursor);
   ctx->launches += 3;
+  if (pad) H2AGG_CUDA(ctx, cudaMemsetAsync(entries, 0xff, (max_entries + 1) * 4, st));  // dummy = identity
   if (n) {
     {
       ScopedKernelTimer tk(ctx, KC_MSM_DIGITS, st);
@@ -735,22 +770,15 @@ int msm_run(h2agg_ctx* ctx, cudaStream_t st, DevBuf& wsbuf, const MsmBases& base
     const uint8_t* cur_pts = d_points;
     const uint32_t* cur_entries = entries;
     for (int r = 1; r <= pair_rounds; r++) {
-      uint32_t* off_r = (uint32_t*)(ws + o_pr_off[r]);
-      msm_half_counts<<<(g.nb + 1 + 255) / 256, 256, 0, st>>>(offsets, g.nb, counts);
-      msm_scan1<<<scan_blocks, SCAN_THREADS, 0, st>>>(counts, g.nb, bsums);
-      msm_scan2<<<1, SCAN_THREADS, 0, st>>>(bsums, scan_blocks);
-      msm_scan3<<<scan_blocks, SCAN_THREADS, 0, st>>>(counts, g.nb, bsums, off_r, cursor);
-      const uint32_t nthr = (uint32_t)align_up((pr_max[r] + PAIR_B - 1) / PAIR_B, MSM_THREADS);
-      msm_pair_round<<<nthr / MSM_THREADS, MSM_THREADS, 0, st>>>(cur_pts, cur_entries, offsets, off_r, g.nb, ws + o_pr_pts[r],
-                                                                ws + o_pr_scratch, nthr);
-      ctx->launches += 5;
+      const uint32_t nthr = (uint32_t)align_up(((max_entries >> r) + PAIR_B - 1) / PAIR_B, MSM_THREADS);
+      msm_pair_round<<<nthr / MSM_THREADS, MSM_THREADS, 0, st>>>(cur_pts, cur_entries, offsets, g.nb, (uint32_t)(r - 1),
+                                                                g.pair_gate, ws + o_pr_pts[r], ws + o_pr_scratch, nthr);
+      ctx->launches++;
       cur_pts = ws + o_pr_pts[r];
       cur_entries = nullptr;
-      offsets = off_r;
     }
-    const size_t acc_chunks = (pair_rounds ? pr_max[pair_rounds] : max_entries) / g.chunk + 1;
-    msm_accumulate<<<(uint32_t)((acc_chunks + MSM_THREADS - 1) / MSM_THREADS), MSM_THREADS, 0, st>>>(
-        cur_pts, cur_entries, offsets, g, head_part, tail_part, buckets);
+    msm_accumulate<<<(uint32_t)((max_chunks + MSM_THREADS - 1) / MSM_THREADS), MSM_THREADS, 0, st>>>(
+        d_points, entries, pair_rounds ? ws + o_pr_pts[pair_rounds] : nullptr, offsets, g, head_part, tail_part, buckets);
     ctx->launches++;
   }
   ScopedKernelTimer t_red(ctx, KC_MSM_REDUCE, st);

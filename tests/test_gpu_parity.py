@@ -310,7 +310,7 @@ def test_ntt_host_batches_pipelined(ctx):
 def test_msm_batched_affine_pair_rounds(ctx, rounds):
     """Force the batched-affine halving rounds on small inputs, including every special case of the
     affine group law (P+P, P-P, identity operands, hot buckets, odd leftovers)."""
-    ctx.set_msm_pair_rounds(rounds)
+    ctx.set_msm_pair_rounds(rounds, gate=0)  # gate 0: run the rounds whatever the size
     try:
         n = 3000
         b = ob.gen_bases(5, n)
@@ -345,8 +345,13 @@ def test_msm_batched_affine_pair_rounds(ctx, rounds):
             s = ob.gen_scalars(60, 0, m)
             bb = ob.gen_bases(61, m)
             assert np.array_equal(ctx.msm_g1(s, bb), ob.best_multiexp(s, bb))
+        # device-side gate: below it the padded list goes straight to the XYZZ path
+        ctx.set_msm_pair_rounds(rounds, gate=1 << 30)
+        s = ob.gen_scalars(62, 1, 5000)
+        bb = ob.gen_bases(63, 5000)
+        assert np.array_equal(ctx.msm_g1(s, bb), ob.best_multiexp(s, bb))
     finally:
-        ctx.set_msm_pair_rounds(-1)
+        ctx.set_msm_pair_rounds(-1, gate=1 << 23)
         ctx.set_msm_window(0)
 
 
