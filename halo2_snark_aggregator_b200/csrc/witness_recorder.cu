@@ -121,14 +121,72 @@ static inline Fq q_small(u64 x) {
   u64 c[4] = {x, 0, 0, 0};
   return q_from_canon(c);
 }
-static Fq q_inv(const Fq& a) {  // a^(p-2); 0 -> 0
-  u64 e[4] = {QP[0] - 2, QP[1], QP[2], QP[3]};
-  Fq r = q_small(1);
-  for (int i = 255; i >= 0; i--) {
-    r = q_mul(r, r);
-    if ((e[i >> 6] >> (i & 63)) & 1) r = q_mul(r, a);
+// 256-bit helpers for the binary extended Euclid below (little-endian u64 x 4)
+static inline bool u256_is_one(const u64* a) { return a[0] == 1 && (a[1] | a[2] | a[3]) == 0; }
+static inline bool u256_geq(const u64* a, const u64* b) {
+  for (int i = 3; i >= 0; i--) {
+    if (a[i] > b[i]) return true;
+    if (a[i] < b[i]) return false;
   }
-  return r;
+  return true;
+}
+static inline void u256_sub(u64* a, const u64* b) {
+  u64 bo = 0;
+  for (int i = 0; i < 4; i++) {
+    u128 d = (u128)a[i] - b[i] - bo;
+    a[i] = (u64)d;
+    bo = (u64)(d >> 64) & 1;
+  }
+}
+static inline void u256_shr1(u64* a, u64 top) {
+  for (int i = 0; i < 3; i++) a[i] = (a[i] >> 1) | (a[i + 1] << 63);
+  a[3] = (a[3] >> 1) | (top << 63);
+}
+// x <- x / 2 mod p
+static inline void q_half(u64* x) {
+  u64 top = 0;
+  if (x[0] & 1) {
+    u128 c = 0;
+    for (int i = 0; i < 4; i++) {
+      c += (u128)x[i] + QP[i];
+      x[i] = (u64)c;
+      c >>= 64;
+    }
+    top = (u64)c;
+  }
+  u256_shr1(x, top);
+}
+// Inverse in Montgomery form (0 -> 0): binary extended Euclid on the Montgomery residue aR gives
+// (aR)^-1; one Montgomery product with R^3 turns that into a^-1 R.  ~1.5 us instead of ~13 us for a
+// 254-bit Fermat ladder: `div` needs one native inverse per curve operation and dominated recording.
+static const u64 QR3[4] = {0xb1cd6dafda1530dfULL, 0x62f210e6a7283db6ULL, 0xef7f0b0c0ada0afbULL, 0x20fd6e902d592544ULL};
+static Fq q_inv(const Fq& a) {
+  if (q_is_zero(a)) return q_zero();
+  u64 u[4] = {a.v[0], a.v[1], a.v[2], a.v[3]};
+  u64 v[4] = {QP[0], QP[1], QP[2], QP[3]};
+  u64 x1[4] = {1, 0, 0, 0}, x2[4] = {0, 0, 0, 0};
+  while (!u256_is_one(u) && !u256_is_one(v)) {
+    while (!(u[0] & 1)) {
+      u256_shr1(u, 0);
+      q_half(x1);
+    }
+    while (!(v[0] & 1)) {
+      u256_shr1(v, 0);
+      q_half(x2);
+    }
+    if (u256_geq(u, v)) {
+      u256_sub(u, v);
+      Fq r = q_sub(Fq{{x1[0], x1[1], x1[2], x1[3]}}, Fq{{x2[0], x2[1], x2[2], x2[3]}});
+      memcpy(x1, r.v, 32);
+    } else {
+      u256_sub(v, u);
+      Fq r = q_sub(Fq{{x2[0], x2[1], x2[2], x2[3]}}, Fq{{x1[0], x1[1], x1[2], x1[3]}});
+      memcpy(x2, r.v, 32);
+    }
+  }
+  const u64* x = u256_is_one(u) ? x1 : x2;
+  Fq r3{{QR3[0], QR3[1], QR3[2], QR3[3]}};
+  return q_mul(Fq{{x[0], x[1], x[2], x[3]}}, r3);
 }
 
 // ---- assigned objects (value semantics: a C++ copy is a Rust `.clone()`) ---------------------------
@@ -177,6 +235,7 @@ struct Recorder {
   std::vector<HScalar> scalars;
 
   Recorder() {
+    ops.reserve(1 << 20);  // 256 MiB of records up front: no reallocation copies while recording
     // limbs of p
     u64 c[4] = {QP[0], QP[1], QP[2], QP[3]};
     canon_to_limbs(c, p_limbs);
