@@ -53,6 +53,7 @@ def load():
         "h2agg_host_register": (ci, [c_vp, c_vp, sz]),
         "h2agg_host_unregister": (ci, [c_vp, c_vp]),
         "h2agg_set_msm_window": (ci, [c_vp, ci]),
+        "h2agg_set_ntt_radix_cap": (ci, [c_vp, ci]),
         "h2agg_set_msm_pair_rounds": (ci, [c_vp, ci]),
         "h2agg_set_msm_pair_gate": (ci, [c_vp, u32]),
         "h2agg_set_srs_precompute": (ci, [c_vp, ci]),

@@ -74,6 +74,9 @@ class Context:
     def set_msm_window(self, c):
         self.check(self.lib.h2agg_set_msm_window(self.h, int(c)))
 
+    def set_ntt_radix_cap(self, log2_radix):
+        self.check(self.lib.h2agg_set_ntt_radix_cap(self.h, int(log2_radix)))
+
     def set_msm_pair_rounds(self, rounds, gate=None):
         self.check(self.lib.h2agg_set_msm_pair_rounds(self.h, int(rounds)))
         if gate is not None:

@@ -188,6 +188,21 @@ int h2agg_set_msm_window(h2agg_ctx* ctx, int c_bits) {
   return 0;
 }
 
+int h2agg_set_ntt_radix_cap(h2agg_ctx* ctx, int log2_radix) {
+  if (!ctx) return 1;
+  LOCK(ctx);
+  CHECK_ARG(ctx, log2_radix >= 2 && log2_radix <= 8, "ntt radix cap must be in [2, 8]");
+  H2AGG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (auto& t : ctx->tw) {  // the table split follows the plan: drop cached tables
+    cudaFree(t.lo);
+    cudaFree(t.hi);
+    cudaFree(t.full);
+  }
+  ctx->tw.clear();
+  ctx->ntt_radix_cap = (uint32_t)log2_radix;
+  return 0;
+}
+
 int h2agg_set_msm_pair_rounds(h2agg_ctx* ctx, int rounds) {
   if (!ctx) return 1;
   LOCK(ctx);

@@ -79,6 +79,7 @@ struct h2agg_ctx {
   uint64_t next_srs = 1;
   int sm_count = 148;
   bool ntt_attr_set = false;
+  uint32_t ntt_radix_cap = 8;   // largest log2 radix of a pass (test hook: 4..8)
   bool ntt_full_tables = true;  // trade N x 32 B of HBM per (omega, k) for one product per element in the first pass  // dynamic shared-memory opt-in done for this device
   // counters (claimed in bench.py as gpu_launches)
   uint64_t launches = 0;

@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) ntt_pass_kernel(const __grid_c
   }
 }
 
-int plan_passes(uint32_t log_n, uint32_t* s);
+int plan_passes(const h2agg_ctx* ctx, uint32_t log_n, uint32_t* s);
 
 static int get_tables(h2agg_ctx* ctx, const uint64_t* omega, uint32_t log_n, TwiddleTable** out) {
   ctx->tick++;
@@ -318,7 +318,7 @@ static int get_tables(h2agg_ctx* ctx, const uint64_t* omega, uint32_t log_n, Twi
   // i.e. a direct T_hi hit; only the first pass pays one multiplication to combine T_lo * T_hi.
   {
     uint32_t sp[4];
-    int T = plan_passes(log_n, sp);
+    int T = plan_passes(ctx, log_n, sp);
     t.lo_bits = (T == 1) ? (log_n + 1) / 2 : sp[0];
   }
   uint32_t hi_bits = log_n - t.lo_bits;
@@ -349,12 +349,15 @@ static int get_tables(h2agg_ctx* ctx, const uint64_t* omega, uint32_t log_n, Twi
 }
 
 // split log_n into pass radices
-int plan_passes(uint32_t log_n, uint32_t* s) {
-  if (log_n <= NTT_TILE_LOG) {
+int plan_passes(const h2agg_ctx* ctx, uint32_t log_n, uint32_t* s) {
+  // ntt_radix_cap (test hook, default 8) lowers the largest per-pass radix so the 2/3/4-pass code paths
+  // can be exercised at sizes the CPU oracle finishes in seconds
+  const uint32_t cap = ctx->ntt_radix_cap;
+  if (log_n <= (cap == 8 ? NTT_TILE_LOG : cap)) {
     s[0] = log_n;
     return 1;
   }
-  int T = (log_n + 7) / 8;
+  int T = (log_n + cap - 1) / cap;
   uint32_t base = log_n / T, extra = log_n % T;
   for (int t = 0; t < T; t++) s[t] = base + (t < (int)extra ? 1 : 0);
   return T;
@@ -388,7 +391,11 @@ int ntt_run(h2agg_ctx* ctx, const void* d_src, void* d_dst, const NttOpts& o, cu
   if (rc) return rc;
 
   uint32_t s[4];
-  int T = plan_passes(o.log_n, s);
+  int T = plan_passes(ctx, o.log_n, s);
+  if (T > 4) {
+    ctx->last_error = "ntt: more than 4 passes needed (lower the size or raise the radix cap)";
+    return 1;
+  }
   const void* cur = d_src;
   void* tmp = nullptr;
   if (T > 1) {

@@ -62,6 +62,9 @@ int h2agg_host_register(h2agg_ctx* ctx, const void* p, size_t bytes);
 int h2agg_host_unregister(h2agg_ctx* ctx, const void* p);
 /* MSM window width c in bits (0 = automatic). Exposed for sweeps and tests. */
 int h2agg_set_msm_window(h2agg_ctx* ctx, int c_bits);
+/* Test hook: cap the log2 radix of an NTT pass (default 8) so the multi-pass code paths (up to 4 passes)
+ * can be checked against the CPU oracle at small sizes; log_n must stay <= 4 * cap. */
+int h2agg_set_ntt_radix_cap(h2agg_ctx* ctx, int log2_radix);
 /* Batched-affine halving rounds run before the XYZZ bucket accumulation: 0..3, -1 = automatic
  * (currently 0: measured slower than the XYZZ path on B200). For tests and sweeps. */
 int h2agg_set_msm_pair_rounds(h2agg_ctx* ctx, int rounds);

@@ -419,3 +419,24 @@ def test_grand_product_full_size_telescopes(ctx):
     finally:
         for d in (d_den, d_num, d_z):
             ctx.dev_free(d)
+
+
+@pytest.mark.parametrize("cap,k", [(4, 9), (4, 12), (4, 13), (4, 16), (3, 11), (5, 17), (6, 21)])
+def test_ntt_multi_pass_paths_vs_oracle(ctx, cap, k):
+    """2-, 3- and 4-pass decompositions (incl. the two-middle-digit transposed store) against the oracle,
+    by capping the per-pass radix; plus the fused coset transforms through the same plans."""
+    ctx.set_ntt_radix_cap(cap)
+    try:
+        a = ob.gen_scalars(0x700 + k, 0, 1 << k)
+        w = fr_limbs(omega(k))
+        got = a.copy()
+        ctx.ntt_fr(got, w, k)
+        assert np.array_equal(got, ob.best_fft(a.copy(), w, k))
+        if k + 2 <= 4 * cap:
+            d = domain_consts(k)
+            ext = ctx.coeff_to_extended(a, k, k + 2, d["zeta"], d["omega_ext"])
+            assert np.array_equal(ext, ob.coeff_to_extended(a, k, k + 2, d["zeta"], d["omega_ext"]))
+            back = ctx.extended_to_coeff(ext.copy(), k + 2, d["omega_ext_inv"], d["ext_n_inv"], d["zeta"], 3 << k)
+            assert np.array_equal(back[: 4 << k], a)
+    finally:
+        ctx.set_ntt_radix_cap(8)
