@@ -389,45 +389,40 @@ def main():
         for i in e_msm:
             h_cols[i] = pinned(n * 32)
             h_cols[i][:] = ctx.d2h(t_cols[i].data_ptr(), 4 * n)
-        max_intt = max([len([i for i in my_ntt if units[i][0] == r and units[i][1] == "intt"]) for r in rounds] + [1])
-        h_ntt = [pinned(n * 32) for _ in range(max_intt)]
-        for hbuf in h_ntt:
-            hbuf[:] = ctx.d2h(t_ntt[0].data_ptr(), 4 * n)
+        fused_rounds = (0, 1, 2)  # rounds whose committed columns are also turned into coefficients and extended
+        max_cols = max([len([i for i in e_msm if units[i][0] == r]) for r in fused_rounds] + [1])
+        h_ntt = [pinned(n * 32) for _ in range(max_cols)]
         h_ext = [pinned(ext_n * 32) for _ in range(4)]
         h_ext[0][:] = ctx.d2h(t_ext[0].data_ptr(), 4 * ext_n)
         h2d = d2h = 0
-        for i in e_units:
-            u = units[i]
-            if u[1] == "msm":
-                h2d += n * 32; d2h += 160
-            elif u[1] == "intt":
-                h2d += n * 32; d2h += n * 32
-            elif u[1] == "coset":
-                h2d += n * 32; d2h += ext_n * 32
-            else:
-                h2d += ext_n * 32; d2h += 3 * n * 32
+        for i in e_msm:
+            h2d += n * 32
+            d2h += 160
+            if units[i][0] in fused_rounds:
+                d2h += n * 32 + ext_n * 32
+        if rank == 0:
+            h2d += ext_n * 32
+            d2h += 3 * n * 32
 
         def step_host():
             outs = []
             for r in rounds:
-                mine_r = [(i, units[i]) for i in e_units if units[i][0] == r]
-                msm_ids = [i for i, u in mine_r if u[1] == "msm"]
-                intt_ids = [i for i, u in mine_r if u[1] == "intt"]
-                coset_ids = [i for i, u in mine_r if u[1] == "coset"]
-                # one batched C-ABI call per commit round, as the patched prover would issue them
-                first = [j for j in msm_ids if j < 64] if r == 3 else msm_ids
+                ids = [i for i in e_msm if units[i][0] == r]
+                if r in fused_rounds:
+                    if ids:
+                        # ONE call per commit round: each column is uploaded once, committed, turned into
+                        # coefficients and evaluated on the extended coset; results come back to pinned buffers
+                        outs.append(ctx.commit_round(srs, [h_cols[j] for j in ids], k, dom.omega_inv, dom.ifft_divisor,
+                                                     coeff_out=h_ntt[: len(ids)], ext_k=k + 2, zeta=dom.g_coset,
+                                                     omega_ext=dom.extended_omega, ext_out=[h_ext[j % 4] for j in range(len(ids))]))
+                    continue
+                first = [j for j in ids if j < 64] if r == 3 else ids
                 if first:
                     outs.append(ctx.msm_g1_batch(srs, [h_cols[j] for j in first], n))
-                if intt_ids:
-                    dom.lagrange_to_coeff_many(h_ntt[: len(intt_ids)])
-                if coset_ids:
-                    dom.coeff_to_extended_many([h_ntt[j % len(h_ntt)] for j in range(len(coset_ids))],
-                                               [h_ext[j % 4] for j in range(len(coset_ids))])
-                for i, u in mine_r:
-                    if u[1] == "ext_intt":
-                        ctx.extended_to_coeff(h_ext[0], k + 2, dom.extended_omega_inv, dom.extended_ifft_divisor, dom.g_coset, 3 * n)
                 if r == 3:
-                    late = [j for j in msm_ids if j >= 64]
+                    if rank == 0:
+                        ctx.extended_to_coeff(h_ext[0], k + 2, dom.extended_omega_inv, dom.extended_ifft_divisor, dom.g_coset, 3 * n)
+                    late = [j for j in ids if j >= 64]
                     if late:
                         outs.append(ctx.msm_g1_batch(srs, [h_cols[j] for j in late], n))
             return outs
@@ -445,7 +440,7 @@ def main():
             dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
             dist.all_reduce(t_b, op=dist.ReduceOp.SUM)
         e2e = {"value": float(t_e.item()), "unit": "s", "h2d_bytes_per_step": int(t_b[0].item()), "d2h_bytes_per_step": int(t_b[1].item()),
-               "note": "host-pointer C ABI with pinned buffers: one batched call per commit round (MSMs, iNTTs, coset NTTs), every column uploaded and every transform result downloaded; lanes overlap H2D / kernels / D2H"}
+               "note": "host-pointer C ABI with pinned buffers: one fused call per commit round (h2agg_commit_round: upload once, commit, lagrange_to_coeff, coeff_to_extended; every coefficient vector and every extended evaluation is downloaded), batched MSM calls for the remaining commitments, one extended_to_coeff; lanes overlap H2D / kernels / D2H"}
         del h_cols, h_ntt, h_ext
 
     # ---- witness path (W1-W5): multi_exp of 8 transcript points through the recording chip + expansion kernel

@@ -187,6 +187,17 @@ class Context:
         b = (c_vp * len(out_cols))(*[c.ctypes.data for c in out_cols])
         self.check(self.lib.h2agg_coeff_to_extended_batch(self.h, a, b, len(coeff_cols), k, ext_k, _ptr(zeta), _ptr(omega_ext)))
 
+    def commit_round(self, srs_id, cols, k, omega_inv, n_inv, coeff_out=None, ext_k=0, zeta=None, omega_ext=None, ext_out=None):
+        """Fused commit round -> affine commitments (len(cols), 8); coefficients / extended evaluations land in the given arrays."""
+        nc = len(cols)
+        a = (c_vp * nc)(*[c.ctypes.data for c in cols])
+        co = (c_vp * nc)(*[c.ctypes.data for c in coeff_out]) if coeff_out is not None else None
+        eo = (c_vp * nc)(*[(c.ctypes.data if c is not None else None) for c in ext_out]) if ext_out is not None else None
+        out = np.zeros(8 * nc, dtype=np.uint64)
+        self.check(self.lib.h2agg_commit_round(self.h, srs_id, a, nc, k, _ptr(omega_inv), _ptr(n_inv), _ptr(out), co, ext_k,
+                                               _ptr(zeta), _ptr(omega_ext), eo))
+        return out.reshape(nc, 8)
+
     def ntt_fr_dev(self, d_a, omega, log_n, scale=None):
         self.check(self.lib.h2agg_ntt_fr_dev(self.h, c_vp(d_a), _ptr(omega), _ptr(scale), log_n))
 

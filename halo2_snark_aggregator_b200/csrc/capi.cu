@@ -623,6 +623,70 @@ int h2agg_coeff_to_extended_batch(h2agg_ctx* ctx, const uint64_t* const* coeff_c
   return ntt_host_batch(ctx, coeff_cols, out_cols, n_cols, (size_t)1 << k, (size_t)1 << ext_k, o);
 }
 
+// One commit round fused per column (see h2agg.h): upload once; MSM, iNTT and (optionally) the coset NTT run
+// back to back on the column's lane; the D2H copies of lane A overlap the kernels of lane B and the upload of lane C.
+int h2agg_commit_round(h2agg_ctx* ctx, uint64_t srs_id, const uint64_t* const* lagrange_cols, size_t n_cols, uint32_t k,
+                       const uint64_t omega_inv[4], const uint64_t n_inv[4], uint64_t* out_affine,
+                       uint64_t* const* coeff_out, uint32_t ext_k, const uint64_t zeta[4], const uint64_t omega_ext[4],
+                       uint64_t* const* ext_out) {
+  if (!ctx) return 1;
+  LOCK(ctx);
+  CHECK_ARG(ctx, srs_id != 0 && lagrange_cols && out_affine && omega_inv && n_inv, "commit_round: null argument");
+  CHECK_ARG(ctx, k >= 1 && k <= 28, "commit_round: k out of range");
+  CHECK_ARG(ctx, !ext_out || (zeta && omega_ext && ext_k >= k && ext_k <= 28 && coeff_out), "commit_round: extended output needs zeta, omega_ext and coefficients");
+  CHECK_ARG(ctx, n_cols * 160 <= ctx->small.cap && n_cols * 160 <= ctx->pinned_cap, "commit_round: too many columns");
+  if (n_cols == 0) return 0;
+  H2AGG_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t n = (size_t)1 << k;
+  MsmBases bases;
+  int rc = resolve_bases(ctx, srs_id, nullptr, nullptr, n, &bases);
+  if (rc) return rc;
+  if ((rc = lanes_init(ctx))) return rc;
+  uint64_t s3[12], in3[12];
+  for (int i = 0; i < 3; i++) memcpy(s3 + 4 * i, n_inv, 32);
+  if (ext_out && (rc = coset_consts(ctx, zeta, nullptr, 0, in3))) return rc;
+  NttOpts oi{omega_inv, k, n, n, nullptr, s3};
+  NttOpts oe{omega_ext, ext_k, n, (size_t)1 << ext_k, in3, nullptr};
+  // make sure the (cached) twiddle tables exist before the lanes fork: a zero-length warm-up is not possible,
+  // so the first column's transforms run on the main stream
+  H2AGG_CUDA(ctx, cudaEventRecord(ctx->fork_ev, ctx->stream));
+  for (int l = 0; l < N_LANES; l++) H2AGG_CUDA(ctx, cudaStreamWaitEvent(ctx->lanes[l].st, ctx->fork_ev, 0));
+  for (size_t i = 0; i < n_cols; i++) {
+    Lane& ln = ctx->lanes[i % N_LANES];
+    CHECK_ARG(ctx, lagrange_cols[i], "commit_round: null column");
+    if ((rc = ensure(ctx, ln.io, n * 32 + 64))) return rc;
+    if (ext_out && ext_out[i] && (rc = ensure(ctx, ln.io_out, ((size_t)1 << ext_k) * 32))) return rc;
+    H2AGG_CUDA(ctx, cudaMemcpyAsync(ln.io.p, lagrange_cols[i], n * 32, cudaMemcpyHostToDevice, ln.st));
+    if ((rc = msm_run(ctx, ln.st, ln.ws, bases, ln.io.p, n, (uint8_t*)ctx->small.p + i * 160, 0, -1))) return rc;
+    if (coeff_out && coeff_out[i]) {
+      cudaStream_t st = ln.st;
+      if (i == 0) {  // tables are generated on the main stream: run column 0's transforms there, then re-fork
+        H2AGG_CUDA(ctx, cudaEventRecord(ln.done, ln.st));
+        H2AGG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ln.done, 0));
+        st = ctx->stream;
+      }
+      if ((rc = ntt_run(ctx, ln.io.p, ln.io.p, oi, st, &ln.ntt_tmp))) return rc;
+      H2AGG_CUDA(ctx, cudaMemcpyAsync(coeff_out[i], ln.io.p, n * 32, cudaMemcpyDeviceToHost, st));
+      if (ext_out && ext_out[i]) {
+        if ((rc = ntt_run(ctx, ln.io.p, ln.io_out.p, oe, st, &ln.ntt_tmp))) return rc;
+        H2AGG_CUDA(ctx, cudaMemcpyAsync(ext_out[i], ln.io_out.p, ((size_t)32) << ext_k, cudaMemcpyDeviceToHost, st));
+      }
+      if (i == 0) {
+        H2AGG_CUDA(ctx, cudaEventRecord(ctx->fork_ev, ctx->stream));
+        for (int l = 0; l < N_LANES; l++) H2AGG_CUDA(ctx, cudaStreamWaitEvent(ctx->lanes[l].st, ctx->fork_ev, 0));
+      }
+    }
+  }
+  for (int l = 0; l < N_LANES; l++) {
+    H2AGG_CUDA(ctx, cudaEventRecord(ctx->lanes[l].done, ctx->lanes[l].st));
+    H2AGG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->lanes[l].done, 0));
+  }
+  H2AGG_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, ctx->small.p, n_cols * 160, cudaMemcpyDeviceToHost, ctx->stream));
+  H2AGG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (size_t i = 0; i < n_cols; i++) memcpy(out_affine + i * 8, (uint8_t*)ctx->pinned + i * 160, 64);
+  return 0;
+}
+
 int h2agg_extended_to_coeff_dev(h2agg_ctx* ctx, void* d_a, uint32_t ext_k, const uint64_t omega_ext_inv[4],
                                 const uint64_t ext_n_inv[4], const uint64_t zeta[4], size_t out_len) {
   if (!ctx) return 1;

@@ -145,6 +145,15 @@ int h2agg_extended_to_coeff(h2agg_ctx* ctx, uint64_t* a /* 2^ext_k * 4, in place
 int h2agg_coeff_to_extended_batch(h2agg_ctx* ctx, const uint64_t* const* coeff_cols, uint64_t* const* out_cols,
                                   size_t n_cols, uint32_t k, uint32_t ext_k, const uint64_t zeta[4],
                                   const uint64_t omega_ext[4]);
+/* One commit round, fused per column and pipelined over the lanes: every Lagrange column is uploaded ONCE,
+ * committed against the SRS (commit_lagrange), turned into coefficients (lagrange_to_coeff) and, when ext_out is
+ * given, evaluated on the extended coset (coeff_to_extended) -- the three things create_proof does with each
+ * committed column.  out_affine: n_cols*8; coeff_out[i]: 2^k*4 (may alias the
+ * input) or NULL array; ext_out[i]: 2^ext_k*4 or NULL array / NULL entries. */
+int h2agg_commit_round(h2agg_ctx* ctx, uint64_t srs_id, const uint64_t* const* lagrange_cols, size_t n_cols, uint32_t k,
+                       const uint64_t omega_inv[4], const uint64_t n_inv[4], uint64_t* out_affine,
+                       uint64_t* const* coeff_out, uint32_t ext_k, const uint64_t zeta[4], const uint64_t omega_ext[4],
+                       uint64_t* const* ext_out);
 int h2agg_coeff_to_extended_dev(h2agg_ctx* ctx, const void* d_coeffs, uint32_t k, uint32_t ext_k,
                                 const uint64_t zeta[4], const uint64_t omega_ext[4], void* d_out);
 int h2agg_extended_to_coeff_dev(h2agg_ctx* ctx, void* d_a, uint32_t ext_k, const uint64_t omega_ext_inv[4],

@@ -440,3 +440,30 @@ def test_ntt_multi_pass_paths_vs_oracle(ctx, cap, k):
             assert np.array_equal(back[: 4 << k], a)
     finally:
         ctx.set_ntt_radix_cap(8)
+
+
+def test_commit_round_fused(ctx):
+    """h2agg_commit_round == commit_lagrange + lagrange_to_coeff + coeff_to_extended done separately (oracle)."""
+    k = 13
+    n = 1 << k
+    d = domain_consts(k)
+    b = ob.gen_bases(0x53525300, n)
+    sid = ctx.srs_register(b)
+    try:
+        cols = [ob.gen_scalars(800 + i, i % 4, n) for i in range(5)]
+        coeff = [np.empty(4 * n, dtype=np.uint64) for _ in cols]
+        ext = [np.empty(4 << (k + 2), dtype=np.uint64) if i != 2 else None for i in range(5)]
+        for _ in range(2):
+            pts = ctx.commit_round(sid, cols, k, d["omega_inv"], d["n_inv"], coeff_out=coeff, ext_k=k + 2, zeta=d["zeta"],
+                                   omega_ext=d["omega_ext"], ext_out=ext)
+            for i, c in enumerate(cols):
+                assert np.array_equal(pts[i], affine_of(ob.best_multiexp(c, b)))
+                want_c = ob.ifft(c.copy(), d["omega_inv"], d["n_inv"], k)
+                assert np.array_equal(coeff[i], want_c)
+                if ext[i] is not None:
+                    assert np.array_equal(ext[i], ob.coeff_to_extended(want_c, k, k + 2, d["zeta"], d["omega_ext"]))
+        # commitments only
+        pts = ctx.commit_round(sid, cols[:2], k, d["omega_inv"], d["n_inv"])
+        assert np.array_equal(pts[1], affine_of(ob.best_multiexp(cols[1], b)))
+    finally:
+        ctx.srs_release(sid)
