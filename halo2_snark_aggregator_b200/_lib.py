@@ -20,6 +20,17 @@ class H2aggError(RuntimeError):
     pass
 
 
+class QuotientArgs(ctypes.Structure):
+    """h2agg_quotient_args (include/h2agg.h)."""
+    _fields_ = [("k", ctypes.c_uint32), ("ext_k", ctypes.c_uint32),
+                ("plan", c_vp), ("n_plan_words", ctypes.c_size_t),
+                ("d_columns", c_vp), ("n_columns", ctypes.c_size_t),
+                ("consts", c_vp), ("n_consts", ctypes.c_size_t),
+                ("y", c_vp), ("beta", c_vp), ("gamma", c_vp), ("theta", c_vp),
+                ("omega_ext", c_vp), ("zeta", c_vp), ("delta", c_vp),
+                ("t_evaluations", c_vp), ("t_len", ctypes.c_size_t)]
+
+
 _lib = None
 
 
@@ -89,6 +100,8 @@ def load():
         "h2agg_batch_invert_dev": (ci, [c_vp, c_vp, sz]),
         "h2agg_grand_product": (ci, [c_vp, c_vp, c_vp, sz, c_vp]),
         "h2agg_grand_product_dev": (ci, [c_vp, c_vp, c_vp, sz, c_vp]),
+        "h2agg_evaluate_h_dev": (ci, [c_vp, ctypes.POINTER(QuotientArgs), c_vp]),
+        "h2agg_poly_fold_dev": (ci, [c_vp, ctypes.POINTER(c_vp), sz, sz, c_vp, c_vp]),
         "h2agg_wit_new": (c_vp, []),
         "h2agg_wit_free": (None, [c_vp]),
         "h2agg_wit_error": (ctypes.c_char_p, [c_vp]),

@@ -53,16 +53,17 @@ class Context:
     def launch_count(self):
         return int(self.lib.h2agg_launch_count(self.h))
 
-    KERNEL_CLASSES = ("msm_accumulate", "msm_digits_sort", "msm_reduce", "ntt_pass", "msm_total", "witness_expand")
+    KERNEL_CLASSES = ("msm_accumulate", "msm_digits_sort", "msm_reduce", "ntt_pass", "msm_total", "witness_expand", "evaluate_h")
 
     def kernel_timing(self, enable):
         self.check(self.lib.h2agg_kernel_timing(self.h, 1 if enable else 0))
 
     def kernel_times(self):
         """{class: (total_ms, launches)} since the last call (synchronises)."""
-        ms = (ctypes.c_double * 6)()
-        cnt = (ctypes.c_uint64 * 6)()
-        self.check(self.lib.h2agg_kernel_times(self.h, ms, cnt, 6))
+        nc = len(self.KERNEL_CLASSES)
+        ms = (ctypes.c_double * nc)()
+        cnt = (ctypes.c_uint64 * nc)()
+        self.check(self.lib.h2agg_kernel_times(self.h, ms, cnt, nc))
         return {k: (ms[i], int(cnt[i])) for i, k in enumerate(self.KERNEL_CLASSES)}
 
     def host_register(self, arr):
@@ -233,6 +234,37 @@ class Context:
 
     def kate_division_dev(self, d_a, n, b, d_q):
         self.check(self.lib.h2agg_kate_division_dev(self.h, c_vp(d_a), n, _ptr(b), c_vp(d_q)))
+
+    # -- N1: quotient numerator on the extended coset (evaluate_h [+ divide_by_vanishing_poly])
+    def evaluate_h_dev(self, plan, d_columns, k, ext_k, y, beta, gamma, theta, d_out, divide=True):
+        """plan: plonk.QuotientPlan; d_columns: device pointers in plan.columns order; challenges: 4-limb arrays."""
+        from . import plonk
+
+        assert len(d_columns) == len(plan.columns), "one device column per plan.columns entry"
+        cols = (c_vp * len(d_columns))(*d_columns)
+        w_ext = plonk.fr_mont(pow(plonk.ROOT_OF_UNITY, 1 << (28 - ext_k), plonk.R_MOD))
+        zeta, delta = plonk.fr_mont(plonk.ZETA), plonk.fr_mont(plonk.DELTA)
+        keep = [cols, w_ext, zeta, delta, plan.words, plan.consts]
+        a = _lib.QuotientArgs()
+        a.k, a.ext_k = k, ext_k
+        a.plan, a.n_plan_words = plan.words.ctypes.data, plan.words.size
+        a.d_columns, a.n_columns = ctypes.cast(cols, c_vp).value, len(d_columns)
+        a.consts, a.n_consts = (plan.consts.ctypes.data if plan.consts.size else None), plan.consts.size // 4
+        a.y, a.beta, a.gamma, a.theta = y.ctypes.data, beta.ctypes.data, gamma.ctypes.data, theta.ctypes.data
+        a.omega_ext, a.zeta, a.delta = w_ext.ctypes.data, zeta.ctypes.data, delta.ctypes.data
+        if divide:
+            t = np.concatenate([plonk.fr_mont(v) for v in plonk.t_evaluations(k, ext_k)])
+            keep.append(t)
+            a.t_evaluations, a.t_len = t.ctypes.data, t.size // 4
+        else:
+            a.t_evaluations, a.t_len = None, 0
+        self.check(self.lib.h2agg_evaluate_h_dev(self.h, ctypes.byref(a), c_vp(d_out)))
+        del keep
+
+    def poly_fold_dev(self, d_polys, n, v, d_out):
+        """out[j] = sum_i polys[i][j] * v^(m-1-i) (GWC: poly_batch = poly_batch * v + poly)"""
+        arr = (c_vp * len(d_polys))(*d_polys)
+        self.check(self.lib.h2agg_poly_fold_dev(self.h, arr, len(d_polys), n, _ptr(v), c_vp(d_out)))
 
     # -- N3: grand-product scans
     def batch_invert(self, a):

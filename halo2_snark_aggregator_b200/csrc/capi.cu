@@ -109,6 +109,8 @@ void h2agg_destroy(h2agg_ctx* ctx) {
   cudaFree(ctx->small.p);
   cudaFree(ctx->poly_ws.p);
   cudaFree(ctx->scan_ws.p);
+  cudaFree(ctx->quot_ws.p);
+  cudaFree(ctx->quot_tw.p);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -152,7 +154,7 @@ int h2agg_kernel_timing(h2agg_ctx* ctx, int enable) {
 int h2agg_kernel_times(h2agg_ctx* ctx, double* ms_per_class, uint64_t* count_per_class, int n_classes) {
   if (!ctx) return 1;
   LOCK(ctx);
-  CHECK_ARG(ctx, ms_per_class && count_per_class && n_classes >= KC_COUNT, "kernel_times: need >= 6 classes");
+  CHECK_ARG(ctx, ms_per_class && count_per_class && n_classes >= KC_COUNT, "kernel_times: need >= 7 classes");
   H2AGG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   for (int i = 0; i < n_classes; i++) { ms_per_class[i] = 0; count_per_class[i] = 0; }
   for (auto& t : ctx->timed) {

@@ -71,6 +71,11 @@ struct h2agg_ctx {
   h2agg::DevBuf small;        // small constants / results
   h2agg::DevBuf poly_ws;      // recursion levels of eval_polynomial / kate_division
   h2agg::DevBuf scan_ws;      // batch_invert / grand_product scratch
+  h2agg::DevBuf quot_ws;      // evaluate_h: device copy of plan / column pointers / constants (two halves)
+  h2agg::DevBuf quot_tw;      // evaluate_h: omega_ext^i two-level table
+  uint64_t quot_omega[4] = {0, 0, 0, 0};
+  uint32_t quot_ext_k = 0;
+  int quot_flip = 0;
   void* pinned = nullptr;     // pinned host bounce buffer for tiny results
   size_t pinned_cap = 0;
   std::vector<h2agg::TwiddleTable> tw;
@@ -126,7 +131,7 @@ inline int ensure(h2agg_ctx* ctx, DevBuf& b, size_t bytes) {
 }
 
 // kernel classes for the timing hook
-enum KernelClass { KC_MSM_ACCUMULATE = 0, KC_MSM_DIGITS = 1, KC_MSM_REDUCE = 2, KC_NTT_PASS = 3, KC_MSM_TOTAL = 4, KC_WITNESS = 5, KC_COUNT = 6 };
+enum KernelClass { KC_MSM_ACCUMULATE = 0, KC_MSM_DIGITS = 1, KC_MSM_REDUCE = 2, KC_NTT_PASS = 3, KC_MSM_TOTAL = 4, KC_WITNESS = 5, KC_QUOTIENT = 6, KC_COUNT = 7 };
 
 struct ScopedKernelTimer {
   h2agg_ctx* ctx;

@@ -54,7 +54,7 @@ int h2agg_synchronize(h2agg_ctx* ctx);
 uint64_t h2agg_launch_count(h2agg_ctx* ctx);
 /* Per-kernel-class device timing with CUDA events on the context's stream (bench.py roofline).
  * classes: 0 msm_accumulate, 1 msm digit/sort kernels, 2 msm bucket+window reduction, 3 ntt pass,
- * 4 whole MSM.  h2agg_kernel_times synchronises, returns the sums since the last call and resets. */
+ * 4 whole MSM, 5 witness expansion, 6 evaluate_h.  h2agg_kernel_times synchronises, returns the sums since the last call and resets. */
 int h2agg_kernel_timing(h2agg_ctx* ctx, int enable);
 int h2agg_kernel_times(h2agg_ctx* ctx, double* ms_per_class, uint64_t* count_per_class, int n_classes);
 /* Pin / unpin a host range so H2D copies run at PCIe speed (the SRS, witness columns). */
@@ -176,6 +176,53 @@ int h2agg_batch_invert(h2agg_ctx* ctx, uint64_t* a /* n*4, in place */, size_t n
 int h2agg_batch_invert_dev(h2agg_ctx* ctx, void* d_a, size_t n);
 int h2agg_grand_product(h2agg_ctx* ctx, const uint64_t* num, const uint64_t* den, size_t n, uint64_t* z /* n*4 */);
 int h2agg_grand_product_dev(h2agg_ctx* ctx, const void* d_num, const void* d_den, size_t n, void* d_z);
+
+/* ---- N1 (next row, rank 1): quotient numerator on the extended coset -----------------------------
+ * Replaces halo2_proofs plonk/evaluation.rs Evaluator::evaluate_h (+ EvaluationDomain::divide_by_vanishing_poly
+ * when t_evaluations is given), reached from create_proof (verify_circuit.rs:986).  The reference's verifier holds
+ * the same equations and fixes their order: gates, permutation, lookups
+ * (halo2-snark-aggregator-api/src/systems/halo2/params.rs:95-150, permutation.rs:54-136, lookup.rs:58-119),
+ * folded as h = h * y + term and divided by X^n - 1 (vanish.rs:28-29).
+ *
+ * d_columns: device pointers to extended-coset evaluation vectors (2^ext_k x 32 B each) of every polynomial the
+ * constraint system touches -- fixed, advice, instance, permutation sigma, l_0, l_last, l_active_row, permutation
+ * products z, and per lookup the product z and the permuted input / table columns -- in any order; the plan
+ * refers to them by index.  Row idx stands for X = zeta * omega_ext^idx; rotation r reads row
+ * (idx + r * 2^(ext_k - k)) mod 2^ext_k.
+ *
+ * plan (uint32 words):
+ *   [0] 0x31485148  [1] number of gate polynomials  [2] number of permutation columns (0 = no argument)
+ *   [3] permutation chunk_len (cs.degree() - 2)  [4] (int32) rotation of "last" = -(blinding_factors + 1)
+ *   [5] number of lookups  [6] [7] [8] column index of l_0, l_last, l_active_row
+ *   gate polynomials, in order, each a POLY
+ *   if [2] > 0: [2] x { value column, sigma column }, then ceil([2] / [3]) x { z column }
+ *   per lookup: n_input_exprs, POLY x n;  n_table_exprs, POLY x n;  z column, permuted input column, permuted table column
+ *   POLY = n_terms, then per term { constant index into consts[] or 0xffffffff (coefficient 1), n_factors,
+ *          n_factors x (column | (uint16)(int16 rotation) << 16) }   -- a sum of products of column queries
+ * An invalid plan (index out of range, truncated section, trailing words) is rejected with status 1. */
+typedef struct h2agg_quotient_args {
+  uint32_t k, ext_k;
+  const uint32_t* plan;
+  size_t n_plan_words;
+  const void* const* d_columns;
+  size_t n_columns;
+  const uint64_t* consts; /* n_consts * 4, Montgomery */
+  size_t n_consts;
+  const uint64_t* y;     /* challenges, 4 limbs each */
+  const uint64_t* beta;
+  const uint64_t* gamma;
+  const uint64_t* theta;
+  const uint64_t* omega_ext; /* generator of the 2^ext_k domain */
+  const uint64_t* zeta;      /* coset shift g_coset (Fr::ZETA) */
+  const uint64_t* delta;     /* Fr::DELTA: the permutation argument's column separator */
+  const uint64_t* t_evaluations; /* t_len x 4: 1 / ((zeta omega_ext^i)^n - 1), or NULL to skip the division */
+  size_t t_len;                  /* power of two (halo2: 2^(ext_k - k)) */
+} h2agg_quotient_args;
+int h2agg_evaluate_h_dev(h2agg_ctx* ctx, const h2agg_quotient_args* args, void* d_out /* 2^ext_k * 32 B */);
+/* GWC multi-opening (halo2_proofs poly/kzg/multiopen/gwc/prover.rs: poly_batch = poly_batch * v + poly):
+ * out[j] = sum_i polys[i][j] * v^(n_polys-1-i).  d_out must not alias an input. */
+int h2agg_poly_fold_dev(h2agg_ctx* ctx, const void* const* d_polys, size_t n_polys, size_t n, const uint64_t v[4],
+                        void* d_out);
 
 /* ---- W1-W5: witness synthesis of halo2-ecc-circuit-lib ---------------------------
  * A recording implementation of the reference's chip surface -- ArithEccChip::{add, sub, scalar_mul,

@@ -722,6 +722,106 @@ void oracle_grand_product(const uint64_t* num, const uint64_t* den, size_t n, ui
   }
 }
 
+// halo2_proofs plonk/evaluation.rs Evaluator::evaluate_h (+ divide_by_vanishing_poly when t_evals != null), driven
+// by the same word program as the device (layout: include/h2agg.h).  Follows halo2's CPU structure: the rows are
+// split over threads (`parallelize`), each chunk starts beta_term = omega_ext^start and steps it per row.  Formulas
+// and fold order are pinned by the reference's verifier (oracle/py/quotient_ref.py, tests/test_quotient_cpu.py).
+void oracle_evaluate_h(const uint32_t* plan, size_t n_words, const uint64_t* const* cols, const uint64_t* consts,
+                       uint32_t k, uint32_t ext_k, const uint64_t* y_, const uint64_t* beta_, const uint64_t* gamma_,
+                       const uint64_t* theta_, const uint64_t* omega_ext_, const uint64_t* zeta_, const uint64_t* delta_,
+                       const uint64_t* t_evals, size_t t_len, uint64_t* out, unsigned threads) {
+  (void)n_words;
+  const size_t size = (size_t)1 << ext_k;
+  const int64_t rs = (int64_t)1 << (ext_k - k);
+  Fr y, beta, gamma, theta, w_ext, zeta, delta;
+  memcpy(y.v, y_, 32); memcpy(beta.v, beta_, 32); memcpy(gamma.v, gamma_, 32); memcpy(theta.v, theta_, 32);
+  memcpy(w_ext.v, omega_ext_, 32); memcpy(zeta.v, zeta_, 32); memcpy(delta.v, delta_, 32);
+  const uint32_t n_gates = plan[1], n_pcols = plan[2], chunk = plan[3], n_lookups = plan[5];
+  const int32_t last_rot = (int32_t)plan[4];
+  const Fr one = Fr::one();
+  const Fr delta_start = mul(beta, zeta);
+  parallelize(size, threads, [&](size_t lo, size_t hi) {
+    u64 e[4] = {lo, 0, 0, 0};
+    Fr beta_term = pow_words(w_ext, e);
+    for (size_t idx = lo; idx < hi; idx++) {
+      auto load = [&](uint32_t col, int64_t rot) {
+        size_t r = (size_t)(((int64_t)idx + rot * rs) & (int64_t)(size - 1));
+        Fr v;
+        memcpy(v.v, cols[col] + 4 * r, 32);
+        return v;
+      };
+      size_t pc = 9;
+      auto poly = [&]() {
+        uint32_t nt = plan[pc++];
+        Fr acc = Fr::zero();
+        for (uint32_t t = 0; t < nt; t++) {
+          uint32_t ci = plan[pc++], nf = plan[pc++];
+          Fr prod = one;
+          if (ci != 0xffffffffu) memcpy(prod.v, consts + 4 * (size_t)ci, 32);
+          for (uint32_t f = 0; f < nf; f++) {
+            uint32_t w = plan[pc++];
+            prod = mul(prod, load(w & 0xffffu, (int16_t)(w >> 16)));
+          }
+          acc = add(acc, prod);
+        }
+        return acc;
+      };
+      auto compress = [&]() {
+        uint32_t ne = plan[pc++];
+        Fr acc = Fr::zero();
+        for (uint32_t i = 0; i < ne; i++) acc = add(mul(acc, theta), poly());
+        return acc;
+      };
+      const Fr l0 = load(plan[6], 0), l_last = load(plan[7], 0), l_active = load(plan[8], 0);
+      Fr value = Fr::zero();
+      auto fold = [&](const Fr& term) { value = add(mul(value, y), term); };
+      for (uint32_t g = 0; g < n_gates; g++) fold(poly());
+      if (n_pcols) {
+        uint32_t n_sets = (n_pcols + chunk - 1) / chunk;
+        size_t pcols = pc, zcols = pc + 2 * (size_t)n_pcols;
+        pc = zcols + n_sets;
+        Fr z0 = load(plan[zcols], 0), zl = load(plan[zcols + n_sets - 1], 0);
+        fold(mul(sub(one, z0), l0));
+        fold(mul(sub(mul(zl, zl), zl), l_last));
+        for (uint32_t s = 1; s < n_sets; s++)
+          fold(mul(sub(load(plan[zcols + s], 0), load(plan[zcols + s - 1], last_rot)), l0));
+        Fr current_delta = mul(delta_start, beta_term);
+        for (uint32_t s = 0; s < n_sets; s++) {
+          Fr left = load(plan[zcols + s], 1), right = load(plan[zcols + s], 0);
+          uint32_t j1 = std::min((s + 1) * chunk, n_pcols);
+          for (uint32_t j = s * chunk; j < j1; j++) {
+            Fr v = load(plan[pcols + 2 * j], 0), sg = load(plan[pcols + 2 * j + 1], 0);
+            left = mul(left, add(add(v, mul(beta, sg)), gamma));
+            right = mul(right, add(add(v, current_delta), gamma));
+            current_delta = mul(current_delta, delta);
+          }
+          fold(mul(sub(left, right), l_active));
+        }
+      }
+      for (uint32_t l = 0; l < n_lookups; l++) {
+        Fr cin = compress(), ctab = compress();
+        Fr table_value = mul(add(cin, beta), add(ctab, gamma));
+        uint32_t zc = plan[pc], ac = plan[pc + 1], sc = plan[pc + 2];
+        pc += 3;
+        Fr z = load(zc, 0), zn = load(zc, 1), a = load(ac, 0), ap = load(ac, -1), st = load(sc, 0);
+        Fr ams = sub(a, st);
+        fold(mul(sub(one, z), l0));
+        fold(mul(sub(mul(z, z), z), l_last));
+        fold(mul(sub(mul(mul(zn, add(a, beta)), add(st, gamma)), mul(z, table_value)), l_active));
+        fold(mul(ams, l0));
+        fold(mul(mul(ams, sub(a, ap)), l_active));
+      }
+      if (t_evals) {
+        Fr t;
+        memcpy(t.v, t_evals + 4 * (idx & (t_len - 1)), 32);
+        value = mul(value, t);
+      }
+      memcpy(out + 4 * idx, value.v, 32);
+      beta_term = mul(beta_term, w_ext);
+    }
+  });
+}
+
 unsigned oracle_hw_threads(void) {
   unsigned t = std::thread::hardware_concurrency();
   return t ? t : 1;

@@ -53,6 +53,7 @@ def oracle():
         lib.oracle_kate_division.argtypes = [c_vp, sz, c_vp, c_vp]
         lib.oracle_batch_invert.argtypes = [c_vp, sz]
         lib.oracle_grand_product.argtypes = [c_vp, c_vp, sz, c_vp]
+        lib.oracle_evaluate_h.argtypes = [c_vp, sz, ctypes.POINTER(c_vp), c_vp, u32, u32] + [c_vp] * 8 + [sz, c_vp, ui]
         lib.oracle_hw_threads.restype = ui
         _o = lib
     return _o
@@ -169,3 +170,14 @@ def grand_product(num, den):
     z = np.zeros_like(num)
     oracle().oracle_grand_product(P(num), P(den), num.size // 4, P(z))
     return z
+
+
+def evaluate_h(plan_words, consts, ext_cols, k, ext_k, y, beta, gamma, theta, omega_ext, zeta, delta, t_evals=None,
+               nthreads=None):
+    """plan-driven C++ restatement of evaluate_h (+ division by the vanishing polynomial when t_evals is given)"""
+    out = np.empty(4 << ext_k, dtype=np.uint64)
+    cols = (c_vp * len(ext_cols))(*[c.ctypes.data for c in ext_cols])
+    oracle().oracle_evaluate_h(P(plan_words), plan_words.size, cols, P(consts) if consts.size else None, k, ext_k, P(y),
+                               P(beta), P(gamma), P(theta), P(omega_ext), P(zeta), P(delta), P(t_evals),
+                               (t_evals.size // 4) if t_evals is not None else 0, P(out), nthreads or threads())
+    return out
