@@ -371,11 +371,98 @@ def main():
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms = float(t_ms.item())
 
-    # ---- end to end through the host-pointer C ABI (pinned host memory, copies inside the timed region)
+    def pinned(nbytes):
+        return torch.empty(nbytes // 8, dtype=torch.int64).pin_memory().numpy().view(np.uint64)
+
+    # ---- the dominant kernel timed ALONE (no lane overlap) on a uniform column: multiplier roofline
+    acc_alone_ms = None
+    uni = [i for i, u in msm_units if u[2] == 0]
+    if rank == 0 and uni:
+        ctx.msm_g1_dev(t_cols[uni[0]].data_ptr(), n, t_stage.data_ptr(), srs_id=srs)
+        ctx.synchronize()
+        ctx.kernel_timing(True)
+        for _ in range(3):
+            ctx.msm_g1_dev(t_cols[uni[0]].data_ptr(), n, t_stage.data_ptr(), srs_id=srs)
+        kt = ctx.kernel_times()
+        ctx.kernel_timing(False)
+        acc_alone_ms = kt["msm_accumulate"][0] / max(kt["msm_accumulate"][1], 1)
+
+    # ---- end to end, resident form (N = 1): witness-side columns arrive from pinned HOST memory once per proof,
+    # every polynomial then stays in HBM through quotient (evaluate_h), evaluation round and GWC opening; only
+    # commitments and evaluations come back.  This is the dataflow of create_proof itself (prover.py).
+    e2e_res = None
+    n1 = None
+    if not args.no_e2e and world == 1:
+        from halo2_snark_aggregator_b200 import plonk
+        from halo2_snark_aggregator_b200.prover import ResidentProver, create_proof_queries
+
+        cs = plonk.aggregation_circuit_cs()
+        pr = ResidentProver(ctx, cs, k, srs, srs)
+        round_names = [
+            [("instance", 0)] + [("advice", i) for i in range(5)],
+            [(w, i) for i in range(7) for w in ("lookup_input", "lookup_table")],
+            [("perm_z", 0), ("perm_z", 1)] + [("lookup_z", i) for i in range(7)],
+        ]
+        witness_side = set(nm for r in round_names for nm in r)
+        for j, nm in enumerate(pr.plan.columns):  # proving-key polynomials: resident across proofs
+            if nm not in witness_side:
+                dc, de = pr.slot(nm)
+                ctx.synth_scalars_dev(SEED_SCALARS + 5000 + j, 0, 0, n, dc)
+                ctx.synth_scalars_dev(SEED_SCALARS + 6000 + j, 0, 0, ext_n, de)
+        unit_of_round = [[i for i, u in enumerate(units) if u[0] == r and u[1] == "msm"] for r in (0, 1, 2)]
+        h_round = []
+        for r in range(3):
+            cols_r = []
+            for i in unit_of_round[r]:
+                hcol = pinned(n * 32)
+                hcol[:] = ctx.d2h(t_cols[i].data_ptr(), 4 * n)
+                cols_r.append(hcol)
+            h_round.append(cols_r)
+        h_random = pinned(n * 32)
+        h_random[:] = ctx.d2h(t_cols[[i for i, u in enumerate(units) if u[0] == 3 and u[1] == "msm"][0]].data_ptr(), 4 * n)
+        queries = create_proof_queries(cs)
+        eval_queries = [q for q in queries if q[0] != ("h", 0)]
+        R_MOD = plonk.R_MOD
+        ch = [pow(3, 100 + i, R_MOD) for i in range(6)]
+
+        def step_resident():
+            outs = [pr.commit_columns(round_names[r], h_round[r]) for r in range(3)]
+            outs.append(pr.commit_coeff_columns([("random", 0)], [h_random]))
+            outs.append(pr.quotient(*ch[:4]))
+            pr.fold_h(ch[4])
+            outs.append(pr.evaluate(eval_queries, ch[4]))
+            outs.append(pr.open(queries, ch[4], ch[5])[1])
+            return outs
+
+        step_resident()
+        barrier()
+        ctx.kernel_timing(True)
+        launches_r0 = ctx.launch_count()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            res_out = step_resident()
+        barrier()
+        e2e_res_s = (time.perf_counter() - t0) / args.e2e_steps
+        launches_r = (ctx.launch_count() - launches_r0) // args.e2e_steps
+        kt = ctx.kernel_times()
+        ctx.kernel_timing(False)
+        h2d_r = 30 * n * 32
+        d2h_r = sum(int(np.asarray(o).nbytes) for o in res_out)
+        qms, qn = kt["evaluate_h"]
+        n1 = {"evaluate_h_ms": qms / max(qn, 1), "rows": ext_n, "columns_read": len(pr.plan.columns),
+              "hbm_gbs": (len(pr.plan.columns) + 1) * ext_n * 32 / (qms / max(qn, 1) * 1e-3) / 1e9 if qn else None,
+              "note": "aggregation circuit's quotient (1 gate, 2 permutation sets, 7 lookups) over 55 resident extended columns, fused with the division by X^n - 1; algorithmic bytes: every column read once + h written"}
+        e2e_res = {"value": e2e_res_s, "unit": "s", "h2d_bytes_per_step": h2d_r, "d2h_bytes_per_step": d2h_r,
+                   "gpu_launches_per_step": int(launches_r),
+                   "work": "38 MSM + 29 iNTT + 29 coset-NTT + 1 iNTT(4n) of the schedule PLUS what create_proof does between them: evaluate_h over 55 extended columns, 70 eval_polynomial, 71-polynomial GWC fold, 4 kate_division",
+                   "note": "ResidentProver (prover.py) over h2agg_commit_round_resident / evaluate_h_dev / eval_polynomial_dev / poly_fold_dev / kate_division_dev / msm_g1_batch_dev: the 30 witness-side columns are uploaded from pinned host memory every step; commitments (38 x 64 B) and evaluations (70 x 32 B) are read back; proving-key polynomials (26 columns, coefficient + extended form) stay resident across proofs as in a prover that caches its pk"}
+        pr.close()
+        del h_round, h_random, pr
+
+    # ---- end to end through the host-pointer C ABI (pinned host memory, copies inside the timed region):
+    # the drop-in shape for an UNMODIFIED halo2 prover loop, where every transform result returns to host memory
     e2e = None
     if not args.no_e2e:
-        def pinned(nbytes):
-            return torch.empty(nbytes // 8, dtype=torch.int64).pin_memory().numpy().view(np.uint64)
 
         # e2e is column-parallel over whole columns: a window-sharded MSM is done whole by its lowest rank
         owner = {}
@@ -580,16 +667,24 @@ def main():
                        "msm_mode": "fixed-base table (2^(c w) P rows resident in HBM)" if table_mode else "plain",
                        "msm_window_bits": cbits, "msm_windows": nwin,
                        "l2": "inputs larger than L2 (each column is 2^%d x 32 B; SRS 2^%d x 64 B), no flush needed" % (k, k)},
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": clock_info,
+            "e2e": e2e_res if e2e_res is not None else e2e, "e2e_host_pointer_abi": e2e if e2e_res is not None else None,
+            "gpu_launches": int(launches), "clocks": clock_info,
             "roofline": {"kernel": "msm_accumulate", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": 7353400000, "peak_source": peak_src,
                          "traffic_note": "dram__bytes_read+write of one msm_accumulate launch on a uniform 2^22 column in table mode (profiles/r01_ncu_summary.md): the gather of 54.5 M precomputed 64-byte points is by design",
                          "algorithmic_bytes_per_launch": msm_bytes, "avg_launch_ms": (acc_ms / acc_n) if acc_n else None,
                          "launches_timed": acc_n,
                          "note": "MSM is bound by the INT32 IMAD pipe, not HBM (SURVEY.md 8d); HBM fraction reported as the metric demands"},
+            "roofline_multiplier": None if not acc_alone_ms else (lambda clk: {
+                "kernel": "msm_accumulate", "bound": "int32 multiplier: IMAD.WIDE.U32 issues once per 4 clk per SM sub-partition (32 lanes/clk/SM; profiles/r01_pipe_rates_b200.jsonl, ncu fmaheavy pipe)",
+                "achieved": 10.0 * n * nwin / (acc_alone_ms * 1e-3) / 1e9, "peak": 148 * 32 * clk * 1e6 / 136 / 1e9, "unit": "G field-mul/s",
+                "frac": (10.0 * n * nwin / (acc_alone_ms * 1e-3)) / (148 * 32 * clk * 1e6 / 136),
+                "launch_ms_alone": acc_alone_ms, "mixed_additions_per_launch": n * nwin,
+                "note": "one launch on a uniform 2^%d column, timed alone; a mixed addition is 8M+2S = 10 Montgomery products of 136 multiplier instructions each" % k})(
+                    float((clock_info or {}).get("sm_mhz") or 1965.0)),
             "cpu_baseline": cpu,
             "witness": witness,
-            "next_rows": {"N2_eval_and_kate_division": n2, "N3_grand_product": n3},
+            "next_rows": {"N1_evaluate_h": n1, "N2_eval_and_kate_division": n2, "N3_grand_product": n3},
             "extra": {
                 "schedule_algorithmic_bytes": sched_bytes, "schedule_hbm_gbs": sched_bytes / (ms * 1e-3) / 1e9,
                 "schedule_hbm_frac": sched_bytes / (ms * 1e-3) / 1e9 / peak,

@@ -199,6 +199,17 @@ class Context:
                                                _ptr(zeta), _ptr(omega_ext), eo))
         return out.reshape(nc, 8)
 
+    def commit_round_resident(self, srs_id, cols, k, omega_inv, n_inv, d_coeff_out, ext_k=0, zeta=None, omega_ext=None, d_ext_out=None):
+        """Commit round whose coefficient / extended forms stay in HBM (device pointers) -> affine commitments (len(cols), 8)."""
+        nc = len(cols)
+        a = (c_vp * nc)(*[c.ctypes.data for c in cols])
+        co = (c_vp * nc)(*d_coeff_out)
+        eo = (c_vp * nc)(*d_ext_out) if d_ext_out is not None else None
+        out = np.zeros(8 * nc, dtype=np.uint64)
+        self.check(self.lib.h2agg_commit_round_resident(self.h, srs_id, a, nc, k, _ptr(omega_inv), _ptr(n_inv), _ptr(out), co, ext_k,
+                                                        _ptr(zeta), _ptr(omega_ext), eo))
+        return out.reshape(nc, 8)
+
     def ntt_fr_dev(self, d_a, omega, log_n, scale=None):
         self.check(self.lib.h2agg_ntt_fr_dev(self.h, c_vp(d_a), _ptr(omega), _ptr(scale), log_n))
 

@@ -627,10 +627,12 @@ int h2agg_coeff_to_extended_batch(h2agg_ctx* ctx, const uint64_t* const* coeff_c
 
 // One commit round fused per column (see h2agg.h): upload once; MSM, iNTT and (optionally) the coset NTT run
 // back to back on the column's lane; the D2H copies of lane A overlap the kernels of lane B and the upload of lane C.
-int h2agg_commit_round(h2agg_ctx* ctx, uint64_t srs_id, const uint64_t* const* lagrange_cols, size_t n_cols, uint32_t k,
-                       const uint64_t omega_inv[4], const uint64_t n_inv[4], uint64_t* out_affine,
-                       uint64_t* const* coeff_out, uint32_t ext_k, const uint64_t zeta[4], const uint64_t omega_ext[4],
-                       uint64_t* const* ext_out) {
+// `resident`: coeff_out / ext_out are caller-owned DEVICE buffers the transforms write straight into (no D2H);
+// otherwise host buffers filled through the lane's staging buffers.
+static int commit_round_impl(h2agg_ctx* ctx, uint64_t srs_id, const uint64_t* const* lagrange_cols, size_t n_cols, uint32_t k,
+                             const uint64_t omega_inv[4], const uint64_t n_inv[4], uint64_t* out_affine,
+                             uint64_t* const* coeff_out, uint32_t ext_k, const uint64_t zeta[4], const uint64_t omega_ext[4],
+                             uint64_t* const* ext_out, bool resident) {
   if (!ctx) return 1;
   LOCK(ctx);
   CHECK_ARG(ctx, srs_id != 0 && lagrange_cols && out_affine && omega_inv && n_inv, "commit_round: null argument");
@@ -657,7 +659,7 @@ int h2agg_commit_round(h2agg_ctx* ctx, uint64_t srs_id, const uint64_t* const* l
     Lane& ln = ctx->lanes[i % N_LANES];
     CHECK_ARG(ctx, lagrange_cols[i], "commit_round: null column");
     if ((rc = ensure(ctx, ln.io, n * 32 + 64))) return rc;
-    if (ext_out && ext_out[i] && (rc = ensure(ctx, ln.io_out, ((size_t)1 << ext_k) * 32))) return rc;
+    if (!resident && ext_out && ext_out[i] && (rc = ensure(ctx, ln.io_out, ((size_t)1 << ext_k) * 32))) return rc;
     H2AGG_CUDA(ctx, cudaMemcpyAsync(ln.io.p, lagrange_cols[i], n * 32, cudaMemcpyHostToDevice, ln.st));
     if ((rc = msm_run(ctx, ln.st, ln.ws, bases, ln.io.p, n, (uint8_t*)ctx->small.p + i * 160, 0, -1))) return rc;
     if (coeff_out && coeff_out[i]) {
@@ -667,11 +669,16 @@ int h2agg_commit_round(h2agg_ctx* ctx, uint64_t srs_id, const uint64_t* const* l
         H2AGG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ln.done, 0));
         st = ctx->stream;
       }
-      if ((rc = ntt_run(ctx, ln.io.p, ln.io.p, oi, st, &ln.ntt_tmp))) return rc;
-      H2AGG_CUDA(ctx, cudaMemcpyAsync(coeff_out[i], ln.io.p, n * 32, cudaMemcpyDeviceToHost, st));
-      if (ext_out && ext_out[i]) {
-        if ((rc = ntt_run(ctx, ln.io.p, ln.io_out.p, oe, st, &ln.ntt_tmp))) return rc;
-        H2AGG_CUDA(ctx, cudaMemcpyAsync(ext_out[i], ln.io_out.p, ((size_t)32) << ext_k, cudaMemcpyDeviceToHost, st));
+      if (resident) {
+        if ((rc = ntt_run(ctx, ln.io.p, coeff_out[i], oi, st, &ln.ntt_tmp))) return rc;
+        if (ext_out && ext_out[i] && (rc = ntt_run(ctx, coeff_out[i], ext_out[i], oe, st, &ln.ntt_tmp))) return rc;
+      } else {
+        if ((rc = ntt_run(ctx, ln.io.p, ln.io.p, oi, st, &ln.ntt_tmp))) return rc;
+        H2AGG_CUDA(ctx, cudaMemcpyAsync(coeff_out[i], ln.io.p, n * 32, cudaMemcpyDeviceToHost, st));
+        if (ext_out && ext_out[i]) {
+          if ((rc = ntt_run(ctx, ln.io.p, ln.io_out.p, oe, st, &ln.ntt_tmp))) return rc;
+          H2AGG_CUDA(ctx, cudaMemcpyAsync(ext_out[i], ln.io_out.p, ((size_t)32) << ext_k, cudaMemcpyDeviceToHost, st));
+        }
       }
       if (i == 0) {
         H2AGG_CUDA(ctx, cudaEventRecord(ctx->fork_ev, ctx->stream));
@@ -687,6 +694,27 @@ int h2agg_commit_round(h2agg_ctx* ctx, uint64_t srs_id, const uint64_t* const* l
   H2AGG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   for (size_t i = 0; i < n_cols; i++) memcpy(out_affine + i * 8, (uint8_t*)ctx->pinned + i * 160, 64);
   return 0;
+}
+
+int h2agg_commit_round(h2agg_ctx* ctx, uint64_t srs_id, const uint64_t* const* lagrange_cols, size_t n_cols, uint32_t k,
+                       const uint64_t omega_inv[4], const uint64_t n_inv[4], uint64_t* out_affine,
+                       uint64_t* const* coeff_out, uint32_t ext_k, const uint64_t zeta[4], const uint64_t omega_ext[4],
+                       uint64_t* const* ext_out) {
+  return commit_round_impl(ctx, srs_id, lagrange_cols, n_cols, k, omega_inv, n_inv, out_affine, coeff_out, ext_k, zeta,
+                           omega_ext, ext_out, false);
+}
+
+int h2agg_commit_round_resident(h2agg_ctx* ctx, uint64_t srs_id, const uint64_t* const* lagrange_cols, size_t n_cols,
+                                uint32_t k, const uint64_t omega_inv[4], const uint64_t n_inv[4], uint64_t* out_affine,
+                                void* const* d_coeff_out, uint32_t ext_k, const uint64_t zeta[4],
+                                const uint64_t omega_ext[4], void* const* d_ext_out) {
+  if (ctx && !d_coeff_out) {
+    LOCK(ctx);
+    ctx->last_error = "commit_round_resident: d_coeff_out is NULL (use h2agg_msm_g1_batch for commitments only)";
+    return 1;
+  }
+  return commit_round_impl(ctx, srs_id, lagrange_cols, n_cols, k, omega_inv, n_inv, out_affine,
+                           (uint64_t* const*)d_coeff_out, ext_k, zeta, omega_ext, (uint64_t* const*)d_ext_out, true);
 }
 
 int h2agg_extended_to_coeff_dev(h2agg_ctx* ctx, void* d_a, uint32_t ext_k, const uint64_t omega_ext_inv[4],

@@ -1,0 +1,189 @@
+"""Device-resident replay of the numeric core of halo2's `create_proof` for one circuit shape.
+
+What the reference runs under halo2-snark-aggregator-circuit/src/verify_circuit.rs:986-994 (external crate
+halo2_proofs, plonk/prover.rs; order restated in SURVEY.md App. B4) is, once the witness columns exist:
+
+    1-3  commit rounds       commit_lagrange + lagrange_to_coeff (+ coeff_to_extended)   K1 / K2 / K3
+    4    quotient            evaluate_h, divide_by_vanishing_poly, extended_to_coeff,     N1 / K3 / K1
+                             commit the n-coefficient pieces of h
+    5    evaluation round    eval_polynomial of every queried polynomial at x * omega^rot  N2
+    6    GWC multi-opening   per point: fold with v, kate_division, commit                N1 (fold) / N2 / K1
+
+`ResidentProver` strings the C-ABI entry points together so that every polynomial stays in HBM between those
+stages: columns arrive from host memory once (h2agg_commit_round_resident) and only commitments and evaluations
+travel back.  It is a host-side orchestration layer -- all arithmetic runs in the CUDA kernels; challenges are
+inputs (in the reference they come from the Rust transcript between the stages).  Not on this path: blinding,
+the lookup permutation / grand products themselves (N3) and the transcript, which stay with the caller.
+"""
+import numpy as np
+
+from . import plonk
+from .domain import EvaluationDomain, fr_to_limbs
+
+_R = plonk.R_MOD
+
+
+class ResidentProver:
+    def __init__(self, ctx, cs, k, srs_lagrange, srs_g):
+        """srs_lagrange / srs_g: ids of the registered ParamsKZG::g_lagrange / g (h2agg_srs_register)."""
+        self.ctx, self.cs, self.k, self.n = ctx, cs, k, 1 << k
+        self.plan = plonk.build_quotient_plan(cs)
+        self.dom = EvaluationDomain(cs.degree(), k, ctx)
+        self.ext_k, self.ext_n = self.dom.extended_k, self.dom.extended_len()
+        self.srs_lagrange, self.srs_g = srs_lagrange, srs_g
+        self.coeff, self.ext = {}, {}      # column name -> device pointer
+        self._owned = []
+        self._t = np.concatenate([plonk.fr_mont(v) for v in plonk.t_evaluations(k, self.ext_k)])
+        self.n_pieces = self.dom.quotient_poly_degree
+        self._scratch = {}
+
+    # -- memory ------------------------------------------------------------------------------------
+    def _alloc(self, nbytes):
+        p = self.ctx.dev_alloc(nbytes)
+        self._owned.append(p)
+        return p
+
+    def _buf(self, key, nbytes):
+        if key not in self._scratch:
+            self._scratch[key] = self._alloc(nbytes)
+        return self._scratch[key]
+
+    def slot(self, name, extended=True):
+        """Device buffers of a column's coefficient (and extended-coset) form, allocated on first use."""
+        if name not in self.coeff:
+            self.coeff[name] = self._alloc(self.n * 32)
+        if extended and name not in self.ext:
+            self.ext[name] = self._alloc(self.ext_n * 32)
+        return self.coeff[name], self.ext.get(name)
+
+    def adopt(self, name, d_coeff, d_ext=None):
+        """Use caller-owned device buffers for a column (e.g. proving-key polynomials kept across proofs)."""
+        self.coeff[name] = d_coeff
+        if d_ext is not None:
+            self.ext[name] = d_ext
+
+    def close(self):
+        self.ctx.synchronize()
+        for p in self._owned:
+            self.ctx.dev_free(p)
+        self._owned = []
+
+    # -- stages 1-3: commit rounds -------------------------------------------------------------------
+    def commit_columns(self, names, lagrange_cols, extended=True):
+        """One commit round from HOST Lagrange columns -> affine commitments (len, 8).  The coefficient and
+        extended forms stay resident under `names`."""
+        slots = [self.slot(nm, extended) for nm in names]
+        d = self.dom
+        return self.ctx.commit_round_resident(
+            self.srs_lagrange, list(lagrange_cols), self.k, d.omega_inv, d.ifft_divisor, [s[0] for s in slots],
+            ext_k=self.ext_k if extended else 0, zeta=d.g_coset if extended else None,
+            omega_ext=d.extended_omega if extended else None, d_ext_out=[s[1] for s in slots] if extended else None)
+
+    def commit_coeff_columns(self, names, coeff_cols):
+        """Polynomials the prover creates in COEFFICIENT form (the vanishing argument's random polynomial):
+        uploaded as they are and committed against `g` (ParamsKZG::commit)."""
+        ptrs = []
+        for nm, col in zip(names, coeff_cols):
+            d, _ = self.slot(nm, extended=False)
+            self.ctx.h2d(d, col)
+            ptrs.append(d)
+        return self._commit_dev(ptrs)
+
+    # -- stage 4: quotient -----------------------------------------------------------------------------
+    def quotient(self, y, beta, gamma, theta):
+        """h = evaluate_h / (X^n - 1) on the coset -> coefficients -> commitments of its n-coefficient pieces."""
+        cols = [self.ext[nm] for nm in self.plan.columns]
+        d_h = self._buf("h", self.ext_n * 32)
+        lim = [fr_to_limbs(v) for v in (y, beta, gamma, theta)]
+        self.ctx.evaluate_h_dev(self.plan, cols, self.k, self.ext_k, *lim, d_h, divide=True)
+        self.dom.extended_to_coeff_dev(d_h)
+        pieces = [d_h + i * self.n * 32 for i in range(self.n_pieces)]
+        for i, p in enumerate(pieces):
+            self.coeff[("h_piece", i)] = p
+        return self._commit_dev(pieces)
+
+    def _commit_dev(self, d_polys):
+        d_out = self._buf("pts", 160 * 64)
+        assert len(d_polys) <= 64
+        self.ctx.msm_g1_batch_dev(d_polys, self.n, d_out, srs_id=self.srs_g)
+        pts = self.ctx.d2h(d_out, 20 * len(d_polys)).reshape(len(d_polys), 20)
+        return pts[:, :8].copy()
+
+    # -- stage 5: evaluation round -------------------------------------------------------------------
+    def rotate_omega(self, x, rot):
+        w = self.dom._omega if rot >= 0 else self.dom._omega_inv
+        return x * pow(w, abs(rot), _R) % _R
+
+    def fold_h(self, x):
+        """vanishing::Constructed::evaluate: h(X) = sum_i piece_i(X) * x^(n i), kept under ("h", 0)."""
+        xn = pow(x, self.n, _R)
+        d = self._buf("h_folded", self.n * 32)
+        self.ctx.poly_fold_dev([self.coeff[("h_piece", i)] for i in reversed(range(self.n_pieces))], self.n,
+                               fr_to_limbs(xn), d)
+        self.coeff[("h", 0)] = d
+
+    def evaluate(self, queries, x):
+        """queries: [(column name, rotation)] -> evaluations at x * omega^rotation, shape (len, 4) Montgomery limbs."""
+        assert len(queries) <= 1024
+        d_ev = self._buf("evals", 32 * 1024)
+        for i, (nm, rot) in enumerate(queries):
+            self.ctx.eval_polynomial_dev(self.coeff[nm], self.n, fr_to_limbs(self.rotate_omega(x, rot)), d_ev + 32 * i)
+        return self.ctx.d2h(d_ev, 4 * len(queries)).reshape(len(queries), 4)
+
+    # -- stage 6: GWC multi-opening ---------------------------------------------------------------------
+    def open(self, queries, x, v):
+        """halo2_proofs poly/kzg/multiopen/gwc/prover.rs: queries are grouped by point in order of first appearance;
+        per point  poly_batch = fold(poly_batch * v + poly),  W = commit(kate_division(poly_batch - eval_batch, point)).
+        The constant eval_batch only changes the remainder kate_division drops, so it is not subtracted here.
+        Returns (rotations in point order, affine W commitments (len, 8))."""
+        order, groups = [], {}
+        for nm, rot in queries:
+            if rot not in groups:
+                groups[rot] = []
+                order.append(rot)
+            groups[rot].append(self.coeff[nm])
+        d_fold = self._buf("fold", self.n * 32)
+        ws = []
+        for j, rot in enumerate(order):
+            d_w = self._buf(("w", j), self.n * 32)
+            self.ctx.poly_fold_dev(groups[rot], self.n, fr_to_limbs(v), d_fold)
+            self.ctx.kate_division_dev(d_fold, self.n, fr_to_limbs(self.rotate_omega(x, rot)), d_w)
+            ws.append(d_w)
+        return order, self._commit_dev(ws)
+
+
+def create_proof_queries(cs):
+    """The (polynomial, rotation) list create_proof opens for a constraint system, in halo2's order: advice queries,
+    permutation products, lookups, fixed queries, permutation sigmas, vanishing (h, random)."""
+    adv, fix, seen = [], [], set()
+    exprs = [p for _, polys in cs.gates for p in polys]
+    for _, ins, tabs in cs.lookups:
+        exprs += ins + tabs
+    for e in exprs:
+        for q in sorted(e.queries()):
+            if q in seen:
+                continue
+            seen.add(q)
+            if q[0] == "advice":
+                adv.append((("advice", q[1]), q[2]))
+            elif q[0] == "fixed":
+                fix.append((("fixed", q[1]), q[2]))
+    for kind, idx in cs.permutation_columns:  # equality-enabled columns are queried at the current row
+        q = (kind, idx, 0)
+        if q not in seen:
+            seen.add(q)
+            (adv if kind == "advice" else fix if kind == "fixed" else []).append(((kind, idx), 0))
+    last = -(cs.blinding_factors() + 1)
+    out = list(adv)
+    sets = cs.num_permutation_sets()
+    for s in range(sets):
+        out += [(("perm_z", s), 0), (("perm_z", s), 1)]
+        if s + 1 < sets:
+            out.append((("perm_z", s), last))
+    for i in range(len(cs.lookups)):
+        out += [(("lookup_z", i), 0), (("lookup_input", i), 0), (("lookup_table", i), 0),
+                (("lookup_input", i), -1), (("lookup_z", i), 1)]
+    out += fix
+    out += [(("sigma", j), 0) for j in range(len(cs.permutation_columns))]
+    out += [(("h", 0), 0), (("random", 0), 0)]
+    return out

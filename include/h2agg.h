@@ -154,6 +154,14 @@ int h2agg_commit_round(h2agg_ctx* ctx, uint64_t srs_id, const uint64_t* const* l
                        const uint64_t omega_inv[4], const uint64_t n_inv[4], uint64_t* out_affine,
                        uint64_t* const* coeff_out, uint32_t ext_k, const uint64_t zeta[4], const uint64_t omega_ext[4],
                        uint64_t* const* ext_out);
+/* Resident form of the commit round: columns still arrive from HOST memory (the witness is produced by the caller),
+ * but their coefficient and extended-coset forms stay in caller-owned DEVICE buffers (d_coeff_out[i]: 2^k*32 B,
+ * d_ext_out[i]: 2^ext_k*32 B or NULL array / NULL entries) where evaluate_h (N1), the evaluation round and the GWC
+ * quotients (N2) consume them, so that only the 64-byte commitments travel back over PCIe. */
+int h2agg_commit_round_resident(h2agg_ctx* ctx, uint64_t srs_id, const uint64_t* const* lagrange_cols, size_t n_cols,
+                                uint32_t k, const uint64_t omega_inv[4], const uint64_t n_inv[4], uint64_t* out_affine,
+                                void* const* d_coeff_out, uint32_t ext_k, const uint64_t zeta[4],
+                                const uint64_t omega_ext[4], void* const* d_ext_out);
 int h2agg_coeff_to_extended_dev(h2agg_ctx* ctx, const void* d_coeffs, uint32_t k, uint32_t ext_k,
                                 const uint64_t zeta[4], const uint64_t omega_ext[4], void* d_out);
 int h2agg_extended_to_coeff_dev(h2agg_ctx* ctx, void* d_a, uint32_t ext_k, const uint64_t omega_ext_inv[4],

@@ -63,3 +63,18 @@ def test_cpp_host_header_compiles(tmp_path):
     src = tmp_path / "t.cpp"
     src.write_text('#include "h2agg.hpp"\nint main(){return 0;}\n')
     subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)])
+
+
+def test_create_proof_query_list_of_the_aggregation_circuit():
+    """~70 evaluations; 4 opening points (x, omega x, omega^-1 x, omega^last x)."""
+    from halo2_snark_aggregator_b200 import plonk
+    from halo2_snark_aggregator_b200.prover import create_proof_queries
+
+    cs = plonk.aggregation_circuit_cs()
+    q = create_proof_queries(cs)
+    evals = [x for x in q if x[0] != ("h", 0)]
+    assert len(evals) == 6 + 17 + 1 + 6 + 5 + 35   # advice, fixed, random, sigma, permutation z, lookups
+    assert len(set(q)) == len(q)
+    rots = list(dict.fromkeys(r for _, r in q))
+    assert sorted(rots) == sorted([0, 1, -1, -(cs.blinding_factors() + 1)])
+    assert sum(1 for _, r in q if r == 0) == 53 and sum(1 for _, r in q if r == 1) == 10 and sum(1 for _, r in q if r == -1) == 7

@@ -1,0 +1,101 @@
+"""Resident prover replay (halo2_snark_aggregator_b200/prover.py) against the CPU oracles, stage by stage:
+commit rounds (K1-K3) -> quotient (N1 + K3 + K1) -> evaluation round (N2) -> GWC multi-opening (fold + N2 + K1).
+Every polynomial stays in HBM between the stages; what comes back (commitments, evaluations) must be bit-identical
+to the composition of the oracle's best_multiexp / ifft / coeff_to_extended / evaluate_h / extended_to_coeff /
+eval_polynomial / kate_division on the same inputs."""
+import random
+
+import numpy as np
+import pytest
+
+import oracle_binding as ob
+import quotient_util as qu
+import quotient_ref as qr
+from halo2_snark_aggregator_b200 import plonk
+from halo2_snark_aggregator_b200.prover import ResidentProver, create_proof_queries
+from util import domain_consts
+
+pytestmark = pytest.mark.gpu
+R = qr.R
+
+
+def _small_cs():
+    E = plonk.Expression
+    cs = plonk.ConstraintSystem(num_fixed=3, num_advice=3, num_instance=1)
+    cs.create_gate("g0", [E.fixed(0) * (E.advice(0) * E.advice(1) - E.advice(2, 1)),
+                          E.fixed(1) * (E.advice(0) + 5) * (E.advice(0, -1) - E.constant(3))])
+    cs.lookup("l", [(E.advice(0) * E.fixed(0), E.fixed(2))])
+    cs.enable_equality("advice", 0)
+    cs.enable_equality("advice", 1)
+    cs.enable_equality("instance", 0)
+    return cs
+
+
+@pytest.mark.parametrize("which,k", [("small", 5), ("aggregation", 6)])
+def test_resident_prover_matches_oracle_composition(ctx, which, k):
+    cs = _small_cs() if which == "small" else plonk.aggregation_circuit_cs()
+    n = 1 << k
+    g = ob.gen_bases(0x6000 + k, n)
+    gl = ob.gen_bases(0x7000 + k, n)
+    sid_g, sid_gl = ctx.srs_register(g), ctx.srs_register(gl)
+    pr = ResidentProver(ctx, cs, k, sid_gl, sid_g)
+    ext_k = pr.ext_k
+    d = domain_consts(k, ext_k)
+    lag = qu.random_lagrange_columns(pr.plan, k, seed=77 + k)
+    lag[("random", 0)] = [random.Random(5).randrange(R) for _ in range(n)]
+    names = list(pr.plan.columns)
+    # --- commit rounds: everything the quotient touches, in three rounds like the prover's phases; "random" has no extended form
+    thirds = [names[0::3], names[1::3], names[2::3]]
+    o_coeff, o_ext = {}, {}
+    for rnd in thirds:
+        got = pr.commit_columns(rnd, [qu.pack(lag[nm]) for nm in rnd])
+        for j, nm in enumerate(rnd):
+            col = qu.pack(lag[nm])
+            want = ob.best_multiexp(col, gl)
+            assert np.array_equal(got[j], want[:8]) or (not want[8:].any() and not got[j].any()), nm
+            o_coeff[nm] = ob.ifft(col.copy(), d["omega_inv"], d["n_inv"], k)
+            o_ext[nm] = ob.coeff_to_extended(o_coeff[nm], k, ext_k, d["zeta"], d["omega_ext"])
+            assert np.array_equal(ctx.d2h(pr.coeff[nm], 4 * n), o_coeff[nm]), nm
+            assert np.array_equal(ctx.d2h(pr.ext[nm], 4 << ext_k), o_ext[nm]), nm
+    pr.commit_columns([("random", 0)], [qu.pack(lag[("random", 0)])], extended=False)
+    o_coeff[("random", 0)] = ob.ifft(qu.pack(lag[("random", 0)]), d["omega_inv"], d["n_inv"], k)
+    # --- quotient
+    rng = random.Random(k)
+    y, beta, gamma, theta, x, v = [rng.randrange(R) for _ in range(6)]
+    h_comms = pr.quotient(y, beta, gamma, theta)
+    ext_ints = {nm: qu.unpack(o_ext[nm]) for nm in names}
+    h = qr.divide_by_vanishing_poly(qr.evaluate_h(qu.oracle_desc(cs), ext_ints, k, ext_k, y, beta, gamma, theta), k, ext_k)
+    q = cs.degree() - 1
+    h_coeff = ob.extended_to_coeff(qu.pack(h), ext_k, d["omega_ext_inv"], d["ext_n_inv"], d["zeta"], n * q)
+    assert len(h_comms) == q
+    for i in range(q):
+        piece = np.ascontiguousarray(h_coeff[4 * n * i: 4 * n * (i + 1)])
+        o_coeff[("h_piece", i)] = piece
+        assert np.array_equal(h_comms[i], ob.best_multiexp(piece, g)[:8]), "h piece %d" % i
+    # --- evaluation round
+    pr.fold_h(x)
+    xn = pow(x, n, R)
+    hp = [qu.unpack(o_coeff[("h_piece", i)]) for i in range(q)]
+    folded = [sum(hp[i][j] * pow(xn, i, R) for i in range(q)) % R for j in range(n)]
+    o_coeff[("h", 0)] = qu.pack(folded)
+    queries = create_proof_queries(cs)
+    evals = pr.evaluate(queries, x)
+    w = qr.omega(k)
+    for (nm, rot), e in zip(queries, evals):
+        pt = x * pow(w, rot, R) % R
+        assert np.array_equal(e, ob.eval_polynomial(o_coeff[nm], qu.pack([pt]))), (nm, rot)
+    # --- GWC multi-opening
+    order, ws = pr.open(queries, x, v)
+    assert order == list(dict.fromkeys(rot for _, rot in queries))
+    for rot, wpt in zip(order, ws):
+        acc = [0] * n
+        for nm, r2 in queries:
+            if r2 == rot:
+                c = qu.unpack(o_coeff[nm])
+                acc = [(a * v + b) % R for a, b in zip(acc, c)]
+        quo = ob.kate_division(qu.pack(acc), qu.pack([x * pow(w, rot, R) % R]))
+        quo = np.concatenate([quo, np.zeros(4, dtype=np.uint64)])
+        assert np.array_equal(wpt, ob.best_multiexp(quo, g)[:8]), "W at rotation %d" % rot
+    pr.close()
+    ctx.srs_release(sid_g)
+    ctx.srs_release(sid_gl)
