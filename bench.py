@@ -605,7 +605,30 @@ def main():
         t_gp = ea.elapsed_time(eb) / 10
         n3 = {"grand_product_ms": t_gp, "hbm_gbs": 96.0 * n / (t_gp * 1e-3) / 1e9, "n": n,
               "note": "algorithmic bytes: numerators + denominators read, running products written; ~6 Fr products per row"}
-        del d_q, d_z
+        # N3 (sorting half): permute_expression_pair over the usable rows of a lookup (17-bit inputs against a 17-bit
+        # table as in the aggregation circuit's range lookups; and a full-width pair, where all 32 radix passes run)
+        u_rows = n - 6
+        d_li, d_lt, d_pa, d_ps = dbuf(n * 32), dbuf(n * 32), dbuf(n * 32), dbuf(n * 32)
+        n3s = {"usable_rows": u_rows}
+        for label, kind in (("range_17bit", 3), ("full_width", 0)):
+            ctx.synth_scalars_dev(SEED_SCALARS + 8100 + kind, kind, 0, n, d_li.data_ptr())
+            if kind == 3:
+                ctx.synth_scalars_dev(SEED_SCALARS + 8200 + kind, kind, 0, n, d_lt.data_ptr())
+            else:
+                d_lt.copy_(d_li)
+            try:
+                ctx.permute_expression_pair_dev(d_li.data_ptr(), d_lt.data_ptr(), u_rows, d_pa.data_ptr(), d_ps.data_ptr())
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(5):
+                    ctx.permute_expression_pair_dev(d_li.data_ptr(), d_lt.data_ptr(), u_rows, d_pa.data_ptr(), d_ps.data_ptr())
+                torch.cuda.synchronize()
+                n3s[label + "_ms"] = (time.perf_counter() - t0) / 5 * 1e3
+            except h2.H2aggError as e:
+                n3s[label + "_error"] = str(e)
+        n3s["note"] = "sort input + sort table (LSD radix, 8-bit digits, constant digits skipped) + table permutation; wall time per call incl. its two small D2H syncs; algorithmic bytes 4 x 32 x rows (two columns in, two out)"
+        n3["permute_expression_pair"] = n3s
+        del d_q, d_z, d_li, d_lt, d_pa, d_ps
 
     # ---- CPU baseline: the oracle port on this box's host cores, bounded sample (rank 0, N=1 only)
     cpu = None

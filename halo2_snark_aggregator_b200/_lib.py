@@ -101,6 +101,10 @@ def load():
         "h2agg_batch_invert_dev": (ci, [c_vp, c_vp, sz]),
         "h2agg_grand_product": (ci, [c_vp, c_vp, c_vp, sz, c_vp]),
         "h2agg_grand_product_dev": (ci, [c_vp, c_vp, c_vp, sz, c_vp]),
+        "h2agg_permute_expression_pair": (ci, [c_vp, c_vp, c_vp, sz, c_vp, c_vp]),
+        "h2agg_permute_expression_pair_dev": (ci, [c_vp, c_vp, c_vp, sz, c_vp, c_vp]),
+        "h2agg_sort_fr": (ci, [c_vp, c_vp, sz]),
+        "h2agg_sort_fr_dev": (ci, [c_vp, c_vp, sz]),
         "h2agg_evaluate_h_dev": (ci, [c_vp, ctypes.POINTER(QuotientArgs), c_vp]),
         "h2agg_poly_fold_dev": (ci, [c_vp, ctypes.POINTER(c_vp), sz, sz, c_vp, c_vp]),
         "h2agg_wit_new": (c_vp, []),

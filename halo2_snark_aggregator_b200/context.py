@@ -291,6 +291,24 @@ class Context:
     def grand_product_dev(self, d_num, d_den, n, d_z):
         self.check(self.lib.h2agg_grand_product_dev(self.h, c_vp(d_num), c_vp(d_den), n, c_vp(d_z)))
 
+    def sort_fr(self, a):
+        out = a.copy()
+        self.check(self.lib.h2agg_sort_fr(self.h, _ptr(out), out.size // 4))
+        return out
+
+    def sort_fr_dev(self, d_a, n):
+        self.check(self.lib.h2agg_sort_fr_dev(self.h, c_vp(d_a), n))
+
+    def permute_expression_pair(self, inp, tab):
+        """lookup::prover::permute_expression_pair over the usable rows -> (permuted_input, permuted_table);
+        raises H2aggError (status 4) when an input value is not in the table."""
+        a, s = np.zeros_like(inp), np.zeros_like(tab)
+        self.check(self.lib.h2agg_permute_expression_pair(self.h, _ptr(inp), _ptr(tab), inp.size // 4, _ptr(a), _ptr(s)))
+        return a, s
+
+    def permute_expression_pair_dev(self, d_inp, d_tab, u, d_pin, d_ptab):
+        self.check(self.lib.h2agg_permute_expression_pair_dev(self.h, c_vp(d_inp), c_vp(d_tab), u, c_vp(d_pin), c_vp(d_ptab)))
+
     # -- field helpers (device)
     def field_op(self, field, op, a, b=None):
         out = np.empty_like(a)

@@ -109,6 +109,7 @@ void h2agg_destroy(h2agg_ctx* ctx) {
   cudaFree(ctx->small.p);
   cudaFree(ctx->poly_ws.p);
   cudaFree(ctx->scan_ws.p);
+  cudaFree(ctx->sort_ws.p);
   cudaFree(ctx->quot_ws.p);
   cudaFree(ctx->quot_tw.p);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);

@@ -17,7 +17,8 @@
  *   G1          {x: Fq, y: Fq, z: Fq}     96 bytes Jacobian, identity z = 0
  * so a Rust slice can be passed as a pointer without conversion.
  *
- * Every function returns 0 on success; 1 = invalid argument, 2 = CUDA failure, 3 = no device.
+ * Every function returns 0 on success; 1 = invalid argument, 2 = CUDA failure, 3 = no device,
+ * 4 = the data violate the caller's constraint system (h2agg_permute_expression_pair only).
  * h2agg_last_error() gives the message.  There is no CPU fallback inside this library: with no
  * usable GPU h2agg_init fails and nothing else can be called.
  *
@@ -184,6 +185,22 @@ int h2agg_batch_invert(h2agg_ctx* ctx, uint64_t* a /* n*4, in place */, size_t n
 int h2agg_batch_invert_dev(h2agg_ctx* ctx, void* d_a, size_t n);
 int h2agg_grand_product(h2agg_ctx* ctx, const uint64_t* num, const uint64_t* den, size_t n, uint64_t* z /* n*4 */);
 int h2agg_grand_product_dev(h2agg_ctx* ctx, const void* d_num, const void* d_den, size_t n, void* d_z);
+
+/* N3, sorting half: halo2_proofs plonk/lookup/prover.rs permute_expression_pair over the usable rows
+ * (n - blinding_factors - 1; the caller appends its random blinding rows):
+ *   permuted_input = the input sorted by Fr::cmp (numeric order of the canonical value);
+ *   permuted_table[row] = permuted_input[row] on every row where the sorted input changes value (one instance of that
+ *   value leaves the table multiset); the remaining table values, ascending, fill the rows of repeated inputs taken
+ *   from the back.  The verifier's view of the result: halo2-snark-aggregator-api/src/systems/halo2/lookup.rs:58-119.
+ * Returns 4 (halo2: Error::ConstraintSystemFailure) when an input value does not occur in the table; the outputs are
+ * then unspecified.  Outputs may alias the inputs.  The _dev form synchronises the stream to read that status. */
+int h2agg_permute_expression_pair(h2agg_ctx* ctx, const uint64_t* input /* u*4 */, const uint64_t* table /* u*4 */,
+                                  size_t usable_rows, uint64_t* permuted_input, uint64_t* permuted_table);
+int h2agg_permute_expression_pair_dev(h2agg_ctx* ctx, const void* d_input, const void* d_table, size_t usable_rows,
+                                      void* d_permuted_input, void* d_permuted_table);
+/* a <- a sorted ascending by Fr::cmp (Montgomery in and out), in place: the sort inside the above, exposed. n <= 2^25. */
+int h2agg_sort_fr(h2agg_ctx* ctx, uint64_t* a /* n*4 */, size_t n);
+int h2agg_sort_fr_dev(h2agg_ctx* ctx, void* d_a, size_t n);
 
 /* ---- N1 (next row, rank 1): quotient numerator on the extended coset -----------------------------
  * Replaces halo2_proofs plonk/evaluation.rs Evaluator::evaluate_h (+ EvaluationDomain::divide_by_vanishing_poly

@@ -20,9 +20,11 @@
 // Deliberately shares NO code with the CUDA path (different limb width, different Montgomery
 // schedule, Jacobian instead of XYZZ coordinates, unsigned windows instead of signed digits).
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <map>
 #include <thread>
 #include <vector>
 
@@ -720,6 +722,64 @@ void oracle_grand_product(const uint64_t* num, const uint64_t* den, size_t n, ui
     memcpy(b.v, d.data() + 4 * i, 32);
     run = mul(run, mul(a, b));
   }
+}
+
+// halo2_proofs plonk/lookup/prover.rs `permute_expression_pair` (external crate) over the usable rows,
+// WITHOUT the random blinding rows the caller appends.  Restated step by step: sort the input (Fr::cmp = numeric order
+// of the canonical value), count the table values in an ordered map (BTreeMap), give every first occurrence of an input
+// value its own table cell and take one instance out of the map, remember the rows of repeated inputs, then hand the
+// leftover table values out in ascending order to the remembered rows popped from the BACK.
+// Returns 0, or 1 when an input value does not occur in the table (halo2: Error::ConstraintSystemFailure).
+struct CanonLess {
+  bool operator()(const std::array<u64, 4>& a, const std::array<u64, 4>& b) const {
+    for (int i = 3; i >= 0; i--)
+      if (a[i] != b[i]) return a[i] < b[i];
+    return false;
+  }
+};
+int oracle_permute_expression_pair(const uint64_t* input, const uint64_t* table, size_t usable_rows, uint64_t* permuted_input,
+                                   uint64_t* permuted_table) {
+  const size_t u = usable_rows;
+  auto canon = [](const uint64_t* p) {
+    Fr a;
+    memcpy(a.v, p, 32);
+    std::array<u64, 4> r;
+    from_mont(a, r.data());
+    return r;
+  };
+  auto mont = [](const std::array<u64, 4>& c, uint64_t* out) {
+    Fr m = to_mont<FrP>(c.data());
+    memcpy(out, m.v, 32);
+  };
+  std::vector<std::array<u64, 4>> in(u);
+  for (size_t i = 0; i < u; i++) in[i] = canon(input + 4 * i);
+  std::sort(in.begin(), in.end(), CanonLess());
+  std::map<std::array<u64, 4>, uint32_t, CanonLess> leftover;
+  for (size_t i = 0; i < u; i++) leftover[canon(table + 4 * i)]++;
+  std::vector<std::array<u64, 4>> tab(u, std::array<u64, 4>{0, 0, 0, 0});
+  std::vector<size_t> repeated;
+  for (size_t row = 0; row < u; row++) {
+    if (row == 0 || in[row] != in[row - 1]) {
+      tab[row] = in[row];
+      auto it = leftover.find(in[row]);
+      if (it == leftover.end() || it->second == 0) return 1;
+      it->second--;
+    } else {
+      repeated.push_back(row);
+    }
+  }
+  for (auto& kv : leftover)
+    for (uint32_t c = 0; c < kv.second; c++) {
+      if (repeated.empty()) return 2;  // cannot happen: |table| = |input|
+      tab[repeated.back()] = kv.first;
+      repeated.pop_back();
+    }
+  if (!repeated.empty()) return 2;
+  for (size_t i = 0; i < u; i++) {
+    mont(in[i], permuted_input + 4 * i);
+    mont(tab[i], permuted_table + 4 * i);
+  }
+  return 0;
 }
 
 // halo2_proofs plonk/evaluation.rs Evaluator::evaluate_h (+ divide_by_vanishing_poly when t_evals != null), driven

@@ -1,0 +1,43 @@
+"""Python big-int pin for the lookup argument's `permute_expression_pair`.  TEST INFRASTRUCTURE.
+
+halo2_proofs plonk/lookup/prover.rs (external crate; scroll-tech/halo2 @ 3370852d, Cargo.lock:1549-1551) -- restated
+from its published algorithm.  What the reference itself holds about this step is the verifier's view of its result
+(halo2-snark-aggregator-api/src/systems/halo2/lookup.rs:58-119): the permuted columns must satisfy
+    (a'(X) - s'(X)) * (a'(X) - a'(omega^-1 X)) = 0   on active rows,   a'(1) = s'(1),
+and be permutations of the inputs (the grand product z).  `check_lookup_constraints` states exactly those properties;
+the tests hold both the restated algorithm and the GPU result against them.
+"""
+
+
+def permute_expression_pair(inp, tab):
+    """ints (canonical) -> (permuted_input, permuted_table); raises ValueError if an input value is not in the table."""
+    u = len(inp)
+    assert len(tab) == u
+    a = sorted(inp)
+    leftover = {}
+    for v in tab:
+        leftover[v] = leftover.get(v, 0) + 1
+    s = [0] * u
+    repeated = []
+    for row, v in enumerate(a):
+        if row == 0 or v != a[row - 1]:
+            s[row] = v
+            if leftover.get(v, 0) == 0:
+                raise ValueError("ConstraintSystemFailure: input value not in table")
+            leftover[v] -= 1
+        else:
+            repeated.append(row)
+    for v in sorted(leftover):          # BTreeMap iteration = ascending
+        for _ in range(leftover[v]):
+            s[repeated.pop()] = v       # Vec::pop = from the back
+    assert not repeated
+    return a, s
+
+
+def check_lookup_constraints(inp, tab, a, s):
+    """The properties the verifier enforces on (a', s') -- independent of how they were produced."""
+    assert sorted(a) == sorted(inp), "a' is not a permutation of the input"
+    assert sorted(s) == sorted(tab), "s' is not a permutation of the table"
+    assert a[0] == s[0]
+    for i in range(1, len(a)):
+        assert a[i] == s[i] or a[i] == a[i - 1], "row %d violates (a'-s')(a'-a'_prev) = 0" % i

@@ -25,6 +25,10 @@ extern "C" {
     pub fn h2agg_intt_fr(ctx: *mut h2agg_ctx, a: *mut u64, omega_inv: *const u64, n_inv: *const u64, log_n: u32) -> c_int;
     pub fn h2agg_coeff_to_extended(ctx: *mut h2agg_ctx, coeffs: *const u64, k: u32, ext_k: u32, zeta: *const u64, omega_ext: *const u64, out: *mut u64) -> c_int;
     pub fn h2agg_extended_to_coeff(ctx: *mut h2agg_ctx, a: *mut u64, ext_k: u32, omega_ext_inv: *const u64, ext_n_inv: *const u64, zeta: *const u64, out_len: usize) -> c_int;
+    pub fn h2agg_eval_polynomial(ctx: *mut h2agg_ctx, poly: *const u64, n: usize, point: *const u64, out: *mut u64) -> c_int;
+    pub fn h2agg_kate_division(ctx: *mut h2agg_ctx, a: *const u64, n: usize, b: *const u64, q: *mut u64) -> c_int;
+    pub fn h2agg_permute_expression_pair(ctx: *mut h2agg_ctx, input: *const u64, table: *const u64, usable_rows: usize, permuted_input: *mut u64, permuted_table: *mut u64) -> c_int;
+    pub fn h2agg_commit_round_resident(ctx: *mut h2agg_ctx, srs_id: u64, lagrange_cols: *const *const u64, n_cols: usize, k: u32, omega_inv: *const u64, n_inv: *const u64, out_affine: *mut u64, d_coeff_out: *const *mut c_void, ext_k: u32, zeta: *const u64, omega_ext: *const u64, d_ext_out: *const *mut c_void) -> c_int;
 }
 
 struct Ctx(*mut h2agg_ctx);
@@ -119,4 +123,30 @@ pub fn extended_to_coeff(a: &mut Vec<Fr>, ext_k: u32, omega_ext_inv: Fr, ext_n_i
     assert_eq!(a.len(), 1 << ext_k);
     check(unsafe { h2agg_extended_to_coeff(ctx(), a.as_mut_ptr() as *mut u64, ext_k, &omega_ext_inv as *const Fr as *const u64, &ext_n_inv as *const Fr as *const u64, &zeta as *const Fr as *const u64, out_len) });
     a.truncate(out_len);
+}
+
+/// Drop-in body for the sort + BTreeMap loop of `plonk::lookup::prover::permute_expression_pair` (usable rows only;
+/// the caller appends its blinding rows).  `Err(())` = an input value is missing from the table, which halo2 reports
+/// as `Error::ConstraintSystemFailure`.
+pub fn permute_expression_pair(input: &[Fr], table: &[Fr]) -> Result<(Vec<Fr>, Vec<Fr>), ()> {
+    assert_eq!(input.len(), table.len());
+    let (mut a, mut s) = (vec![Fr::zero(); input.len()], vec![Fr::zero(); input.len()]);
+    let rc = unsafe { h2agg_permute_expression_pair(ctx(), input.as_ptr() as *const u64, table.as_ptr() as *const u64, input.len(), a.as_mut_ptr() as *mut u64, s.as_mut_ptr() as *mut u64) };
+    if rc == 4 {
+        return Err(());
+    }
+    check(rc);
+    Ok((a, s))
+}
+
+/// Drop-in bodies for `halo2_proofs::arithmetic::{eval_polynomial, kate_division}`.
+pub fn eval_polynomial(poly: &[Fr], point: Fr) -> Fr {
+    let mut out = Fr::zero();
+    check(unsafe { h2agg_eval_polynomial(ctx(), poly.as_ptr() as *const u64, poly.len(), &point as *const Fr as *const u64, &mut out as *mut Fr as *mut u64) });
+    out
+}
+pub fn kate_division(a: &[Fr], b: Fr) -> Vec<Fr> {
+    let mut q = vec![Fr::zero(); a.len() - 1];
+    check(unsafe { h2agg_kate_division(ctx(), a.as_ptr() as *const u64, a.len(), &b as *const Fr as *const u64, q.as_mut_ptr() as *mut u64) });
+    q
 }

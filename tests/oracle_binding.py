@@ -54,6 +54,8 @@ def oracle():
         lib.oracle_batch_invert.argtypes = [c_vp, sz]
         lib.oracle_grand_product.argtypes = [c_vp, c_vp, sz, c_vp]
         lib.oracle_evaluate_h.argtypes = [c_vp, sz, ctypes.POINTER(c_vp), c_vp, u32, u32] + [c_vp] * 8 + [sz, c_vp, ui]
+        lib.oracle_permute_expression_pair.argtypes = [c_vp, c_vp, sz, c_vp, c_vp]
+        lib.oracle_permute_expression_pair.restype = ci
         lib.oracle_hw_threads.restype = ui
         _o = lib
     return _o
@@ -170,6 +172,13 @@ def grand_product(num, den):
     z = np.zeros_like(num)
     oracle().oracle_grand_product(P(num), P(den), num.size // 4, P(z))
     return z
+
+
+def permute_expression_pair(inp, tab):
+    """-> (status, permuted_input, permuted_table); status 1 = an input value is missing from the table"""
+    a, b = np.zeros_like(inp), np.zeros_like(tab)
+    rc = oracle().oracle_permute_expression_pair(P(inp), P(tab), inp.size // 4, P(a), P(b))
+    return rc, a, b
 
 
 def evaluate_h(plan_words, consts, ext_cols, k, ext_k, y, beta, gamma, theta, omega_ext, zeta, delta, t_evals=None,

@@ -142,3 +142,28 @@ def test_batch_invert_and_grand_product_vs_python_bigint():
         want.append(run)
         run = run * x * pow(y, -1, R_MOD) % R_MOD
     assert z == want
+
+
+def test_permute_expression_pair_oracle_vs_python_pin():
+    """C++ restatement of halo2's permute_expression_pair == the Python big-int restatement, and both satisfy the
+    properties the reference's verifier enforces on (a', s') (systems/halo2/lookup.rs:58-119)."""
+    import random
+
+    import lookup_ref as lr
+    import quotient_util as qu
+
+    rng = random.Random(3)
+    for u in (1, 2, 3, 17, 256, 1500):
+        pool = [rng.randrange(qu.R) for _ in range(max(1, u // 4))] + list(range(5))
+        table = [rng.choice(pool) for _ in range(u)]
+        inp = [rng.choice(table) for _ in range(u)]
+        a, s = lr.permute_expression_pair(inp, table)
+        lr.check_lookup_constraints(inp, table, a, s)
+        rc, ga, gs = ob.permute_expression_pair(qu.pack(inp), qu.pack(table))
+        assert rc == 0 and qu.unpack(ga) == a and qu.unpack(gs) == s
+    assert ob.permute_expression_pair(qu.pack([5, 6]), qu.pack([5, 5]))[0] == 1
+    with pytest.raises(ValueError):
+        lr.permute_expression_pair([5, 6], [5, 5])
+    # hand-checked example: leftovers ascending go to repeated rows from the back
+    a, s = lr.permute_expression_pair([2, 1, 2, 2, 1], [1, 2, 7, 3, 9])
+    assert a == [1, 1, 2, 2, 2] and s == [1, 9, 2, 7, 3]
