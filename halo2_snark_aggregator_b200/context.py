@@ -199,16 +199,46 @@ class Context:
                                                _ptr(zeta), _ptr(omega_ext), eo))
         return out.reshape(nc, 8)
 
-    def commit_round_resident(self, srs_id, cols, k, omega_inv, n_inv, d_coeff_out, ext_k=0, zeta=None, omega_ext=None, d_ext_out=None):
-        """Commit round whose coefficient / extended forms stay in HBM (device pointers) -> affine commitments (len(cols), 8)."""
+    def commit_round_resident(self, srs_id, cols, k, omega_inv, n_inv, d_coeff_out, ext_k=0, zeta=None, omega_ext=None, d_ext_out=None,
+                              d_lagrange_out=None):
+        """Commit round whose coefficient / extended (/ Lagrange) forms stay in HBM (device pointers) -> affine commitments (len(cols), 8)."""
         nc = len(cols)
         a = (c_vp * nc)(*[c.ctypes.data for c in cols])
         co = (c_vp * nc)(*d_coeff_out)
         eo = (c_vp * nc)(*d_ext_out) if d_ext_out is not None else None
+        lo = (c_vp * nc)(*d_lagrange_out) if d_lagrange_out is not None else None
         out = np.zeros(8 * nc, dtype=np.uint64)
-        self.check(self.lib.h2agg_commit_round_resident(self.h, srs_id, a, nc, k, _ptr(omega_inv), _ptr(n_inv), _ptr(out), co, ext_k,
+        self.check(self.lib.h2agg_commit_round_resident(self.h, srs_id, a, nc, k, _ptr(omega_inv), _ptr(n_inv), _ptr(out), lo, co, ext_k,
                                                         _ptr(zeta), _ptr(omega_ext), eo))
         return out.reshape(nc, 8)
+
+    def commit_round_dev(self, srs_id, d_cols, k, omega_inv, n_inv, d_coeff_out, ext_k=0, zeta=None, omega_ext=None, d_ext_out=None):
+        """The same round for Lagrange columns already in HBM."""
+        nc = len(d_cols)
+        a = (c_vp * nc)(*d_cols)
+        co = (c_vp * nc)(*d_coeff_out)
+        eo = (c_vp * nc)(*d_ext_out) if d_ext_out is not None else None
+        out = np.zeros(8 * nc, dtype=np.uint64)
+        self.check(self.lib.h2agg_commit_round_dev(self.h, srs_id, a, nc, k, _ptr(omega_inv), _ptr(n_inv), _ptr(out), co, ext_k,
+                                                   _ptr(zeta), _ptr(omega_ext), eo))
+        return out.reshape(nc, 8)
+
+    # -- N3: lookup / permutation arguments on resident Lagrange columns
+    def compress_expressions_dev(self, words, consts, d_columns, k, theta, d_out):
+        """words: uint32 array { n_exprs, POLY x n_exprs }; consts: Montgomery limbs (n_consts*4) or empty."""
+        cols = (c_vp * len(d_columns))(*d_columns)
+        self.check(self.lib.h2agg_compress_expressions_dev(self.h, words.ctypes.data, words.size, cols, len(d_columns),
+                                                           consts.ctypes.data if consts.size else None, consts.size // 4, k,
+                                                           _ptr(theta), c_vp(d_out)))
+
+    def lookup_product_dev(self, d_a, d_s, d_ap, d_sp, n, beta, gamma, d_z):
+        self.check(self.lib.h2agg_lookup_product_dev(self.h, c_vp(d_a), c_vp(d_s), c_vp(d_ap), c_vp(d_sp), n, _ptr(beta), _ptr(gamma), c_vp(d_z)))
+
+    def permutation_product_dev(self, d_values, d_sigmas, k, omega, beta_delta_start, delta, beta, gamma, d_last_z, d_z):
+        v = (c_vp * len(d_values))(*d_values)
+        s = (c_vp * len(d_sigmas))(*d_sigmas)
+        self.check(self.lib.h2agg_permutation_product_dev(self.h, v, s, len(d_values), k, _ptr(omega), _ptr(beta_delta_start), _ptr(delta),
+                                                          _ptr(beta), _ptr(gamma), c_vp(d_last_z) if d_last_z else None, c_vp(d_z)))
 
     def ntt_fr_dev(self, d_a, omega, log_n, scale=None):
         self.check(self.lib.h2agg_ntt_fr_dev(self.h, c_vp(d_a), _ptr(omega), _ptr(scale), log_n))

@@ -110,6 +110,8 @@ void h2agg_destroy(h2agg_ctx* ctx) {
   cudaFree(ctx->poly_ws.p);
   cudaFree(ctx->scan_ws.p);
   cudaFree(ctx->sort_ws.p);
+  cudaFree(ctx->args_ws.p);
+  cudaFree(ctx->args_meta.p);
   cudaFree(ctx->quot_ws.p);
   cudaFree(ctx->quot_tw.p);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
@@ -633,7 +635,8 @@ int h2agg_coeff_to_extended_batch(h2agg_ctx* ctx, const uint64_t* const* coeff_c
 static int commit_round_impl(h2agg_ctx* ctx, uint64_t srs_id, const uint64_t* const* lagrange_cols, size_t n_cols, uint32_t k,
                              const uint64_t omega_inv[4], const uint64_t n_inv[4], uint64_t* out_affine,
                              uint64_t* const* coeff_out, uint32_t ext_k, const uint64_t zeta[4], const uint64_t omega_ext[4],
-                             uint64_t* const* ext_out, bool resident) {
+                             uint64_t* const* ext_out, bool resident, void* const* d_lagrange_keep = nullptr,
+                             bool src_on_device = false) {
   if (!ctx) return 1;
   LOCK(ctx);
   CHECK_ARG(ctx, srs_id != 0 && lagrange_cols && out_affine && omega_inv && n_inv, "commit_round: null argument");
@@ -659,10 +662,17 @@ static int commit_round_impl(h2agg_ctx* ctx, uint64_t srs_id, const uint64_t* co
   for (size_t i = 0; i < n_cols; i++) {
     Lane& ln = ctx->lanes[i % N_LANES];
     CHECK_ARG(ctx, lagrange_cols[i], "commit_round: null column");
-    if ((rc = ensure(ctx, ln.io, n * 32 + 64))) return rc;
+    if (!src_on_device && !(d_lagrange_keep && d_lagrange_keep[i]) && (rc = ensure(ctx, ln.io, n * 32 + 64))) return rc;
     if (!resident && ext_out && ext_out[i] && (rc = ensure(ctx, ln.io_out, ((size_t)1 << ext_k) * 32))) return rc;
-    H2AGG_CUDA(ctx, cudaMemcpyAsync(ln.io.p, lagrange_cols[i], n * 32, cudaMemcpyHostToDevice, ln.st));
-    if ((rc = msm_run(ctx, ln.st, ln.ws, bases, ln.io.p, n, (uint8_t*)ctx->small.p + i * 160, 0, -1))) return rc;
+    // the Lagrange column: already in HBM, uploaded into the caller's resident buffer, or staged in the lane
+    void* col = ln.io.p;
+    if (src_on_device) {
+      col = const_cast<uint64_t*>(lagrange_cols[i]);
+    } else {
+      if (d_lagrange_keep && d_lagrange_keep[i]) col = d_lagrange_keep[i];
+      H2AGG_CUDA(ctx, cudaMemcpyAsync(col, lagrange_cols[i], n * 32, cudaMemcpyHostToDevice, ln.st));
+    }
+    if ((rc = msm_run(ctx, ln.st, ln.ws, bases, col, n, (uint8_t*)ctx->small.p + i * 160, 0, -1))) return rc;
     if (coeff_out && coeff_out[i]) {
       cudaStream_t st = ln.st;
       if (i == 0) {  // tables are generated on the main stream: run column 0's transforms there, then re-fork
@@ -671,7 +681,7 @@ static int commit_round_impl(h2agg_ctx* ctx, uint64_t srs_id, const uint64_t* co
         st = ctx->stream;
       }
       if (resident) {
-        if ((rc = ntt_run(ctx, ln.io.p, coeff_out[i], oi, st, &ln.ntt_tmp))) return rc;
+        if ((rc = ntt_run(ctx, col, coeff_out[i], oi, st, &ln.ntt_tmp))) return rc;
         if (ext_out && ext_out[i] && (rc = ntt_run(ctx, coeff_out[i], ext_out[i], oe, st, &ln.ntt_tmp))) return rc;
       } else {
         if ((rc = ntt_run(ctx, ln.io.p, ln.io.p, oi, st, &ln.ntt_tmp))) return rc;
@@ -707,15 +717,30 @@ int h2agg_commit_round(h2agg_ctx* ctx, uint64_t srs_id, const uint64_t* const* l
 
 int h2agg_commit_round_resident(h2agg_ctx* ctx, uint64_t srs_id, const uint64_t* const* lagrange_cols, size_t n_cols,
                                 uint32_t k, const uint64_t omega_inv[4], const uint64_t n_inv[4], uint64_t* out_affine,
-                                void* const* d_coeff_out, uint32_t ext_k, const uint64_t zeta[4],
-                                const uint64_t omega_ext[4], void* const* d_ext_out) {
+                                void* const* d_lagrange_out, void* const* d_coeff_out, uint32_t ext_k,
+                                const uint64_t zeta[4], const uint64_t omega_ext[4], void* const* d_ext_out) {
   if (ctx && !d_coeff_out) {
     LOCK(ctx);
     ctx->last_error = "commit_round_resident: d_coeff_out is NULL (use h2agg_msm_g1_batch for commitments only)";
     return 1;
   }
   return commit_round_impl(ctx, srs_id, lagrange_cols, n_cols, k, omega_inv, n_inv, out_affine,
-                           (uint64_t* const*)d_coeff_out, ext_k, zeta, omega_ext, (uint64_t* const*)d_ext_out, true);
+                           (uint64_t* const*)d_coeff_out, ext_k, zeta, omega_ext, (uint64_t* const*)d_ext_out, true,
+                           d_lagrange_out, false);
+}
+
+int h2agg_commit_round_dev(h2agg_ctx* ctx, uint64_t srs_id, const void* const* d_lagrange_cols, size_t n_cols, uint32_t k,
+                           const uint64_t omega_inv[4], const uint64_t n_inv[4], uint64_t* out_affine,
+                           void* const* d_coeff_out, uint32_t ext_k, const uint64_t zeta[4], const uint64_t omega_ext[4],
+                           void* const* d_ext_out) {
+  if (ctx && !d_coeff_out) {
+    LOCK(ctx);
+    ctx->last_error = "commit_round_dev: d_coeff_out is NULL (use h2agg_msm_g1_batch_dev for commitments only)";
+    return 1;
+  }
+  return commit_round_impl(ctx, srs_id, (const uint64_t* const*)d_lagrange_cols, n_cols, k, omega_inv, n_inv, out_affine,
+                           (uint64_t* const*)d_coeff_out, ext_k, zeta, omega_ext, (uint64_t* const*)d_ext_out, true, nullptr,
+                           true);
 }
 
 int h2agg_extended_to_coeff_dev(h2agg_ctx* ctx, void* d_a, uint32_t ext_k, const uint64_t omega_ext_inv[4],

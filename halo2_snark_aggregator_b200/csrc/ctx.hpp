@@ -71,6 +71,9 @@ struct h2agg_ctx {
   h2agg::DevBuf small;        // small constants / results
   h2agg::DevBuf poly_ws;      // recursion levels of eval_polynomial / kate_division
   h2agg::DevBuf scan_ws;      // batch_invert / grand_product scratch
+  h2agg::DevBuf args_ws;      // lookup / permutation products: numerators and denominators
+  h2agg::DevBuf args_meta;    // compress_expressions: device copies of expression lists (four slots)
+  int args_flip = 0;
   h2agg::DevBuf sort_ws;      // sort_fr / permute_expression_pair: key ping-pong buffers, histograms, flags
   h2agg::DevBuf quot_ws;      // evaluate_h: device copy of plan / column pointers / constants (two halves)
   h2agg::DevBuf quot_tw;      // evaluate_h: omega_ext^i two-level table

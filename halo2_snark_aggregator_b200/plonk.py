@@ -282,6 +282,34 @@ class QuotientPlan:
         return w
 
 
+class ExpressionList:
+    """{ n_exprs, POLY x n_exprs } word list + constants for h2agg_compress_expressions_dev; `index` maps
+    (kind, column) to a position in the caller's column array."""
+
+    def __init__(self, exprs, index):
+        self._consts, self._const_index = [], {}
+        w = [len(exprs)]
+        for e in exprs:
+            terms = e.expand()
+            w.append(len(terms))
+            for mono in sorted(terms):
+                c = terms[mono]
+                if c == 1:
+                    w.append(NOCONST)
+                else:
+                    if c not in self._const_index:
+                        self._const_index[c] = len(self._consts)
+                        self._consts.append(c)
+                    w.append(self._const_index[c])
+                w.append(len(mono))
+                for kind, col, rot in mono:
+                    assert -32768 <= rot < 32768
+                    w.append(index[(kind, col)] | ((rot & 0xFFFF) << 16))
+        self.words = np.array(w, dtype=np.uint32)
+        self.consts = (np.concatenate([fr_mont(c) for c in self._consts]) if self._consts
+                       else np.zeros(0, dtype=np.uint64))
+
+
 def build_quotient_plan(cs):
     return QuotientPlan(cs)
 

@@ -4,6 +4,8 @@ What the reference runs under halo2-snark-aggregator-circuit/src/verify_circuit.
 halo2_proofs, plonk/prover.rs; order restated in SURVEY.md App. B4) is, once the witness columns exist:
 
     1-3  commit rounds       commit_lagrange + lagrange_to_coeff (+ coeff_to_extended)   K1 / K2 / K3
+         (2: permuted lookup columns = compress_expressions + permute_expression_pair;    N3
+          3: permutation / lookup grand products)                                        N3
     4    quotient            evaluate_h, divide_by_vanishing_poly, extended_to_coeff,     N1 / K3 / K1
                              commit the n-coefficient pieces of h
     5    evaluation round    eval_polynomial of every queried polynomial at x * omega^rot  N2
@@ -12,8 +14,9 @@ halo2_proofs, plonk/prover.rs; order restated in SURVEY.md App. B4) is, once the
 `ResidentProver` strings the C-ABI entry points together so that every polynomial stays in HBM between those
 stages: columns arrive from host memory once (h2agg_commit_round_resident) and only commitments and evaluations
 travel back.  It is a host-side orchestration layer -- all arithmetic runs in the CUDA kernels; challenges are
-inputs (in the reference they come from the Rust transcript between the stages).  Not on this path: blinding,
-the lookup permutation / grand products themselves (N3) and the transcript, which stay with the caller.
+inputs (in the reference they come from the Rust transcript between the stages) and so are the blinding values
+(halo2 draws them from its RNG).  The second and third round can either be uploaded like the first
+(`commit_columns`) or be computed from the resident advice / fixed columns (`lookup_round`, `product_round`).
 """
 import numpy as np
 
@@ -31,7 +34,7 @@ class ResidentProver:
         self.dom = EvaluationDomain(cs.degree(), k, ctx)
         self.ext_k, self.ext_n = self.dom.extended_k, self.dom.extended_len()
         self.srs_lagrange, self.srs_g = srs_lagrange, srs_g
-        self.coeff, self.ext = {}, {}      # column name -> device pointer
+        self.coeff, self.ext, self.lag = {}, {}, {}      # column name -> device pointer (coefficient / extended / Lagrange form)
         self._owned = []
         self._t = np.concatenate([plonk.fr_mont(v) for v in plonk.t_evaluations(k, self.ext_k)])
         self.n_pieces = self.dom.quotient_poly_degree
@@ -69,15 +72,83 @@ class ResidentProver:
         self._owned = []
 
     # -- stages 1-3: commit rounds -------------------------------------------------------------------
-    def commit_columns(self, names, lagrange_cols, extended=True):
+    def lagrange_slot(self, name):
+        if name not in self.lag:
+            self.lag[name] = self._alloc(self.n * 32)
+        return self.lag[name]
+
+    def commit_columns(self, names, lagrange_cols, extended=True, keep_lagrange=False):
         """One commit round from HOST Lagrange columns -> affine commitments (len, 8).  The coefficient and
-        extended forms stay resident under `names`."""
+        extended forms (and, on request, the Lagrange form the lookup / permutation arguments read) stay resident
+        under `names`."""
         slots = [self.slot(nm, extended) for nm in names]
         d = self.dom
         return self.ctx.commit_round_resident(
             self.srs_lagrange, list(lagrange_cols), self.k, d.omega_inv, d.ifft_divisor, [s[0] for s in slots],
             ext_k=self.ext_k if extended else 0, zeta=d.g_coset if extended else None,
-            omega_ext=d.extended_omega if extended else None, d_ext_out=[s[1] for s in slots] if extended else None)
+            omega_ext=d.extended_omega if extended else None, d_ext_out=[s[1] for s in slots] if extended else None,
+            d_lagrange_out=[self.lagrange_slot(nm) for nm in names] if keep_lagrange else None)
+
+    def _commit_resident(self, names):
+        """Commit round for Lagrange columns the device produced itself (self.lag[name])."""
+        slots = [self.slot(nm) for nm in names]
+        d = self.dom
+        return self.ctx.commit_round_dev(self.srs_lagrange, [self.lag[nm] for nm in names], self.k, d.omega_inv, d.ifft_divisor,
+                                         [s[0] for s in slots], ext_k=self.ext_k, zeta=d.g_coset, omega_ext=d.extended_omega,
+                                         d_ext_out=[s[1] for s in slots])
+
+    # -- stage 2: lookup arguments (commit_permuted) -----------------------------------------------------
+    def usable_rows(self):
+        return self.n - (self.cs.blinding_factors() + 1)
+
+    def lookup_round(self, theta, blind):
+        """Per lookup: compress the input / table expressions over the resident Lagrange columns, sort + permute them
+        over the usable rows (permute_expression_pair), append the caller's blinding rows, commit.
+        blind(name, rows) -> uint64 array rows*4 (the values halo2 draws from its RNG)."""
+        names = [nm for nm in self.lag if nm[0] in ("fixed", "advice", "instance")]
+        index = {nm: i for i, nm in enumerate(names)}
+        cols = [self.lag[nm] for nm in names]
+        u, tail = self.usable_rows(), self.cs.blinding_factors() + 1
+        th = fr_to_limbs(theta)
+        out_names = []
+        for i, (_, ins, tabs) in enumerate(self.cs.lookups):
+            for side, exprs in (("input", ins), ("table", tabs)):
+                prog = plonk.ExpressionList(exprs, index)
+                self.ctx.compress_expressions_dev(prog.words, prog.consts, cols, self.k, th,
+                                                  self.lagrange_slot(("lookup_%s_compressed" % side, i)))
+            pa, ps = self.lagrange_slot(("lookup_input", i)), self.lagrange_slot(("lookup_table", i))
+            self.ctx.permute_expression_pair_dev(self.lag[("lookup_input_compressed", i)], self.lag[("lookup_table_compressed", i)],
+                                                 u, pa, ps)
+            for nm, p in ((("lookup_input", i), pa), (("lookup_table", i), ps)):
+                self.ctx.h2d(p + 32 * u, np.ascontiguousarray(blind(nm, tail)))
+                out_names.append(nm)
+        return self._commit_resident(out_names)
+
+    # -- stage 3: grand products (permutation::commit, lookup commit_product) ------------------------------
+    def product_round(self, beta, gamma, blind):
+        bf = self.cs.blinding_factors()
+        u = self.usable_rows()
+        b, g = fr_to_limbs(beta), fr_to_limbs(gamma)
+        out_names = []
+        chunk = self.cs.chunk_len()
+        pcs = self.cs.permutation_columns
+        last = None
+        for s in range(self.cs.num_permutation_sets()):
+            cols = pcs[s * chunk:(s + 1) * chunk]
+            z = self.lagrange_slot(("perm_z", s))
+            self.ctx.permutation_product_dev([self.lag[c] for c in cols], [self.lag[("sigma", s * chunk + j)] for j in range(len(cols))],
+                                             self.k, self.dom.omega, fr_to_limbs(beta * pow(plonk.DELTA, s * chunk, _R)),
+                                             fr_to_limbs(plonk.DELTA), b, g, last, z)
+            self.ctx.h2d(z + 32 * (self.n - bf), np.ascontiguousarray(blind(("perm_z", s), bf)))
+            last = z + 32 * u
+            out_names.append(("perm_z", s))
+        for i in range(len(self.cs.lookups)):
+            z = self.lagrange_slot(("lookup_z", i))
+            self.ctx.lookup_product_dev(self.lag[("lookup_input_compressed", i)], self.lag[("lookup_table_compressed", i)],
+                                        self.lag[("lookup_input", i)], self.lag[("lookup_table", i)], self.n, b, g, z)
+            self.ctx.h2d(z + 32 * (self.n - bf), np.ascontiguousarray(blind(("lookup_z", i), bf)))
+            out_names.append(("lookup_z", i))
+        return self._commit_resident(out_names)
 
     def commit_coeff_columns(self, names, coeff_cols):
         """Polynomials the prover creates in COEFFICIENT form (the vanishing argument's random polynomial):

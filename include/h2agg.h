@@ -161,8 +161,15 @@ int h2agg_commit_round(h2agg_ctx* ctx, uint64_t srs_id, const uint64_t* const* l
  * quotients (N2) consume them, so that only the 64-byte commitments travel back over PCIe. */
 int h2agg_commit_round_resident(h2agg_ctx* ctx, uint64_t srs_id, const uint64_t* const* lagrange_cols, size_t n_cols,
                                 uint32_t k, const uint64_t omega_inv[4], const uint64_t n_inv[4], uint64_t* out_affine,
+                                void* const* d_lagrange_out /* NULL, or per column NULL / 2^k*32 B: keep the Lagrange form too */,
                                 void* const* d_coeff_out, uint32_t ext_k, const uint64_t zeta[4],
                                 const uint64_t omega_ext[4], void* const* d_ext_out);
+/* The same round for Lagrange columns that are ALREADY in HBM (columns the device produced itself: the permuted
+ * lookup columns and the grand products of the second and third round).  The commitments come back to the host. */
+int h2agg_commit_round_dev(h2agg_ctx* ctx, uint64_t srs_id, const void* const* d_lagrange_cols, size_t n_cols, uint32_t k,
+                           const uint64_t omega_inv[4], const uint64_t n_inv[4], uint64_t* out_affine,
+                           void* const* d_coeff_out, uint32_t ext_k, const uint64_t zeta[4], const uint64_t omega_ext[4],
+                           void* const* d_ext_out);
 int h2agg_coeff_to_extended_dev(h2agg_ctx* ctx, const void* d_coeffs, uint32_t k, uint32_t ext_k,
                                 const uint64_t zeta[4], const uint64_t omega_ext[4], void* d_out);
 int h2agg_extended_to_coeff_dev(h2agg_ctx* ctx, void* d_a, uint32_t ext_k, const uint64_t omega_ext_inv[4],
@@ -198,6 +205,26 @@ int h2agg_permute_expression_pair(h2agg_ctx* ctx, const uint64_t* input /* u*4 *
                                   size_t usable_rows, uint64_t* permuted_input, uint64_t* permuted_table);
 int h2agg_permute_expression_pair_dev(h2agg_ctx* ctx, const void* d_input, const void* d_table, size_t usable_rows,
                                       void* d_permuted_input, void* d_permuted_table);
+/* N3, the row-wise steps around the sort and the running products (halo2_proofs plonk/lookup/prover.rs and
+ * plonk/permutation/prover.rs; the recurrences are the ones the reference's verifier checks,
+ * halo2-snark-aggregator-api/src/systems/halo2/lookup.rs:58-119, permutation.rs:54-136).  Device-resident, asynchronous.
+ *   compress_expressions: exprs = { n_exprs, POLY x n_exprs } (POLY as in the quotient plan below) over LAGRANGE columns of
+ *       2^k rows; a rotation r reads row (i + r) mod 2^k; out[i] = fold(acc * theta + expr_j(i)).
+ *   lookup_product: z[0] = 1, z[i+1] = z[i] (A[i] + beta)(S[i] + gamma) / ((A'[i] + beta)(S'[i] + gamma)), n rows.
+ *   permutation_product (one column set of <= 16 columns): z[0] = *d_last_z (1 if NULL),
+ *       z[i+1] = z[i] prod_j (v_j[i] + beta delta^(first + j) omega^i + gamma) / (v_j[i] + beta sigma_j[i] + gamma);
+ *       beta_delta_start = beta * delta^first, `first` = index of the set's first column in the permutation.
+ * All n = 2^k rows are produced; the caller overwrites the last blinding_factors rows with its random values. */
+int h2agg_compress_expressions_dev(h2agg_ctx* ctx, const uint32_t* exprs, size_t n_words, const void* const* d_columns,
+                                   size_t n_columns, const uint64_t* consts, size_t n_consts, uint32_t k,
+                                   const uint64_t theta[4], void* d_out);
+int h2agg_lookup_product_dev(h2agg_ctx* ctx, const void* d_input, const void* d_table, const void* d_permuted_input,
+                             const void* d_permuted_table, size_t n, const uint64_t beta[4], const uint64_t gamma[4],
+                             void* d_z);
+int h2agg_permutation_product_dev(h2agg_ctx* ctx, const void* const* d_values, const void* const* d_sigmas, size_t n_cols,
+                                  uint32_t k, const uint64_t omega[4], const uint64_t beta_delta_start[4],
+                                  const uint64_t delta[4], const uint64_t beta[4], const uint64_t gamma[4],
+                                  const void* d_last_z, void* d_z);
 /* a <- a sorted ascending by Fr::cmp (Montgomery in and out), in place: the sort inside the above, exposed. n <= 2^25. */
 int h2agg_sort_fr(h2agg_ctx* ctx, uint64_t* a /* n*4 */, size_t n);
 int h2agg_sort_fr_dev(h2agg_ctx* ctx, void* d_a, size_t n);

@@ -41,3 +41,50 @@ def check_lookup_constraints(inp, tab, a, s):
     assert a[0] == s[0]
     for i in range(1, len(a)):
         assert a[i] == s[i] or a[i] == a[i - 1], "row %d violates (a'-s')(a'-a'_prev) = 0" % i
+
+
+# ---- the row-wise steps around the sort (halo2_proofs plonk/lookup/prover.rs, plonk/permutation/prover.rs) -------------
+R = 0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001
+DELTA = pow(7, 1 << 28, R)
+
+
+def compress_expressions(exprs, cols, n, theta):
+    """lookup::Argument::commit_permuted's compress_expressions: every expression (nested tuples as in quotient_ref)
+    is evaluated on the Lagrange domain -- rotation r of row i reads row (i + r) mod n -- and folded acc*theta + e."""
+    import quotient_ref as qr
+
+    out = []
+    for i in range(n):
+        acc = 0
+        for e in exprs:
+            acc = (acc * theta + qr.eval_expr(e, lambda kind, col, rot: cols[(kind, col)][(i + rot) % n])) % R
+        out.append(acc)
+    return out
+
+
+def lookup_product(A, S, Ap, Sp, beta, gamma):
+    """lookup::Permuted::commit_product before blinding: z[0] = 1, z[i+1] = z[i] (A+b)(S+g) / ((A'+b)(S'+g)); n values."""
+    z = [1]
+    for i in range(len(A) - 1):
+        num = (A[i] + beta) * (S[i] + gamma) % R
+        den = (Ap[i] + beta) * (Sp[i] + gamma) % R
+        z.append(z[-1] * num % R * pow(den, -1, R) % R)
+    return z
+
+
+def permutation_product(values, sigmas, k, omega, beta, gamma, first_index, last_z=1):
+    """permutation::Argument::commit for ONE column set, before blinding: z[0] = last_z,
+    z[i+1] = z[i] prod_j (v_j[i] + beta delta^(first+j) omega^i + gamma) / (v_j[i] + beta sigma_j[i] + gamma)."""
+    n = 1 << k
+    z = [last_z % R]
+    w = 1
+    for i in range(n - 1):
+        num = den = 1
+        d = beta * pow(DELTA, first_index, R) % R
+        for v, s in zip(values, sigmas):
+            num = num * (v[i] + d * w + gamma) % R
+            den = den * (v[i] + beta * s[i] + gamma) % R
+            d = d * DELTA % R
+        z.append(z[-1] * num % R * pow(den, -1, R) % R)
+        w = w * omega % R
+    return z

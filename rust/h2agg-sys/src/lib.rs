@@ -28,7 +28,7 @@ extern "C" {
     pub fn h2agg_eval_polynomial(ctx: *mut h2agg_ctx, poly: *const u64, n: usize, point: *const u64, out: *mut u64) -> c_int;
     pub fn h2agg_kate_division(ctx: *mut h2agg_ctx, a: *const u64, n: usize, b: *const u64, q: *mut u64) -> c_int;
     pub fn h2agg_permute_expression_pair(ctx: *mut h2agg_ctx, input: *const u64, table: *const u64, usable_rows: usize, permuted_input: *mut u64, permuted_table: *mut u64) -> c_int;
-    pub fn h2agg_commit_round_resident(ctx: *mut h2agg_ctx, srs_id: u64, lagrange_cols: *const *const u64, n_cols: usize, k: u32, omega_inv: *const u64, n_inv: *const u64, out_affine: *mut u64, d_coeff_out: *const *mut c_void, ext_k: u32, zeta: *const u64, omega_ext: *const u64, d_ext_out: *const *mut c_void) -> c_int;
+    pub fn h2agg_commit_round_resident(ctx: *mut h2agg_ctx, srs_id: u64, lagrange_cols: *const *const u64, n_cols: usize, k: u32, omega_inv: *const u64, n_inv: *const u64, out_affine: *mut u64, d_lagrange_out: *const *mut c_void, d_coeff_out: *const *mut c_void, ext_k: u32, zeta: *const u64, omega_ext: *const u64, d_ext_out: *const *mut c_void) -> c_int;
 }
 
 struct Ctx(*mut h2agg_ctx);

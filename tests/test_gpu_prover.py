@@ -99,3 +99,93 @@ def test_resident_prover_matches_oracle_composition(ctx, which, k):
     pr.close()
     ctx.srs_release(sid_g)
     ctx.srs_release(sid_gl)
+
+
+def _satisfiable_columns(cs, which, k, seed):
+    """Lagrange columns whose lookups can be satisfied: range tables i mod 16, 0/1 selectors, small advice values."""
+    rng = random.Random(seed)
+    n = 1 << k
+    lag = {}
+    for i in range(cs.num_fixed):
+        lag[("fixed", i)] = [rng.randrange(R) for _ in range(n)]
+    for i in range(cs.num_advice):
+        lag[("advice", i)] = [rng.randrange(16) for _ in range(n)]
+    for i in range(cs.num_instance):
+        lag[("instance", i)] = [rng.randrange(R) for _ in range(n)]
+    for j in range(len(cs.permutation_columns)):
+        lag[("sigma", j)] = [rng.randrange(R) for _ in range(n)]
+    sel_tab = [(9, 10), (11, 12), (13, 14), (15, 16)] if which == "aggregation" else [(0, 2)]
+    for sel, tab in sel_tab:
+        lag[("fixed", sel)] = [rng.randrange(2) for _ in range(n)]
+        lag[("fixed", tab)] = [i % 16 for i in range(n)]
+    return lag
+
+
+@pytest.mark.parametrize("which,k", [("small", 5), ("aggregation", 6)])
+def test_lookup_and_product_rounds_from_resident_columns(ctx, which, k):
+    """Rounds 2 and 3 computed on the device from the resident advice / fixed / sigma columns: permuted lookup
+    columns and grand products (values, commitments, coefficient and extended forms) against the Python restatement."""
+    import lookup_ref as lr
+
+    cs = _small_cs() if which == "small" else plonk.aggregation_circuit_cs()
+    n = 1 << k
+    gl = ob.gen_bases(0x7100 + k, n)
+    sid = ctx.srs_register(gl)
+    pr = ResidentProver(ctx, cs, k, sid, sid)
+    d = domain_consts(k, pr.ext_k)
+    lag = _satisfiable_columns(cs, which, k, 9 + k)
+    first = [nm for nm in lag]
+    pr.commit_columns(first, [qu.pack(lag[nm]) for nm in first], keep_lagrange=True)
+    rng = random.Random(4)
+    theta, beta, gamma = [rng.randrange(R) for _ in range(3)]
+    blinds = {}
+
+    def blind(name, rows):
+        blinds[name] = [rng.randrange(R) for _ in range(rows)]
+        return qu.pack(blinds[name])
+
+    bf = cs.blinding_factors()
+    u = n - bf - 1
+    w = qr.omega(k)
+
+    def check(names, comms, want_cols):
+        for nm, c in zip(names, comms):
+            col = qu.pack(want_cols[nm])
+            assert np.array_equal(ctx.d2h(pr.lag[nm], 4 * n), col), nm
+            assert np.array_equal(c, ob.best_multiexp(col, gl)[:8]), nm
+            co = ob.ifft(col.copy(), d["omega_inv"], d["n_inv"], k)
+            assert np.array_equal(ctx.d2h(pr.coeff[nm], 4 * n), co), nm
+            assert np.array_equal(ctx.d2h(pr.ext[nm], 4 << pr.ext_k), ob.coeff_to_extended(co, k, pr.ext_k, d["zeta"], d["omega_ext"])), nm
+
+    # --- round 2
+    comms = pr.lookup_round(theta, blind)
+    want, names, comp = {}, [], {}
+    for i, (_, ins, tabs) in enumerate(cs.lookups):
+        A = lr.compress_expressions([e.to_tuple() for e in ins], lag, n, theta)
+        S = lr.compress_expressions([e.to_tuple() for e in tabs], lag, n, theta)
+        comp[i] = (A, S)
+        pa, ps = lr.permute_expression_pair(A[:u], S[:u])
+        want[("lookup_input", i)] = pa + blinds[("lookup_input", i)]
+        want[("lookup_table", i)] = ps + blinds[("lookup_table", i)]
+        names += [("lookup_input", i), ("lookup_table", i)]
+    check(names, comms, want)
+    # --- round 3
+    comms = pr.product_round(beta, gamma, blind)
+    names = []
+    chunk = cs.chunk_len()
+    last = 1
+    for s in range(cs.num_permutation_sets()):
+        cols = cs.permutation_columns[s * chunk:(s + 1) * chunk]
+        z = lr.permutation_product([lag[c] for c in cols], [lag[("sigma", s * chunk + j)] for j in range(len(cols))], k, w, beta,
+                                   gamma, s * chunk, last)
+        last = z[u]
+        want[("perm_z", s)] = z[: n - bf] + blinds[("perm_z", s)]
+        names.append(("perm_z", s))
+    for i in range(len(cs.lookups)):
+        z = lr.lookup_product(comp[i][0], comp[i][1], want[("lookup_input", i)], want[("lookup_table", i)], beta, gamma)
+        assert z[u] == 1
+        want[("lookup_z", i)] = z[: n - bf] + blinds[("lookup_z", i)]
+        names.append(("lookup_z", i))
+    check(names, comms, want)
+    pr.close()
+    ctx.srs_release(sid)

@@ -167,3 +167,52 @@ def test_permute_expression_pair_oracle_vs_python_pin():
     # hand-checked example: leftovers ascending go to repeated rows from the back
     a, s = lr.permute_expression_pair([2, 1, 2, 2, 1], [1, 2, 7, 3, 9])
     assert a == [1, 1, 2, 2, 2] and s == [1, 9, 2, 7, 3]
+
+
+def test_lookup_and_permutation_product_restatements_telescope():
+    """oracle/py/lookup_ref.py: with a valid permuted pair the lookup product returns to 1 at the last usable row, and
+    with sigma columns that encode a real copy-constraint cycle the chained permutation products do too -- the two
+    facts the reference's verifier relies on (systems/halo2/lookup.rs:58-119, permutation.rs:54-136)."""
+    import random
+
+    import lookup_ref as lr
+    import quotient_ref as qr
+
+    R = lr.R
+    rng = random.Random(12)
+    k, bf = 6, 5
+    n = 1 << k
+    u = n - bf - 1
+    table = [i % 16 for i in range(n)]
+    inp = [rng.randrange(16) for _ in range(n)]
+    pa, ps = lr.permute_expression_pair(inp[:u], table[:u])
+    pa += [rng.randrange(R) for _ in range(bf + 1)]
+    ps += [rng.randrange(R) for _ in range(bf + 1)]
+    beta, gamma = rng.randrange(R), rng.randrange(R)
+    z = lr.lookup_product(inp, table, pa, ps, beta, gamma)
+    assert z[0] == 1 and z[u] == 1 and any(v != 1 for v in z[1:u])
+    # permutation: 4 columns in 2 sets of 2 (chunk_len 2); a 3-cycle of equal cells across columns, rows < u
+    w = qr.omega(k)
+    m, chunk = 4, 2
+    values = [[rng.randrange(R) for _ in range(n)] for _ in range(m)]
+    ident = [[pow(lr.DELTA, j, R) * pow(w, i, R) % R for i in range(n)] for j in range(m)]
+    sig = [list(c) for c in ident]
+    cells = [(0, 3), (2, 17), (3, 40)]
+    v = rng.randrange(R)
+    for j, i in cells:
+        values[j][i] = v
+    for (j, i), (j2, i2) in zip(cells, cells[1:] + cells[:1]):
+        sig[j][i] = ident[j2][i2]
+    last = 1
+    zs = []
+    for s in range(2):
+        zz = lr.permutation_product(values[s * chunk:(s + 1) * chunk], sig[s * chunk:(s + 1) * chunk], k, w, beta, gamma, s * chunk, last)
+        last = zz[u]
+        zs.append(zz)
+    assert zs[0][0] == 1 and zs[1][0] == zs[0][u] and zs[0][u] != 1 and zs[1][u] == 1
+    # a broken copy constraint does not telescope
+    values[0][3] = (v + 1) % R
+    last = 1
+    for s in range(2):
+        last = lr.permutation_product(values[s * chunk:(s + 1) * chunk], sig[s * chunk:(s + 1) * chunk], k, w, beta, gamma, s * chunk, last)[u]
+    assert last != 1
