@@ -262,8 +262,22 @@ __global__ void __launch_bounds__(MSM_THREADS) msm_accumulate(const uint8_t* __r
       if (bbeg < start) acc.store(head_part + (size_t)t * 128);
       else acc.store(bucket_sums + (size_t)b * 128);
       acc = G1Xyzz::identity();
+      // next non-empty bucket = the one that owns slot k.  Usually the neighbour; but a column of small values with
+      // a few full-width ones (every real halo2 column: 17-bit cells + random blinding rows) leaves gaps of 10^5 empty
+      // buckets, so after a few linear steps fall back to the binary search (offsets[b+1] <= k < offsets[nb]).
       b++;
-      while ((__ldg(offsets + b + 1) >> sh) <= k) b++;  // skip empty buckets; k < total so this terminates
+      for (uint32_t tries = 0; (__ldg(offsets + b + 1) >> sh) <= k; ) {
+        b++;
+        if (++tries == 4) {
+          uint32_t lo2 = b, hi2 = g.nb;  // offsets[lo2] <= k < offsets[hi2]
+          while (hi2 - lo2 > 1) {
+            uint32_t mid = (lo2 + hi2) >> 1;
+            if ((__ldg(offsets + mid) >> sh) <= k) lo2 = mid; else hi2 = mid;
+          }
+          b = lo2;
+          break;
+        }
+      }
       bbeg = __ldg(offsets + b) >> sh;
       bend = __ldg(offsets + b + 1) >> sh;
     }

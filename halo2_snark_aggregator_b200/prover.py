@@ -40,6 +40,23 @@ class ResidentProver:
         self.n_pieces = self.dom.quotient_poly_degree
         self._scratch = {}
 
+    # -- optional stage trace (bench / profiling): set self.trace = {} to collect synchronised stage times in ms
+    trace = None
+    trace_kernels = False
+
+    def _mark(self, label):
+        if self.trace is None:
+            return
+        import time
+
+        self.ctx.synchronize()
+        now = time.perf_counter()
+        if getattr(self, "_t_last", None) is not None:
+            self.trace[label] = self.trace.get(label, 0.0) + (now - self._t_last) * 1e3
+            if self.trace_kernels:  # per-kernel-class CUDA-event sums of the stage (needs ctx.kernel_timing(True))
+                self.trace[label + ".kernel_class_ms"] = {kk: round(vv[0], 3) for kk, vv in self.ctx.kernel_times().items() if vv[1]}
+        self._t_last = time.perf_counter()
+
     # -- memory ------------------------------------------------------------------------------------
     def _alloc(self, nbytes):
         p = self.ctx.dev_alloc(nbytes)
@@ -111,18 +128,24 @@ class ResidentProver:
         u, tail = self.usable_rows(), self.cs.blinding_factors() + 1
         th = fr_to_limbs(theta)
         out_names = []
+        self._mark("-")
         for i, (_, ins, tabs) in enumerate(self.cs.lookups):
             for side, exprs in (("input", ins), ("table", tabs)):
                 prog = plonk.ExpressionList(exprs, index)
                 self.ctx.compress_expressions_dev(prog.words, prog.consts, cols, self.k, th,
                                                   self.lagrange_slot(("lookup_%s_compressed" % side, i)))
+            self._mark("lookup.compress_expressions")
             pa, ps = self.lagrange_slot(("lookup_input", i)), self.lagrange_slot(("lookup_table", i))
             self.ctx.permute_expression_pair_dev(self.lag[("lookup_input_compressed", i)], self.lag[("lookup_table_compressed", i)],
                                                  u, pa, ps)
+            self._mark("lookup.permute_expression_pair")
             for nm, p in ((("lookup_input", i), pa), (("lookup_table", i), ps)):
                 self.ctx.h2d(p + 32 * u, np.ascontiguousarray(blind(nm, tail)))
                 out_names.append(nm)
-        return self._commit_resident(out_names)
+            self._mark("lookup.blinding_rows")
+        out = self._commit_resident(out_names)
+        self._mark("lookup.commit_round_dev")
+        return out
 
     # -- stage 3: grand products (permutation::commit, lookup commit_product) ------------------------------
     def product_round(self, beta, gamma, blind):
@@ -133,6 +156,7 @@ class ResidentProver:
         chunk = self.cs.chunk_len()
         pcs = self.cs.permutation_columns
         last = None
+        self._mark("-")
         for s in range(self.cs.num_permutation_sets()):
             cols = pcs[s * chunk:(s + 1) * chunk]
             z = self.lagrange_slot(("perm_z", s))
@@ -142,13 +166,17 @@ class ResidentProver:
             self.ctx.h2d(z + 32 * (self.n - bf), np.ascontiguousarray(blind(("perm_z", s), bf)))
             last = z + 32 * u
             out_names.append(("perm_z", s))
+        self._mark("products.permutation")
         for i in range(len(self.cs.lookups)):
             z = self.lagrange_slot(("lookup_z", i))
             self.ctx.lookup_product_dev(self.lag[("lookup_input_compressed", i)], self.lag[("lookup_table_compressed", i)],
                                         self.lag[("lookup_input", i)], self.lag[("lookup_table", i)], self.n, b, g, z)
             self.ctx.h2d(z + 32 * (self.n - bf), np.ascontiguousarray(blind(("lookup_z", i), bf)))
             out_names.append(("lookup_z", i))
-        return self._commit_resident(out_names)
+        self._mark("products.lookup")
+        out = self._commit_resident(out_names)
+        self._mark("products.commit_round_dev")
+        return out
 
     def commit_coeff_columns(self, names, coeff_cols):
         """Polynomials the prover creates in COEFFICIENT form (the vanishing argument's random polynomial):

@@ -467,3 +467,54 @@ def test_commit_round_fused(ctx):
         assert np.array_equal(pts[1], affine_of(ob.best_multiexp(cols[1], b)))
     finally:
         ctx.srs_release(sid)
+
+
+@pytest.mark.parametrize("kind,n_wide", [(3, 6), (1, 6), (3, 1), (1, 40)])
+def test_msm_small_values_with_blinding_rows(ctx, kind, n_wide):
+    """The shape of every real halo2 column: small cells plus a few full-width random blinding rows at the end, sorted or
+    not.  The wide scalars occupy isolated buckets far above the dense ones (gaps of ~10^5 empty buckets that the bucket
+    walk of msm_accumulate has to jump, not step through)."""
+    import time
+
+    n = 1 << 16
+    bases = ob.gen_bases(0x91, n)
+    s = ob.gen_scalars(0x92 + kind, kind, n)
+    s[4 * (n - n_wide):] = ob.gen_scalars(0x93, 0, n_wide)
+    sid = ctx.srs_register(bases)
+    try:
+        for sort_first in (False, True):
+            col = s.copy()
+            if sort_first:  # like a permuted lookup column: sorted small values, blinding rows stay at the end
+                col[: 4 * (n - n_wide)] = ctx.sort_fr(np.ascontiguousarray(s[: 4 * (n - n_wide)]))
+            want = ob.best_multiexp(col, bases)
+            assert np.array_equal(ctx.msm_g1(col, srs_id=sid), want)      # table mode
+            assert np.array_equal(ctx.msm_g1(col, bases), want)            # plain mode
+    finally:
+        ctx.srs_release(sid)
+
+
+def test_msm_blinding_rows_do_not_slow_the_bucket_walk(ctx):
+    """Full size: a 17-bit column with 6 full-width rows must cost about what the plain 17-bit column costs
+    (before the bucket walk jumped empty ranges it was ~20x slower)."""
+    n = 1 << 22
+    d_b, d_s, d_w, d_o = ctx.dev_alloc(n * 64), ctx.dev_alloc(n * 32), ctx.dev_alloc(6 * 32), ctx.dev_alloc(160)
+    try:
+        ctx.synth_bases_dev(0x53525300 + 22, 0, n, d_b)
+        sid = ctx.srs_register_dev(d_b, n)
+        ctx.synth_scalars_dev(0x94, 3, 0, n, d_s)
+        times = []
+        for tail in (False, True):
+            if tail:
+                ctx.synth_scalars_dev(0x95, 0, 0, 6, d_s + 32 * (n - 6))
+            ctx.msm_g1_dev(d_s, n, d_o, srs_id=sid)
+            ctx.synchronize()
+            ctx.kernel_timing(True)
+            for _ in range(3):
+                ctx.msm_g1_dev(d_s, n, d_o, srs_id=sid)
+            times.append(ctx.kernel_times()["msm_total"][0] / 3)
+            ctx.kernel_timing(False)
+        assert times[1] < 2.0 * times[0] + 1.0, times
+        ctx.srs_release(sid)
+    finally:
+        for p in (d_b, d_s, d_w, d_o):
+            ctx.dev_free(p)
