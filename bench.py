@@ -425,7 +425,11 @@ def main():
                 ctx.h2d(d_l, small_column(special[nm]))
             else:
                 ctx.synth_scalars_dev(SEED_SCALARS + 5000 + j, 0, 0, n, d_l)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
         pr._commit_resident(pk_names)   # 23 x (MSM + iNTT + coset NTT): the fixed / sigma commitments of the vk, too
+        torch.cuda.synchronize()
+        keygen_s = time.perf_counter() - t0
         for j, nm in enumerate([("l0", 0), ("l_last", 0), ("l_active_row", 0)]):
             dc, de = pr.slot(nm)
             ctx.synth_scalars_dev(SEED_SCALARS + 6000 + j, 0, 0, ext_n, de)
@@ -488,7 +492,8 @@ def main():
         barrier()
         e2e_res_s = (time.perf_counter() - t0) / args.e2e_steps
         launches_r = (ctx.launch_count() - launches_r0) // args.e2e_steps
-        torch.cuda.synchronize()
+        kt = ctx.kernel_times()
+        ctx.kernel_timing(False)
         step_resident(stage_ms)   # one more, untimed for the headline, with a synchronize after every stage
         pr.trace, pr.trace_kernels = {}, True
         ctx.kernel_timing(True)
@@ -496,8 +501,6 @@ def main():
         ctx.kernel_timing(False)
         stage_ms["rounds_2_3_detail"] = {kk: vv for kk, vv in pr.trace.items() if kk != "-"}
         pr.trace = None
-        kt = ctx.kernel_times()
-        ctx.kernel_timing(False)
         h2d_r = 7 * n * 32 + 23 * 6 * 32
         d2h_r = sum(int(np.asarray(o).nbytes) for o in res_out)
         qms, qn = kt["evaluate_h"]
@@ -506,8 +509,9 @@ def main():
               "note": "aggregation circuit's quotient (1 gate, 2 permutation sets, 7 lookups) over 55 resident extended columns, fused with the division by X^n - 1; algorithmic bytes: every column read once + h written"}
         e2e_res = {"value": e2e_res_s, "unit": "s", "h2d_bytes_per_step": h2d_r, "d2h_bytes_per_step": d2h_r,
                    "gpu_launches_per_step": int(launches_r), "stage_ms_synchronised": stage_ms,
+                   "keygen_transforms_s": keygen_s,
                    "work": "witness in, proof elements out: the schedule's 38 MSM + 29 iNTT + 29 coset-NTT + 1 iNTT(4n) PLUS everything create_proof does between them -- 14 compress_expressions, 7 permute_expression_pair (sorts), 2 permutation + 7 lookup grand products, evaluate_h over 55 extended columns, 70 eval_polynomial, the 71-polynomial GWC fold, 4 kate_division",
-                   "note": "ResidentProver (prover.py) over the C ABI: instance + 5 advice columns and the random polynomial are uploaded from pinned host memory every step (7 x 2^k x 32 B); commitments (38 x 64 B) and evaluations (70 x 32 B) are read back; rounds 2 and 3 are computed on the device from the resident columns; proving-key polynomials (fixed, sigma, l_*) stay resident across proofs as in a prover that caches its pk; challenges and blinding values are inputs"}
+                   "note": "ResidentProver (prover.py) over the C ABI: instance + 5 advice columns and the random polynomial are uploaded from pinned host memory every step (7 x 2^k x 32 B); commitments (38 x 64 B) and evaluations (70 x 32 B) are read back; rounds 2 and 3 are computed on the device from the resident columns; proving-key polynomials (fixed, sigma, l_*) stay resident across proofs as in a prover that caches its pk (keygen_transforms_s: the 23 commit + lagrange_to_coeff + coeff_to_extended of keygen_vk/pk, once, first use of the lanes included); challenges and blinding values are inputs"}
         pr.close()
         del h_round0, h_random, pr
 
@@ -752,10 +756,11 @@ def main():
                          "note": "MSM is bound by the INT32 IMAD pipe, not HBM (SURVEY.md 8d); HBM fraction reported as the metric demands"},
             "roofline_multiplier": None if not acc_alone_ms else (lambda clk: {
                 "kernel": "msm_accumulate", "bound": "int32 multiplier: IMAD.WIDE.U32 issues once per 4 clk per SM sub-partition (32 lanes/clk/SM; profiles/r01_pipe_rates_b200.jsonl, ncu fmaheavy pipe)",
-                "achieved": 10.0 * n * nwin / (acc_alone_ms * 1e-3) / 1e9, "peak": 148 * 32 * clk * 1e6 / 136 / 1e9, "unit": "G field-mul/s",
-                "frac": (10.0 * n * nwin / (acc_alone_ms * 1e-3)) / (148 * 32 * clk * 1e6 / 136),
+                "achieved": 1288.0 * n * nwin / (acc_alone_ms * 1e-3) / 1e12, "peak": 148 * 32 * clk * 1e6 / 1e12, "unit": "T multiplier-instr/s",
+                "frac": (1288.0 * n * nwin / (acc_alone_ms * 1e-3)) / (148 * 32 * clk * 1e6),
                 "launch_ms_alone": acc_alone_ms, "mixed_additions_per_launch": n * nwin,
-                "note": "one launch on a uniform 2^%d column, timed alone; a mixed addition is 8M+2S = 10 Montgomery products of 136 multiplier instructions each" % k})(
+                "mixed_additions_per_s": n * nwin / (acc_alone_ms * 1e-3),
+                "note": "one launch on a uniform 2^%d column, timed alone; a mixed addition (8M+2S) is 8 single Montgomery products of 136 multiplier instructions + 1 dual product (a*b - c*d, one reduction) of 208 = 1288 multiplier instructions" % k})(
                     float((clock_info or {}).get("sm_mhz") or 1965.0)),
             "cpu_baseline": cpu,
             "witness": witness,

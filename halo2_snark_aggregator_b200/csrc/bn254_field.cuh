@@ -262,6 +262,29 @@ __device__ __forceinline__ Fp<T> operator*(const Fp<T>& a, const Fp<T>& b) {
 }
 #endif
 
+// a*b + c*d with ONE Montgomery reduction (generated dual-product schedule: 200 wide MADs + 8 instead of 2 x 136).
+// Inputs < p < 2^254 keep every row below 2^288, the result below 1.5 p.
+template <class T>
+__device__ __forceinline__ Fp<T> fp_mul_add2(const Fp<T>& a, const Fp<T>& b, const Fp<T>& c, const Fp<T>& d) {
+#ifdef H2AGG_PORTABLE_MUL
+  return a * b + c * d;
+#else
+  Fp<T> r;
+  if constexpr (T::IS_FR) {
+    H2AGG_MONT_MUL_ADD2_FR(r.v, a.v, b.v, c.v, d.v);
+  } else {
+    H2AGG_MONT_MUL_ADD2_FQ(r.v, a.v, b.v, c.v, d.v);
+  }
+  fp_reduce_once<T>(r.v);
+  return r;
+#endif
+}
+// a*b - c*d
+template <class T>
+__device__ __forceinline__ Fp<T> fp_mul_sub2(const Fp<T>& a, const Fp<T>& b, const Fp<T>& c, const Fp<T>& d) {
+  return fp_mul_add2(a, b, fp_neg(c), d);
+}
+
 template <class T>
 __device__ __forceinline__ Fp<T> fp_sqr(const Fp<T>& a) {
   return a * a;

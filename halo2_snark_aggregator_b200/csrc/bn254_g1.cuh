@@ -3,7 +3,8 @@
 // Affine layout = halo2curves `G1Affine {x, y}` (64 B, Montgomery Fq, identity = (0,0));
 // Jacobian layout = halo2curves `G1 {x, y, z}` (96 B, identity z = 0)  -- SURVEY.md App. A.
 // Buckets are kept in XYZZ coordinates (x = X/ZZ, y = Y/ZZZ, ZZ^3 = ZZZ^2, identity ZZ = 0):
-// mixed add 8M+2S, full add 12M+2S, double 6M+4S(+small), no inversions until the very end.
+// mixed add 8M+2S, full add 12M+2S, double 6M+4S(+small), no inversions until the very end; every Y3 = a*b - c*d
+// is ONE dual-product Montgomery reduction (fp_mul_sub2).
 // Formulas: EFD "shortw/xyzz" madd-2008-s, add-2008-s, dbl-2008-s-1, mdbl-2008-s-1 (a = 0).
 #pragma once
 #include "bn254_field.cuh"
@@ -59,7 +60,7 @@ __device__ __forceinline__ G1Xyzz xyzz_mdbl(const G1Affine& a) {
   Fq xx = fp_sqr(a.x);
   Fq m = fp_dbl(xx) + xx;
   r.x = fp_sqr(m) - fp_dbl(s);
-  r.y = m * (s - r.x) - w * a.y;
+  r.y = fp_mul_sub2(m, s - r.x, w, a.y);
   r.zz = v;
   r.zzz = w;
   return r;
@@ -76,7 +77,7 @@ __device__ __forceinline__ G1Xyzz xyzz_dbl(const G1Xyzz& p) {
   Fq xx = fp_sqr(p.x);
   Fq m = fp_dbl(xx) + xx;
   r.x = fp_sqr(m) - fp_dbl(s);
-  r.y = m * (s - r.x) - w * p.y;
+  r.y = fp_mul_sub2(m, s - r.x, w, p.y);
   r.zz = v * p.zz;
   r.zzz = w * p.zzz;
   return r;
@@ -103,7 +104,7 @@ __device__ __forceinline__ void xyzz_madd(G1Xyzz& acc, const G1Affine& q) {
   Fq ppp = p * pp;
   Fq qq = acc.x * pp;
   Fq x3 = fp_sqr(r) - ppp - fp_dbl(qq);
-  acc.y = r * (qq - x3) - acc.y * ppp;
+  acc.y = fp_mul_sub2(r, qq - x3, acc.y, ppp);  // one reduction for both products
   acc.x = x3;
   acc.zz = acc.zz * pp;
   acc.zzz = acc.zzz * ppp;
@@ -128,7 +129,7 @@ __device__ __forceinline__ void xyzz_add(G1Xyzz& acc, const G1Xyzz& b) {
   Fq ppp = p * pp;
   Fq qq = u1 * pp;
   Fq x3 = fp_sqr(r) - ppp - fp_dbl(qq);
-  acc.y = r * (qq - x3) - s1 * ppp;
+  acc.y = fp_mul_sub2(r, qq - x3, s1, ppp);
   acc.x = x3;
   acc.zz = acc.zz * b.zz * pp;
   acc.zzz = acc.zzz * b.zzz * ppp;

@@ -59,8 +59,10 @@ class Gen:
         self.cmad(even, [self.imm(self.p[j]) for j in (0, 2, 4, 6)], mi)
         self.emit("addc.u32 %s, %s, 0;" % (odd[7], odd[7]))
 
-    def row(self, even, odd, A, bi, first):
-        """One CIOS row; returns the (even, odd) register-name lists after the row."""
+    def row(self, even, odd, A, bi, first, C=None, di=None):
+        """One CIOS row; returns the (even, odd) register-name lists after the row.
+        With (C, di) the row also accumulates C * di before the reduction step (dual product a*b + c*d: the top
+        pair holds A7*b + C7*d + m*p7 + carries < 3 * 2^62, so the odd chain still never carries out)."""
         if first:
             for k in range(4):
                 odd[2 * k], odd[2 * k + 1] = self.new(), self.new()
@@ -84,6 +86,10 @@ class Gen:
             odd[:] = nodd
             self.cmad(even, [A[j] for j in (0, 2, 4, 6)], bi)
             self.emit("addc.u32 %s, %s, 0;" % (odd[7], odd[7]))
+        if C is not None:
+            self.cmad(odd, [C[j] for j in (1, 3, 5, 7)], di)
+            self.cmad(even, [C[j] for j in (0, 2, 4, 6)], di)
+            self.emit("addc.u32 %s, %s, 0;" % (odd[7], odd[7]))
         self.redc(even, odd)
 
     def mont_mul(self):
@@ -103,13 +109,36 @@ class Gen:
         return self.lines
 
 
-def run_ptx(lines, a, b):
+    def mont_mul_add2(self):
+        """r = (a*b + c*d) * 2^-256 mod p, r in [0, 2p): one reduction for two products (200 wide MADs + 8 mul.lo
+        instead of 2 x 136).  Operands %8..%15 a, %16..%23 b, %24..%31 c, %32..%39 d."""
+        A = ["%%%d" % (8 + i) for i in range(8)]
+        B = ["%%%d" % (16 + i) for i in range(8)]
+        C = ["%%%d" % (24 + i) for i in range(8)]
+        D = ["%%%d" % (32 + i) for i in range(8)]
+        even, odd = [None] * 8, [None] * 8
+        for i in range(0, 8, 2):
+            self.row(even, odd, A, B[i], i == 0, C, D[i])
+            self.row(odd, even, A, B[i + 1], False, C, D[i + 1])
+        self.emit("add.cc.u32 %s, %s, %s;" % (even[0], even[0], odd[1]))
+        for j in range(1, 7):
+            self.emit("addc.cc.u32 %s, %s, %s;" % (even[j], even[j], odd[j + 1]))
+        self.emit("addc.u32 %s, %s, 0;" % (even[7], even[7]))
+        for j in range(8):
+            self.emit("mov.u32 %%%d, %s;" % (j, even[j]))
+        return self.lines
+
+
+def run_ptx(lines, a, b, c=0, d=0):
     """Minimal interpreter for exactly the instruction forms emitted above."""
     regs = {}
     for i in range(8):
         regs["%%%d" % (8 + i)] = (a >> (32 * i)) & M32
         regs["%%%d" % (16 + i)] = (b >> (32 * i)) & M32
+        regs["%%%d" % (24 + i)] = (c >> (32 * i)) & M32
+        regs["%%%d" % (32 + i)] = (d >> (32 * i)) & M32
     cc = 0
+    pending = 0  # a carry of 1 written by a .cc instruction that no instruction has consumed yet
 
     def val(x):
         x = x.strip()
@@ -123,6 +152,12 @@ def run_ptx(lines, a, b):
         m = re.match(r"([a-z0-9.]+)\s+(.*);", ln)
         op, args = m.group(1), [s.strip() for s in m.group(2).split(",")]
         d = args[0]
+        consumes = op.startswith("madc") or op.startswith("addc")
+        if consumes:
+            pending = 0
+        elif ".cc" in op:
+            # a fresh chain starts here: a carry of 1 nobody consumed would be lost -- the schedule's bounds forbid that
+            assert pending == 0, "carry dropped before: " + ln
         if op == "mov.u32":
             regs[d] = val(args[1])
         elif op == "mul.lo.u32":
@@ -137,16 +172,33 @@ def run_ptx(lines, a, b):
             regs[d] = s & M32
             if ".cc." in op:
                 cc = s >> 32
+                pending = cc
         elif op.startswith("add"):
             base = op.split(".")[0]
             s = val(args[1]) + val(args[2]) + (cc if base == "addc" else 0)
             regs[d] = s & M32
             if ".cc." in op:
                 cc = s >> 32
+                pending = cc
         else:
             raise ValueError(op)
         assert cc in (0, 1)
+    assert pending == 0, "carry out of the last chain"
     return sum(regs["%%%d" % i] << (32 * i) for i in range(8))
+
+
+def selfcheck_add2(P, lines, rounds=400):
+    rinv = pow(1 << 256, -1, P)
+    rng = random.Random(0xADD2 ^ (P & 0xFFFF))
+    top = (1 << 254) - 1  # also operands above p (the schedule only needs < 2^254)
+    cases = [(0, 0, 0, 0), (P - 1, P - 1, P - 1, P - 1), (P - 1, P - 1, 0, 0), (0, 0, P - 1, P - 1), (1, 1, P - 1, 1),
+             (top, top, top, top), (P - 1, 1 << 253, P - 1, (1 << 253) + 12345)]
+    cases += [tuple(rng.randrange(P) for _ in range(4)) for _ in range(rounds)]
+    cases += [tuple(rng.choice((P - 1, P - 2, top, (1 << 224) - 1, 0xFFFFFFFF << 192 | 0xFFFFFFFF)) for _ in range(4)) for _ in range(100)]
+    for a, b, c, d in cases:
+        r = run_ptx(lines, a, b, c, d)
+        assert r < 2 * P, "bound violated"
+        assert r % P == ((a * b + c * d) * rinv) % P, (hex(a), hex(b), hex(c), hex(d), hex(r))
 
 
 def selfcheck(P, lines, rounds=400):
@@ -158,6 +210,22 @@ def selfcheck(P, lines, rounds=400):
         r = run_ptx(lines, a, b)
         assert r < 2 * P, "row bound violated"
         assert r % P == (a * b * rinv) % P, (hex(a), hex(b), hex(r))
+
+
+def c_body_add2(name, lines, ntemps):
+    out = []
+    out.append("// GENERATED by tools/gen_mont_ptx.py -- do not edit. %s: r = (a*b + c*d)*2^-256 mod p, r in [0,2p)" % name)
+    out.append("#define H2AGG_MONT_MUL_ADD2_%s(r, a, b, c, d) \\" % name)
+    out.append('  asm("{\\n\\t.reg .u32 t<%d>;\\n\\t" \\' % ntemps)
+    for ln in lines:
+        out.append('      "%s\\n\\t" \\' % ln)
+    out.append('      "}" \\')
+    out.append('      : "=r"((r)[0]), "=r"((r)[1]), "=r"((r)[2]), "=r"((r)[3]), "=r"((r)[4]), "=r"((r)[5]), "=r"((r)[6]), "=r"((r)[7]) \\')
+    for nm, last in (("a", False), ("b", False), ("c", False), ("d", True)):
+        out.append('      %s "r"((%s)[0]), "r"((%s)[1]), "r"((%s)[2]), "r"((%s)[3]), "r"((%s)[4]), "r"((%s)[5]), "r"((%s)[6]), "r"((%s)[7])%s \\' % (
+            ":" if nm == "a" else " ", nm, nm, nm, nm, nm, nm, nm, nm, ")" if last else ","))
+    text = "\n".join(out)
+    return text[:-2] + "\n"  # drop the continuation after the closing parenthesis
 
 
 def c_body(name, lines, ntemps):
@@ -184,6 +252,11 @@ def main():
         selfcheck(P, lines)
         text += c_body(name, lines, g.ntemps) + "\n"
         print("%s: %d PTX instructions, %d temps, self-check ok" % (name, len(lines), g.ntemps))
+        g2 = Gen(P)
+        lines2 = g2.mont_mul_add2()
+        selfcheck_add2(P, lines2)
+        text += c_body_add2(name, lines2, g2.ntemps) + "\n"
+        print("%s add2: %d PTX instructions, %d temps, self-check ok" % (name, len(lines2), g2.ntemps))
     with open(dst, "w") as f:
         f.write(text)
     print("wrote", os.path.normpath(dst))

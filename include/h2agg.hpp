@@ -129,4 +129,33 @@ struct EvaluationDomain {
   }
 };
 
+// halo2_proofs::arithmetic::{eval_polynomial, kate_division} and plonk::lookup::prover::permute_expression_pair
+// (usable rows only; the caller appends its blinding rows) -- host-vector forms of the "next" rows.
+inline Fr eval_polynomial(const Context& c, const std::vector<Fr>& poly, const Fr& point) {
+  Fr out;
+  c.check(h2agg_eval_polynomial(c.raw(), reinterpret_cast<const uint64_t*>(poly.data()), poly.size(), point.l, out.l));
+  return out;
+}
+inline std::vector<Fr> kate_division(const Context& c, const std::vector<Fr>& a, const Fr& b) {
+  if (a.empty()) throw std::invalid_argument("kate_division: empty polynomial");
+  std::vector<Fr> q(a.size() - 1);
+  c.check(h2agg_kate_division(c.raw(), reinterpret_cast<const uint64_t*>(a.data()), a.size(), b.l,
+                              reinterpret_cast<uint64_t*>(q.data())));
+  return q;
+}
+// returns false where halo2 returns Error::ConstraintSystemFailure (an input value is not in the table)
+inline bool permute_expression_pair(const Context& c, const std::vector<Fr>& input, const std::vector<Fr>& table,
+                                    std::vector<Fr>& permuted_input, std::vector<Fr>& permuted_table) {
+  if (input.size() != table.size()) throw std::invalid_argument("permute_expression_pair: lengths differ");
+  permuted_input.resize(input.size());
+  permuted_table.resize(input.size());
+  int rc = h2agg_permute_expression_pair(c.raw(), reinterpret_cast<const uint64_t*>(input.data()),
+                                         reinterpret_cast<const uint64_t*>(table.data()), input.size(),
+                                         reinterpret_cast<uint64_t*>(permuted_input.data()),
+                                         reinterpret_cast<uint64_t*>(permuted_table.data()));
+  if (rc == 4) return false;
+  c.check(rc);
+  return true;
+}
+
 }  // namespace h2agg_host
