@@ -756,11 +756,11 @@ def main():
                          "note": "MSM is bound by the INT32 IMAD pipe, not HBM (SURVEY.md 8d); HBM fraction reported as the metric demands"},
             "roofline_multiplier": None if not acc_alone_ms else (lambda clk: {
                 "kernel": "msm_accumulate", "bound": "int32 multiplier: IMAD.WIDE.U32 issues once per 4 clk per SM sub-partition (32 lanes/clk/SM; profiles/r01_pipe_rates_b200.jsonl, ncu fmaheavy pipe)",
-                "achieved": 1288.0 * n * nwin / (acc_alone_ms * 1e-3) / 1e12, "peak": 148 * 32 * clk * 1e6 / 1e12, "unit": "T multiplier-instr/s",
-                "frac": (1288.0 * n * nwin / (acc_alone_ms * 1e-3)) / (148 * 32 * clk * 1e6),
+                "achieved": 1240.0 * n * nwin / (acc_alone_ms * 1e-3) / 1e12, "peak": 148 * 32 * clk * 1e6 / 1e12, "unit": "T multiplier-instr/s",
+                "frac": (1240.0 * n * nwin / (acc_alone_ms * 1e-3)) / (148 * 32 * clk * 1e6),
                 "launch_ms_alone": acc_alone_ms, "mixed_additions_per_launch": n * nwin,
                 "mixed_additions_per_s": n * nwin / (acc_alone_ms * 1e-3),
-                "note": "one launch on a uniform 2^%d column, timed alone; a mixed addition (8M+2S) is 8 single Montgomery products of 136 multiplier instructions + 1 dual product (a*b - c*d, one reduction) of 208 = 1288 multiplier instructions" % k})(
+                "note": "one launch on a uniform 2^%d column, timed alone; a mixed addition (8M+2S) is 6 Montgomery products of 136 multiplier instructions, 2 squarings of 108 and 1 dual product (a*b - c*d, one reduction) of 208 = 1240 multiplier instructions (was 10 x 136 = 1360 before the dedicated schedules)" % k})(
                     float((clock_info or {}).get("sm_mhz") or 1965.0)),
             "cpu_baseline": cpu,
             "witness": witness,

@@ -285,9 +285,22 @@ __device__ __forceinline__ Fp<T> fp_mul_sub2(const Fp<T>& a, const Fp<T>& b, con
   return fp_mul_add2(a, b, fp_neg(c), d);
 }
 
+// a^2 with the generated squaring schedule: 36 + 72 multiplier instructions instead of 136 (a must be < 2^254,
+// which every fully reduced element is)
 template <class T>
 __device__ __forceinline__ Fp<T> fp_sqr(const Fp<T>& a) {
+#ifdef H2AGG_PORTABLE_MUL
   return a * a;
+#else
+  Fp<T> r;
+  if constexpr (T::IS_FR) {
+    H2AGG_MONT_SQR_FR(r.v, a.v);
+  } else {
+    H2AGG_MONT_SQR_FQ(r.v, a.v);
+  }
+  fp_reduce_once<T>(r.v);
+  return r;
+#endif
 }
 
 // Montgomery -> canonical integer (still 8 x u32 LE)

@@ -47,10 +47,18 @@ class Gen:
 
     # acc[0..7] (+)= x[0,2,4,6] * y with one carry chain through the four aligned pairs
     def cmad(self, acc, xs, y):
+        """xs may start with None entries (limbs known to be zero): their products are skipped and the carry chain
+        starts at the first present limb.  Returns False if nothing was emitted."""
+        started = False
         for k in range(4):
-            lo = "mad.lo.cc.u32" if k == 0 else "madc.lo.cc.u32"
+            if xs[k] is None:
+                assert not started, "zero limbs must be leading"
+                continue
+            lo = "madc.lo.cc.u32" if started else "mad.lo.cc.u32"
+            started = True
             self.emit("%s %s, %s, %s, %s;" % (lo, acc[2 * k], y, xs[k], acc[2 * k]))
             self.emit("madc.hi.cc.u32 %s, %s, %s, %s;" % (acc[2 * k + 1], y, xs[k], acc[2 * k + 1]))
+        return started
 
     def redc(self, even, odd):
         mi = self.new()
@@ -78,14 +86,19 @@ class Gen:
             nodd = [None] * 8
             for k in range(3):  # shift the odd array down two limbs while accumulating
                 nodd[2 * k], nodd[2 * k + 1] = self.new(), self.new()
-                self.emit("madc.lo.cc.u32 %s, %s, %s, %s;" % (nodd[2 * k], A[2 * k + 1], bi, odd[2 * k + 2]))
-                self.emit("madc.hi.cc.u32 %s, %s, %s, %s;" % (nodd[2 * k + 1], A[2 * k + 1], bi, odd[2 * k + 3]))
+                if A[2 * k + 1] is None:  # zero limb (squaring rows): the shift still carries
+                    self.emit("addc.cc.u32 %s, %s, 0;" % (nodd[2 * k], odd[2 * k + 2]))
+                    self.emit("addc.cc.u32 %s, %s, 0;" % (nodd[2 * k + 1], odd[2 * k + 3]))
+                else:
+                    self.emit("madc.lo.cc.u32 %s, %s, %s, %s;" % (nodd[2 * k], A[2 * k + 1], bi, odd[2 * k + 2]))
+                    self.emit("madc.hi.cc.u32 %s, %s, %s, %s;" % (nodd[2 * k + 1], A[2 * k + 1], bi, odd[2 * k + 3]))
             nodd[6], nodd[7] = self.new(), self.new()
+            assert A[7] is not None
             self.emit("madc.lo.cc.u32 %s, %s, %s, 0;" % (nodd[6], A[7], bi))
             self.emit("madc.hi.u32 %s, %s, %s, 0;" % (nodd[7], A[7], bi))
             odd[:] = nodd
-            self.cmad(even, [A[j] for j in (0, 2, 4, 6)], bi)
-            self.emit("addc.u32 %s, %s, 0;" % (odd[7], odd[7]))
+            if self.cmad(even, [A[j] for j in (0, 2, 4, 6)], bi):
+                self.emit("addc.u32 %s, %s, 0;" % (odd[7], odd[7]))
         if C is not None:
             self.cmad(odd, [C[j] for j in (1, 3, 5, 7)], di)
             self.cmad(even, [C[j] for j in (0, 2, 4, 6)], di)
@@ -108,6 +121,39 @@ class Gen:
             self.emit("mov.u32 %%%d, %s;" % (j, even[j]))
         return self.lines
 
+
+    def mont_sqr(self):
+        """r = a*a * 2^-256 mod p, r in [0, 2p), with 36 + 72 multiplier instructions instead of 136:
+        a^2 = sum_i a_i 2^(32 i) * V_i,  V_i = a_i 2^(32 i) + 2 * sum_{j>i} a_j 2^(32 j), i.e. CIOS row i multiplies by
+        a vector with i leading zero limbs (products skipped); the limbs of V_i above i are those of 2a, the one at
+        i + 1 with its lowest bit (the top bit of a_i, which belongs to 2 a_i) cleared.  a < 2^254, so 2a has 8 limbs."""
+        A = ["%%%d" % (8 + i) for i in range(8)]
+        a2 = [self.new() for _ in range(8)]
+        self.emit("add.cc.u32 %s, %s, %s;" % (a2[0], A[0], A[0]))
+        for j in range(1, 7):
+            self.emit("addc.cc.u32 %s, %s, %s;" % (a2[j], A[j], A[j]))
+        self.emit("addc.u32 %s, %s, %s;" % (a2[7], A[7], A[7]))
+        even, odd = [None] * 8, [None] * 8
+        for i in range(8):
+            V = [None] * 8
+            V[i] = A[i]
+            if i + 1 < 8:
+                m = self.new()
+                self.emit("and.b32 %s, %s, 0xfffffffe;" % (m, a2[i + 1]))
+                V[i + 1] = m
+            for j in range(i + 2, 8):
+                V[j] = a2[j]
+            if i % 2 == 0:
+                self.row(even, odd, V, A[i], i == 0)
+            else:
+                self.row(odd, even, V, A[i], False)
+        self.emit("add.cc.u32 %s, %s, %s;" % (even[0], even[0], odd[1]))
+        for j in range(1, 7):
+            self.emit("addc.cc.u32 %s, %s, %s;" % (even[j], even[j], odd[j + 1]))
+        self.emit("addc.u32 %s, %s, 0;" % (even[7], even[7]))
+        for j in range(8):
+            self.emit("mov.u32 %%%d, %s;" % (j, even[j]))
+        return self.lines
 
     def mont_mul_add2(self):
         """r = (a*b + c*d) * 2^-256 mod p, r in [0, 2p): one reduction for two products (200 wide MADs + 8 mul.lo
@@ -155,11 +201,13 @@ def run_ptx(lines, a, b, c=0, d=0):
         consumes = op.startswith("madc") or op.startswith("addc")
         if consumes:
             pending = 0
-        elif ".cc" in op:
+        elif ".cc" in op or op == "and.b32":
             # a fresh chain starts here: a carry of 1 nobody consumed would be lost -- the schedule's bounds forbid that
             assert pending == 0, "carry dropped before: " + ln
         if op == "mov.u32":
             regs[d] = val(args[1])
+        elif op == "and.b32":
+            regs[d] = val(args[1]) & val(args[2])
         elif op == "mul.lo.u32":
             regs[d] = (val(args[1]) * val(args[2])) & M32
         elif op == "mul.hi.u32":
@@ -201,6 +249,20 @@ def selfcheck_add2(P, lines, rounds=400):
         assert r % P == ((a * b + c * d) * rinv) % P, (hex(a), hex(b), hex(c), hex(d), hex(r))
 
 
+def selfcheck_sqr(P, lines, rounds=600):
+    rinv = pow(1 << 256, -1, P)
+    rng = random.Random(0x5152 ^ (P & 0xFFFF))
+    top = (1 << 254) - 1
+    cases = [0, 1, 2, P - 1, P - 2, top, (1 << 253), (1 << 253) - 1, 0x80000000, 0xFFFFFFFF, sum(0x80000000 << (32 * i) for i in range(7)),
+             sum(0xFFFFFFFF << (32 * i) for i in range(7)) | (0x3FFFFFFF << 224), (1 << 256) % P]
+    cases += [rng.randrange(P) for _ in range(rounds)]
+    cases += [rng.randrange(1 << 254) & ~(rng.randrange(1 << 254)) for _ in range(100)]
+    for a in cases:
+        r = run_ptx(lines, a, 0)
+        assert r < 2 * P, "bound violated"
+        assert r % P == (a * a * rinv) % P, (hex(a), hex(r))
+
+
 def selfcheck(P, lines, rounds=400):
     rinv = pow(1 << 256, -1, P)
     rng = random.Random(0xB200 ^ (P & 0xFFFF))
@@ -228,6 +290,19 @@ def c_body_add2(name, lines, ntemps):
     return text[:-2] + "\n"  # drop the continuation after the closing parenthesis
 
 
+def c_body_sqr(name, lines, ntemps):
+    out = []
+    out.append("// GENERATED by tools/gen_mont_ptx.py -- do not edit. %s: r = a*a*2^-256 mod p, r in [0,2p), a < 2^254" % name)
+    out.append("#define H2AGG_MONT_SQR_%s(r, a) \\" % name)
+    out.append('  asm("{\\n\\t.reg .u32 t<%d>;\\n\\t" \\' % ntemps)
+    for ln in lines:
+        out.append('      "%s\\n\\t" \\' % ln)
+    out.append('      "}" \\')
+    out.append('      : "=r"((r)[0]), "=r"((r)[1]), "=r"((r)[2]), "=r"((r)[3]), "=r"((r)[4]), "=r"((r)[5]), "=r"((r)[6]), "=r"((r)[7]) \\')
+    out.append('      : "r"((a)[0]), "r"((a)[1]), "r"((a)[2]), "r"((a)[3]), "r"((a)[4]), "r"((a)[5]), "r"((a)[6]), "r"((a)[7]))')
+    return "\n".join(out) + "\n"
+
+
 def c_body(name, lines, ntemps):
     out = []
     out.append("// GENERATED by tools/gen_mont_ptx.py -- do not edit. %s: r = a*b*2^-256 mod p, r in [0,2p)" % name)
@@ -252,6 +327,12 @@ def main():
         selfcheck(P, lines)
         text += c_body(name, lines, g.ntemps) + "\n"
         print("%s: %d PTX instructions, %d temps, self-check ok" % (name, len(lines), g.ntemps))
+        g3 = Gen(P)
+        lines3 = g3.mont_sqr()
+        selfcheck_sqr(P, lines3)
+        text += c_body_sqr(name, lines3, g3.ntemps) + "\n"
+        nmul = sum(1 for ln in lines3 if ln.startswith(("mad.lo", "madc.lo", "mul.lo")))
+        print("%s sqr: %d PTX instructions (%d multiplier pairs/singles), %d temps, self-check ok" % (name, len(lines3), nmul, g3.ntemps))
         g2 = Gen(P)
         lines2 = g2.mont_mul_add2()
         selfcheck_add2(P, lines2)
