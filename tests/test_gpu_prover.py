@@ -189,3 +189,114 @@ def test_lookup_and_product_rounds_from_resident_columns(ctx, which, k):
     check(names, comms, want)
     pr.close()
     ctx.srs_release(sid)
+
+
+def _drive_proof(ctx, cs, k, lag, sid, tamper=None):
+    """witness in -> proof elements out, challenges from the ShaWrite transcript (T1) in create_proof's order.
+    Returns (desc of what the verifier needs)."""
+    from halo2_snark_aggregator_b200.transcript import ShaWrite
+
+    n = 1 << k
+    pr = ResidentProver(ctx, cs, k, sid, sid)
+    rng = random.Random(31)
+    t = ShaWrite()
+    # halo2 absorbs the instance values first (the vk digest before them is an external-crate format: not restated)
+    for v in lag[("instance", 0)]:
+        t.common_scalar_int(v)
+    pk = [nm for nm in lag if nm[0] in ("fixed", "sigma", "l0", "l_last", "l_active_row")]
+    pr.commit_columns(pk, [qu.pack(lag[nm]) for nm in pk], keep_lagrange=True)          # keygen: not part of the proof
+    wit = [("instance", 0)] + [("advice", i) for i in range(cs.num_advice)]
+    for c in pr.commit_columns(wit, [qu.pack(lag[nm]) for nm in wit], keep_lagrange=True)[1:]:
+        t.write_point(c)                                                                  # advice commitments
+    theta = t.squeeze_challenge()
+
+    def blind(name, rows):
+        return qu.pack([rng.randrange(R) for _ in range(rows)])
+
+    for c in pr.lookup_round(theta, blind):
+        t.write_point(c)
+    beta, gamma = t.squeeze_challenge(), t.squeeze_challenge()
+    for c in pr.product_round(beta, gamma, blind):
+        t.write_point(c)
+    t.write_point(pr.commit_coeff_columns([("random", 0)], [qu.pack([rng.randrange(R) for _ in range(n)])])[0])
+    y = t.squeeze_challenge()
+    for c in pr.quotient(y, beta, gamma, theta):
+        t.write_point(c)
+    x = t.squeeze_challenge()
+    pr.fold_h(x)
+    queries = create_proof_queries(cs) + [(("instance", 0), 0)]
+    evals = pr.evaluate(queries, x)
+    for e in evals[:-1]:
+        t.write_scalar(e)
+    v = t.squeeze_challenge()
+    order, ws = pr.open(queries[:-1], x, v)
+    for c in ws:
+        t.write_point(c)
+    proof = t.finalize()
+    ev = {q: qu.unpack(e)[0] for q, e in zip(queries, evals)}
+    pr.close()
+    return dict(x=x, y=y, beta=beta, gamma=gamma, theta=theta, ev=ev, proof=proof, n_w=len(ws))
+
+
+def _valid_aggregation_witness(k, seed):
+    """Columns that SATISFY the aggregation circuit's constraint system: gate coefficients zero (the base gate has no
+    selector: all-zero coefficient rows are how unused rows look), range tables i mod 16 with 0/1 selectors and small
+    advice cells, and sigma columns encoding one real copy cycle between equal cells."""
+    cs = plonk.aggregation_circuit_cs()
+    lag = _satisfiable_columns(cs, "aggregation", k, seed)
+    n = 1 << k
+    for i in range(9):
+        lag[("fixed", i)] = [0] * n
+    w = qr.omega(k)
+    ident = [[pow(plonk.DELTA, j, R) * pow(w, i, R) % R for i in range(n)] for j in range(len(cs.permutation_columns))]
+    for j in range(len(cs.permutation_columns)):
+        lag[("sigma", j)] = list(ident[j])
+    cells = [(0, 3), (2, 17), (5, 9), (4, 20)]        # (permutation column index, row): a0[3] = a2[17] = instance[9] = a4[20]
+    val = 11
+    for j, i in cells:
+        lag[cs.permutation_columns[j]][i] = val
+    for (j, i), (j2, i2) in zip(cells, cells[1:] + cells[:1]):
+        lag[("sigma", j)][i] = ident[j2][i2]
+    l0, l_last, l_active = qu.lagrange_selectors(k, cs.blinding_factors())
+    lag[("l0", 0)], lag[("l_last", 0)], lag[("l_active_row", 0)] = l0, l_last, l_active
+    return cs, lag
+
+
+def test_device_proof_satisfies_the_reference_verifiers_equation(ctx):
+    """End to end: a satisfying witness goes in, every round runs on the device with Fiat-Shamir challenges from the
+    ShaWrite transcript, and the evaluations that come out satisfy the equation the REFERENCE's verifier checks --
+    h(x) (x^n - 1) = fold_y(gates, permutation, lookups)(x), restated from
+    halo2-snark-aggregator-api/src/systems/halo2/{params,permutation,lookup,vanish}.rs (oracle/py/quotient_ref.py).
+    The identity holds only if the permuted columns, the grand products and the quotient are all right."""
+    k = 6
+    n = 1 << k
+    cs, lag = _valid_aggregation_witness(k, 3)
+    sid = ctx.srs_register(ob.gen_bases(0x7200 + k, n))
+    out = _drive_proof(ctx, cs, k, lag, sid)
+    desc = qu.oracle_desc(cs)
+
+    def ev(name, rot):
+        return out["ev"][(name, rot)]
+
+    want = qr.verifier_h_eval(desc, ev, k, out["x"], out["y"], out["beta"], out["gamma"], out["theta"])
+    assert out["ev"][(("h", 0), 0)] == want
+    # proof bytes: 5 + 14 + 9 + 1 + 4 + 4 points of 64 B and 70 scalars of 32 B
+    assert out["n_w"] == 4 and len(out["proof"]) == 64 * (5 + 14 + 9 + 1 + 4 + 4) + 32 * 71
+
+    # a broken copy constraint: same flow, the verifier's equation must fail
+    lag2 = {nm: list(v) for nm, v in lag.items()}
+    lag2[("advice", 0)][3] = 12
+    out2 = _drive_proof(ctx, cs, k, lag2, sid)
+    want2 = qr.verifier_h_eval(desc, lambda nm, rot: out2["ev"][(nm, rot)], k, out2["x"], out2["y"], out2["beta"], out2["gamma"],
+                               out2["theta"])
+    assert out2["ev"][(("h", 0), 0)] != want2
+
+    # a cell outside the range table: the lookup round reports it like halo2 (ConstraintSystemFailure)
+    lag3 = {nm: list(v) for nm, v in lag.items()}
+    lag3[("advice", 1)][5] = 16
+    lag3[("fixed", 9)][5] = 1
+    from halo2_snark_aggregator_b200 import H2aggError
+    with pytest.raises(H2aggError) as e:
+        _drive_proof(ctx, cs, k, lag3, sid)
+    assert "error 4" in str(e.value)
+    ctx.srs_release(sid)
