@@ -191,36 +191,45 @@ def test_lookup_and_product_rounds_from_resident_columns(ctx, which, k):
     ctx.srs_release(sid)
 
 
-def _drive_proof(ctx, cs, k, lag, sid, tamper=None):
+def _drive_proof(ctx, cs, k, lag, sid, sid_g=None):
     """witness in -> proof elements out, challenges from the ShaWrite transcript (T1) in create_proof's order.
     Returns (desc of what the verifier needs)."""
     from halo2_snark_aggregator_b200.transcript import ShaWrite
 
     n = 1 << k
-    pr = ResidentProver(ctx, cs, k, sid, sid)
+    pr = ResidentProver(ctx, cs, k, sid, sid if sid_g is None else sid_g)
     rng = random.Random(31)
     t = ShaWrite()
+    comm = {}
     # halo2 absorbs the instance values first (the vk digest before them is an external-crate format: not restated)
     for v in lag[("instance", 0)]:
         t.common_scalar_int(v)
     pk = [nm for nm in lag if nm[0] in ("fixed", "sigma", "l0", "l_last", "l_active_row")]
-    pr.commit_columns(pk, [qu.pack(lag[nm]) for nm in pk], keep_lagrange=True)          # keygen: not part of the proof
+    comm.update(zip(pk, pr.commit_columns(pk, [qu.pack(lag[nm]) for nm in pk], keep_lagrange=True)))   # keygen: not part of the proof
     wit = [("instance", 0)] + [("advice", i) for i in range(cs.num_advice)]
-    for c in pr.commit_columns(wit, [qu.pack(lag[nm]) for nm in wit], keep_lagrange=True)[1:]:
+    cw = pr.commit_columns(wit, [qu.pack(lag[nm]) for nm in wit], keep_lagrange=True)
+    comm.update(zip(wit, cw))
+    for c in cw[1:]:
         t.write_point(c)                                                                  # advice commitments
     theta = t.squeeze_challenge()
 
     def blind(name, rows):
         return qu.pack([rng.randrange(R) for _ in range(rows)])
 
-    for c in pr.lookup_round(theta, blind):
+    names2 = [(w_, i) for i in range(len(cs.lookups)) for w_ in ("lookup_input", "lookup_table")]
+    for nm, c in zip(names2, pr.lookup_round(theta, blind)):
+        comm[nm] = c
         t.write_point(c)
     beta, gamma = t.squeeze_challenge(), t.squeeze_challenge()
-    for c in pr.product_round(beta, gamma, blind):
+    names3 = [("perm_z", s_) for s_ in range(cs.num_permutation_sets())] + [("lookup_z", i) for i in range(len(cs.lookups))]
+    for nm, c in zip(names3, pr.product_round(beta, gamma, blind)):
+        comm[nm] = c
         t.write_point(c)
-    t.write_point(pr.commit_coeff_columns([("random", 0)], [qu.pack([rng.randrange(R) for _ in range(n)])])[0])
+    comm[("random", 0)] = pr.commit_coeff_columns([("random", 0)], [qu.pack([rng.randrange(R) for _ in range(n)])])[0]
+    t.write_point(comm[("random", 0)])
     y = t.squeeze_challenge()
-    for c in pr.quotient(y, beta, gamma, theta):
+    for i, c in enumerate(pr.quotient(y, beta, gamma, theta)):
+        comm[("h_piece", i)] = c
         t.write_point(c)
     x = t.squeeze_challenge()
     pr.fold_h(x)
@@ -235,7 +244,8 @@ def _drive_proof(ctx, cs, k, lag, sid, tamper=None):
     proof = t.finalize()
     ev = {q: qu.unpack(e)[0] for q, e in zip(queries, evals)}
     pr.close()
-    return dict(x=x, y=y, beta=beta, gamma=gamma, theta=theta, ev=ev, proof=proof, n_w=len(ws))
+    return dict(x=x, y=y, beta=beta, gamma=gamma, theta=theta, v=v, ev=ev, proof=proof, n_w=len(ws), comm=comm, order=order,
+                ws=ws, queries=queries[:-1])
 
 
 def _valid_aggregation_witness(k, seed):
@@ -300,3 +310,47 @@ def test_device_proof_satisfies_the_reference_verifiers_equation(ctx):
         _drive_proof(ctx, cs, k, lag3, sid)
     assert "error 4" in str(e.value)
     ctx.srs_release(sid)
+
+
+def test_device_proof_openings_verify_against_a_trapdoor_srs(ctx):
+    """The other half of verify_proof: the GWC opening check e(W, [s - z]_2) = e(F - [e]_1, [1]_2) per point, done in
+    the group with the trapdoor s of a toy SRS (g_i = s^i G, g_lagrange_i = L_i(s) G) and textbook affine arithmetic on
+    Python integers: (s - z) W = sum_i v^(m-1-i) (C_i - e_i G).  It ties together what the device produced -- the
+    commitments (MSM against both SRS forms), the coefficient forms behind the evaluations (iNTT), the fold, the Kate
+    quotients and their commitments."""
+    import bn254_ref as ref
+
+    k = 6
+    n = 1 << k
+    cs, lag = _valid_aggregation_witness(k, 5)
+    s_trap = 0x1234567890ABCDEF1234567890ABCDEF % R
+    w = qr.omega(k)
+    G = ref.G1_GEN
+    g = [ref.g1_mul(pow(s_trap, i, R), G) for i in range(n)]
+    # L_i(s) = (s^n - 1) w^i / (n (s - w^i))
+    sn1 = (pow(s_trap, n, R) - 1) % R
+    gl = [ref.g1_mul(sn1 * pow(w, i, R) % R * pow(n * (s_trap - pow(w, i, R)) % R, -1, R) % R, G) for i in range(n)]
+    sid_g = ctx.srs_register(np.array(ref.pack_points(g), dtype=np.uint64))
+    sid_gl = ctx.srs_register(np.array(ref.pack_points(gl), dtype=np.uint64))
+    out = _drive_proof(ctx, cs, k, lag, sid_gl, sid_g)
+    x, v = out["x"], out["v"]
+    pt = lambda c: ref.unpack_point([int(t_) for t_ in c])
+    C = {nm: pt(c) for nm, c in out["comm"].items()}
+    # h(X) = sum_i x^(n i) h_i(X): its commitment is the same combination of the piece commitments
+    xn = pow(x, n, R)
+    C[("h", 0)] = None
+    for i in reversed(range(cs.degree() - 1)):
+        C[("h", 0)] = ref.g1_add(ref.g1_mul(xn, C[("h", 0)]), C[("h_piece", i)])
+    assert all(ref.on_curve(p) for p in C.values())
+    for rot, wpt in zip(out["order"], out["ws"]):
+        z = x * pow(w, rot, R) % R
+        F, E = None, 0
+        for nm, r2 in out["queries"]:
+            if r2 == rot:
+                F = ref.g1_add(ref.g1_mul(v, F), C[nm])
+                E = (E * v + out["ev"][(nm, r2)]) % R
+        lhs = ref.g1_mul((s_trap - z) % R, pt(wpt))
+        rhs = ref.g1_add(F, ref.g1_neg(ref.g1_mul(E, G)))
+        assert lhs == rhs, "opening at rotation %d" % rot
+    ctx.srs_release(sid_g)
+    ctx.srs_release(sid_gl)
