@@ -339,6 +339,20 @@ class Context:
     def permute_expression_pair_dev(self, d_inp, d_tab, u, d_pin, d_ptab):
         self.check(self.lib.h2agg_permute_expression_pair_dev(self.h, c_vp(d_inp), c_vp(d_tab), u, c_vp(d_pin), c_vp(d_ptab)))
 
+    # -- N4: PrimeField::to_repr / from_repr in bulk
+    def fr_to_repr(self, limbs):
+        """Montgomery limbs (n*4 uint64) -> n*32 bytes, little-endian canonical"""
+        out = np.empty_like(limbs)
+        self.check(self.lib.h2agg_fr_repr(self.h, 0, _ptr(limbs), _ptr(out), limbs.size // 4))
+        return out.tobytes()
+
+    def fr_from_repr(self, data):
+        """n*32 bytes -> Montgomery limbs; raises H2aggError (status 4) on a non-canonical value"""
+        a = np.frombuffer(data, dtype=np.uint64).copy()
+        out = np.empty_like(a)
+        self.check(self.lib.h2agg_fr_repr(self.h, 1, _ptr(a), _ptr(out), a.size // 4))
+        return out
+
     # -- field helpers (device)
     def field_op(self, field, op, a, b=None):
         out = np.empty_like(a)

@@ -788,7 +788,52 @@ __global__ void field_op_kernel(int op, const F* a, const F* b, F* out, size_t n
   r.store(out + i);
 }
 
+// PrimeField::to_repr / from_repr in bulk: Montgomery limbs <-> 32-byte little-endian canonical integers.
+// from_repr counts the inputs that are not < r (Rust returns None for those; the callers unwrap()).
+__global__ void fr_repr_kernel(int from_repr, const Fr* in, Fr* out, size_t n, uint32_t* bad) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr x = Fr::load(in + i);
+  if (!from_repr) {
+    fp_from_mont(x).store(out + i);
+    return;
+  }
+  bool ge = true;  // x >= r ?
+#pragma unroll
+  for (int j = 7; j >= 0; j--) {
+    if (x.v[j] != FrTag::P(j)) { ge = x.v[j] > FrTag::P(j); break; }
+  }
+  if (ge) atomicAdd(bad, 1u);
+  fp_to_mont(x).store(out + i);
+}
+
 extern "C" {
+
+int h2agg_fr_repr(h2agg_ctx* ctx, int from_repr, const void* in, void* out, size_t n) {
+  if (!ctx) return 1;
+  LOCK(ctx);
+  CHECK_ARG(ctx, (in && out) || n == 0, "fr_repr: null argument");
+  if (n == 0) return 0;
+  H2AGG_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc = ensure(ctx, ctx->io_a, n * 32);
+  if (rc) return rc;
+  uint32_t* bad = (uint32_t*)((uint8_t*)ctx->small.p + 8192);
+  H2AGG_CUDA(ctx, cudaMemsetAsync(bad, 0, 4, ctx->stream));
+  H2AGG_CUDA(ctx, cudaMemcpyAsync(ctx->io_a.p, in, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  fr_repr_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(from_repr, (const Fr*)ctx->io_a.p, (Fr*)ctx->io_a.p, n, bad);
+  ctx->launches++;
+  H2AGG_CUDA(ctx, cudaGetLastError());
+  H2AGG_CUDA(ctx, cudaMemcpyAsync(out, ctx->io_a.p, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  H2AGG_CUDA(ctx, cudaMemcpyAsync((uint8_t*)ctx->pinned + 8192, bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  H2AGG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  uint32_t nbad;
+  memcpy(&nbad, (uint8_t*)ctx->pinned + 8192, 4);
+  if (from_repr && nbad) {
+    ctx->last_error = "fr_repr: " + std::to_string(nbad) + " value(s) are not canonical (>= r): PrimeField::from_repr returns None";
+    return 4;
+  }
+  return 0;
+}
 
 int h2agg_field_op(h2agg_ctx* ctx, int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
   if (!ctx) return 1;

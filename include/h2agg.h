@@ -307,6 +307,13 @@ int h2agg_wit_point_value(h2agg_witness* w, int64_t h, uint64_t out_xy[8], int* 
 int h2agg_witness_expand(h2agg_ctx* ctx, h2agg_witness* w, uint64_t* const advice_cols[5], size_t n_rows);
 int h2agg_witness_expand_dev(h2agg_ctx* ctx, h2agg_witness* w, void* const d_cols[5], size_t n_rows);
 
+/* ---- N4 (data formats either side of the path): PrimeField::to_repr / from_repr in bulk -----------------------
+ * The reference's stage files hold scalars as 32-byte little-endian canonical integers
+ * (halo2-snark-aggregator-circuit/src/fs.rs:134-146 load_instances, :169-180 write_verify_circuit_instance,
+ * :182-197 write_verify_circuit_final_pair).  from_repr = 0: Montgomery limbs -> repr bytes; 1: repr bytes -> Montgomery
+ * limbs, status 4 if a value is not < r (from_repr(..).unwrap() would panic).  Host pointers, n x 32 B each way. */
+int h2agg_fr_repr(h2agg_ctx* ctx, int from_repr, const void* in, void* out, size_t n);
+
 /* ---- small helpers used by tests and the host layer (run on the device) ---------------------- */
 /* out[i] = a[i] * b[i] in Fr (field = 0) or Fq (field = 1); host pointers; Montgomery form. */
 int h2agg_field_mul(h2agg_ctx* ctx, int field, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n);

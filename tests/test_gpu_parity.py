@@ -518,3 +518,19 @@ def test_msm_blinding_rows_do_not_slow_the_bucket_walk(ctx):
     finally:
         for p in (d_b, d_s, d_w, d_o):
             ctx.dev_free(p)
+
+
+def test_fr_repr_bulk(ctx):
+    """N4: PrimeField::to_repr / from_repr for whole vectors (the reference's stage files, fs.rs:134-197)."""
+    from halo2_snark_aggregator_b200 import H2aggError, fs
+    from util import R_MOD
+
+    vals = [0, 1, R_MOD - 1, 12345 << 200] + [pow(7, i, R_MOD) for i in range(1, 1000)]
+    limbs = np.concatenate([fr_limbs(v) for v in vals])
+    data = ctx.fr_to_repr(limbs)
+    assert data == b"".join(fs.to_repr(v) for v in vals)
+    assert fs.load_instances(data) == [[vals]]
+    assert np.array_equal(ctx.fr_from_repr(data), limbs)
+    with pytest.raises(H2aggError) as e:
+        ctx.fr_from_repr(data + fs.to_repr(R_MOD))
+    assert "error 4" in str(e.value)
