@@ -99,6 +99,7 @@ def load():
         "h2agg_extended_to_coeff_dev": (ci, [c_vp, c_vp, u32, c_vp, c_vp, c_vp, sz]),
         "h2agg_eval_polynomial": (ci, [c_vp, c_vp, sz, c_vp, c_vp]),
         "h2agg_eval_polynomial_dev": (ci, [c_vp, c_vp, sz, c_vp, c_vp]),
+        "h2agg_eval_polynomials_dev": (ci, [c_vp, ctypes.POINTER(c_vp), sz, sz, c_vp, c_vp]),
         "h2agg_kate_division": (ci, [c_vp, c_vp, sz, c_vp, c_vp]),
         "h2agg_kate_division_dev": (ci, [c_vp, c_vp, sz, c_vp, c_vp]),
         "h2agg_batch_invert": (ci, [c_vp, c_vp, sz]),

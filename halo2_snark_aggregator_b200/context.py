@@ -267,6 +267,11 @@ class Context:
     def eval_polynomial_dev(self, d_poly, n, point, d_out32):
         self.check(self.lib.h2agg_eval_polynomial_dev(self.h, c_vp(d_poly), n, _ptr(point), c_vp(d_out32)))
 
+    def eval_polynomials_dev(self, d_polys, n, point, d_out):
+        """d_out[i] = polys[i](point): many polynomials of n coefficients at one point"""
+        arr = (c_vp * len(d_polys))(*d_polys)
+        self.check(self.lib.h2agg_eval_polynomials_dev(self.h, arr, len(d_polys), n, _ptr(point), c_vp(d_out)))
+
     def kate_division(self, a, b):
         n = a.size // 4
         q = np.zeros(4 * max(n - 1, 0), dtype=np.uint64)

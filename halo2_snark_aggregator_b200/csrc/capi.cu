@@ -108,6 +108,7 @@ void h2agg_destroy(h2agg_ctx* ctx) {
   for (auto e : ctx->ev_pool) cudaEventDestroy(e);
   cudaFree(ctx->small.p);
   cudaFree(ctx->poly_ws.p);
+  cudaFree(ctx->poly_many_ws.p);
   cudaFree(ctx->scan_ws.p);
   cudaFree(ctx->sort_ws.p);
   cudaFree(ctx->args_ws.p);

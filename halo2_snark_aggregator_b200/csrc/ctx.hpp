@@ -70,6 +70,7 @@ struct h2agg_ctx {
   cudaEvent_t fork_ev = nullptr;
   h2agg::DevBuf small;        // small constants / results
   h2agg::DevBuf poly_ws;      // recursion levels of eval_polynomial / kate_division
+  h2agg::DevBuf poly_many_ws; // eval_polynomials: two level buffers for 64 polynomials at a time
   h2agg::DevBuf scan_ws;      // batch_invert / grand_product scratch
   h2agg::DevBuf args_ws;      // lookup / permutation products: numerators and denominators
   h2agg::DevBuf args_meta;    // compress_expressions: device copies of expression lists (four slots)

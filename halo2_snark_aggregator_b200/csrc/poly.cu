@@ -16,6 +16,7 @@
 #include "../../include/h2agg.h"
 #include "bn254_field.cuh"
 #include "ctx.hpp"
+#include <algorithm>
 #include <cstring>
 
 namespace h2agg {
@@ -140,6 +141,82 @@ int poly_eval_dev(h2agg_ctx* ctx, const void* d_a, size_t n, const uint64_t poin
   return 0;
 }
 
+// ---- many polynomials of the same length at ONE point (the evaluation round of create_proof opens ~50 polynomials at
+// x and a handful at each rotated point): the same chunked recursion with the polynomial index as blockIdx.y, so the
+// whole group costs five launches instead of five per polynomial.
+static constexpr uint32_t EVAL_BATCH = 64;
+struct EvalBatchArgs {
+  const Fr* polys[EVAL_BATCH];  // level 0: one pointer per polynomial
+  const Fr* base;               // later levels: vector p at base + p * stride
+  size_t stride;
+  size_t n, m;                  // input length, number of chunks
+  const Fr* y_ptr;
+  Fr* s;                        // out: [p][m]
+};
+__global__ void __launch_bounds__(128) poly_chunk_horner_batch(const __grid_constant__ EvalBatchArgs a) {
+  size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.m) return;
+  const uint32_t p = blockIdx.y;
+  const Fr* __restrict__ v = a.base ? a.base + p * a.stride : a.polys[p];
+  const Fr y = Fr::load(a.y_ptr);
+  size_t lo = c * POLY_L, hi = lo + POLY_L;
+  if (hi > a.n) hi = a.n;
+  Fr acc = Fr::zero();
+  for (size_t i = hi; i-- > lo;) acc = acc * y + Fr::load_nc(v + i);
+  acc.store(a.s + p * a.m + c);
+}
+// one thread per polynomial finishes its short vector
+__global__ void poly_eval_serial_batch(const EvalBatchArgs a, uint32_t n_polys, Fr* out) {
+  uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_polys) return;
+  const Fr* v = a.base ? a.base + p * a.stride : a.polys[p];
+  const Fr y = Fr::load(a.y_ptr);
+  Fr acc = Fr::zero();
+  for (size_t i = a.n; i-- > 0;) acc = acc * y + Fr::load(v + i);
+  acc.store(out + p);
+}
+
+int poly_eval_many_dev(h2agg_ctx* ctx, const void* const* d_polys, size_t n_polys, size_t n, const uint64_t point[4], void* d_out) {
+  if (n_polys == 0) return 0;
+  // workspace: pow table + two ping-pong level buffers of EVAL_BATCH x ceil(n / L) entries
+  const size_t m1 = (n + POLY_L - 1) / POLY_L;
+  int rc = ensure(ctx, ctx->poly_many_ws, (64 + 2 * EVAL_BATCH * m1) * 32 + 256);
+  if (rc) return rc;
+  Fr* pow2 = (Fr*)ctx->poly_many_ws.p;
+  Fr* lvl[2] = {pow2 + 64, pow2 + 64 + EVAL_BATCH * m1};
+  Fr x;
+  memcpy(x.v, point, 32);
+  cudaStream_t st = ctx->stream;
+  poly_pow2_table<<<1, 32, 0, st>>>(x, 48, pow2);
+  ctx->launches++;
+  for (size_t done = 0; done < n_polys; done += EVAL_BATCH) {
+    const uint32_t P = (uint32_t)std::min<size_t>(EVAL_BATCH, n_polys - done);
+    EvalBatchArgs a;
+    memset(&a, 0, sizeof(a));
+    for (uint32_t p = 0; p < P; p++) a.polys[p] = (const Fr*)d_polys[done + p];
+    a.n = n;
+    uint32_t lg = 0;
+    int flip = 0;
+    while (a.n > POLY_SERIAL) {
+      a.m = (a.n + POLY_L - 1) / POLY_L;
+      a.y_ptr = pow2 + lg;
+      a.s = lvl[flip];
+      poly_chunk_horner_batch<<<dim3((unsigned)((a.m + 127) / 128), P), 128, 0, st>>>(a);
+      ctx->launches++;
+      a.base = lvl[flip];
+      a.stride = a.m;
+      a.n = a.m;
+      flip ^= 1;
+      lg += 6;
+    }
+    a.y_ptr = pow2 + lg;
+    poly_eval_serial_batch<<<(P + 31) / 32, 32, 0, st>>>(a, P, (Fr*)d_out + done);
+    ctx->launches++;
+  }
+  H2AGG_CUDA(ctx, cudaGetLastError());
+  return 0;
+}
+
 // division: d_q receives n entries, q[n-1] = 0 (halo2 returns the first n-1)
 int poly_kate_dev(h2agg_ctx* ctx, const void* d_a, size_t n, const uint64_t b[4], void* d_q) {
   if (n == 0) return 0;
@@ -195,6 +272,17 @@ int h2agg_eval_polynomial_dev(h2agg_ctx* ctx, const void* d_poly, size_t n, cons
   if (!d_poly || !point || !d_out32) { ctx->last_error = "eval_polynomial: null argument"; return 1; }
   H2AGG_CUDA(ctx, cudaSetDevice(ctx->device));
   return poly_eval_dev(ctx, d_poly, n, point, d_out32);
+}
+
+int h2agg_eval_polynomials_dev(h2agg_ctx* ctx, const void* const* d_polys, size_t n_polys, size_t n, const uint64_t point[4],
+                               void* d_out) {
+  if (!ctx) return 1;
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+  if (!point || (n_polys && (!d_polys || !d_out))) { ctx->last_error = "eval_polynomials: null argument"; return 1; }
+  for (size_t i = 0; i < n_polys; i++)
+    if (!d_polys[i]) { ctx->last_error = "eval_polynomials: null polynomial"; return 1; }
+  H2AGG_CUDA(ctx, cudaSetDevice(ctx->device));
+  return poly_eval_many_dev(ctx, d_polys, n_polys, n, point, d_out);
 }
 
 int h2agg_eval_polynomial(h2agg_ctx* ctx, const uint64_t* poly, size_t n, const uint64_t point[4], uint64_t out[4]) {

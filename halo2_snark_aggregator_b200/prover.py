@@ -225,9 +225,18 @@ class ResidentProver:
         """queries: [(column name, rotation)] -> evaluations at x * omega^rotation, shape (len, 4) Montgomery limbs."""
         assert len(queries) <= 1024
         d_ev = self._buf("evals", 32 * 1024)
+        groups = {}  # one batched call per opening point
         for i, (nm, rot) in enumerate(queries):
-            self.ctx.eval_polynomial_dev(self.coeff[nm], self.n, fr_to_limbs(self.rotate_omega(x, rot)), d_ev + 32 * i)
-        return self.ctx.d2h(d_ev, 4 * len(queries)).reshape(len(queries), 4)
+            groups.setdefault(rot, []).append(i)
+        off, where = 0, [0] * len(queries)
+        for rot, idxs in groups.items():
+            self.ctx.eval_polynomials_dev([self.coeff[queries[i][0]] for i in idxs], self.n,
+                                          fr_to_limbs(self.rotate_omega(x, rot)), d_ev + 32 * off)
+            for j, i in enumerate(idxs):
+                where[i] = off + j
+            off += len(idxs)
+        flat = self.ctx.d2h(d_ev, 4 * len(queries)).reshape(len(queries), 4)
+        return flat[where]
 
     # -- stage 6: GWC multi-opening ---------------------------------------------------------------------
     def open(self, queries, x, v):

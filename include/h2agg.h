@@ -182,6 +182,10 @@ int h2agg_extended_to_coeff_dev(h2agg_ctx* ctx, void* d_a, uint32_t ext_k, const
  *                      (the last one is zero). */
 int h2agg_eval_polynomial(h2agg_ctx* ctx, const uint64_t* poly /* n*4 */, size_t n, const uint64_t point[4], uint64_t out[4]);
 int h2agg_eval_polynomial_dev(h2agg_ctx* ctx, const void* d_poly, size_t n, const uint64_t point[4], void* d_out32);
+/* n_polys polynomials of n coefficients each at ONE point -> d_out[i] = polys[i](point) (n_polys x 32 B): what the
+ * evaluation round does per opening point, in five launches for the whole group instead of five per polynomial. */
+int h2agg_eval_polynomials_dev(h2agg_ctx* ctx, const void* const* d_polys, size_t n_polys, size_t n, const uint64_t point[4],
+                               void* d_out);
 int h2agg_kate_division(h2agg_ctx* ctx, const uint64_t* a /* n*4 */, size_t n, const uint64_t b[4], uint64_t* q /* (n-1)*4 */);
 int h2agg_kate_division_dev(h2agg_ctx* ctx, const void* d_a, size_t n, const uint64_t b[4], void* d_q /* n*32 B */);
 

@@ -534,3 +534,23 @@ def test_fr_repr_bulk(ctx):
     with pytest.raises(H2aggError) as e:
         ctx.fr_from_repr(data + fs.to_repr(R_MOD))
     assert "error 4" in str(e.value)
+
+
+@pytest.mark.parametrize("n,m", [(1, 3), (64, 2), (65, 5), (4096, 1), (5000, 70), (1 << 16, 9)])
+def test_eval_polynomials_batch(ctx, n, m):
+    """h2agg_eval_polynomials_dev: many polynomials at one point == the single-polynomial oracle, including more than
+    one launch group (70 > 64) and lengths that are not multiples of the chunk."""
+    polys = [ob.gen_scalars(0x4400 + 7 * i + n, 0, n) for i in range(m)]
+    pt = ob.gen_scalars(0x4499 + n, 0, 1)
+    d = []
+    for p in polys:
+        q = ctx.dev_alloc(n * 32)
+        ctx.h2d(q, p)
+        d.append(q)
+    d_out = ctx.dev_alloc(m * 32)
+    ctx.eval_polynomials_dev(d, n, pt, d_out)
+    got = ctx.d2h(d_out, 4 * m).reshape(m, 4)
+    for i in range(m):
+        assert np.array_equal(got[i], ob.eval_polynomial(polys[i], pt)), i
+    for q in d + [d_out]:
+        ctx.dev_free(q)
