@@ -753,6 +753,10 @@ def main():
                          "traffic_note": "dram__bytes_read+write of one msm_accumulate launch on a uniform 2^22 column in table mode (profiles/r01_ncu_summary.md): the gather of 54.5 M precomputed 64-byte points is by design",
                          "algorithmic_bytes_per_launch": msm_bytes, "avg_launch_ms": (acc_ms / acc_n) if acc_n else None,
                          "launches_timed": acc_n,
+                         "launch_ms_alone_uniform_column": acc_alone_ms,
+                         "achieved_alone": (msm_bytes / (acc_alone_ms * 1e-3) / 1e9) if acc_alone_ms else None,
+                         "frac_alone": (msm_bytes / (acc_alone_ms * 1e-3) / 1e9 / peak) if acc_alone_ms else None,
+                         "timing_note": "avg_launch_ms is the CUDA-event duration inside the timed region, where up to 8 lanes run their kernels concurrently, so it includes time shared with other lanes' kernels; *_alone is one launch on a uniform column with nothing else on the GPU",
                          "note": "MSM is bound by the INT32 IMAD pipe, not HBM (SURVEY.md 8d); HBM fraction reported as the metric demands"},
             "roofline_multiplier": None if not acc_alone_ms else (lambda clk: {
                 "kernel": "msm_accumulate", "bound": "int32 multiplier: IMAD.WIDE.U32 issues once per 4 clk per SM sub-partition (32 lanes/clk/SM; profiles/r01_pipe_rates_b200.jsonl, ncu fmaheavy pipe)",

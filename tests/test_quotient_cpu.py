@@ -181,3 +181,45 @@ def test_cpp_oracle_matches_python_oracle(k, divide):
     got = ob.evaluate_h(plan.words, plan.consts, cols, k, ext_k, qu.pack([y]), qu.pack([beta]), qu.pack([gamma]),
                         qu.pack([theta]), qu.pack([qr.omega(ext_k)]), qu.pack([qr.ZETA]), qu.pack([qr.DELTA]), t, nthreads=3)
     assert qu.unpack(got) == want
+
+
+def test_expression_list_words_evaluate_like_the_oracle():
+    """plonk.ExpressionList (the word program h2agg_compress_expressions_dev runs) interpreted in plain Python equals
+    the tree evaluation of oracle/py/lookup_ref.compress_expressions, rotations wrapping mod n."""
+    import lookup_ref as lr
+
+    E = plonk.Expression
+    k = 4
+    n = 1 << k
+    rng = random.Random(21)
+    names = [("advice", 0), ("advice", 1), ("fixed", 0), ("instance", 0)]
+    index = {nm: i for i, nm in enumerate(names)}
+    cols = {nm: [rng.randrange(R) for _ in range(n)] for nm in names}
+    exprs = [E.advice(0) * E.fixed(0), E.advice(1, 1) * 3 + E.constant(9), E.instance(0, -2) * E.advice(0) * E.advice(0, 1) - E.fixed(0)]
+    prog = plonk.ExpressionList(exprs, index)
+    w = [int(x) for x in prog.words]
+    consts = qu.unpack(prog.consts) if prog.consts.size else []
+    theta = rng.randrange(R)
+    got = []
+    for i in range(n):
+        pc = 1
+        acc = 0
+        for _ in range(w[0]):
+            nt = w[pc]
+            pc += 1
+            s = 0
+            for _ in range(nt):
+                ci, nf = w[pc], w[pc + 1]
+                pc += 2
+                prod = 1 if ci == plonk.NOCONST else consts[ci]
+                for _ in range(nf):
+                    word = w[pc]
+                    pc += 1
+                    rot = word >> 16
+                    rot = rot - 65536 if rot >= 32768 else rot
+                    prod = prod * cols[names[word & 0xFFFF]][(i + rot) % n] % R
+                s = (s + prod) % R
+            acc = (acc * theta + s) % R
+        assert pc == len(w)
+        got.append(acc)
+    assert got == lr.compress_expressions([e.to_tuple() for e in exprs], cols, n, theta)
