@@ -106,6 +106,11 @@ class ResidentProver:
             omega_ext=d.extended_omega if extended else None, d_ext_out=[s[1] for s in slots] if extended else None,
             d_lagrange_out=[self.lagrange_slot(nm) for nm in names] if keep_lagrange else None)
 
+    def commit_device_columns(self, names):
+        """Commit round for Lagrange columns that are ALREADY in HBM under `lagrange_slot(name)` -- e.g. the five advice
+        columns the witness-expansion kernel wrote (h2agg_witness_expand_dev): the witness never visits host memory."""
+        return self._commit_resident(names)
+
     def _commit_resident(self, names):
         """Commit round for Lagrange columns the device produced itself (self.lag[name])."""
         slots = [self.slot(nm) for nm in names]

@@ -81,3 +81,37 @@ def test_multi_exp_22_points_realistic_w_g(ctx):
     cols = chip.expand(ctx)
     _compare(b, cols)
     chip.close()
+
+
+def test_witness_kernel_feeds_the_resident_prover(ctx):
+    """W -> K hand-off without host memory: the recorder's op list is expanded straight into the prover's resident
+    Lagrange slots, and round 1 (commit + lagrange_to_coeff + coeff_to_extended) runs from there."""
+    import oracle_binding as ob
+    from halo2_snark_aggregator_b200 import plonk
+    from halo2_snark_aggregator_b200.prover import ResidentProver
+    from util import domain_consts
+
+    chip = h2.B200EccChip()
+    b, _ = ws.run("multi_exp_1", chip)
+    k = 17
+    n = 1 << k
+    assert chip.rows() <= n
+    bases = ob.gen_bases(0x53525311, n)
+    sid = ctx.srs_register(bases)
+    pr = ResidentProver(ctx, plonk.aggregation_circuit_cs(), k, sid, sid)
+    names = [("advice", i) for i in range(5)]
+    chip.expand_dev(ctx, [pr.lagrange_slot(nm) for nm in names], n)
+    comms = pr.commit_device_columns(names)
+    d = domain_consts(k, pr.ext_k)
+    want_cols = E.advice_columns(b.ctx)
+    for c in (1, 4):
+        col = np.zeros((n, 4), dtype=np.uint64)
+        col[: b.ctx.offset] = ws.fr_mont_rows(want_cols[c])
+        col = np.ascontiguousarray(col).ravel()
+        assert np.array_equal(comms[c], ob.best_multiexp(col, bases)[:8])
+        co = ob.ifft(col.copy(), d["omega_inv"], d["n_inv"], k)
+        assert np.array_equal(ctx.d2h(pr.coeff[names[c]], 4 * n), co)
+        assert np.array_equal(ctx.d2h(pr.ext[names[c]], 4 << pr.ext_k), ob.coeff_to_extended(co, k, pr.ext_k, d["zeta"], d["omega_ext"]))
+    pr.close()
+    ctx.srs_release(sid)
+    chip.close()
