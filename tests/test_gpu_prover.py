@@ -354,3 +354,105 @@ def test_device_proof_openings_verify_against_a_trapdoor_srs(ctx):
         assert lhs == rhs, "opening at rotation %d" % rot
     ctx.srs_release(sid_g)
     ctx.srs_release(sid_gl)
+
+
+def _write_sections(path, sections):
+    with open(path, "wb") as f:
+        for tag, arr in sections:
+            a = np.ascontiguousarray(np.asarray(arr, dtype=np.uint64))
+            f.write(np.array([tag, a.size], dtype=np.uint64).tobytes())
+            f.write(a.tobytes())
+
+
+def test_cpp_resident_prover_equals_python_twin(ctx, tmp_path):
+    """include/h2agg_prover.hpp (the C++ host driver a compiled prover would link) against prover.py on the same
+    inputs: every commitment, evaluation and W point of the whole pipeline, bit for bit.  The Python twin is itself
+    held against the CPU oracles above."""
+    import os
+    import subprocess
+
+    k = 6
+    n = 1 << k
+    cs, lag = _valid_aggregation_witness(k, 8)
+    plan = plonk.build_quotient_plan(cs)
+    ext_k = cs.extended_k(k)
+    idx = plan.index
+    bf = cs.blinding_factors()
+    rng = random.Random(77)
+    g, gl = ob.gen_bases(0x7300, n), ob.gen_bases(0x7301, n)
+    theta, beta, gamma, y, x, v = [rng.randrange(R) for _ in range(6)]
+    w = qr.omega(k)
+    pk = [nm for nm in plan.columns if nm[0] in ("fixed", "sigma", "l0", "l_last", "l_active_row")]
+    wit = [("instance", 0)] + [("advice", i) for i in range(cs.num_advice)]
+    blinds2 = {nm: [rng.randrange(R) for _ in range(bf + 1)] for i in range(len(cs.lookups)) for nm in (("lookup_input", i), ("lookup_table", i))}
+    znames = [("perm_z", s) for s in range(cs.num_permutation_sets())] + [("lookup_z", i) for i in range(len(cs.lookups))]
+    blinds3 = {nm: [rng.randrange(R) for _ in range(bf)] for nm in znames}
+    random_poly = [rng.randrange(R) for _ in range(n)]
+    queries = create_proof_queries(cs)
+
+    # ---- Python twin
+    sid_g, sid_gl = ctx.srs_register(g), ctx.srs_register(gl)
+    pr = ResidentProver(ctx, cs, k, sid_gl, sid_g)
+    want = []
+    want.append(pr.commit_columns(pk, [qu.pack(lag[nm]) for nm in pk], keep_lagrange=True))
+    want.append(pr.commit_columns(wit, [qu.pack(lag[nm]) for nm in wit], keep_lagrange=True))
+    blind = lambda nm, rows: qu.pack((blinds2 if nm in blinds2 else blinds3)[nm])
+    want.append(pr.lookup_round(theta, blind))
+    want.append(pr.product_round(beta, gamma, blind))
+    want.append(pr.commit_coeff_columns([("random", 0)], [qu.pack(random_poly)]))
+    want.append(pr.quotient(y, beta, gamma, theta))
+    pr.fold_h(x)
+    want.append(pr.evaluate(queries, x))
+    want.append(pr.open(queries, x, v)[1])
+    pr.close()
+    ctx.srs_release(sid_g)
+    ctx.srs_release(sid_gl)
+    ctx.synchronize()
+    want = np.concatenate([np.asarray(a, dtype=np.uint64).ravel() for a in want])
+
+    # ---- the same job for the C++ driver
+    fr = plonk.fr_mont
+    w_ext = qr.omega(ext_k)
+    ids = dict(idx)
+    ids[("random", 0)] = len(plan.columns)
+    ids[("h", 0)] = len(plan.columns) + 1
+    expr_names = [nm for nm in plan.columns if nm[0] in ("fixed", "advice", "instance")]
+    eidx = {nm: i for i, nm in enumerate(expr_names)}
+    sec = [(1, [k, ext_k, bf, cs.chunk_len(), cs.degree() - 1, len(plan.columns)]),
+           (2, plan.words.astype(np.uint64)), (3, plan.consts),
+           (4, np.concatenate([fr(c) for c in (w, pow(w, -1, R), pow(n, -1, R), w_ext, pow(w_ext, -1, R), pow(1 << ext_k, -1, R),
+                                               plonk.ZETA, plonk.DELTA)])),
+           (5, np.concatenate([fr(t) for t in plonk.t_evaluations(k, ext_k)])),
+           (6, [idx[nm] for nm in expr_names])]
+    for i, (_, ins, tabs) in enumerate(cs.lookups):
+        pi, pt = plonk.ExpressionList(ins, eidx), plonk.ExpressionList(tabs, eidx)
+        sec += [(7, pi.words.astype(np.uint64)), (8, pi.consts), (9, pt.words.astype(np.uint64)), (10, pt.consts),
+                (11, [idx[("lookup_z", i)], idx[("lookup_input", i)], idx[("lookup_table", i)]])]
+    sec += [(12, [idx[c] for c in cs.permutation_columns]), (13, [idx[("sigma", j)] for j in range(len(cs.permutation_columns))]),
+            (14, [idx[("perm_z", s)] for s in range(cs.num_permutation_sets())]), (15, gl), (16, g), (17, [idx[nm] for nm in pk])]
+    sec += [(18, qu.pack(lag[nm])) for nm in pk]
+    sec += [(19, [idx[nm] for nm in wit])] + [(20, qu.pack(lag[nm])) for nm in wit]
+    sec += [(21, np.concatenate([fr(c) for c in (theta, beta, gamma, y, v)])),
+            (22, np.concatenate([fr(beta * pow(plonk.DELTA, s * cs.chunk_len(), R)) for s in range(cs.num_permutation_sets())]))]
+    for i in range(len(cs.lookups)):
+        sec += [(23, qu.pack(blinds2[("lookup_input", i)])), (23, qu.pack(blinds2[("lookup_table", i)]))]
+    sec += [(24, qu.pack(blinds3[nm])) for nm in znames]
+    sec += [(25, qu.pack(random_poly)), (26, fr(pow(x, n, R)))]
+    m64 = (1 << 64) - 1
+    sec.append((27, [val for nm, rot in queries for val in (ids[nm], rot & m64)]))
+    rots = list(dict.fromkeys(rot for _, rot in queries))
+    pts = []
+    for rot in rots:
+        pts.append(np.array([rot & m64], dtype=np.uint64))
+        pts.append(fr(x * pow(w, rot, R) % R))
+    sec.append((28, np.concatenate(pts)))
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    _write_sections(fin, sec)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "cpp", "prover_main")
+    assert os.path.exists(exe), "tests/cpp/prover_main is not built (python -c 'import __graft_entry__ as g; g.build()')"
+    r = subprocess.run([exe, fin, fout], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr + r.stdout
+    got = np.fromfile(fout, dtype=np.uint64)
+    assert got.size == want.size
+    assert np.array_equal(got, want)
