@@ -36,6 +36,7 @@ namespace h2agg {
 static constexpr int MSM_THREADS = 128;
 static constexpr uint32_t HOT_PIECES = 8;  // buckets cut into more pieces than this get a whole CTA
 static constexpr uint32_t WSUM_L = 4;      // arity of the window-sum tree
+static constexpr uint32_t WSUM_QUAD_MAX = 16384;  // levels with at most this many outputs use the four-lane kernel
 static constexpr uint32_t ENTRY_DUMMY = 0xffffffffu;  // padding slot of the sorted entry list
 
 struct MsmGeom {
@@ -511,6 +512,81 @@ __global__ void __launch_bounds__(MSM_THREADS) msm_wsum(const uint8_t* __restric
   acc.store(c_out + ob);
 }
 
+// The same node, spread over four adjacent lanes so that the serial chain of a level is 5 point operations instead of
+// 14 (the levels with few outputs are pure latency: ten of them cost ~1.3 ms per MSM, which is what bounds the small
+// configurations).  Lane roles within a quad:  R running sums (S3, +S2, +S1, +S0, then two doublings),
+// A  acc = r3 + r2 + r1 (fed by R through shuffles) and finally + csum,  C  csum = C3 + C2 + C1 + C0,  the 4th lane idles.
+// All lanes execute the same xyzz_add / xyzz_dbl calls in lockstep on role-selected operands.
+__device__ __forceinline__ G1Xyzz xyzz_shfl(const G1Xyzz& p, int src_lane) {
+  G1Xyzz r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    r.x.v[i] = __shfl_sync(0xffffffffu, p.x.v[i], src_lane);
+    r.y.v[i] = __shfl_sync(0xffffffffu, p.y.v[i], src_lane);
+    r.zz.v[i] = __shfl_sync(0xffffffffu, p.zz.v[i], src_lane);
+    r.zzz.v[i] = __shfl_sync(0xffffffffu, p.zzz.v[i], src_lane);
+  }
+  return r;
+}
+
+__global__ void __launch_bounds__(MSM_THREADS) msm_wsum_quad(const uint8_t* __restrict__ s_in, const uint8_t* __restrict__ c_in,
+                                                              uint32_t nsets, uint32_t m, uint8_t* __restrict__ s_out,
+                                                              uint8_t* __restrict__ c_out) {
+  static_assert(WSUM_L == 4, "the quad kernel is written for arity 4");
+  const uint32_t mo = (m + WSUM_L - 1) / WSUM_L;
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t gid = tid >> 2, role = tid & 3;  // 0 = R, 1 = A, 2 = C, 3 = idle
+  const int lane = threadIdx.x & 31, base_lane = lane & ~3;
+  const bool live = gid < nsets * mo;             // whole quads are live or not; dead quads still take part in the shuffles
+  const uint32_t w = live ? gid / mo : 0, t = live ? gid % mo : 0;
+  const uint32_t first = t * WSUM_L;
+  const uint32_t cnt = live ? min(WSUM_L, m - first) : 0;
+  const size_t base = ((size_t)w * m + first) * 128;
+  auto item = [&](const uint8_t* arr, uint32_t i) { return (live && i < cnt) ? G1Xyzz::load(arr + base + (size_t)i * 128) : G1Xyzz::identity(); };
+  // step 0: R holds S3, C holds C3; operands of the first addition
+  G1Xyzz acc = G1Xyzz::identity();
+  if (role == 0) acc = item(s_in, 3);
+  if (role == 2) acc = item(c_in, 3);
+  G1Xyzz r_prev = xyzz_shfl(acc, base_lane);      // r3, for A
+  // step 1: R += S2, C += C2
+  {
+    G1Xyzz y = G1Xyzz::identity();
+    if (role == 0) y = item(s_in, 2);
+    if (role == 2) y = item(c_in, 2);
+    xyzz_add(acc, y);
+  }
+  G1Xyzz r_cur = xyzz_shfl(acc, base_lane);       // r2
+  if (role == 1) acc = r_prev;                     // A starts at r3 ...
+  // step 2: R += S1, A += r2, C += C1
+  {
+    G1Xyzz y = G1Xyzz::identity();
+    if (role == 0) y = item(s_in, 1);
+    if (role == 1) y = r_cur;
+    if (role == 2) y = item(c_in, 1);
+    xyzz_add(acc, y);
+  }
+  r_cur = xyzz_shfl(acc, base_lane);              // r1
+  // step 3: R += S0, A += r1, C += C0
+  {
+    G1Xyzz y = G1Xyzz::identity();
+    if (role == 0) y = item(s_in, 0);
+    if (role == 1) y = r_cur;
+    if (role == 2) y = item(c_in, 0);
+    xyzz_add(acc, y);
+  }
+  G1Xyzz csum = xyzz_shfl(acc, base_lane + 2);
+  // step 4: A += csum; R doubles twice (4 * running)
+  if (role == 1) xyzz_add(acc, csum);
+  if (role == 0) {
+    acc = xyzz_dbl(acc);
+    acc = xyzz_dbl(acc);
+  }
+  if (!live) return;
+  const size_t ob = ((size_t)w * mo + t) * 128;
+  if (role == 0) acc.store(s_out + ob);
+  if (role == 1) acc.store(c_out + ob);
+}
+
 __device__ __forceinline__ void write_out160(const G1Xyzz& acc, uint8_t* out160) {
   G1Affine a = xyzz_to_affine(acc);
   bool id = acc.is_identity();
@@ -811,8 +887,12 @@ int msm_run(h2agg_ctx* ctx, cudaStream_t st, DevBuf& wsbuf, const MsmBases& base
   do {  // at least one level so that the final C holds sum (idx+1) * B_idx
     uint32_t mo = (m + WSUM_L - 1) / WSUM_L;
     uint32_t total = g.nsets * mo;
-    msm_wsum<<<(total + MSM_THREADS - 1) / MSM_THREADS, MSM_THREADS, 0, st>>>(s_in, c_in, g.nsets, m, lvl_s[flip],
-                                                                              lvl_c[flip]);
+    if (total <= WSUM_QUAD_MAX)  // few outputs: latency-bound, spread every node over four lanes
+      msm_wsum_quad<<<(4 * total + MSM_THREADS - 1) / MSM_THREADS, MSM_THREADS, 0, st>>>(s_in, c_in, g.nsets, m, lvl_s[flip],
+                                                                                      lvl_c[flip]);
+    else
+      msm_wsum<<<(total + MSM_THREADS - 1) / MSM_THREADS, MSM_THREADS, 0, st>>>(s_in, c_in, g.nsets, m, lvl_s[flip],
+                                                                                lvl_c[flip]);
     ctx->launches++;
     s_in = lvl_s[flip];
     c_in = lvl_c[flip];
