@@ -46,7 +46,8 @@ struct MsmGeom {
   uint32_t bpw;        // buckets per window = 2^(c-1)
   uint32_t nsets;      // bucket sets: nwin (plain) or 1 (table)
   uint32_t nb;         // nsets * bpw
-  uint32_t chunk;      // T
+  uint32_t chunk;      // T (upper bound; see msm_chunk_len)
+  uint32_t max_chunks; // launch size of msm_accumulate = capacity of the head / tail partial arrays
   uint32_t win_begin, win_end;
   uint32_t table;      // 1: entries index the precomputed table [w][srs_n]
   uint32_t srs_n;      // row length of the table
@@ -221,6 +222,17 @@ __global__ void __launch_bounds__(SCAN_THREADS) msm_scan3(const uint32_t* __rest
   }
 }
 
+// Chunk length actually used: g.chunk when the sorted list is long, shorter (down to MSM_MIN_CHUNK, a power of two) when
+// it is short -- a column of small cells has n entries instead of n * W, and with 128-entry chunks only a few hundred
+// threads per SM would share the work (latency-bound).  The number of chunks never exceeds the launch size
+// max_chunks = max_entries / g.chunk + 1.  Every kernel evaluates this on the same `total`.
+static constexpr uint32_t MSM_MIN_CHUNK = 16;
+__host__ __device__ __forceinline__ uint32_t msm_chunk_len(uint32_t total, uint32_t chunk, uint32_t max_chunks) {
+  uint32_t c = chunk;
+  while (c > MSM_MIN_CHUNK && (unsigned long long)(total + (c >> 1) - 1) / (c >> 1) <= (unsigned long long)max_chunks) c >>= 1;
+  return c;
+}
+
 // ---- K1: bucket accumulation over fixed-size chunks of the sorted entry list ---------------------------
 // Piece bookkeeping for a bucket [beg, end) cut by chunk boundaries (chunk t = [tT, (t+1)T)):
 //   entirely inside one chunk           -> written straight to bucket_sums[b]
@@ -241,10 +253,11 @@ __global__ void __launch_bounds__(MSM_THREADS) msm_accumulate(const uint8_t* __r
   const uint32_t* __restrict__ entries = paired ? nullptr : entries_in;
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t total = __ldg(offsets + g.nb) >> sh;
-  const unsigned long long start64 = (unsigned long long)t * g.chunk;
+  const uint32_t chunk = msm_chunk_len(total, g.chunk, g.max_chunks);
+  const unsigned long long start64 = (unsigned long long)t * chunk;
   if (start64 >= total) return;
   const uint32_t start = (uint32_t)start64;
-  const uint32_t end = (uint32_t)min((unsigned long long)total, start64 + g.chunk);
+  const uint32_t end = (uint32_t)min((unsigned long long)total, start64 + chunk);
   // largest b with offsets[b] <= start: the (non-empty) bucket that owns slot `start`
   uint32_t lo = 0, hi = g.nb;  // offsets[lo] <= start < offsets[hi]
   while (hi - lo > 1) {
@@ -430,6 +443,19 @@ __global__ void __launch_bounds__(MSM_THREADS) msm_pair_round(const uint8_t* __r
   }
 }
 
+// a whole XYZZ point from another lane of the warp
+__device__ __forceinline__ G1Xyzz xyzz_shfl(const G1Xyzz& p, int src_lane) {
+  G1Xyzz r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    r.x.v[i] = __shfl_sync(0xffffffffu, p.x.v[i], src_lane);
+    r.y.v[i] = __shfl_sync(0xffffffffu, p.y.v[i], src_lane);
+    r.zz.v[i] = __shfl_sync(0xffffffffu, p.zz.v[i], src_lane);
+    r.zzz.v[i] = __shfl_sync(0xffffffffu, p.zzz.v[i], src_lane);
+  }
+  return r;
+}
+
 // stitch buckets that straddle chunk boundaries; empty buckets -> identity; hot ones are queued
 __global__ void __launch_bounds__(MSM_THREADS) msm_fold(const uint32_t* __restrict__ offsets, MsmGeom g,
                                                          const uint8_t* __restrict__ head_part,
@@ -444,7 +470,8 @@ __global__ void __launch_bounds__(MSM_THREADS) msm_fold(const uint32_t* __restri
     G1Xyzz::identity().store(bucket_sums + (size_t)b * 128);
     return;
   }
-  uint32_t t0 = beg / g.chunk, t1 = (end - 1) / g.chunk;
+  const uint32_t chunk = msm_chunk_len(offsets[g.nb] >> sh, g.chunk, g.max_chunks);
+  uint32_t t0 = beg / chunk, t1 = (end - 1) / chunk;
   if (t0 == t1) return;  // complete, already written by its chunk
   if (t1 - t0 + 1 > HOT_PIECES) {
     hot_list[atomicAdd(hot_count, 1u)] = b;
@@ -455,34 +482,77 @@ __global__ void __launch_bounds__(MSM_THREADS) msm_fold(const uint32_t* __restri
   acc.store(bucket_sums + (size_t)b * 128);
 }
 
-__global__ void __launch_bounds__(256) msm_fold_hot(const uint32_t* __restrict__ offsets, MsmGeom g,
-                                                     const uint8_t* __restrict__ head_part,
-                                                     const uint8_t* __restrict__ tail_part,
-                                                     uint8_t* __restrict__ bucket_sums,
+// A hot bucket's pieces are cut into HOT_SPLIT slices, one CTA each (a column of small cells has a handful of very hot
+// buckets -- the value 1 -- and a single CTA walking 10^4 pieces would be the longest kernel of the MSM): stage 1 reduces
+// every slice into the head_part slot at the slice's start (in place: slices are disjoint), stage 2 adds the slice sums
+// and the bucket's first piece.
+static constexpr uint32_t HOT_SPLIT = 16;
+
+__device__ __forceinline__ void hot_slice(uint32_t t0, uint32_t t1, uint32_t j, uint32_t& lo, uint32_t& hi) {
+  const uint32_t pieces = t1 - t0;  // head pieces t0+1 .. t1
+  const uint32_t sz = (pieces + HOT_SPLIT - 1) / HOT_SPLIT;
+  lo = t0 + 1 + j * sz;
+  hi = min(lo + sz, t1 + 1);
+}
+
+__global__ void __launch_bounds__(256) msm_fold_hot(const uint32_t* __restrict__ offsets, MsmGeom g, uint8_t* head_part,
                                                      const uint32_t* __restrict__ hot_count,
                                                      const uint32_t* __restrict__ hot_list) {
   __shared__ uint4 sh[256 * 8];  // one XYZZ point (128 B) per thread
-  uint32_t nhot = *hot_count;
+  const uint32_t nhot = *hot_count;
   const uint32_t sh2 = (g.pair_rounds && offsets[g.nb] >= g.pair_gate) ? g.pair_rounds : 0;
-  for (uint32_t h = blockIdx.x; h < nhot; h += gridDim.x) {
-    uint32_t b = hot_list[h];
-    uint32_t beg = offsets[b] >> sh2, end = offsets[b + 1] >> sh2;
-    uint32_t t0 = beg / g.chunk, t1 = (end - 1) / g.chunk;
+  const uint32_t chunk = msm_chunk_len(offsets[g.nb] >> sh2, g.chunk, g.max_chunks);
+  for (uint32_t item = blockIdx.x; item < nhot * HOT_SPLIT; item += gridDim.x) {
+    const uint32_t b = hot_list[item / HOT_SPLIT];
+    const uint32_t beg = offsets[b] >> sh2, end = offsets[b + 1] >> sh2;
+    uint32_t lo, hi;
+    hot_slice(beg / chunk, (end - 1) / chunk, item % HOT_SPLIT, lo, hi);
+    if (lo >= hi) continue;  // CTA-uniform
     G1Xyzz acc = G1Xyzz::identity();
-    if (threadIdx.x == 0) acc = G1Xyzz::load(tail_part + (size_t)t0 * 128);
-    for (uint32_t t = t0 + 1 + threadIdx.x; t <= t1; t += blockDim.x) xyzz_add(acc, G1Xyzz::load(head_part + (size_t)t * 128));
+    for (uint32_t t = lo + threadIdx.x; t < hi; t += blockDim.x) xyzz_add(acc, G1Xyzz::load(head_part + (size_t)t * 128));
     acc.store(sh + threadIdx.x * 8);
     __syncthreads();
     for (uint32_t o = 128; o > 0; o >>= 1) {
-      if (threadIdx.x < o) {
+      if (threadIdx.x < o && threadIdx.x + o < hi - lo) {  // partners beyond the slice hold the identity
         G1Xyzz a = G1Xyzz::load(sh + threadIdx.x * 8);
         xyzz_add(a, G1Xyzz::load(sh + (threadIdx.x + o) * 8));
         a.store(sh + threadIdx.x * 8);
       }
       __syncthreads();
     }
-    if (threadIdx.x == 0) G1Xyzz::load(sh).store(bucket_sums + (size_t)b * 128);
+    if (threadIdx.x == 0) G1Xyzz::load(sh).store(head_part + (size_t)lo * 128);
     __syncthreads();
+  }
+}
+
+// stage 2: one warp per hot bucket; lane j < HOT_SPLIT holds slice j's sum, lane HOT_SPLIT the bucket's first piece
+__global__ void __launch_bounds__(128) msm_fold_hot2(const uint32_t* __restrict__ offsets, MsmGeom g,
+                                                      const uint8_t* __restrict__ head_part,
+                                                      const uint8_t* __restrict__ tail_part, uint8_t* __restrict__ bucket_sums,
+                                                      const uint32_t* __restrict__ hot_count,
+                                                      const uint32_t* __restrict__ hot_list) {
+  static_assert(HOT_SPLIT < 32, "slice sums + the first piece must fit one warp");
+  const uint32_t nhot = *hot_count;
+  const uint32_t sh2 = (g.pair_rounds && offsets[g.nb] >= g.pair_gate) ? g.pair_rounds : 0;
+  const uint32_t chunk = msm_chunk_len(offsets[g.nb] >> sh2, g.chunk, g.max_chunks);
+  const uint32_t lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t h = warp; h < nhot; h += nwarps) {  // warp-uniform
+    const uint32_t b = hot_list[h];
+    const uint32_t beg = offsets[b] >> sh2, end = offsets[b + 1] >> sh2;
+    const uint32_t t0 = beg / chunk, t1 = (end - 1) / chunk;
+    G1Xyzz acc = G1Xyzz::identity();
+    if (lane < HOT_SPLIT) {
+      uint32_t lo, hi;
+      hot_slice(t0, t1, lane, lo, hi);
+      if (lo < hi) acc = G1Xyzz::load(head_part + (size_t)lo * 128);
+    } else if (lane == HOT_SPLIT) {
+      acc = G1Xyzz::load(tail_part + (size_t)t0 * 128);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      G1Xyzz other = xyzz_shfl(acc, (int)((lane + o) & 31));  // wrapped reads are ignored below
+      if (lane + o < 32) xyzz_add(acc, other);
+    }
+    if (lane == 0) acc.store(bucket_sums + (size_t)b * 128);
   }
 }
 
@@ -517,18 +587,6 @@ __global__ void __launch_bounds__(MSM_THREADS) msm_wsum(const uint8_t* __restric
 // configurations).  Lane roles within a quad:  R running sums (S3, +S2, +S1, +S0, then two doublings),
 // A  acc = r3 + r2 + r1 (fed by R through shuffles) and finally + csum,  C  csum = C3 + C2 + C1 + C0,  the 4th lane idles.
 // All lanes execute the same xyzz_add / xyzz_dbl calls in lockstep on role-selected operands.
-__device__ __forceinline__ G1Xyzz xyzz_shfl(const G1Xyzz& p, int src_lane) {
-  G1Xyzz r;
-#pragma unroll
-  for (int i = 0; i < 8; i++) {
-    r.x.v[i] = __shfl_sync(0xffffffffu, p.x.v[i], src_lane);
-    r.y.v[i] = __shfl_sync(0xffffffffu, p.y.v[i], src_lane);
-    r.zz.v[i] = __shfl_sync(0xffffffffu, p.zz.v[i], src_lane);
-    r.zzz.v[i] = __shfl_sync(0xffffffffu, p.zzz.v[i], src_lane);
-  }
-  return r;
-}
-
 __global__ void __launch_bounds__(MSM_THREADS) msm_wsum_quad(const uint8_t* __restrict__ s_in, const uint8_t* __restrict__ c_in,
                                                               uint32_t nsets, uint32_t m, uint8_t* __restrict__ s_out,
                                                               uint8_t* __restrict__ c_out) {
@@ -793,6 +851,7 @@ int msm_run(h2agg_ctx* ctx, cudaStream_t st, DevBuf& wsbuf, const MsmBases& base
     return 1;
   }
   const size_t max_chunks = max_entries / g.chunk + 1;
+  g.max_chunks = (uint32_t)max_chunks;
   const uint32_t scan_blocks = (g.nb + 1 + SCAN_BLOCK - 1) / SCAN_BLOCK;
   if (scan_blocks > SCAN_BLOCK) {
     ctx->last_error = "msm: too many buckets for the scan";
@@ -874,8 +933,9 @@ int msm_run(h2agg_ctx* ctx, cudaStream_t st, DevBuf& wsbuf, const MsmBases& base
   ScopedKernelTimer t_red(ctx, KC_MSM_REDUCE, st);
   msm_fold<<<(g.nb + MSM_THREADS - 1) / MSM_THREADS, MSM_THREADS, 0, st>>>(offsets, g, head_part, tail_part, buckets,
                                                                             hot_count, hot_list);
-  msm_fold_hot<<<ctx->sm_count * 2, 256, 0, st>>>(offsets, g, head_part, tail_part, buckets, hot_count, hot_list);
-  ctx->launches += 2;
+  msm_fold_hot<<<ctx->sm_count * 2, 256, 0, st>>>(offsets, g, head_part, hot_count, hot_list);
+  msm_fold_hot2<<<16, 128, 0, st>>>(offsets, g, head_part, tail_part, buckets, hot_count, hot_list);
+  ctx->launches += 3;
   H2AGG_CUDA(ctx, cudaGetLastError());
 
   // window sums
