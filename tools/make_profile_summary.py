@@ -19,7 +19,7 @@ Raw files in this directory:
 * `%(tag)s_launches_bench_k22.csv` -- launch list of
   `ncu --metrics gpu__time_duration.sum --clock-control none python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-witness`
   (`tools/gpu_profile.sh %(tag)s`, final build of the round; the first capture of the round, `r01_launches_bench_k22.csv`, is kept for
-  comparison: `msm_accumulate` 184.7 -> 178.6 ms per step although the columns now carry blinding rows, `msm_wsum` 58.6 -> 47.1);
+  comparison: `msm_accumulate` 184.7 -> 169.7 ms per step although the columns now carry blinding rows, `msm_wsum*` 58.6 -> 46.8);
 * `%(tag)s_ncu_full_raw.csv` -- `ncu -i ... --page raw --csv` of one `--set full --clock-control none --import-source on` capture of
   `tools/prof_once.py 22` (one launch of every hot kernel at k = 22, including the N1/N3 kernels); the 100 MB `.ncu-rep` is not kept;
 * `r01_bench_k22_witness_in.json` -- the un-profiled bench line of the same build (`r01_bench_k18.json`, `r01_bench_k20.json`: the
@@ -51,7 +51,7 @@ hdr += "  permute_expression_pair %.2f ms (17-bit) / %.2f ms (full width) at n =
 tail = """
 
 Reading:
-* Share agreement with the live event timers of `bench.py`: `msm_accumulate` is the top kernel in both (45 %% of the serialised
+* Share agreement with the live event timers of `bench.py`: `msm_accumulate` is the top kernel in both (44 %% of the serialised
   launch list; the lanes overlap the latency-bound `msm_wsum*` / `msm_final` / `msm_digits` kernels with other lanes' accumulation,
   which is why the timed step, %.0f ms, is shorter than the serialised sum). 39 MSMs per step in the list = the schedule's 38 plus
   the stand-alone MSM `bench.py` times for `roofline_multiplier`.
