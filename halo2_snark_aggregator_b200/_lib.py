@@ -91,6 +91,7 @@ def load():
         "h2agg_commit_round_dev": (ci, [c_vp, u64, ctypes.POINTER(c_vp), sz, u32, c_vp, c_vp, c_vp, ctypes.POINTER(c_vp), u32, c_vp, c_vp, ctypes.POINTER(c_vp)]),
         "h2agg_compress_expressions_dev": (ci, [c_vp, c_vp, sz, ctypes.POINTER(c_vp), sz, c_vp, sz, u32, c_vp, c_vp]),
         "h2agg_lookup_product_dev": (ci, [c_vp, c_vp, c_vp, c_vp, c_vp, sz, c_vp, c_vp, c_vp]),
+        "h2agg_lookup_products_dev": (ci, [c_vp, sz, ctypes.POINTER(c_vp), ctypes.POINTER(c_vp), ctypes.POINTER(c_vp), ctypes.POINTER(c_vp), sz, c_vp, c_vp, ctypes.POINTER(c_vp)]),
         "h2agg_permutation_product_dev": (ci, [c_vp, ctypes.POINTER(c_vp), ctypes.POINTER(c_vp), sz, u32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
         "h2agg_ntt_fr_dev": (ci, [c_vp, c_vp, c_vp, c_vp, u32]),
         "h2agg_coeff_to_extended": (ci, [c_vp, c_vp, u32, u32, c_vp, c_vp, c_vp]),

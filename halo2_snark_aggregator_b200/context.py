@@ -234,6 +234,12 @@ class Context:
     def lookup_product_dev(self, d_a, d_s, d_ap, d_sp, n, beta, gamma, d_z):
         self.check(self.lib.h2agg_lookup_product_dev(self.h, c_vp(d_a), c_vp(d_s), c_vp(d_ap), c_vp(d_sp), n, _ptr(beta), _ptr(gamma), c_vp(d_z)))
 
+    def lookup_products_dev(self, d_a, d_s, d_ap, d_sp, n, beta, gamma, d_z):
+        """all lookups at once (lists of device pointers): lookup i runs on lane i mod 8"""
+        m = len(d_z)
+        arr = lambda v: (c_vp * m)(*v)
+        self.check(self.lib.h2agg_lookup_products_dev(self.h, m, arr(d_a), arr(d_s), arr(d_ap), arr(d_sp), n, _ptr(beta), _ptr(gamma), arr(d_z)))
+
     def permutation_product_dev(self, d_values, d_sigmas, k, omega, beta_delta_start, delta, beta, gamma, d_last_z, d_z):
         v = (c_vp * len(d_values))(*d_values)
         s = (c_vp * len(d_sigmas))(*d_sigmas)

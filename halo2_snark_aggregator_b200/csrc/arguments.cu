@@ -22,7 +22,8 @@
 
 namespace h2agg {
 
-int grand_product_dev(h2agg_ctx* ctx, const void* d_num, const void* d_den, size_t n, void* d_z);  // scan.cu
+int grand_product_dev(h2agg_ctx* ctx, const void* d_num, const void* d_den, size_t n, void* d_z, cudaStream_t st,
+                      DevBuf* ws);  // scan.cu
 
 static constexpr uint32_t ANOCONST = 0xffffffffu;
 
@@ -216,7 +217,51 @@ int h2agg_lookup_product_dev(h2agg_ctx* ctx, const void* d_input, const void* d_
       (const Fr*)d_input, (const Fr*)d_table, (const Fr*)d_permuted_input, (const Fr*)d_permuted_table, n, b, g, num, den);
   ctx->launches++;
   H2AGG_CUDA(ctx, cudaGetLastError());
-  return grand_product_dev(ctx, num, den, n, d_z);
+  return grand_product_dev(ctx, num, den, n, d_z, nullptr, nullptr);
+}
+
+// All lookups of a constraint system at once: lookup i runs on lane i % N_LANES with that lane's scratch, so the
+// latency chains of the grand products (an inversion and ~15 small launches each) overlap instead of queueing up.
+int h2agg_lookup_products_dev(h2agg_ctx* ctx, size_t n_lookups, const void* const* d_inputs, const void* const* d_tables,
+                              const void* const* d_permuted_inputs, const void* const* d_permuted_tables, size_t n,
+                              const uint64_t beta[4], const uint64_t gamma[4], void* const* d_z) {
+  if (!ctx) return 1;
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+  if (!beta || !gamma || (n_lookups && (!d_inputs || !d_tables || !d_permuted_inputs || !d_permuted_tables || !d_z))) {
+    ctx->last_error = "lookup_products: null argument";
+    return 1;
+  }
+  for (size_t i = 0; i < n_lookups; i++)
+    if (!d_inputs[i] || !d_tables[i] || !d_permuted_inputs[i] || !d_permuted_tables[i] || !d_z[i]) {
+      ctx->last_error = "lookup_products: null column pointer";
+      return 1;
+    }
+  if (n == 0 || n_lookups == 0) return 0;
+  H2AGG_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc = lanes_init(ctx);
+  if (rc) return rc;
+  Fr b, g;
+  memcpy(b.v, beta, 32);
+  memcpy(g.v, gamma, 32);
+  H2AGG_CUDA(ctx, cudaEventRecord(ctx->fork_ev, ctx->stream));
+  for (int l = 0; l < N_LANES; l++) H2AGG_CUDA(ctx, cudaStreamWaitEvent(ctx->lanes[l].st, ctx->fork_ev, 0));
+  for (size_t i = 0; i < n_lookups; i++) {
+    Lane& ln = ctx->lanes[i % N_LANES];
+    if ((rc = ensure(ctx, ln.args_ws, 2 * n * 32))) return rc;
+    Fr* num = (Fr*)ln.args_ws.p;
+    Fr* den = num + n;
+    lookup_num_den_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ln.st>>>((const Fr*)d_inputs[i], (const Fr*)d_tables[i],
+                                                                          (const Fr*)d_permuted_inputs[i],
+                                                                          (const Fr*)d_permuted_tables[i], n, b, g, num, den);
+    ctx->launches++;
+    H2AGG_CUDA(ctx, cudaGetLastError());
+    if ((rc = grand_product_dev(ctx, num, den, n, d_z[i], ln.st, &ln.scan_ws))) return rc;
+  }
+  for (int l = 0; l < N_LANES; l++) {
+    H2AGG_CUDA(ctx, cudaEventRecord(ctx->lanes[l].done, ctx->lanes[l].st));
+    H2AGG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->lanes[l].done, 0));
+  }
+  return 0;
 }
 
 int h2agg_permutation_product_dev(h2agg_ctx* ctx, const void* const* d_values, const void* const* d_sigmas, size_t n_cols,
@@ -255,7 +300,7 @@ int h2agg_permutation_product_dev(h2agg_ctx* ctx, const void* const* d_values, c
   perm_num_den_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(a);
   ctx->launches++;
   H2AGG_CUDA(ctx, cudaGetLastError());
-  if ((rc = grand_product_dev(ctx, a.num, a.den, n, d_z))) return rc;
+  if ((rc = grand_product_dev(ctx, a.num, a.den, n, d_z, nullptr, nullptr))) return rc;
   if (d_last_z) {
     scale_by_element_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((Fr*)d_z, n, (const Fr*)d_last_z);
     ctx->launches++;

@@ -100,6 +100,8 @@ void h2agg_destroy(h2agg_ctx* ctx) {
     cudaFree(ctx->lanes[i].io.p);
     cudaFree(ctx->lanes[i].io_out.p);
     cudaFree(ctx->lanes[i].ntt_tmp.p);
+    cudaFree(ctx->lanes[i].scan_ws.p);
+    cudaFree(ctx->lanes[i].args_ws.p);
     if (ctx->lanes[i].done) cudaEventDestroy(ctx->lanes[i].done);
     if (ctx->lanes[i].st) cudaStreamDestroy(ctx->lanes[i].st);
   }

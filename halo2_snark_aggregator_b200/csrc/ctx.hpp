@@ -50,6 +50,8 @@ struct Lane {
   DevBuf io;        // staging for host-pointer batches
   DevBuf io_out;    // NTT batches: result staging (coset transforms are out of place)
   DevBuf ntt_tmp;   // NTT ping-pong buffer of this lane
+  DevBuf scan_ws;   // grand-product scratch of this lane (batched lookup products)
+  DevBuf args_ws;   // numerators / denominators of this lane
   cudaEvent_t done = nullptr;
 };
 // Measured on B200 (k = 18 / 22 schedule): 3 lanes 47.7 / 337.5 ms, 6 lanes 40.2 / 331.7, 12 lanes 38.7 / 331.7 -- the

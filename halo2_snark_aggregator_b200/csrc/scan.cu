@@ -131,7 +131,8 @@ struct ScanWs {
   int levels;
 };
 
-static int scan_ws(h2agg_ctx* ctx, size_t n, ScanWs* w) {
+static int scan_ws(h2agg_ctx* ctx, size_t n, ScanWs* w, DevBuf* buf_in = nullptr) {
+  DevBuf& buf = buf_in ? *buf_in : ctx->scan_ws;
   size_t total = 2 * n + 64;
   size_t m = n;
   w->levels = 0;
@@ -141,9 +142,9 @@ static int scan_ws(h2agg_ctx* ctx, size_t n, ScanWs* w) {
     w->len[++w->levels] = m;
     total += 3 * m;
   }
-  int rc = ensure(ctx, ctx->scan_ws, total * 32 + 256);
+  int rc = ensure(ctx, buf, total * 32 + 256);
   if (rc) return rc;
-  Fr* p = (Fr*)ctx->scan_ws.p;
+  Fr* p = (Fr*)buf.p;
   w->a = p; p += n;
   w->b = p; p += n;
   w->spare = p; p += 64;
@@ -157,8 +158,9 @@ static int scan_ws(h2agg_ctx* ctx, size_t n, ScanWs* w) {
 }
 
 // out[i] = 1 / a[i] (zeros stay zero); `prefix0` is n elements of scratch for level 0; out may alias a
-static int batch_invert_levels(h2agg_ctx* ctx, const ScanWs& w, const Fr* a, size_t n, Fr* prefix0, Fr* out) {
-  cudaStream_t st = ctx->stream;
+static int batch_invert_levels(h2agg_ctx* ctx, const ScanWs& w, const Fr* a, size_t n, Fr* prefix0, Fr* out,
+                               cudaStream_t st_in = nullptr) {
+  cudaStream_t st = st_in ? st_in : ctx->stream;
   if (w.levels == 0) {
     inv_serial<<<1, 32, 0, st>>>(a, n, out);
     ctx->launches++;
@@ -197,14 +199,15 @@ int batch_invert_dev(h2agg_ctx* ctx, void* d_a, size_t n) {
 }
 
 // z[0] = 1, z[i+1] = z[i] * num[i] / den[i]
-int grand_product_dev(h2agg_ctx* ctx, const void* d_num, const void* d_den, size_t n, void* d_z) {
+// `st` / `ws`: run on another stream with its own scratch (lane-parallel batches); default = the context's
+int grand_product_dev(h2agg_ctx* ctx, const void* d_num, const void* d_den, size_t n, void* d_z, cudaStream_t st_in, DevBuf* ws) {
   if (n == 0) return 0;
   ScanWs w;
-  int rc = scan_ws(ctx, n, &w);
+  int rc = scan_ws(ctx, n, &w, ws);
   if (rc) return rc;
-  cudaStream_t st = ctx->stream;
+  cudaStream_t st = st_in ? st_in : ctx->stream;
   // 1. inverted denominators -> w.b (prefix scratch in w.a)
-  rc = batch_invert_levels(ctx, w, (const Fr*)d_den, n, w.a, w.b);
+  rc = batch_invert_levels(ctx, w, (const Fr*)d_den, n, w.a, w.b, st);
   if (rc) return rc;
   // 2. ratios -> w.a, chunk totals up the levels
   if (w.levels == 0) {  // n <= SCAN_L: one chunk forms the ratios, one thread scans them
@@ -271,7 +274,7 @@ int h2agg_grand_product_dev(h2agg_ctx* ctx, const void* d_num, const void* d_den
   std::lock_guard<std::recursive_mutex> lock(ctx->mu);
   if (!d_num || !d_den || !d_z) { ctx->last_error = "grand_product: null argument"; return 1; }
   H2AGG_CUDA(ctx, cudaSetDevice(ctx->device));
-  return grand_product_dev(ctx, d_num, d_den, n, d_z);
+  return grand_product_dev(ctx, d_num, d_den, n, d_z, nullptr, nullptr);
 }
 
 int h2agg_grand_product(h2agg_ctx* ctx, const uint64_t* num, const uint64_t* den, size_t n, uint64_t* z) {
@@ -288,7 +291,7 @@ int h2agg_grand_product(h2agg_ctx* ctx, const uint64_t* num, const uint64_t* den
   uint8_t* d_den = d_num + n * 32;
   H2AGG_CUDA(ctx, cudaMemcpyAsync(d_num, num, n * 32, cudaMemcpyHostToDevice, ctx->stream));
   H2AGG_CUDA(ctx, cudaMemcpyAsync(d_den, den, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-  rc = grand_product_dev(ctx, d_num, d_den, n, ctx->io_b.p);
+  rc = grand_product_dev(ctx, d_num, d_den, n, ctx->io_b.p, nullptr, nullptr);
   if (rc) return rc;
   H2AGG_CUDA(ctx, cudaMemcpyAsync(z, ctx->io_b.p, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
   H2AGG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

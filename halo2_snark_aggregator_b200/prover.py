@@ -172,11 +172,14 @@ class ResidentProver:
             last = z + 32 * u
             out_names.append(("perm_z", s))
         self._mark("products.permutation")
-        for i in range(len(self.cs.lookups)):
-            z = self.lagrange_slot(("lookup_z", i))
-            self.ctx.lookup_product_dev(self.lag[("lookup_input_compressed", i)], self.lag[("lookup_table_compressed", i)],
-                                        self.lag[("lookup_input", i)], self.lag[("lookup_table", i)], self.n, b, g, z)
-            self.ctx.h2d(z + 32 * (self.n - bf), np.ascontiguousarray(blind(("lookup_z", i), bf)))
+        L = range(len(self.cs.lookups))
+        zs = [self.lagrange_slot(("lookup_z", i)) for i in L]
+        if zs:  # all lookup products in one call: their latency chains overlap on the lanes
+            self.ctx.lookup_products_dev([self.lag[("lookup_input_compressed", i)] for i in L], [self.lag[("lookup_table_compressed", i)] for i in L],
+                                         [self.lag[("lookup_input", i)] for i in L], [self.lag[("lookup_table", i)] for i in L],
+                                         self.n, b, g, zs)
+        for i in L:
+            self.ctx.h2d(zs[i] + 32 * (self.n - bf), np.ascontiguousarray(blind(("lookup_z", i), bf)))
             out_names.append(("lookup_z", i))
         self._mark("products.lookup")
         out = self._commit_resident(out_names)

@@ -225,6 +225,11 @@ int h2agg_compress_expressions_dev(h2agg_ctx* ctx, const uint32_t* exprs, size_t
 int h2agg_lookup_product_dev(h2agg_ctx* ctx, const void* d_input, const void* d_table, const void* d_permuted_input,
                              const void* d_permuted_table, size_t n, const uint64_t beta[4], const uint64_t gamma[4],
                              void* d_z);
+/* lookup_product for all lookups of a constraint system in one call (lookup i on lane i mod 8: the latency chains of
+ * the grand products overlap); same results as n_lookups calls of h2agg_lookup_product_dev. */
+int h2agg_lookup_products_dev(h2agg_ctx* ctx, size_t n_lookups, const void* const* d_inputs, const void* const* d_tables,
+                              const void* const* d_permuted_inputs, const void* const* d_permuted_tables, size_t n,
+                              const uint64_t beta[4], const uint64_t gamma[4], void* const* d_z);
 int h2agg_permutation_product_dev(h2agg_ctx* ctx, const void* const* d_values, const void* const* d_sigmas, size_t n_cols,
                                   uint32_t k, const uint64_t omega[4], const uint64_t beta_delta_start[4],
                                   const uint64_t delta[4], const uint64_t beta[4], const uint64_t gamma[4],

@@ -154,13 +154,21 @@ class ResidentProver {
       last = (const uint8_t*)z + 32 * u;
       out_ids.push_back(s_.perm_z[st]);
     }
+    std::vector<const void*> in_a, in_s, in_ap, in_sp;
+    std::vector<void*> zs;
     for (size_t i = 0; i < L; i++) {
       const ProverShape::Lookup& lk = s_.lookups[i];
-      void* z = lagrange(lk.z_col);
-      c_.check(h2agg_lookup_product_dev(c_.raw(), scratch(key_compressed(i, 0), n_ * 32), scratch(key_compressed(i, 1), n_ * 32),
-                                        lagrange(lk.input_col), lagrange(lk.table_col), n_, beta.l, gamma.l, z));
-      put_tail(z, blinds[sets + i], bf);
-      out_ids.push_back(lk.z_col);
+      in_a.push_back(scratch(key_compressed(i, 0), n_ * 32));
+      in_s.push_back(scratch(key_compressed(i, 1), n_ * 32));
+      in_ap.push_back(lagrange(lk.input_col));
+      in_sp.push_back(lagrange(lk.table_col));
+      zs.push_back(lagrange(lk.z_col));
+    }
+    // all lookup products in one call: their latency chains overlap on the lanes
+    c_.check(h2agg_lookup_products_dev(c_.raw(), L, in_a.data(), in_s.data(), in_ap.data(), in_sp.data(), n_, beta.l, gamma.l, zs.data()));
+    for (size_t i = 0; i < L; i++) {
+      put_tail(zs[i], blinds[sets + i], bf);
+      out_ids.push_back(s_.lookups[i].z_col);
     }
     return commit_device_columns(out_ids);
   }

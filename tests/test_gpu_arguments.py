@@ -130,3 +130,24 @@ def test_lookup_argument_full_size_telescopes(ctx):
         assert ap[i] == sp[i] or ap[i] == ap[i - 1]
     for p in (d_a, d_s, d_ap, d_sp, d_z):
         ctx.dev_free(p)
+
+
+@pytest.mark.parametrize("n,m", [(64, 1), (1000, 3), (4096, 11)])
+def test_lookup_products_batch_equals_single_calls(ctx, n, m):
+    """h2agg_lookup_products_dev (lookup i on lane i mod 8, private scratch per lane) == m single calls == the oracle;
+    m = 11 makes lanes carry two products each."""
+    rng = random.Random(n + m)
+    beta, gamma = rng.randrange(R), rng.randrange(R)
+    cols = [[[rng.randrange(R) for _ in range(n)] for _ in range(4)] for _ in range(m)]
+    d = [[_upload(ctx, v) for v in c] for c in cols]
+    dz = [ctx.dev_alloc(n * 32) for _ in range(m)]
+    for _ in range(2):   # twice: the second round reuses the lanes' scratch while nothing else is pending
+        ctx.lookup_products_dev([c[0] for c in d], [c[1] for c in d], [c[2] for c in d], [c[3] for c in d], n, fr_limbs(beta),
+                                fr_limbs(gamma), dz)
+        for i in range(m):
+            assert qu.unpack(ctx.d2h(dz[i], 4 * n)) == lr.lookup_product(*cols[i], beta, gamma), i
+    for c in d:
+        for p in c:
+            ctx.dev_free(p)
+    for p in dz:
+        ctx.dev_free(p)
