@@ -749,8 +749,8 @@ def main():
             "e2e": e2e_res if e2e_res is not None else e2e, "e2e_host_pointer_abi": e2e if e2e_res is not None else None,
             "gpu_launches": int(launches), "clocks": clock_info,
             "roofline": {"kernel": "msm_accumulate", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": 7353400000, "peak_source": peak_src,
-                         "traffic_note": "dram__bytes_read+write of one msm_accumulate launch on a uniform 2^22 column in table mode (profiles/r01_ncu_summary.md): the gather of 54.5 M precomputed 64-byte points is by design",
+                         "frac": (achieved / peak) if achieved else None, "traffic": 7366600000, "peak_source": peak_src,
+                         "traffic_note": "dram__bytes_read+write of one msm_accumulate launch on a uniform 2^22 column in table mode (profiles/r01e_ncu_full_raw.csv, summarised in profiles/r01_ncu_summary.md): the gather of 54.5 M precomputed 64-byte points is by design",
                          "algorithmic_bytes_per_launch": msm_bytes, "avg_launch_ms": (acc_ms / acc_n) if acc_n else None,
                          "launches_timed": acc_n,
                          "launch_ms_alone_uniform_column": acc_alone_ms,
