@@ -111,6 +111,44 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def cpu_between_the_schedule(ob, k, cores):
+    """What create_proof does BETWEEN the schedule's MSMs and NTTs, on the CPU port: evaluate_h, the lookup sorts, the
+    grand products, the evaluation round and the Kate divisions, timed on bounded samples (2^min(k,16) rows) and scaled
+    linearly in the row count.  Informational: the b200 arm's e2e includes this work, the schedule metric does not."""
+    import numpy as np
+    from halo2_snark_aggregator_b200 import plonk
+
+    ks = min(k, 16)
+    n_s, scale = 1 << ks, float(1 << (k - min(k, 16)))
+    cs = plonk.aggregation_circuit_cs()
+    plan = plonk.build_quotient_plan(cs)
+    ext_ks = cs.extended_k(ks)
+    cols = [ob.gen_scalars(0x9100 + i, 0, 1 << ext_ks) for i in range(len(plan.columns))]
+    fm = plonk.fr_mont
+    w_ext = pow(plonk.ROOT_OF_UNITY, 1 << (28 - ext_ks), plonk.R_MOD)
+    t_ev = np.concatenate([fm(v) for v in plonk.t_evaluations(ks, ext_ks)])
+    per = {}
+    t0 = time.perf_counter()
+    ob.evaluate_h(plan.words, plan.consts, cols, ks, ext_ks, fm(3 ** 100), fm(5 ** 90), fm(7 ** 80), fm(11 ** 70), fm(w_ext),
+                  fm(plonk.ZETA), fm(plonk.DELTA), t_ev, cores)
+    per["evaluate_h"] = (time.perf_counter() - t0) * scale
+    del cols
+    a = ob.gen_scalars(0x8801, 3, n_s)
+    tab = np.ascontiguousarray(a.reshape(n_s, 4)[::-1]).ravel()
+    t0 = time.perf_counter()
+    rc, pa, ps = ob.permute_expression_pair(a, tab)
+    per["permute_expression_pair"] = (time.perf_counter() - t0) * scale
+    u = ob.gen_scalars(0x8802, 0, n_s)
+    v = ob.gen_scalars(0x8803, 0, n_s)
+    t0 = time.perf_counter(); ob.grand_product(u, v); per["grand_product"] = (time.perf_counter() - t0) * scale
+    pt = ob.gen_scalars(0x8804, 0, 1)
+    t0 = time.perf_counter(); ob.eval_polynomial(u, pt); per["eval_polynomial"] = (time.perf_counter() - t0) * scale
+    t0 = time.perf_counter(); ob.kate_division(u, pt); per["kate_division"] = (time.perf_counter() - t0) * scale
+    counts = {"evaluate_h": 1, "permute_expression_pair": 7, "grand_product": 9, "eval_polynomial": 70, "kate_division": 4}
+    return {"per_unit_s": per, "counts": counts, "total_s": sum(per[key] * counts[key] for key in counts),
+            "sample": "2^%d rows per unit, scaled x%g; evaluate_h on %d threads, the other units single-threaded as restated" % (ks, scale, cores)}
+
+
 def run_reference_arm(args, rank, world):
     """CPU restatement of the reference's path on the host cores (rank 0 only)."""
     if rank != 0:
@@ -155,6 +193,11 @@ def run_reference_arm(args, rank, world):
     sched = sum(per[key] * counts[key] for key in counts)
     sample = ("per step: 4 MSM(2^%d) one per scalar kind + 1 iNTT(n) + 1 coset-NTT(n->4n) + 1 ext-iNTT(4n), "
               "scaled to the 38 MSM + 59 NTT schedule by unit counts %s" % (k, json.dumps(counts)))
+    between = None
+    try:  # informational only: never let it take the line down
+        between = cpu_between_the_schedule(ob, k, cores)
+    except Exception as e:  # pragma: no cover
+        between = {"error": repr(e)}
     line = {
         "impl": "reference", "metric": "aggregation proving time (s) at k=%d (prover-schedule replay: 38 MSM + 59 NTT)" % k,
         "value": sched, "unit": "s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -162,6 +205,8 @@ def run_reference_arm(args, rank, world):
         "data": "synthetic", "config": {"workload": "aggregation-circuit prover schedule, k=%d, 1 proof" % k, "k": k},
         "cpu_baseline": {"value": sched, "unit": "s", "cores": cores, "kind": "port", "sample": sample,
                          "per_unit_s": per, "sample_wall_s": wall,
+                         "between_the_schedule": between,
+                         "full_pipeline_estimate_s": (sched + between["total_s"]) if between and "total_s" in between else None,
                          "note": "C++ restatement of halo2 (v2022_09_10) best_multiexp/best_fft/EvaluationDomain; the Rust reference cannot be built here"},
         "e2e": {"value": sched, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -715,7 +760,13 @@ def main():
         t0 = time.perf_counter(); ob.extended_to_coeff(e, k + 2, d["omega_ext_inv"], d["ext_n_inv"], d["zeta"], 3 << k, cores); per["ext_intt"] = time.perf_counter() - t0
         counts = {"msm0": 18, "msm1": 5, "msm2": 1, "msm3": 14, "intt": 29, "coset": 29, "ext_intt": 1}
         sched = sum(per[key] * counts[key] for key in counts)
+        try:  # informational only: never let it take the line down
+            between = cpu_between_the_schedule(ob, k, cores)
+        except Exception as e:  # pragma: no cover
+            between = {"error": repr(e)}
         cpu = {"value": sched, "unit": "s", "cores": cores, "kind": "port",
+               "between_the_schedule": between,
+               "full_pipeline_estimate_s": (sched + between["total_s"]) if "total_s" in between else None,
                "sample": "one MSM(2^%d) per scalar kind + 1 iNTT(n) + 1 coset-NTT(n->4n) + 1 ext-iNTT(4n) timed once, scaled by the schedule's unit counts %s" % (k, json.dumps(counts)),
                "per_unit_s": per, "gpu_matches_oracle_on_sampled_msms": parity,
                "note": "C++ restatement of halo2 (v2022_09_10) CPU algorithms, not the Rust reference (no cargo/rustc in this image)"}
