@@ -36,7 +36,6 @@ class ResidentProver:
         self.srs_lagrange, self.srs_g = srs_lagrange, srs_g
         self.coeff, self.ext, self.lag = {}, {}, {}      # column name -> device pointer (coefficient / extended / Lagrange form)
         self._owned = []
-        self._t = np.concatenate([plonk.fr_mont(v) for v in plonk.t_evaluations(k, self.ext_k)])
         self.n_pieces = self.dom.quotient_poly_degree
         self._scratch = {}
 

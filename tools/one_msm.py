@@ -1,5 +1,9 @@
-import os, sys
-sys.path.insert(0, "/root/repo")
+"""One table-mode MSM of a 17-bit column at k = 22 (twice), for `ncu --metrics gpu__time_duration.sum -k regex:msm_` captures
+of the per-launch times of the reduce phase."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import halo2_snark_aggregator_b200 as h2
 k = 22; n = 1 << k
 ctx = h2.Context(0)
