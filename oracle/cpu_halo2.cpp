@@ -782,6 +782,95 @@ int oracle_permute_expression_pair(const uint64_t* input, const uint64_t* table,
   return 0;
 }
 
+// halo2_proofs plonk/lookup/prover.rs compress_expressions: each expression of the list (word layout of
+// include/h2agg.h: { n_exprs, POLY x n_exprs }) is evaluated on the Lagrange domain -- rotation r of row i reads row
+// (i + r) mod n -- and folded acc = acc * theta + e.  Row-parallel like halo2's `parallelize`.
+void oracle_compress_expressions(const uint32_t* exprs, const uint64_t* const* cols, const uint64_t* consts, uint32_t k,
+                                 const uint64_t* theta_, uint64_t* out, unsigned threads) {
+  const size_t n = (size_t)1 << k;
+  Fr theta;
+  memcpy(theta.v, theta_, 32);
+  const Fr one = Fr::one();
+  parallelize(n, threads, [&](size_t lo, size_t hi) {
+    for (size_t idx = lo; idx < hi; idx++) {
+      size_t pc = 0;
+      const uint32_t ne = exprs[pc++];
+      Fr acc = Fr::zero();
+      for (uint32_t e = 0; e < ne; e++) {
+        const uint32_t nt = exprs[pc++];
+        Fr sum = Fr::zero();
+        for (uint32_t t = 0; t < nt; t++) {
+          const uint32_t ci = exprs[pc++], nf = exprs[pc++];
+          Fr prod = one;
+          if (ci != 0xffffffffu) memcpy(prod.v, consts + 4 * (size_t)ci, 32);
+          for (uint32_t f = 0; f < nf; f++) {
+            const uint32_t w = exprs[pc++];
+            const size_t r = (size_t)(((int64_t)idx + (int16_t)(w >> 16)) & (int64_t)(n - 1));
+            Fr v;
+            memcpy(v.v, cols[w & 0xffffu] + 4 * r, 32);
+            prod = mul(prod, v);
+          }
+          sum = add(sum, prod);
+        }
+        acc = add(mul(acc, theta), sum);
+      }
+      memcpy(out + 4 * idx, acc.v, 32);
+    }
+  });
+}
+
+// halo2_proofs plonk/lookup/prover.rs commit_product before blinding: denominators (a' + beta)(s' + gamma) batch-inverted,
+// times (a + beta)(s + gamma), running product from 1; n values.
+void oracle_lookup_product(const uint64_t* A, const uint64_t* S, const uint64_t* Ap, const uint64_t* Sp, size_t n,
+                           const uint64_t* beta_, const uint64_t* gamma_, uint64_t* z) {
+  Fr beta, gamma;
+  memcpy(beta.v, beta_, 32);
+  memcpy(gamma.v, gamma_, 32);
+  std::vector<uint64_t> num(4 * n), den(4 * n);
+  auto at = [](const uint64_t* p, size_t i) { Fr v; memcpy(v.v, p + 4 * i, 32); return v; };
+  for (size_t i = 0; i < n; i++) {
+    Fr d = mul(add(at(Ap, i), beta), add(at(Sp, i), gamma));
+    Fr m = mul(add(at(A, i), beta), add(at(S, i), gamma));
+    memcpy(den.data() + 4 * i, d.v, 32);
+    memcpy(num.data() + 4 * i, m.v, 32);
+  }
+  oracle_grand_product(num.data(), den.data(), n, z);
+}
+
+// halo2_proofs plonk/permutation/prover.rs commit for ONE column set before blinding: modified_values = prod_j
+// (v_j + beta sigma_j + gamma), batch-inverted, times prod_j (v_j + delta^j' omega^i beta + gamma) with deltaomega stepping
+// by omega per row and by delta per column; z[0] = last_z.
+void oracle_permutation_product(const uint64_t* const* values, const uint64_t* const* sigmas, size_t n_cols, uint32_t k,
+                                const uint64_t* omega_, const uint64_t* beta_delta_start_, const uint64_t* delta_,
+                                const uint64_t* beta_, const uint64_t* gamma_, const uint64_t* last_z, uint64_t* z) {
+  const size_t n = (size_t)1 << k;
+  Fr omega, bds, delta, beta, gamma;
+  memcpy(omega.v, omega_, 32); memcpy(bds.v, beta_delta_start_, 32); memcpy(delta.v, delta_, 32);
+  memcpy(beta.v, beta_, 32); memcpy(gamma.v, gamma_, 32);
+  std::vector<Fr> num(n, Fr::one()), den(n, Fr::one());
+  auto at = [](const uint64_t* p, size_t i) { Fr v; memcpy(v.v, p + 4 * i, 32); return v; };
+  for (size_t j = 0; j < n_cols; j++)
+    for (size_t i = 0; i < n; i++) den[i] = mul(den[i], add(add(mul(beta, at(sigmas[j], i)), gamma), at(values[j], i)));
+  Fr col_start = bds;  // beta * delta^(first + j)
+  for (size_t j = 0; j < n_cols; j++) {
+    Fr deltaomega = col_start;
+    for (size_t i = 0; i < n; i++) {
+      num[i] = mul(num[i], add(add(deltaomega, gamma), at(values[j], i)));
+      deltaomega = mul(deltaomega, omega);
+    }
+    col_start = mul(col_start, delta);
+  }
+  oracle_grand_product((const uint64_t*)num.data(), (const uint64_t*)den.data(), n, z);
+  if (last_z) {
+    Fr lz;
+    memcpy(lz.v, last_z, 32);
+    for (size_t i = 0; i < n; i++) {
+      Fr v = mul(at(z, i), lz);
+      memcpy(z + 4 * i, v.v, 32);
+    }
+  }
+}
+
 // halo2_proofs plonk/evaluation.rs Evaluator::evaluate_h (+ divide_by_vanishing_poly when t_evals != null), driven
 // by the same word program as the device (layout: include/h2agg.h).  Follows halo2's CPU structure: the rows are
 // split over threads (`parallelize`), each chunk starts beta_term = omega_ext^start and steps it per row.  Formulas

@@ -56,6 +56,9 @@ def oracle():
         lib.oracle_evaluate_h.argtypes = [c_vp, sz, ctypes.POINTER(c_vp), c_vp, u32, u32] + [c_vp] * 8 + [sz, c_vp, ui]
         lib.oracle_permute_expression_pair.argtypes = [c_vp, c_vp, sz, c_vp, c_vp]
         lib.oracle_permute_expression_pair.restype = ci
+        lib.oracle_compress_expressions.argtypes = [c_vp, ctypes.POINTER(c_vp), c_vp, u32, c_vp, c_vp, ui]
+        lib.oracle_lookup_product.argtypes = [c_vp] * 4 + [sz, c_vp, c_vp, c_vp]
+        lib.oracle_permutation_product.argtypes = [ctypes.POINTER(c_vp), ctypes.POINTER(c_vp), sz, u32] + [c_vp] * 7
         lib.oracle_hw_threads.restype = ui
         _o = lib
     return _o
@@ -179,6 +182,28 @@ def permute_expression_pair(inp, tab):
     a, b = np.zeros_like(inp), np.zeros_like(tab)
     rc = oracle().oracle_permute_expression_pair(P(inp), P(tab), inp.size // 4, P(a), P(b))
     return rc, a, b
+
+
+def compress_expressions(words, consts, cols, k, theta, nthreads=None):
+    out = np.empty(4 << k, dtype=np.uint64)
+    arr = (c_vp * len(cols))(*[c.ctypes.data for c in cols])
+    oracle().oracle_compress_expressions(P(words), arr, P(consts) if consts.size else None, k, P(theta), P(out), nthreads or threads())
+    return out
+
+
+def lookup_product(A, S, Ap, Sp, beta, gamma):
+    z = np.empty_like(A)
+    oracle().oracle_lookup_product(P(A), P(S), P(Ap), P(Sp), A.size // 4, P(beta), P(gamma), P(z))
+    return z
+
+
+def permutation_product(values, sigmas, k, omega, beta_delta_start, delta, beta, gamma, last_z=None):
+    z = np.empty(4 << k, dtype=np.uint64)
+    v = (c_vp * len(values))(*[c.ctypes.data for c in values])
+    s = (c_vp * len(sigmas))(*[c.ctypes.data for c in sigmas])
+    oracle().oracle_permutation_product(v, s, len(values), k, P(omega), P(beta_delta_start), P(delta), P(beta), P(gamma),
+                                        P(last_z) if last_z is not None else None, P(z))
+    return z
 
 
 def evaluate_h(plan_words, consts, ext_cols, k, ext_k, y, beta, gamma, theta, omega_ext, zeta, delta, t_evals=None,

@@ -216,3 +216,43 @@ def test_lookup_and_permutation_product_restatements_telescope():
     for s in range(2):
         last = lr.permutation_product(values[s * chunk:(s + 1) * chunk], sig[s * chunk:(s + 1) * chunk], k, w, beta, gamma, s * chunk, last)[u]
     assert last != 1
+
+
+def test_cpp_argument_restatements_match_the_python_ones():
+    """oracle/cpu_halo2.cpp compress_expressions / lookup_product / permutation_product (the ones that scale to 2^22 rows)
+    == oracle/py/lookup_ref.py on big ints."""
+    import random
+
+    import lookup_ref as lr
+    import quotient_ref as qr
+    import quotient_util as qu
+    from halo2_snark_aggregator_b200 import plonk
+
+    R = lr.R
+    rng = random.Random(41)
+    E = plonk.Expression
+    for k in (1, 5):
+        n = 1 << k
+        names = [("advice", 0), ("advice", 1), ("fixed", 0), ("instance", 0)]
+        cols = {nm: [rng.randrange(R) for _ in range(n)] for nm in names}
+        index = {nm: i for i, nm in enumerate(names)}
+        exprs = [E.advice(0) * E.fixed(0), E.advice(1, 1) * 3 + E.constant(9), E.instance(0, -2) * E.advice(0) * E.advice(0, 1) - E.fixed(0)]
+        prog = plonk.ExpressionList(exprs, index)
+        theta = rng.randrange(R)
+        got = ob.compress_expressions(prog.words, prog.consts, [qu.pack(cols[nm]) for nm in names], k, qu.pack([theta]), 3)
+        assert qu.unpack(got) == lr.compress_expressions([e.to_tuple() for e in exprs], cols, n, theta)
+    for n in (1, 2, 65, 300):
+        A, S, Ap, Sp = ([rng.randrange(R) for _ in range(n)] for _ in range(4))
+        beta, gamma = rng.randrange(R), rng.randrange(R)
+        got = ob.lookup_product(*(qu.pack(v) for v in (A, S, Ap, Sp)), qu.pack([beta]), qu.pack([gamma]))
+        assert qu.unpack(got) == lr.lookup_product(A, S, Ap, Sp, beta, gamma)
+    for k, m, first, lz in ((1, 1, 0, None), (4, 3, 3, 12345), (7, 2, 0, None)):
+        n = 1 << k
+        values = [[rng.randrange(R) for _ in range(n)] for _ in range(m)]
+        sigmas = [[rng.randrange(R) for _ in range(n)] for _ in range(m)]
+        beta, gamma = rng.randrange(R), rng.randrange(R)
+        w = qr.omega(k)
+        got = ob.permutation_product([qu.pack(v) for v in values], [qu.pack(v) for v in sigmas], k, qu.pack([w]),
+                                     qu.pack([beta * pow(lr.DELTA, first, R) % R]), qu.pack([lr.DELTA]), qu.pack([beta]), qu.pack([gamma]),
+                                     qu.pack([lz]) if lz is not None else None)
+        assert qu.unpack(got) == lr.permutation_product(values, sigmas, k, w, beta, gamma, first, lz if lz is not None else 1)
