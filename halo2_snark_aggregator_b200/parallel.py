@@ -80,3 +80,91 @@ def plan_phase(msm_costs, other_costs, world, n_windows):
         plan.append((u, r, None))
         load[r] += other_costs[u]
     return plan
+
+
+# ---- row-sharded quotient (groundwork for the multi-GPU resident prover) --------------------------
+# evaluate_h is pointwise in the coset row, except that a query with rotation r reads row idx + r * 2^(ext_k - k).  If
+# rank g owns the rows [begin, end) of h it needs, of EVERY column, those rows plus a halo of max|negative rotation| rows
+# below and max positive rotation rows above (wrapping around the domain).  The columns are produced column-parallel (each
+# by the rank that committed it), so one exchange of row slices precedes the quotient.
+
+
+def quotient_row_shards(ext_n, world):
+    """Contiguous row ranges [begin, end) of the extended coset, one per rank."""
+    return [(ext_n * g // world, ext_n * (g + 1) // world) for g in range(world)]
+
+
+def rotation_halo(rotations, rot_scale):
+    """(rows below, rows above) a shard needs for the given query rotations; rot_scale = 2^(ext_k - k)."""
+    lo = max([0] + [-r for r in rotations]) * rot_scale
+    hi = max([0] + [r for r in rotations]) * rot_scale
+    return lo, hi
+
+
+def constraint_system_rotations(cs):
+    """Every rotation evaluate_h applies for a plonk.ConstraintSystem: the expressions' queries, z(omega X), a'(omega^-1 X)
+    and the permutation argument's z(omega^last X)."""
+    rots = {0}
+    exprs = [p for _, polys in cs.gates for p in polys]
+    for _, ins, tabs in cs.lookups:
+        exprs += ins + tabs
+    for e in exprs:
+        rots |= {q[2] for q in e.queries()}
+    if cs.lookups:
+        rots |= {1, -1}
+    if cs.permutation_columns:
+        rots.add(1)
+        if cs.num_permutation_sets() > 1:
+            rots.add(-(cs.blinding_factors() + 1))
+    return sorted(rots)
+
+
+class RowWindow:
+    """Rows [begin - halo_lo, end + halo_hi) (mod ext_n) of one column, addressed by GLOBAL row index."""
+
+    def __init__(self, data, begin, end, halo_lo, halo_hi, ext_n):
+        self.data, self.first, self.ext_n = data, (begin - halo_lo) % ext_n, ext_n
+        self.count = min(ext_n, (end - begin) + halo_lo + halo_hi)
+        assert len(data) == self.count
+
+    def __getitem__(self, idx):
+        off = (idx - self.first) % self.ext_n
+        if off >= self.count:
+            raise IndexError("row %d is outside this rank's window" % idx)
+        return self.data[off]
+
+
+def window_rows(begin, end, halo_lo, halo_hi, ext_n):
+    """Global row indices of a RowWindow, in storage order."""
+    count = min(ext_n, (end - begin) + halo_lo + halo_hi)
+    first = (begin - halo_lo) % ext_n
+    return [(first + i) % ext_n for i in range(count)]
+
+
+def exchange_row_windows(dist, torch, owned, owner_of, names, shards, halo, ext_n, world, rank, limbs=4):
+    """One exchange before the quotient: every rank sends, of each column it owns, the row window of every other rank.
+
+    owned: {name -> int64 tensor (ext_n, limbs)} for the columns this rank produced; owner_of: {name -> rank} for all
+    `names`.  Returns {name -> int64 tensor (window rows, limbs)} for ALL names.  Point-to-point (batch_isend_irecv: the
+    grouped send/recv that NCCL turns into one all-to-all over NVLink; gloo runs it as is)."""
+    halo_lo, halo_hi = halo
+    rows = [torch.tensor(window_rows(b, e, halo_lo, halo_hi, ext_n), dtype=torch.long) for (b, e) in shards]
+    out, ops, keep = {}, [], []
+    for nm in names:
+        src = owner_of[nm]
+        if src == rank:
+            col = owned[nm]
+            out[nm] = col[rows[rank]].clone()
+            for dst in range(world):
+                if dst != rank:
+                    buf = col[rows[dst]].contiguous()
+                    keep.append(buf)
+                    ops.append(dist.P2POp(dist.isend, buf, dst))
+        else:
+            buf = torch.empty((len(rows[rank]), limbs), dtype=torch.int64)
+            out[nm] = buf
+            ops.append(dist.P2POp(dist.irecv, buf, src))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    return out

@@ -109,3 +109,87 @@ def test_plan_phase_is_complete_and_balanced():
                 load[rk] += (mc[x] * ((w[1] - w[0]) / nwin if w else 1.0)) if x in mc else oc[x]
             ideal = (sum(mc.values()) + sum(oc.values())) / world
             assert max(load) <= ideal + 12.5 * (2.0 / nwin) + 12.5 * (0 if n_msm % world == 0 or world // max(n_msm % world, 1) > 1 else 1) + 1.2
+
+
+def _quotient_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "py"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import random
+
+    import quotient_ref as qr
+    import quotient_util as qu
+    from halo2_snark_aggregator_b200 import parallel as par
+    from halo2_snark_aggregator_b200 import plonk
+
+    cs = plonk.aggregation_circuit_cs()
+    plan = plonk.build_quotient_plan(cs)
+    k = 4
+    ext_k = cs.extended_k(k)
+    ext_n = 1 << ext_k
+    rng = random.Random(5)  # same stream on every rank: the full columns are known everywhere only to CHECK the result
+    full = {nm: [rng.randrange(qr.R) for _ in range(ext_n)] for nm in plan.columns}
+    y, beta, gamma, theta = [rng.randrange(qr.R) for _ in range(4)]
+    names = list(plan.columns)
+    owner_of = {nm: i % world for i, nm in enumerate(names)}          # column-parallel ownership
+    to_t = lambda col: torch.from_numpy(qu.pack(col).view(np.int64).reshape(ext_n, 4).copy())
+    owned = {nm: to_t(full[nm]) for nm in names if owner_of[nm] == rank}
+    shards = par.quotient_row_shards(ext_n, world)
+    halo = par.rotation_halo(par.constraint_system_rotations(cs), 1 << (ext_k - k))
+    got = par.exchange_row_windows(dist, torch, owned, owner_of, names, shards, halo, ext_n, world, rank)
+    begin, end = shards[rank]
+    cols = {}
+    for nm in names:
+        vals = qu.unpack(got[nm].numpy().view(np.uint64).reshape(-1))
+        cols[nm] = par.RowWindow(vals, begin, end, halo[0], halo[1], ext_n)
+    mine = qr.evaluate_h(qu.oracle_desc(cs), cols, k, ext_k, y, beta, gamma, theta, rows=list(range(begin, end)))
+    want = qr.evaluate_h(qu.oracle_desc(cs), full, k, ext_k, y, beta, gamma, theta, rows=list(range(begin, end)))
+    # a row outside the window must not be readable (the halo is exactly what the rotations need)
+    outside_ok = True
+    if halo[0] + halo[1] + (end - begin) < ext_n:
+        try:
+            cols[names[0]][(end + halo[1]) % ext_n]
+            outside_ok = False
+        except IndexError:
+            pass
+    q.put((rank, mine == want, outside_ok, halo))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_world2_row_sharded_quotient_exchange():
+    """Groundwork for the multi-GPU resident prover: columns owned column-parallel, one point-to-point exchange of row
+    windows (shard + rotation halo, wrapping), and every rank's shard of h equals the single-process evaluate_h."""
+    world = 2
+    port = 31500 + os.getpid() % 2000
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_quotient_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(r[0] for r in res) == [0, 1]
+    assert all(r[1] for r in res), "row-sharded evaluate_h must equal the full one on the shard"
+    assert all(r[2] for r in res)
+    assert res[0][3] == (24, 4)   # aggregation circuit: last rotation -6 and next rotation +1 at 4 coset rows per row
+
+
+def test_rotation_halo_of_the_aggregation_circuit():
+    from halo2_snark_aggregator_b200 import parallel as par
+    from halo2_snark_aggregator_b200 import plonk
+
+    cs = plonk.aggregation_circuit_cs()
+    assert par.constraint_system_rotations(cs) == [-6, -1, 0, 1]
+    assert par.rotation_halo([-6, -1, 0, 1], 4) == (24, 4)
+    for world in (1, 2, 4, 8):
+        sh = par.quotient_row_shards(1 << 24, world)
+        assert sh[0][0] == 0 and sh[-1][1] == 1 << 24 and all(a[1] == b[0] for a, b in zip(sh, sh[1:]))
+    w = par.window_rows(0, 8, 3, 2, 16)
+    assert w == [13, 14, 15, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9]
+    rw = par.RowWindow(list(range(100, 113)), 0, 8, 3, 2, 16)
+    assert rw[13] == 100 and rw[0] == 103 and rw[9] == 112
