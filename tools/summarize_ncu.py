@@ -65,7 +65,7 @@ agg = launches()
 setup = ("msm_build_table", "ntt_gen_full_table", "ntt_gen_tables", "synth_bases_kernel", "synth_scalars_kernel", "quot_gen_tables")
 step_rows = [(k, v) for k, v in agg.items() if k not in setup]
 tot = sum(v[1] for _, v in step_rows) / steps
-print("## Launch list of the bench step (`%s_launches.csv`: %d bench steps under ncu, per-step averages; cold-cache, serialised: compare SHARES)\n" % (tag, steps))
+print("## Launch list of the bench step (`%s_launches_bench_k22.csv`: %d bench steps under ncu, per-step averages; cold-cache, serialised: compare SHARES)\n" % (tag, steps))
 print("| kernel | launches / step | ms / step (serialised) | share |\n|---|---|---|---|")
 for k, v in sorted(step_rows, key=lambda kv: -kv[1][1]):
     print("| `%s` | %.0f | %.2f | %.1f%% |" % (k, v[0] / steps, v[1] / steps, 100 * v[1] / steps / tot))
@@ -74,5 +74,5 @@ print("\nOne-time set-up in the same capture:\n\n| kernel | launches | total ms 
 for k in setup:
     if k in agg:
         print("| `%s` | %d | %.1f |" % (k, agg[k][0], agg[k][1]))
-print("\n## `--set full` highlights (`%s_full_raw.csv`; one launch each, k = 22)\n" % tag)
+print("\n## `--set full` highlights (`%s_ncu_full_raw.csv`; one launch each, k = 22)\n" % tag)
 print(full())
