@@ -58,6 +58,27 @@ def schedule():
     return units
 
 
+BLIND_ROWS = 6  # every committed halo2 column ends in blinding_factors + 1 full-width random rows
+
+
+def workload_config(k):
+    """The workload, identical for both arms (the driver compares the two `config` dicts)."""
+    return {"workload": "aggregation-circuit prover schedule (SURVEY.md App. C), k=%d: 38 MSM(2^%d) + 29 iNTT(2^%d) + 29 coset-NTT(2^%d->2^%d) + 1 iNTT(2^%d)" % (k, k, k, k, k + 2, k + 2),
+            "k": k, "proofs": 1,
+            "scalars": "witness-like mixture (SURVEY.md 8d): 5x kind1, 1x kind2, 14x 17-bit, 18x uniform Fr; every small-valued column ends in 6 full-width blinding rows as real halo2 columns do",
+            "l2": "inputs larger than L2 (each column is 2^%d x 32 B; SRS 2^%d x 64 B), no flush needed" % (k, k)}
+
+
+def oracle_column(ob, k, unit_index, kind):
+    """The scalar column of schedule unit `unit_index` as the oracle's generators produce it: bit-identical to what
+    the b200 arm synthesises on the device (h2agg_synth_scalars_dev), blinding rows included."""
+    n = 1 << k
+    col = ob.gen_scalars(SEED_SCALARS + 1000 * k + unit_index, kind, n)
+    if kind != 0 and n > BLIND_ROWS:
+        col[4 * (n - BLIND_ROWS):] = ob.gen_scalars(SEED_SCALARS + 1000 * k + 500 + unit_index, 0, BLIND_ROWS)
+    return col
+
+
 def algorithmic_bytes(k):
     n = 1 << k
     return 38 * (96 * n + 96) + 29 * (64 * n) + 29 * (160 * n) + 1 * (256 * n)
@@ -150,7 +171,10 @@ def cpu_between_the_schedule(ob, k, cores):
 
 
 def run_reference_arm(args, rank, world):
-    """CPU restatement of the reference's path on the host cores (rank 0 only)."""
+    """CPU restatement of the reference's path on the host cores (rank 0 only): FULL replays of the schedule -- every one
+    of the 38 MSMs on its own column and the 59 transforms -- not an extrapolation from one unit per kind.  A replay is
+    minutes of CPU time at k = 22, so `steps` / `warmup` in the line are the replays actually run (1 / 0 there; the
+    requested values are kept under *_requested); at small k the requested counts are honoured."""
     if rank != 0:
         return
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -162,37 +186,59 @@ def run_reference_arm(args, rank, world):
     n = 1 << k
     cores = ob.threads()
     d = domain_consts(k)
+    units = schedule()
     bases = ob.gen_bases(SEED_BASES + k, n)
-    cols = {kind: ob.gen_scalars(SEED_SCALARS + 1000 * k + kind, kind, n) for kind in range(4)}
     a = ob.gen_scalars(SEED_SCALARS + 77, 0, n)
-    ext = np.empty(4 << (k + 2), dtype=np.uint64)
-    counts = {"msm0": 18, "msm1": 5, "msm2": 1, "msm3": 14, "intt": 29, "coset": 29, "ext_intt": 1}
+    ext_seed = ob.gen_scalars(SEED_SCALARS + 99, 0, n << 2)
+    heavy = k >= 20
+    steps = 1 if heavy else max(1, args.steps)
+    warmup = 0 if heavy else min(args.warmup, 1)
 
-    def one_step():
-        t = {}
-        for kind in range(4):
-            t0 = time.perf_counter(); ob.best_multiexp(cols[kind], bases, cores); t["msm%d" % kind] = time.perf_counter() - t0
-        x = a.copy()
-        t0 = time.perf_counter(); ob.ifft(x, d["omega_inv"], d["n_inv"], k, cores); t["intt"] = time.perf_counter() - t0
-        t0 = time.perf_counter(); e = ob.coeff_to_extended(x, k, k + 2, d["zeta"], d["omega_ext"], cores); t["coset"] = time.perf_counter() - t0
-        t0 = time.perf_counter(); ob.extended_to_coeff(e, k + 2, d["omega_ext_inv"], d["ext_n_inv"], d["zeta"], 3 << k, cores); t["ext_intt"] = time.perf_counter() - t0
-        return t
+    def replay(per):
+        digest = 0
+        for i, (r, what, kind) in enumerate(units):
+            t0 = time.perf_counter()
+            if what == "msm":
+                col = oracle_column(ob, k, i, kind)   # generation is outside the timed span
+                t0 = time.perf_counter()
+                pt = ob.best_multiexp(col, bases, cores)
+                digest ^= int(pt[0])
+                key = "msm%d" % kind
+            elif what == "intt":
+                x = a.copy()
+                t0 = time.perf_counter()
+                ob.ifft(x, d["omega_inv"], d["n_inv"], k, cores)
+                key = "intt"
+            elif what == "coset":
+                t0 = time.perf_counter()
+                ob.coeff_to_extended(a, k, k + 2, d["zeta"], d["omega_ext"], cores)
+                key = "coset"
+            else:
+                e = ext_seed.copy()
+                t0 = time.perf_counter()
+                ob.extended_to_coeff(e, k + 2, d["omega_ext_inv"], d["ext_n_inv"], d["zeta"], 3 << k, cores)
+                key = "ext_intt"
+            dt = time.perf_counter() - t0
+            per[key] = per.get(key, 0.0) + dt
+        return digest
 
-    for _ in range(args.warmup):
-        one_step()
-        if args.k >= 20:
-            break  # CPU steps are seconds long and have no JIT/caches to warm: one warm-up pass is enough
-    acc = {key: 0.0 for key in counts}
+    for _ in range(warmup):
+        replay({})
+    per_total, step_s = {}, []
     t_begin = time.perf_counter()
-    for _ in range(args.steps):
-        t = one_step()
-        for key in acc:
-            acc[key] += t[key]
+    for _ in range(steps):
+        before = sum(per_total.values())
+        replay(per_total)
+        step_s.append(sum(per_total.values()) - before)
     wall = time.perf_counter() - t_begin
-    per = {key: acc[key] / args.steps for key in acc}
-    sched = sum(per[key] * counts[key] for key in counts)
-    sample = ("per step: 4 MSM(2^%d) one per scalar kind + 1 iNTT(n) + 1 coset-NTT(n->4n) + 1 ext-iNTT(4n), "
-              "scaled to the 38 MSM + 59 NTT schedule by unit counts %s" % (k, json.dumps(counts)))
+    counts = {}
+    for _, what, kind in units:
+        key = ("msm%d" % kind) if what == "msm" else what
+        counts[key] = counts.get(key, 0) + 1
+    sched = sum(step_s) / len(step_s)
+    per = {key: per_total[key] / steps / counts[key] for key in per_total}
+    sample = ("%d full replay(s) of the schedule: all 38 MSM(2^%d), each on its own synthetic column, + 29 iNTT(n) + 29 coset-NTT(n->4n) "
+              "+ 1 ext-iNTT(4n); value = mean measured seconds per replay (column generation excluded)" % (steps, k))
     between = None
     try:  # informational only: never let it take the line down
         between = cpu_between_the_schedule(ob, k, cores)
@@ -200,14 +246,15 @@ def run_reference_arm(args, rank, world):
         between = {"error": repr(e)}
     line = {
         "impl": "reference", "metric": "aggregation proving time (s) at k=%d (prover-schedule replay: 38 MSM + 59 NTT)" % k,
-        "value": sched, "unit": "s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "value": sched, "unit": "s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+        "steps_requested": args.steps, "warmup_requested": args.warmup,
         "ms_per_step": sched * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "u256-mod-p (4x64-bit Montgomery limbs)",
-        "data": "synthetic", "config": {"workload": "aggregation-circuit prover schedule, k=%d, 1 proof" % k, "k": k},
+        "data": "synthetic", "config": workload_config(k),
         "cpu_baseline": {"value": sched, "unit": "s", "cores": cores, "kind": "port", "sample": sample,
-                         "per_unit_s": per, "sample_wall_s": wall,
+                         "per_unit_s": per, "unit_counts": counts, "sample_wall_s": wall,
                          "between_the_schedule": between,
                          "full_pipeline_estimate_s": (sched + between["total_s"]) if between and "total_s" in between else None,
-                         "note": "C++ restatement of halo2 (v2022_09_10) best_multiexp/best_fft/EvaluationDomain; the Rust reference cannot be built here"},
+                         "note": "C++ restatement of halo2 (v2022_09_10) best_multiexp/best_fft/EvaluationDomain on %d host threads (the reference pins 24 rayon threads, halo2-snark-aggregator-sdk/src/lib.rs:52-55); the Rust reference cannot be built here" % cores},
         "e2e": {"value": sched, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -224,6 +271,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-witness", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison of the timed path's commitments (profiling runs only)")
     ap.add_argument("--overlap-ntt", action="store_true", help="run a phase's NTTs on a second stream beside its MSM batch (measured: no gain, the step is multiplier-bound)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--msm-window", type=int, default=0)
@@ -304,7 +352,6 @@ def main():
     all_msm = [i for i, u in enumerate(units) if u[1] == "msm"]
     my_ntt = sorted(set(u for ph in plan for (u, rk, w) in ph if rk == rank and units[u][1] != "msm"))
     t_cols = {}
-    BLIND_ROWS = 6  # every committed halo2 column ends in blinding_factors + 1 full-width random rows
     for i, u in msm_units:
         t_cols[i] = dbuf(n * 32)
         ctx.synth_scalars_dev(SEED_SCALARS + 1000 * k + i, u[2], 0, n, t_cols[i].data_ptr())
@@ -394,7 +441,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
+    if args.warmup < 3:
+        raise SystemExit("bench.py: --warmup must be >= 3 (timing rules)")
+    for _ in range(args.warmup):
         step_device()
     barrier()
     clocks = ClockSampler(local_rank)
@@ -731,45 +780,72 @@ def main():
         n3["permute_expression_pair"] = n3s
         del d_q, d_z, d_li, d_lt, d_pa, d_ps
 
-    # ---- CPU baseline: the oracle port on this box's host cores, bounded sample (rank 0, N=1 only)
+    # ---- parity of the timed path, at EVERY N (rank 0): the commitments the last timed step left in t_final -- per
+    # phase one whole-column MSM and one window-sharded MSM (gather + g1_sum path) where the plan has one, plus one MSM
+    # per scalar kind -- against the oracle's best_multiexp on the same (regenerated) column.  A mismatch fails the run.
+    parity = None
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and not args.no_parity:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import oracle_binding as ob
         from util import domain_consts
 
         cores = ob.threads()
-        d = domain_consts(k)
         h_bases = ctx.d2h(t_bases.data_ptr(), 8 * n)
-        per = {}
-        first_of_kind = {}
-        for i, u in msm_units:
-            first_of_kind.setdefault(u[2], i)
         gpu_pts_all = ctx.d2h(t_final.data_ptr(), 20 * len(units)).reshape(len(units), 20)
-        gpu_pts = {i: gpu_pts_all[i] for i in all_msm}
-        parity = True
-        for kind, i in sorted(first_of_kind.items()):
-            s = ctx.d2h(t_cols[i].data_ptr(), 4 * n)
+        pick = {}   # unit -> how it was computed
+        for ph in plan:
+            seen_whole = seen_shard = False
+            by_unit = {}
+            for (u, rk, w) in ph:
+                if units[u][1] == "msm":
+                    by_unit.setdefault(u, []).append((rk, w))
+            for u, parts in sorted(by_unit.items()):
+                sharded = any(w is not None for _, w in parts)
+                if sharded and not seen_shard:
+                    pick[u] = "window-sharded over ranks %s" % sorted(rk for rk, _ in parts)
+                    seen_shard = True
+                elif not sharded and not seen_whole:
+                    pick[u] = "whole column on rank %d" % parts[0][0]
+                    seen_whole = True
+        for i in all_msm:   # and one of every scalar kind
+            if not any(units[j][2] == units[i][2] for j in pick):
+                pick[i] = "whole column (first of scalar kind %d)" % units[i][2]
+        per, checked, ok = {}, [], True
+        for i in sorted(pick):
+            kind = units[i][2]
+            col = oracle_column(ob, k, i, kind)
             t0 = time.perf_counter()
-            want = ob.best_multiexp(s, h_bases, cores)
-            per["msm%d" % kind] = time.perf_counter() - t0
-            parity = parity and bool(np.array_equal(want, gpu_pts[i][8:]))
-        a = ob.gen_scalars(SEED_SCALARS + 77, 0, n)
-        t0 = time.perf_counter(); ob.ifft(a, d["omega_inv"], d["n_inv"], k, cores); per["intt"] = time.perf_counter() - t0
-        t0 = time.perf_counter(); e = ob.coeff_to_extended(a, k, k + 2, d["zeta"], d["omega_ext"], cores); per["coset"] = time.perf_counter() - t0
-        t0 = time.perf_counter(); ob.extended_to_coeff(e, k + 2, d["omega_ext_inv"], d["ext_n_inv"], d["zeta"], 3 << k, cores); per["ext_intt"] = time.perf_counter() - t0
-        counts = {"msm0": 18, "msm1": 5, "msm2": 1, "msm3": 14, "intt": 29, "coset": 29, "ext_intt": 1}
-        sched = sum(per[key] * counts[key] for key in counts)
-        try:  # informational only: never let it take the line down
-            between = cpu_between_the_schedule(ob, k, cores)
-        except Exception as e:  # pragma: no cover
-            between = {"error": repr(e)}
-        cpu = {"value": sched, "unit": "s", "cores": cores, "kind": "port",
-               "between_the_schedule": between,
-               "full_pipeline_estimate_s": (sched + between["total_s"]) if "total_s" in between else None,
-               "sample": "one MSM(2^%d) per scalar kind + 1 iNTT(n) + 1 coset-NTT(n->4n) + 1 ext-iNTT(4n) timed once, scaled by the schedule's unit counts %s" % (k, json.dumps(counts)),
-               "per_unit_s": per, "gpu_matches_oracle_on_sampled_msms": parity,
-               "note": "C++ restatement of halo2 (v2022_09_10) CPU algorithms, not the Rust reference (no cargo/rustc in this image)"}
+            want = ob.best_multiexp(col, h_bases, cores)
+            per.setdefault("msm%d" % kind, time.perf_counter() - t0)
+            good = bool(np.array_equal(want, gpu_pts_all[i][8:]))
+            ok = ok and good
+            checked.append({"unit": i, "round": units[i][0], "scalar_kind": kind, "how": pick[i], "equal": good})
+        parity = {"ok": ok, "parity_checked_units": len(checked), "units": checked,
+                  "what": "t_final (the commitments of the last timed step) == oracle best_multiexp on the same column, bit for bit"}
+        if not ok:
+            print(json.dumps({"error": "parity mismatch between the timed GPU path and the oracle", "parity": parity}), file=sys.stderr, flush=True)
+            raise SystemExit(1)
+
+        # ---- CPU baseline: the oracle port on this box's host cores, bounded sample (rank 0, N=1 only)
+        if world == 1 and not args.no_cpu_baseline:
+            d = domain_consts(k)
+            a = ob.gen_scalars(SEED_SCALARS + 77, 0, n)
+            t0 = time.perf_counter(); ob.ifft(a, d["omega_inv"], d["n_inv"], k, cores); per["intt"] = time.perf_counter() - t0
+            t0 = time.perf_counter(); e = ob.coeff_to_extended(a, k, k + 2, d["zeta"], d["omega_ext"], cores); per["coset"] = time.perf_counter() - t0
+            t0 = time.perf_counter(); ob.extended_to_coeff(e, k + 2, d["omega_ext_inv"], d["ext_n_inv"], d["zeta"], 3 << k, cores); per["ext_intt"] = time.perf_counter() - t0
+            counts = {"msm0": 18, "msm1": 5, "msm2": 1, "msm3": 14, "intt": 29, "coset": 29, "ext_intt": 1}
+            sched = sum(per[key] * counts[key] for key in counts)
+            try:  # informational only: never let it take the line down
+                between = cpu_between_the_schedule(ob, k, cores)
+            except Exception as e:  # pragma: no cover
+                between = {"error": repr(e)}
+            cpu = {"value": sched, "unit": "s", "cores": cores, "kind": "port",
+                   "between_the_schedule": between,
+                   "full_pipeline_estimate_s": (sched + between["total_s"]) if "total_s" in between else None,
+                   "sample": "one MSM(2^%d) per scalar kind + 1 iNTT(n) + 1 coset-NTT(n->4n) + 1 ext-iNTT(4n) timed once, scaled by the schedule's unit counts %s (the --impl reference arm measures a FULL replay)" % (k, json.dumps(counts)),
+                   "per_unit_s": per, "gpu_matches_oracle_on_sampled_msms": ok,
+                   "note": "C++ restatement of halo2 (v2022_09_10) CPU algorithms, not the Rust reference (no cargo/rustc in this image)"}
 
     if rank == 0:
         peaks = {}
@@ -788,15 +864,13 @@ def main():
         adds_uniform = n * nwin + 2 * nwin * (1 << (cbits - 1))
         line = {
             "metric": "aggregation proving time (s) at k=%d (prover-schedule replay: 38 MSM + 59 NTT)" % k,
-            "value": ms / 1e3, "unit": "s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "value": ms / 1e3, "unit": "s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
             "dtype": "u256-mod-p (8x32-bit Montgomery limbs, integer)", "data": "synthetic",
-            "config": {"workload": "aggregation-circuit prover schedule (SURVEY.md App. C), k=%d: 38 MSM(2^%d) + 29 iNTT(2^%d) + 29 coset-NTT(2^%d->2^%d) + 1 iNTT(2^%d)" % (k, k, k, k, k + 2, k + 2),
-                       "k": k, "scalars": "witness-like mixture (SURVEY.md 8d): 5x kind1, 1x kind2, 14x 17-bit, 18x uniform Fr; every small-valued column ends in 6 full-width blinding rows as real halo2 columns do",
-                       "parallelism": ("%s over %d GPU(s), one all-gather of commitments per commit phase" % ({"windows": "window-sharded MSM + column-parallel NTT", "columns": "column-parallel (round-robin)", "auto": "cost-balanced column-parallel, leftover MSMs window-sharded"}[mode], world)),
-                       "msm_mode": "fixed-base table (2^(c w) P rows resident in HBM)" if table_mode else "plain",
-                       "msm_window_bits": cbits, "msm_windows": nwin,
-                       "l2": "inputs larger than L2 (each column is 2^%d x 32 B; SRS 2^%d x 64 B), no flush needed" % (k, k)},
+            "config": workload_config(k),
+            "impl_config": {"parallelism": ("%s over %d GPU(s), one all-gather of commitments per commit phase" % ({"windows": "window-sharded MSM + column-parallel NTT", "columns": "column-parallel (round-robin)", "auto": "cost-balanced column-parallel, leftover MSMs window-sharded"}[mode], world)),
+                            "msm_mode": "fixed-base table (2^(c w) P rows resident in HBM)" if table_mode else "plain",
+                            "msm_window_bits": cbits, "msm_windows": nwin},
             "e2e": e2e_res if e2e_res is not None else e2e, "e2e_host_pointer_abi": e2e if e2e_res is not None else None,
             "gpu_launches": int(launches), "clocks": clock_info,
             "roofline": {"kernel": "msm_accumulate", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -818,6 +892,7 @@ def main():
                 "note": "one launch on a uniform 2^%d column, timed alone; a mixed addition (8M+2S) is 6 Montgomery products of 136 multiplier instructions, 2 squarings of 108 and 1 dual product (a*b - c*d, one reduction) of 208 = 1240 multiplier instructions (was 10 x 136 = 1360 before the dedicated schedules)" % k})(
                     float((clock_info or {}).get("sm_mhz") or 1965.0)),
             "cpu_baseline": cpu,
+            "parity": parity,
             "witness": witness,
             "next_rows": {"N1_evaluate_h": n1, "N2_eval_and_kate_division": n2, "N3_grand_product": n3},
             "extra": {

@@ -243,8 +243,8 @@ int h2agg_lookup_products_dev(h2agg_ctx* ctx, size_t n_lookups, const void* cons
   Fr b, g;
   memcpy(b.v, beta, 32);
   memcpy(g.v, gamma, 32);
-  H2AGG_CUDA(ctx, cudaEventRecord(ctx->fork_ev, ctx->stream));
-  for (int l = 0; l < N_LANES; l++) H2AGG_CUDA(ctx, cudaStreamWaitEvent(ctx->lanes[l].st, ctx->fork_ev, 0));
+  LaneFork lf(ctx);
+  if ((rc = lf.fork())) return rc;
   for (size_t i = 0; i < n_lookups; i++) {
     Lane& ln = ctx->lanes[i % N_LANES];
     if ((rc = ensure(ctx, ln.args_ws, 2 * n * 32))) return rc;
@@ -257,11 +257,7 @@ int h2agg_lookup_products_dev(h2agg_ctx* ctx, size_t n_lookups, const void* cons
     H2AGG_CUDA(ctx, cudaGetLastError());
     if ((rc = grand_product_dev(ctx, num, den, n, d_z[i], ln.st, &ln.scan_ws))) return rc;
   }
-  for (int l = 0; l < N_LANES; l++) {
-    H2AGG_CUDA(ctx, cudaEventRecord(ctx->lanes[l].done, ctx->lanes[l].st));
-    H2AGG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->lanes[l].done, 0));
-  }
-  return 0;
+  return lf.join();
 }
 
 int h2agg_permutation_product_dev(h2agg_ctx* ctx, const void* const* d_values, const void* const* d_sigmas, size_t n_cols,

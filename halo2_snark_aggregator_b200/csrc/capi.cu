@@ -514,34 +514,21 @@ static int ntt_host_batch(h2agg_ctx* ctx, const uint64_t* const* src, uint64_t* 
   int rc = lanes_init(ctx);
   if (rc) return rc;
   const size_t N = (size_t)1 << o.log_n;
-  // twiddle tables are created on the main stream before the lanes fork
   o.src_n = in_n;
   o.dst_n = out_n;
-  H2AGG_CUDA(ctx, cudaEventRecord(ctx->fork_ev, ctx->stream));
-  for (int l = 0; l < N_LANES; l++) H2AGG_CUDA(ctx, cudaStreamWaitEvent(ctx->lanes[l].st, ctx->fork_ev, 0));
-  bool tables_ready = false;
+  // the (cached) twiddle tables are generated on the main stream: before the lanes fork off it
+  if ((rc = ntt_warm_tables(ctx, o.omega, o.log_n))) return rc;
+  LaneFork lf(ctx);
+  if ((rc = lf.fork())) return rc;
   for (size_t i = 0; i < n_cols; i++) {
     Lane& ln = ctx->lanes[i % N_LANES];
     if ((rc = ensure(ctx, ln.io, in_n * 32))) return rc;
     if ((rc = ensure(ctx, ln.io_out, N * 32))) return rc;
     H2AGG_CUDA(ctx, cudaMemcpyAsync(ln.io.p, src[i], in_n * 32, cudaMemcpyHostToDevice, ln.st));
-    if (!tables_ready) {
-      // first column: run on the main stream so the (cached) table generation is ordered before every lane
-      H2AGG_CUDA(ctx, cudaEventRecord(ln.done, ln.st));
-      H2AGG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ln.done, 0));
-      if ((rc = ntt_run(ctx, ln.io.p, ln.io_out.p, o, ctx->stream, &ln.ntt_tmp))) return rc;
-      H2AGG_CUDA(ctx, cudaEventRecord(ctx->fork_ev, ctx->stream));
-      for (int l = 0; l < N_LANES; l++) H2AGG_CUDA(ctx, cudaStreamWaitEvent(ctx->lanes[l].st, ctx->fork_ev, 0));
-      tables_ready = true;
-    } else {
-      if ((rc = ntt_run(ctx, ln.io.p, ln.io_out.p, o, ln.st, &ln.ntt_tmp))) return rc;
-    }
+    if ((rc = ntt_run(ctx, ln.io.p, ln.io_out.p, o, ln.st, &ln.ntt_tmp))) return rc;
     H2AGG_CUDA(ctx, cudaMemcpyAsync(dst[i], ln.io_out.p, out_n * 32, cudaMemcpyDeviceToHost, ln.st));
   }
-  for (int l = 0; l < N_LANES; l++) {
-    H2AGG_CUDA(ctx, cudaEventRecord(ctx->lanes[l].done, ctx->lanes[l].st));
-    H2AGG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->lanes[l].done, 0));
-  }
+  if ((rc = lf.join())) return rc;
   H2AGG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return 0;
 }
@@ -658,10 +645,12 @@ static int commit_round_impl(h2agg_ctx* ctx, uint64_t srs_id, const uint64_t* co
   if (ext_out && (rc = coset_consts(ctx, zeta, nullptr, 0, in3))) return rc;
   NttOpts oi{omega_inv, k, n, n, nullptr, s3};
   NttOpts oe{omega_ext, ext_k, n, (size_t)1 << ext_k, in3, nullptr};
-  // make sure the (cached) twiddle tables exist before the lanes fork: a zero-length warm-up is not possible,
-  // so the first column's transforms run on the main stream
-  H2AGG_CUDA(ctx, cudaEventRecord(ctx->fork_ev, ctx->stream));
-  for (int l = 0; l < N_LANES; l++) H2AGG_CUDA(ctx, cudaStreamWaitEvent(ctx->lanes[l].st, ctx->fork_ev, 0));
+  // the (cached) twiddle tables are generated on the main stream: make sure both exist before the lanes fork off
+  // it, whichever columns ask for transforms (coeff_out / ext_out may hold NULL entries anywhere)
+  if (coeff_out && (rc = ntt_warm_tables(ctx, omega_inv, k))) return rc;
+  if (ext_out && (rc = ntt_warm_tables(ctx, omega_ext, ext_k))) return rc;
+  LaneFork lf(ctx);
+  if ((rc = lf.fork())) return rc;
   for (size_t i = 0; i < n_cols; i++) {
     Lane& ln = ctx->lanes[i % N_LANES];
     CHECK_ARG(ctx, lagrange_cols[i], "commit_round: null column");
@@ -678,11 +667,6 @@ static int commit_round_impl(h2agg_ctx* ctx, uint64_t srs_id, const uint64_t* co
     if ((rc = msm_run(ctx, ln.st, ln.ws, bases, col, n, (uint8_t*)ctx->small.p + i * 160, 0, -1))) return rc;
     if (coeff_out && coeff_out[i]) {
       cudaStream_t st = ln.st;
-      if (i == 0) {  // tables are generated on the main stream: run column 0's transforms there, then re-fork
-        H2AGG_CUDA(ctx, cudaEventRecord(ln.done, ln.st));
-        H2AGG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ln.done, 0));
-        st = ctx->stream;
-      }
       if (resident) {
         if ((rc = ntt_run(ctx, col, coeff_out[i], oi, st, &ln.ntt_tmp))) return rc;
         if (ext_out && ext_out[i] && (rc = ntt_run(ctx, coeff_out[i], ext_out[i], oe, st, &ln.ntt_tmp))) return rc;
@@ -694,16 +678,9 @@ static int commit_round_impl(h2agg_ctx* ctx, uint64_t srs_id, const uint64_t* co
           H2AGG_CUDA(ctx, cudaMemcpyAsync(ext_out[i], ln.io_out.p, ((size_t)32) << ext_k, cudaMemcpyDeviceToHost, st));
         }
       }
-      if (i == 0) {
-        H2AGG_CUDA(ctx, cudaEventRecord(ctx->fork_ev, ctx->stream));
-        for (int l = 0; l < N_LANES; l++) H2AGG_CUDA(ctx, cudaStreamWaitEvent(ctx->lanes[l].st, ctx->fork_ev, 0));
-      }
     }
   }
-  for (int l = 0; l < N_LANES; l++) {
-    H2AGG_CUDA(ctx, cudaEventRecord(ctx->lanes[l].done, ctx->lanes[l].st));
-    H2AGG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->lanes[l].done, 0));
-  }
+  if ((rc = lf.join())) return rc;
   H2AGG_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, ctx->small.p, n_cols * 160, cudaMemcpyDeviceToHost, ctx->stream));
   H2AGG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   for (size_t i = 0; i < n_cols; i++) memcpy(out_affine + i * 8, (uint8_t*)ctx->pinned + i * 160, 64);

@@ -179,6 +179,35 @@ struct NttOpts {
 int ntt_run(h2agg_ctx* ctx, const void* d_src, void* d_dst, const NttOpts& o, cudaStream_t st = nullptr,
             DevBuf* tmp = nullptr);
 
+// Make sure the cached twiddle tables of (omega, log_n) exist; generation is enqueued on ctx->stream.
+int ntt_warm_tables(h2agg_ctx* ctx, const uint64_t* omega, uint32_t log_n);
+
+// Fork the lanes off ctx->stream and join them back.  The guard's destructor covers the error returns in between:
+// work already enqueued on the lanes (copies into caller buffers included) is drained before the entry point returns.
+struct LaneFork {
+  h2agg_ctx* ctx;
+  bool joined = false;
+  explicit LaneFork(h2agg_ctx* c) : ctx(c) {}
+  int fork() {
+    H2AGG_CUDA(ctx, cudaEventRecord(ctx->fork_ev, ctx->stream));
+    for (int l = 0; l < N_LANES; l++) H2AGG_CUDA(ctx, cudaStreamWaitEvent(ctx->lanes[l].st, ctx->fork_ev, 0));
+    return 0;
+  }
+  int join() {
+    joined = true;
+    for (int l = 0; l < N_LANES; l++) {
+      H2AGG_CUDA(ctx, cudaEventRecord(ctx->lanes[l].done, ctx->lanes[l].st));
+      H2AGG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->lanes[l].done, 0));
+    }
+    return 0;
+  }
+  ~LaneFork() {
+    if (joined) return;
+    for (int l = 0; l < N_LANES; l++)
+      if (ctx->lanes[l].st) cudaStreamSynchronize(ctx->lanes[l].st);
+  }
+};
+
 // MSM over G1: d_scalars n x 32 B (Montgomery Fr), d_bases n x 64 B affine.
 // Writes affine (64 B) + jacobian (96 B, z = 1 or 0) to d_out (160 B, device).
 // Windows [win_begin, win_end) only (pass 0, -1 for all): partial = sum_w 2^(c w) B_w.

@@ -789,8 +789,8 @@ int msm_run_batch(h2agg_ctx* ctx, const MsmBases& bases, const void* const* cols
   if (n_cols == 1 && !host_cols)
     return msm_run(ctx, ctx->stream, ctx->msm_ws, bases, cols[0], n, d_out160s, win_begin, win_end);
   if ((rc = lanes_init(ctx))) return rc;
-  H2AGG_CUDA(ctx, cudaEventRecord(ctx->fork_ev, ctx->stream));
-  for (int l = 0; l < N_LANES; l++) H2AGG_CUDA(ctx, cudaStreamWaitEvent(ctx->lanes[l].st, ctx->fork_ev, 0));
+  LaneFork lf(ctx);
+  if ((rc = lf.fork())) return rc;
   for (size_t i = 0; i < n_cols; i++) {
     Lane& ln = ctx->lanes[i % N_LANES];
     const void* d_col = cols[i];
@@ -801,11 +801,7 @@ int msm_run_batch(h2agg_ctx* ctx, const MsmBases& bases, const void* const* cols
     }
     if ((rc = msm_run(ctx, ln.st, ln.ws, bases, d_col, n, d_out160s + i * 160, win_begin, win_end))) return rc;
   }
-  for (int l = 0; l < N_LANES; l++) {
-    H2AGG_CUDA(ctx, cudaEventRecord(ctx->lanes[l].done, ctx->lanes[l].st));
-    H2AGG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->lanes[l].done, 0));
-  }
-  return 0;
+  return lf.join();
 }
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

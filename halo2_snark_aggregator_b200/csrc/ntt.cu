@@ -305,7 +305,8 @@ static int get_tables(h2agg_ctx* ctx, const uint64_t* omega, uint32_t log_n, Twi
     size_t v = 0;
     for (size_t i = 1; i < ctx->tw.size(); i++)
       if (ctx->tw[i].last_use < ctx->tw[v].last_use) v = i;
-    H2AGG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    // lanes may still be reading the victim: drain the device, not just the main stream
+    H2AGG_CUDA(ctx, cudaDeviceSynchronize());
     cudaFree(ctx->tw[v].lo);
     cudaFree(ctx->tw[v].hi);
     cudaFree(ctx->tw[v].full);
@@ -346,6 +347,14 @@ static int get_tables(h2agg_ctx* ctx, const uint64_t* omega, uint32_t log_n, Twi
   ctx->tw.push_back(t);
   *out = &ctx->tw.back();
   return 0;
+}
+
+// Create (or touch) the cached tables of (omega, log_n) on ctx->stream.  Callers that run transforms on lane streams
+// call this BEFORE they fork the lanes off ctx->stream, so the generation kernels are ordered before every lane.
+int ntt_warm_tables(h2agg_ctx* ctx, const uint64_t* omega, uint32_t log_n) {
+  if (log_n == 0 || log_n > 28) return 0;
+  TwiddleTable* tw;
+  return get_tables(ctx, omega, log_n, &tw);
 }
 
 // split log_n into pass radices

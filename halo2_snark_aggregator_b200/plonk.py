@@ -103,6 +103,18 @@ class Expression:
             return self.a.queries()
         return self.a.queries() | self.b.queries()
 
+    def leaves(self):
+        """(kind, col, rot) of every column query, left to right -- the order in which the closure that built the
+        expression called meta.query_*, which is the order halo2 registers the queries in."""
+        k = self.kind
+        if k == "const":
+            return []
+        if k in ("fixed", "advice", "instance"):
+            return [(k, self.a, self.b)]
+        if k in ("neg", "scaled"):
+            return self.a.leaves()
+        return self.a.leaves() + self.b.leaves()
+
     def expand(self):
         """{sorted tuple of (kind, col, rot) queries: coefficient mod r}: the sum-of-products form"""
         k = self.kind
@@ -141,14 +153,41 @@ class ConstraintSystem:
         self.gates = []        # list of (name, [Expression])
         self.lookups = []      # list of (name, [input Expression], [table Expression])
         self.permutation_columns = []  # [(kind, index)] in enable_equality order
+        # ConstraintSystem::{advice,fixed,instance}_queries: (column, rotation) in REGISTRATION order.  create_proof
+        # writes its evaluations and GWC folds its polynomials in this order, and the reference's verifier walks the
+        # same lists (halo2-snark-aggregator-api/src/systems/halo2/params.rs:156-205), so it is part of the format.
+        self.queries = {"advice": [], "fixed": [], "instance": []}
+
+    def _query(self, kind, col, rot):
+        """ConstraintSystem::query_{advice,fixed,instance}_index: append (column, rotation) unless already there."""
+        q = (col, rot)
+        if q not in self.queries[kind]:
+            self.queries[kind].append(q)
 
     def create_gate(self, name, polys):
-        self.gates.append((name, list(polys)))
+        """The caller's closure queries cells while it builds the polynomials: leaves left to right (write the
+        Python expression in the order the Rust closure calls meta.query_*)."""
+        polys = list(polys)
+        for p in polys:
+            for kind, col, rot in p.leaves():
+                self._query(kind, col, rot)
+        self.gates.append((name, polys))
 
     def lookup(self, name, pairs):
+        """ConstraintSystem::lookup: table_map runs first (it queries the input cells), then every TableColumn is
+        queried as a fixed column at the current row."""
+        pairs = list(pairs)
+        for inp, _ in pairs:
+            for kind, col, rot in inp.leaves():
+                self._query(kind, col, rot)
+        for _, tab in pairs:
+            for kind, col, rot in tab.leaves():
+                self._query(kind, col, rot)
         self.lookups.append((name, [p[0] for p in pairs], [p[1] for p in pairs]))
 
     def enable_equality(self, kind, index):
+        """ConstraintSystem::enable_equality: query_any_index(column, Rotation::cur()) then permutation.add_column."""
+        self._query(kind, index, 0)
         if (kind, index) not in self.permutation_columns:
             self.permutation_columns.append((kind, index))
 
@@ -167,20 +206,8 @@ class ConstraintSystem:
     def blinding_factors(self):
         """max(3, most queries on one advice column) + 2 (ConstraintSystem::blinding_factors)."""
         per_col = {}
-        seen = set()
-        exprs = [p for _, polys in self.gates for p in polys]
-        for _, ins, tabs in self.lookups:
-            exprs += ins + tabs
-        for e in exprs:
-            for q in e.queries():
-                if q[0] == "advice" and q not in seen:
-                    seen.add(q)
-                    per_col[q[1]] = per_col.get(q[1], 0) + 1
-        for kind, idx in self.permutation_columns:  # the permutation argument queries its columns at cur
-            q = (kind, idx, 0)
-            if kind == "advice" and q not in seen:
-                seen.add(q)
-                per_col[idx] = per_col.get(idx, 0) + 1
+        for col, _ in self.queries["advice"]:
+            per_col[col] = per_col.get(col, 0) + 1
         return max([3] + list(per_col.values())) + 2
 
     def chunk_len(self):

@@ -268,37 +268,48 @@ class ResidentProver:
 
 
 def create_proof_queries(cs):
-    """The (polynomial, rotation) list create_proof opens for a constraint system, in halo2's order: advice queries,
-    permutation products, lookups, fixed queries, permutation sigmas, vanishing (h, random)."""
-    adv, fix, seen = [], [], set()
-    exprs = [p for _, polys in cs.gates for p in polys]
-    for _, ins, tabs in cs.lookups:
-        exprs += ins + tabs
-    for e in exprs:
-        for q in sorted(e.queries()):
-            if q in seen:
-                continue
-            seen.add(q)
-            if q[0] == "advice":
-                adv.append((("advice", q[1]), q[2]))
-            elif q[0] == "fixed":
-                fix.append((("fixed", q[1]), q[2]))
-    for kind, idx in cs.permutation_columns:  # equality-enabled columns are queried at the current row
-        q = (kind, idx, 0)
-        if q not in seen:
-            seen.add(q)
-            (adv if kind == "advice" else fix if kind == "fixed" else []).append(((kind, idx), 0))
+    """The (polynomial, rotation) list create_proof opens for a constraint system, in halo2's order -- the order the
+    reference's verifier rebuilds it in (halo2-snark-aggregator-api/src/systems/halo2/params.rs:156-224): instance
+    queries, advice queries (both in REGISTRATION order, `ConstraintSystem.queries`), permutation products
+    (permutation.rs:138-181: (x, omega x) for every set first, then omega^last x for all but the last set in REVERSE set
+    order), lookups (lookup.rs:119-165: z, a', s' at x, a' at omega^-1 x, z at omega x), fixed queries, permutation
+    sigmas, vanishing (h, random; vanish.rs:60-75).  GWC folds poly_batch = poly_batch * v + poly in this order per
+    opening point, so the W commitments depend on it."""
+    out = [(("instance", c), r) for c, r in cs.queries["instance"]]
+    out += [(("advice", c), r) for c, r in cs.queries["advice"]]
     last = -(cs.blinding_factors() + 1)
-    out = list(adv)
+    sets = cs.num_permutation_sets()
+    for s in range(sets):
+        out += [(("perm_z", s), 0), (("perm_z", s), 1)]
+    for s in reversed(range(sets - 1)):
+        out.append((("perm_z", s), last))
+    for i in range(len(cs.lookups)):
+        out += [(("lookup_z", i), 0), (("lookup_input", i), 0), (("lookup_table", i), 0),
+                (("lookup_input", i), -1), (("lookup_z", i), 1)]
+    out += [(("fixed", c), r) for c, r in cs.queries["fixed"]]
+    out += [(("sigma", j), 0) for j in range(len(cs.permutation_columns))]
+    out += [(("h", 0), 0), (("random", 0), 0)]
+    return out
+
+
+def transcript_eval_order(cs):
+    """The order create_proof WRITES its evaluations to the transcript (halo2_proofs plonk/prover.rs), which is the
+    order the reference's verifier reads them back (halo2-snark-aggregator-api/src/systems/halo2/verify.rs:446-462,
+    :198-230 permutation sets, :294-312 lookups): instance evals, advice evals, fixed evals, random_eval, the
+    permutation sigmas, per permutation set z(x), z(omega x) and -- except for the last set -- z(omega^last x), per
+    lookup z(x), z(omega x), a'(x), a'(omega^-1 x), s'(x).  h(x) is never written: the verifier derives it."""
+    out = [(("instance", c), r) for c, r in cs.queries["instance"]]
+    out += [(("advice", c), r) for c, r in cs.queries["advice"]]
+    out += [(("fixed", c), r) for c, r in cs.queries["fixed"]]
+    out.append((("random", 0), 0))
+    out += [(("sigma", j), 0) for j in range(len(cs.permutation_columns))]
+    last = -(cs.blinding_factors() + 1)
     sets = cs.num_permutation_sets()
     for s in range(sets):
         out += [(("perm_z", s), 0), (("perm_z", s), 1)]
         if s + 1 < sets:
             out.append((("perm_z", s), last))
     for i in range(len(cs.lookups)):
-        out += [(("lookup_z", i), 0), (("lookup_input", i), 0), (("lookup_table", i), 0),
-                (("lookup_input", i), -1), (("lookup_z", i), 1)]
-    out += fix
-    out += [(("sigma", j), 0) for j in range(len(cs.permutation_columns))]
-    out += [(("h", 0), 0), (("random", 0), 0)]
+        out += [(("lookup_z", i), 0), (("lookup_z", i), 1), (("lookup_input", i), 0), (("lookup_input", i), -1),
+                (("lookup_table", i), 0)]
     return out

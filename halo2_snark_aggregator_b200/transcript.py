@@ -37,12 +37,20 @@ class ShaWrite:
         self.state.update(bytes(31) + b"\x02" + s.to_bytes(32, "big"))
 
     # -- Montgomery limb inputs as they come out of the library
-    def write_point(self, jac12_or_aff8):
-        """jac12: the 12-limb normalised Jacobian `h2agg_msm_g1` returns (or 8 affine limbs)."""
+    @staticmethod
+    def _affine(jac12_or_aff8):
         limbs = [int(v) for v in jac12_or_aff8]
         if (len(limbs) == 12 and not any(limbs[8:12])) or (len(limbs) == 8 and not any(limbs)):
             raise IOError("cannot write points at infinity to the transcript")
-        x, y = _canon(limbs[0:4], _P, _RINV_P), _canon(limbs[4:8], _P, _RINV_P)
+        return _canon(limbs[0:4], _P, _RINV_P), _canon(limbs[4:8], _P, _RINV_P)
+
+    def common_point(self, jac12_or_aff8):
+        """absorb without emitting (instance commitments: the verifier recomputes them)"""
+        self.common_point_xy(*self._affine(jac12_or_aff8))
+
+    def write_point(self, jac12_or_aff8):
+        """jac12: the 12-limb normalised Jacobian `h2agg_msm_g1` returns (or 8 affine limbs)."""
+        x, y = self._affine(jac12_or_aff8)
         self.common_point_xy(x, y)
         self.out += x.to_bytes(32, "little") + y.to_bytes(32, "little")
 

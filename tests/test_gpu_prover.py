@@ -12,7 +12,7 @@ import oracle_binding as ob
 import quotient_util as qu
 import quotient_ref as qr
 from halo2_snark_aggregator_b200 import plonk
-from halo2_snark_aggregator_b200.prover import ResidentProver, create_proof_queries
+from halo2_snark_aggregator_b200.prover import ResidentProver, create_proof_queries, transcript_eval_order
 from util import domain_consts
 
 pytestmark = pytest.mark.gpu
@@ -95,6 +95,79 @@ def test_resident_prover_matches_oracle_composition(ctx, which, k):
                 acc = [(a * v + b) % R for a, b in zip(acc, c)]
         quo = ob.kate_division(qu.pack(acc), qu.pack([x * pow(w, rot, R) % R]))
         quo = np.concatenate([quo, np.zeros(4, dtype=np.uint64)])
+        assert np.array_equal(wpt, ob.best_multiexp(quo, g)[:8]), "W at rotation %d" % rot
+    pr.close()
+    ctx.srs_release(sid_g)
+    ctx.srs_release(sid_gl)
+
+
+def test_resident_prover_at_k16_matches_the_cpp_oracle_composition(ctx):
+    """The same stage-by-stage check for the aggregation circuit's constraint system at k = 16 (extended domain 2^18:
+    multi-pass NTT plans, table-mode MSM with c = 14, a 55-column evaluate_h over 262 144 coset rows), with the C++
+    oracle on packed arrays throughout: best_multiexp / ifft / coeff_to_extended / the plan-driven evaluate_h (itself
+    equal to the big-int restatement, tests/test_quotient_cpu.py) / extended_to_coeff / eval_polynomial / kate_division."""
+    cs = plonk.aggregation_circuit_cs()
+    k = 16
+    n = 1 << k
+    g = ob.gen_bases(0x6100 + k, n)
+    gl = ob.gen_bases(0x7100 + k, n)
+    sid_g, sid_gl = ctx.srs_register(g), ctx.srs_register(gl)
+    pr = ResidentProver(ctx, cs, k, sid_gl, sid_g)
+    ext_k = pr.ext_k
+    d = domain_consts(k, ext_k)
+    names = list(pr.plan.columns)
+    lag = {nm: ob.gen_scalars(0x9000 + i, 0, n) for i, nm in enumerate(names)}
+    l0, l_last, l_active = qu.lagrange_selectors(k, cs.blinding_factors())
+    lag[("l0", 0)], lag[("l_last", 0)], lag[("l_active_row", 0)] = qu.pack(l0), qu.pack(l_last), qu.pack(l_active)
+    lag[("random", 0)] = ob.gen_scalars(0x9100, 0, n)
+    o_coeff, o_ext = {}, {}
+    for rnd in (names[0::3], names[1::3], names[2::3]):
+        got = pr.commit_columns(rnd, [lag[nm] for nm in rnd])
+        for j, nm in enumerate(rnd):
+            want = ob.best_multiexp(lag[nm], gl)
+            assert np.array_equal(got[j], want[:8]), nm
+            o_coeff[nm] = ob.ifft(lag[nm].copy(), d["omega_inv"], d["n_inv"], k)
+            o_ext[nm] = ob.coeff_to_extended(o_coeff[nm], k, ext_k, d["zeta"], d["omega_ext"])
+            assert np.array_equal(ctx.d2h(pr.coeff[nm], 4 * n), o_coeff[nm]), nm
+            assert np.array_equal(ctx.d2h(pr.ext[nm], 4 << ext_k), o_ext[nm]), nm
+    pr.commit_columns([("random", 0)], [lag[("random", 0)]], extended=False)
+    o_coeff[("random", 0)] = ob.ifft(lag[("random", 0)].copy(), d["omega_inv"], d["n_inv"], k)
+    rng = random.Random(k)
+    y, beta, gamma, theta, x, v = [rng.randrange(R) for _ in range(6)]
+    fr = plonk.fr_mont
+    h_comms = pr.quotient(y, beta, gamma, theta)
+    t_ev = np.concatenate([fr(t) for t in plonk.t_evaluations(k, ext_k)])
+    h = ob.evaluate_h(pr.plan.words, pr.plan.consts, [o_ext[nm] for nm in names], k, ext_k, fr(y), fr(beta), fr(gamma), fr(theta),
+                      d["omega_ext"], d["zeta"], fr(plonk.DELTA), t_ev)
+    q = cs.degree() - 1
+    h_coeff = ob.extended_to_coeff(h, ext_k, d["omega_ext_inv"], d["ext_n_inv"], d["zeta"], n * q)
+    for i in range(q):
+        piece = np.ascontiguousarray(h_coeff[4 * n * i: 4 * n * (i + 1)])
+        o_coeff[("h_piece", i)] = piece
+        assert np.array_equal(h_comms[i], ob.best_multiexp(piece, g)[:8]), "h piece %d" % i
+        assert np.array_equal(ctx.d2h(pr.coeff[("h_piece", i)], 4 * n), piece), "h piece %d coefficients" % i
+    pr.fold_h(x)
+    xn = pow(x, n, R)
+
+    def scale_add(acc, c, poly):     # acc * c + poly on packed arrays through the oracle's field ops
+        return ob.field_op(0, 0, ob.field_op(0, 3, acc, np.tile(fr(c), n)), poly)
+
+    folded = np.zeros(4 * n, dtype=np.uint64)
+    for i in reversed(range(q)):
+        folded = scale_add(folded, xn, o_coeff[("h_piece", i)])
+    o_coeff[("h", 0)] = folded
+    queries = create_proof_queries(cs)
+    evals = pr.evaluate(queries, x)
+    w = qr.omega(k)
+    for (nm, rot), e in zip(queries, evals):
+        assert np.array_equal(e, ob.eval_polynomial(o_coeff[nm], fr(x * pow(w, rot, R) % R))), (nm, rot)
+    order, ws = pr.open(queries, x, v)
+    for rot, wpt in zip(order, ws):
+        acc = np.zeros(4 * n, dtype=np.uint64)
+        for nm, r2 in queries:
+            if r2 == rot:
+                acc = scale_add(acc, v, o_coeff[nm])
+        quo = np.concatenate([ob.kate_division(acc, fr(x * pow(w, rot, R) % R)), np.zeros(4, dtype=np.uint64)])
         assert np.array_equal(wpt, ob.best_multiexp(quo, g)[:8]), "W at rotation %d" % rot
     pr.close()
     ctx.srs_release(sid_g)
@@ -201,14 +274,13 @@ def _drive_proof(ctx, cs, k, lag, sid, sid_g=None):
     rng = random.Random(31)
     t = ShaWrite()
     comm = {}
-    # halo2 absorbs the instance values first (the vk digest before them is an external-crate format: not restated)
-    for v in lag[("instance", 0)]:
-        t.common_scalar_int(v)
+    # (the vk digest halo2 absorbs first is an external-crate format: not restated)
     pk = [nm for nm in lag if nm[0] in ("fixed", "sigma", "l0", "l_last", "l_active_row")]
     comm.update(zip(pk, pr.commit_columns(pk, [qu.pack(lag[nm]) for nm in pk], keep_lagrange=True)))   # keygen: not part of the proof
     wit = [("instance", 0)] + [("advice", i) for i in range(cs.num_advice)]
     cw = pr.commit_columns(wit, [qu.pack(lag[nm]) for nm in wit], keep_lagrange=True)
     comm.update(zip(wit, cw))
+    t.common_point(cw[0])          # instance commitment: absorbed, not written (API/systems/halo2/verify.rs:74-92)
     for c in cw[1:]:
         t.write_point(c)                                                                  # advice commitments
     theta = t.squeeze_challenge()
@@ -233,19 +305,20 @@ def _drive_proof(ctx, cs, k, lag, sid, sid_g=None):
         t.write_point(c)
     x = t.squeeze_challenge()
     pr.fold_h(x)
-    queries = create_proof_queries(cs) + [(("instance", 0), 0)]
+    queries = create_proof_queries(cs)
     evals = pr.evaluate(queries, x)
-    for e in evals[:-1]:
-        t.write_scalar(e)
+    ev_limbs = dict(zip(queries, evals))
+    for q in transcript_eval_order(cs):      # halo2's write order; h(x) is not part of the proof
+        t.write_scalar(ev_limbs[q])
     v = t.squeeze_challenge()
-    order, ws = pr.open(queries[:-1], x, v)
+    order, ws = pr.open(queries, x, v)
     for c in ws:
         t.write_point(c)
     proof = t.finalize()
     ev = {q: qu.unpack(e)[0] for q, e in zip(queries, evals)}
     pr.close()
     return dict(x=x, y=y, beta=beta, gamma=gamma, theta=theta, v=v, ev=ev, proof=proof, n_w=len(ws), comm=comm, order=order,
-                ws=ws, queries=queries[:-1])
+                ws=ws, queries=queries)
 
 
 def _valid_aggregation_witness(k, seed):
@@ -290,7 +363,8 @@ def test_device_proof_satisfies_the_reference_verifiers_equation(ctx):
 
     want = qr.verifier_h_eval(desc, ev, k, out["x"], out["y"], out["beta"], out["gamma"], out["theta"])
     assert out["ev"][(("h", 0), 0)] == want
-    # proof bytes: 5 + 14 + 9 + 1 + 4 + 4 points of 64 B and 70 scalars of 32 B
+    # proof bytes: 5 + 14 + 9 + 1 + 4 + 4 points of 64 B and 71 scalars of 32 B (1 instance, 6 advice, 17 fixed,
+    # 1 random, 6 sigma, 5 permutation z, 35 lookup: SURVEY.md App. C)
     assert out["n_w"] == 4 and len(out["proof"]) == 64 * (5 + 14 + 9 + 1 + 4 + 4) + 32 * 71
 
     # a broken copy constraint: same flow, the verifier's equation must fail

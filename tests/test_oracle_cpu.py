@@ -256,3 +256,42 @@ def test_cpp_argument_restatements_match_the_python_ones():
                                      qu.pack([beta * pow(lr.DELTA, first, R) % R]), qu.pack([lr.DELTA]), qu.pack([beta]), qu.pack([gamma]),
                                      qu.pack([lz]) if lz is not None else None)
         assert qu.unpack(got) == lr.permutation_product(values, sigmas, k, w, beta, gamma, first, lz if lz is not None else 1)
+
+
+# ---------------------------------------------------------------- external known answers (not minted by this repository)
+def _kat_point(x_hex, y_hex):
+    from util import fq_limbs
+    return np.concatenate([fq_limbs(int(x_hex, 16)), fq_limbs(int(y_hex, 16))])
+
+
+def test_external_kat_ecmul_ecadd_pin_both_oracles():
+    """EIP-196 ecMul / ecAdd vectors (tests/golden/make_external_kat.py): the precompiles the reference's generated
+    verifier calls (halo2-snark-aggregator-solidity/templates/verifier.sol:159-215).  An MSM of one pair is ecMul, an
+    MSM of two pairs with unit scalars is ecAdd -- through best_multiexp (bucket method), the naive double-and-add and
+    the Python big-int group law."""
+    kat = golden("external_kat.json")
+    one = fr_limbs(1)
+    for c in kat["ecmul"]:
+        s = int(c["scalar"], 16) % ref.R
+        base = _kat_point(c["x"], c["y"])
+        want = _kat_point(c["out_x"], c["out_y"])
+        assert np.array_equal(affine_of(ob.best_multiexp(fr_limbs(s), base)), want), c["name"]
+        assert np.array_equal(affine_of(ob.msm_naive(fr_limbs(s), base)), want), c["name"]
+        assert ref.g1_mul(s, (int(c["x"], 16), int(c["y"], 16))) == (int(c["out_x"], 16), int(c["out_y"], 16))
+    for c in kat["ecadd"]:
+        bases = np.concatenate([_kat_point(c["ax"], c["ay"]), _kat_point(c["bx"], c["by"])])
+        want = _kat_point(c["out_x"], c["out_y"])
+        assert np.array_equal(affine_of(ob.best_multiexp(np.concatenate([one, one]), bases)), want), c["name"]
+
+
+def test_moduli_equal_the_reference_templates_constants():
+    """q_mod / p_mod as the reference's Solidity template holds them (verifier.sol:41, :144, :292): the oracle's -1
+    in either field must be modulus - 1."""
+    m = golden("external_kat.json")["moduli"]
+    r, p = int(m["q_mod_decimal"]), int(m["p_mod_decimal"])
+    assert r == int(m["r_hex"], 16) == ref.R and p == ref.P
+    for field, mod in ((0, r), (1, p)):
+        lim = fr_limbs if field == 0 else __import__("util").fq_limbs
+        minus_one = ob.field_op(field, 1, lim(0), lim(1))          # 0 - 1
+        assert np.array_equal(minus_one, lim(mod - 1))
+        assert np.array_equal(ob.field_op(field, 0, minus_one, lim(1)), lim(0))  # (mod - 1) + 1 wraps to 0
