@@ -12,4 +12,4 @@ from .context import Context, default_context  # noqa: F401
 from .arithmetic import best_fft, best_multiexp  # noqa: F401
 from .domain import EvaluationDomain  # noqa: F401
 from .params import ParamsKZG  # noqa: F401
-from .witness import B200EccChip  # noqa: F401
+from .witness import B200Context, B200EccChip, B200EncodeChip, B200ScalarChip  # noqa: F401

@@ -50,7 +50,7 @@ def load():
             "libh2agg.so is not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'`. "
             "There is no CPU fallback for the product path." % LIB_PATH)
     lib = ctypes.CDLL(LIB_PATH)
-    sz, u32, u64, ci = ctypes.c_size_t, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_int
+    sz, u32, u64, ci, i64 = ctypes.c_size_t, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_int, ctypes.c_int64
     sig = {
         "h2agg_init": (ci, [ci, ctypes.POINTER(c_vp)]),
         "h2agg_destroy": (None, [c_vp]),
@@ -129,6 +129,21 @@ def load():
         "h2agg_wit_ecc_shamir": (ctypes.c_int64, [c_vp, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64), sz]),
         "h2agg_wit_ecc_constant_mul": (ctypes.c_int64, [c_vp, c_vp, ctypes.c_int64]),
         "h2agg_wit_point_value": (ci, [c_vp, ctypes.c_int64, c_vp, ctypes.POINTER(ci)]),
+        "h2agg_wit_field_assign_const": (i64, [c_vp, c_vp]),
+        "h2agg_wit_field_add": (i64, [c_vp, i64, i64]),
+        "h2agg_wit_field_sub": (i64, [c_vp, i64, i64]),
+        "h2agg_wit_field_mul": (i64, [c_vp, i64, i64]),
+        "h2agg_wit_field_square": (i64, [c_vp, i64]),
+        "h2agg_wit_field_div": (i64, [c_vp, i64, i64]),
+        "h2agg_wit_field_sum_with_coeff_and_constant": (i64, [c_vp, ctypes.POINTER(i64), c_vp, sz, c_vp]),
+        "h2agg_wit_field_mul_add_constant": (i64, [c_vp, i64, i64, c_vp]),
+        "h2agg_wit_scalar_value": (ci, [c_vp, i64, c_vp]),
+        "h2agg_wit_scalar_cell": (ci, [c_vp, i64, ctypes.POINTER(u32), ctypes.POINTER(u32)]),
+        "h2agg_wit_encode_point": (ci, [c_vp, i64, ctypes.POINTER(i64)]),
+        "h2agg_wit_ecc_assign_identity": (i64, [c_vp]),
+        "h2agg_wit_ecc_assert_equal": (ci, [c_vp, i64, i64]),
+        "h2agg_wit_assert_not_identity": (ci, [c_vp, i64]),
+        "h2agg_wit_expose_final_pair": (ci, [c_vp, i64, i64, ctypes.POINTER(i64)]),
         "h2agg_witness_expand": (ci, [c_vp, c_vp, ctypes.POINTER(c_vp), sz]),
         "h2agg_witness_expand_dev": (ci, [c_vp, c_vp, ctypes.POINTER(c_vp), sz]),
         "h2agg_fr_repr": (ci, [c_vp, ci, c_vp, c_vp, sz]),

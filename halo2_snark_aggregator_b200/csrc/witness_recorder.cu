@@ -189,6 +189,135 @@ static Fq q_inv(const Fq& a) {
   return q_mul(Fq{{x[0], x[1], x[2], x[3]}}, r3);
 }
 
+
+// ---- host Fr on CANONICAL 256-bit values (native scalars of the ScalarChip, gates/base_gate.rs BaseGateOps) -----
+// AssignedValue<Fr> handles carry canonical integers (that is what decompose_scalar and the RAW256 records consume);
+// a product is two Montgomery steps: mont(mont(a, b), R^2) = a b.
+namespace fr {
+static const u64 RP[4] = {0x43e1f593f0000001ULL, 0x2833e84879b97091ULL, 0xb85045b68181585dULL, 0x30644e72e131a029ULL};
+static const u64 RR2[4] = {0x1bb8e645ae216da7ULL, 0x53fe3ab1e35c59e3ULL, 0x8c49833d53bb8085ULL, 0x0216d0b17f4e44a5ULL};
+static const u64 RINV = 0xc2e1f593efffffffULL;
+struct V {
+  u64 v[4];
+};
+static inline V zero() { return V{{0, 0, 0, 0}}; }
+static inline V small(u64 x) { return V{{x, 0, 0, 0}}; }
+static inline V from_u128(u128 x) { return V{{(u64)x, (u64)(x >> 64), 0, 0}}; }
+static inline bool is_zero(const V& a) { return (a.v[0] | a.v[1] | a.v[2] | a.v[3]) == 0; }
+static inline bool geq_p(const u64* a) {
+  for (int i = 3; i >= 0; i--) {
+    if (a[i] > RP[i]) return true;
+    if (a[i] < RP[i]) return false;
+  }
+  return true;
+}
+static inline void sub_p(u64* a) {
+  u64 b = 0;
+  for (int i = 0; i < 4; i++) {
+    u128 d = (u128)a[i] - RP[i] - b;
+    a[i] = (u64)d;
+    b = (u64)(d >> 64) & 1;
+  }
+}
+static inline V add(const V& a, const V& b) {
+  V r;
+  u128 c = 0;
+  for (int i = 0; i < 4; i++) {
+    c += (u128)a.v[i] + b.v[i];
+    r.v[i] = (u64)c;
+    c >>= 64;
+  }
+  if (geq_p(r.v)) sub_p(r.v);
+  return r;
+}
+static inline V sub(const V& a, const V& b) {
+  V r;
+  u64 bo = 0;
+  for (int i = 0; i < 4; i++) {
+    u128 d = (u128)a.v[i] - b.v[i] - bo;
+    r.v[i] = (u64)d;
+    bo = (u64)(d >> 64) & 1;
+  }
+  if (bo) {
+    u128 c = 0;
+    for (int i = 0; i < 4; i++) {
+      c += (u128)r.v[i] + RP[i];
+      r.v[i] = (u64)c;
+      c >>= 64;
+    }
+  }
+  return r;
+}
+static inline V neg(const V& a) { return sub(zero(), a); }
+static inline V mont(const V& a, const V& b) {
+  u64 t[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < 4; i++) {
+    u128 c = 0;
+    for (int j = 0; j < 4; j++) {
+      c += (u128)a.v[j] * b.v[i] + t[j];
+      t[j] = (u64)c;
+      c >>= 64;
+    }
+    c += t[4];
+    t[4] = (u64)c;
+    t[5] = (u64)(c >> 64);
+    u64 m = t[0] * RINV;
+    c = ((u128)m * RP[0] + t[0]) >> 64;
+    for (int j = 1; j < 4; j++) {
+      c += (u128)m * RP[j] + t[j];
+      t[j - 1] = (u64)c;
+      c >>= 64;
+    }
+    c += t[4];
+    t[3] = (u64)c;
+    t[4] = t[5] + (u64)(c >> 64);
+  }
+  V r{{t[0], t[1], t[2], t[3]}};
+  if (t[4] || geq_p(r.v)) sub_p(r.v);
+  return r;
+}
+static inline V mul(const V& a, const V& b) { return mont(mont(a, b), V{{RR2[0], RR2[1], RR2[2], RR2[3]}}); }
+static inline void half(u64* x) {
+  u64 top = 0;
+  if (x[0] & 1) {
+    u128 c = 0;
+    for (int i = 0; i < 4; i++) {
+      c += (u128)x[i] + RP[i];
+      x[i] = (u64)c;
+      c >>= 64;
+    }
+    top = (u64)c;
+  }
+  u256_shr1(x, top);
+}
+// binary extended Euclid on the canonical value: a^-1 mod r (0 -> 0)
+static V inv(const V& a) {
+  if (is_zero(a)) return zero();
+  u64 u[4] = {a.v[0], a.v[1], a.v[2], a.v[3]};
+  u64 v[4] = {RP[0], RP[1], RP[2], RP[3]};
+  V x1 = small(1), x2 = zero();
+  while (!u256_is_one(u) && !u256_is_one(v)) {
+    while (!(u[0] & 1)) {
+      u256_shr1(u, 0);
+      half(x1.v);
+    }
+    while (!(v[0] & 1)) {
+      u256_shr1(v, 0);
+      half(x2.v);
+    }
+    if (u256_geq(u, v)) {
+      u256_sub(u, v);
+      x1 = sub(x1, x2);
+    } else {
+      u256_sub(v, u);
+      x2 = sub(x2, x1);
+    }
+  }
+  return u256_is_one(u) ? x1 : x2;
+}
+static inline bool canonical(const u64* a) { return !geq_p(a); }
+}  // namespace fr
+
 // ---- assigned objects (value semantics: a C++ copy is a Rust `.clone()`) ---------------------------
 struct Cell {
   uint32_t row = 0;
@@ -199,6 +328,7 @@ struct HInt {  // AssignedInteger, chips/integer_chip.rs:12-48
   Cell cell[4];
   uint32_t overflows = 0;
   bool native_cached = false;
+  Cell native_cell;  // where the cached native lives (column 0 of its sum row), valid when native_cached
   Fq w;  // value mod p (Montgomery)
 };
 struct HCond {  // AssignedCondition / small AssignedValue
@@ -378,6 +508,7 @@ struct Recorder {
     op.row = offset;
     put_limbs(op.v, a);
     ops.push_back(op);
+    a.native_cell = Cell{offset, 0};
     offset += 1;
     a.native_cached = true;
   }
@@ -455,6 +586,7 @@ struct Recorder {
     offset += 4 + 1 + 1 + (a.native_cached ? 0 : 1) + 2;
     rem.overflows = 0;
     rem.native_cached = true;
+    rem.native_cell = Cell{r0 + 5, 0};  // native(rem) follows the [d, v] row
     a = rem;
   }
   void conditionally_reduce(HInt& a) {
@@ -537,10 +669,11 @@ struct Recorder {
     HInt& fresh = fresh_is_y ? *y : z;
     for (int i = 0; i < 4; i++) fresh.cell[i] = Cell{offset + (uint32_t)(3 - i), 4};
     uint32_t rows = 4 + 4 + 10 + 4 + 4;
-    rows += x.native_cached ? 0 : 1;
-    if (!sq) rows += y->native_cached ? 0 : 1;
+    // natives in the order _mul_equation_on_native asks for them: a, b, (d), rem   :254-320
+    if (!x.native_cached) x.native_cell = Cell{offset + rows++, 0};
+    if (!sq && !y->native_cached) y->native_cell = Cell{offset + rows++, 0};
     rows += 1;
-    rows += z.native_cached ? 0 : 1;
+    if (!z.native_cached) z.native_cell = Cell{offset + rows++, 0};
     rows += 1;
     offset += rows;
     x.native_cached = true;
@@ -580,6 +713,7 @@ struct Recorder {
     put_limbs(op.v, a);
     ops.push_back(op);
     uint32_t rows = 1 + 2 + (a.native_cached ? 0 : 1) + 1 + 2 + 1 + 2 + 1 + 1;
+    if (!a.native_cached) a.native_cell = Cell{offset + 3, 0};  // after is_pure_zero's sum + 2 inversion rows
     offset += rows;
     a.native_cached = true;
     HCond c;
@@ -828,6 +962,135 @@ struct Recorder {
     }
     return acc;
   }
+
+  // ---- ScalarChip = BaseGateOps on native Fr values (halo2-snark-aggregator-circuit/src/chips/scalar_chip.rs:17-127
+  // over gates/base_gate.rs:193-511).  Every recipe is one or more RAW256 rows of canonical cells; the value the chain
+  // continues with is computed here (a handful of host products per row -- the native-field part of an aggregation
+  // witness is ~5 % of its rows, the wrong-field part goes through the expansion kernel).
+  HScalar sc_cell(const fr::V& v, uint32_t row, uint8_t col) {
+    HScalar s;
+    memcpy(s.v, v.v, 32);
+    s.cell = Cell{row, col};
+    return s;
+  }
+  static fr::V sv(const HScalar& s) { return fr::V{{s.v[0], s.v[1], s.v[2], s.v[3]}}; }
+  uint32_t sc_row(const fr::V* c0, const fr::V* c1 = nullptr, const fr::V* c2 = nullptr, const fr::V* c3 = nullptr,
+                  const fr::V* c4 = nullptr) {
+    u64 cells[5][4];
+    memset(cells, 0, sizeof(cells));
+    const fr::V* c[5] = {c0, c1, c2, c3, c4};
+    for (int i = 0; i < 5; i++)
+      if (c[i]) memcpy(cells[i], c[i]->v, 32);
+    return raw256_row(cells);
+  }
+  HScalar sc_assign(const fr::V& v) {  // BaseGateOps::assign / assign_constant: advice [v, 0, 0, 0, 0]   :499-511
+    return sc_cell(v, sc_row(&v), 0);
+  }
+  // BaseGateOps::sum_with_constant (:193-262): sum_i coeff_i * elem_i + constant, chained over rows through next_coeff
+  HScalar sc_sum_with_constant(const std::vector<std::pair<HScalar, fr::V>>& elems, const fr::V& constant) {
+    const size_t columns = 5;
+    bool have_acc = false;
+    fr::V acc = fr::zero();
+    size_t curr = 0;
+    while (elems.size() - curr + (have_acc ? 1 : 0) + 1 > columns) {
+      const size_t line_len = columns - (have_acc ? 1 : 0);
+      fr::V line_sum = fr::zero();
+      fr::V cells[5] = {fr::zero(), fr::zero(), fr::zero(), fr::zero(), fr::zero()};
+      for (size_t i = 0; i < line_len; i++) {
+        cells[i] = sv(elems[curr + i].first);
+        line_sum = fr::add(line_sum, fr::mul(cells[i], elems[curr + i].second));
+      }
+      if (have_acc) cells[4] = acc;  // one_line_with_last_base: the running sum rides in the last column
+      sc_row(&cells[0], &cells[1], &cells[2], &cells[3], &cells[4]);
+      curr += line_len;
+      acc = fr::add(acc, line_sum);
+      have_acc = true;
+    }
+    fr::V sum = fr::add(constant, acc);
+    fr::V cells[5] = {fr::zero(), fr::zero(), fr::zero(), fr::zero(), fr::zero()};
+    size_t k = 1;
+    for (size_t i = curr; i < elems.size(); i++, k++) {
+      cells[k] = sv(elems[i].first);
+      sum = fr::add(sum, fr::mul(cells[k], elems[i].second));
+    }
+    cells[0] = sum;
+    if (have_acc) cells[4] = acc;
+    return sc_cell(sum, sc_row(&cells[0], &cells[1], &cells[2], &cells[3], &cells[4]), 0);
+  }
+  HScalar sc_add(const HScalar& a, const HScalar& b) { return sc_sum_with_constant({{a, fr::small(1)}, {b, fr::small(1)}}, fr::zero()); }
+  HScalar sc_sub(const HScalar& a, const HScalar& b) {
+    return sc_sum_with_constant({{a, fr::small(1)}, {b, fr::neg(fr::small(1))}}, fr::zero());
+  }
+  HScalar sc_mul(const HScalar& a, const HScalar& b) {  // :302-324 [a, b, c] -> cells[2]
+    fr::V x = sv(a), y = sv(b), c = fr::mul(x, y);
+    return sc_cell(c, sc_row(&x, &y, &c), 2);
+  }
+  HScalar sc_div_unsafe(const HScalar& a, const HScalar& b) {  // :478-497 [b, c, a] -> cells[1]; b = 0 panics in Rust
+    fr::V x = sv(a), y = sv(b);
+    if (fr::is_zero(y)) throw std::runtime_error("div_unsafe: division by zero (the reference unwraps the inverse)");
+    fr::V c = fr::mul(fr::inv(y), x);
+    return sc_cell(c, sc_row(&y, &c, &x), 1);
+  }
+  HScalar sc_mul_add_constant(const HScalar& a, const HScalar& b, const fr::V& c) {  // :326-349 [a, b, d] -> cells[2]
+    fr::V x = sv(a), y = sv(b), d = fr::add(fr::mul(x, y), c);
+    return sc_cell(d, sc_row(&x, &y, &d), 2);
+  }
+  // value of IntegerChip::native(a) = sum_i limb_i * 2^(68 i) in Fr (limbs may carry overflow)   five/integer_chip.rs:595-621
+  static fr::V native_value(const HInt& a) {
+    static const fr::V E[4] = {fr::V{{1, 0, 0, 0}}, fr::V{{0, 0x10, 0, 0}}, fr::V{{0, 0, 0x100, 0}}, fr::V{{0, 0, 0, 0x1000}}};
+    fr::V acc = fr::zero();
+    for (int i = 0; i < 4; i++) acc = fr::add(acc, fr::mul(fr::from_u128(a.limb[i]), E[i]));
+    return acc;
+  }
+  // PoseidonEncodeChip::encode_point (chips/encode_chip.rs:18-33): native(x), native(y) on CLONES of the coordinates
+  // (the caches the clones acquire are dropped, so encoding the same point again costs the rows again)
+  void encode_point(const HPoint& p, HScalar out[2]) {
+    HInt px = p.x, py = p.y;
+    native(px);
+    out[0] = sc_cell(native_value(px), px.native_cell.row, px.native_cell.col);
+    native(py);
+    out[1] = sc_cell(native_value(py), py.native_cell.row, py.native_cell.col);
+  }
+  HScalar int_get_last_bit(const HInt& a) {  // five/integer_chip.rs:874-901 (a reduced: limb 0 < 2^68)
+    const u128 l0 = a.limb[0];
+    const u128 d = l0 >> 1;
+    const u64 bit = (u64)(l0 & 1);
+    limb_row(d, 4);                            // assign_nonleading_limb(l0 / 2)
+    uint32_t r = row5(d, bit, l0);             // 2 d + bit - l0 = 0
+    bg_assert_bit(bit);
+    return sc_cell(fr::small(bit), r, 1);
+  }
+  // Halo2VerifierCircuits::synthesize, second region (verify_circuit.rs:264-368): reduce the four coordinates, take the
+  // parity bits of the y's, pack x (and the bit) into two 136-bit halves per point -> the four cells bound to the
+  // instance column by constrain_instance.
+  void expose_final_pair(HPoint p[2], HScalar out[4]) {
+    static const fr::V E1{{0, 0x10, 0, 0}}, E2{{0, 0, 0x100, 0}};
+    for (int i = 0; i < 2; i++) {
+      reduce(p[i].x);
+      reduce(p[i].y);
+    }
+    HScalar bit[2];
+    for (int i = 0; i < 2; i++) bit[i] = int_get_last_bit(p[i].y);
+    for (int i = 0; i < 2; i++) {
+      const HInt& x = p[i].x;
+      HScalar l[4];
+      for (int j = 0; j < 4; j++) l[j] = sc_cell(fr::from_u128(x.limb[j]), x.cell[j].row, x.cell[j].col);
+      out[2 * i] = sc_sum_with_constant({{l[0], fr::small(1)}, {l[1], E1}}, fr::zero());
+      out[2 * i + 1] = sc_sum_with_constant({{l[2], fr::small(1)}, {l[3], E1}, {bit[i], E2}}, fr::zero());
+    }
+  }
+  // EccChipOps::assert_equal (chips/ecc_chip.rs:528-548), used for the `coherent` commitments (verify_circuit.rs:487-493)
+  void ecc_assert_equal(HPoint& a, HPoint& b) {
+    HCond eq_x = int_is_equal(a.x, b.x);
+    HCond eq_y = int_is_equal(a.y, b.y);
+    HCond eq_z = bg_xnor(eq_x, eq_y);
+    HCond eq_xy = bg_mul(eq_x, eq_y);
+    HCond eq_xyz = bg_mul(eq_xy, eq_z);
+    HCond both = bg_mul(a.z, b.z);
+    HCond eq = bg_or(eq_xyz, both);
+    if (!eq.value) throw std::runtime_error("assert_equal: the points differ");
+    bg_assert_constant(eq);
+  }
 };
 
 // native affine group law for constant_mul's table of constants (host, Fq Montgomery)
@@ -901,6 +1164,10 @@ int64_t h2agg_wit_assign_constant_point(h2agg_witness* w, const uint64_t xy[8]) 
 }
 // scalar: Montgomery Fr (4 limbs) as the chips hold it; assigned with BaseGateOps::assign (1 row)
 int64_t h2agg_wit_assign_scalar(h2agg_witness* w, const uint64_t s_canonical[4]) {
+  if (!s_canonical || !fr::canonical(s_canonical)) {
+    w->err = "assign_scalar: NULL or not a canonical value < r";
+    return -1;
+  }
   HScalar s;
   memcpy(s.v, s_canonical, 32);
   uint64_t cells[5][4];
@@ -910,32 +1177,41 @@ int64_t h2agg_wit_assign_scalar(h2agg_witness* w, const uint64_t s_canonical[4])
   w->rec.scalars.push_back(s);
   return (int64_t)w->rec.scalars.size() - 1;
 }
+// The trait-level operations take their operands the way the reference's adapter does
+// (halo2-snark-aggregator-circuit/src/chips/ecc_chip.rs:34-52, 99-131): `add` runs on `a.clone()` and `b.clone()`,
+// `sub` on `a.clone()`, `scalar_mul` on `rhs.clone()`, `normalize` on `v.clone()`, `multi_exp` on a moved Vec.  The
+// curvature / native caches an operation fills in are therefore DROPPED with the clone: a handle keeps the caches it had
+// when it was created, and a later operation on it pays for the curvature rows again -- part of the row layout.
 int64_t h2agg_wit_ecc_add(h2agg_witness* w, int64_t a, int64_t b) {
   WIT_TRY(w, {
+    HPoint aa = w->rec.points.at(a);
     HPoint bb = w->rec.points.at(b);
-    HPoint r = w->rec.ecc_add(w->rec.points.at(a), bb);
+    HPoint r = w->rec.ecc_add(aa, bb);
     w->rec.points.push_back(r);
   });
   return (int64_t)w->rec.points.size() - 1;
 }
 int64_t h2agg_wit_ecc_sub(h2agg_witness* w, int64_t a, int64_t b) {
   WIT_TRY(w, {
+    HPoint aa = w->rec.points.at(a);
     HPoint bb = w->rec.points.at(b);
-    HPoint r = w->rec.ecc_sub(w->rec.points.at(a), bb);
+    HPoint r = w->rec.ecc_sub(aa, bb);
     w->rec.points.push_back(r);
   });
   return (int64_t)w->rec.points.size() - 1;
 }
 int64_t h2agg_wit_ecc_double(h2agg_witness* w, int64_t a) {
   WIT_TRY(w, {
-    HPoint r = w->rec.ecc_double(w->rec.points.at(a));
+    HPoint aa = w->rec.points.at(a);
+    HPoint r = w->rec.ecc_double(aa);
     w->rec.points.push_back(r);
   });
   return (int64_t)w->rec.points.size() - 1;
 }
 int64_t h2agg_wit_ecc_reduce(h2agg_witness* w, int64_t a) {
   WIT_TRY(w, {
-    HPoint r = w->rec.ecc_reduce(w->rec.points.at(a));
+    HPoint aa = w->rec.points.at(a);
+    HPoint r = w->rec.ecc_reduce(aa);
     w->rec.points.push_back(r);
   });
   return (int64_t)w->rec.points.size() - 1;
@@ -943,7 +1219,8 @@ int64_t h2agg_wit_ecc_reduce(h2agg_witness* w, int64_t a) {
 // ArithEccChip::scalar_mul -> EccChipOps::mul
 int64_t h2agg_wit_ecc_mul(h2agg_witness* w, int64_t a, int64_t s) {
   WIT_TRY(w, {
-    HPoint r = w->rec.ecc_mul(w->rec.points.at(a), w->rec.scalars.at(s));
+    HPoint aa = w->rec.points.at(a);
+    HPoint r = w->rec.ecc_mul(aa, w->rec.scalars.at(s));
     w->rec.points.push_back(r);
   });
   return (int64_t)w->rec.points.size() - 1;
@@ -986,6 +1263,108 @@ int64_t h2agg_wit_ecc_constant_mul(h2agg_witness* w, const uint64_t base_xy[8], 
     r.points.push_back(acc);
   });
   return (int64_t)w->rec.points.size() - 1;
+}
+
+// ---- ArithFieldChip: ScalarChip over the base gate (halo2-snark-aggregator-circuit/src/chips/scalar_chip.rs:17-127,
+//      trait at halo2-snark-aggregator-api/src/arith/field.rs:6-105, common.rs:3-42).  Scalars are CANONICAL < r. -----
+static bool scalar_arg_ok(h2agg_witness* w, const uint64_t* v) {
+  if (!v || !fr::canonical(v)) {
+    w->err = "scalar argument is NULL or not a canonical value < r";
+    return false;
+  }
+  return true;
+}
+static int64_t push_scalar(h2agg_witness* w, const HScalar& s) {
+  w->rec.scalars.push_back(s);
+  return (int64_t)w->rec.scalars.size() - 1;
+}
+int64_t h2agg_wit_field_assign_const(h2agg_witness* w, const uint64_t c_canonical[4]) {  // assign_const / _zero / _one
+  if (!scalar_arg_ok(w, c_canonical)) return -1;
+  return push_scalar(w, w->rec.sc_assign(fr::V{{c_canonical[0], c_canonical[1], c_canonical[2], c_canonical[3]}}));
+}
+int64_t h2agg_wit_field_add(h2agg_witness* w, int64_t a, int64_t b) {
+  WIT_TRY(w, { return push_scalar(w, w->rec.sc_add(w->rec.scalars.at(a), w->rec.scalars.at(b))); });
+}
+int64_t h2agg_wit_field_sub(h2agg_witness* w, int64_t a, int64_t b) {
+  WIT_TRY(w, { return push_scalar(w, w->rec.sc_sub(w->rec.scalars.at(a), w->rec.scalars.at(b))); });
+}
+int64_t h2agg_wit_field_mul(h2agg_witness* w, int64_t a, int64_t b) {
+  WIT_TRY(w, { return push_scalar(w, w->rec.sc_mul(w->rec.scalars.at(a), w->rec.scalars.at(b))); });
+}
+int64_t h2agg_wit_field_square(h2agg_witness* w, int64_t a) { return h2agg_wit_field_mul(w, a, a); }  // scalar_chip.rs:101-107
+int64_t h2agg_wit_field_div(h2agg_witness* w, int64_t a, int64_t b) {  // div_unsafe
+  WIT_TRY(w, { return push_scalar(w, w->rec.sc_div_unsafe(w->rec.scalars.at(a), w->rec.scalars.at(b))); });
+}
+int64_t h2agg_wit_field_sum_with_coeff_and_constant(h2agg_witness* w, const int64_t* elems, const uint64_t* coeffs_canonical,
+                                                    size_t n, const uint64_t constant_canonical[4]) {
+  if (!scalar_arg_ok(w, constant_canonical)) return -1;
+  WIT_TRY(w, {
+    std::vector<std::pair<HScalar, fr::V>> e;
+    for (size_t i = 0; i < n; i++) {
+      if (!scalar_arg_ok(w, coeffs_canonical + 4 * i)) return -1;
+      e.push_back({w->rec.scalars.at(elems[i]), fr::V{{coeffs_canonical[4 * i], coeffs_canonical[4 * i + 1], coeffs_canonical[4 * i + 2], coeffs_canonical[4 * i + 3]}}});
+    }
+    return push_scalar(w, w->rec.sc_sum_with_constant(e, fr::V{{constant_canonical[0], constant_canonical[1], constant_canonical[2], constant_canonical[3]}}));
+  });
+}
+int64_t h2agg_wit_field_mul_add_constant(h2agg_witness* w, int64_t a, int64_t b, const uint64_t c_canonical[4]) {
+  if (!scalar_arg_ok(w, c_canonical)) return -1;
+  WIT_TRY(w, {
+    return push_scalar(w, w->rec.sc_mul_add_constant(w->rec.scalars.at(a), w->rec.scalars.at(b),
+                                                     fr::V{{c_canonical[0], c_canonical[1], c_canonical[2], c_canonical[3]}}));
+  });
+}
+int h2agg_wit_scalar_value(h2agg_witness* w, int64_t h, uint64_t out_canonical[4]) {  // to_value
+  if (h < 0 || (size_t)h >= w->rec.scalars.size()) return -1;
+  memcpy(out_canonical, w->rec.scalars[h].v, 32);
+  return 0;
+}
+int h2agg_wit_scalar_cell(h2agg_witness* w, int64_t h, uint32_t* column, uint32_t* row) {  // AssignedValue.cell
+  if (h < 0 || (size_t)h >= w->rec.scalars.size()) return -1;
+  *column = w->rec.scalars[h].cell.col;
+  *row = w->rec.scalars[h].cell.row;
+  return 0;
+}
+
+// ---- Encode: PoseidonEncodeChip (halo2-snark-aggregator-circuit/src/chips/encode_chip.rs:14-51) --------------------
+int h2agg_wit_encode_point(h2agg_witness* w, int64_t point, int64_t out_natives[2]) {
+  WIT_TRY(w, {
+    HScalar n2[2];
+    w->rec.encode_point(w->rec.points.at(point), n2);
+    out_natives[0] = push_scalar(w, n2[0]);
+    out_natives[1] = push_scalar(w, n2[1]);
+  });
+  return 0;
+}
+
+// ---- what Halo2VerifierCircuits::synthesize does around the chips (verify_circuit.rs:264-368, 487-496) ---------------
+int64_t h2agg_wit_ecc_assign_identity(h2agg_witness* w) {  // ArithCommonChip::assign_zero of the EccChip
+  WIT_TRY(w, { w->rec.points.push_back(w->rec.assign_identity()); });
+  return (int64_t)w->rec.points.size() - 1;
+}
+int h2agg_wit_ecc_assert_equal(h2agg_witness* w, int64_t a, int64_t b) {
+  WIT_TRY(w, {
+    HPoint aa = w->rec.points.at(a);   // `&mut commits[..].clone()` on the left, in place on the right (:488-492)
+    w->rec.ecc_assert_equal(aa, w->rec.points.at(b));
+  });
+  return 0;
+}
+int h2agg_wit_assert_not_identity(h2agg_witness* w, int64_t point) {  // base_gate.assert_false(&p.z)
+  WIT_TRY(w, {
+    const HPoint& p = w->rec.points.at(point);
+    if (p.z.value) throw std::runtime_error("assert_false: the point is the identity");
+    w->rec.bg_assert_constant(p.z);
+  });
+  return 0;
+}
+int h2agg_wit_expose_final_pair(h2agg_witness* w, int64_t w_x, int64_t w_g, int64_t out_cells[4]) {
+  WIT_TRY(w, {
+    HPoint p[2] = {w->rec.points.at(w_x), w->rec.points.at(w_g)};
+    HScalar out[4];
+    w->rec.expose_final_pair(p, out);
+    for (int i = 0; i < 4; i++) out_cells[i] = push_scalar(w, out[i]);
+  });
+  return 0;
 }
 // value of a point handle: canonical affine (x mod p, y mod p) as Montgomery limbs + identity flag
 int h2agg_wit_point_value(h2agg_witness* w, int64_t h, uint64_t out_xy[8], int* is_identity) {

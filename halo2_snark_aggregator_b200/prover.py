@@ -248,7 +248,9 @@ class ResidentProver:
     # -- stage 6: GWC multi-opening ---------------------------------------------------------------------
     def open(self, queries, x, v):
         """halo2_proofs poly/kzg/multiopen/gwc/prover.rs: queries are grouped by point in order of first appearance;
-        per point  poly_batch = fold(poly_batch * v + poly),  W = commit(kate_division(poly_batch - eval_batch, point)).
+        per point  poly_batch = sum_i v^i poly_i  (the queries of a point are zipped with powers(v); the reference's
+        verifier rebuilds exactly this combination, halo2-snark-aggregator-api/src/systems/halo2/multiopen.rs:55-61:
+        `.rev().reduce(|acc, q| v * acc + q)`),  W = commit(kate_division(poly_batch - eval_batch, point)).
         The constant eval_batch only changes the remainder kate_division drops, so it is not subtracted here.
         Returns (rotations in point order, affine W commitments (len, 8))."""
         order, groups = [], {}
@@ -261,7 +263,7 @@ class ResidentProver:
         ws = []
         for j, rot in enumerate(order):
             d_w = self._buf(("w", j), self.n * 32)
-            self.ctx.poly_fold_dev(groups[rot], self.n, fr_to_limbs(v), d_fold)
+            self.ctx.poly_fold_dev(groups[rot][::-1], self.n, fr_to_limbs(v), d_fold)   # poly_fold: first argument = highest power
             self.ctx.kate_division_dev(d_fold, self.n, fr_to_limbs(self.rotate_omega(x, rot)), d_w)
             ws.append(d_w)
         return order, self._commit_dev(ws)

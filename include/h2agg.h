@@ -286,7 +286,7 @@ int h2agg_poly_fold_dev(h2agg_ctx* ctx, const void* const* d_polys, size_t n_pol
                         void* d_out);
 
 /* ---- W1-W5: witness synthesis of halo2-ecc-circuit-lib ---------------------------
- * A recording implementation of the reference's chip surface -- ArithEccChip::{add, sub, scalar_mul,
+ * A recording implementation of the reference's chip surface -- ArithFieldChip (ScalarChip), Encode, and ArithEccChip::{add, sub, scalar_mul,
  * scalar_mul_constant, multi_exp, assign_var, assign_const, normalize}
  * (halo2-snark-aggregator-api/src/arith/ecc.rs:5-61, common.rs:3-42) as bound to
  * EccChipOps::{add, sub, mul, constant_mul, shamir, assign_point, assign_constant_point, reduce}
@@ -311,6 +311,43 @@ int64_t h2agg_wit_ecc_mul(h2agg_witness* w, int64_t a, int64_t s);              
 int64_t h2agg_wit_ecc_shamir(h2agg_witness* w, const int64_t* pts, const int64_t* scalars, size_t n); /* multi_exp */
 int64_t h2agg_wit_ecc_constant_mul(h2agg_witness* w, const uint64_t base_xy[8], int64_t s); /* scalar_mul_constant */
 int h2agg_wit_point_value(h2agg_witness* w, int64_t h, uint64_t out_xy[8], int* is_identity); /* to_value */
+/* The trait-level point operations above take their operands as the reference's adapter does
+ * (halo2-snark-aggregator-circuit/src/chips/ecc_chip.rs:34-52, 99-131: add on a.clone() / b.clone(), sub on a.clone(),
+ * scalar_mul on rhs.clone(), normalize on v.clone(), multi_exp on a moved Vec): the curvature / native caches an operation
+ * fills in die with the clone, a handle keeps the caches it was created with -- that is part of the row layout.
+ *
+ * ArithFieldChip: ScalarChip over FiveColumnBaseGate (halo2-snark-aggregator-circuit/src/chips/scalar_chip.rs:17-127;
+ * traits halo2-snark-aggregator-api/src/arith/field.rs:6-105, common.rs:3-42).  Handles are AssignedValue<Fr>; values
+ * cross the ABI as CANONICAL 256-bit integers < r (status -1 otherwise).  The provided trait methods (sum_with_constant,
+ * mul_add, mul_add_accumulate, pow_constant, field.rs:37-104) are compositions of these and stay with the caller.
+ *   assign_var   = h2agg_wit_assign_scalar  (BaseGateOps::assign)           assign_const / _zero / _one = _field_assign_const
+ *   add, sub     = sum_with_constant([(a,1),(b,+-1)], 0)                    mul, square = [a, b, ab]
+ *   div          = div_unsafe: [b, a/b, a]; b = 0 is an error (Rust unwraps) mul_add_constant = [a, b, ab + c] */
+int64_t h2agg_wit_field_assign_const(h2agg_witness* w, const uint64_t c_canonical[4]);
+int64_t h2agg_wit_field_add(h2agg_witness* w, int64_t a, int64_t b);
+int64_t h2agg_wit_field_sub(h2agg_witness* w, int64_t a, int64_t b);
+int64_t h2agg_wit_field_mul(h2agg_witness* w, int64_t a, int64_t b);
+int64_t h2agg_wit_field_square(h2agg_witness* w, int64_t a);
+int64_t h2agg_wit_field_div(h2agg_witness* w, int64_t a, int64_t b);
+int64_t h2agg_wit_field_sum_with_coeff_and_constant(h2agg_witness* w, const int64_t* elems, const uint64_t* coeffs_canonical /* n*4 */,
+                                                    size_t n, const uint64_t constant_canonical[4]);
+int64_t h2agg_wit_field_mul_add_constant(h2agg_witness* w, int64_t a, int64_t b, const uint64_t c_canonical[4]);
+int h2agg_wit_scalar_value(h2agg_witness* w, int64_t h, uint64_t out_canonical[4]);           /* to_value */
+/* AssignedValue.cell: (advice column, row) -- what constrain_instance (verify_circuit.rs:357-367) and copy constraints bind */
+int h2agg_wit_scalar_cell(h2agg_witness* w, int64_t h, uint32_t* column, uint32_t* row);
+/* Encode: PoseidonEncodeChip::encode_point (halo2-snark-aggregator-circuit/src/chips/encode_chip.rs:18-33) = the natives
+ * of x and y, taken on clones of the coordinates; encode_scalar / decode_scalar are the identity (:35-51). */
+int h2agg_wit_encode_point(h2agg_witness* w, int64_t point, int64_t out_natives[2]);
+/* What Halo2VerifierCircuits::synthesize does around the chip calls:
+ *   assign_identity          ArithCommonChip::assign_zero of the EccChip (ecc_chip.rs:54-56)
+ *   ecc_assert_equal         the `coherent` commitment pairs (verify_circuit.rs:487-493)
+ *   assert_not_identity      base_gate.assert_false(&p.z) (:495-496)
+ *   expose_final_pair        second region (:264-344): reduce the coordinates of (w_x, w_g), take the parity bits of the
+ *                            y's, pack each point into two 136-bit halves -> 4 cells for constrain_instance rows 0..3 */
+int64_t h2agg_wit_ecc_assign_identity(h2agg_witness* w);
+int h2agg_wit_ecc_assert_equal(h2agg_witness* w, int64_t a, int64_t b);
+int h2agg_wit_assert_not_identity(h2agg_witness* w, int64_t point);
+int h2agg_wit_expose_final_pair(h2agg_witness* w, int64_t w_x, int64_t w_g, int64_t out_cells[4]);
 /* Expand everything recorded into the 5 advice columns (n_rows Fr each, Montgomery; rows past the
  * recorded offset are zero like unassigned halo2 cells).  Host pointers / device pointers. */
 int h2agg_witness_expand(h2agg_ctx* ctx, h2agg_witness* w, uint64_t* const advice_cols[5], size_t n_rows);

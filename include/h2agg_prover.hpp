@@ -257,7 +257,10 @@ class ResidentProver {
     std::vector<const void*> ws;
     for (size_t j = 0; j < order.size(); j++) {
       void* w = scratch(KEY_W + j, n_ * 32);
-      auto& g = groups[order[j]];
+      // GWC folds query i of a point with v^i (halo2_proofs gwc/prover.rs zips the queries with powers(v); the reference's
+      // verifier rebuilds exactly that, halo2-snark-aggregator-api/src/systems/halo2/multiopen.rs:55-61):
+      // poly_fold gives its first argument the highest power, so the group goes in reversed
+      std::vector<const void*> g(groups[order[j]].rbegin(), groups[order[j]].rend());
       c_.check(h2agg_poly_fold_dev(c_.raw(), g.data(), g.size(), n_, v.l, fold));
       c_.check(h2agg_kate_division_dev(c_.raw(), fold, n_, points.at(order[j]).l, w));
       ws.push_back(w);

@@ -103,6 +103,17 @@ def bg_mul(ctx, a, b):  # :302-324
     return one_line(ctx, [(a, 0), (b, 0), (a.value * b.value % R, -1)], 0, ((1,), 0))[2]
 
 
+def bg_mul_add_constant(ctx, a, b, c):  # :326-349
+    d = (a.value * b.value + c) % R
+    return one_line(ctx, [(a, 0), (b, 0), (d, -1)], c, ((1,), 0))[2]
+
+
+def bg_div_unsafe(ctx, a, b):  # :478-497  b * c - a = 0, c = a / b (b = 0: `invert().unwrap()` panics)
+    assert b.value % R, "div_unsafe: division by zero"
+    c = pow(b.value, -1, R) * a.value % R
+    return one_line(ctx, [(b, 0), (c, 0), (a, -1)], 0, ((1,), 0))[1]
+
+
 def bg_mul_add(ctx, a, b, c, c_coeff):  # :351-380
     d = (a.value * b.value + c.value * c_coeff) % R
     return one_line(ctx, [(a, 0), (b, 0), (c, c_coeff), (d, -1)], 0, ((1,), 0))[3]
@@ -142,6 +153,7 @@ def bg_assign(ctx, v):  # :507-511
 
 
 def bg_assert_constant(ctx, a, b):  # :525-538
+    assert a.value % R == b % R, "assert_constant fails"
     one_line(ctx, [(a, -1)], b)
 
 
@@ -712,6 +724,23 @@ def ecc_constant_mul(ctx, base, s, g1_add):  # :245-279; base: affine tuple; g1_
         acc = slot if acc is None else ecc_add(ctx, slot, acc)
         base = g1_add(g1_add(b2, base), base)
     return acc
+
+
+def expose_final_pair(ctx, w_x, w_g):
+    """Halo2VerifierCircuits::synthesize, second region (halo2-snark-aggregator-circuit/src/verify_circuit.rs:264-344):
+    reduce the coordinates, take the parity bits of the y's, pack each point into two 136-bit halves -> the four cells
+    constrain_instance binds to instance rows 0..3 (:357-360)."""
+    pts = [w_x.clone(), w_g.clone()]
+    for p in pts:
+        reduce(ctx, p.x)
+        reduce(ctx, p.y)
+    bits = [int_get_last_bit(ctx, p.y) for p in pts]
+    e = Helper.limb_modulus_exps
+    out = []
+    for p, bit in zip(pts, bits):
+        out.append(sum_with_constant(ctx, [(p.x.limbs_le[0], e[0]), (p.x.limbs_le[1], e[1])], 0))
+        out.append(sum_with_constant(ctx, [(p.x.limbs_le[2], e[0]), (p.x.limbs_le[3], e[1]), (bit, e[2])], 0))
+    return out
 
 
 # ------------------------------------------------------------------------------------ MockProver

@@ -89,7 +89,7 @@ def test_resident_prover_matches_oracle_composition(ctx, which, k):
     assert order == list(dict.fromkeys(rot for _, rot in queries))
     for rot, wpt in zip(order, ws):
         acc = [0] * n
-        for nm, r2 in queries:
+        for nm, r2 in reversed(queries):      # query i of a point is weighted v^i
             if r2 == rot:
                 c = qu.unpack(o_coeff[nm])
                 acc = [(a * v + b) % R for a, b in zip(acc, c)]
@@ -164,7 +164,7 @@ def test_resident_prover_at_k16_matches_the_cpp_oracle_composition(ctx):
     order, ws = pr.open(queries, x, v)
     for rot, wpt in zip(order, ws):
         acc = np.zeros(4 * n, dtype=np.uint64)
-        for nm, r2 in queries:
+        for nm, r2 in reversed(queries):      # query i of a point is weighted v^i
             if r2 == rot:
                 acc = scale_add(acc, v, o_coeff[nm])
         quo = np.concatenate([ob.kate_division(acc, fr(x * pow(w, rot, R) % R)), np.zeros(4, dtype=np.uint64)])
@@ -389,7 +389,7 @@ def test_device_proof_satisfies_the_reference_verifiers_equation(ctx):
 def test_device_proof_openings_verify_against_a_trapdoor_srs(ctx):
     """The other half of verify_proof: the GWC opening check e(W, [s - z]_2) = e(F - [e]_1, [1]_2) per point, done in
     the group with the trapdoor s of a toy SRS (g_i = s^i G, g_lagrange_i = L_i(s) G) and textbook affine arithmetic on
-    Python integers: (s - z) W = sum_i v^(m-1-i) (C_i - e_i G).  It ties together what the device produced -- the
+    Python integers: (s - z) W = sum_i v^i (C_i - e_i G).  It ties together what the device produced -- the
     commitments (MSM against both SRS forms), the coefficient forms behind the evaluations (iNTT), the fold, the Kate
     quotients and their commitments."""
     import bn254_ref as ref
@@ -419,7 +419,7 @@ def test_device_proof_openings_verify_against_a_trapdoor_srs(ctx):
     for rot, wpt in zip(out["order"], out["ws"]):
         z = x * pow(w, rot, R) % R
         F, E = None, 0
-        for nm, r2 in out["queries"]:
+        for nm, r2 in reversed(out["queries"]):   # query i of a point is weighted v^i
             if r2 == rot:
                 F = ref.g1_add(ref.g1_mul(v, F), C[nm])
                 E = (E * v + out["ev"][(nm, r2)]) % R

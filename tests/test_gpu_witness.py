@@ -115,3 +115,46 @@ def test_witness_kernel_feeds_the_resident_prover(ctx):
     pr.close()
     ctx.srs_release(sid)
     chip.close()
+
+
+def test_full_aggregation_witness_all_five_advice_columns(ctx):
+    """W6: the advice columns of a COMPLETE aggregation witness -- Poseidon transcript + ScalarChip expression evaluation +
+    instance commitment (scalar_mul_constant) + both multi_exps + the final-pair packing -- for one tiny inner proof
+    (oracle/py/mini_prover.py), driven by the restated verify_aggregation_proofs_in_chip (oracle/py/verifier_ref.py,
+    api/src/systems/halo2/verify.rs:835-942) through the product's ArithEccChip / ArithFieldChip / Encode chips, against the
+    same driver over the circuit-chip oracle.  ~0.9 M rows; the oracle's rows pass gate + lookups + copy constraints; and
+    the columns then go through commit_lagrange on the device like any advice column."""
+    import aggregation_util as au
+    import oracle_binding as ob
+    import verifier_ref as V
+
+    inner = au.tiny_inner_proof()
+    ochips, octx = V.ref_chips()
+    oout = V.synthesize(ochips, au.circuits_data(inner))
+    E.check(octx)
+    chips, w = au.b200_chips()
+    out = V.synthesize(chips, au.circuits_data(inner))
+    assert w.rows() == octx.offset
+    k = 20
+    n = 1 << k
+    assert w.rows() <= n - 6
+    cols = w.expand(ctx, n_rows=n)
+
+    class _B:
+        pass
+
+    b = _B()
+    b.ctx = octx
+    _compare(b, cols)
+    # the exposed cells really hold what constrain_instance binds (verify_circuit.rs:357-367)
+    rinv = pow(1 << 256, -1, E.R)
+    for h, c in zip(out["instance_cells"], oout["instance_cells"]):
+        col, row = chips.schip.cell(h)
+        limbs = cols[col, row]
+        got = sum(int(x) << (64 * i) for i, x in enumerate(limbs)) * rinv % E.R
+        assert got == c.value == chips.schip.to_value(h)
+    # and one column through the commit path: commit_lagrange(a4) on the device == oracle best_multiexp
+    bases = ob.gen_bases(0x53525320, n)
+    a4 = np.ascontiguousarray(cols[4]).ravel()
+    assert np.array_equal(ctx.msm_g1(a4, bases), ob.best_multiexp(a4, bases))
+    w.close()

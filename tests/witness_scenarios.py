@@ -53,20 +53,23 @@ class Both:
         h = self.chip.assign_scalar(s) if self.chip else None
         return (o, h)
 
+    # The oracle side takes its operands exactly as the reference's adapter does
+    # (halo2-snark-aggregator-circuit/src/chips/ecc_chip.rs:34-52, 99-131): add(&mut a.clone(), &mut b.clone()),
+    # sub(&mut a.clone(), b), mul(&mut rhs.clone(), lhs), reduce(&mut v.clone()) -- caches filled in by an op die with the clone.
     def add(self, a, b):
-        return (E.ecc_add(self.ctx, a[0], b[0].clone()), self.chip.add(a[1], b[1]) if self.chip else None)
+        return (E.ecc_add(self.ctx, a[0].clone(), b[0].clone()), self.chip.add(a[1], b[1]) if self.chip else None)
 
     def sub(self, a, b):
-        return (E.ecc_sub(self.ctx, a[0], b[0].clone()), self.chip.sub(a[1], b[1]) if self.chip else None)
+        return (E.ecc_sub(self.ctx, a[0].clone(), b[0]), self.chip.sub(a[1], b[1]) if self.chip else None)
 
     def double(self, a):
-        return (E.ecc_double(self.ctx, a[0]), self.chip.double(a[1]) if self.chip else None)
+        return (E.ecc_double(self.ctx, a[0].clone()), self.chip.double(a[1]) if self.chip else None)
 
     def normalize(self, a):
-        return (E.ecc_reduce(self.ctx, a[0]), self.chip.normalize(a[1]) if self.chip else None)
+        return (E.ecc_reduce(self.ctx, a[0].clone()), self.chip.normalize(a[1]) if self.chip else None)
 
     def scalar_mul(self, s, a):
-        return (E.ecc_mul(self.ctx, a[0], s[0]), self.chip.scalar_mul(s[1], a[1]) if self.chip else None)
+        return (E.ecc_mul(self.ctx, a[0].clone(), s[0]), self.chip.scalar_mul(s[1], a[1]) if self.chip else None)
 
     def multi_exp(self, pts, scalars):
         o = E.ecc_shamir(self.ctx, [p[0].clone() for p in pts], [s[0] for s in scalars])
