@@ -288,8 +288,9 @@ class Context:
         self.check(self.lib.h2agg_kate_division_dev(self.h, c_vp(d_a), n, _ptr(b), c_vp(d_q)))
 
     # -- N1: quotient numerator on the extended coset (evaluate_h [+ divide_by_vanishing_poly])
-    def evaluate_h_dev(self, plan, d_columns, k, ext_k, y, beta, gamma, theta, d_out, divide=True):
-        """plan: plonk.QuotientPlan; d_columns: device pointers in plan.columns order; challenges: 4-limb arrays."""
+    def evaluate_h_dev(self, plan, d_columns, k, ext_k, y, beta, gamma, theta, d_out, divide=True, rows=None, col_row0=None):
+        """plan: plonk.QuotientPlan; d_columns: device pointers in plan.columns order; challenges: 4-limb arrays.
+        rows = (row_begin, row_count) evaluates a window only; col_row0[c] = global row of element 0 of column c's buffer."""
         from . import plonk
 
         assert len(d_columns) == len(plan.columns), "one device column per plan.columns entry"
@@ -310,13 +311,25 @@ class Context:
             a.t_evaluations, a.t_len = t.ctypes.data, t.size // 4
         else:
             a.t_evaluations, a.t_len = None, 0
-        self.check(self.lib.h2agg_evaluate_h_dev(self.h, ctypes.byref(a), c_vp(d_out)))
+        if rows is None:
+            self.check(self.lib.h2agg_evaluate_h_dev(self.h, ctypes.byref(a), c_vp(d_out)))
+        else:
+            r0 = np.ascontiguousarray(col_row0, dtype=np.uint64) if col_row0 is not None else None
+            self.check(self.lib.h2agg_evaluate_h_rows_dev(self.h, ctypes.byref(a), int(rows[0]), int(rows[1]),
+                                                          _ptr(r0), c_vp(d_out)))
         del keep
 
     def poly_fold_dev(self, d_polys, n, v, d_out):
         """out[j] = sum_i polys[i][j] * v^(m-1-i) (GWC: poly_batch = poly_batch * v + poly)"""
         arr = (c_vp * len(d_polys))(*d_polys)
         self.check(self.lib.h2agg_poly_fold_dev(self.h, arr, len(d_polys), n, _ptr(v), c_vp(d_out)))
+
+    def poly_lincomb_dev(self, d_polys, weights, n, d_out):
+        """out[j] = sum_i weights[i] * polys[i][j]; weights: (m, 4) or flat Montgomery limbs"""
+        m = len(d_polys)
+        arr = (c_vp * max(m, 1))(*d_polys)
+        w = np.ascontiguousarray(weights, dtype=np.uint64).reshape(-1) if m else np.zeros(4, dtype=np.uint64)
+        self.check(self.lib.h2agg_poly_lincomb_dev(self.h, arr, _ptr(w), m, n, c_vp(d_out)))
 
     # -- N3: grand-product scans
     def batch_invert(self, a):

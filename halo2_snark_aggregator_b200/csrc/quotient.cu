@@ -41,6 +41,10 @@ struct QuotKernelArgs {
   uint32_t n_terms;   // number of folded terms: h = sum_j term_j * y^(n_terms - 1 - j)
   Fr* out;
   uint32_t lo_bits, ext_k, rot_scale, t_mask;
+  // row window (multi-GPU row sharding): this launch produces rows [row_begin, row_begin + row_count); column c's buffer
+  // starts at global row col_row0[c] (cyclically), so a buffer only needs the window plus its rotation halo
+  uint32_t row_begin, row_count;
+  const uint32_t* col_row0;  // null = every buffer is the whole column (row0 = 0)
   Fr y, beta, gamma, theta, zeta, delta;
 };
 
@@ -65,8 +69,9 @@ __global__ void quot_y_powers(Fr y, uint32_t n, Fr* out) {
 }
 
 __device__ __forceinline__ Fr q_load(const QuotKernelArgs& a, uint32_t col, int rot, uint32_t idx, uint32_t mask) {
-  uint32_t r = (idx + (uint32_t)(rot * (int)a.rot_scale)) & mask;
-  return Fr::load_nc(a.cols[col] + r);
+  uint32_t r = idx + (uint32_t)(rot * (int)a.rot_scale);
+  if (a.col_row0) r -= __ldg(a.col_row0 + col);
+  return Fr::load_nc(a.cols[col] + (r & mask));
 }
 
 // sum of products: n_terms, then per term { const index or QNOCONST, n_factors, factor words (col | rot << 16) }
@@ -106,16 +111,17 @@ __device__ __forceinline__ Fr q_compress(const QuotKernelArgs& a, uint32_t& pc, 
 }
 
 __global__ void __launch_bounds__(256) quot_evaluate_h(const __grid_constant__ QuotKernelArgs a) {
-  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t local = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t mask = (1u << a.ext_k) - 1;
-  if (idx > mask) return;
+  if (local >= a.row_count) return;
+  const uint32_t idx = (a.row_begin + local) & mask;
   const uint32_t* __restrict__ plan = a.plan;
   const uint32_t n_gates = plan[1], n_pcols = plan[2], chunk_len = plan[3];
   const int last_rot = (int)plan[4];
   const uint32_t n_lookups = plan[5];
-  const Fr l0 = Fr::load_nc(a.cols[plan[6]] + idx);
-  const Fr l_last = Fr::load_nc(a.cols[plan[7]] + idx);
-  const Fr l_active = Fr::load_nc(a.cols[plan[8]] + idx);
+  const Fr l0 = q_load(a, plan[6], 0, idx, mask);
+  const Fr l_last = q_load(a, plan[7], 0, idx, mask);
+  const Fr l_active = q_load(a, plan[8], 0, idx, mask);
   const Fr one = Fr::one();
   uint32_t pc = QPLAN_HEADER;
   // halo2 folds h = h * y + term over the ordered term list, i.e. h = sum_j term_j * y^(N-1-j).  Most terms carry one
@@ -194,7 +200,7 @@ __global__ void __launch_bounds__(256) quot_evaluate_h(const __grid_constant__ Q
   Fr value = acc_plain + fp_mul_add2(acc_l0, l0, acc_last, l_last) + acc_active * l_active;
 
   if (a.t_evals) value = value * Fr::load_nc(a.t_evals + (idx & a.t_mask));
-  value.store(a.out + idx);
+  value.store(a.out + local);
 }
 
 // out[j] = sum_i polys[i][j] * v^(m-1-i)   (Horner over the list: acc = acc * v + poly_i), m <= 64 per launch
@@ -287,8 +293,26 @@ using namespace h2agg;
 
 extern "C" {
 
+static int evaluate_h_impl(h2agg_ctx* ctx, const h2agg_quotient_args* q, uint64_t row_begin, uint64_t row_count,
+                           const uint64_t* col_row0, void* d_out);
+
 int h2agg_evaluate_h_dev(h2agg_ctx* ctx, const h2agg_quotient_args* q, void* d_out) {
   if (!ctx) return 1;
+  if (!q) { ctx->last_error = "evaluate_h: null argument"; return 1; }
+  return evaluate_h_impl(ctx, q, 0, q->ext_k <= 28 ? ((uint64_t)1 << q->ext_k) : 0, nullptr, d_out);
+}
+
+int h2agg_evaluate_h_rows_dev(h2agg_ctx* ctx, const h2agg_quotient_args* q, uint64_t row_begin, uint64_t row_count,
+                              const uint64_t* col_row0, void* d_out) {
+  if (!ctx) return 1;
+  if (!q) { ctx->last_error = "evaluate_h: null argument"; return 1; }
+  return evaluate_h_impl(ctx, q, row_begin, row_count, col_row0, d_out);
+}
+
+}  // extern "C"
+
+static int evaluate_h_impl(h2agg_ctx* ctx, const h2agg_quotient_args* q, uint64_t row_begin, uint64_t row_count,
+                           const uint64_t* col_row0, void* d_out) {
   std::lock_guard<std::recursive_mutex> lock(ctx->mu);
   if (!q || !d_out || !q->plan || !q->d_columns || !q->y || !q->beta || !q->gamma || !q->theta || !q->omega_ext ||
       !q->zeta || !q->delta || (q->n_consts && !q->consts)) {
@@ -307,6 +331,12 @@ int h2agg_evaluate_h_dev(h2agg_ctx* ctx, const h2agg_quotient_args* q, void* d_o
   }
   for (size_t i = 0; i < q->n_columns; i++)
     if (!q->d_columns[i]) { ctx->last_error = "evaluate_h: null column pointer"; return 1; }
+  const uint64_t size = (uint64_t)1 << q->ext_k;
+  if (row_begin >= size || row_count > size) { ctx->last_error = "evaluate_h: row window outside the extended domain"; return 1; }
+  if (col_row0)
+    for (size_t i = 0; i < q->n_columns; i++)
+      if (col_row0[i] >= size) { ctx->last_error = "evaluate_h: column window start outside the extended domain"; return 1; }
+  if (row_count == 0) return 0;
   H2AGG_CUDA(ctx, cudaSetDevice(ctx->device));
   uint32_t lo_bits;
   int rc = quot_tables(ctx, q->omega_ext, q->ext_k, &lo_bits);
@@ -321,7 +351,8 @@ int h2agg_evaluate_h_dev(h2agg_ctx* ctx, const h2agg_quotient_args* q, void* d_o
     n_terms += 2 + (n_sets - 1) + n_sets;
   }
   size_t off_y = off_t + q->t_len * 32;
-  size_t total = off_y + (size_t)n_terms * 32 + 32;
+  size_t off_row0 = off_y + (size_t)n_terms * 32 + 32;
+  size_t total = off_row0 + (col_row0 ? q->n_columns * 4 : 0);
   // the previous call's kernel may still be reading the old copy: alternate two halves of the buffer
   rc = ensure(ctx, ctx->quot_ws, 2 * total + 64);
   if (rc) return rc;
@@ -332,6 +363,11 @@ int h2agg_evaluate_h_dev(h2agg_ctx* ctx, const h2agg_quotient_args* q, void* d_o
   memcpy(stage.data() + off_cols, q->d_columns, q->n_columns * 8);
   if (q->n_consts) memcpy(stage.data() + off_consts, q->consts, q->n_consts * 32);
   if (q->t_evaluations) memcpy(stage.data() + off_t, q->t_evaluations, q->t_len * 32);
+  if (col_row0)
+    for (size_t i = 0; i < q->n_columns; i++) {
+      uint32_t r0 = (uint32_t)col_row0[i];
+      memcpy(stage.data() + off_row0 + 4 * i, &r0, 4);
+    }
   H2AGG_CUDA(ctx, cudaMemcpyAsync(base, stage.data(), total, cudaMemcpyHostToDevice, ctx->stream));
   H2AGG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `stage` is pageable and dies with this frame
   QuotKernelArgs a;
@@ -345,6 +381,9 @@ int h2agg_evaluate_h_dev(h2agg_ctx* ctx, const h2agg_quotient_args* q, void* d_o
   a.y_pow = (const Fr*)(base + off_y);
   a.n_terms = n_terms;
   a.out = (Fr*)d_out;
+  a.row_begin = (uint32_t)row_begin;
+  a.row_count = (uint32_t)row_count;
+  a.col_row0 = col_row0 ? (const uint32_t*)(base + off_row0) : nullptr;
   a.lo_bits = lo_bits;
   a.ext_k = q->ext_k;
   a.rot_scale = 1u << (q->ext_k - q->k);
@@ -354,7 +393,7 @@ int h2agg_evaluate_h_dev(h2agg_ctx* ctx, const h2agg_quotient_args* q, void* d_o
   memcpy(a.theta.v, q->theta, 32);
   memcpy(a.zeta.v, q->zeta, 32);
   memcpy(a.delta.v, q->delta, 32);
-  size_t rows = (size_t)1 << q->ext_k;
+  size_t rows = (size_t)row_count;
   if (n_terms) {
     quot_y_powers<<<1, 32, 0, ctx->stream>>>(a.y, n_terms, (Fr*)(base + off_y));
     ctx->launches++;
@@ -364,6 +403,61 @@ int h2agg_evaluate_h_dev(h2agg_ctx* ctx, const h2agg_quotient_args* q, void* d_o
     quot_evaluate_h<<<(unsigned)((rows + 255) / 256), 256, 0, ctx->stream>>>(a);
   }
   ctx->launches++;
+  H2AGG_CUDA(ctx, cudaGetLastError());
+  return 0;
+}
+
+// out[j] = sum_i w_i * polys[i][j]: the general linear combination (a rank's share of a GWC fold: its own polynomials
+// with the powers of v they carry in the full list; weights 1 add the gathered partial folds)
+struct LincombArgs {
+  const Fr* polys[32];
+  Fr w[32];
+  uint32_t m;
+  uint32_t accumulate;
+  Fr* out;
+  size_t n;
+};
+
+__global__ void __launch_bounds__(256) poly_lincomb_kernel(const __grid_constant__ LincombArgs a) {
+  size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= a.n) return;
+  Fr acc = a.accumulate ? Fr::load(a.out + j) : Fr::zero();
+  for (uint32_t i = 0; i < a.m; i++) acc = acc + a.w[i] * Fr::load_nc(a.polys[i] + j);
+  acc.store(a.out + j);
+}
+
+extern "C" {
+
+int h2agg_poly_lincomb_dev(h2agg_ctx* ctx, const void* const* d_polys, const uint64_t* weights, size_t n_polys, size_t n,
+                           void* d_out) {
+  if (!ctx) return 1;
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+  if (!d_out || (n_polys && (!d_polys || !weights))) { ctx->last_error = "poly_lincomb: null argument"; return 1; }
+  for (size_t i = 0; i < n_polys; i++)
+    if (!d_polys[i]) { ctx->last_error = "poly_lincomb: null polynomial"; return 1; }
+  if (n == 0) return 0;
+  H2AGG_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (n_polys == 0) {
+    H2AGG_CUDA(ctx, cudaMemsetAsync(d_out, 0, n * 32, ctx->stream));
+    return 0;
+  }
+  size_t done = 0;
+  while (done < n_polys) {
+    LincombArgs a;
+    a.accumulate = done ? 1 : 0;
+    size_t m = n_polys - done;
+    if (m > 32) m = 32;
+    for (size_t i = 0; i < m; i++) {
+      a.polys[i] = (const Fr*)d_polys[done + i];
+      memcpy(a.w[i].v, weights + 4 * (done + i), 32);
+    }
+    a.m = (uint32_t)m;
+    a.out = (Fr*)d_out;
+    a.n = n;
+    poly_lincomb_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    done += m;
+  }
   H2AGG_CUDA(ctx, cudaGetLastError());
   return 0;
 }

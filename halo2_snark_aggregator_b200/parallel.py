@@ -168,3 +168,79 @@ def exchange_row_windows(dist, torch, owned, owner_of, names, shards, halo, ext_
         for req in dist.batch_isend_irecv(ops):
             req.wait()
     return out
+
+
+# ---- multi-GPU resident prover: static work plan (dist_prover.py) ------------------------------------------------------
+# Measured single-B200 costs at k = 22 (ms); only the RATIOS matter for the balance.
+COST = {"msm_small": 2.6, "msm_uniform": 12.5, "intt": 1.0, "coset": 3.4, "sort": 1.6, "product": 1.2, "shard_fixed": 0.5}
+
+
+def window_units(n_items, n_windows, world):
+    """Spread n_items MSMs of n_windows windows each over `world` ranks at WINDOW granularity (McNaughton's wrap-around
+    rule): the n_items * n_windows window units are laid out item after item and cut into `world` contiguous ranges, so
+    every rank gets the same number of windows (+-1), at most two MSMs per rank are partial and an MSM is cut into at most
+    ceil(world / n_items) + 1 shards.  Returns per rank a list of (item, win_begin, win_end)."""
+    total = n_items * n_windows
+    out = []
+    for r in range(world):
+        lo, hi = total * r // world, total * (r + 1) // world
+        mine = []
+        u = lo
+        while u < hi:
+            item, w = divmod(u, n_windows)
+            w_end = min(n_windows, w + (hi - u))
+            mine.append((item, w, w_end))
+            u += w_end - w
+        out.append(mine)
+    return out
+
+
+def prover_plan(n_witness, n_lookups, n_perm_sets, world, cost=None):
+    """Who does what in the column-parallel rounds of the multi-GPU prover.  Everything here is a pure function of the
+    circuit shape and the world size, so every rank computes the same plan without talking.
+
+    round 1   witness column j (instance + advice) -> rank j mod world
+    round 2   lookup i (compress, sort / permute, 2 commits, 2 x (iNTT + coset NTT)) -> rank i mod world
+    round 3   lookup product i stays with lookup i (its inputs are resident there); the permutation products (a chain
+              through z_s[u]) all go to the least loaded rank; then MSMs are moved, largest first from the most loaded
+              rank, into a POOL that is window-sharded over all ranks (`window_units`) as long as that lowers the
+              makespan -- so 9 grand products on 8 ranks no longer cost two MSMs on one of them.
+    Returns dict(witness=[rank], lookup=[rank], perm_rank=int, pooled_z=[names], load_ms=[per rank estimate of round 3])."""
+    c = dict(COST)
+    if cost:
+        c.update(cost)
+    witness = [j % world for j in range(n_witness)]
+    lookup = [i % world for i in range(n_lookups)]
+    transforms = c["intt"] + c["coset"]
+    fixed = [0.0] * world          # work that cannot move: products + transforms
+    msms = {}                      # name -> owner
+    for i, r in enumerate(lookup):
+        fixed[r] += c["product"] + transforms
+        msms[("lookup_z", i)] = r
+    base = [fixed[r] + c["msm_uniform"] * sum(1 for o in msms.values() if o == r) for r in range(world)]
+    perm_rank = min(range(world), key=lambda r: (base[r], -r)) if n_perm_sets else 0   # ties: the highest rank (lookups fill the low ones)
+    for s in range(n_perm_sets):
+        fixed[perm_rank] += c["product"] + transforms
+        msms[("perm_z", s)] = perm_rank
+    pooled = []
+
+    def makespan(pool):
+        per = [fixed[r] + c["msm_uniform"] * sum(1 for nm, o in msms.items() if o == r and nm not in pool) for r in range(world)]
+        share = (len(pool) * c["msm_uniform"]) / world + (c["shard_fixed"] * 2 if pool else 0.0)
+        return max(per) + share, per
+
+    best, _ = makespan(pooled)
+    while world > 1:
+        _, per = makespan(pooled)
+        r = max(range(world), key=lambda q: (per[q], q))
+        cand = sorted(nm for nm, o in msms.items() if o == r and nm not in pooled)
+        if not cand:
+            break
+        trial, _ = makespan(pooled + [cand[-1]])
+        if trial + 1e-9 < best:
+            pooled.append(cand[-1])
+            best = trial
+        else:
+            break
+    _, per = makespan(pooled)
+    return dict(witness=witness, lookup=lookup, perm_rank=perm_rank, pooled_z=sorted(pooled), load_ms=per, makespan_ms=best)

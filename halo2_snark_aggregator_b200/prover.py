@@ -27,9 +27,12 @@ _R = plonk.R_MOD
 
 
 class ResidentProver:
-    def __init__(self, ctx, cs, k, srs_lagrange, srs_g):
-        """srs_lagrange / srs_g: ids of the registered ParamsKZG::g_lagrange / g (h2agg_srs_register)."""
+    def __init__(self, ctx, cs, k, srs_lagrange, srs_g, alloc=None):
+        """srs_lagrange / srs_g: ids of the registered ParamsKZG::g_lagrange / g (h2agg_srs_register).
+        alloc(nbytes) -> device pointer: caller-owned memory instead of h2agg_dev_alloc (the multi-GPU driver allocates
+        torch tensors so that NCCL can address the same buffers)."""
         self.ctx, self.cs, self.k, self.n = ctx, cs, k, 1 << k
+        self._ext_alloc = alloc
         self.plan = plonk.build_quotient_plan(cs)
         self.dom = EvaluationDomain(cs.degree(), k, ctx)
         self.ext_k, self.ext_n = self.dom.extended_k, self.dom.extended_len()
@@ -58,6 +61,8 @@ class ResidentProver:
 
     # -- memory ------------------------------------------------------------------------------------
     def _alloc(self, nbytes):
+        if self._ext_alloc is not None:
+            return self._ext_alloc(nbytes)
         p = self.ctx.dev_alloc(nbytes)
         self._owned.append(p)
         return p
@@ -122,10 +127,11 @@ class ResidentProver:
     def usable_rows(self):
         return self.n - (self.cs.blinding_factors() + 1)
 
-    def lookup_round(self, theta, blind):
+    def lookup_round(self, theta, blind, only=None):
         """Per lookup: compress the input / table expressions over the resident Lagrange columns, sort + permute them
         over the usable rows (permute_expression_pair), append the caller's blinding rows, commit.
-        blind(name, rows) -> uint64 array rows*4 (the values halo2 draws from its RNG)."""
+        blind(name, rows) -> uint64 array rows*4 (the values halo2 draws from its RNG).
+        only: lookup indices to run (the multi-GPU driver gives every rank its share); default all."""
         names = [nm for nm in self.lag if nm[0] in ("fixed", "advice", "instance")]
         index = {nm: i for i, nm in enumerate(names)}
         cols = [self.lag[nm] for nm in names]
@@ -134,6 +140,8 @@ class ResidentProver:
         out_names = []
         self._mark("-")
         for i, (_, ins, tabs) in enumerate(self.cs.lookups):
+            if only is not None and i not in only:
+                continue
             for side, exprs in (("input", ins), ("table", tabs)):
                 prog = plonk.ExpressionList(exprs, index)
                 self.ctx.compress_expressions_dev(prog.words, prog.consts, cols, self.k, th,
@@ -152,15 +160,15 @@ class ResidentProver:
         return out
 
     # -- stage 3: grand products (permutation::commit, lookup commit_product) ------------------------------
-    def product_round(self, beta, gamma, blind):
+    def permutation_products(self, beta, gamma, blind):
+        """The permutation argument's running products, one per column set, chained through z_s[u] -> names"""
         bf = self.cs.blinding_factors()
         u = self.usable_rows()
         b, g = fr_to_limbs(beta), fr_to_limbs(gamma)
-        out_names = []
         chunk = self.cs.chunk_len()
         pcs = self.cs.permutation_columns
         last = None
-        self._mark("-")
+        names = []
         for s in range(self.cs.num_permutation_sets()):
             cols = pcs[s * chunk:(s + 1) * chunk]
             z = self.lagrange_slot(("perm_z", s))
@@ -169,17 +177,28 @@ class ResidentProver:
                                              fr_to_limbs(plonk.DELTA), b, g, last, z)
             self.ctx.h2d(z + 32 * (self.n - bf), np.ascontiguousarray(blind(("perm_z", s), bf)))
             last = z + 32 * u
-            out_names.append(("perm_z", s))
-        self._mark("products.permutation")
-        L = range(len(self.cs.lookups))
+            names.append(("perm_z", s))
+        return names
+
+    def lookup_products(self, beta, gamma, blind, only=None):
+        """The lookup arguments' running products (all selected lookups in one call: their latency chains overlap on the lanes)"""
+        bf = self.cs.blinding_factors()
+        b, g = fr_to_limbs(beta), fr_to_limbs(gamma)
+        L = [i for i in range(len(self.cs.lookups)) if only is None or i in only]
         zs = [self.lagrange_slot(("lookup_z", i)) for i in L]
-        if zs:  # all lookup products in one call: their latency chains overlap on the lanes
+        if zs:
             self.ctx.lookup_products_dev([self.lag[("lookup_input_compressed", i)] for i in L], [self.lag[("lookup_table_compressed", i)] for i in L],
                                          [self.lag[("lookup_input", i)] for i in L], [self.lag[("lookup_table", i)] for i in L],
                                          self.n, b, g, zs)
-        for i in L:
-            self.ctx.h2d(zs[i] + 32 * (self.n - bf), np.ascontiguousarray(blind(("lookup_z", i), bf)))
-            out_names.append(("lookup_z", i))
+        for z, i in zip(zs, L):
+            self.ctx.h2d(z + 32 * (self.n - bf), np.ascontiguousarray(blind(("lookup_z", i), bf)))
+        return [("lookup_z", i) for i in L]
+
+    def product_round(self, beta, gamma, blind):
+        self._mark("-")
+        out_names = self.permutation_products(beta, gamma, blind)
+        self._mark("products.permutation")
+        out_names += self.lookup_products(beta, gamma, blind)
         self._mark("products.lookup")
         out = self._commit_resident(out_names)
         self._mark("products.commit_round_dev")

@@ -280,10 +280,21 @@ typedef struct h2agg_quotient_args {
   size_t t_len;                  /* power of two (halo2: 2^(ext_k - k)) */
 } h2agg_quotient_args;
 int h2agg_evaluate_h_dev(h2agg_ctx* ctx, const h2agg_quotient_args* args, void* d_out /* 2^ext_k * 32 B */);
+/* Row window of the same computation (multi-GPU row sharding of the quotient): rows
+ * [row_begin, row_begin + row_count) of the coset go to d_out[0 .. row_count).  col_row0[c] (NULL = all zero) is the
+ * global row held by element 0 of column c's buffer, cyclically: a rank only needs each column on its window plus the
+ * rotation halo (rot * 2^(ext_k - k) rows either side), not the whole 2^ext_k vector. */
+int h2agg_evaluate_h_rows_dev(h2agg_ctx* ctx, const h2agg_quotient_args* args, uint64_t row_begin, uint64_t row_count,
+                              const uint64_t* col_row0 /* n_columns or NULL */, void* d_out /* row_count * 32 B */);
 /* GWC multi-opening (halo2_proofs poly/kzg/multiopen/gwc/prover.rs: poly_batch = poly_batch * v + poly):
  * out[j] = sum_i polys[i][j] * v^(n_polys-1-i).  d_out must not alias an input. */
 int h2agg_poly_fold_dev(h2agg_ctx* ctx, const void* const* d_polys, size_t n_polys, size_t n, const uint64_t v[4],
                         void* d_out);
+/* out[j] = sum_i weights[i] * polys[i][j] (weights: n_polys x 4 Montgomery limbs; n_polys = 0 zeroes out).  One rank's
+ * share of a fold -- its own polynomials with the powers of v they carry in the full query list -- and, with unit
+ * weights, the sum of the gathered shares.  d_out must not alias an input. */
+int h2agg_poly_lincomb_dev(h2agg_ctx* ctx, const void* const* d_polys, const uint64_t* weights, size_t n_polys, size_t n,
+                           void* d_out);
 
 /* ---- W1-W5: witness synthesis of halo2-ecc-circuit-lib ---------------------------
  * A recording implementation of the reference's chip surface -- ArithFieldChip (ScalarChip), Encode, and ArithEccChip::{add, sub, scalar_mul,

@@ -530,3 +530,15 @@ def test_cpp_resident_prover_equals_python_twin(ctx, tmp_path):
     got = np.fromfile(fout, dtype=np.uint64)
     assert got.size == want.size
     assert np.array_equal(got, want)
+
+
+def test_distributed_prover_world1_equals_resident_prover():
+    """halo2_snark_aggregator_b200/dist_prover.py with one rank issues no collective and must reproduce the
+    ResidentProver bit for bit (tests/dist_prover_main.py; the same script runs under torchrun for 2 / 4 / 8 GPUs)."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "dist_prover_main.py"), "11"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "DIST_PROVER_OK world=1" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
