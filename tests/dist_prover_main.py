@@ -9,6 +9,7 @@ The single-GPU prover is itself held against the CPU oracles in tests/test_gpu_p
 import os
 import random
 import sys
+import zlib
 
 import numpy as np
 
@@ -82,7 +83,7 @@ def main():
 
     def blind(name, nrows):
         if (name, nrows) not in blind_vals:
-            blind_vals[(name, nrows)] = ob.gen_scalars(0xB000 + (hash(str(name)) & 0xFFF), 0, nrows)
+            blind_vals[(name, nrows)] = ob.gen_scalars(0xB000 + (zlib.crc32(str(name).encode()) & 0xFFF), 0, nrows)   # the same in every process
         return blind_vals[(name, nrows)]
 
     # proving-key side: the same on every rank
