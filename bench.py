@@ -484,17 +484,21 @@ def main():
         ctx.kernel_timing(False)
         acc_alone_ms = kt["msm_accumulate"][0] / max(kt["msm_accumulate"][1], 1)
 
-    # ---- end to end, resident form (N = 1): witness-side columns arrive from pinned HOST memory once per proof,
-    # every polynomial then stays in HBM through quotient (evaluate_h), evaluation round and GWC opening; only
-    # commitments and evaluations come back.  This is the dataflow of create_proof itself (prover.py).
+    # ---- end to end at EVERY N: witness in (pinned HOST columns on their owner ranks), proof elements out.  Every
+    # polynomial stays in HBM through rounds 1-3, the quotient (evaluate_h), the evaluation round and the GWC opening;
+    # only commitments and evaluations come back.  N = 1 is the ResidentProver flow; N > 1 spreads the same proof over
+    # the GPUs (dist_prover.py: column-parallel rounds + window-unit MSM pool, row-sharded quotient fed by one NVLink
+    # exchange, point-to-point GWC folds).  This is the dataflow of create_proof itself.
     e2e_res = None
     n1 = None
-    if not args.no_e2e and world == 1:
+    if not args.no_e2e:
         from halo2_snark_aggregator_b200 import plonk
+        from halo2_snark_aggregator_b200.dist_prover import DistributedProver
         from halo2_snark_aggregator_b200.prover import ResidentProver, create_proof_queries
 
         cs = plonk.aggregation_circuit_cs()
-        pr = ResidentProver(ctx, cs, k, srs, srs)
+        dp = DistributedProver(ctx, cs, k, srs, srs, torch, dist if world > 1 else None, rank, world, dev)
+        pr = dp.pr
         R_MOD = plonk.R_MOD
         r2 = np.tile(plonk.fr_mont(1 << 256), n)  # Montgomery form of R: a (canonical limbs) * R2 -> Montgomery form of a
 
@@ -504,115 +508,161 @@ def main():
             canon[:, 0] = vals
             return ctx.field_op(0, 3, canon.reshape(-1), r2)
 
-        # ---- proving-key side (keygen_pk's work, once): fixed + sigma columns in Lagrange, coefficient and extended
-        # form; the range tables hold every 17-bit value, selectors are 0/1, so that the lookups are satisfiable
-        pk_names = [("fixed", i) for i in range(cs.num_fixed)] + [("sigma", j) for j in range(len(cs.permutation_columns))]
+        # ---- proving-key side (keygen_pk's work, once, replicated on every rank): fixed + sigma columns in Lagrange,
+        # coefficient and extended form; the range tables hold every 17-bit value, selectors are 0/1 (lookups satisfiable)
         rows = np.arange(n, dtype=np.uint64)
         special = {("fixed", 9): np.ones(n, dtype=np.uint64)}
         for sel, tab in ((9, 10), (11, 12), (13, 14), (15, 16)):
             special[("fixed", tab)] = rows & np.uint64((1 << 17) - 1)
             if sel != 9:
                 special[("fixed", sel)] = (rows % np.uint64(3) != 0).astype(np.uint64)
-        for j, nm in enumerate(pk_names):
-            d_l = pr.lagrange_slot(nm)
+
+        def fill_pk(nm, d_l):
             if nm in special:
                 ctx.h2d(d_l, small_column(special[nm]))
             else:
-                ctx.synth_scalars_dev(SEED_SCALARS + 5000 + j, 0, 0, n, d_l)
+                ctx.synth_scalars_dev(SEED_SCALARS + 5000 + dp.pk_names.index(nm), 0, 0, n, d_l)
+
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        pr._commit_resident(pk_names)   # 23 x (MSM + iNTT + coset NTT): the fixed / sigma commitments of the vk, too
+        dp.load_proving_key(fill_pk)    # 23 x (MSM + iNTT + coset NTT): the fixed / sigma commitments of the vk, too
         torch.cuda.synchronize()
         keygen_s = time.perf_counter() - t0
         for j, nm in enumerate([("l0", 0), ("l_last", 0), ("l_active_row", 0)]):
             dc, de = pr.slot(nm)
             ctx.synth_scalars_dev(SEED_SCALARS + 6000 + j, 0, 0, ext_n, de)
         del r2
-        # ---- witness side: instance + 5 advice columns in pinned host memory (a0..a3 are 17-bit-or-smaller values)
-        round0 = [("instance", 0)] + [("advice", i) for i in range(5)]
-        h_round0 = []
-        for i in [i for i, u in enumerate(units) if u[0] == 0 and u[1] == "msm"]:
+        # ---- witness side: instance + 5 advice columns in pinned host memory ON THEIR OWNER RANK (a0..a3 are
+        # 17-bit-or-smaller values), generated on the device from the schedule's seeds so that every rank agrees
+        tmp = dbuf(n * 32)
+
+        def witness_column(unit_index):
+            u = units[unit_index]
+            ctx.synth_scalars_dev(SEED_SCALARS + 1000 * k + unit_index, u[2], 0, n, tmp.data_ptr())
+            if u[2] != 0 and n > BLIND_ROWS:
+                ctx.synth_scalars_dev(SEED_SCALARS + 1000 * k + 500 + unit_index, 0, 0, BLIND_ROWS, tmp.data_ptr() + 32 * (n - BLIND_ROWS))
             hcol = pinned(n * 32)
-            hcol[:] = ctx.d2h(t_cols[i].data_ptr(), 4 * n)
-            h_round0.append(hcol)
-        h_random = pinned(n * 32)
-        h_random[:] = ctx.d2h(t_cols[[i for i, u in enumerate(units) if u[0] == 3 and u[1] == "msm"][0]].data_ptr(), 4 * n)
+            hcol[:] = ctx.d2h(tmp.data_ptr(), 4 * n)
+            return hcol
+
+        round0_units = [i for i, u in enumerate(units) if u[0] == 0 and u[1] == "msm"]
+        host_cols = {nm: witness_column(round0_units[j]) for j, nm in enumerate(dp.witness) if dp.owner[nm] == rank}
+        random_unit = [i for i, u in enumerate(units) if u[0] == 3 and u[1] == "msm"][0]
+        h_random = witness_column(random_unit) if dp.owner[("random", 0)] == rank else None
         blind_pool = pinned(64 * 32)
-        blind_pool[:] = ctx.d2h(t_ntt[0].data_ptr(), 4 * 64)
+        ctx.synth_scalars_dev(SEED_SCALARS + 77, 0, 0, 64, tmp.data_ptr())
+        blind_pool[:] = ctx.d2h(tmp.data_ptr(), 4 * 64)
 
         def blind(name, nrows):
             return blind_pool[: 4 * nrows]
 
-        queries = create_proof_queries(cs)
-        eval_queries = [q for q in queries if q[0] != ("h", 0)]
-        ch = [pow(3, 100 + i, R_MOD) for i in range(6)]
-
+        ch = [pow(3, 100 + i, R_MOD) for i in range(6)]     # y, beta, gamma, theta, x, v
+        challenge = {"theta": ch[3], "beta_gamma": (ch[1], ch[2]), "y": ch[0], "x": ch[4], "v": ch[5]}
         stage_ms = {}
 
-        def step_resident(stages=None):
+        def step_e2e(stages=None):
             t_prev = [time.perf_counter()]
 
-            def mark(name):
+            def on_stage(stage, out):
                 if stages is not None:
                     torch.cuda.synchronize()
                     now = time.perf_counter()
-                    stages[name] = (now - t_prev[0]) * 1e3
+                    label = {"theta": "round1_commit_6_columns", "beta_gamma": "round2_lookup_permuted_14_columns",
+                             "y": "round3_grand_products_9_columns_and_random_poly", "x": "quotient_evaluate_h_intt4n_4_commits",
+                             "v": "evaluation_round_71"}[stage]
+                    stages[label] = (now - t_prev[0]) * 1e3
                     t_prev[0] = now
+                return challenge[stage]
 
-            outs = [pr.commit_columns(round0, h_round0, keep_lagrange=True)]   # round 1: the witness arrives
-            mark("round1_commit_6_columns")
-            outs.append(pr.lookup_round(ch[3], blind))                          # round 2: 14 permuted lookup columns
-            mark("round2_lookup_permuted_14_columns")
-            outs.append(pr.product_round(ch[1], ch[2], blind))                  # round 3: 2 + 7 grand products
-            mark("round3_grand_products_9_columns")
-            outs.append(pr.commit_coeff_columns([("random", 0)], [h_random]))
-            mark("random_poly_commit")
-            outs.append(pr.quotient(*ch[:4]))
-            mark("quotient_evaluate_h_intt4n_4_commits")
-            pr.fold_h(ch[4])
-            outs.append(pr.evaluate(eval_queries, ch[4]))
-            mark("evaluation_round_70")
-            outs.append(pr.open(queries, ch[4], ch[5])[1])
-            mark("gwc_open_4_points")
-            return outs
+            out = dp.prove(host_cols, h_random, blind, on_stage)
+            if stages is not None:
+                torch.cuda.synchronize()
+                stages["gwc_open_4_points"] = (time.perf_counter() - t_prev[0]) * 1e3
+            return out
 
-        step_resident()
+        step_e2e()
         barrier()
         ctx.kernel_timing(True)
         launches_r0 = ctx.launch_count()
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
-            res_out = step_resident()
+            res_out = step_e2e()
         barrier()
         e2e_res_s = (time.perf_counter() - t0) / args.e2e_steps
         launches_r = (ctx.launch_count() - launches_r0) // args.e2e_steps
         kt = ctx.kernel_times()
         ctx.kernel_timing(False)
-        step_resident(stage_ms)   # one more, untimed for the headline, with a synchronize after every stage
-        pr.trace, pr.trace_kernels = {}, True
-        ctx.kernel_timing(True)
-        step_resident()           # and one with the prover's own finer trace of rounds 2 and 3
-        ctx.kernel_timing(False)
-        stage_ms["rounds_2_3_detail"] = {kk: vv for kk, vv in pr.trace.items() if kk != "-"}
-        pr.trace = None
-        h2d_r = 7 * n * 32 + 23 * 6 * 32
-        d2h_r = sum(int(np.asarray(o).nbytes) for o in res_out)
+        step_e2e(stage_ms)        # one more, untimed for the headline, with a synchronize after every stage
+        if world == 1:
+            pr.trace, pr.trace_kernels = {}, True
+            ctx.kernel_timing(True)
+            step_e2e()            # and one with the prover's own finer trace of rounds 2 and 3
+            ctx.kernel_timing(False)
+            stage_ms["rounds_2_3_detail"] = {kk: vv for kk, vv in pr.trace.items() if kk != "-"}
+            pr.trace = None
+        h2d_r = sum(int(v.nbytes) for v in host_cols.values()) + (int(h_random.nbytes) if h_random is not None else 0) + 23 * 6 * 32
+        d2h_r = sum(int(np.asarray(res_out[key]).nbytes) for key in ("round1", "round2", "round3", "random", "h", "evals", "w"))
+        t_e = torch.tensor([e2e_res_s], dtype=torch.float64, device=dev)
+        t_b = torch.tensor([float(h2d_r), float(dp.nvlink_bytes), float(launches_r)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t_b, op=dist.ReduceOp.SUM)
+        # parity of the e2e outputs (rank 0): N > 1 against the single-GPU ResidentProver on the same inputs, bit for bit
+        # (that prover is held against the CPU oracles at k = 16 in tests/test_gpu_prover.py); at every N the six round-1
+        # commitments against the oracle's best_multiexp
+        e2e_parity = None
+        if rank == 0 and not args.no_parity:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import oracle_binding as ob
+
+            h_bases = ctx.d2h(t_bases.data_ptr(), 8 * n)
+            ok_oracle = all(np.array_equal(res_out["round1"][j], ob.best_multiexp(oracle_column(ob, k, round0_units[j], units[round0_units[j]][2]), h_bases)[:8])
+                            for j in range(len(dp.witness)))
+            e2e_parity = {"round1_commitments_equal_oracle_best_multiexp": bool(ok_oracle)}
+            if world > 1:
+                ref = ResidentProver(ctx, cs, k, srs, srs)
+                for nm in dp.pk_names + [("l0", 0), ("l_last", 0), ("l_active_row", 0)]:   # the proving key is already resident: share it
+                    ref.adopt(nm, pr.coeff.get(nm), pr.ext.get(nm))
+                    if nm in pr.lag:
+                        ref.lag[nm] = pr.lag[nm]
+                all_cols = {nm: witness_column(round0_units[j]) for j, nm in enumerate(dp.witness)}
+                want = {"round1": ref.commit_columns(dp.witness, [all_cols[nm] for nm in dp.witness], keep_lagrange=True)}
+                want["round2"] = ref.lookup_round(ch[3], blind)
+                want["round3"] = ref.product_round(ch[1], ch[2], blind)
+                want["random"] = ref.commit_coeff_columns([("random", 0)], [witness_column(random_unit)])[0]
+                want["h"] = ref.quotient(*ch[:4])
+                ref.fold_h(ch[4])
+                queries = create_proof_queries(cs)
+                want["evals"] = ref.evaluate([q for q in queries if q[0] != ("h", 0)], ch[4])
+                want["w"] = ref.open(queries, ch[4], ch[5])[1]
+                bad = [key for key in want if not np.array_equal(np.asarray(res_out[key]), np.asarray(want[key]))]
+                e2e_parity["all_outputs_equal_single_gpu_prover"] = not bad
+                e2e_parity["mismatching"] = bad
+                ref.close()
+                del all_cols
+            if not all(v for kk, v in e2e_parity.items() if kk != "mismatching"):
+                print(json.dumps({"error": "e2e parity mismatch", "parity": e2e_parity}), file=sys.stderr, flush=True)
+                raise SystemExit(1)
+        if world > 1:
+            dist.barrier()
         qms, qn = kt["evaluate_h"]
-        n1 = {"evaluate_h_ms": qms / max(qn, 1), "rows": ext_n, "columns_read": len(pr.plan.columns),
-              "hbm_gbs": (len(pr.plan.columns) + 1) * ext_n * 32 / (qms / max(qn, 1) * 1e-3) / 1e9 if qn else None,
-              "note": "aggregation circuit's quotient (1 gate, 2 permutation sets, 7 lookups) over 55 resident extended columns, fused with the division by X^n - 1; algorithmic bytes: every column read once + h written"}
-        e2e_res = {"value": e2e_res_s, "unit": "s", "h2d_bytes_per_step": h2d_r, "d2h_bytes_per_step": d2h_r,
-                   "gpu_launches_per_step": int(launches_r), "stage_ms_synchronised": stage_ms,
+        n1 = {"evaluate_h_ms": qms / max(qn, 1), "rows": ext_n // world, "columns_read": len(pr.plan.columns),
+              "hbm_gbs": (len(pr.plan.columns) + 1) * (ext_n // world) * 32 / (qms / max(qn, 1) * 1e-3) / 1e9 if qn else None,
+              "note": "aggregation circuit's quotient (1 gate, 2 permutation sets, 7 lookups) over 55 resident extended columns, fused with the division by X^n - 1; algorithmic bytes: every column read once + h written (per rank: its row window)"}
+        e2e_res = {"value": float(t_e.item()), "unit": "s", "h2d_bytes_per_step": int(t_b[0].item()), "d2h_bytes_per_step": d2h_r * world,
+                   "nvlink_bytes_received_per_step": int(t_b[1].item()),
+                   "gpu_launches_per_step": int(t_b[2].item()), "stage_ms_synchronised_rank0": stage_ms,
+                   "parity": e2e_parity, "plan": {kk: dp.plan[kk] for kk in ("witness", "lookup", "perm_rank", "pooled_z")} if world > 1 else None,
                    "keygen_transforms_s": keygen_s,
-                   "work": "witness in, proof elements out: the schedule's 38 MSM + 29 iNTT + 29 coset-NTT + 1 iNTT(4n) PLUS everything create_proof does between them -- 14 compress_expressions, 7 permute_expression_pair (sorts), 2 permutation + 7 lookup grand products, evaluate_h over 55 extended columns, 70 eval_polynomial, the 71-polynomial GWC fold, 4 kate_division",
-                   "note": "ResidentProver (prover.py) over the C ABI: instance + 5 advice columns and the random polynomial are uploaded from pinned host memory every step (7 x 2^k x 32 B); commitments (38 x 64 B) and evaluations (70 x 32 B) are read back; rounds 2 and 3 are computed on the device from the resident columns; proving-key polynomials (fixed, sigma, l_*) stay resident across proofs as in a prover that caches its pk (keygen_transforms_s: the 23 commit + lagrange_to_coeff + coeff_to_extended of keygen_vk/pk, once, first use of the lanes included); challenges and blinding values are inputs"}
-        pr.close()
-        del h_round0, h_random, pr
+                   "work": "witness in, proof elements out: the schedule's 38 MSM + 29 iNTT + 29 coset-NTT + 1 iNTT(4n) PLUS everything create_proof does between them -- 14 compress_expressions, 7 permute_expression_pair (sorts), 2 permutation + 7 lookup grand products, evaluate_h over 55 extended columns, 71 eval_polynomial, the 72-polynomial GWC fold, 4 kate_division",
+                   "note": "DistributedProver / ResidentProver over the C ABI: instance + 5 advice columns and the random polynomial are uploaded from pinned host memory every step by their owner ranks (7 x 2^k x 32 B in total); commitments (38 x 64 B) and evaluations (71 x 32 B) are read back on every rank (each drives the transcript); rounds 2 and 3 are computed on the device from the resident columns; proving-key polynomials (fixed, sigma, l_*) stay resident across proofs, replicated per rank, as in a prover that caches its pk (keygen_transforms_s: the 23 commit + lagrange_to_coeff + coeff_to_extended of keygen_vk/pk, once); challenges and blinding values are inputs"}
+        dp.close()
+        del host_cols, h_random, pr, dp
 
     # ---- end to end through the host-pointer C ABI (pinned host memory, copies inside the timed region):
     # the drop-in shape for an UNMODIFIED halo2 prover loop, where every transform result returns to host memory
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and world == 1:
 
         # e2e is column-parallel over whole columns: a window-sharded MSM is done whole by its lowest rank
         owner = {}
