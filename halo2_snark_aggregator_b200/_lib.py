@@ -65,8 +65,6 @@ def load():
         "h2agg_host_unregister": (ci, [c_vp, c_vp]),
         "h2agg_set_msm_window": (ci, [c_vp, ci]),
         "h2agg_set_ntt_radix_cap": (ci, [c_vp, ci]),
-        "h2agg_set_msm_pair_rounds": (ci, [c_vp, ci]),
-        "h2agg_set_msm_pair_gate": (ci, [c_vp, u32]),
         "h2agg_set_srs_precompute": (ci, [c_vp, ci]),
         "h2agg_srs_config": (ci, [c_vp, u64, ctypes.POINTER(ci), ctypes.POINTER(ci), ctypes.POINTER(ci)]),
         "h2agg_msm_config": (ci, [c_vp, sz, ctypes.POINTER(ci), ctypes.POINTER(ci)]),

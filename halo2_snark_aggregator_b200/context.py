@@ -78,11 +78,6 @@ class Context:
     def set_ntt_radix_cap(self, log2_radix):
         self.check(self.lib.h2agg_set_ntt_radix_cap(self.h, int(log2_radix)))
 
-    def set_msm_pair_rounds(self, rounds, gate=None):
-        self.check(self.lib.h2agg_set_msm_pair_rounds(self.h, int(rounds)))
-        if gate is not None:
-            self.check(self.lib.h2agg_set_msm_pair_gate(self.h, int(gate)))
-
     def set_srs_precompute(self, enable):
         self.check(self.lib.h2agg_set_srs_precompute(self.h, 1 if enable else 0))
 

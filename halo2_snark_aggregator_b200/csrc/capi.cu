@@ -211,21 +211,6 @@ int h2agg_set_ntt_radix_cap(h2agg_ctx* ctx, int log2_radix) {
   return 0;
 }
 
-int h2agg_set_msm_pair_rounds(h2agg_ctx* ctx, int rounds) {
-  if (!ctx) return 1;
-  LOCK(ctx);
-  CHECK_ARG(ctx, rounds >= -1 && rounds <= 3, "msm pair rounds must be -1 (auto) or 0..3");
-  ctx->msm_pair_rounds = rounds;
-  return 0;
-}
-
-int h2agg_set_msm_pair_gate(h2agg_ctx* ctx, uint32_t min_entries) {
-  if (!ctx) return 1;
-  LOCK(ctx);
-  ctx->msm_pair_gate = min_entries;
-  return 0;
-}
-
 int h2agg_set_srs_precompute(h2agg_ctx* ctx, int enable) {
   if (!ctx) return 1;
   LOCK(ctx);
@@ -664,7 +649,7 @@ static int commit_round_impl(h2agg_ctx* ctx, uint64_t srs_id, const uint64_t* co
       if (d_lagrange_keep && d_lagrange_keep[i]) col = d_lagrange_keep[i];
       H2AGG_CUDA(ctx, cudaMemcpyAsync(col, lagrange_cols[i], n * 32, cudaMemcpyHostToDevice, ln.st));
     }
-    if ((rc = msm_run(ctx, ln.st, ln.ws, bases, col, n, (uint8_t*)ctx->small.p + i * 160, 0, -1))) return rc;
+    if ((rc = msm_run(ctx, ln.st, ln.ws, bases, col, n, (uint8_t*)ctx->small.p + i * 160, 0, -1, false))) return rc;
     if (coeff_out && coeff_out[i]) {
       cudaStream_t st = ln.st;
       if (resident) {
@@ -681,6 +666,7 @@ static int commit_round_impl(h2agg_ctx* ctx, uint64_t srs_id, const uint64_t* co
     }
   }
   if ((rc = lf.join())) return rc;
+  if ((rc = g1_normalize(ctx, ctx->stream, ctx->small.p, n_cols))) return rc;   // ONE inversion for the whole round
   H2AGG_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, ctx->small.p, n_cols * 160, cudaMemcpyDeviceToHost, ctx->stream));
   H2AGG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   for (size_t i = 0; i < n_cols; i++) memcpy(out_affine + i * 8, (uint8_t*)ctx->pinned + i * 160, 64);

@@ -100,8 +100,6 @@ struct h2agg_ctx {
   uint64_t launches = 0;
   // MSM tuning (0 = auto; a forced width also forces plain mode)
   int msm_window_bits = 0;
-  int msm_pair_rounds = -1;    // batched-affine halving rounds before the XYZZ accumulation (-1 = auto)
-  uint32_t msm_pair_gate = 1u << 23;  // ... run only when the (padded) entry count reaches this (device-side)
   bool srs_precompute = true;  // build the 2^(c w) P table when an SRS is registered
   // per-kernel-class device timing (CUDA events on ctx->stream), enabled by h2agg_kernel_timing
   bool timing = false;
@@ -211,8 +209,11 @@ struct LaneFork {
 // MSM over G1: d_scalars n x 32 B (Montgomery Fr), d_bases n x 64 B affine.
 // Writes affine (64 B) + jacobian (96 B, z = 1 or 0) to d_out (160 B, device).
 // Windows [win_begin, win_end) only (pass 0, -1 for all): partial = sum_w 2^(c w) B_w.
+// normalize = false leaves the XYZZ result (128 B) in the slot: the caller normalises a whole round with g1_normalize.
 int msm_run(h2agg_ctx* ctx, cudaStream_t st, DevBuf& ws, const MsmBases& bases, const void* d_scalars, size_t n,
-            void* d_out160, int win_begin, int win_end);
+            void* d_out160, int win_begin, int win_end, bool normalize = true);
+// XYZZ results in 160-byte slots -> affine + normalised Jacobian, one inversion for all n.
+int g1_normalize(h2agg_ctx* ctx, cudaStream_t st, void* d_out160s, size_t n);
 int msm_build_srs_table(h2agg_ctx* ctx, Srs& s);
 int msm_table_config(size_t srs_n, int* c, int* nwin);
 int witness_expand_dev(h2agg_ctx* ctx, const void* d_ops, size_t n_ops, void* const d_cols[5], size_t n_rows);

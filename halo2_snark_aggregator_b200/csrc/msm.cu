@@ -24,8 +24,9 @@
 //                          (witness columns are full of 0/1/17-bit values) is split across threads
 //                          by construction.  Bases are gathered as 4 x 16-byte read-only loads.
 //      msm_fold / msm_fold_hot  stitch the pieces of buckets that straddle chunks (CTA tree for hot ones)
-//      msm_wsum            sum_d d * B_d by a 4-ary (S, C) reduction tree
-//      msm_final           Horner over windows (plain mode), one inversion, affine + Jacobian(z=1) out
+//      msm_wsum            sum_d d * B_d by a 4-ary (S, C) reduction tree: the big levels one launch each, every level
+//      msm_wsum_tail       below 2048 items + the Horner over windows (plain mode) in ONE single-CTA launch (XYZZ out)
+//      g1_normalize_batch  affine + Jacobian(z=1) for all results of a round with one inversion
 #include "bn254_g1.cuh"
 #include "ctx.hpp"
 #include <algorithm>
@@ -37,7 +38,6 @@ static constexpr int MSM_THREADS = 128;
 static constexpr uint32_t HOT_PIECES = 8;  // buckets cut into more pieces than this get a whole CTA
 static constexpr uint32_t WSUM_L = 4;      // arity of the window-sum tree
 static constexpr uint32_t WSUM_QUAD_MAX = 16384;  // levels with at most this many outputs use the four-lane kernel
-static constexpr uint32_t ENTRY_DUMMY = 0xffffffffu;  // padding slot of the sorted entry list
 
 struct MsmGeom {
   uint32_t n;          // scalars in this MSM
@@ -51,8 +51,6 @@ struct MsmGeom {
   uint32_t win_begin, win_end;
   uint32_t table;      // 1: entries index the precomputed table [w][srs_n]
   uint32_t srs_n;      // row length of the table
-  uint32_t pair_rounds;  // batched-affine halving rounds compiled into this launch sequence (0..3)
-  uint32_t pair_gate;    // ... which only run when the padded entry count reaches this
 };
 
 int msm_window_config(size_t n, int forced_c, int* c_out, int* nwin_out) {
@@ -166,13 +164,13 @@ __device__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total, uint32_t* 
   return woff + inc - v;
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) msm_scan1(const uint32_t* __restrict__ counts, uint32_t nb, uint32_t pad,
+__global__ void __launch_bounds__(SCAN_THREADS) msm_scan1(const uint32_t* __restrict__ counts, uint32_t nb,
                                                            uint32_t* block_sums) {
   __shared__ uint32_t sh[SCAN_THREADS / 32];
   uint32_t base = blockIdx.x * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS;
   uint32_t acc = 0;
 #pragma unroll
-  for (uint32_t k = 0; k < SCAN_ITEMS; k++) acc += (base + k < nb) ? ((counts[base + k] + pad) & ~pad) : 0;
+  for (uint32_t k = 0; k < SCAN_ITEMS; k++) acc += (base + k < nb) ? counts[base + k] : 0;
   uint32_t tot;
   block_exclusive_scan(acc, &tot, sh);
   if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
@@ -198,7 +196,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) msm_scan2(uint32_t* block_sums, 
 }
 
 // offsets[nb+1] and cursor[nb] (= offsets, consumed by the scatter)
-__global__ void __launch_bounds__(SCAN_THREADS) msm_scan3(const uint32_t* __restrict__ counts, uint32_t nb, uint32_t pad,
+__global__ void __launch_bounds__(SCAN_THREADS) msm_scan3(const uint32_t* __restrict__ counts, uint32_t nb,
                                                            const uint32_t* __restrict__ block_sums, uint32_t* offsets,
                                                            uint32_t* cursor) {
   __shared__ uint32_t sh[SCAN_THREADS / 32];
@@ -207,7 +205,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) msm_scan3(const uint32_t* __rest
   uint32_t acc = 0;
 #pragma unroll
   for (uint32_t k = 0; k < SCAN_ITEMS; k++) {
-    cnt[k] = (base + k < nb) ? ((counts[base + k] + pad) & ~pad) : 0;
+    cnt[k] = (base + k < nb) ? counts[base + k] : 0;
     acc += cnt[k];
   }
   uint32_t tot;
@@ -238,21 +236,14 @@ __host__ __device__ __forceinline__ uint32_t msm_chunk_len(uint32_t total, uint3
 //   entirely inside one chunk           -> written straight to bucket_sums[b]
 //   first piece (bucket starts in t)    -> tail_part[t]
 //   every later piece (chunks t+1..)    -> head_part[t']
-__global__ void __launch_bounds__(MSM_THREADS) msm_accumulate(const uint8_t* __restrict__ bases_in,
-                                                               const uint32_t* __restrict__ entries_in,
-                                                               const uint8_t* __restrict__ paired_pts,
+__global__ void __launch_bounds__(MSM_THREADS) msm_accumulate(const uint8_t* __restrict__ bases,
+                                                               const uint32_t* __restrict__ entries,
                                                                const uint32_t* __restrict__ offsets, MsmGeom g,
                                                                uint8_t* __restrict__ head_part,
                                                                uint8_t* __restrict__ tail_part,
                                                                uint8_t* __restrict__ bucket_sums) {
-  // after `pair_rounds` halving rounds (if the device-side gate let them run) the points are already in
-  // bucket order in `paired_pts` and every offset is divided by 2^rounds
-  const bool paired = g.pair_rounds && __ldg(offsets + g.nb) >= g.pair_gate;
-  const uint32_t sh = paired ? g.pair_rounds : 0;
-  const uint8_t* __restrict__ bases = paired ? paired_pts : bases_in;
-  const uint32_t* __restrict__ entries = paired ? nullptr : entries_in;
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t total = __ldg(offsets + g.nb) >> sh;
+  const uint32_t total = __ldg(offsets + g.nb);
   const uint32_t chunk = msm_chunk_len(total, g.chunk, g.max_chunks);
   const unsigned long long start64 = (unsigned long long)t * chunk;
   if (start64 >= total) return;
@@ -262,10 +253,10 @@ __global__ void __launch_bounds__(MSM_THREADS) msm_accumulate(const uint8_t* __r
   uint32_t lo = 0, hi = g.nb;  // offsets[lo] <= start < offsets[hi]
   while (hi - lo > 1) {
     uint32_t mid = (lo + hi) >> 1;
-    if ((__ldg(offsets + mid) >> sh) <= start) lo = mid; else hi = mid;
+    if (__ldg(offsets + mid) <= start) lo = mid; else hi = mid;
   }
   uint32_t b = lo;
-  uint32_t bbeg = __ldg(offsets + b) >> sh, bend = __ldg(offsets + b + 1) >> sh;
+  uint32_t bbeg = __ldg(offsets + b), bend = __ldg(offsets + b + 1);
   G1Xyzz acc = G1Xyzz::identity();
   // ONE flat loop over the chunk: the bucket switch is a short predicated side branch, so the
   // lanes of a warp stay converged on the expensive mixed addition (a nested per-bucket loop
@@ -280,23 +271,22 @@ __global__ void __launch_bounds__(MSM_THREADS) msm_accumulate(const uint8_t* __r
       // a few full-width ones (every real halo2 column: 17-bit cells + random blinding rows) leaves gaps of 10^5 empty
       // buckets, so after a few linear steps fall back to the binary search (offsets[b+1] <= k < offsets[nb]).
       b++;
-      for (uint32_t tries = 0; (__ldg(offsets + b + 1) >> sh) <= k; ) {
+      for (uint32_t tries = 0; __ldg(offsets + b + 1) <= k; ) {
         b++;
         if (++tries == 4) {
           uint32_t lo2 = b, hi2 = g.nb;  // offsets[lo2] <= k < offsets[hi2]
           while (hi2 - lo2 > 1) {
             uint32_t mid = (lo2 + hi2) >> 1;
-            if ((__ldg(offsets + mid) >> sh) <= k) lo2 = mid; else hi2 = mid;
+            if (__ldg(offsets + mid) <= k) lo2 = mid; else hi2 = mid;
           }
           b = lo2;
           break;
         }
       }
-      bbeg = __ldg(offsets + b) >> sh;
-      bend = __ldg(offsets + b + 1) >> sh;
+      bbeg = __ldg(offsets + b);
+      bend = __ldg(offsets + b + 1);
     }
-    uint32_t e = entries ? __ldg(entries + k) : k;  // no entry list: the points are already in bucket order
-    if (e == ENTRY_DUMMY) continue;                 // padding slot
+    uint32_t e = __ldg(entries + k);
     G1Affine q = G1Affine::load_nc(bases + (size_t)(e & 0x7fffffffu) * 64);
     if (e >> 31) q.y = fp_neg(q.y);
     xyzz_madd(acc, q);
@@ -304,143 +294,6 @@ __global__ void __launch_bounds__(MSM_THREADS) msm_accumulate(const uint8_t* __r
   if (bbeg < start) acc.store(head_part + (size_t)t * 128);
   else if (bend > end) acc.store(tail_part + (size_t)t * 128);
   else acc.store(bucket_sums + (size_t)b * 128);
-}
-
-// ---- batched-affine pair rounds ------------------------------------------------------------------------
-// Before the XYZZ accumulation the sorted list can be halved a few times: neighbours (2k, 2k+1) are added
-// in AFFINE coordinates with a shared inversion (Montgomery's trick: a forward pass of running denominator
-// products, one inversion, a backward pass): 5M + 1S per addition instead of the 8M + 2S of an XYZZ mixed
-// addition, which is what matters on a part whose 256-bit multiplier (the fmaheavy pipe) is the bound.
-// Every bucket's slice of the sorted list is padded to a multiple of 2^rounds with dummy (identity) entries,
-// so pairs never straddle buckets, the bucket offsets simply halve, and a round is a plain map over pairs.
-// The inversion is shared by a whole CTA (prefix/suffix product scans in shared memory, one Fermat inversion
-// per 128 x PAIR_B additions).  P = Q, P = -Q and identities are handled exactly.
-// The rounds are gated ON THE DEVICE by the number of entries (small-scalar witness columns have few and would
-// only pay the extra latency): every kernel evaluates the same predicate on offsets[nb].
-static constexpr uint32_t PAIR_B = 256;
-
-__device__ __forceinline__ G1Affine pair_load(const uint8_t* __restrict__ points, const uint32_t* __restrict__ entries,
-                                              uint32_t i) {
-  G1Affine a;
-  if (entries) {
-    uint32_t e = __ldg(entries + i);
-    if (e == ENTRY_DUMMY) {
-      a.x = Fq::zero();
-      a.y = Fq::zero();
-      return a;
-    }
-    a = G1Affine::load_nc(points + (size_t)(e & 0x7fffffffu) * 64);
-    if (e >> 31) a.y = fp_neg(a.y);
-    return a;
-  }
-  return G1Affine::load_nc(points + (size_t)i * 64);
-}
-
-// classification shared by both passes: 0 copy p, 1 copy q, 2 identity, 3 double, 4 general
-__device__ __forceinline__ int pair_denominator(const G1Affine& p, const G1Affine& q, Fq& d) {
-  d = Fq::one();
-  if (q.is_identity()) return 0;
-  if (p.is_identity()) return 1;
-  if (p.x == q.x) {
-    if (p.y == q.y && !p.y.is_zero()) {
-      d = fp_dbl(p.y);
-      return 3;
-    }
-    return 2;
-  }
-  d = q.x - p.x;
-  return 4;
-}
-
-// 1 / run for every thread of the CTA with ONE inversion: inclusive prefix and suffix product scans
-__device__ __forceinline__ Fq block_shared_inverse(const Fq& run, uint4* sh /* 2 * MSM_THREADS * 2 uint4 */) {
-  const uint32_t t = threadIdx.x;
-  uint4* pre = sh;
-  uint4* suf = sh + 2 * MSM_THREADS;
-  Fq p = run, q = run;
-  for (uint32_t off = 1; off < MSM_THREADS; off <<= 1) {
-    pre[2 * t] = p.lo4(); pre[2 * t + 1] = p.hi4();
-    suf[2 * t] = q.lo4(); suf[2 * t + 1] = q.hi4();
-    __syncthreads();
-    if (t >= off) p = p * Fq::from_halves(pre[2 * (t - off)], pre[2 * (t - off) + 1]);
-    if (t + off < MSM_THREADS) q = q * Fq::from_halves(suf[2 * (t + off)], suf[2 * (t + off) + 1]);
-    __syncthreads();
-  }
-  pre[2 * t] = p.lo4(); pre[2 * t + 1] = p.hi4();
-  suf[2 * t] = q.lo4(); suf[2 * t + 1] = q.hi4();
-  __syncthreads();
-  __shared__ uint4 inv_total[2];
-  if (t == 0) {
-    Fq it = fp_inv(Fq::from_halves(pre[2 * (MSM_THREADS - 1)], pre[2 * (MSM_THREADS - 1) + 1]));
-    inv_total[0] = it.lo4();
-    inv_total[1] = it.hi4();
-  }
-  __syncthreads();
-  Fq r = Fq::from_halves(inv_total[0], inv_total[1]);
-  if (t > 0) r = r * Fq::from_halves(pre[2 * (t - 1)], pre[2 * (t - 1) + 1]);
-  if (t + 1 < MSM_THREADS) r = r * Fq::from_halves(suf[2 * (t + 1)], suf[2 * (t + 1) + 1]);
-  __syncthreads();
-  return r;
-}
-
-__global__ void __launch_bounds__(MSM_THREADS) msm_pair_round(const uint8_t* __restrict__ points,
-                                                               const uint32_t* __restrict__ entries,
-                                                               const uint32_t* __restrict__ offsets, uint32_t nb,
-                                                               uint32_t shift_in, uint32_t gate, uint8_t* __restrict__ out,
-                                                               uint8_t* __restrict__ scratch, uint32_t nthreads) {
-  __shared__ uint4 sh[4 * MSM_THREADS];
-  const uint32_t padded_total = __ldg(offsets + nb);
-  if (padded_total < gate) return;  // grid-uniform
-  const uint32_t total_out = (padded_total >> shift_in) >> 1;
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  const unsigned long long start64 = (unsigned long long)t * PAIR_B;
-  const bool active = start64 < total_out;
-  const uint32_t start = active ? (uint32_t)start64 : 0;
-  const uint32_t end = active ? (uint32_t)min((unsigned long long)total_out, start64 + PAIR_B) : 0;
-  if ((unsigned long long)blockIdx.x * blockDim.x * PAIR_B >= total_out) return;  // whole CTA idle
-  Fq run = Fq::one();
-  // forward: running products of the denominators
-#pragma unroll 2
-  for (uint32_t o = start; o < end; o++) {
-    G1Affine p = pair_load(points, entries, 2 * o);
-    G1Affine q = pair_load(points, entries, 2 * o + 1);
-    Fq d;
-    pair_denominator(p, q, d);
-    run.store(scratch + ((size_t)(o - start) * nthreads + t) * 32);
-    run = run * d;
-  }
-  Fq inv = block_shared_inverse(run, sh);
-  // backward: peel the individual inverses off and finish the additions
-#pragma unroll 2
-  for (uint32_t o = end; o-- > start;) {
-    G1Affine p = pair_load(points, entries, 2 * o);
-    G1Affine q = pair_load(points, entries, 2 * o + 1);
-    Fq d;
-    const int kind = pair_denominator(p, q, d);
-    Fq dinv = inv * Fq::load(scratch + ((size_t)(o - start) * nthreads + t) * 32);
-    inv = inv * d;
-    G1Affine r;
-    if (kind >= 3) {
-      Fq lam;
-      if (kind == 4) {
-        lam = (q.y - p.y) * dinv;
-      } else {
-        Fq xx = fp_sqr(p.x);
-        lam = (fp_dbl(xx) + xx) * dinv;
-      }
-      r.x = fp_sqr(lam) - p.x - q.x;  // q.x == p.x when doubling
-      r.y = lam * (p.x - r.x) - p.y;
-    } else if (kind == 0) {
-      r = p;
-    } else if (kind == 1) {
-      r = q;
-    } else {
-      r.x = Fq::zero();
-      r.y = Fq::zero();
-    }
-    r.x.store(out + (size_t)o * 64);
-    r.y.store(out + (size_t)o * 64 + 32);
-  }
 }
 
 // a whole XYZZ point from another lane of the warp
@@ -464,13 +317,12 @@ __global__ void __launch_bounds__(MSM_THREADS) msm_fold(const uint32_t* __restri
                                                          uint32_t* hot_list) {
   uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= g.nb) return;
-  const uint32_t sh = (g.pair_rounds && offsets[g.nb] >= g.pair_gate) ? g.pair_rounds : 0;
-  uint32_t beg = offsets[b] >> sh, end = offsets[b + 1] >> sh;
+  uint32_t beg = offsets[b], end = offsets[b + 1];
   if (beg == end) {
     G1Xyzz::identity().store(bucket_sums + (size_t)b * 128);
     return;
   }
-  const uint32_t chunk = msm_chunk_len(offsets[g.nb] >> sh, g.chunk, g.max_chunks);
+  const uint32_t chunk = msm_chunk_len(offsets[g.nb], g.chunk, g.max_chunks);
   uint32_t t0 = beg / chunk, t1 = (end - 1) / chunk;
   if (t0 == t1) return;  // complete, already written by its chunk
   if (t1 - t0 + 1 > HOT_PIECES) {
@@ -500,11 +352,10 @@ __global__ void __launch_bounds__(256) msm_fold_hot(const uint32_t* __restrict__
                                                      const uint32_t* __restrict__ hot_list) {
   __shared__ uint4 sh[256 * 8];  // one XYZZ point (128 B) per thread
   const uint32_t nhot = *hot_count;
-  const uint32_t sh2 = (g.pair_rounds && offsets[g.nb] >= g.pair_gate) ? g.pair_rounds : 0;
-  const uint32_t chunk = msm_chunk_len(offsets[g.nb] >> sh2, g.chunk, g.max_chunks);
+  const uint32_t chunk = msm_chunk_len(offsets[g.nb], g.chunk, g.max_chunks);
   for (uint32_t item = blockIdx.x; item < nhot * HOT_SPLIT; item += gridDim.x) {
     const uint32_t b = hot_list[item / HOT_SPLIT];
-    const uint32_t beg = offsets[b] >> sh2, end = offsets[b + 1] >> sh2;
+    const uint32_t beg = offsets[b], end = offsets[b + 1];
     uint32_t lo, hi;
     hot_slice(beg / chunk, (end - 1) / chunk, item % HOT_SPLIT, lo, hi);
     if (lo >= hi) continue;  // CTA-uniform
@@ -533,12 +384,11 @@ __global__ void __launch_bounds__(128) msm_fold_hot2(const uint32_t* __restrict_
                                                       const uint32_t* __restrict__ hot_list) {
   static_assert(HOT_SPLIT < 32, "slice sums + the first piece must fit one warp");
   const uint32_t nhot = *hot_count;
-  const uint32_t sh2 = (g.pair_rounds && offsets[g.nb] >= g.pair_gate) ? g.pair_rounds : 0;
-  const uint32_t chunk = msm_chunk_len(offsets[g.nb] >> sh2, g.chunk, g.max_chunks);
+  const uint32_t chunk = msm_chunk_len(offsets[g.nb], g.chunk, g.max_chunks);
   const uint32_t lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   for (uint32_t h = warp; h < nhot; h += nwarps) {  // warp-uniform
     const uint32_t b = hot_list[h];
-    const uint32_t beg = offsets[b] >> sh2, end = offsets[b + 1] >> sh2;
+    const uint32_t beg = offsets[b], end = offsets[b + 1];
     const uint32_t t0 = beg / chunk, t1 = (end - 1) / chunk;
     G1Xyzz acc = G1Xyzz::identity();
     if (lane < HOT_SPLIT) {
@@ -645,6 +495,141 @@ __global__ void __launch_bounds__(MSM_THREADS) msm_wsum_quad(const uint8_t* __re
   if (role == 1) acc.store(c_out + ob);
 }
 
+// One quad node of the tree (see msm_wsum_quad): lanes (R, A, C, idle) of a quad cooperate on a node; all lanes of the
+// warp execute the same calls.  `live` quads write their node; dead quads only take part in the shuffles.
+__device__ __forceinline__ void wsum_quad_node(const uint8_t* __restrict__ s_in, const uint8_t* __restrict__ c_in, uint32_t m,
+                                               uint32_t mo, uint32_t gid, bool live, uint32_t role, int base_lane,
+                                               uint8_t* __restrict__ s_out, uint8_t* __restrict__ c_out) {
+  const uint32_t w = live ? gid / mo : 0, t = live ? gid % mo : 0;
+  const uint32_t first = t * WSUM_L;
+  const uint32_t cnt = live ? min(WSUM_L, m - first) : 0;
+  const size_t base = ((size_t)w * m + first) * 128;
+  auto item = [&](const uint8_t* arr, uint32_t i) { return (live && i < cnt) ? G1Xyzz::load(arr + base + (size_t)i * 128) : G1Xyzz::identity(); };
+  G1Xyzz acc = G1Xyzz::identity();
+  if (role == 0) acc = item(s_in, 3);
+  if (role == 2) acc = item(c_in, 3);
+  G1Xyzz r_prev = xyzz_shfl(acc, base_lane);
+  {
+    G1Xyzz y = G1Xyzz::identity();
+    if (role == 0) y = item(s_in, 2);
+    if (role == 2) y = item(c_in, 2);
+    xyzz_add(acc, y);
+  }
+  G1Xyzz r_cur = xyzz_shfl(acc, base_lane);
+  if (role == 1) acc = r_prev;
+  {
+    G1Xyzz y = G1Xyzz::identity();
+    if (role == 0) y = item(s_in, 1);
+    if (role == 1) y = r_cur;
+    if (role == 2) y = item(c_in, 1);
+    xyzz_add(acc, y);
+  }
+  r_cur = xyzz_shfl(acc, base_lane);
+  {
+    G1Xyzz y = G1Xyzz::identity();
+    if (role == 0) y = item(s_in, 0);
+    if (role == 1) y = r_cur;
+    if (role == 2) y = item(c_in, 0);
+    xyzz_add(acc, y);
+  }
+  G1Xyzz csum = xyzz_shfl(acc, base_lane + 2);
+  if (role == 1) xyzz_add(acc, csum);
+  if (role == 0) {
+    acc = xyzz_dbl(acc);
+    acc = xyzz_dbl(acc);
+  }
+  if (!live) return;
+  const size_t ob = ((size_t)w * mo + t) * 128;
+  if (role == 0) acc.store(s_out + ob);
+  if (role == 1) acc.store(c_out + ob);
+}
+
+// The tail of an MSM in ONE launch of one CTA: every remaining level of the window-sum tree (from <= WSUM_TAIL_MAX items
+// over all sets down to one per set) and the Horner over the windows.  These levels are pure latency -- a handful of dependent point
+// operations each -- and used to be seven launches of msm_wsum_quad plus msm_final; the result stays in XYZZ form (no
+// inversion here: the caller normalises all results of a round with ONE inversion, g1_normalize_batch).
+static constexpr uint32_t WSUM_TAIL_THREADS = 256;   // 255 registers per thread: the quad node keeps several XYZZ points live
+static constexpr uint32_t WSUM_TAIL_MAX = 2048;
+
+__global__ void __launch_bounds__(WSUM_TAIL_THREADS) msm_wsum_tail(const uint8_t* s_in, const uint8_t* c_in, MsmGeom g, uint32_t m,
+                                                                    uint8_t* s0, uint8_t* c0, uint8_t* s1, uint8_t* c1,
+                                                                    uint8_t* out_xyzz) {
+  const uint32_t role = threadIdx.x & 3;
+  const int base_lane = (threadIdx.x & 31) & ~3;
+  uint8_t* lvl_s[2] = {s0, s1};
+  uint8_t* lvl_c[2] = {c0, c1};
+  int flip = 0;
+  bool first = true;
+  while (m > 1 || first) {  // at least one level so that C holds sum (idx + 1) * B_idx
+    first = false;
+    const uint32_t mo = (m + WSUM_L - 1) / WSUM_L;
+    const uint32_t total = g.nsets * mo;
+    for (uint32_t q0 = 0; q0 < total; q0 += WSUM_TAIL_THREADS / 4) {   // CTA-uniform trip count
+      const uint32_t gid = q0 + (threadIdx.x >> 2);
+      wsum_quad_node(s_in, c_in, m, mo, gid, gid < total, role, base_lane, lvl_s[flip], lvl_c[flip]);
+    }
+    __syncthreads();   // global writes of this CTA are visible to it after the barrier
+    s_in = lvl_s[flip];
+    c_in = lvl_c[flip];
+    flip ^= 1;
+    m = mo;
+  }
+  if (threadIdx.x != 0) return;
+  G1Xyzz acc = G1Xyzz::identity();
+  if (g.table) {
+    acc = G1Xyzz::load(c_in);
+  } else {  // plain mode: Horner over windows [wb, we), times 2^(c*wb)
+    for (int w = (int)g.win_end - 1; w >= (int)g.win_begin; w--) {
+      if (!acc.is_identity())
+        for (uint32_t k = 0; k < g.c; k++) acc = xyzz_dbl(acc);
+      xyzz_add(acc, G1Xyzz::load(c_in + (size_t)w * 128));
+    }
+    if (!acc.is_identity())
+      for (uint32_t k = 0; k < g.c * g.win_begin; k++) acc = xyzz_dbl(acc);
+  }
+  acc.store(out_xyzz);
+}
+
+// XYZZ results (128 B at the start of each 160-byte slot) -> affine (64 B) + normalised Jacobian (96 B) in place, with ONE
+// inversion for the whole batch (Montgomery's trick over the ZZZ's; 1/ZZ = ZZZ^-2 ZZ^2).  One thread: n is a commit
+// round's column count.
+__global__ void g1_normalize_batch(uint8_t* out160s, uint32_t n) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  Fq run = Fq::one();
+  for (uint32_t i = 0; i < n; i++) {   // prefix products parked in the slot's spare 32 bytes
+    G1Xyzz p = G1Xyzz::load(out160s + (size_t)i * 160);
+    run.store(out160s + (size_t)i * 160 + 128);
+    if (!p.is_identity()) run = run * p.zzz;
+  }
+  Fq inv = fp_inv(run);
+  for (uint32_t i = n; i-- > 0;) {
+    uint8_t* o = out160s + (size_t)i * 160;
+    G1Xyzz p = G1Xyzz::load(o);
+    const bool id = p.is_identity();
+    Fq x = Fq::zero(), y = Fq::zero();
+    if (!id) {
+      Fq izzz = inv * Fq::load(o + 128);
+      inv = inv * p.zzz;
+      Fq izz = fp_sqr(izzz) * fp_sqr(p.zz);
+      x = p.x * izz;
+      y = p.y * izzz;
+    }
+    x.store(o);
+    y.store(o + 32);
+    x.store(o + 64);
+    (id ? Fq::one() : y).store(o + 96);
+    (id ? Fq::zero() : Fq::one()).store(o + 128);
+  }
+}
+
+int g1_normalize(h2agg_ctx* ctx, cudaStream_t st, void* d_out160s, size_t n) {
+  if (n == 0) return 0;
+  g1_normalize_batch<<<1, 32, 0, st>>>((uint8_t*)d_out160s, (uint32_t)n);
+  ctx->launches++;
+  H2AGG_CUDA(ctx, cudaGetLastError());
+  return 0;
+}
+
 __device__ __forceinline__ void write_out160(const G1Xyzz& acc, uint8_t* out160) {
   G1Affine a = xyzz_to_affine(acc);
   bool id = acc.is_identity();
@@ -653,24 +638,6 @@ __device__ __forceinline__ void write_out160(const G1Xyzz& acc, uint8_t* out160)
   a.x.store(out160 + 64);
   (id ? Fq::one() : a.y).store(out160 + 96);
   (id ? Fq::zero() : Fq::one()).store(out160 + 128);
-}
-
-// plain mode: Horner over windows [wb, we), times 2^(c*wb); table mode: the single set is the answer
-__global__ void msm_final(const uint8_t* __restrict__ wsum_c, MsmGeom g, uint8_t* out160) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  G1Xyzz acc = G1Xyzz::identity();
-  if (g.table) {
-    acc = G1Xyzz::load(wsum_c);
-  } else {
-    for (int w = (int)g.win_end - 1; w >= (int)g.win_begin; w--) {
-      if (!acc.is_identity())
-        for (uint32_t k = 0; k < g.c; k++) acc = xyzz_dbl(acc);
-      xyzz_add(acc, G1Xyzz::load(wsum_c + (size_t)w * 128));
-    }
-    if (!acc.is_identity())
-      for (uint32_t k = 0; k < g.c * g.win_begin; k++) acc = xyzz_dbl(acc);
-  }
-  write_out160(acc, out160);
 }
 
 // one thread per output: out[j] = sum_i point(i, j); point(i, j) at pts + i * stride + j * 160 (Jacobian, 96 B)
@@ -787,7 +754,7 @@ int msm_run_batch(h2agg_ctx* ctx, const MsmBases& bases, const void* const* cols
   if (n_cols == 0) return 0;
   int rc;
   if (n_cols == 1 && !host_cols)
-    return msm_run(ctx, ctx->stream, ctx->msm_ws, bases, cols[0], n, d_out160s, win_begin, win_end);
+    return msm_run(ctx, ctx->stream, ctx->msm_ws, bases, cols[0], n, d_out160s, win_begin, win_end, true);
   if ((rc = lanes_init(ctx))) return rc;
   LaneFork lf(ctx);
   if ((rc = lf.fork())) return rc;
@@ -799,15 +766,16 @@ int msm_run_batch(h2agg_ctx* ctx, const MsmBases& bases, const void* const* cols
       if (n) H2AGG_CUDA(ctx, cudaMemcpyAsync(ln.io.p, cols[i], n * 32, cudaMemcpyHostToDevice, ln.st));
       d_col = ln.io.p;
     }
-    if ((rc = msm_run(ctx, ln.st, ln.ws, bases, d_col, n, d_out160s + i * 160, win_begin, win_end))) return rc;
+    if ((rc = msm_run(ctx, ln.st, ln.ws, bases, d_col, n, d_out160s + i * 160, win_begin, win_end, false))) return rc;
   }
-  return lf.join();
+  if ((rc = lf.join())) return rc;
+  return g1_normalize(ctx, ctx->stream, d_out160s, n_cols);   // ONE inversion for the whole round
 }
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 int msm_run(h2agg_ctx* ctx, cudaStream_t st, DevBuf& wsbuf, const MsmBases& bases, const void* d_scalars, size_t n,
-            void* d_out160, int win_begin, int win_end) {
+            void* d_out160, int win_begin, int win_end, bool normalize) {
   if (n >= (1ull << 31)) {
     ctx->last_error = "msm: n must be < 2^31";
     return 1;
@@ -834,14 +802,7 @@ int msm_run(h2agg_ctx* ctx, cudaStream_t st, DevBuf& wsbuf, const MsmBases& base
   if (g.win_begin > g.win_end) g.win_begin = g.win_end;
   g.chunk = 128;
   const uint8_t* d_points = (const uint8_t*)(table ? bases.d_table : bases.d_bases);
-  // "auto" (-1) keeps the batched-affine rounds off: measured on B200 they do not beat the XYZZ path yet
-  // (DESIGN.md 7b); 1..3 turns them on, gated on the device by the number of entries.
-  const int pair_rounds = (ctx->msm_pair_rounds >= 0) ? ctx->msm_pair_rounds : 0;
-  const uint32_t pad = pair_rounds ? ((1u << pair_rounds) - 1) : 0;
-  g.pair_rounds = (uint32_t)pair_rounds;
-  g.pair_gate = ctx->msm_pair_gate;
-  // every non-empty bucket is padded to a multiple of 2^pair_rounds
-  const size_t max_entries = (size_t)n * (g.win_end - g.win_begin) + (size_t)pad * g.nb;
+  const size_t max_entries = (size_t)n * (g.win_end - g.win_begin);
   if (max_entries >= (1ull << 32) - 1) {
     ctx->last_error = "msm: n * windows exceeds the 32-bit entry index";
     return 1;
@@ -863,14 +824,6 @@ int msm_run(h2agg_ctx* ctx, cudaStream_t st, DevBuf& wsbuf, const MsmBases& base
   size_t o_bsums = carve((size_t)scan_blocks * 4);
   size_t o_hot = carve((size_t)(g.nb + 1) * 4 + 256);
   size_t o_entries = carve((max_entries + 1) * 4);
-  // batched-affine pair rounds: outputs of the rounds + prefix-product scratch
-  size_t o_pr_pts[4] = {0, 0, 0, 0};
-  size_t o_pr_scratch = 0, pr_threads = 0;
-  for (int r = 1; r <= pair_rounds; r++) o_pr_pts[r] = carve(((max_entries >> r) + 1) * 64);
-  if (pair_rounds > 0) {
-    pr_threads = align_up(((max_entries >> 1) + PAIR_B - 1) / PAIR_B, MSM_THREADS);
-    o_pr_scratch = carve(pr_threads * PAIR_B * 32);
-  }
   size_t o_head = carve(max_chunks * 128);
   size_t o_tail = carve(max_chunks * 128);
   size_t o_buckets = carve((size_t)g.nb * 128);
@@ -900,11 +853,10 @@ int msm_run(h2agg_ctx* ctx, cudaStream_t st, DevBuf& wsbuf, const MsmBases& base
     msm_digits<false><<<dgrid, 256, 0, st>>>((const uint4*)d_scalars, g, counts, nullptr);
     ctx->launches++;
   }
-  msm_scan1<<<scan_blocks, SCAN_THREADS, 0, st>>>(counts, g.nb, pad, bsums);
+  msm_scan1<<<scan_blocks, SCAN_THREADS, 0, st>>>(counts, g.nb, bsums);
   msm_scan2<<<1, SCAN_THREADS, 0, st>>>(bsums, scan_blocks);
-  msm_scan3<<<scan_blocks, SCAN_THREADS, 0, st>>>(counts, g.nb, pad, bsums, offsets, cursor);
+  msm_scan3<<<scan_blocks, SCAN_THREADS, 0, st>>>(counts, g.nb, bsums, offsets, cursor);
   ctx->launches += 3;
-  if (pad) H2AGG_CUDA(ctx, cudaMemsetAsync(entries, 0xff, (max_entries + 1) * 4, st));  // dummy = identity
   if (n) {
     {
       ScopedKernelTimer tk(ctx, KC_MSM_DIGITS, st);
@@ -912,18 +864,8 @@ int msm_run(h2agg_ctx* ctx, cudaStream_t st, DevBuf& wsbuf, const MsmBases& base
       ctx->launches++;
     }
     ScopedKernelTimer tk(ctx, KC_MSM_ACCUMULATE, st);
-    const uint8_t* cur_pts = d_points;
-    const uint32_t* cur_entries = entries;
-    for (int r = 1; r <= pair_rounds; r++) {
-      const uint32_t nthr = (uint32_t)align_up(((max_entries >> r) + PAIR_B - 1) / PAIR_B, MSM_THREADS);
-      msm_pair_round<<<nthr / MSM_THREADS, MSM_THREADS, 0, st>>>(cur_pts, cur_entries, offsets, g.nb, (uint32_t)(r - 1),
-                                                                g.pair_gate, ws + o_pr_pts[r], ws + o_pr_scratch, nthr);
-      ctx->launches++;
-      cur_pts = ws + o_pr_pts[r];
-      cur_entries = nullptr;
-    }
     msm_accumulate<<<(uint32_t)((max_chunks + MSM_THREADS - 1) / MSM_THREADS), MSM_THREADS, 0, st>>>(
-        d_points, entries, pair_rounds ? ws + o_pr_pts[pair_rounds] : nullptr, offsets, g, head_part, tail_part, buckets);
+        d_points, entries, offsets, g, head_part, tail_part, buckets);
     ctx->launches++;
   }
   ScopedKernelTimer t_red(ctx, KC_MSM_REDUCE, st);
@@ -940,7 +882,7 @@ int msm_run(h2agg_ctx* ctx, cudaStream_t st, DevBuf& wsbuf, const MsmBases& base
   uint8_t* lvl_c[2] = {ws + o_lvl_c0, ws + o_lvl_c1};
   uint32_t m = g.bpw;
   int flip = 0;
-  do {  // at least one level so that the final C holds sum (idx+1) * B_idx
+  while ((size_t)g.nsets * m > WSUM_TAIL_MAX) {   // the big levels: one launch each
     uint32_t mo = (m + WSUM_L - 1) / WSUM_L;
     uint32_t total = g.nsets * mo;
     if (total <= WSUM_QUAD_MAX)  // few outputs: latency-bound, spread every node over four lanes
@@ -954,10 +896,13 @@ int msm_run(h2agg_ctx* ctx, cudaStream_t st, DevBuf& wsbuf, const MsmBases& base
     c_in = lvl_c[flip];
     flip ^= 1;
     m = mo;
-  } while (m > 1);
-  msm_final<<<1, 32, 0, st>>>(c_in, g, (uint8_t*)d_out160);
+  }
+  // every remaining level + the Horner over the windows: one CTA, one launch; XYZZ result into the 160-byte slot
+  msm_wsum_tail<<<1, WSUM_TAIL_THREADS, 0, st>>>(s_in, c_in, g, m, lvl_s[flip], lvl_c[flip], lvl_s[flip ^ 1], lvl_c[flip ^ 1],
+                                                 (uint8_t*)d_out160);
   ctx->launches++;
   H2AGG_CUDA(ctx, cudaGetLastError());
+  if (normalize) return g1_normalize(ctx, st, d_out160, 1);
   return 0;
 }
 

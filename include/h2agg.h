@@ -66,11 +66,6 @@ int h2agg_set_msm_window(h2agg_ctx* ctx, int c_bits);
 /* Test hook: cap the log2 radix of an NTT pass (default 8) so the multi-pass code paths (up to 4 passes)
  * can be checked against the CPU oracle at small sizes; log_n must stay <= 4 * cap. */
 int h2agg_set_ntt_radix_cap(h2agg_ctx* ctx, int log2_radix);
-/* Batched-affine halving rounds run before the XYZZ bucket accumulation: 0..3, -1 = automatic
- * (currently 0: measured slower than the XYZZ path on B200). For tests and sweeps. */
-int h2agg_set_msm_pair_rounds(h2agg_ctx* ctx, int rounds);
-/* The rounds only run (decided on the device) when an MSM has at least this many digit entries. */
-int h2agg_set_msm_pair_gate(h2agg_ctx* ctx, uint32_t min_entries);
 /* Fixed-base tables: when an SRS is registered, precompute 2^(c w) P_i for every window w
  * (W x the SRS size in HBM, c up to 20) so all windows share one bucket set.  Default on. */
 int h2agg_set_srs_precompute(h2agg_ctx* ctx, int enable);

@@ -384,11 +384,9 @@ def test_ntt_host_batches_pipelined(ctx):
         assert np.array_equal(o, ob.coeff_to_extended(c, k, k + 2, d["zeta"], d["omega_ext"]))
 
 
-@pytest.mark.parametrize("rounds", [1, 2, 3])
-def test_msm_batched_affine_pair_rounds(ctx, rounds):
-    """Force the batched-affine halving rounds on small inputs, including every special case of the
-    affine group law (P+P, P-P, identity operands, hot buckets, odd leftovers)."""
-    ctx.set_msm_pair_rounds(rounds, gate=0)  # gate 0: run the rounds whatever the size
+def test_msm_special_cases_of_the_group_law(ctx):
+    """Every special case of the group law in the bucket path (P+P, P-P, identity operands, hot buckets, odd leftovers),
+    plain and table mode, all scalar kinds."""
     try:
         n = 3000
         b = ob.gen_bases(5, n)
@@ -412,24 +410,19 @@ def test_msm_batched_affine_pair_rounds(ctx, rounds):
             s = ob.gen_scalars(77, 0, n)
             assert np.array_equal(ctx.msm_g1(s, same), ob.best_multiexp(s, same))
             ctx.set_msm_window(0)
-        sid = ctx.srs_register(b)  # table mode + pair rounds
-        try:
-            for kind in (0, 1):
-                s = ob.gen_scalars(50 + kind, kind, n)
-                assert np.array_equal(ctx.msm_g1(s, srs_id=sid), ob.best_multiexp(s, b))
-        finally:
-            ctx.srs_release(sid)
+        for bases in (b, same, holes, pm):   # table mode
+            sid = ctx.srs_register(bases)
+            try:
+                for kind in (0, 1):
+                    s = ob.gen_scalars(50 + kind, kind, n)
+                    assert np.array_equal(ctx.msm_g1(s, srs_id=sid), ob.best_multiexp(s, bases))
+            finally:
+                ctx.srs_release(sid)
         for m in (1, 2, 3, 255, 1 << 14):
             s = ob.gen_scalars(60, 0, m)
             bb = ob.gen_bases(61, m)
             assert np.array_equal(ctx.msm_g1(s, bb), ob.best_multiexp(s, bb))
-        # device-side gate: below it the padded list goes straight to the XYZZ path
-        ctx.set_msm_pair_rounds(rounds, gate=1 << 30)
-        s = ob.gen_scalars(62, 1, 5000)
-        bb = ob.gen_bases(63, 5000)
-        assert np.array_equal(ctx.msm_g1(s, bb), ob.best_multiexp(s, bb))
     finally:
-        ctx.set_msm_pair_rounds(-1, gate=1 << 23)
         ctx.set_msm_window(0)
 
 

@@ -23,8 +23,6 @@ ctx.synth_bases_dev(0x53525300 + k, 0, n, d_b)
 for i, kind in enumerate((0, 1, 2)):
     ctx.synth_scalars_dev(0x1000 + i, kind, 0, n, d_s[i])
 ctx.synchronize()
-if os.environ.get("PAIR"):
-    ctx.set_msm_pair_rounds(int(os.environ["PAIR"]), gate=int(os.environ.get("GATE", str(1 << 23))))
 sid = ctx.srs_register_dev(d_b, n) if os.environ.get("TABLE", "1") == "1" else 0
 print("srs config", ctx.srs_config(sid) if sid else None)
 ctx.kernel_timing(True)
