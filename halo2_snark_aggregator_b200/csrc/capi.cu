@@ -199,7 +199,7 @@ int h2agg_set_msm_window(h2agg_ctx* ctx, int c_bits) {
 int h2agg_set_ntt_radix_cap(h2agg_ctx* ctx, int log2_radix) {
   if (!ctx) return 1;
   LOCK(ctx);
-  CHECK_ARG(ctx, log2_radix >= 2 && log2_radix <= 8, "ntt radix cap must be in [2, 8]");
+  CHECK_ARG(ctx, log2_radix >= 2 && log2_radix <= 11, "ntt radix cap must be in [2, 11]");
   H2AGG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   for (auto& t : ctx->tw) {  // the table split follows the plan: drop cached tables
     cudaFree(t.lo);

@@ -544,12 +544,12 @@ __device__ __forceinline__ void wsum_quad_node(const uint8_t* __restrict__ s_in,
   if (role == 1) acc.store(c_out + ob);
 }
 
-// The tail of an MSM in ONE launch of one CTA: every remaining level of the window-sum tree (from <= WSUM_TAIL_MAX items
-// over all sets down to one per set) and the Horner over the windows.  These levels are pure latency -- a handful of dependent point
-// operations each -- and used to be seven launches of msm_wsum_quad plus msm_final; the result stays in XYZZ form (no
-// inversion here: the caller normalises all results of a round with ONE inversion, g1_normalize_batch).
+// The tail of an MSM in ONE launch of one CTA: the last levels of the window-sum tree (from <= WSUM_TAIL_MAX items over all
+// sets down to one per set) and the Horner over the windows -- four launches of msm_wsum_quad plus msm_final before.  The
+// result stays in XYZZ form (no inversion here: the caller normalises all results of a round with ONE inversion,
+// g1_normalize_batch, instead of a 170 us Fermat ladder on the critical path of every MSM).
 static constexpr uint32_t WSUM_TAIL_THREADS = 256;   // 255 registers per thread: the quad node keeps several XYZZ points live
-static constexpr uint32_t WSUM_TAIL_MAX = 2048;
+static constexpr uint32_t WSUM_TAIL_MAX = 256;    // = one iteration per level for the CTA (measured: a larger tail serialises ~17 us point operations and loses to one launch per level)
 
 __global__ void __launch_bounds__(WSUM_TAIL_THREADS) msm_wsum_tail(const uint8_t* s_in, const uint8_t* c_in, MsmGeom g, uint32_t m,
                                                                     uint8_t* s0, uint8_t* c0, uint8_t* s1, uint8_t* c1,

@@ -362,7 +362,7 @@ int plan_passes(const h2agg_ctx* ctx, uint32_t log_n, uint32_t* s) {
   // ntt_radix_cap (test hook, default 8) lowers the largest per-pass radix so the 2/3/4-pass code paths
   // can be exercised at sizes the CPU oracle finishes in seconds
   const uint32_t cap = ctx->ntt_radix_cap;
-  if (log_n <= (cap == 8 ? NTT_TILE_LOG : cap)) {
+  if (log_n <= (cap >= 8 ? NTT_TILE_LOG : cap)) {
     s[0] = log_n;
     return 1;
   }
