@@ -60,6 +60,20 @@ def schedule():
 
 BLIND_ROWS = 6  # every committed halo2 column ends in blinding_factors + 1 full-width random rows
 
+# dram__bytes_read.sum + dram__bytes_write.sum and the fmaheavy pipe utilisation of ONE launch of each hot kernel at
+# k = 22, from the `ncu --set full --clock-control none` captures summarised under profiles/ (bench.py never runs under a
+# profiler; these are the committed numbers of the capture named in `note`).
+NCU = {
+    "msm_accumulate": {"dram_bytes": 7371500000, "fmaheavy_pct": 86.5,
+                       "note": "profiles/r01_ncu_summary.md (r01e capture): 7.246 GB read + 0.126 GB written per launch on a uniform 2^22 column in table mode vs 0.403 GB algorithmic -- the gather of 54.5 M precomputed 64-byte points is by design (HBM bytes traded for multiplier instructions); L2 serves 19.6 % of it"},
+    "ntt_pass_intt": {"dram_bytes": 290000000, "fmaheavy_pct": 74.2,
+                      "note": "profiles/r01_ncu_summary.md: iNTT 2^22 passes move 0.44 / 0.21 / 0.22 GB (avg 0.29) vs 0.27 GB algorithmic per pass; the first pass also streams the 128 MiB inter-pass twiddle table"},
+    "ntt_pass_coset": {"dram_bytes": 1387000000, "fmaheavy_pct": 78.7,
+                       "note": "profiles/r01_ncu_summary.md: coset NTT 2^22 -> 2^24 passes move 2.12 / 1.02 / 1.03 GB (avg 1.39) vs 0.94 GB algorithmic per pass; the first pass also streams the 512 MiB inter-pass twiddle table"},
+    "quot_evaluate_h": {"dram_bytes": 34766000000, "fmaheavy_pct": 82.5,
+                        "note": "profiles/r01_ncu_summary.md: 32.03 GB read + 2.74 GB written vs 30.1 GB algorithmic (55 columns + h, 512 MiB each): every column is read once, rotations hit L2"},
+}
+
 
 def workload_config(k):
     """The workload, identical for both arms (the driver compares the two `config` dicts)."""
@@ -471,18 +485,47 @@ def main():
     def pinned(nbytes):
         return torch.empty(nbytes // 8, dtype=torch.int64).pin_memory().numpy().view(np.uint64)
 
-    # ---- the dominant kernel timed ALONE (no lane overlap) on a uniform column: multiplier roofline
-    acc_alone_ms = None
-    uni = [i for i, u in msm_units if u[2] == 0]
-    if rank == 0 and uni:
-        ctx.msm_g1_dev(t_cols[uni[0]].data_ptr(), n, t_stage.data_ptr(), srs_id=srs)
-        ctx.synchronize()
-        ctx.kernel_timing(True)
-        for _ in range(3):
-            ctx.msm_g1_dev(t_cols[uni[0]].data_ptr(), n, t_stage.data_ptr(), srs_id=srs)
-        kt = ctx.kernel_times()
-        ctx.kernel_timing(False)
-        acc_alone_ms = kt["msm_accumulate"][0] / max(kt["msm_accumulate"][1], 1)
+    # ---- kernel durations that cannot exceed the step: every hot kernel timed ALONE (one call at a time on the main
+    # stream, nothing else on the GPU, CUDA events around each launch).  msm_accumulate per scalar kind, weighted by the
+    # schedule's unit counts, is the launch duration the `roofline` object uses.
+    alone = None
+    if rank == 0:
+        alone = {"msm_accumulate_ms": {}, "msm_total_ms": {}}
+        kind_counts = {}
+        for _, u in [(i, units[i]) for i in all_msm]:
+            kind_counts[u[2]] = kind_counts.get(u[2], 0) + 1
+        t_probe = dbuf(n * 32)
+        for kind in sorted(kind_counts):
+            i = [j for j in all_msm if units[j][2] == kind][0]
+            ctx.synth_scalars_dev(SEED_SCALARS + 1000 * k + i, kind, 0, n, t_probe.data_ptr())
+            if kind != 0 and n > BLIND_ROWS:
+                ctx.synth_scalars_dev(SEED_SCALARS + 1000 * k + 500 + i, 0, 0, BLIND_ROWS, t_probe.data_ptr() + 32 * (n - BLIND_ROWS))
+            ctx.msm_g1_dev(t_probe.data_ptr(), n, t_stage.data_ptr(), srs_id=srs)
+            ctx.synchronize()
+            ctx.kernel_timing(True)
+            for _ in range(3):
+                ctx.msm_g1_dev(t_probe.data_ptr(), n, t_stage.data_ptr(), srs_id=srs)
+            kt = ctx.kernel_times()
+            ctx.kernel_timing(False)
+            alone["msm_accumulate_ms"][kind] = kt["msm_accumulate"][0] / max(kt["msm_accumulate"][1], 1)
+            alone["msm_total_ms"][kind] = kt["msm_total"][0] / max(kt["msm_total"][1], 1)
+        alone["msm_unit_counts_by_scalar_kind"] = kind_counts
+        tot = sum(kind_counts.values())
+        alone["msm_accumulate_schedule_avg_ms"] = sum(alone["msm_accumulate_ms"][kd] * c for kd, c in kind_counts.items()) / tot
+        for label, fn in (("intt", lambda: dom.lagrange_to_coeff_dev(t_ntt[0].data_ptr())),
+                          ("coset", lambda: dom.coeff_to_extended_dev(t_ntt[0].data_ptr(), t_ext[0].data_ptr())),
+                          ("ext_intt", lambda: dom.extended_to_coeff_dev(t_ext[0].data_ptr()))):
+            fn()
+            ctx.synchronize()
+            ctx.kernel_timing(True)
+            for _ in range(3):
+                fn()
+            kt = ctx.kernel_times()
+            ctx.kernel_timing(False)
+            alone["ntt_%s_pass_ms" % label] = kt["ntt_pass"][0] / max(kt["ntt_pass"][1], 1)
+            alone["ntt_%s_passes" % label] = kt["ntt_pass"][1] // 3
+        del t_probe
+    acc_alone_ms = alone["msm_accumulate_ms"].get(0) if alone else None
 
     # ---- end to end at EVERY N: witness in (pinned HOST columns on their owner ranks), proof elements out.  Every
     # polynomial stays in HBM through rounds 1-3, the quotient (evaluate_h), the evaluation round and the GWC opening;
@@ -923,24 +966,42 @@ def main():
                             "msm_window_bits": cbits, "msm_windows": nwin},
             "e2e": e2e_res if e2e_res is not None else e2e, "e2e_host_pointer_abi": e2e if e2e_res is not None else None,
             "gpu_launches": int(launches), "clocks": clock_info,
-            "roofline": {"kernel": "msm_accumulate", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": 7366600000, "peak_source": peak_src,
-                         "traffic_note": "dram__bytes_read+write of one msm_accumulate launch on a uniform 2^22 column in table mode (profiles/r01e_ncu_full_raw.csv, summarised in profiles/r01_ncu_summary.md): the gather of 54.5 M precomputed 64-byte points is by design",
-                         "algorithmic_bytes_per_launch": msm_bytes, "avg_launch_ms": (acc_ms / acc_n) if acc_n else None,
-                         "launches_timed": acc_n,
-                         "launch_ms_alone_uniform_column": acc_alone_ms,
-                         "achieved_alone": (msm_bytes / (acc_alone_ms * 1e-3) / 1e9) if acc_alone_ms else None,
-                         "frac_alone": (msm_bytes / (acc_alone_ms * 1e-3) / 1e9 / peak) if acc_alone_ms else None,
-                         "timing_note": "avg_launch_ms is the CUDA-event duration inside the timed region, where up to 8 lanes run their kernels concurrently, so it includes time shared with other lanes' kernels; *_alone is one launch on a uniform column with nothing else on the GPU",
-                         "note": "MSM is bound by the INT32 IMAD pipe, not HBM (SURVEY.md 8d); HBM fraction reported as the metric demands"},
-            "roofline_multiplier": None if not acc_alone_ms else (lambda clk: {
-                "kernel": "msm_accumulate", "bound": "int32 multiplier: IMAD.WIDE.U32 issues once per 4 clk per SM sub-partition (32 lanes/clk/SM; profiles/r01_pipe_rates_b200.jsonl, ncu fmaheavy pipe)",
-                "achieved": 1240.0 * n * nwin / (acc_alone_ms * 1e-3) / 1e12, "peak": 148 * 32 * clk * 1e6 / 1e12, "unit": "T multiplier-instr/s",
-                "frac": (1240.0 * n * nwin / (acc_alone_ms * 1e-3)) / (148 * 32 * clk * 1e6),
-                "launch_ms_alone": acc_alone_ms, "mixed_additions_per_launch": n * nwin,
-                "mixed_additions_per_s": n * nwin / (acc_alone_ms * 1e-3),
-                "note": "one launch on a uniform 2^%d column, timed alone; a mixed addition (8M+2S) is 6 Montgomery products of 136 multiplier instructions, 2 squarings of 108 and 1 dual product (a*b - c*d, one reduction) of 208 = 1240 multiplier instructions (was 10 x 136 = 1360 before the dedicated schedules)" % k})(
-                    float((clock_info or {}).get("sm_mhz") or 1965.0)),
+            "roofline": (lambda t_ms: {
+                "kernel": "msm_accumulate", "bound": "hbm", "achieved": msm_bytes / (t_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": msm_bytes / (t_ms * 1e-3) / 1e9 / peak, "traffic": NCU["msm_accumulate"]["dram_bytes"], "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": msm_bytes, "avg_launch_ms": t_ms,
+                "launch_ms_by_scalar_kind": alone["msm_accumulate_ms"], "unit_counts_by_scalar_kind": alone["msm_unit_counts_by_scalar_kind"],
+                "launch_ms_uniform_column": acc_alone_ms,
+                "frac_uniform_column": (msm_bytes / (acc_alone_ms * 1e-3) / 1e9 / peak) if acc_alone_ms else None,
+                "share_of_step_non_overlapped": t_ms * len(all_msm) / ms,
+                "timing_note": "avg_launch_ms = CUDA-event duration of ONE launch with nothing else on the GPU, per scalar kind of the schedule (0 uniform Fr x18, 1 witness a0..a3 x5, 2 witness a4 x1, 3 17-bit permuted x14), weighted by those counts: 38 launches x avg <= the step. (The event spans taken inside the timed region overlap across the 8 lanes and are reported under extra.in_step_event_ms only.)",
+                "traffic_note": NCU["msm_accumulate"]["note"],
+                "note": "MSM is bound by the 256-bit multiplier (IMAD.WIDE on the fmaheavy pipe), not by HBM (SURVEY.md 8d); the HBM fraction is reported because the metric asks for it"})(alone["msm_accumulate_schedule_avg_ms"]),
+            "roofline_other_kernels": [
+                {"kernel": "ntt_pass_kernel (iNTT 2^%d, %d passes)" % (k, alone["ntt_intt_passes"]), "bound": "hbm", "unit": "GB/s", "peak": peak,
+                 "algorithmic_bytes_per_launch": 64 * n // alone["ntt_intt_passes"], "avg_launch_ms": alone["ntt_intt_pass_ms"],
+                 "achieved": 64 * n / alone["ntt_intt_passes"] / (alone["ntt_intt_pass_ms"] * 1e-3) / 1e9,
+                 "frac": 64 * n / alone["ntt_intt_passes"] / (alone["ntt_intt_pass_ms"] * 1e-3) / 1e9 / peak,
+                 "hbm_round_trip_bytes_per_launch": 64 * n, "note": "SURVEY.md 8d counts 64 N bytes per NTT (read once, write once); a launch is one of its passes, each of which is one HBM round trip of 64 N",
+                 "traffic": NCU["ntt_pass_intt"]["dram_bytes"], "traffic_note": NCU["ntt_pass_intt"]["note"]},
+                {"kernel": "ntt_pass_kernel (coset NTT 2^%d -> 2^%d, %d passes)" % (k, k + 2, alone["ntt_coset_passes"]), "bound": "hbm", "unit": "GB/s", "peak": peak,
+                 "algorithmic_bytes_per_launch": 160 * n // alone["ntt_coset_passes"], "avg_launch_ms": alone["ntt_coset_pass_ms"],
+                 "achieved": 160 * n / alone["ntt_coset_passes"] / (alone["ntt_coset_pass_ms"] * 1e-3) / 1e9,
+                 "frac": 160 * n / alone["ntt_coset_passes"] / (alone["ntt_coset_pass_ms"] * 1e-3) / 1e9 / peak,
+                 "hbm_round_trip_bytes_per_launch": (32 * n + 5 * 32 * ext_n) // 3,
+                 "traffic": NCU["ntt_pass_coset"]["dram_bytes"], "traffic_note": NCU["ntt_pass_coset"]["note"],
+                 "note": "SURVEY.md 8d counts 160 n bytes per coset NTT; one HBM round trip per pass: the first pass reads n and writes 4n, the other two read and write 4n"},
+                None if not n1 else {"kernel": "quot_evaluate_h", "bound": "hbm", "unit": "GB/s", "peak": peak,
+                 "algorithmic_bytes_per_launch": (n1["columns_read"] + 1) * n1["rows"] * 32, "avg_launch_ms": n1["evaluate_h_ms"],
+                 "achieved": n1["hbm_gbs"], "frac": (n1["hbm_gbs"] / peak) if n1["hbm_gbs"] else None,
+                 "traffic": NCU["quot_evaluate_h"]["dram_bytes"] // world, "traffic_note": NCU["quot_evaluate_h"]["note"]}],
+            "roofline_multiplier": {
+                "bound": "256-bit multiplier: IMAD.WIDE.U32 issues on the fmaheavy half of the FMA pipe, one warp instruction per 4 clk per SM sub-partition (profiles/r01_pipe_rates_b200.jsonl)",
+                "ncu_pipe_fmaheavy_pct_of_peak": {kk: vv["fmaheavy_pct"] for kk, vv in NCU.items()},
+                "source": "ncu --set full, sm__inst_executed_pipe_fmaheavy.avg.pct_of_peak_sustained_active, one launch each at k = 22 (profiles/, see NCU table in bench.py)",
+                "field_mul_per_s_uniform_msm": (10.0 * n * nwin / (acc_alone_ms * 1e-3)) if acc_alone_ms else None,
+                "field_mul_per_s_peak": 148 * 4 * 8 * float((clock_info or {}).get("sm_mhz") or 1965.0) * 1e6 / 136,
+                "note": "a mixed addition is 8M + 2S; peak = 148 SMs x 4 sub-partitions x 8 lanes/clk / 136 wide MADs per Montgomery product; the NTT passes retire (N/2) log2 N + 2N products in their measured time at 90-96 % of that peak (DESIGN.md section 4)"},
             "cpu_baseline": cpu,
             "parity": parity,
             "witness": witness,
@@ -948,11 +1009,11 @@ def main():
             "extra": {
                 "schedule_algorithmic_bytes": sched_bytes, "schedule_hbm_gbs": sched_bytes / (ms * 1e-3) / 1e9,
                 "schedule_hbm_frac": sched_bytes / (ms * 1e-3) / 1e9 / peak,
-                "msm_avg_ms": (msm_ms / msm_n) if msm_n else None, "msm_launch_share_of_step": (msm_ms / args.steps / ms) if msm_n else None,
-                "msm_accumulate_share_of_step": (acc_ms / args.steps / ms) if acc_n else None,
-                "ntt_pass_avg_ms": (ntt_ms / ntt_n) if ntt_n else None, "ntt_share_of_step": (ntt_ms / args.steps / ms) if ntt_n else None,
-                "ntt_pass_hbm_gbs": ((64 * n * 29 / 3 * 3 + 160 * n * 29 + 256 * n) * args.steps / (ntt_ms * 1e-3) / 1e9) if ntt_n else None,
-                "msm_pairs_per_s_schedule_avg": (n / (msm_ms / msm_n * 1e-3)) if msm_n else None,
+                "in_step_event_ms": {"note": "CUDA-event spans taken INSIDE the timed region; up to 8 lanes run concurrently, so these overlap and their sum exceeds the step",
+                                     "msm_total_avg": (msm_ms / msm_n) if msm_n else None, "msm_accumulate_avg": (acc_ms / acc_n) if acc_n else None,
+                                     "ntt_pass_avg": (ntt_ms / ntt_n) if ntt_n else None},
+                "kernels_alone": alone,
+                "msm_pairs_per_s_uniform_column_alone": (n / (alone["msm_total_ms"][0] * 1e-3)) if alone and 0 in alone["msm_total_ms"] else None,
                 "msm_g1_adds_uniform_column": adds_uniform,
             },
         }
