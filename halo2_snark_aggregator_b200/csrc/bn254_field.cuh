@@ -252,11 +252,19 @@ __device__ __forceinline__ Fp<T> operator*(const Fp<T>& a, const Fp<T>& b) {
 template <class T>
 __device__ __forceinline__ Fp<T> operator*(const Fp<T>& a, const Fp<T>& b) {
   Fp<T> r;
+#ifdef H2AGG_KARATSUBA
+  if constexpr (T::IS_FR) {
+    H2AGG_MONT_MUL_FR_K(r.v, a.v, b.v);
+  } else {
+    H2AGG_MONT_MUL_FQ_K(r.v, a.v, b.v);
+  }
+#else
   if constexpr (T::IS_FR) {
     H2AGG_MONT_MUL_FR(r.v, a.v, b.v);
   } else {
     H2AGG_MONT_MUL_FQ(r.v, a.v, b.v);
   }
+#endif
   fp_reduce_once<T>(r.v);
   return r;
 }
@@ -270,11 +278,19 @@ __device__ __forceinline__ Fp<T> fp_mul_add2(const Fp<T>& a, const Fp<T>& b, con
   return a * b + c * d;
 #else
   Fp<T> r;
+#ifdef H2AGG_KARATSUBA
+  if constexpr (T::IS_FR) {
+    H2AGG_MONT_MUL_ADD2_FR_K(r.v, a.v, b.v, c.v, d.v);
+  } else {
+    H2AGG_MONT_MUL_ADD2_FQ_K(r.v, a.v, b.v, c.v, d.v);
+  }
+#else
   if constexpr (T::IS_FR) {
     H2AGG_MONT_MUL_ADD2_FR(r.v, a.v, b.v, c.v, d.v);
   } else {
     H2AGG_MONT_MUL_ADD2_FQ(r.v, a.v, b.v, c.v, d.v);
   }
+#endif
   fp_reduce_once<T>(r.v);
   return r;
 #endif

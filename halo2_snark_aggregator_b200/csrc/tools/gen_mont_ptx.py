@@ -19,6 +19,7 @@ the GPU.  Run:  python gen_mont_ptx.py   (writes ../gen/mont_mul_bn254.inc)
 import os
 import random
 import re
+import sys
 
 FR = 0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001
 FQ = 0x30644e72e131a029b85045b68181585d97816a916871ca8d3c208c16d87cfd47
@@ -175,6 +176,156 @@ class Gen:
         return self.lines
 
 
+
+    # ------------------------------------------------------------------------------------------------ Karatsuba variant
+    # a*b over two 128-bit halves: three 4x4-limb products (48 wide MADs instead of 64) + additions, then the Montgomery
+    # reduction of the low half row by row (64 wide MADs + 8 mul.lo) and one addition of the high half:
+    # 112 + 8 multiplier instructions instead of 128 + 8.  The extra work is additions, which issue on the ALU pipe while
+    # the multiplier (the bound of every kernel here) is busy.
+    def prod4(self, X, Y):
+        """X, Y: 4 register names each (128-bit values) -> 8 fresh registers holding X * Y.  Row-wise product scanning with
+        the even/odd column arrays of `row` (window of 5 limbs: X * y + carry-in < 2^160), one finished limb per row."""
+        out = []
+        E = [self.new() for _ in range(4)]      # positions 0..3
+        O = [self.new() for _ in range(4)]      # positions 1..4
+        for k in range(2):
+            self.emit("mul.lo.u32 %s, %s, %s;" % (O[2 * k], X[2 * k + 1], Y[0]))
+            self.emit("mul.hi.u32 %s, %s, %s;" % (O[2 * k + 1], X[2 * k + 1], Y[0]))
+        for k in range(2):
+            self.emit("mul.lo.u32 %s, %s, %s;" % (E[2 * k], X[2 * k], Y[0]))
+            self.emit("mul.hi.u32 %s, %s, %s;" % (E[2 * k + 1], X[2 * k], Y[0]))
+        out.append(E[0])
+        for i in range(1, 4):
+            E, O = O, E                           # the array at positions 1.. becomes the one at 0..
+            self.emit("add.cc.u32 %s, %s, %s;" % (E[0], E[0], O[1]))
+            nO = [self.new() for _ in range(4)]
+            self.emit("madc.lo.cc.u32 %s, %s, %s, %s;" % (nO[0], X[1], Y[i], O[2]))
+            self.emit("madc.hi.cc.u32 %s, %s, %s, %s;" % (nO[1], X[1], Y[i], O[3]))
+            self.emit("madc.lo.cc.u32 %s, %s, %s, 0;" % (nO[2], X[3], Y[i]))
+            self.emit("madc.hi.u32 %s, %s, %s, 0;" % (nO[3], X[3], Y[i]))
+            O = nO
+            self.emit("mad.lo.cc.u32 %s, %s, %s, %s;" % (E[0], X[0], Y[i], E[0]))
+            self.emit("madc.hi.cc.u32 %s, %s, %s, %s;" % (E[1], X[0], Y[i], E[1]))
+            self.emit("madc.lo.cc.u32 %s, %s, %s, %s;" % (E[2], X[2], Y[i], E[2]))
+            self.emit("madc.hi.cc.u32 %s, %s, %s, %s;" % (E[3], X[2], Y[i], E[3]))
+            self.emit("addc.u32 %s, %s, 0;" % (O[3], O[3]))
+            out.append(E[0])
+        # remaining limbs 4..7 = E[1..3] + O[0..3] (O one position up)
+        hi = [self.new() for _ in range(4)]
+        self.emit("add.cc.u32 %s, %s, %s;" % (hi[0], E[1], O[0]))
+        self.emit("addc.cc.u32 %s, %s, %s;" % (hi[1], E[2], O[1]))
+        self.emit("addc.cc.u32 %s, %s, %s;" % (hi[2], E[3], O[2]))
+        self.emit("addc.u32 %s, %s, 0;" % (hi[3], O[3]))
+        return out + hi
+
+    def add_n(self, dst, x, y, carry_out=None):
+        """dst = x + y over len(x) limbs (y may be shorter: zero extended); carry_out: register that receives the carry"""
+        n = len(x)
+        for j in range(n):
+            op = "add.cc.u32" if j == 0 else ("addc.cc.u32" if (j < n - 1 or carry_out) else "addc.u32")
+            self.emit("%s %s, %s, %s;" % (op, dst[j], x[j], y[j] if j < len(y) else "0"))
+        if carry_out:
+            self.emit("addc.u32 %s, 0, 0;" % carry_out)
+
+    def sub_n(self, dst, x, y):
+        """dst = x - y over len(x) limbs (no final borrow by construction)"""
+        n = len(x)
+        for j in range(n):
+            op = "sub.cc.u32" if j == 0 else ("subc.cc.u32" if j < n - 1 else "subc.u32")
+            self.emit("%s %s, %s, %s;" % (op, dst[j], x[j], y[j] if j < len(y) else "0"))
+
+    def product_karatsuba(self, A, B):
+        """-> 16 registers holding A * B (A, B: 8 register names)"""
+        A0, A1, B0, B1 = A[:4], A[4:], B[:4], B[4:]
+        z0 = self.prod4(A0, B0)
+        z2 = self.prod4(A1, B1)
+        sa, sb = [self.new() for _ in range(4)], [self.new() for _ in range(4)]
+        ca, cb = self.new(), self.new()
+        self.add_n(sa, A0, A1, ca)
+        self.add_n(sb, B0, B1, cb)
+        z1 = self.prod4(sa, sb) + [self.new()]                       # 9 limbs
+        # (sa + ca 2^128)(sb + cb 2^128) = sa sb + (ca sb + cb sa) 2^128 + ca cb 2^256
+        ma, mb = self.new(), self.new()
+        self.emit("sub.u32 %s, 0, %s;" % (ma, ca))                   # all-ones mask when the carry is set
+        self.emit("sub.u32 %s, 0, %s;" % (mb, cb))
+        ta, tb = [self.new() for _ in range(4)], [self.new() for _ in range(4)]
+        for j in range(4):
+            self.emit("and.b32 %s, %s, %s;" % (ta[j], sb[j], ma))
+            self.emit("and.b32 %s, %s, %s;" % (tb[j], sa[j], mb))
+        cc = self.new()
+        self.emit("and.b32 %s, %s, %s;" % (cc, ca, cb))
+        self.emit("mov.u32 %s, %s;" % (z1[8], cc))
+        top = z1[4:9]
+        self.add_n(top, top, ta)
+        self.add_n(top, top, tb)
+        # middle term = z1 - z0 - z2 (>= 0, < 2^257)
+        self.sub_n(z1, z1, z0)
+        self.sub_n(z1, z1, z2)
+        # T = z0 + mid 2^128 + z2 2^256
+        T = z0 + z2
+        self.add_n(T[4:16], T[4:16], z1)
+        return T
+
+    def red_row(self, even, odd, first):
+        """One row of the Montgomery reduction of an 8-limb window (the CIOS row without its a*b_i part): the position-0
+        limb is completed, m = limb * (-p^-1) mod 2^32, m * p is added with the shift of the odd array fused into the MADs."""
+        mi = self.new()
+        if first:
+            self.emit("mul.lo.u32 %s, %s, %s;" % (mi, even[0], self.imm(self.inv)))
+            for k in range(4):
+                odd[2 * k], odd[2 * k + 1] = self.new(), self.new()
+                self.emit("mul.lo.u32 %s, %s, %s;" % (odd[2 * k], mi, self.imm(self.p[2 * k + 1])))
+                self.emit("mul.hi.u32 %s, %s, %s;" % (odd[2 * k + 1], mi, self.imm(self.p[2 * k + 1])))
+        else:
+            self.emit("add.cc.u32 %s, %s, %s;" % (even[0], even[0], odd[1]))
+            self.emit("mul.lo.u32 %s, %s, %s;" % (mi, even[0], self.imm(self.inv)))
+            nodd = [None] * 8
+            for k in range(3):
+                nodd[2 * k], nodd[2 * k + 1] = self.new(), self.new()
+                self.emit("madc.lo.cc.u32 %s, %s, %s, %s;" % (nodd[2 * k], mi, self.imm(self.p[2 * k + 1]), odd[2 * k + 2]))
+                self.emit("madc.hi.cc.u32 %s, %s, %s, %s;" % (nodd[2 * k + 1], mi, self.imm(self.p[2 * k + 1]), odd[2 * k + 3]))
+            nodd[6], nodd[7] = self.new(), self.new()
+            self.emit("madc.lo.cc.u32 %s, %s, %s, 0;" % (nodd[6], mi, self.imm(self.p[7])))
+            self.emit("madc.hi.u32 %s, %s, %s, 0;" % (nodd[7], mi, self.imm(self.p[7])))
+            odd[:] = nodd
+        self.cmad(even, [self.imm(self.p[j]) for j in (0, 2, 4, 6)], mi)
+        self.emit("addc.u32 %s, %s, 0;" % (odd[7], odd[7]))
+
+    def reduce16(self, T):
+        """T: 16 registers (a product < p^2 or a sum of two) -> result registers r[0..7] = T 2^-256 mod p, in [0, 2p)"""
+        even, odd = list(T[:8]), [None] * 8
+        for i in range(0, 8, 2):
+            self.red_row(even, odd, i == 0)
+            self.red_row(odd, even, False)
+        self.emit("add.cc.u32 %s, %s, %s;" % (even[0], even[0], odd[1]))
+        for j in range(1, 7):
+            self.emit("addc.cc.u32 %s, %s, %s;" % (even[j], even[j], odd[j + 1]))
+        self.emit("addc.u32 %s, %s, 0;" % (even[7], even[7]))
+        self.add_n(even, even, T[8:16])           # + the high half: U + T_hi < p + 1 + p^2 / 2^256 < 2p
+        return even
+
+    def mont_mul_k(self):
+        A = ["%%%d" % (8 + i) for i in range(8)]
+        B = ["%%%d" % (16 + i) for i in range(8)]
+        r = self.reduce16(self.product_karatsuba(A, B))
+        for j in range(8):
+            self.emit("mov.u32 %%%d, %s;" % (j, r[j]))
+        return self.lines
+
+    def mont_mul_add2_k(self):
+        A = ["%%%d" % (8 + i) for i in range(8)]
+        B = ["%%%d" % (16 + i) for i in range(8)]
+        C = ["%%%d" % (24 + i) for i in range(8)]
+        D = ["%%%d" % (32 + i) for i in range(8)]
+        T = self.product_karatsuba(A, B)
+        U = self.product_karatsuba(C, D)
+        self.add_n(T, T, U)                        # < 2 p^2 < 2^509
+        r = self.reduce16(T)
+        for j in range(8):
+            self.emit("mov.u32 %%%d, %s;" % (j, r[j]))
+        return self.lines
+
+
 def run_ptx(lines, a, b, c=0, d=0):
     """Minimal interpreter for exactly the instruction forms emitted above."""
     regs = {}
@@ -184,6 +335,7 @@ def run_ptx(lines, a, b, c=0, d=0):
         regs["%%%d" % (24 + i)] = (c >> (32 * i)) & M32
         regs["%%%d" % (32 + i)] = (d >> (32 * i)) & M32
     cc = 0
+    bw = 0       # borrow flag of sub.cc / subc chains (kept apart from the carry so that a mixed-up chain is caught)
     pending = 0  # a carry of 1 written by a .cc instruction that no instruction has consumed yet
 
     def val(x):
@@ -198,10 +350,11 @@ def run_ptx(lines, a, b, c=0, d=0):
         m = re.match(r"([a-z0-9.]+)\s+(.*);", ln)
         op, args = m.group(1), [s.strip() for s in m.group(2).split(",")]
         d = args[0]
+        assert not (bw and not op.startswith("sub")), "borrow pending across a non-sub instruction: " + ln
         consumes = op.startswith("madc") or op.startswith("addc")
         if consumes:
             pending = 0
-        elif ".cc" in op or op == "and.b32":
+        elif ".cc" in op or op in ("and.b32", "sub.u32"):
             # a fresh chain starts here: a carry of 1 nobody consumed would be lost -- the schedule's bounds forbid that
             assert pending == 0, "carry dropped before: " + ln
         if op == "mov.u32":
@@ -228,6 +381,16 @@ def run_ptx(lines, a, b, c=0, d=0):
             if ".cc." in op:
                 cc = s >> 32
                 pending = cc
+        elif op.startswith("sub"):
+            # PTX sub.cc / subc: CC.CF holds the BORROW of the subtraction chain
+            base = op.split(".")[0]
+            s = val(args[1]) - val(args[2]) - (bw if base == "subc" else 0)
+            regs[d] = s & M32
+            if ".cc." in op:
+                bw = 1 if s < 0 else 0
+            elif base == "subc":
+                assert s >= 0, "borrow out of the last limb: " + ln
+                bw = 0
         else:
             raise ValueError(op)
         assert cc in (0, 1)
@@ -338,6 +501,24 @@ def main():
         selfcheck_add2(P, lines2)
         text += c_body_add2(name, lines2, g2.ntemps) + "\n"
         print("%s add2: %d PTX instructions, %d temps, self-check ok" % (name, len(lines2), g2.ntemps))
+        if "--with-karatsuba" not in sys.argv:
+            continue
+        # Measured on B200 and REJECTED: 120 instead of 136 multiplier instructions per product, but the
+        # ~100 extra additions (IADD3.X / IMAD.X) cost more issue slots than the 16 wide MADs save:
+        # msm_accumulate 8.09 -> 9.82 ms, coset NTT 3.39 -> 3.74 ms.  Kept behind this flag (+ -DH2AGG_KARATSUBA) so the
+        # experiment can be repeated.
+        gk = Gen(P)
+        lk = gk.mont_mul_k()
+        selfcheck(P, lk, rounds=1500)
+        text += c_body(name + "_K", lk, gk.ntemps) + "\n"
+        nm = sum(1 for ln in lk if ln.startswith(("mad.lo", "madc.lo", "mul.lo")))
+        print("%s karatsuba: %d PTX instructions (%d multiplier pairs/singles), %d temps, self-check ok" % (name, len(lk), nm, gk.ntemps))
+        gk2 = Gen(P)
+        lk2 = gk2.mont_mul_add2_k()
+        selfcheck_add2(P, lk2, rounds=1000)
+        text += c_body_add2(name + "_K", lk2, gk2.ntemps) + "\n"
+        nm = sum(1 for ln in lk2 if ln.startswith(("mad.lo", "madc.lo", "mul.lo")))
+        print("%s karatsuba add2: %d PTX instructions (%d multiplier pairs/singles), %d temps, self-check ok" % (name, len(lk2), nm, gk2.ntemps))
     with open(dst, "w") as f:
         f.write(text)
     print("wrote", os.path.normpath(dst))
