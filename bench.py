@@ -568,12 +568,9 @@ def main():
 
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        dp.load_proving_key(fill_pk)    # 23 x (MSM + iNTT + coset NTT): the fixed / sigma commitments of the vk, too
+        dp.load_proving_key(fill_pk)    # keygen_pk: 23 x (MSM + iNTT + coset NTT) for fixed / sigma (the vk's commitments, too) + l_0, l_last, l_active_row
         torch.cuda.synchronize()
         keygen_s = time.perf_counter() - t0
-        for j, nm in enumerate([("l0", 0), ("l_last", 0), ("l_active_row", 0)]):
-            dc, de = pr.slot(nm)
-            ctx.synth_scalars_dev(SEED_SCALARS + 6000 + j, 0, 0, ext_n, de)
         del r2
         # ---- witness side: instance + 5 advice columns in pinned host memory ON THEIR OWNER RANK (a0..a3 are
         # 17-bit-or-smaller values), generated on the device from the schedule's seeds so that every rank agrees

@@ -147,6 +147,9 @@ def load():
         "h2agg_witness_expand": (ci, [c_vp, c_vp, ctypes.POINTER(c_vp), sz]),
         "h2agg_witness_expand_dev": (ci, [c_vp, c_vp, ctypes.POINTER(c_vp), sz]),
         "h2agg_fr_repr": (ci, [c_vp, ci, c_vp, c_vp, sz]),
+        "h2agg_g1_decompress": (ci, [c_vp, c_vp, c_vp, sz]),
+        "h2agg_g1_decompress_dev": (ci, [c_vp, c_vp, c_vp, sz]),
+        "h2agg_g1_compress": (ci, [c_vp, c_vp, c_vp, sz]),
         "h2agg_field_mul": (ci, [c_vp, ci, c_vp, c_vp, c_vp, sz]),
         "h2agg_field_op": (ci, [c_vp, ci, ci, c_vp, c_vp, c_vp, sz]),
         "h2agg_dev_alloc": (ci, [c_vp, sz, ctypes.POINTER(c_vp)]),

@@ -372,6 +372,24 @@ class Context:
         self.check(self.lib.h2agg_fr_repr(self.h, 1, _ptr(a), _ptr(out), a.size // 4))
         return out
 
+    # -- N4: G1Affine::to_bytes / from_bytes in bulk (the point codec of ParamsKZG files and Poseidon transcripts)
+    def g1_decompress(self, data):
+        """n*32 bytes -> affine Montgomery limbs (n*8 uint64); raises H2aggError (status 4) on an invalid encoding"""
+        buf = np.frombuffer(bytes(data), dtype=np.uint8).copy()
+        n = buf.size // 32
+        out = np.empty(8 * n, dtype=np.uint64)
+        self.check(self.lib.h2agg_g1_decompress(self.h, c_vp(buf.ctypes.data), _ptr(out), n))
+        return out
+
+    def g1_decompress_dev(self, d_in, d_out, n):
+        self.check(self.lib.h2agg_g1_decompress_dev(self.h, c_vp(d_in), c_vp(d_out), n))
+
+    def g1_compress(self, affine):
+        n = affine.size // 8
+        out = np.empty(32 * n, dtype=np.uint8)
+        self.check(self.lib.h2agg_g1_compress(self.h, _ptr(affine), c_vp(out.ctypes.data), n))
+        return out.tobytes()
+
     # -- field helpers (device)
     def field_op(self, field, op, a, b=None):
         out = np.empty_like(a)

@@ -137,11 +137,9 @@ class DistributedProver:
 
     # ---- proving key: replicated on every rank ------------------------------------------------------------------------
     def load_proving_key(self, fill):
-        """fill(name, d_lagrange): write the Lagrange column of every fixed / sigma polynomial into HBM (keygen_pk's
-        output).  Commits (the vk's fixed / permutation commitments) + lagrange_to_coeff + coeff_to_extended once."""
-        for nm in self.pk_names:
-            fill(nm, self.pr.lagrange_slot(nm))
-        return self.pr._commit_resident(self.pk_names)
+        """ResidentProver.keygen_pk on every rank (the key is replicated): fixed / sigma commitments + their coefficient and
+        extended forms + l_0, l_last, l_active_row; fill(name, d_lagrange) writes a Lagrange column into HBM."""
+        return self.pr.keygen_pk(fill)
 
     # ---- round 1: witness columns --------------------------------------------------------------------------------------
     def round1(self, host_cols):

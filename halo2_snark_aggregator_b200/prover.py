@@ -92,6 +92,37 @@ class ResidentProver:
             self.ctx.dev_free(p)
         self._owned = []
 
+    # -- keygen: the proving key's polynomials, once per (params, vk) ----------------------------------
+    def pk_names(self):
+        cs = self.cs
+        return [("fixed", i) for i in range(cs.num_fixed)] + [("sigma", j) for j in range(len(cs.permutation_columns))]
+
+    def keygen_pk(self, fill):
+        """The numeric part of `keygen_vk` + `keygen_pk` (halo2_proofs plonk/keygen.rs; the reference runs keygen_pk inside
+        EVERY verify_run, halo2-snark-aggregator-circuit/src/verify_circuit.rs:974-979, and keygen_vk in verify_setup,
+        :760-761): for the fixed columns and the permutation's sigma columns -- commit (the vk's fixed / permutation
+        commitments), lagrange_to_coeff, coeff_to_extended -- plus l_0, l_last and l_active_row on the extended domain.
+        fill(name, d_lagrange) writes the Lagrange form of ("fixed", i) / ("sigma", j) into the given device buffer
+        (2^k x 32 B, Montgomery): the assignment of those cells is circuit synthesis and stays with the caller.
+        Everything stays resident under the same names, so the key is computed once per process and reused by every proof
+        (`ProvingKeyCache`).  -> {"fixed": (num_fixed, 8), "sigma": (num_perm_columns, 8)} affine commitments."""
+        names = self.pk_names()
+        for nm in names:
+            fill(nm, self.lagrange_slot(nm))
+        comm = self._commit_resident(names)
+        nf = self.cs.num_fixed
+        # l_0 = L_0, l_last = L_(n - blinding_factors - 1), l_active_row = 1 - (l_last + l_blind) = sum of L_i over the usable rows
+        one = plonk.fr_mont(1)
+        n, last = self.n, self.n - self.cs.blinding_factors() - 1
+        col = np.zeros((n, 4), dtype=np.uint64)
+        sel = [("l0", 0), ("l_last", 0), ("l_active_row", 0)]
+        for nm, rows in zip(sel, (slice(0, 1), slice(last, last + 1), slice(0, last))):
+            col[:] = 0
+            col[rows] = one
+            self.ctx.h2d(self.lagrange_slot(nm), col.reshape(-1))
+        self._commit_resident(sel)      # (their commitments are not part of the vk; the transforms are what is needed)
+        return {"fixed": comm[:nf], "sigma": comm[nf:]}
+
     # -- stages 1-3: commit rounds -------------------------------------------------------------------
     def lagrange_slot(self, name):
         if name not in self.lag:
@@ -286,6 +317,30 @@ class ResidentProver:
             self.ctx.kate_division_dev(d_fold, self.n, fr_to_limbs(self.rotate_omega(x, rot)), d_w)
             ws.append(d_w)
         return order, self._commit_dev(ws)
+
+
+class ProvingKeyCache:
+    """The reference recomputes keygen_pk in every verify_run (verify_circuit.rs:974-979: the proving key is never
+    persisted).  Here a prover whose key is resident is kept per (device context, circuit shape, k,
+    caller's key id -- e.g. the vk digest) for the life of the process, so the 26 x (MSM + iNTT + coset NTT) of the key are
+    paid once, not per proof."""
+
+    def __init__(self):
+        self._provers = {}
+
+    def get(self, key_id, make_prover, fill):
+        """make_prover() -> a fresh ResidentProver; fill as for keygen_pk.  -> (prover, commitments, cached?)"""
+        if key_id in self._provers:
+            pr, comm = self._provers[key_id]
+            return pr, comm, True
+        pr = make_prover()
+        comm = pr.keygen_pk(fill)
+        self._provers[key_id] = (pr, comm)
+        return pr, comm, False
+
+    def drop(self, key_id):
+        pr, _ = self._provers.pop(key_id)
+        pr.close()
 
 
 def create_proof_queries(cs):

@@ -366,6 +366,17 @@ int h2agg_witness_expand_dev(h2agg_ctx* ctx, h2agg_witness* w, void* const d_col
  * limbs, status 4 if a value is not < r (from_repr(..).unwrap() would panic).  Host pointers, n x 32 B each way. */
 int h2agg_fr_repr(h2agg_ctx* ctx, int from_repr, const void* in, void* out, size_t n);
 
+/* N4: the G1 point codec of the stage files.  ParamsKZG::read / write (halo2_proofs poly/kzg/commitment.rs) hold g and
+ * g_lagrange as COMPRESSED points -- halo2curves 0.2.1 G1Affine::to_bytes / from_bytes: 32-byte little-endian x, parity of
+ * y in bit 7 of byte 31, identity = 32 zero bytes.  The reference decodes the 2 x 2^k points of verify_circuit.params at the
+ * start of every verify_run (halo2-snark-aggregator-circuit/src/fs.rs:109-115) and of HALO2_PARAMS_k in get_params_cached
+ * (verify_circuit.rs:701-731); the inner proofs' transcript points use the same encoding
+ * (halo2-snark-aggregator-api/src/systems/halo2/transcript.rs:63-65).  decompress: one Fq square root per point; status 4
+ * when an encoding is not a curve point or x >= p (from_bytes(..) is None; the reference unwraps). */
+int h2agg_g1_decompress(h2agg_ctx* ctx, const uint8_t* in /* n*32 */, uint64_t* out_affine /* n*8, Montgomery */, size_t n);
+int h2agg_g1_decompress_dev(h2agg_ctx* ctx, const void* d_in /* n*32 B */, void* d_out_affine /* n*64 B */, size_t n);
+int h2agg_g1_compress(h2agg_ctx* ctx, const uint64_t* affine /* n*8 */, uint8_t* out /* n*32 */, size_t n);
+
 /* ---- small helpers used by tests and the host layer (run on the device) ---------------------- */
 /* out[i] = a[i] * b[i] in Fr (field = 0) or Fq (field = 1); host pointers; Montgomery form. */
 int h2agg_field_mul(h2agg_ctx* ctx, int field, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n);

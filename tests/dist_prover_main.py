@@ -98,16 +98,13 @@ def main():
 
     dp = DistributedProver(ctx, cs, k, sid_gl, sid_g, torch, dist if world > 1 else None, rank, world, dev)
     dp.load_proving_key(fill)
-    selectors(dp.pr)
     host = {nm: cols[nm] for nm in dp.witness}
     out = dp.prove(host, cols[("random", 0)], blind, lambda stage, _o: ch[stage])
     ctx.synchronize()
 
     # the single-GPU prover on this rank, same inputs
     pr = ResidentProver(ctx, cs, k, sid_gl, sid_g)
-    pk = dp.pk_names
-    pr.commit_columns(pk, [cols[nm] for nm in pk], keep_lagrange=True)
-    selectors(pr)
+    pr.keygen_pk(fill)
     want = {}
     want["round1"] = pr.commit_columns(dp.witness, [cols[nm] for nm in dp.witness], keep_lagrange=True)
     want["round2"] = pr.lookup_round(ch["theta"], blind)

@@ -625,3 +625,47 @@ def test_eval_polynomials_batch(ctx, n, m):
         assert np.array_equal(got[i], ob.eval_polynomial(polys[i], pt)), i
     for q in d + [d_out]:
         ctx.dev_free(q)
+
+
+# ---------------------------------------------------------------- N4: point codec (ParamsKZG files, Poseidon transcripts)
+def test_g1_point_codec_vs_python_restatement(ctx):
+    """h2agg_g1_compress / _decompress against the Python restatement of halo2curves G1Affine::{to_bytes, from_bytes}
+    (oracle/py/mini_prover.py point_to_bytes / point_from_bytes): round trip on 5000 points incl. identities, both
+    parities, and rejection of encodings that are not curve points / not canonical."""
+    import bn254_ref as ref
+    import mini_prover as mp
+    import halo2_snark_aggregator_b200 as h2
+
+    n = 5000
+    b = ob.gen_bases(0xC0DEC, n)
+    b.reshape(-1, 8)[::97] = 0                                   # identities
+    enc = ctx.g1_compress(b)
+    pts = [ref.unpack_point([int(v) for v in b[8 * i:8 * i + 8]]) for i in range(n)]
+    assert enc == b"".join(mp.point_to_bytes(p) for p in pts)
+    assert {e[31] >> 7 for e in (enc[32 * i:32 * i + 32] for i in range(n))} == {0, 1}
+    assert np.array_equal(ctx.g1_decompress(enc), b)
+    assert all(mp.point_from_bytes(enc[32 * i:32 * i + 32]) == pts[i] for i in range(0, n, 50))
+    bad_x = next(x for x in range(2, 100) if pow((x ** 3 + 3) % ref.P, (ref.P - 1) // 2, ref.P) != 1)   # x^3 + 3 is not a square
+    for bad in (bad_x.to_bytes(32, "little"), (ref.P + 1).to_bytes(32, "little"), bytes(31) + b"\x80"):
+        with pytest.raises(h2.H2aggError) as e:
+            ctx.g1_decompress(enc[:64] + bad)
+        assert "error 4" in str(e.value)
+
+
+def test_params_kzg_read_write_round_trip(ctx):
+    """ParamsKZG::write -> read: both SRS tables come back bit-identical and commit the same (k = 12)."""
+    from halo2_snark_aggregator_b200.params import ParamsKZG
+
+    k = 12
+    n = 1 << k
+    g, gl = ob.gen_bases(0xA1, n), ob.gen_bases(0xA2, n)
+    p1 = ParamsKZG(k, g, gl, ctx, g2_bytes=bytes(range(64)), s_g2_bytes=bytes(range(64, 128)))
+    blob = p1.write()
+    assert len(blob) == 4 + 64 * n + 128 and blob[:4] == k.to_bytes(4, "little")
+    p2 = ParamsKZG.read(blob, ctx)
+    s = ob.gen_scalars(0xA3, 0, n)
+    assert np.array_equal(p2.commit_lagrange(s), ob.best_multiexp(s, gl))
+    assert np.array_equal(p2.commit(s), ob.best_multiexp(s, g))
+    assert p2.write() == blob
+    p1.release()
+    p2.release()

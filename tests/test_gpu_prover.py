@@ -542,3 +542,40 @@ def test_distributed_prover_world1_equals_resident_prover():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, os.path.join(root, "tests", "dist_prover_main.py"), "11"], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "DIST_PROVER_OK world=1" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def test_keygen_pk_and_proving_key_cache(ctx):
+    """ResidentProver.keygen_pk: the vk's fixed / permutation commitments = oracle best_multiexp of the Lagrange columns;
+    l_0 / l_last / l_active_row on the extended domain = oracle transforms of the halo2 keygen definitions; and the
+    ProvingKeyCache hands the same resident prover back instead of recomputing the key (the reference recomputes
+    keygen_pk in every verify_run, verify_circuit.rs:974-979)."""
+    from halo2_snark_aggregator_b200.prover import ProvingKeyCache
+
+    cs = plonk.aggregation_circuit_cs()
+    k = 7
+    n = 1 << k
+    gl = ob.gen_bases(0x7400, n)
+    sid = ctx.srs_register(gl)
+    cols = {}
+    calls = []
+
+    def fill(nm, d_l):
+        calls.append(nm)
+        cols[nm] = ob.gen_scalars(0x7500 + len(cols), 0, n)
+        ctx.h2d(d_l, cols[nm])
+
+    cache = ProvingKeyCache()
+    pr, comm, cached = cache.get(("vk-digest", k), lambda: ResidentProver(ctx, cs, k, sid, sid), fill)
+    assert not cached and len(calls) == cs.num_fixed + len(cs.permutation_columns)
+    d = domain_consts(k, pr.ext_k)
+    for i in range(cs.num_fixed):
+        assert np.array_equal(comm["fixed"][i], ob.best_multiexp(cols[("fixed", i)], gl)[:8])
+    for j in range(len(cs.permutation_columns)):
+        assert np.array_equal(comm["sigma"][j], ob.best_multiexp(cols[("sigma", j)], gl)[:8])
+    for nm, vals in zip((("l0", 0), ("l_last", 0), ("l_active_row", 0)), qu.lagrange_selectors(k, cs.blinding_factors())):
+        co = ob.ifft(qu.pack(vals), d["omega_inv"], d["n_inv"], k)
+        assert np.array_equal(ctx.d2h(pr.ext[nm], 4 << pr.ext_k), ob.coeff_to_extended(co, k, pr.ext_k, d["zeta"], d["omega_ext"])), nm
+    pr2, comm2, cached2 = cache.get(("vk-digest", k), lambda: 1 / 0, fill)
+    assert cached2 and pr2 is pr and len(calls) == cs.num_fixed + len(cs.permutation_columns)
+    cache.drop(("vk-digest", k))
+    ctx.srs_release(sid)

@@ -120,3 +120,10 @@ def test_kernel_constants():
     assert val(words("W_P_LIMB0")) == E.P % (1 << 68)
     assert val(words("W_NATIVE")) == E.P % E.R
     assert val(words("W_INV_2_136")) == pow(1 << 136, -1, E.R)
+
+
+def test_codec_square_root_exponent_constant():
+    src = open(os.path.join(ROOT, "halo2_snark_aggregator_b200", "csrc", "codec.cu")).read()
+    m = re.search(r"FQ_SQRT_EXP\[8\]\s*=\s*\{(.*?)\};", src, re.S)
+    words = [int(x, 16) for x in re.findall(r"0x[0-9a-f]+", m.group(1))]
+    assert sum(w << (32 * i) for i, w in enumerate(words)) == (E.P + 1) // 4 and E.P % 4 == 3
