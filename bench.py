@@ -770,44 +770,75 @@ def main():
                "note": "host-pointer C ABI with pinned buffers: one fused call per commit round (h2agg_commit_round: upload once, commit, lagrange_to_coeff, coeff_to_extended; every coefficient vector and every extended evaluation is downloaded), batched MSM calls for the remaining commitments, one extended_to_coeff; lanes overlap H2D / kernels / D2H"}
         del h_cols, h_ntt, h_ext
 
-    # ---- witness path (W1-W5): multi_exp of 8 transcript points through the recording chip + expansion kernel
+    # ---- witness path (W1-W6): the rows of an aggregation circuit are ~95 % multi_exp (EccChipOps::shamir) rows, so the
+    # headline workload is ONE multi_exp of 68 transcript points (>= 2^21 rows: what aggregating three inner proofs
+    # costs) through the recording chip + the expansion kernel, timed end to end (assign, record, H2D of the records,
+    # kernel) in steady state -- the first, untimed pass page-locks the record chunks and faults them in, a long-lived
+    # prover pays that once.  Next to it: the op mix of a whole aggregation (Poseidon transcript, ScalarChip
+    # expressions, instance commitments, two multi_exps) driven op by op through the Python mirror of the chips, where
+    # the ~30k tiny ScalarChip calls per proof are bound by the Python/ctypes call overhead, not by the recorder.
     witness = None
     if rank == 0 and not args.no_witness:
         from halo2_snark_aggregator_b200 import B200EccChip
+        from halo2_snark_aggregator_b200.witness import B200Context, B200EncodeChip, B200ScalarChip
+        from halo2_snark_aggregator_b200.witness_workload import record_aggregation_like
 
-        npts = 8
-        pts_dev = dbuf(npts * 64)
-        ctx.synth_bases_dev(SEED_BASES + 7, 0, npts, pts_dev.data_ptr())
-        pts = ctx.d2h(pts_dev.data_ptr(), 8 * npts).reshape(npts, 8)
-        chip = B200EccChip()
-        t0 = time.perf_counter()
-        hp = [chip.assign_var(pts[i]) for i in range(npts)]
-        hs = [chip.assign_scalar((0x1234567 * (i + 3)) ** 9 % ((1 << 253) - 1)) for i in range(npts)]
-        chip.multi_exp(hp, hs)
-        t_rec = time.perf_counter() - t0
-        rows, nops = chip.rows(), chip.ops()
-        wk = 20
-        while (1 << wk) < rows:
-            wk += 1
+        npts = 68
+        pts_dev = dbuf(4096 * 64)
+        ctx.synth_bases_dev(SEED_BASES + 7, 0, 4096, pts_dev.data_ptr())
+        all_pts = ctx.d2h(pts_dev.data_ptr(), 8 * 4096).reshape(4096, 8)
+        pts = all_pts[:npts]
+        wk = 22
         d_cols = [dbuf((1 << wk) * 32) for _ in range(5)]
         ptrs = [t.data_ptr() for t in d_cols]
-        chip.expand_dev(ctx, ptrs, 1 << wk)  # warm-up
-        ctx.synchronize()
-        ctx.kernel_timing(True)
-        t0 = time.perf_counter()
-        for _ in range(3):
+
+        def one_multi_exp():
+            chip = B200EccChip()
+            t0 = time.perf_counter()
+            hp = [chip.assign_var(pts[i]) for i in range(npts)]
+            hs = [chip.assign_scalar((0x1234567 * (i + 3)) ** 9 % ((1 << 253) - 1)) for i in range(npts)]
+            chip.multi_exp(hp, hs)
+            t1 = time.perf_counter()
+            rows_, nops_ = chip.rows(), chip.ops()
+            assert rows_ <= (1 << wk)
             chip.expand_dev(ctx, ptrs, 1 << wk)
-        ctx.synchronize()
-        t_exp = (time.perf_counter() - t0) / 3
+            ctx.synchronize()
+            t2 = time.perf_counter()
+            chip.close()
+            return rows_, nops_, t1 - t0, t2 - t1
+
+        one_multi_exp()  # untimed: page-locks / faults in the record chunks, loads the kernel
+        ctx.kernel_timing(True)
+        runs = [one_multi_exp() for _ in range(3)]
         kt = ctx.kernel_times()["witness_expand"]
         ctx.kernel_timing(False)
         kms = kt[0] / max(kt[1], 1)
+        rows, nops = runs[0][0], runs[0][1]
+        t_rec = sum(r[2] for r in runs) / len(runs)
+        t_exp = sum(r[3] for r in runs) / len(runs)
         witness = {"workload": "multi_exp (shamir) of %d transcript points: assign_point x%d + decompose + tables + 64 windows" % (npts, npts),
-                   "rows": rows, "op_records": nops, "host_record_s": t_rec, "expand_incl_h2d_s": t_exp, "expand_kernel_ms": kms,
+                   "rows": rows, "op_records": nops, "host_record_s": t_rec, "host_threads": int(os.environ.get("H2AGG_WIT_THREADS", min(16, os.cpu_count() or 1))),
+                   "expand_incl_h2d_s": t_exp, "expand_kernel_ms": kms,
                    "rows_per_s_total": rows / (t_rec + t_exp), "kernel_written_gbs": 160.0 * rows / (kms * 1e-3) / 1e9 if kms else None,
+                   "h2d_bytes": 256 * nops,
                    "algorithmic_bytes": "5*32*R written + 256 B/op record read",
+                   "how": "steady state, mean of 3: new recorder, assign, record (candidate tables and the 64 inner window sums on host threads, the accumulator chain sequential), H2D of the records from page-locked chunks, expansion kernel, synchronise",
                    "note": "row layout and every advice cell are bit-exact vs the Python restatement of halo2-ecc-circuit-lib (tests/test_gpu_witness.py)"}
-        chip.close()
+        # the whole op mix of an aggregation of 2 proofs, op by op through the Python chips
+        wctx = B200Context()
+        pchip, schip, echip = B200EccChip(wctx), B200ScalarChip(wctx), B200EncodeChip(wctx)
+        t0 = time.perf_counter()
+        record_aggregation_like(schip, pchip, echip, lambda i: all_pts[i % 4096], 2)
+        t1 = time.perf_counter()
+        arows, aops = wctx.rows(), wctx.ops()
+        if arows <= (1 << wk):
+            wctx.expand_dev(ctx, ptrs, 1 << wk)
+            ctx.synchronize()
+        t2 = time.perf_counter()
+        witness["aggregation_like_2_proofs"] = {
+            "rows": arows, "op_records": aops, "host_record_s": t1 - t0, "expand_incl_h2d_s": t2 - t1, "rows_per_s_total": arows / (t2 - t0),
+            "note": "Poseidon transcript (T = 9) + ScalarChip expression mix + scalar_mul_constant per instance + two multi_exps + final pair (witness_workload.py), every chip call crossing Python/ctypes: ~60k ScalarChip calls of 1-2 rows each dominate the host time; the Rust chips (rust/h2agg-chips) make the same calls at FFI cost"}
+        wctx.close()
         del d_cols
 
     # ---- N2 (next row): evaluation + Kate division of a 2^k coefficient vector, device resident

@@ -114,6 +114,7 @@ def load():
         "h2agg_poly_lincomb_dev": (ci, [c_vp, ctypes.POINTER(c_vp), c_vp, sz, sz, c_vp]),
         "h2agg_evaluate_h_rows_dev": (ci, [c_vp, ctypes.POINTER(QuotientArgs), u64, u64, c_vp, c_vp]),
         "h2agg_wit_new": (c_vp, []),
+        "h2agg_wit_set_threads": (ci, [ci]),
         "h2agg_wit_free": (None, [c_vp]),
         "h2agg_wit_error": (ctypes.c_char_p, [c_vp]),
         "h2agg_wit_rows": (u64, [c_vp]),

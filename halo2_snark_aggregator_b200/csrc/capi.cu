@@ -10,6 +10,10 @@ using namespace h2agg;
 
 static thread_local std::string g_init_error;
 
+namespace h2agg {
+std::atomic<int> g_any_device{-1};
+}
+
 #define LOCK(ctx) std::lock_guard<std::recursive_mutex> lock_((ctx)->mu)
 #define CHECK_ARG(ctx, cond, msg) \
   do {                            \
@@ -73,6 +77,8 @@ int h2agg_init(int device_id, h2agg_ctx** out) {
     h2agg_destroy(ctx);
     return 2;
   }
+  int none = -1;
+  h2agg::g_any_device.compare_exchange_strong(none, device_id);
   *out = ctx;
   return 0;
 }

@@ -1,5 +1,6 @@
 // Library context: device, stream, scratch arenas, cached twiddle tables, registered SRS.
 #pragma once
+#include <atomic>
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
@@ -59,6 +60,12 @@ struct Lane {
 // lazily per lane actually used.
 static constexpr int N_LANES = 8;
 
+}  // namespace h2agg
+
+namespace h2agg {
+// device of the first context created in this process (-1: none yet): the witness recorder, which has no context of its
+// own, page-locks its record chunks only once a device is known to exist
+extern std::atomic<int> g_any_device;
 }  // namespace h2agg
 
 struct h2agg_ctx {

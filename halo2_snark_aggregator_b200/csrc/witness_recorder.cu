@@ -16,8 +16,14 @@
 #include "../../include/h2agg.h"
 #include "ctx.hpp"
 #include "witness_ops.h"
+#include "host_modinv.hpp"
+#include <atomic>
+#include <cstdlib>
 #include <cstring>
+#include <exception>
+#include <mutex>
 #include <stdexcept>
+#include <thread>
 #include <vector>
 
 typedef unsigned __int128 u128;
@@ -121,72 +127,16 @@ static inline Fq q_small(u64 x) {
   u64 c[4] = {x, 0, 0, 0};
   return q_from_canon(c);
 }
-// 256-bit helpers for the binary extended Euclid below (little-endian u64 x 4)
-static inline bool u256_is_one(const u64* a) { return a[0] == 1 && (a[1] | a[2] | a[3]) == 0; }
-static inline bool u256_geq(const u64* a, const u64* b) {
-  for (int i = 3; i >= 0; i--) {
-    if (a[i] > b[i]) return true;
-    if (a[i] < b[i]) return false;
-  }
-  return true;
-}
-static inline void u256_sub(u64* a, const u64* b) {
-  u64 bo = 0;
-  for (int i = 0; i < 4; i++) {
-    u128 d = (u128)a[i] - b[i] - bo;
-    a[i] = (u64)d;
-    bo = (u64)(d >> 64) & 1;
-  }
-}
-static inline void u256_shr1(u64* a, u64 top) {
-  for (int i = 0; i < 3; i++) a[i] = (a[i] >> 1) | (a[i + 1] << 63);
-  a[3] = (a[3] >> 1) | (top << 63);
-}
-// x <- x / 2 mod p
-static inline void q_half(u64* x) {
-  u64 top = 0;
-  if (x[0] & 1) {
-    u128 c = 0;
-    for (int i = 0; i < 4; i++) {
-      c += (u128)x[i] + QP[i];
-      x[i] = (u64)c;
-      c >>= 64;
-    }
-    top = (u64)c;
-  }
-  u256_shr1(x, top);
-}
-// Inverse in Montgomery form (0 -> 0): binary extended Euclid on the Montgomery residue aR gives
-// (aR)^-1; one Montgomery product with R^3 turns that into a^-1 R.  ~1.5 us instead of ~13 us for a
-// 254-bit Fermat ladder: `div` needs one native inverse per curve operation and dominated recording.
+// Inverse in Montgomery form (0 -> 0): the safegcd inverse (host_modinv.hpp) of the Montgomery residue aR is (aR)^-1;
+// one Montgomery product with R^3 turns that into a^-1 R.  `div` needs one native inverse per curve operation.
 static const u64 QR3[4] = {0xb1cd6dafda1530dfULL, 0x62f210e6a7283db6ULL, 0xef7f0b0c0ada0afbULL, 0x20fd6e902d592544ULL};
+static const modinv::Modulus Q_MODULUS = modinv::make_modulus(QP);
 static Fq q_inv(const Fq& a) {
   if (q_is_zero(a)) return q_zero();
-  u64 u[4] = {a.v[0], a.v[1], a.v[2], a.v[3]};
-  u64 v[4] = {QP[0], QP[1], QP[2], QP[3]};
-  u64 x1[4] = {1, 0, 0, 0}, x2[4] = {0, 0, 0, 0};
-  while (!u256_is_one(u) && !u256_is_one(v)) {
-    while (!(u[0] & 1)) {
-      u256_shr1(u, 0);
-      q_half(x1);
-    }
-    while (!(v[0] & 1)) {
-      u256_shr1(v, 0);
-      q_half(x2);
-    }
-    if (u256_geq(u, v)) {
-      u256_sub(u, v);
-      Fq r = q_sub(Fq{{x1[0], x1[1], x1[2], x1[3]}}, Fq{{x2[0], x2[1], x2[2], x2[3]}});
-      memcpy(x1, r.v, 32);
-    } else {
-      u256_sub(v, u);
-      Fq r = q_sub(Fq{{x2[0], x2[1], x2[2], x2[3]}}, Fq{{x1[0], x1[1], x1[2], x1[3]}});
-      memcpy(x2, r.v, 32);
-    }
-  }
-  const u64* x = u256_is_one(u) ? x1 : x2;
+  Fq x;
+  modinv::inverse(a.v, Q_MODULUS, x.v);
   Fq r3{{QR3[0], QR3[1], QR3[2], QR3[3]}};
-  return q_mul(Fq{{x[0], x[1], x[2], x[3]}}, r3);
+  return q_mul(x, r3);
 }
 
 
@@ -277,43 +227,12 @@ static inline V mont(const V& a, const V& b) {
   return r;
 }
 static inline V mul(const V& a, const V& b) { return mont(mont(a, b), V{{RR2[0], RR2[1], RR2[2], RR2[3]}}); }
-static inline void half(u64* x) {
-  u64 top = 0;
-  if (x[0] & 1) {
-    u128 c = 0;
-    for (int i = 0; i < 4; i++) {
-      c += (u128)x[i] + RP[i];
-      x[i] = (u64)c;
-      c >>= 64;
-    }
-    top = (u64)c;
-  }
-  u256_shr1(x, top);
-}
-// binary extended Euclid on the canonical value: a^-1 mod r (0 -> 0)
+// a^-1 mod r on the canonical value (0 -> 0)
+static const modinv::Modulus R_MODULUS = modinv::make_modulus(RP);
 static V inv(const V& a) {
-  if (is_zero(a)) return zero();
-  u64 u[4] = {a.v[0], a.v[1], a.v[2], a.v[3]};
-  u64 v[4] = {RP[0], RP[1], RP[2], RP[3]};
-  V x1 = small(1), x2 = zero();
-  while (!u256_is_one(u) && !u256_is_one(v)) {
-    while (!(u[0] & 1)) {
-      u256_shr1(u, 0);
-      half(x1.v);
-    }
-    while (!(v[0] & 1)) {
-      u256_shr1(v, 0);
-      half(x2.v);
-    }
-    if (u256_geq(u, v)) {
-      u256_sub(u, v);
-      x1 = sub(x1, x2);
-    } else {
-      u256_sub(v, u);
-      x2 = sub(x2, x1);
-    }
-  }
-  return u256_is_one(u) ? x1 : x2;
+  V x;
+  modinv::inverse(a.v, R_MODULUS, x.v);
+  return x;
 }
 static inline bool canonical(const u64* a) { return !geq_p(a); }
 }  // namespace fr
@@ -353,8 +272,166 @@ struct HScalar {  // AssignedValue<Fr>: canonical 256-bit
 static const u128 LIMB_MASK = (((u128)1) << 68) - 1;
 static const int OVERFLOW_LIMIT = 64, OVERFLOW_THRESHOLD = 32;
 
+
+// ---- op-record storage: fixed-size chunks, page-locked when a device context exists ------------------------------
+// Records are only ever appended and later streamed to the GPU, so they live in 2 MiB chunks carved from page-locked
+// slabs (cudaHostAlloc, portable) once some h2agg_ctx exists in the process -- the H2D copy of a 2^21-row witness is
+// ~110 MB and runs at PCIe speed from pinned memory, at a fraction of it from pageable memory.  Without a device
+// (recording only: the CPU tests) chunks are plain heap memory.  Chunks go back to a process-wide pool.
+static const uint32_t CHUNK_OPS = 8192;
+static const size_t SLAB_CHUNKS = 16;  // 32 MiB per cudaHostAlloc
+struct ChunkPool {
+  std::mutex mu;
+  std::vector<WitnessOp*> free_pinned, free_plain;
+  size_t pinned_bytes = 0;
+  size_t plain_keep = 2048;  // heap chunks kept for reuse (4 GiB): a fresh chunk costs ~0.5 ms of page faults
+  size_t pinned_cap = 1024ull << 20;
+  ChunkPool() {
+    if (const char* e = getenv("H2AGG_WIT_PINNED_MB")) pinned_cap = (size_t)atoll(e) << 20;
+  }
+  WitnessOp* get(bool* pinned) {
+    {
+      std::lock_guard<std::mutex> l(mu);
+      if (free_pinned.empty() && g_any_device.load() >= 0 && pinned_bytes + SLAB_CHUNKS * CHUNK_OPS * sizeof(WitnessOp) <= pinned_cap) {
+        void* slab = nullptr;
+        int prev = -1;
+        cudaGetDevice(&prev);
+        cudaSetDevice(g_any_device.load());
+        cudaError_t e = cudaHostAlloc(&slab, SLAB_CHUNKS * CHUNK_OPS * sizeof(WitnessOp), cudaHostAllocPortable);
+        if (prev >= 0) cudaSetDevice(prev);
+        if (e == cudaSuccess) {
+          pinned_bytes += SLAB_CHUNKS * CHUNK_OPS * sizeof(WitnessOp);
+          for (size_t i = 0; i < SLAB_CHUNKS; i++) free_pinned.push_back((WitnessOp*)slab + i * CHUNK_OPS);
+        } else {
+          cudaGetLastError();
+          pinned_cap = 0;  // do not try again
+        }
+      }
+      if (!free_pinned.empty()) {
+        WitnessOp* c = free_pinned.back();
+        free_pinned.pop_back();
+        *pinned = true;
+        return c;
+      }
+    }
+    *pinned = false;
+    {
+      std::lock_guard<std::mutex> l(mu);
+      if (!free_plain.empty()) {
+        WitnessOp* c = free_plain.back();
+        free_plain.pop_back();
+        return c;
+      }
+    }
+    void* m = nullptr;
+    if (posix_memalign(&m, 4096, CHUNK_OPS * sizeof(WitnessOp)) != 0) throw std::bad_alloc();
+    return (WitnessOp*)m;
+  }
+  void put(WitnessOp* c, bool pinned) {
+    std::lock_guard<std::mutex> l(mu);
+    if (pinned) free_pinned.push_back(c);
+    else if (free_plain.size() < plain_keep) free_plain.push_back(c);
+    else free(c);
+  }
+};
+static ChunkPool& chunk_pool() {
+  static ChunkPool* p = new ChunkPool();  // never destroyed: chunks may be returned during static teardown
+  return *p;
+}
+
+struct OpChunk {
+  WitnessOp* p = nullptr;
+  uint32_t n = 0;
+  bool pinned = false;
+};
+struct OpStore {
+  std::vector<OpChunk> chunks;
+  size_t total = 0;
+  OpStore() = default;
+  OpStore(const OpStore&) = delete;
+  OpStore& operator=(const OpStore&) = delete;
+  OpStore(OpStore&& o) noexcept : chunks(std::move(o.chunks)), total(o.total) { o.chunks.clear(); o.total = 0; }
+  ~OpStore() { clear(); }
+  void clear() {
+    for (auto& c : chunks) chunk_pool().put(c.p, c.pinned);
+    chunks.clear();
+    total = 0;
+  }
+  size_t size() const { return total; }
+  void push_back(const WitnessOp& op) {
+    if (chunks.empty() || chunks.back().n == CHUNK_OPS) {
+      OpChunk c;
+      c.p = chunk_pool().get(&c.pinned);
+      chunks.push_back(c);
+    }
+    OpChunk& c = chunks.back();
+    c.p[c.n++] = op;
+    total++;
+  }
+  void add_to_rows(uint32_t delta) {  // rows recorded relative to a tag become absolute (mod 2^32 arithmetic)
+    for (auto& c : chunks)
+      for (uint32_t i = 0; i < c.n; i++) c.p[i].row += delta;
+  }
+  void absorb(OpStore& o) {  // take over the chunks of a child store (no copies)
+    for (auto& c : o.chunks) chunks.push_back(c);
+    total += o.total;
+    o.chunks.clear();
+    o.total = 0;
+  }
+};
+
+// ---- a few host threads for the independent sections of a multi_exp ------------------------------------------------
+static std::atomic<unsigned> g_wit_threads{0};  // 0 = not decided yet
+static unsigned wit_threads() {
+  unsigned n = g_wit_threads.load();
+  if (n) return n;
+  unsigned t = std::thread::hardware_concurrency();
+  if (t == 0) t = 1;
+  if (t > 16) t = 16;
+  if (const char* e = getenv("H2AGG_WIT_THREADS")) {
+    int v = atoi(e);
+    if (v >= 1) t = (unsigned)v;
+  }
+  g_wit_threads.store(t);
+  return t;
+}
+template <class F>
+static void parallel_for(size_t n_tasks, F&& task) {
+  const unsigned nt = (unsigned)std::min<size_t>(wit_threads(), n_tasks);
+  if (nt <= 1) {
+    for (size_t i = 0; i < n_tasks; i++) task(i);
+    return;
+  }
+  std::atomic<size_t> next{0};
+  std::exception_ptr err;
+  std::mutex err_mu;
+  auto worker = [&] {
+    for (;;) {
+      const size_t i = next.fetch_add(1);
+      if (i >= n_tasks) return;
+      try {
+        task(i);
+      } catch (...) {
+        std::lock_guard<std::mutex> l(err_mu);
+        if (!err) err = std::current_exception();
+        next.store(n_tasks);
+        return;
+      }
+    }
+  };
+  std::vector<std::thread> th;
+  for (unsigned t = 1; t < nt; t++) th.emplace_back(worker);
+  worker();
+  for (auto& t : th) t.join();
+  if (err) std::rethrow_exception(err);
+}
+
+// Rows recorded by a child recorder (an independent section of a multi_exp, recorded on its own thread) are relative
+// to this tag until the section is stitched into the parent at its final row offset.
+static const uint32_t REL_TAG = 0x80000000u;
+
 struct Recorder {
-  std::vector<WitnessOp> ops;
+  OpStore ops;
   uint32_t offset = 0;
   // pending RAW128 record
   bool raw_open = false;
@@ -365,7 +442,6 @@ struct Recorder {
   std::vector<HScalar> scalars;
 
   Recorder() {
-    ops.reserve(1 << 20);  // 256 MiB of records up front: no reallocation copies while recording
     // limbs of p
     u64 c[4] = {QP[0], QP[1], QP[2], QP[3]};
     canon_to_limbs(c, p_limbs);
@@ -903,9 +979,22 @@ struct Recorder {
     return be;
   }
   HPoint pick_candidate(const std::vector<HPoint>& candidates, const std::vector<HCond>& bits_le) {
-    std::vector<HPoint> curr = candidates;  // clone
+    bool all_curv = candidates.size() == 16 && bits_le.size() == 4;
+    for (const HPoint& c : candidates) all_curv = all_curv && c.has_curv;
+    if (all_curv) {
+      // every candidate already carries its curvature (shamir's tables): bisec_point_with_curvature mutates nothing,
+      // so the reference's clone of the table is not needed -- halve in place over a small array
+      HPoint buf[8];
+      for (int k = 0; k < 8; k++)
+        buf[k] = bisec_point_with_curvature(bits_le[0], const_cast<HPoint&>(candidates[2 * k + 1]), const_cast<HPoint&>(candidates[2 * k]));
+      for (int level = 1, len = 4; level < 4; level++, len >>= 1)
+        for (int k = 0; k < len; k++) buf[k] = bisec_point_with_curvature(bits_le[level], buf[2 * k + 1], buf[2 * k]);
+      return buf[0];
+    }
+    std::vector<HPoint> curr = candidates;  // clone: curvature rows a candidate acquires here are dropped with it
     for (const HCond& bit : bits_le) {
       std::vector<HPoint> next;
+      next.reserve(curr.size() / 2);
       for (size_t k = 0; k + 1 < curr.size(); k += 2) next.push_back(bisec_point_with_curvature(bit, curr[k + 1], curr[k]));
       curr.swap(next);
     }
@@ -928,38 +1017,98 @@ struct Recorder {
     }
     return acc;
   }
-  HPoint ecc_shamir(std::vector<HPoint>& pts, const std::vector<HScalar>& scalars) {  // :139-244
+  // -- sections recorded on their own threads: a child starts at REL_TAG, the parent stitches it in at its offset
+  static void fix_cell(Cell& c, uint32_t delta) {
+    if (c.row & REL_TAG) c.row += delta;
+  }
+  static void fix_int(HInt& a, uint32_t delta) {
+    for (int i = 0; i < 4; i++) fix_cell(a.cell[i], delta);
+    fix_cell(a.native_cell, delta);
+  }
+  static void fix_point(HPoint& p, uint32_t delta) {
+    fix_int(p.x, delta);
+    fix_int(p.y, delta);
+    fix_cell(p.z.cell, delta);
+    fix_int(p.curv.v, delta);
+    fix_cell(p.curv.z.cell, delta);
+  }
+  void begin_child() {
+    offset = REL_TAG;
+  }
+  uint32_t child_rows() const { return offset - REL_TAG; }
+
+  // EccChipOps::shamir (:139-244).  The row layout is the reference's, row for row; the ORDER OF RECORDING is not: the
+  // candidate table of each point, and the inner sum of each window (which does not depend on the accumulator -- the
+  // reference itself relies on every inner round having the same size, :193-226), are independent of one another, so
+  // they are recorded concurrently into child recorders and stitched in at their row offsets.  Only the 63 x (4
+  // doublings + 1 addition) of the accumulator chain stay sequential.
+  HPoint ecc_shamir(std::vector<HPoint>& pts, const std::vector<HScalar>& scalars) {
     std::vector<std::vector<std::vector<HCond>>> windows;
     for (auto& s : scalars) windows.push_back(decompose_scalar(s, 4));
     HPoint identity = assign_identity();
-    std::vector<std::vector<HPoint>> pc;
-    for (auto& a : pts) {
-      std::vector<HPoint> cands;
-      cands.push_back(identity);
-      cands.push_back(a);
-      for (int i = 2; i < 16; i++) {
-        HPoint ai = ecc_add(cands[i - 1], a);
-        curvature(ai);
-        cands.push_back(ai);
+    flush_raw();
+    const size_t np = pts.size();
+    std::vector<std::vector<HPoint>> pc(np);
+    {
+      std::vector<Recorder> kids(np);
+      parallel_for(np, [&](size_t pi) {
+        Recorder& r = kids[pi];
+        r.begin_child();
+        std::vector<HPoint>& cands = pc[pi];
+        cands.reserve(16);
+        cands.push_back(identity);
+        cands.push_back(pts[pi]);
+        for (int i = 2; i < 16; i++) {
+          HPoint ai = r.ecc_add(cands[i - 1], pts[pi]);
+          r.curvature(ai);
+          cands.push_back(ai);
+        }
+        r.flush_raw();
+      });
+      std::vector<uint32_t> delta(np);
+      for (size_t pi = 0; pi < np; pi++) {
+        delta[pi] = offset - REL_TAG;
+        offset += kids[pi].child_rows();
       }
-      pc.push_back(cands);
+      parallel_for(np, [&](size_t pi) {
+        kids[pi].ops.add_to_rows(delta[pi]);
+        for (HPoint& c : pc[pi]) fix_point(c, delta[pi]);
+      });
+      for (size_t pi = 0; pi < np; pi++) ops.absorb(kids[pi].ops);
     }
+    const size_t nw = windows.empty() ? 0 : windows[0].size();
+    std::vector<Recorder> kids(nw);
+    std::vector<HPoint> inner(nw);
+    parallel_for(nw, [&](size_t wi) {
+      Recorder& r = kids[wi];
+      r.begin_child();
+      bool have_inner = false;
+      HPoint in;
+      for (size_t pi = 0; pi < np; pi++) {
+        HPoint ci = r.pick_candidate(pc[pi], windows[pi][wi]);
+        if (!have_inner) { in = ci; have_inner = true; }
+        else in = r.ecc_add(ci, in);
+      }
+      r.flush_raw();
+      inner[wi] = in;
+    });
+    std::vector<uint32_t> delta(nw);
     bool have_acc = false;
     HPoint acc;
-    for (size_t wi = 0; wi < windows[0].size(); wi++) {
-      bool have_inner = false;
-      HPoint inner;
-      for (size_t pi = 0; pi < pts.size(); pi++) {
-        HPoint ci = pick_candidate(pc[pi], windows[pi][wi]);
-        if (!have_inner) { inner = ci; have_inner = true; }
-        else inner = ecc_add(ci, inner);
-      }
-      if (!have_acc) { acc = inner; have_acc = true; }
+    for (size_t wi = 0; wi < nw; wi++) {
+      flush_raw();
+      delta[wi] = offset - REL_TAG;
+      offset += kids[wi].child_rows();
+      fix_point(inner[wi], delta[wi]);
+      if (!have_acc) { acc = inner[wi]; have_acc = true; }
       else {
         for (int k = 0; k < 4; k++) acc = ecc_double(acc);
-        acc = ecc_add(inner, acc);
+        acc = ecc_add(inner[wi], acc);
       }
     }
+    flush_raw();
+    parallel_for(nw, [&](size_t wi) { kids[wi].ops.add_to_rows(delta[wi]); });
+    for (size_t wi = 0; wi < nw; wi++) ops.absorb(kids[wi].ops);
     return acc;
   }
 
@@ -1144,6 +1293,11 @@ static Fq fq_from_mont_words(const uint64_t* w) { return Fq{{w[0], w[1], w[2], w
 extern "C" {
 
 h2agg_witness* h2agg_wit_new(void) { return new h2agg_witness(); }
+int h2agg_wit_set_threads(int n) {
+  const int prev = (int)wit_threads();
+  if (n >= 1) g_wit_threads.store((unsigned)(n > 256 ? 256 : n));
+  return prev;
+}
 void h2agg_wit_free(h2agg_witness* w) { delete w; }
 const char* h2agg_wit_error(h2agg_witness* w) { return w ? w->err.c_str() : ""; }
 uint64_t h2agg_wit_rows(h2agg_witness* w) { return w->rec.offset; }
@@ -1376,6 +1530,21 @@ int h2agg_wit_point_value(h2agg_witness* w, int64_t h, uint64_t out_xy[8], int* 
   return 0;
 }
 
+}  // extern "C"
+
+// record chunks -> one contiguous device array (the order of records is irrelevant: each names its own rows)
+static int upload_ops(h2agg_ctx* ctx, const OpStore& ops) {
+  size_t at = 0;
+  for (const OpChunk& c : ops.chunks) {
+    if (!c.n) continue;
+    H2AGG_CUDA(ctx, cudaMemcpyAsync((uint8_t*)ctx->io_a.p + at * sizeof(WitnessOp), c.p, (size_t)c.n * sizeof(WitnessOp), cudaMemcpyHostToDevice, ctx->stream));
+    at += c.n;
+  }
+  return 0;
+}
+
+extern "C" {
+
 // Run the expansion kernel over everything recorded so far: 5 advice columns of n_rows Fr each
 // (host pointers; rows beyond the recorded offset stay zero like unassigned halo2 cells).
 int h2agg_witness_expand(h2agg_ctx* ctx, h2agg_witness* w, uint64_t* const advice_cols[5], size_t n_rows) {
@@ -1392,7 +1561,8 @@ int h2agg_witness_expand(h2agg_ctx* ctx, h2agg_witness* w, uint64_t* const advic
   if (rc) return rc;
   rc = ensure(ctx, ctx->io_b, n_rows * 32 * 5);
   if (rc) return rc;
-  if (n_ops) H2AGG_CUDA(ctx, cudaMemcpyAsync(ctx->io_a.p, w->rec.ops.data(), n_ops * sizeof(WitnessOp), cudaMemcpyHostToDevice, ctx->stream));
+  rc = upload_ops(ctx, w->rec.ops);
+  if (rc) return rc;
   void* cols[5];
   for (int c = 0; c < 5; c++) cols[c] = (uint8_t*)ctx->io_b.p + (size_t)c * n_rows * 32;
   rc = witness_expand_dev(ctx, ctx->io_a.p, n_ops, cols, n_rows);
@@ -1415,7 +1585,8 @@ int h2agg_witness_expand_dev(h2agg_ctx* ctx, h2agg_witness* w, void* const d_col
   const size_t n_ops = w->rec.ops.size();
   int rc = ensure(ctx, ctx->io_a, n_ops * sizeof(WitnessOp) + 256);
   if (rc) return rc;
-  if (n_ops) H2AGG_CUDA(ctx, cudaMemcpyAsync(ctx->io_a.p, w->rec.ops.data(), n_ops * sizeof(WitnessOp), cudaMemcpyHostToDevice, ctx->stream));
+  rc = upload_ops(ctx, w->rec.ops);
+  if (rc) return rc;
   return witness_expand_dev(ctx, ctx->io_a.p, n_ops, d_cols, n_rows);
 }
 

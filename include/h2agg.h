@@ -302,6 +302,10 @@ int h2agg_poly_lincomb_dev(h2agg_ctx* ctx, const void* const* d_polys, const uin
  * Montgomery Fq pairs, (0,0) = identity; scalars are CANONICAL 256-bit integers < r. */
 typedef struct h2agg_witness h2agg_witness;
 h2agg_witness* h2agg_wit_new(void);
+/* Host threads a multi_exp records its independent sections on (candidate tables, inner window sums); default
+ * min(16, cores) or $H2AGG_WIT_THREADS.  n < 1 only queries.  Returns the previous value.  The recorded layout and
+ * values do not depend on it. */
+int h2agg_wit_set_threads(int n);
 void h2agg_wit_free(h2agg_witness* w);
 const char* h2agg_wit_error(h2agg_witness* w);
 uint64_t h2agg_wit_rows(h2agg_witness* w); /* current row offset = rows the layout occupies */

@@ -158,3 +158,31 @@ def test_full_aggregation_witness_all_five_advice_columns(ctx):
     a4 = np.ascontiguousarray(cols[4]).ravel()
     assert np.array_equal(ctx.msm_g1(a4, bases), ob.best_multiexp(a4, bases))
     w.close()
+
+
+def test_multi_exp_columns_do_not_depend_on_host_threads(ctx):
+    """Sections of a multi_exp recorded on 1 / 8 host threads (chunked, page-locked record store) expand to the same
+    five advice columns, bit for bit."""
+    import random
+
+    import bn254_ref as ref
+
+    lib = h2._lib.load()
+    rng = random.Random(23)
+    pts = [ws.xy_mont(ref.g1_mul(rng.randrange(1, ref.R), ref.G1_GEN)) for _ in range(6)]
+    scalars = [rng.randrange(ref.R) for _ in range(6)]
+    prev = lib.h2agg_wit_set_threads(0)
+    cols = []
+    try:
+        for threads in (1, 8):
+            lib.h2agg_wit_set_threads(threads)
+            chip = h2.B200EccChip()
+            hp = [chip.assign_var(p) for p in pts]
+            hs = [chip.assign_scalar(s) for s in scalars]
+            chip.multi_exp(hp, hs)
+            cols.append(chip.expand(ctx, n_rows=chip.rows() + 5))
+            chip.close()
+    finally:
+        lib.h2agg_wit_set_threads(prev)
+    assert cols[0].shape == cols[1].shape and np.array_equal(cols[0], cols[1])
+    assert cols[0][:, :-5].any()

@@ -127,3 +127,52 @@ def test_codec_square_root_exponent_constant():
     m = re.search(r"FQ_SQRT_EXP\[8\]\s*=\s*\{(.*?)\};", src, re.S)
     words = [int(x, 16) for x in re.findall(r"0x[0-9a-f]+", m.group(1))]
     assert sum(w << (32 * i) for i, w in enumerate(words)) == (E.P + 1) // 4 and E.P % 4 == 3
+
+
+def test_recorder_multi_exp_layout_does_not_depend_on_host_threads():
+    """The candidate tables and the inner window sums of a multi_exp are recorded on host threads and stitched in at
+    their row offsets: rows, record count, result and the cells of the final pair must not depend on the thread count."""
+    import ctypes
+
+    lib = h2._lib.load()
+    rng = random.Random(11)
+    pts = [ref.g1_mul(rng.randrange(1, ref.R), ref.G1_GEN) for _ in range(5)]
+    pts[3] = pts[1]                                     # P + P inside the inner sums
+    scalars = [rng.randrange(ref.R) for _ in range(5)]
+    scalars[2] = 0
+    seen = []
+    prev = lib.h2agg_wit_set_threads(0)
+    try:
+        for threads in (1, 3, 8):
+            lib.h2agg_wit_set_threads(threads)
+            chip = h2.B200EccChip()
+            hp = [chip.assign_var(ws.xy_mont(p)) for p in pts]
+            hs = [chip.assign_scalar(s) for s in scalars]
+            r = chip.multi_exp(hp, hs)
+            r2 = chip.multi_exp(hp[:2], hs[:2])
+            cells = [chip.scalar_chip.cell(h) for h in chip.expose_final_pair(r2, r)]
+            xy, ident = chip.to_value(r)
+            seen.append((chip.rows(), chip.ops(), xy.tobytes(), ident, tuple(cells)))
+            chip.close()
+    finally:
+        lib.h2agg_wit_set_threads(prev)
+    assert seen[0] == seen[1] == seen[2]
+    want = None
+    for p, s in zip(pts, scalars):
+        want = ref.g1_add(want, ref.g1_mul(s, p))
+    assert np.array_equal(np.frombuffer(seen[0][2], dtype=np.uint64), ws.xy_mont(want))
+
+
+def test_host_modular_inverse_through_div():
+    """ScalarChip::div goes through the safegcd inverse (csrc/host_modinv.hpp): a / b * b == a for edge values."""
+    from halo2_snark_aggregator_b200.witness import B200Context, B200ScalarChip
+
+    w = B200Context()
+    s = B200ScalarChip(w)
+    rng = random.Random(5)
+    vals = [1, 2, ref.R - 1, ref.R - 2, (1 << 253) + 5, 1 << 62, (1 << 62) - 1, (1 << 124) + 1] + [rng.randrange(1, ref.R) for _ in range(200)]
+    for b in vals:
+        a = rng.randrange(ref.R)
+        q = s.to_value(s.div(s.assign_var(a), s.assign_var(b)))
+        assert q == a * pow(b, -1, ref.R) % ref.R
+    w.close()
