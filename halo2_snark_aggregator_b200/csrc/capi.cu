@@ -98,6 +98,7 @@ void h2agg_destroy(h2agg_ctx* ctx) {
   }
   cudaFree(ctx->ntt_tmp.p);
   cudaFree(ctx->io_a.p);
+  cudaFree(ctx->wit_ws.p);
   cudaFree(ctx->io_b.p);
   cudaFree(ctx->msm_ws.p);
   for (int i = 0; i < N_LANES; i++) {

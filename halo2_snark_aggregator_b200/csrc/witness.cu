@@ -7,8 +7,11 @@
 // the advice cells, so the output is exactly the 5 advice columns (Montgomery Fr, the layout
 // halo2 holds in memory); fixed cells and copy constraints belong to keygen.
 //
-// One thread per op record (witness_ops.h); records are grouped by opcode on the host so a warp
-// runs one recipe.  The heavy recipe is MULEQ: 560-bit product, exact division by p through
+// One thread per op record (witness_ops.h); the recorder keeps one store per opcode, so the device array
+// is grouped by opcode and every recipe is its own kernel.  The three inversions of `is_zero` are not
+// done per thread (three 254-step Fermat ladders each): a first kernel writes the values to invert, the
+// batched inversion of scan.cu inverts all of them at once, a second kernel writes the rows.
+// The heavy recipe is MULEQ: 560-bit product, exact division by p through
 // p^-1 mod 2^288, 68-bit limbs, 17-bit range chunks, the limb-product chain, the carry words
 // v0/v1 (computed in Fr, as the reference does), natives -- 29-31 rows x 5 cells per record.
 #include "bn254_field.cuh"
@@ -134,9 +137,8 @@ __device__ __forceinline__ void put_assign_w(const Cols& o, uint32_t row, const 
 
 __device__ __forceinline__ void l68_from_u128(const uint64_t* l, L68& out) { out.lo = l[0]; out.hi = (uint32_t)l[1]; }
 
-// (is_zero condition, inverse) rows of BaseGateOps::invert                              gates/base_gate.rs:439-476
-__device__ __forceinline__ Fr put_invert(const Cols& o, uint32_t row, const Fr& a) {
-  Fr b = a.is_zero() ? Fr::zero() : fp_inv(a);
+// (is_zero condition, inverse) rows of BaseGateOps::invert, b = a^-1 (0 for a = 0)       gates/base_gate.rs:439-476
+__device__ __forceinline__ Fr put_invert(const Cols& o, uint32_t row, const Fr& a, const Fr& b) {
   Fr c = Fr::one() - a * b;
   Fr z = Fr::zero();
   put_row(o, row, a, c, z, z, z);
@@ -307,34 +309,52 @@ __device__ void expand_reduce(const WitnessOp& op, const Cols& o) {
   put_row(o, row++, df, rf[0], af[0], vf, zero);
 }
 
-__device__ void expand_iszero(const WitnessOp& op, const Cols& o) {
-  const bool ca = op.flags & 1;
-  const uint64_t* A = op.v;
-  uint32_t row = op.row;
-  const Fr zero = Fr::zero();
-  Fr af[4];
-  for (int i = 0; i < 4; i++) af[i] = limb128_to_fr(A + 2 * i);
-  // is_pure_zero                                                                          :53-66
-  Fr s = af[0] + af[1] + af[2] + af[3];
-  put_row(o, row++, s, af[0], af[1], af[2], af[3]);
-  Fr c1 = put_invert(o, row, s);
-  row += 2;
-  // is_pure_w_modulus                                                                     :68-102
-  Fr na = native_of(af);
-  if (!ca) put_row(o, row++, na, af[0], af[1], af[2], af[3]);
+// the three values is_zero inverts: the limb sum, native(a) - (p mod r), limb_0 - p_0       :53-102
+__device__ __forceinline__ void iszero_values(const WitnessOp& op, Fr* af, Fr& s, Fr& na, Fr& nd, Fr& ld) {
+  for (int i = 0; i < 4; i++) af[i] = limb128_to_fr(op.v + 2 * i);
+  s = af[0] + af[1] + af[2] + af[3];
+  na = native_of(af);
   Fr wn;
   for (int i = 0; i < 8; i++) wn.v[i] = W_NATIVE[i];
   wn = fp_to_mont(wn);
-  Fr nd = na - wn;
-  put_row(o, row++, nd, na, zero, zero, zero);
-  Fr c2 = put_invert(o, row, nd);
-  row += 2;
+  nd = na - wn;
   Fr p0 = Fr::zero();
   p0.v[0] = W_P_LIMB0[0]; p0.v[1] = W_P_LIMB0[1]; p0.v[2] = W_P_LIMB0[2];
   p0 = fp_to_mont(p0);
-  Fr ld = af[0] - p0;
+  ld = af[0] - p0;
+}
+
+__global__ void __launch_bounds__(128) witness_iszero_values_kernel(const WitnessOp* __restrict__ ops, uint32_t n_ops, Fr* __restrict__ vals) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_ops) return;
+  Fr af[4], s, na, nd, ld;
+  iszero_values(ops[i], af, s, na, nd, ld);
+  s.store(vals + 3 * (size_t)i);
+  nd.store(vals + 3 * (size_t)i + 1);
+  ld.store(vals + 3 * (size_t)i + 2);
+}
+
+// inv = the batch-inverted values of witness_iszero_values_kernel (zeros stay zero, as BaseGateOps::invert wants)
+__global__ void __launch_bounds__(128) witness_iszero_rows_kernel(const WitnessOp* __restrict__ ops, uint32_t n_ops, const Fr* __restrict__ inv, Cols o) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_ops) return;
+  const WitnessOp& op = ops[i];
+  const bool ca = op.flags & 1;
+  uint32_t row = op.row;
+  const Fr zero = Fr::zero();
+  Fr af[4], s, na, nd, ld;
+  iszero_values(op, af, s, na, nd, ld);
+  // is_pure_zero                                                                          :53-66
+  put_row(o, row++, s, af[0], af[1], af[2], af[3]);
+  Fr c1 = put_invert(o, row, s, Fr::load(inv + 3 * (size_t)i));
+  row += 2;
+  // is_pure_w_modulus                                                                     :68-102
+  if (!ca) put_row(o, row++, na, af[0], af[1], af[2], af[3]);
+  put_row(o, row++, nd, na, zero, zero, zero);
+  Fr c2 = put_invert(o, row, nd, Fr::load(inv + 3 * (size_t)i + 1));
+  row += 2;
   put_row(o, row++, ld, af[0], zero, zero, zero);
-  Fr c3 = put_invert(o, row, ld);
+  Fr c3 = put_invert(o, row, ld, Fr::load(inv + 3 * (size_t)i + 2));
   row += 2;
   Fr cand = c2 * c3;
   put_row(o, row++, c2, c3, cand, zero, zero);
@@ -342,57 +362,79 @@ __device__ void expand_iszero(const WitnessOp& op, const Cols& o) {
   put_row(o, row++, c1, cand, cor, zero, zero);
 }
 
+template <uint32_t OPC>
 __global__ void __launch_bounds__(128) witness_expand_kernel(const WitnessOp* __restrict__ ops, uint32_t n_ops, Cols o) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_ops) return;
   const WitnessOp& op = ops[i];
-  switch (op.opcode) {
-    case WOP_RAW128: {
-      for (uint32_t r = 0; r < op.aux; r++) {
-        const uint64_t* c = op.v + 10 * r;
-        put_row(o, op.row + r, fr_from_u128(c[0], c[1]), fr_from_u128(c[2], c[3]), fr_from_u128(c[4], c[5]),
-                fr_from_u128(c[6], c[7]), fr_from_u128(c[8], c[9]));
-      }
-      break;
+  if (OPC == WOP_RAW128) {
+    for (uint32_t r = 0; r < op.aux; r++) {
+      const uint64_t* c = op.v + 10 * r;
+      put_row(o, op.row + r, fr_from_u128(c[0], c[1]), fr_from_u128(c[2], c[3]), fr_from_u128(c[4], c[5]),
+              fr_from_u128(c[6], c[7]), fr_from_u128(c[8], c[9]));
     }
-    case WOP_RAW256: {
-      Fr cells[5];
-      for (int c = 0; c < 5; c++) {
-        Fr a;
-        for (int k = 0; k < 4; k++) { a.v[2 * k] = (uint32_t)op.v[4 * c + k]; a.v[2 * k + 1] = (uint32_t)(op.v[4 * c + k] >> 32); }
-        cells[c] = fp_to_mont(a);
-      }
-      put_row(o, op.row, cells[0], cells[1], cells[2], cells[3], cells[4]);
-      break;
+  } else if (OPC == WOP_RAW256) {
+    Fr cells[5];
+    for (int c = 0; c < 5; c++) {
+      Fr a;
+      for (int k = 0; k < 4; k++) { a.v[2 * k] = (uint32_t)op.v[4 * c + k]; a.v[2 * k + 1] = (uint32_t)(op.v[4 * c + k] >> 32); }
+      cells[c] = fp_to_mont(a);
     }
-    case WOP_NATIVE: {
-      Fr af[4];
-      for (int k = 0; k < 4; k++) af[k] = limb128_to_fr(op.v + 2 * k);
-      put_row(o, op.row, native_of(af), af[0], af[1], af[2], af[3]);
-      break;
-    }
-    case WOP_REDUCE: expand_reduce(op, o); break;
-    case WOP_ISZERO: expand_iszero(op, o); break;
-    case WOP_MULEQ: expand_muleq(op, o); break;
-    default: break;
+    put_row(o, op.row, cells[0], cells[1], cells[2], cells[3], cells[4]);
+  } else if (OPC == WOP_NATIVE) {
+    Fr af[4];
+    for (int k = 0; k < 4; k++) af[k] = limb128_to_fr(op.v + 2 * k);
+    put_row(o, op.row, native_of(af), af[0], af[1], af[2], af[3]);
+  } else if (OPC == WOP_REDUCE) {
+    expand_reduce(op, o);
+  } else if (OPC == WOP_MULEQ) {
+    expand_muleq(op, o);
   }
 }
 
-// d_ops: n_ops records on the device; d_cols: 5 device columns of n_rows Fr (zero-filled here:
-// halo2 leaves unassigned advice cells at zero)
-int witness_expand_dev(h2agg_ctx* ctx, const void* d_ops, size_t n_ops, void* const d_cols[5], size_t n_rows) {
+template <uint32_t OPC>
+static void launch_expand(h2agg_ctx* ctx, const WitnessOp* ops, size_t n, const Cols& o) {
+  if (!n) return;
+  witness_expand_kernel<OPC><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ops, (uint32_t)n, o);
+  ctx->launches++;
+}
+
+// d_ops: records on the device grouped by opcode (counts[opc] of each, in opcode order); d_cols: 5 device columns of
+// n_rows Fr (zero-filled here: halo2 leaves unassigned advice cells at zero)
+int witness_expand_dev(h2agg_ctx* ctx, const void* d_ops, const size_t* counts, void* const d_cols[5], size_t n_rows) {
   Cols o;
   for (int c = 0; c < 5; c++) {
     o.c[c] = (Fr*)d_cols[c];
     H2AGG_CUDA(ctx, cudaMemsetAsync(d_cols[c], 0, n_rows * 32, ctx->stream));
   }
   o.n_rows = (uint32_t)n_rows;
-  if (n_ops) {
-    ScopedKernelTimer tk(ctx, KC_WITNESS, ctx->stream);
-    witness_expand_kernel<<<(unsigned)((n_ops + 127) / 128), 128, 0, ctx->stream>>>((const WitnessOp*)d_ops, (uint32_t)n_ops, o);
-    ctx->launches++;
-    H2AGG_CUDA(ctx, cudaGetLastError());
+  const WitnessOp* seg[WOP_COUNT];
+  size_t at = 0;
+  for (uint32_t k = 0; k < WOP_COUNT; k++) {
+    seg[k] = (const WitnessOp*)d_ops + at;
+    at += counts[k];
   }
+  if (!at) return 0;
+  const size_t niz = counts[WOP_ISZERO];
+  if (niz) {
+    int rc = ensure(ctx, ctx->wit_ws, niz * 3 * sizeof(Fr));
+    if (rc) return rc;
+  }
+  ScopedKernelTimer tk(ctx, KC_WITNESS, ctx->stream);
+  launch_expand<WOP_MULEQ>(ctx, seg[WOP_MULEQ], counts[WOP_MULEQ], o);
+  launch_expand<WOP_REDUCE>(ctx, seg[WOP_REDUCE], counts[WOP_REDUCE], o);
+  launch_expand<WOP_RAW128>(ctx, seg[WOP_RAW128], counts[WOP_RAW128], o);
+  launch_expand<WOP_RAW256>(ctx, seg[WOP_RAW256], counts[WOP_RAW256], o);
+  launch_expand<WOP_NATIVE>(ctx, seg[WOP_NATIVE], counts[WOP_NATIVE], o);
+  if (niz) {
+    witness_iszero_values_kernel<<<(unsigned)((niz + 127) / 128), 128, 0, ctx->stream>>>(seg[WOP_ISZERO], (uint32_t)niz, (Fr*)ctx->wit_ws.p);
+    ctx->launches++;
+    int rc = batch_invert_dev(ctx, ctx->wit_ws.p, niz * 3);
+    if (rc) return rc;
+    witness_iszero_rows_kernel<<<(unsigned)((niz + 127) / 128), 128, 0, ctx->stream>>>(seg[WOP_ISZERO], (uint32_t)niz, (const Fr*)ctx->wit_ws.p, o);
+    ctx->launches++;
+  }
+  H2AGG_CUDA(ctx, cudaGetLastError());
   return 0;
 }
 

@@ -1,7 +1,8 @@
 // Op records exchanged between the host-side recorder (witness_recorder.cu) and the row-expansion
 // kernel (witness.cu).  One record = one fixed row recipe of halo2-ecc-circuit-lib
 // (SURVEY.md 8a rows W1-W5); `row` is the first advice row it owns, so records are independent
-// and the expansion is embarrassingly parallel.
+// and the expansion is embarrassingly parallel.  The recorder keeps one store per opcode, so the device array is
+// grouped by opcode and every recipe runs as its own kernel (its own register budget, no divergence).
 #pragma once
 #include <cstdint>
 
@@ -16,6 +17,7 @@ enum WitnessOpcode : uint32_t {
   WOP_MULEQ = 5,    // x = v[0..8), y = v[8..16), z = v[16..24): x*y = d*p + z         :104-320, 709-782
                     // flags: bit0/1/2 native cached for x/y/z, bit3 square (y is x),
                     //        bit4 the freshly assign_w'd integer is y (div) instead of z (mul)
+  WOP_COUNT = 6,
 };
 
 struct alignas(16) WitnessOp {

@@ -344,39 +344,48 @@ struct OpChunk {
   uint32_t n = 0;
   bool pinned = false;
 };
-struct OpStore {
-  std::vector<OpChunk> chunks;
-  size_t total = 0;
+struct OpStore {  // one chunk list per opcode: the device array comes out grouped by recipe
+  std::vector<OpChunk> chunks[WOP_COUNT];
+  size_t count[WOP_COUNT] = {0, 0, 0, 0, 0, 0};
   OpStore() = default;
   OpStore(const OpStore&) = delete;
   OpStore& operator=(const OpStore&) = delete;
-  OpStore(OpStore&& o) noexcept : chunks(std::move(o.chunks)), total(o.total) { o.chunks.clear(); o.total = 0; }
   ~OpStore() { clear(); }
   void clear() {
-    for (auto& c : chunks) chunk_pool().put(c.p, c.pinned);
-    chunks.clear();
-    total = 0;
+    for (uint32_t k = 0; k < WOP_COUNT; k++) {
+      for (auto& c : chunks[k]) chunk_pool().put(c.p, c.pinned);
+      chunks[k].clear();
+      count[k] = 0;
+    }
   }
-  size_t size() const { return total; }
+  size_t size() const {
+    size_t t = 0;
+    for (uint32_t k = 0; k < WOP_COUNT; k++) t += count[k];
+    return t;
+  }
   void push_back(const WitnessOp& op) {
-    if (chunks.empty() || chunks.back().n == CHUNK_OPS) {
+    std::vector<OpChunk>& ch = chunks[op.opcode];
+    if (ch.empty() || ch.back().n == CHUNK_OPS) {
       OpChunk c;
       c.p = chunk_pool().get(&c.pinned);
-      chunks.push_back(c);
+      ch.push_back(c);
     }
-    OpChunk& c = chunks.back();
+    OpChunk& c = ch.back();
     c.p[c.n++] = op;
-    total++;
+    count[op.opcode]++;
   }
   void add_to_rows(uint32_t delta) {  // rows recorded relative to a tag become absolute (mod 2^32 arithmetic)
-    for (auto& c : chunks)
-      for (uint32_t i = 0; i < c.n; i++) c.p[i].row += delta;
+    for (uint32_t k = 0; k < WOP_COUNT; k++)
+      for (auto& c : chunks[k])
+        for (uint32_t i = 0; i < c.n; i++) c.p[i].row += delta;
   }
   void absorb(OpStore& o) {  // take over the chunks of a child store (no copies)
-    for (auto& c : o.chunks) chunks.push_back(c);
-    total += o.total;
-    o.chunks.clear();
-    o.total = 0;
+    for (uint32_t k = 0; k < WOP_COUNT; k++) {
+      for (auto& c : o.chunks[k]) chunks[k].push_back(c);
+      count[k] += o.count[k];
+      o.chunks[k].clear();
+      o.count[k] = 0;
+    }
   }
 };
 
@@ -1535,11 +1544,12 @@ int h2agg_wit_point_value(h2agg_witness* w, int64_t h, uint64_t out_xy[8], int* 
 // record chunks -> one contiguous device array (the order of records is irrelevant: each names its own rows)
 static int upload_ops(h2agg_ctx* ctx, const OpStore& ops) {
   size_t at = 0;
-  for (const OpChunk& c : ops.chunks) {
-    if (!c.n) continue;
-    H2AGG_CUDA(ctx, cudaMemcpyAsync((uint8_t*)ctx->io_a.p + at * sizeof(WitnessOp), c.p, (size_t)c.n * sizeof(WitnessOp), cudaMemcpyHostToDevice, ctx->stream));
-    at += c.n;
-  }
+  for (uint32_t k = 0; k < WOP_COUNT; k++)
+    for (const OpChunk& c : ops.chunks[k]) {
+      if (!c.n) continue;
+      H2AGG_CUDA(ctx, cudaMemcpyAsync((uint8_t*)ctx->io_a.p + at * sizeof(WitnessOp), c.p, (size_t)c.n * sizeof(WitnessOp), cudaMemcpyHostToDevice, ctx->stream));
+      at += c.n;
+    }
   return 0;
 }
 
@@ -1565,7 +1575,7 @@ int h2agg_witness_expand(h2agg_ctx* ctx, h2agg_witness* w, uint64_t* const advic
   if (rc) return rc;
   void* cols[5];
   for (int c = 0; c < 5; c++) cols[c] = (uint8_t*)ctx->io_b.p + (size_t)c * n_rows * 32;
-  rc = witness_expand_dev(ctx, ctx->io_a.p, n_ops, cols, n_rows);
+  rc = witness_expand_dev(ctx, ctx->io_a.p, w->rec.ops.count, cols, n_rows);
   if (rc) return rc;
   for (int c = 0; c < 5; c++) H2AGG_CUDA(ctx, cudaMemcpyAsync(advice_cols[c], cols[c], n_rows * 32, cudaMemcpyDeviceToHost, ctx->stream));
   H2AGG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1587,7 +1597,7 @@ int h2agg_witness_expand_dev(h2agg_ctx* ctx, h2agg_witness* w, void* const d_col
   if (rc) return rc;
   rc = upload_ops(ctx, w->rec.ops);
   if (rc) return rc;
-  return witness_expand_dev(ctx, ctx->io_a.p, n_ops, d_cols, n_rows);
+  return witness_expand_dev(ctx, ctx->io_a.p, w->rec.ops.count, d_cols, n_rows);
 }
 
 }  // extern "C"

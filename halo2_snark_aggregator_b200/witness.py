@@ -32,6 +32,16 @@ def _limbs(v):
     return np.array([(v >> (64 * i)) & _M64 for i in range(4)], dtype=np.uint64)
 
 
+_U64x4 = ctypes.c_uint64 * 4
+
+
+def _c4(v):
+    """canonical scalar -> 4 x u64 for a C-ABI argument (plain ctypes: the ScalarChip calls are tiny, numpy
+    array construction would dominate them)"""
+    v %= R_MOD
+    return _U64x4(v & _M64, (v >> 64) & _M64, (v >> 128) & _M64, v >> 192)
+
+
 class B200Context:
     """`Context` of the circuit chips (halo2-ecc-circuit-lib/src/gates/base_gate.rs:113-140): the row offset plus, here,
     the op records the expansion kernel consumes."""
@@ -104,10 +114,10 @@ class B200ScalarChip:
         return self.assign_const(1)
 
     def assign_const(self, c):
-        return self.w._h(self.lib.h2agg_wit_field_assign_const(self.w.h, _p(_limbs(c))))
+        return self.w._h(self.lib.h2agg_wit_field_assign_const(self.w.h, _c4(c)))
 
     def assign_var(self, v):
-        return self.w._h(self.lib.h2agg_wit_assign_scalar(self.w.h, _p(_limbs(v))))
+        return self.w._h(self.lib.h2agg_wit_assign_scalar(self.w.h, _c4(v)))
 
     def to_value(self, h):
         out = np.zeros(4, dtype=np.uint64)
@@ -138,11 +148,15 @@ class B200ScalarChip:
     def sum_with_coeff_and_constant(self, a_with_coeff, b):
         n = len(a_with_coeff)
         hs = (ctypes.c_int64 * max(n, 1))(*[h for h, _ in a_with_coeff])
-        co = np.concatenate([_limbs(c) for _, c in a_with_coeff]) if n else np.zeros(4, dtype=np.uint64)
-        return self.w._h(self.lib.h2agg_wit_field_sum_with_coeff_and_constant(self.w.h, hs, _p(co), n, _p(_limbs(b))))
+        words = []
+        for _, c in a_with_coeff:
+            c %= R_MOD
+            words += [c & _M64, (c >> 64) & _M64, (c >> 128) & _M64, c >> 192]
+        co = (ctypes.c_uint64 * max(4 * n, 4))(*words)
+        return self.w._h(self.lib.h2agg_wit_field_sum_with_coeff_and_constant(self.w.h, hs, co, n, _c4(b)))
 
     def mul_add_constant(self, a, b, c):
-        return self.w._h(self.lib.h2agg_wit_field_mul_add_constant(self.w.h, a, b, _p(_limbs(c))))
+        return self.w._h(self.lib.h2agg_wit_field_mul_add_constant(self.w.h, a, b, _c4(c)))
 
     # -- ArithFieldChip: provided methods (api/src/arith/field.rs:37-104)
     def sum_with_constant(self, a, b):
