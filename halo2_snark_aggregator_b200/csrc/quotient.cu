@@ -119,9 +119,6 @@ __global__ void __launch_bounds__(256) quot_evaluate_h(const __grid_constant__ Q
   const uint32_t n_gates = plan[1], n_pcols = plan[2], chunk_len = plan[3];
   const int last_rot = (int)plan[4];
   const uint32_t n_lookups = plan[5];
-  const Fr l0 = q_load(a, plan[6], 0, idx, mask);
-  const Fr l_last = q_load(a, plan[7], 0, idx, mask);
-  const Fr l_active = q_load(a, plan[8], 0, idx, mask);
   const Fr one = Fr::one();
   uint32_t pc = QPLAN_HEADER;
   // halo2 folds h = h * y + term over the ordered term list, i.e. h = sum_j term_j * y^(N-1-j).  Most terms carry one
@@ -197,7 +194,10 @@ __global__ void __launch_bounds__(256) quot_evaluate_h(const __grid_constant__ Q
     fold_l0(a_minus_s);
     fold_active(a_minus_s * (ain - ain_prev));
   }
-  Fr value = acc_plain + fp_mul_add2(acc_l0, l0, acc_last, l_last) + acc_active * l_active;
+  // the three selector columns are only needed now: loading them up front kept 24 registers live through every loop
+  // (the kernel sits at the 128-register budget of two CTAs per SM and spilled inside the lookup loop)
+  Fr value = acc_plain + fp_mul_add2(acc_l0, q_load(a, plan[6], 0, idx, mask), acc_last, q_load(a, plan[7], 0, idx, mask));
+  value = value + acc_active * q_load(a, plan[8], 0, idx, mask);
 
   if (a.t_evals) value = value * Fr::load_nc(a.t_evals + (idx & a.t_mask));
   value.store(a.out + local);
