@@ -347,14 +347,61 @@ def main():
             phases.append([i for i in ids if units[i][1] == "msm" and i >= 64])
         else:
             phases.append(ids)
-    # measured single-GPU costs (ms) drive the balance
-    COST = {("msm", 0): 12.5, ("msm", 1): 2.6, ("msm", 2): 6.0, ("msm", 3): 2.6, ("intt", 0): 1.1, ("coset", 0): 4.0, ("ext_intt", 0): 4.4}
+    # Costs (ms) that drive the balance.  Defaults are single-B200 measurements at k = 22; with more than one rank the
+    # units are timed once at start-up on rank 0 (each kind alone, CUDA events) and broadcast, so every rank plans from
+    # the same MEASURED numbers at whatever k is being run.  An MSM's cost is split into the part every window shard
+    # pays again (digit passes over all scalars, scans, the bucket tree: total - accumulate) and the divisible rest.
+    COST = {("msm", 0): 10.5, ("msm", 1): 2.1, ("msm", 2): 6.1, ("msm", 3): 2.1, ("intt", 0): 0.9, ("coset", 0): 3.4, ("ext_intt", 0): 3.8}
+    FIXED = {0: 2.45, 1: 1.5, 2: 3.25, 3: 1.4}
+    cost_source = "defaults (single-B200 measurements at k = 22)"
+    if world > 1:
+        t_cost = torch.zeros(11, dtype=torch.float64, device=dev)
+        if rank == 0:
+            t_probe = dbuf(n * 32)
+            t_o = dbuf(160)
+            t_e = dbuf(ext_n * 32)
+            vals = []
+            for kind in (0, 1, 2, 3):
+                ctx.synth_scalars_dev(SEED_SCALARS + 4242 + kind, kind, 0, n, t_probe.data_ptr())
+                if kind != 0 and n > BLIND_ROWS:
+                    ctx.synth_scalars_dev(SEED_SCALARS + 4300 + kind, 0, 0, BLIND_ROWS, t_probe.data_ptr() + 32 * (n - BLIND_ROWS))
+                ctx.msm_g1_dev(t_probe.data_ptr(), n, t_o.data_ptr(), srs_id=srs)
+                ctx.synchronize()
+                ctx.kernel_timing(True)
+                for _ in range(2):
+                    ctx.msm_g1_dev(t_probe.data_ptr(), n, t_o.data_ptr(), srs_id=srs)
+                kt = ctx.kernel_times()
+                ctx.kernel_timing(False)
+                tot_ms = kt["msm_total"][0] / max(kt["msm_total"][1], 1)
+                acc_ms = kt["msm_accumulate"][0] / max(kt["msm_accumulate"][1], 1)
+                vals += [tot_ms, max(tot_ms - acc_ms, 0.0)]
+            ctx.synth_scalars_dev(SEED_SCALARS + 4400, 0, 0, n, t_probe.data_ptr())
+            for fn in (lambda: dom.lagrange_to_coeff_dev(t_probe.data_ptr()),
+                       lambda: dom.coeff_to_extended_dev(t_probe.data_ptr(), t_e.data_ptr()),
+                       lambda: dom.extended_to_coeff_dev(t_e.data_ptr())):
+                fn()
+                ctx.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(3):
+                    fn()
+                ctx.synchronize()
+                vals.append((time.perf_counter() - t0) / 3 * 1e3)
+            t_cost.copy_(torch.tensor(vals, dtype=torch.float64))
+            del t_probe, t_o, t_e
+        dist.broadcast(t_cost, 0)
+        cv = [float(x) for x in t_cost.cpu().tolist()]
+        for kind in (0, 1, 2, 3):
+            COST[("msm", kind)] = cv[2 * kind]
+            FIXED[kind] = cv[2 * kind + 1]
+        COST[("intt", 0)], COST[("coset", 0)], COST[("ext_intt", 0)] = cv[8], cv[9], cv[10]
+        cost_source = "measured on rank 0 at start-up, broadcast"
     plan = []  # per phase: [(unit, rank, windows)]
     for ids in phases:
         mc = {i: COST[(units[i][1], units[i][2])] for i in ids if units[i][1] == "msm"}
+        mf = {i: FIXED[units[i][2]] for i in ids if units[i][1] == "msm"}
         oc = {i: COST[(units[i][1], units[i][2])] for i in ids if units[i][1] != "msm"}
         if mode == "auto":
-            plan.append(par.plan_phase(mc, oc, world, nwin))
+            plan.append(par.plan_phase(mc, oc, world, nwin, mf))
         elif mode == "windows":
             shards = par.window_shards(nwin, world)
             plan.append([(i, rk, shards[rk]) for i in mc for rk in range(world) if shards[rk][1] > shards[rk][0]] +
@@ -385,26 +432,28 @@ def main():
     t_gather = torch.zeros(world * slots_max * 160, dtype=torch.uint8, device=dev)
     t_final = torch.zeros(len(units) * 160, dtype=torch.uint8, device=dev)   # every commitment, on every rank
     t_stage = torch.zeros(slots_max * 160, dtype=torch.uint8, device=dev)
+    # everything this rank owes to a phase -- whole columns and window shards of others -- goes out in ONE batched call
+    # (per-column window ranges), so a shard's latency-bound prologue / epilogue overlaps the other columns' accumulation
     my_calls = []
     for p_i, ph in enumerate(plan):
-        by_win = {}
-        for (u, rk, w) in ph:
-            if rk == rank and units[u][1] == "msm":
-                by_win.setdefault(w, []).append(u)
+        mine = sorted((u, w) for (u, rk, w) in ph if rk == rank and units[u][1] == "msm")
         calls = []
-        for w, us in sorted(by_win.items(), key=lambda kv: (kv[0] is not None, kv[0] or (0, 0))):
-            us = sorted(us)
+        if mine:
+            us = [u for u, _ in mine]
+            ws = [w for _, w in mine]
             idx = torch.tensor([phase_msms[p_i].index(u) for u in us], dtype=torch.long, device=dev)
-            calls.append((w, us, idx))
+            calls.append((ws if any(w is not None for w in ws) else None, us, idx))
         my_calls.append(calls)
     ctx.synchronize()
 
     s_ntt = torch.cuda.Stream(device=dev)  # the phase's NTTs run beside its MSM batch (independent columns)
     ev_fork, ev_join = torch.cuda.Event(), torch.cuda.Event()
 
-    def step_device():
+    def step_device(marks=None):
         c = 0
         for p_i, ph in enumerate(plan):
+            if marks is not None:
+                marks[p_i].record(stream)
             nm = len(phase_msms[p_i])
             ntt_here = [(u, rk, w) for (u, rk, w) in ph if rk == rank and units[u][1] != "msm"]
             if ntt_here:
@@ -436,6 +485,8 @@ def main():
                         t_final[j * 160:(j + 1) * 160] = t_stage[q * 160:(q + 1) * 160]
             if ntt_here and args.overlap_ntt:
                 stream.wait_event(ev_join)
+            if marks is not None:
+                marks[len(plan) + 1 + p_i].record(stream)   # this rank's own work of the phase is done
             if nm and world > 1:
                 # every rank needs every commitment of the phase to drive the transcript: ONE all-gather of
                 # <= 14 x 160 B, then a local add over ranks (whole results and window-shard partials alike;
@@ -448,6 +499,8 @@ def main():
                 else:
                     for q, j in enumerate(phase_msms[p_i]):
                         t_final[j * 160:(j + 1) * 160] = t_stage[q * 160:(q + 1) * 160]
+        if marks is not None:
+            marks[len(plan)].record(stream)
 
     def barrier():
         torch.cuda.synchronize()
@@ -481,6 +534,30 @@ def main():
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms = float(t_ms.item())
+
+    # ---- per-phase timings (one extra, untimed-for-`value` step): for every phase the time each rank is busy with its
+    # own units and the span of the phase including the wait for the slowest rank + the all-gather
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(2 * len(plan) + 1)]
+    step_device(marks)
+    barrier()
+    t_ph = torch.tensor([[marks[i].elapsed_time(marks[len(plan) + 1 + i]), marks[i].elapsed_time(marks[i + 1])] for i in range(len(plan))],
+                        dtype=torch.float64, device=dev)
+    if world > 1:
+        t_all = torch.empty((world,) + tuple(t_ph.shape), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(t_all, t_ph)
+    else:
+        t_all = t_ph.unsqueeze(0)
+    ph_all = t_all.cpu().tolist()
+    phase_report = []
+    for i, ids in enumerate(phases):
+        kinds = {}
+        for u in ids:
+            key = units[u][1] + (str(units[u][2]) if units[u][1] == "msm" else "")
+            kinds[key] = kinds.get(key, 0) + 1
+        busy = [ph_all[r][i][0] for r in range(world)]
+        phase_report.append({"units": kinds, "busy_ms_by_rank": [round(x, 3) for x in busy], "busy_ms_max": max(busy),
+                             "busy_ms_mean": sum(busy) / world, "span_ms_rank0": ph_all[0][i][1],
+                             "sharded": sorted(set(u for (u, rk, w) in plan[i] if w is not None))})
 
     def pinned(nbytes):
         return torch.empty(nbytes // 8, dtype=torch.int64).pin_memory().numpy().view(np.uint64)
@@ -991,7 +1068,10 @@ def main():
             "config": workload_config(k),
             "impl_config": {"parallelism": ("%s over %d GPU(s), one all-gather of commitments per commit phase" % ({"windows": "window-sharded MSM + column-parallel NTT", "columns": "column-parallel (round-robin)", "auto": "cost-balanced column-parallel, leftover MSMs window-sharded"}[mode], world)),
                             "msm_mode": "fixed-base table (2^(c w) P rows resident in HBM)" if table_mode else "plain",
-                            "msm_window_bits": cbits, "msm_windows": nwin},
+                            "msm_window_bits": cbits, "msm_windows": nwin,
+                            "plan_costs_ms": {"%s%s" % (kk[0], kk[1] if kk[0] == "msm" else ""): round(v, 3) for kk, v in COST.items()},
+                            "plan_msm_fixed_ms": {str(kk): round(v, 3) for kk, v in FIXED.items()}, "plan_cost_source": cost_source},
+            "phases": phase_report,
             "e2e": e2e_res if e2e_res is not None else e2e, "e2e_host_pointer_abi": e2e if e2e_res is not None else None,
             "gpu_launches": int(launches), "clocks": clock_info,
             "roofline": (lambda t_ms: {

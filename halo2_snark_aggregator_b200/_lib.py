@@ -75,6 +75,7 @@ def load():
         "h2agg_msm_g1_batch": (ci, [c_vp, u64, ctypes.POINTER(c_vp), sz, sz, c_vp]),
         "h2agg_msm_g1_batch_dev": (ci, [c_vp, u64, c_vp, ctypes.POINTER(c_vp), sz, sz, c_vp]),
         "h2agg_msm_g1_batch_windows_dev": (ci, [c_vp, u64, c_vp, ctypes.POINTER(c_vp), sz, sz, ci, ci, c_vp]),
+        "h2agg_msm_g1_batch_ranges_dev": (ci, [c_vp, u64, c_vp, ctypes.POINTER(c_vp), sz, sz, ctypes.POINTER(ci), ctypes.POINTER(ci), c_vp]),
         "h2agg_g1_sum_dev": (ci, [c_vp, c_vp, sz, sz, sz, c_vp]),
         "h2agg_msm_g1_dev": (ci, [c_vp, u64, c_vp, c_vp, sz, c_vp]),
         "h2agg_msm_g1_windows": (ci, [c_vp, u64, c_vp, c_vp, sz, ci, ci, c_vp]),

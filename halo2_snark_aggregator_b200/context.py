@@ -152,9 +152,15 @@ class Context:
         return out.reshape(len(cols), 8)
 
     def msm_g1_batch_dev(self, d_cols, n, d_out160s, d_bases=0, srs_id=0, windows=None):
+        """windows: None (all), one (begin, end) for the batch, or a list with one (begin, end) / None per column."""
         arr = (c_vp * len(d_cols))(*d_cols)
         if windows is None:
             self.check(self.lib.h2agg_msm_g1_batch_dev(self.h, srs_id, c_vp(d_bases), arr, len(d_cols), n, c_vp(d_out160s)))
+        elif isinstance(windows, list):
+            assert len(windows) == len(d_cols)
+            lo = (ctypes.c_int * len(d_cols))(*[0 if w is None else w[0] for w in windows])
+            hi = (ctypes.c_int * len(d_cols))(*[-1 if w is None else w[1] for w in windows])
+            self.check(self.lib.h2agg_msm_g1_batch_ranges_dev(self.h, srs_id, c_vp(d_bases), arr, len(d_cols), n, lo, hi, c_vp(d_out160s)))
         else:
             self.check(self.lib.h2agg_msm_g1_batch_windows_dev(self.h, srs_id, c_vp(d_bases), arr, len(d_cols), n, windows[0], windows[1], c_vp(d_out160s)))
 

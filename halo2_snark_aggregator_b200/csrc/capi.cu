@@ -422,6 +422,18 @@ int h2agg_msm_g1_batch_windows_dev(h2agg_ctx* ctx, uint64_t srs_id, const void* 
   return msm_run_batch(ctx, d_bases, d_cols, n_cols, n, (uint8_t*)d_out160s, false, win_begin, win_end);
 }
 
+int h2agg_msm_g1_batch_ranges_dev(h2agg_ctx* ctx, uint64_t srs_id, const void* d_bases_in, const void* const* d_cols,
+                                  size_t n_cols, size_t n, const int* win_begins, const int* win_ends, void* d_out160s) {
+  if (!ctx) return 1;
+  LOCK(ctx);
+  CHECK_ARG(ctx, d_cols && d_out160s && win_begins && win_ends, "msm_batch_ranges_dev: null argument");
+  H2AGG_CUDA(ctx, cudaSetDevice(ctx->device));
+  MsmBases d_bases;
+  int rc = resolve_bases(ctx, srs_id, nullptr, d_bases_in, n, &d_bases);
+  if (rc) return rc;
+  return msm_run_batch(ctx, d_bases, d_cols, n_cols, n, (uint8_t*)d_out160s, false, 0, -1, win_begins, win_ends);
+}
+
 int h2agg_g1_sum_dev(h2agg_ctx* ctx, const void* d_points, size_t m, size_t stride_bytes, size_t n_out, void* d_out160s) {
   if (!ctx) return 1;
   LOCK(ctx);

@@ -229,8 +229,10 @@ int witness_expand_dev(h2agg_ctx* ctx, const void* d_ops, const size_t* counts, 
 int batch_invert_dev(h2agg_ctx* ctx, void* d_a, size_t n);
 // n_cols MSMs against the same bases, alternating lanes; joins back into ctx->stream.
 // Columns are device pointers, or host pointers when `host_cols` (then staged through the lanes).
+// `win_begins` / `win_ends` (optional, n_cols entries): a window range per column instead of one for the batch.
 int msm_run_batch(h2agg_ctx* ctx, const MsmBases& bases, const void* const* cols, size_t n_cols, size_t n,
-                  uint8_t* d_out160s, bool host_cols, int win_begin = 0, int win_end = -1);
+                  uint8_t* d_out160s, bool host_cols, int win_begin = 0, int win_end = -1, const int* win_begins = nullptr,
+                  const int* win_ends = nullptr);
 int lanes_init(h2agg_ctx* ctx);
 // sum of m affine-or-jacobian(96 B) points -> d_out160
 int g1_sum_jacobian(h2agg_ctx* ctx, const void* d_points96, size_t m, void* d_out160, size_t stride = 96, size_t n_out = 1);

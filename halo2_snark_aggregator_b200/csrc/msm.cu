@@ -750,11 +750,12 @@ int lanes_init(h2agg_ctx* ctx) {
 }
 
 int msm_run_batch(h2agg_ctx* ctx, const MsmBases& bases, const void* const* cols, size_t n_cols, size_t n,
-                  uint8_t* d_out160s, bool host_cols, int win_begin, int win_end) {
+                  uint8_t* d_out160s, bool host_cols, int win_begin, int win_end, const int* win_begins, const int* win_ends) {
   if (n_cols == 0) return 0;
   int rc;
   if (n_cols == 1 && !host_cols)
-    return msm_run(ctx, ctx->stream, ctx->msm_ws, bases, cols[0], n, d_out160s, win_begin, win_end, true);
+    return msm_run(ctx, ctx->stream, ctx->msm_ws, bases, cols[0], n, d_out160s, win_begins ? win_begins[0] : win_begin,
+                   win_ends ? win_ends[0] : win_end, true);
   if ((rc = lanes_init(ctx))) return rc;
   LaneFork lf(ctx);
   if ((rc = lf.fork())) return rc;
@@ -766,7 +767,9 @@ int msm_run_batch(h2agg_ctx* ctx, const MsmBases& bases, const void* const* cols
       if (n) H2AGG_CUDA(ctx, cudaMemcpyAsync(ln.io.p, cols[i], n * 32, cudaMemcpyHostToDevice, ln.st));
       d_col = ln.io.p;
     }
-    if ((rc = msm_run(ctx, ln.st, ln.ws, bases, d_col, n, d_out160s + i * 160, win_begin, win_end, false))) return rc;
+    if ((rc = msm_run(ctx, ln.st, ln.ws, bases, d_col, n, d_out160s + i * 160, win_begins ? win_begins[i] : win_begin,
+                      win_ends ? win_ends[i] : win_end, false)))
+      return rc;
   }
   if ((rc = lf.join())) return rc;
   return g1_normalize(ctx, ctx->stream, d_out160s, n_cols);   // ONE inversion for the whole round

@@ -44,42 +44,89 @@ def gather_round(dist, torch, local, slots, world, device):
     return out
 
 
-def plan_phase(msm_costs, other_costs, world, n_windows):
+def plan_phase(msm_costs, other_costs, world, n_windows, msm_fixed=None):
     """Balance one phase of a commit round over `world` ranks (hybrid of 8e-1 and 8e-2).
 
-    msm_costs / other_costs: {unit -> estimated cost}.  Whole MSMs are dealt longest-first to the least
-    loaded rank while at least `world` of them remain; the remainder (fewer MSMs than ranks) is
-    window-sharded, each over a contiguous group of world // remainder ranks, so no rank idles while
-    a neighbour runs a whole 2^k-point MSM.  NTT-like units then fill the least loaded ranks.
+    msm_costs / other_costs: {unit -> estimated cost}; msm_fixed: {unit -> the part of an MSM's cost every window shard
+    pays again} (digit passes over all scalars, scans, the bucket tree; default 0).  Whole MSMs are dealt longest-first
+    to the least loaded rank while at least `world` of them remain.  The remainder (fewer MSMs than ranks) is
+    window-sharded: every MSM gets world // remainder ranks, spare ranks go one at a time to the MSM whose shards are
+    the most expensive, and within that allowance the number of shards is the one that minimises the phase's makespan
+    given what the ranks already carry (a shard costs fixed + variable * its windows / n_windows, so more shards are
+    not always better).  NTT-like units fill the least loaded ranks, before or after the shards -- whichever order
+    ends sooner (a phase of 29 transforms and one MSM wants the MSM on the ranks that got fewer transforms).
     Returns [(unit, rank, None | (win_begin, win_end))]."""
-    load = [0.0] * world
-    plan = []
+    fixed = dict(msm_fixed or {})
     msms = sorted(msm_costs, key=lambda u: (-msm_costs[u], u))
     n_whole = (len(msms) // world) * world
-    for u in msms[:n_whole]:
-        r = min(range(world), key=lambda k: (load[k], k))
-        plan.append((u, r, None))
-        load[r] += msm_costs[u]
-    rest = msms[n_whole:]
+    whole, rest = msms[:n_whole], msms[n_whole:]
+
+    def shard_cost(u, windows):
+        f = min(fixed.get(u, 0.0), msm_costs[u])
+        return f + (msm_costs[u] - f) * windows / n_windows
+
+    # ranks each leftover MSM may use
+    allow = {}
     if rest:
-        g = max(1, world // len(rest))
-        order = sorted(range(world), key=lambda k: (load[k], k))
-        for j, u in enumerate(rest):
-            ranks = order[j * g:(j + 1) * g] if g > 1 else [order[j % world]]
-            if len(ranks) == 1:
-                plan.append((u, ranks[0], None))
-                load[ranks[0]] += msm_costs[u]
-                continue
-            shards = window_shards(n_windows, len(ranks))
-            for r, (lo, hi) in zip(ranks, shards):
-                if hi > lo:
-                    plan.append((u, r, (lo, hi)))
-                    load[r] += msm_costs[u] * (hi - lo) / n_windows
-    for u in sorted(other_costs, key=lambda x: (-other_costs[x], x)):
-        r = min(range(world), key=lambda k: (load[k], k))
-        plan.append((u, r, None))
-        load[r] += other_costs[u]
-    return plan
+        g0 = max(1, world // len(rest))
+        allow = {u: min(g0, n_windows) for u in rest}
+        spare = world - g0 * len(rest) if world >= len(rest) else 0
+        for _ in range(max(0, spare)):
+            cand = [u for u in rest if allow[u] < n_windows]
+            if not cand:
+                break
+            u = max(cand, key=lambda x: (shard_cost(x, -(-n_windows // allow[x])), -x if isinstance(x, int) else 0))
+            allow[u] += 1
+
+    def build(others_first):
+        load = [0.0] * world
+        plan = []
+        for u in whole:
+            r = min(range(world), key=lambda k: (load[k], k))
+            plan.append((u, r, None))
+            load[r] += msm_costs[u]
+
+        def place_others():
+            for u in sorted(other_costs, key=lambda x: (-other_costs[x], x)):
+                r = min(range(world), key=lambda k: (load[k], k))
+                plan.append((u, r, None))
+                load[r] += other_costs[u]
+
+        def place_rest():
+            for u in rest:
+                best = None
+                for g in range(1, allow[u] + 1):
+                    ranks = sorted(range(world), key=lambda k: (load[k], k))[:g]
+                    shards = window_shards(n_windows, g)
+                    trial = list(load)
+                    for r, (lo, hi) in zip(ranks, shards):
+                        trial[r] += shard_cost(u, hi - lo) if g > 1 else msm_costs[u]
+                    mk = max(trial)
+                    if best is None or mk < best[0] - 1e-9:
+                        best = (mk, g, ranks, shards)
+                _, g, ranks, shards = best
+                if g == 1:
+                    plan.append((u, ranks[0], None))
+                    load[ranks[0]] += msm_costs[u]
+                else:
+                    for r, (lo, hi) in zip(ranks, shards):
+                        if hi > lo:
+                            plan.append((u, r, (lo, hi)))
+                            load[r] += shard_cost(u, hi - lo)
+
+        if others_first:
+            place_others()
+            place_rest()
+        else:
+            place_rest()
+            place_others()
+        return max(load) if load else 0.0, plan
+
+    mk_a, plan_a = build(False)
+    if not rest or not other_costs:
+        return plan_a
+    mk_b, plan_b = build(True)
+    return plan_b if mk_b < mk_a - 1e-9 else plan_a
 
 
 # ---- row-sharded quotient (groundwork for the multi-GPU resident prover, DESIGN.md section 9) --------------------------

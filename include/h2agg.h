@@ -110,6 +110,13 @@ int h2agg_msm_g1_windows_dev(h2agg_ctx* ctx, uint64_t srs_id, const void* d_base
 int h2agg_msm_g1_batch_windows_dev(h2agg_ctx* ctx, uint64_t srs_id, const void* d_bases_affine,
                                    const void* const* d_scalar_cols, size_t n_cols, size_t n, int win_begin, int win_end,
                                    void* d_out160s);
+/* The same with a window range PER COLUMN (win_begins[i], win_ends[i]; win_end < 0 = all windows): everything a rank
+ * owes to one commit phase -- whole columns and window shards of others -- goes out in one call, so the latency-bound
+ * prologue / epilogue of a shard (digit passes, scans, bucket tree) runs on its lane beside the other columns' bucket
+ * accumulation instead of after it. */
+int h2agg_msm_g1_batch_ranges_dev(h2agg_ctx* ctx, uint64_t srs_id, const void* d_bases_affine,
+                                  const void* const* d_scalar_cols, size_t n_cols, size_t n, const int* win_begins,
+                                  const int* win_ends, void* d_out160s);
 /* Device-side combine of all-gathered partials: out[j] = sum_{i<m} P(i, j), the Jacobian point P(i, j)
  * living at d_points + i * stride_bytes + j * 160; writes n_out x 160 B (affine + Jacobian). */
 int h2agg_g1_sum_dev(h2agg_ctx* ctx, const void* d_points, size_t m, size_t stride_bytes, size_t n_out, void* d_out160s);

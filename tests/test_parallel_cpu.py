@@ -193,3 +193,47 @@ def test_rotation_halo_of_the_aggregation_circuit():
     assert w == [13, 14, 15, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9]
     rw = par.RowWindow(list(range(100, 113)), 0, 8, 3, 2, 16)
     assert rw[13] == 100 and rw[0] == 103 and rw[9] == 112
+
+
+def test_plan_phase_covers_every_window_once_and_uses_the_fixed_cost_model():
+    """Every MSM of a phase is either whole on one rank or cut into window ranges that tile [0, n_windows) exactly;
+    spare ranks go to the MSM whose shards are the most expensive; a phase of many transforms and one MSM puts the MSM
+    on the ranks that carry fewer transforms."""
+    from halo2_snark_aggregator_b200 import parallel as par
+
+    nw = 13
+    tot = {0: 10.5, 1: 2.08, 2: 6.11, 3: 2.09}
+    fx = {0: 2.45, 1: 1.48, 2: 3.25, 3: 1.39}
+
+    def check(kinds, others, world):
+        mc = {i: tot[k] for i, k in enumerate(kinds)}
+        mf = {i: fx[k] for i, k in enumerate(kinds)}
+        oc = {100 + i: c for i, c in enumerate(others)}
+        plan = par.plan_phase(mc, oc, world, nw, mf)
+        seen = {}
+        for u, r, w in plan:
+            assert 0 <= r < world
+            seen.setdefault(u, []).append(w)
+        assert set(seen) == set(mc) | set(oc)
+        for u, ws in seen.items():
+            if u in oc or ws == [None]:
+                assert ws == [None]
+                continue
+            ws = sorted(ws)
+            assert ws[0][0] == 0 and ws[-1][1] == nw and all(a[1] == b[0] for a, b in zip(ws, ws[1:]))
+        return plan
+
+    for world in (1, 2, 3, 4, 8):
+        for kinds, others in (([1, 1, 1, 1, 1, 2], [0.9] * 6), ([3] * 14, [0.9] * 14), ([0] * 9, [0.9] * 9), ([0], [3.4] * 29), ([0] * 4, [])):
+            check(kinds, others, world)
+    # 6 MSMs on 8 ranks: the two spare ranks both go to the expensive `a4`-like column (unit 5)
+    plan = check([1, 1, 1, 1, 1, 2], [0.9] * 6, 8)
+    assert sorted(w for u, r, w in plan if u == 5) == [(0, 4), (4, 8), (8, 13)]
+    assert all(w is None for u, r, w in plan if u < 5)
+    # 29 transforms + 1 MSM on 8 ranks: the MSM's shards sit on ranks that got 3 transforms, not 4
+    plan = check([0], [3.4] * 29, 8)
+    n_other = {r: sum(1 for u, rr, w in plan if rr == r and u >= 100) for r in range(8)}
+    assert all(n_other[r] == 3 for u, r, w in plan if u == 0)
+    # 4 MSMs on 8 ranks: two shards each, disjoint rank pairs
+    plan = check([0] * 4, [], 8)
+    assert sorted(r for u, r, w in plan) == list(range(8))
