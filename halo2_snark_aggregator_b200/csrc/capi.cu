@@ -110,6 +110,7 @@ void h2agg_destroy(h2agg_ctx* ctx) {
     cudaFree(ctx->lanes[i].scan_ws.p);
     cudaFree(ctx->lanes[i].args_ws.p);
     if (ctx->lanes[i].done) cudaEventDestroy(ctx->lanes[i].done);
+    if (ctx->lanes[i].up) cudaEventDestroy(ctx->lanes[i].up);
     if (ctx->lanes[i].st) cudaStreamDestroy(ctx->lanes[i].st);
   }
   if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
@@ -655,6 +656,10 @@ static int commit_round_impl(h2agg_ctx* ctx, uint64_t srs_id, const uint64_t* co
   if (ext_out && (rc = ntt_warm_tables(ctx, omega_ext, ext_k))) return rc;
   LaneFork lf(ctx);
   if ((rc = lf.fork())) return rc;
+  // Few columns (a rank's share of a round on a multi-GPU prover): the MSM and the transforms of a column only share
+  // their INPUT, so with device-resident outputs they run on two lanes -- the ~20-kernel latency chain of the MSM beside
+  // the pipe-bound NTT passes instead of in front of them.
+  const bool split = resident && coeff_out && 2 * n_cols <= (size_t)N_LANES;
   for (size_t i = 0; i < n_cols; i++) {
     Lane& ln = ctx->lanes[i % N_LANES];
     CHECK_ARG(ctx, lagrange_cols[i], "commit_round: null column");
@@ -668,12 +673,18 @@ static int commit_round_impl(h2agg_ctx* ctx, uint64_t srs_id, const uint64_t* co
       if (d_lagrange_keep && d_lagrange_keep[i]) col = d_lagrange_keep[i];
       H2AGG_CUDA(ctx, cudaMemcpyAsync(col, lagrange_cols[i], n * 32, cudaMemcpyHostToDevice, ln.st));
     }
+    // where the transforms of column i run (an in-place lagrange_to_coeff must stay behind the MSM that reads the column)
+    Lane& ln_t = (split && coeff_out[i] && (const void*)coeff_out[i] != (const void*)col) ? ctx->lanes[n_cols + i] : ln;
+    if (&ln_t != &ln) {
+      H2AGG_CUDA(ctx, cudaEventRecord(ln.up, ln.st));
+      H2AGG_CUDA(ctx, cudaStreamWaitEvent(ln_t.st, ln.up, 0));
+    }
     if ((rc = msm_run(ctx, ln.st, ln.ws, bases, col, n, (uint8_t*)ctx->small.p + i * 160, 0, -1, false))) return rc;
     if (coeff_out && coeff_out[i]) {
-      cudaStream_t st = ln.st;
+      cudaStream_t st = ln_t.st;
       if (resident) {
-        if ((rc = ntt_run(ctx, col, coeff_out[i], oi, st, &ln.ntt_tmp))) return rc;
-        if (ext_out && ext_out[i] && (rc = ntt_run(ctx, coeff_out[i], ext_out[i], oe, st, &ln.ntt_tmp))) return rc;
+        if ((rc = ntt_run(ctx, col, coeff_out[i], oi, st, &ln_t.ntt_tmp))) return rc;
+        if (ext_out && ext_out[i] && (rc = ntt_run(ctx, coeff_out[i], ext_out[i], oe, st, &ln_t.ntt_tmp))) return rc;
       } else {
         if ((rc = ntt_run(ctx, ln.io.p, ln.io.p, oi, st, &ln.ntt_tmp))) return rc;
         H2AGG_CUDA(ctx, cudaMemcpyAsync(coeff_out[i], ln.io.p, n * 32, cudaMemcpyDeviceToHost, st));

@@ -54,6 +54,7 @@ struct Lane {
   DevBuf scan_ws;   // grand-product scratch of this lane (batched lookup products)
   DevBuf args_ws;   // numerators / denominators of this lane
   cudaEvent_t done = nullptr;
+  cudaEvent_t up = nullptr;   // "this lane's column is in HBM": lets a second lane start the column's transforms
 };
 // Measured on B200 (k = 18 / 22 schedule): 3 lanes 47.7 / 337.5 ms, 6 lanes 40.2 / 331.7, 12 lanes 38.7 / 331.7 -- the
 // small sizes are bound by the ~20-launch latency chain of an MSM, which more lanes overlap; buffers are allocated

@@ -745,6 +745,7 @@ int lanes_init(h2agg_ctx* ctx) {
   for (int i = 0; i < N_LANES; i++) {
     H2AGG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->lanes[i].st, cudaStreamNonBlocking));
     H2AGG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->lanes[i].done, cudaEventDisableTiming));
+    H2AGG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->lanes[i].up, cudaEventDisableTiming));
   }
   return 0;
 }

@@ -106,23 +106,31 @@ class DistributedProver:
 
     def _pool_msm(self, items):
         """items: [(device pointer of n scalars, srs id, n windows)] present on EVERY rank -> affine commitments (len, 8).
-        The window units of all items are cut into `world` contiguous ranges (parallel.window_units)."""
-        ctx, t = self.ctx, self.torch
+        The window units of all items are cut into `world` contiguous ranges (parallel.window_units); everything this
+        rank owes goes out in ONE batched call per SRS with a window range per column (h2agg_msm_g1_batch_ranges_dev),
+        so the latency-bound ends of one shard run beside the accumulation of the next; one all-gather + local add + one
+        read-back for the whole list."""
+        ctx = self.ctx
         m = len(items)
         if m == 0:
             return np.zeros((0, 8), dtype=np.uint64)
-        nwin = items[0][2]
-        assert all(it[2] == nwin for it in items)
         d_part = self._buf(("pool_part", m), m * 160)
         self.tensor(d_part, m * 160).zero_()
-        by_call = {}
-        for (item, w0, w1) in par.window_units(m, nwin, self.world)[self.rank]:
-            by_call.setdefault((items[item][1], w0, w1), []).append(item)
+        # the window units are laid out item after item; items may differ in their window count (two SRS forms)
+        total = sum(it[2] for it in items)
+        lo, hi = total * self.rank // self.world, total * (self.rank + 1) // self.world
+        by_srs, base = {}, 0
+        for i, (ptr, srs, nwin) in enumerate(items):
+            w0, w1 = max(lo, base) - base, min(hi, base + nwin) - base
+            if w1 > w0:
+                by_srs.setdefault(srs, []).append((i, w0, w1, nwin))
+            base += nwin
         d_stage = self._buf(("pool_stage", m), m * 160)
-        for (srs, w0, w1), idxs in sorted(by_call.items()):
-            whole = (w0 == 0 and w1 == nwin)
-            ctx.msm_g1_batch_dev([items[i][0] for i in idxs], self.n, d_stage, srs_id=srs, windows=None if whole else (w0, w1))
-            for q, i in enumerate(idxs):
+        for srs, mine in sorted(by_srs.items()):
+            wins = [None if (w0 == 0 and w1 == nwin) else (w0, w1) for (_, w0, w1, nwin) in mine]
+            ctx.msm_g1_batch_dev([items[i][0] for (i, _, _, _) in mine], self.n, d_stage, srs_id=srs,
+                                 windows=wins if any(w is not None for w in wins) else None)
+            for q, (i, _, _, _) in enumerate(mine):
                 self.tensor(d_part, 160, 160 * i).copy_(self.tensor(d_stage, 160, 160 * q))
         if self.world == 1:
             return ctx.d2h(d_part, 20 * m).reshape(m, 20)[:, :8].copy()
@@ -199,8 +207,8 @@ class DistributedProver:
             self.tensor(dc, n * 32).copy_(self.tensor(pr.lag[nm], n * 32))
             pr.dom.lagrange_to_coeff_dev(dc)
             pr.dom.coeff_to_extended_dev(dc, de)
-        pool_c = self._pool_msm([(pr.lag[nm], pr.srs_lagrange, self.nwin_l) for nm in pooled])
-        rand_c = self._pool_msm([(d_rand, pr.srs_g, self.nwin_g)])[0]
+        pool_all = self._pool_msm([(pr.lag[nm], pr.srs_lagrange, self.nwin_l) for nm in pooled] + [(d_rand, pr.srs_g, self.nwin_g)])
+        pool_c, rand_c = pool_all[:len(pooled)], pool_all[len(pooled)]
         comm = self._share_rows(len(znames), 8, got)
         for j, nm in enumerate(pooled):
             comm[znames.index(nm)] = pool_c[j]
@@ -322,16 +330,20 @@ class DistributedProver:
         d_out = self._buf(("w_part", P), P * 160)
         self.tensor(d_out, P * 160).zero_()
         one = fr_to_limbs(1)
-        d_stage = self._buf("w_stage", 160)
+        d_stage = self._buf("w_stage", 160 * max(1, len(units[rank])))
+        d_ws, wins = [], []
         for (p, w0, w1) in units[rank]:
-            d_fold = self._buf("fold_sum", n * 32)
+            d_fold = self._buf(("fold_sum", p), n * 32)
             parts = [d_part[p]] + [recv[(p, s)] for s in range(world) if s != rank]
             ctx.poly_lincomb_dev(parts, np.tile(one, len(parts)), n, d_fold)
             d_w = self._buf(("w_poly", p), n * 32)
             ctx.kate_division_dev(d_fold, n, fr_to_limbs(pr.rotate_omega(x, order[p])), d_w)
-            whole = (w0 == 0 and w1 == self.nwin_g)
-            ctx.msm_g1_batch_dev([d_w], n, d_stage, srs_id=pr.srs_g, windows=None if whole else (w0, w1))
-            self.tensor(d_out, 160, 160 * p).copy_(self.tensor(d_stage, 160))
+            d_ws.append(d_w)
+            wins.append(None if (w0 == 0 and w1 == self.nwin_g) else (w0, w1))
+        if d_ws:   # all of this rank's window ranges in one batched call
+            ctx.msm_g1_batch_dev(d_ws, n, d_stage, srs_id=pr.srs_g, windows=wins if any(w is not None for w in wins) else None)
+            for q, (p, _, _) in enumerate(units[rank]):
+                self.tensor(d_out, 160, 160 * p).copy_(self.tensor(d_stage, 160, 160 * q))
         if world == 1:
             return order, ctx.d2h(d_out, 20 * P).reshape(P, 20)[:, :8].copy()
         d_all = self._buf(("w_all", P), world * P * 160)
