@@ -7,8 +7,8 @@ TAG=${1:-r01b}
 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-witness > gpurun_out/${TAG}_launches_bench.log 2>&1
 ncu --set full --clock-control none --import-source on \
-    -k regex:"msm_accumulate|ntt_pass_kernel|quot_evaluate_h|sort_scatter|lookup_mark_leftover|perm_num_den|msm_digits|witness_expand" \
-    -c 26 -f -o gpurun_out/${TAG}_full python tools/prof_once.py 22 > gpurun_out/${TAG}_full.log 2>&1
+    -k regex:"msm_accumulate|ntt_pass_kernel|quot_evaluate_h|sort_scatter|lookup_mark_leftover|perm_num_den|msm_digits|witness_expand|witness_iszero" \
+    -c 40 -f -o gpurun_out/${TAG}_full python tools/prof_once.py 22 > gpurun_out/${TAG}_full.log 2>&1
 ncu -i gpurun_out/${TAG}_full.ncu-rep --page raw --csv > gpurun_out/${TAG}_full_raw.csv 2> gpurun_out/${TAG}_full_raw.err
 ls -la gpurun_out/${TAG}_full.ncu-rep
 # the report itself is too large to bring back with everything else: keep only the CSV
