@@ -114,6 +114,9 @@ def load():
         "h2agg_poly_fold_dev": (ci, [c_vp, ctypes.POINTER(c_vp), sz, sz, c_vp, c_vp]),
         "h2agg_poly_lincomb_dev": (ci, [c_vp, ctypes.POINTER(c_vp), c_vp, sz, sz, c_vp]),
         "h2agg_evaluate_h_rows_dev": (ci, [c_vp, ctypes.POINTER(QuotientArgs), u64, u64, c_vp, c_vp]),
+        "h2agg_set_defer_transforms": (ci, [c_vp, ci]),
+        "h2agg_transforms_join": (ci, [c_vp]),
+        "h2agg_transforms_dev": (ci, [c_vp, ctypes.POINTER(c_vp), sz, u32, c_vp, c_vp, ctypes.POINTER(c_vp), u32, c_vp, c_vp, ctypes.POINTER(c_vp)]),
         "h2agg_wit_new": (c_vp, []),
         "h2agg_wit_set_threads": (ci, [ci]),
         "h2agg_wit_free": (None, [c_vp]),

@@ -200,6 +200,20 @@ class Context:
                                                _ptr(zeta), _ptr(omega_ext), eo))
         return out.reshape(nc, 8)
 
+    def set_defer_transforms(self, enable):
+        """commit_round_resident / _dev: NTT passes on the background stream; see include/h2agg.h"""
+        self.check(self.lib.h2agg_set_defer_transforms(self.h, 1 if enable else 0))
+
+    def transforms_join(self):
+        self.check(self.lib.h2agg_transforms_join(self.h))
+
+    def transforms_dev(self, d_cols, k, omega_inv, n_inv, d_coeff_out, ext_k=0, zeta=None, omega_ext=None, d_ext_out=None):
+        nc = len(d_cols)
+        a = (c_vp * nc)(*d_cols)
+        co = (c_vp * nc)(*d_coeff_out)
+        eo = (c_vp * nc)(*d_ext_out) if d_ext_out is not None else None
+        self.check(self.lib.h2agg_transforms_dev(self.h, a, nc, k, _ptr(omega_inv), _ptr(n_inv), co, ext_k, _ptr(zeta), _ptr(omega_ext), eo))
+
     def commit_round_resident(self, srs_id, cols, k, omega_inv, n_inv, d_coeff_out, ext_k=0, zeta=None, omega_ext=None, d_ext_out=None,
                               d_lagrange_out=None):
         """Commit round whose coefficient / extended (/ Lagrange) forms stay in HBM (device pointers) -> affine commitments (len(cols), 8)."""

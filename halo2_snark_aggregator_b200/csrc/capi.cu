@@ -12,7 +12,26 @@ static thread_local std::string g_init_error;
 
 namespace h2agg {
 std::atomic<int> g_any_device{-1};
+
+int bg_stream_get(h2agg_ctx* ctx, cudaStream_t* out) {
+  if (!ctx->bg_stream) {
+    int least = 0, greatest = 0;
+    H2AGG_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    H2AGG_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->bg_stream, cudaStreamNonBlocking, least));
+    H2AGG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->bg_ev, cudaEventDisableTiming));
+  }
+  *out = ctx->bg_stream;
+  return 0;
 }
+
+int bg_join(h2agg_ctx* ctx) {
+  if (!ctx->bg_pending || !ctx->bg_stream) return 0;
+  H2AGG_CUDA(ctx, cudaEventRecord(ctx->bg_ev, ctx->bg_stream));
+  H2AGG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->bg_ev, 0));
+  ctx->bg_pending = false;
+  return 0;
+}
+}  // namespace h2agg
 
 #define LOCK(ctx) std::lock_guard<std::recursive_mutex> lock_((ctx)->mu)
 #define CHECK_ARG(ctx, cond, msg) \
@@ -99,6 +118,12 @@ void h2agg_destroy(h2agg_ctx* ctx) {
   cudaFree(ctx->ntt_tmp.p);
   cudaFree(ctx->io_a.p);
   cudaFree(ctx->wit_ws.p);
+  if (ctx->bg_stream) {
+    cudaStreamSynchronize(ctx->bg_stream);
+    cudaStreamDestroy(ctx->bg_stream);
+    cudaEventDestroy(ctx->bg_ev);
+  }
+  cudaFree(ctx->bg_ntt_tmp.p);
   cudaFree(ctx->io_b.p);
   cudaFree(ctx->msm_ws.p);
   for (int i = 0; i < N_LANES; i++) {
@@ -149,8 +174,23 @@ int h2agg_set_stream(h2agg_ctx* ctx, void* cuda_stream) {
 int h2agg_synchronize(h2agg_ctx* ctx) {
   if (!ctx) return 1;
   LOCK(ctx);
+  int rc = bg_join(ctx);
+  if (rc) return rc;
   H2AGG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return 0;
+}
+
+int h2agg_set_defer_transforms(h2agg_ctx* ctx, int enable) {
+  if (!ctx) return 1;
+  LOCK(ctx);
+  ctx->defer_transforms = enable != 0;
+  return 0;
+}
+
+int h2agg_transforms_join(h2agg_ctx* ctx) {
+  if (!ctx) return 1;
+  LOCK(ctx);
+  return bg_join(ctx);
 }
 
 uint64_t h2agg_launch_count(h2agg_ctx* ctx) { return ctx ? ctx->launches : 0; }
@@ -659,7 +699,18 @@ static int commit_round_impl(h2agg_ctx* ctx, uint64_t srs_id, const uint64_t* co
   // Few columns (a rank's share of a round on a multi-GPU prover): the MSM and the transforms of a column only share
   // their INPUT, so with device-resident outputs they run on two lanes -- the ~20-kernel latency chain of the MSM beside
   // the pipe-bound NTT passes instead of in front of them.
-  const bool split = resident && coeff_out && 2 * n_cols <= (size_t)N_LANES;
+  // Deferred transforms: the commitments gate the next Fiat-Shamir challenge, the coefficient / extended forms are only
+  // needed in the quotient and evaluation stages -- with h2agg_set_defer_transforms the NTT passes go to the low-priority
+  // background stream (after the column is in HBM) and this call returns as soon as the MSMs are done; they then fill the
+  // latency-bound stretches of the following rounds.  h2agg_transforms_join orders the main stream after them.
+  const bool defer = resident && coeff_out && ctx->defer_transforms;
+  cudaStream_t bg = nullptr;
+  if (defer) {
+    if ((rc = bg_stream_get(ctx, &bg))) return rc;
+    H2AGG_CUDA(ctx, cudaStreamWaitEvent(bg, ctx->fork_ev, 0));   // everything the main stream holds so far
+    ctx->bg_pending = true;
+  }
+  const bool split = !defer && resident && coeff_out && 2 * n_cols <= (size_t)N_LANES;
   for (size_t i = 0; i < n_cols; i++) {
     Lane& ln = ctx->lanes[i % N_LANES];
     CHECK_ARG(ctx, lagrange_cols[i], "commit_round: null column");
@@ -682,7 +733,12 @@ static int commit_round_impl(h2agg_ctx* ctx, uint64_t srs_id, const uint64_t* co
     if ((rc = msm_run(ctx, ln.st, ln.ws, bases, col, n, (uint8_t*)ctx->small.p + i * 160, 0, -1, false))) return rc;
     if (coeff_out && coeff_out[i]) {
       cudaStream_t st = ln_t.st;
-      if (resident) {
+      if (defer) {
+        H2AGG_CUDA(ctx, cudaEventRecord(ln.up, ln.st));           // the column is in HBM (lanes reuse `up`: stream order keeps it safe)
+        H2AGG_CUDA(ctx, cudaStreamWaitEvent(bg, ln.up, 0));
+        if ((rc = ntt_run(ctx, col, coeff_out[i], oi, bg, &ctx->bg_ntt_tmp))) return rc;
+        if (ext_out && ext_out[i] && (rc = ntt_run(ctx, coeff_out[i], ext_out[i], oe, bg, &ctx->bg_ntt_tmp))) return rc;
+      } else if (resident) {
         if ((rc = ntt_run(ctx, col, coeff_out[i], oi, st, &ln_t.ntt_tmp))) return rc;
         if (ext_out && ext_out[i] && (rc = ntt_run(ctx, coeff_out[i], ext_out[i], oe, st, &ln_t.ntt_tmp))) return rc;
       } else {
@@ -737,6 +793,46 @@ int h2agg_commit_round_dev(h2agg_ctx* ctx, uint64_t srs_id, const void* const* d
   return commit_round_impl(ctx, srs_id, (const uint64_t* const*)d_lagrange_cols, n_cols, k, omega_inv, n_inv, out_affine,
                            (uint64_t* const*)d_coeff_out, ext_k, zeta, omega_ext, (uint64_t* const*)d_ext_out, true, nullptr,
                            true);
+}
+
+// The transform half of a commit round alone (columns whose commitment is computed elsewhere, e.g. window-sharded over
+// other GPUs): lagrange_to_coeff (+ coeff_to_extended), out of place, on the background stream when transforms are
+// deferred, else on the main stream.
+int h2agg_transforms_dev(h2agg_ctx* ctx, const void* const* d_lagrange_cols, size_t n_cols, uint32_t k,
+                         const uint64_t omega_inv[4], const uint64_t n_inv[4], void* const* d_coeff_out, uint32_t ext_k,
+                         const uint64_t zeta[4], const uint64_t omega_ext[4], void* const* d_ext_out) {
+  if (!ctx) return 1;
+  LOCK(ctx);
+  CHECK_ARG(ctx, d_lagrange_cols && d_coeff_out && omega_inv && n_inv, "transforms_dev: null argument");
+  CHECK_ARG(ctx, k >= 1 && k <= 28, "transforms_dev: k out of range");
+  CHECK_ARG(ctx, !d_ext_out || (zeta && omega_ext && ext_k >= k && ext_k <= 28), "transforms_dev: extended output needs zeta, omega_ext");
+  if (n_cols == 0) return 0;
+  H2AGG_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t n = (size_t)1 << k;
+  int rc;
+  uint64_t s3[12], in3[12];
+  for (int i = 0; i < 3; i++) memcpy(s3 + 4 * i, n_inv, 32);
+  if (d_ext_out && (rc = coset_consts(ctx, zeta, nullptr, 0, in3))) return rc;
+  NttOpts oi{omega_inv, k, n, n, nullptr, s3};
+  NttOpts oe{omega_ext, ext_k, n, (size_t)1 << ext_k, in3, nullptr};
+  if ((rc = ntt_warm_tables(ctx, omega_inv, k))) return rc;
+  if (d_ext_out && (rc = ntt_warm_tables(ctx, omega_ext, ext_k))) return rc;
+  cudaStream_t st = ctx->stream;
+  DevBuf* tmp = &ctx->ntt_tmp;
+  if (ctx->defer_transforms) {
+    if ((rc = lanes_init(ctx))) return rc;   // (creates fork_ev)
+    if ((rc = bg_stream_get(ctx, &st))) return rc;
+    H2AGG_CUDA(ctx, cudaEventRecord(ctx->fork_ev, ctx->stream));
+    H2AGG_CUDA(ctx, cudaStreamWaitEvent(st, ctx->fork_ev, 0));
+    ctx->bg_pending = true;
+    tmp = &ctx->bg_ntt_tmp;
+  }
+  for (size_t i = 0; i < n_cols; i++) {
+    CHECK_ARG(ctx, d_lagrange_cols[i] && d_coeff_out[i], "transforms_dev: null column");
+    if ((rc = ntt_run(ctx, d_lagrange_cols[i], d_coeff_out[i], oi, st, tmp))) return rc;
+    if (d_ext_out && d_ext_out[i] && (rc = ntt_run(ctx, d_coeff_out[i], d_ext_out[i], oe, st, tmp))) return rc;
+  }
+  return 0;
 }
 
 int h2agg_extended_to_coeff_dev(h2agg_ctx* ctx, void* d_a, uint32_t ext_k, const uint64_t omega_ext_inv[4],

@@ -95,6 +95,12 @@ struct h2agg_ctx {
   uint64_t quot_omega[4] = {0, 0, 0, 0};
   uint32_t quot_ext_k = 0;
   int quot_flip = 0;
+  // deferred transforms (h2agg_set_defer_transforms): the NTTs of a commit round run on a background stream
+  bool defer_transforms = false;
+  bool bg_pending = false;          // something was enqueued on bg_stream since the last join
+  cudaStream_t bg_stream = nullptr;
+  cudaEvent_t bg_ev = nullptr;
+  h2agg::DevBuf bg_ntt_tmp;         // the background stream's own NTT ping-pong buffer
   void* pinned = nullptr;     // pinned host bounce buffer for tiny results
   size_t pinned_cap = 0;
   std::vector<h2agg::TwiddleTable> tw;
@@ -172,6 +178,11 @@ struct ScopedKernelTimer {
     ctx->timed.push_back(t);
   }
 };
+
+// Make ctx->stream wait for everything enqueued on the background stream (no-op when nothing is pending).
+int bg_join(h2agg_ctx* ctx);
+// Background stream, created on first use; `after` (optional) is an event it must wait for.
+int bg_stream_get(h2agg_ctx* ctx, cudaStream_t* out);
 
 // ---- internal device-pointer API (all asynchronous on ctx->stream) -------------------------
 // NTT over Fr. `src` has src_n valid elements (rest of the 2^log_n domain is implicit zero),

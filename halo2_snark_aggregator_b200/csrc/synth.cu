@@ -121,6 +121,7 @@ int h2agg_memcpy_d2h(h2agg_ctx* ctx, void* dst, const void* d_src, size_t bytes)
   if (!ctx) return 1;
   std::lock_guard<std::recursive_mutex> lock(ctx->mu);
   H2AGG_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (int rc = bg_join(ctx)) return rc;   // a host read is a synchronisation point: deferred transforms included
   H2AGG_CUDA(ctx, cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   H2AGG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return 0;

@@ -202,11 +202,8 @@ class DistributedProver:
         if whole:
             c = pr._commit_resident(whole)
             got = {znames.index(nm): c[j] for j, nm in enumerate(whole)}
-        for nm in self.mine(pooled):   # owned and pooled: the transforms only
-            dc, de = pr.slot(nm)
-            self.tensor(dc, n * 32).copy_(self.tensor(pr.lag[nm], n * 32))
-            pr.dom.lagrange_to_coeff_dev(dc)
-            pr.dom.coeff_to_extended_dev(dc, de)
+        if self.mine(pooled):          # owned and pooled: the transforms only (background stream)
+            pr.transform_resident(self.mine(pooled))
         pool_all = self._pool_msm([(pr.lag[nm], pr.srs_lagrange, self.nwin_l) for nm in pooled] + [(d_rand, pr.srs_g, self.nwin_g)])
         pool_c, rand_c = pool_all[:len(pooled)], pool_all[len(pooled)]
         comm = self._share_rows(len(znames), 8, got)
@@ -256,6 +253,7 @@ class DistributedProver:
 
     def quotient(self, y, beta, gamma, theta):
         pr, ctx, n = self.pr, self.ctx, self.n
+        pr.join_transforms()           # the exchange reads the extended forms the background stream produced
         cols, row0 = self._exchange_windows()
         lo, hi = self.shards[self.rank]
         d_h = pr._buf("h", self.ext_n * 32)
@@ -290,6 +288,7 @@ class DistributedProver:
     # ---- GWC multi-opening ---------------------------------------------------------------------------------------------
     def open(self, queries, x, v):
         pr, ctx, n, dist, rank, world = self.pr, self.ctx, self.n, self.dist, self.rank, self.world
+        pr.join_transforms()
         order, groups = [], {}
         for nm, rot in queries:
             if rot not in groups:

@@ -42,6 +42,19 @@ class ResidentProver:
         self.n_pieces = self.dom.quotient_poly_degree
         self._scratch = {}
 
+    # The commitments of a round gate the next Fiat-Shamir challenge; its coefficient / extended forms are only read by
+    # the quotient and the evaluation round.  With defer_transforms the NTT passes of every commit round run on the
+    # context's background stream (h2agg_set_defer_transforms) and fill the latency-bound stretches of the following
+    # rounds; `join_transforms` is called where their results are first needed.
+    defer_transforms = True
+
+    def _deferred(self, on):
+        if self.defer_transforms:
+            self.ctx.set_defer_transforms(on)
+
+    def join_transforms(self):
+        self.ctx.transforms_join()
+
     # -- optional stage trace (bench / profiling): set self.trace = {} to collect synchronised stage times in ms
     trace = None
     trace_kernels = False
@@ -135,11 +148,17 @@ class ResidentProver:
         under `names`."""
         slots = [self.slot(nm, extended) for nm in names]
         d = self.dom
-        return self.ctx.commit_round_resident(
-            self.srs_lagrange, list(lagrange_cols), self.k, d.omega_inv, d.ifft_divisor, [s[0] for s in slots],
-            ext_k=self.ext_k if extended else 0, zeta=d.g_coset if extended else None,
-            omega_ext=d.extended_omega if extended else None, d_ext_out=[s[1] for s in slots] if extended else None,
-            d_lagrange_out=[self.lagrange_slot(nm) for nm in names] if keep_lagrange else None)
+        # deferred transforms read the Lagrange column after this call returns: it must live in its own buffer then
+        keep = keep_lagrange or self.defer_transforms
+        self._deferred(True)
+        try:
+            return self.ctx.commit_round_resident(
+                self.srs_lagrange, list(lagrange_cols), self.k, d.omega_inv, d.ifft_divisor, [s[0] for s in slots],
+                ext_k=self.ext_k if extended else 0, zeta=d.g_coset if extended else None,
+                omega_ext=d.extended_omega if extended else None, d_ext_out=[s[1] for s in slots] if extended else None,
+                d_lagrange_out=[self.lagrange_slot(nm) for nm in names] if keep else None)
+        finally:
+            self._deferred(False)
 
     def commit_device_columns(self, names):
         """Commit round for Lagrange columns that are ALREADY in HBM under `lagrange_slot(name)` -- e.g. the five advice
@@ -150,9 +169,24 @@ class ResidentProver:
         """Commit round for Lagrange columns the device produced itself (self.lag[name])."""
         slots = [self.slot(nm) for nm in names]
         d = self.dom
-        return self.ctx.commit_round_dev(self.srs_lagrange, [self.lag[nm] for nm in names], self.k, d.omega_inv, d.ifft_divisor,
-                                         [s[0] for s in slots], ext_k=self.ext_k, zeta=d.g_coset, omega_ext=d.extended_omega,
-                                         d_ext_out=[s[1] for s in slots])
+        self._deferred(True)
+        try:
+            return self.ctx.commit_round_dev(self.srs_lagrange, [self.lag[nm] for nm in names], self.k, d.omega_inv, d.ifft_divisor,
+                                             [s[0] for s in slots], ext_k=self.ext_k, zeta=d.g_coset, omega_ext=d.extended_omega,
+                                             d_ext_out=[s[1] for s in slots])
+        finally:
+            self._deferred(False)
+
+    def transform_resident(self, names):
+        """lagrange_to_coeff + coeff_to_extended of resident Lagrange columns whose commitment is computed elsewhere."""
+        slots = [self.slot(nm) for nm in names]
+        d = self.dom
+        self._deferred(True)
+        try:
+            self.ctx.transforms_dev([self.lag[nm] for nm in names], self.k, d.omega_inv, d.ifft_divisor, [s[0] for s in slots],
+                                    ext_k=self.ext_k, zeta=d.g_coset, omega_ext=d.extended_omega, d_ext_out=[s[1] for s in slots])
+        finally:
+            self._deferred(False)
 
     # -- stage 2: lookup arguments (commit_permuted) -----------------------------------------------------
     def usable_rows(self):
@@ -248,6 +282,7 @@ class ResidentProver:
     # -- stage 4: quotient -----------------------------------------------------------------------------
     def quotient(self, y, beta, gamma, theta):
         """h = evaluate_h / (X^n - 1) on the coset -> coefficients -> commitments of its n-coefficient pieces."""
+        self.join_transforms()
         cols = [self.ext[nm] for nm in self.plan.columns]
         d_h = self._buf("h", self.ext_n * 32)
         lim = [fr_to_limbs(v) for v in (y, beta, gamma, theta)]
@@ -281,6 +316,7 @@ class ResidentProver:
     def evaluate(self, queries, x):
         """queries: [(column name, rotation)] -> evaluations at x * omega^rotation, shape (len, 4) Montgomery limbs."""
         assert len(queries) <= 1024
+        self.join_transforms()
         d_ev = self._buf("evals", 32 * 1024)
         groups = {}  # one batched call per opening point
         for i, (nm, rot) in enumerate(queries):
@@ -303,6 +339,7 @@ class ResidentProver:
         `.rev().reduce(|acc, q| v * acc + q)`),  W = commit(kate_division(poly_batch - eval_batch, point)).
         The constant eval_batch only changes the remainder kate_division drops, so it is not subtracted here.
         Returns (rotations in point order, affine W commitments (len, 8))."""
+        self.join_transforms()
         order, groups = [], {}
         for nm, rot in queries:
             if rot not in groups:

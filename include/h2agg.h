@@ -172,6 +172,19 @@ int h2agg_commit_round_dev(h2agg_ctx* ctx, uint64_t srs_id, const void* const* d
                            const uint64_t omega_inv[4], const uint64_t n_inv[4], uint64_t* out_affine,
                            void* const* d_coeff_out, uint32_t ext_k, const uint64_t zeta[4], const uint64_t omega_ext[4],
                            void* const* d_ext_out);
+/* Deferred transforms.  create_proof needs a column's COMMITMENT before the next Fiat-Shamir challenge, but its coefficient
+ * and extended forms only in the quotient / evaluation stages.  With enable = 1, h2agg_commit_round_resident / _dev put
+ * their lagrange_to_coeff / coeff_to_extended passes on the context's low-priority background stream (ordered after the
+ * column's upload) and return as soon as the commitments are there, so the pipe-bound NTT passes fill the latency-bound
+ * stretches of the following rounds (sorts, scans, MSM tails, host round trips).  h2agg_transforms_join makes the main
+ * stream wait for them; h2agg_synchronize and h2agg_memcpy_d2h join implicitly.  Default off. */
+int h2agg_set_defer_transforms(h2agg_ctx* ctx, int enable);
+int h2agg_transforms_join(h2agg_ctx* ctx);
+/* The transform half of a commit round alone -- lagrange_to_coeff (+ coeff_to_extended when d_ext_out), out of place --
+ * for columns whose commitment is computed elsewhere (window-sharded over other GPUs).  Background stream when deferred. */
+int h2agg_transforms_dev(h2agg_ctx* ctx, const void* const* d_lagrange_cols, size_t n_cols, uint32_t k,
+                         const uint64_t omega_inv[4], const uint64_t n_inv[4], void* const* d_coeff_out, uint32_t ext_k,
+                         const uint64_t zeta[4], const uint64_t omega_ext[4], void* const* d_ext_out);
 int h2agg_coeff_to_extended_dev(h2agg_ctx* ctx, const void* d_coeffs, uint32_t k, uint32_t ext_k,
                                 const uint64_t zeta[4], const uint64_t omega_ext[4], void* d_out);
 int h2agg_extended_to_coeff_dev(h2agg_ctx* ctx, void* d_a, uint32_t ext_k, const uint64_t omega_ext_inv[4],
