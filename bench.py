@@ -285,6 +285,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-witness", action="store_true")
+    ap.add_argument("--launch-list-only", action="store_true",
+                    help="stop after the timed region (for `ncu --metrics gpu__time_duration.sum`: the launch list then holds exactly warmup + steps schedule steps)")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison of the timed path's commitments (profiling runs only)")
     ap.add_argument("--overlap-ntt", action="store_true", help="run a phase's NTTs on a second stream beside its MSM batch (measured: no gain, the step is multiplier-bound)")
     ap.add_argument("--e2e-steps", type=int, default=2)
@@ -534,6 +536,12 @@ def main():
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms = float(t_ms.item())
+
+    if args.launch_list_only:
+        if rank == 0:
+            print(json.dumps({"value": ms * 1e-3, "unit": "s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                              "gpu_launches": int(launches), "note": "launch-list run: nothing but the schedule steps was launched"}), flush=True)
+        return
 
     # ---- per-phase timings (one extra, untimed-for-`value` step): for every phase the time each rank is busy with its
     # own units and the span of the phase including the wait for the slowest rank + the all-gather

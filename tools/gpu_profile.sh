@@ -5,7 +5,7 @@ set -x
 mkdir -p gpurun_out
 TAG=${1:-r01b}
 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/${TAG}_launches.csv \
-    python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-witness > gpurun_out/${TAG}_launches_bench.log 2>&1
+    python bench.py --steps 1 --warmup 3 --launch-list-only > gpurun_out/${TAG}_launches_bench.log 2>&1
 ncu --set full --clock-control none --import-source on \
     -k regex:"msm_accumulate|ntt_pass_kernel|quot_evaluate_h|sort_scatter|lookup_mark_leftover|perm_num_den|msm_digits|witness_expand|witness_iszero" \
     -c 40 -f -o gpurun_out/${TAG}_full python tools/prof_once.py 22 > gpurun_out/${TAG}_full.log 2>&1
