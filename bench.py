@@ -288,7 +288,12 @@ def main():
     ap.add_argument("--launch-list-only", action="store_true",
                     help="stop after the timed region (for `ncu --metrics gpu__time_duration.sum`: the launch list then holds exactly warmup + steps schedule steps)")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison of the timed path's commitments (profiling runs only)")
-    ap.add_argument("--overlap-ntt", action="store_true", help="run a phase's NTTs on a second stream beside its MSM batch (measured: no gain, the step is multiplier-bound)")
+    ap.add_argument("--ntt-schedule", default="auto", choices=["auto", "inline", "overlap", "deferred"],
+                    help="inline: a phase's transforms run on the main stream in front of its MSM batch; overlap: on a second stream, "
+                         "joined at the end of the phase; deferred (what the resident provers do with h2agg_set_defer_transforms): on a "
+                         "second stream, joined only where their results are needed -- before the h commits and at the end of the step. "
+                         "auto = inline on one GPU (measured at k = 22: 0.3315 / 0.3328 / 0.3339 s -- the step is multiplier-bound, a second "
+                         "stream only adds contention), deferred on several (N = 8: 57.3 -> 56.6 ms: the transforms fill the MSM tails)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--msm-window", type=int, default=0)
     ap.add_argument("--parallelism", default="auto", choices=["auto", "columns", "windows"])
@@ -451,15 +456,26 @@ def main():
     s_ntt = torch.cuda.Stream(device=dev)  # the phase's NTTs run beside its MSM batch (independent columns)
     ev_fork, ev_join = torch.cuda.Event(), torch.cuda.Event()
 
+    if args.ntt_schedule == "auto":
+        args.ntt_schedule = "inline" if world == 1 else "deferred"
+    overlap_ntt = args.ntt_schedule != "inline"
+    deferred_ntt = args.ntt_schedule == "deferred"
+    # the h-piece commits are the only MSMs that consume transform results (coset NTTs -> iNTT(4n) -> pieces of h)
+    needs_transforms = [bool(ids) and all(units[i][1] == "msm" and i >= 64 for i in ids) and units[ids[0]][0] == 3 for ids in phases]
+
     def step_device(marks=None):
         c = 0
+        pending = False
         for p_i, ph in enumerate(plan):
             if marks is not None:
                 marks[p_i].record(stream)
+            if pending and needs_transforms[p_i]:
+                stream.wait_event(ev_join)
+                pending = False
             nm = len(phase_msms[p_i])
             ntt_here = [(u, rk, w) for (u, rk, w) in ph if rk == rank and units[u][1] != "msm"]
             if ntt_here:
-                if args.overlap_ntt:
+                if overlap_ntt:
                     ev_fork.record(stream)
                     s_ntt.wait_event(ev_fork)
                     ctx.set_stream(s_ntt.cuda_stream)
@@ -472,9 +488,10 @@ def main():
                     else:
                         dom.extended_to_coeff_dev(t_ext[c % 2].data_ptr())
                     c += 1
-                if args.overlap_ntt:
+                if overlap_ntt:
                     ev_join.record(s_ntt)
                     ctx.set_stream(stream.cuda_stream)
+                    pending = True
             if nm and world > 1:
                 t_send.zero_()
             for (w, us, idx) in my_calls[p_i]:
@@ -485,8 +502,9 @@ def main():
                 elif dst == t_stage.data_ptr():
                     for q, j in enumerate(us):
                         t_final[j * 160:(j + 1) * 160] = t_stage[q * 160:(q + 1) * 160]
-            if ntt_here and args.overlap_ntt:
+            if pending and not deferred_ntt:
                 stream.wait_event(ev_join)
+                pending = False
             if marks is not None:
                 marks[len(plan) + 1 + p_i].record(stream)   # this rank's own work of the phase is done
             if nm and world > 1:
@@ -501,6 +519,8 @@ def main():
                 else:
                     for q, j in enumerate(phase_msms[p_i]):
                         t_final[j * 160:(j + 1) * 160] = t_stage[q * 160:(q + 1) * 160]
+        if pending:
+            stream.wait_event(ev_join)
         if marks is not None:
             marks[len(plan)].record(stream)
 
@@ -1076,7 +1096,7 @@ def main():
             "config": workload_config(k),
             "impl_config": {"parallelism": ("%s over %d GPU(s), one all-gather of commitments per commit phase" % ({"windows": "window-sharded MSM + column-parallel NTT", "columns": "column-parallel (round-robin)", "auto": "cost-balanced column-parallel, leftover MSMs window-sharded"}[mode], world)),
                             "msm_mode": "fixed-base table (2^(c w) P rows resident in HBM)" if table_mode else "plain",
-                            "msm_window_bits": cbits, "msm_windows": nwin,
+                            "msm_window_bits": cbits, "msm_windows": nwin, "ntt_schedule": args.ntt_schedule,
                             "plan_costs_ms": {"%s%s" % (kk[0], kk[1] if kk[0] == "msm" else ""): round(v, 3) for kk, v in COST.items()},
                             "plan_msm_fixed_ms": {str(kk): round(v, 3) for kk, v in FIXED.items()}, "plan_cost_source": cost_source},
             "phases": phase_report,
