@@ -85,7 +85,7 @@ struct h2agg_ctx {
   h2agg::DevBuf poly_ws;      // recursion levels of eval_polynomial / kate_division
   h2agg::DevBuf poly_many_ws; // eval_polynomials: two level buffers for 64 polynomials at a time
   h2agg::DevBuf scan_ws;      // batch_invert / grand_product scratch
-  h2agg::DevBuf wit_ws;       // witness expansion: the values is_zero inverts (3 per record), batch-inverted
+  h2agg::DevBuf wit_ws;       // witness expansion: index array grouping the records by opcode + the values is_zero inverts
   h2agg::DevBuf args_ws;      // lookup / permutation products: numerators and denominators
   h2agg::DevBuf args_meta;    // compress_expressions: device copies of expression lists (four slots)
   int args_flip = 0;
@@ -236,7 +236,7 @@ int msm_run(h2agg_ctx* ctx, cudaStream_t st, DevBuf& ws, const MsmBases& bases, 
 int g1_normalize(h2agg_ctx* ctx, cudaStream_t st, void* d_out160s, size_t n);
 int msm_build_srs_table(h2agg_ctx* ctx, Srs& s);
 int msm_table_config(size_t srs_n, int* c, int* nwin);
-// d_ops: records grouped by opcode (counts[opc] records of opcode opc, in opcode order)
+// d_ops: records in recording order; counts[opc] = how many carry opcode opc
 int witness_expand_dev(h2agg_ctx* ctx, const void* d_ops, const size_t* counts, void* const d_cols[5], size_t n_rows);
 int batch_invert_dev(h2agg_ctx* ctx, void* d_a, size_t n);
 // n_cols MSMs against the same bases, alternating lanes; joins back into ctx->stream.

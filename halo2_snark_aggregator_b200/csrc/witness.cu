@@ -7,8 +7,10 @@
 // the advice cells, so the output is exactly the 5 advice columns (Montgomery Fr, the layout
 // halo2 holds in memory); fixed cells and copy constraints belong to keygen.
 //
-// One thread per op record (witness_ops.h); the recorder keeps one store per opcode, so the device array
-// is grouped by opcode and every recipe is its own kernel.  The three inversions of `is_zero` are not
+// One thread per op record (witness_ops.h).  The records arrive in recording order; a first kernel groups
+// their indices by opcode (the host knows the per-opcode counts, so this is one scatter with warp-aggregated
+// cursors), and every recipe then runs as its own kernel over its index range: own register budget, no
+// divergence.  The three inversions of `is_zero` are not
 // done per thread (three 254-step Fermat ladders each): a first kernel writes the values to invert, the
 // batched inversion of scan.cu inverts all of them at once, a second kernel writes the rows.
 // The heavy recipe is MULEQ: 560-bit product, exact division by p through
@@ -324,21 +326,23 @@ __device__ __forceinline__ void iszero_values(const WitnessOp& op, Fr* af, Fr& s
   ld = af[0] - p0;
 }
 
-__global__ void __launch_bounds__(128) witness_iszero_values_kernel(const WitnessOp* __restrict__ ops, uint32_t n_ops, Fr* __restrict__ vals) {
+__global__ void __launch_bounds__(128) witness_iszero_values_kernel(const WitnessOp* __restrict__ ops, const uint32_t* __restrict__ idx,
+                                                                    uint32_t n_ops, Fr* __restrict__ vals) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_ops) return;
   Fr af[4], s, na, nd, ld;
-  iszero_values(ops[i], af, s, na, nd, ld);
+  iszero_values(ops[idx[i]], af, s, na, nd, ld);
   s.store(vals + 3 * (size_t)i);
   nd.store(vals + 3 * (size_t)i + 1);
   ld.store(vals + 3 * (size_t)i + 2);
 }
 
 // inv = the batch-inverted values of witness_iszero_values_kernel (zeros stay zero, as BaseGateOps::invert wants)
-__global__ void __launch_bounds__(128) witness_iszero_rows_kernel(const WitnessOp* __restrict__ ops, uint32_t n_ops, const Fr* __restrict__ inv, Cols o) {
+__global__ void __launch_bounds__(128) witness_iszero_rows_kernel(const WitnessOp* __restrict__ ops, const uint32_t* __restrict__ idx,
+                                                                  uint32_t n_ops, const Fr* __restrict__ inv, Cols o) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_ops) return;
-  const WitnessOp& op = ops[i];
+  const WitnessOp& op = ops[idx[i]];
   const bool ca = op.flags & 1;
   uint32_t row = op.row;
   const Fr zero = Fr::zero();
@@ -362,11 +366,27 @@ __global__ void __launch_bounds__(128) witness_iszero_rows_kernel(const WitnessO
   put_row(o, row++, c1, cand, cor, zero, zero);
 }
 
+// idx[off[opc] + j] = index of the j-th record with opcode opc (any order within an opcode).  One atomic per opcode
+// present in a warp: the lanes with the same opcode elect a leader, which reserves their slots.
+__global__ void __launch_bounds__(256) witness_group_kernel(const WitnessOp* __restrict__ ops, uint32_t n_ops, uint32_t* cursor /*[WOP_COUNT], preset to the offsets*/,
+                                                            uint32_t* __restrict__ idx) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i < n_ops;
+  const uint32_t opc = live ? ops[i].opcode : 0xffffffffu;
+  const unsigned peers = __match_any_sync(0xffffffffu, opc);
+  if (!live || opc >= WOP_COUNT) return;
+  const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+  uint32_t base = 0;
+  if (lane == leader) base = atomicAdd(cursor + opc, (uint32_t)__popc(peers));
+  base = __shfl_sync(peers, base, leader);
+  idx[base + __popc(peers & ((1u << lane) - 1))] = i;
+}
+
 template <uint32_t OPC>
-__global__ void __launch_bounds__(128) witness_expand_kernel(const WitnessOp* __restrict__ ops, uint32_t n_ops, Cols o) {
+__global__ void __launch_bounds__(128) witness_expand_kernel(const WitnessOp* __restrict__ ops, const uint32_t* __restrict__ idx, uint32_t n_ops, Cols o) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_ops) return;
-  const WitnessOp& op = ops[i];
+  const WitnessOp& op = ops[idx[i]];
   if (OPC == WOP_RAW128) {
     for (uint32_t r = 0; r < op.aux; r++) {
       const uint64_t* c = op.v + 10 * r;
@@ -393,14 +413,14 @@ __global__ void __launch_bounds__(128) witness_expand_kernel(const WitnessOp* __
 }
 
 template <uint32_t OPC>
-static void launch_expand(h2agg_ctx* ctx, const WitnessOp* ops, size_t n, const Cols& o) {
+static void launch_expand(h2agg_ctx* ctx, const WitnessOp* ops, const uint32_t* idx, size_t n, const Cols& o) {
   if (!n) return;
-  witness_expand_kernel<OPC><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ops, (uint32_t)n, o);
+  witness_expand_kernel<OPC><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ops, idx, (uint32_t)n, o);
   ctx->launches++;
 }
 
-// d_ops: records on the device grouped by opcode (counts[opc] of each, in opcode order); d_cols: 5 device columns of
-// n_rows Fr (zero-filled here: halo2 leaves unassigned advice cells at zero)
+// d_ops: n records on the device in recording order, counts[opc] of each opcode (known to the recorder); d_cols: 5
+// device columns of n_rows Fr (zero-filled here: halo2 leaves unassigned advice cells at zero)
 int witness_expand_dev(h2agg_ctx* ctx, const void* d_ops, const size_t* counts, void* const d_cols[5], size_t n_rows) {
   Cols o;
   for (int c = 0; c < 5; c++) {
@@ -408,30 +428,37 @@ int witness_expand_dev(h2agg_ctx* ctx, const void* d_ops, const size_t* counts, 
     H2AGG_CUDA(ctx, cudaMemsetAsync(d_cols[c], 0, n_rows * 32, ctx->stream));
   }
   o.n_rows = (uint32_t)n_rows;
-  const WitnessOp* seg[WOP_COUNT];
-  size_t at = 0;
+  size_t n_ops = 0;
+  uint32_t off[WOP_COUNT];
   for (uint32_t k = 0; k < WOP_COUNT; k++) {
-    seg[k] = (const WitnessOp*)d_ops + at;
-    at += counts[k];
+    off[k] = (uint32_t)n_ops;
+    n_ops += counts[k];
   }
-  if (!at) return 0;
+  if (!n_ops) return 0;
   const size_t niz = counts[WOP_ISZERO];
-  if (niz) {
-    int rc = ensure(ctx, ctx->wit_ws, niz * 3 * sizeof(Fr));
-    if (rc) return rc;
-  }
+  // scratch: [ index array n_ops x 4 | cursors | values is_zero inverts ]
+  const size_t o_cur = (n_ops * 4 + 255) & ~(size_t)255, o_vals = o_cur + 256;
+  int rc = ensure(ctx, ctx->wit_ws, o_vals + niz * 3 * sizeof(Fr) + 256);
+  if (rc) return rc;
+  uint32_t* idx = (uint32_t*)ctx->wit_ws.p;
+  uint32_t* cursor = (uint32_t*)((uint8_t*)ctx->wit_ws.p + o_cur);
+  Fr* vals = (Fr*)((uint8_t*)ctx->wit_ws.p + o_vals);
+  const WitnessOp* ops = (const WitnessOp*)d_ops;
   ScopedKernelTimer tk(ctx, KC_WITNESS, ctx->stream);
-  launch_expand<WOP_MULEQ>(ctx, seg[WOP_MULEQ], counts[WOP_MULEQ], o);
-  launch_expand<WOP_REDUCE>(ctx, seg[WOP_REDUCE], counts[WOP_REDUCE], o);
-  launch_expand<WOP_RAW128>(ctx, seg[WOP_RAW128], counts[WOP_RAW128], o);
-  launch_expand<WOP_RAW256>(ctx, seg[WOP_RAW256], counts[WOP_RAW256], o);
-  launch_expand<WOP_NATIVE>(ctx, seg[WOP_NATIVE], counts[WOP_NATIVE], o);
+  H2AGG_CUDA(ctx, cudaMemcpyAsync(cursor, off, sizeof(off), cudaMemcpyHostToDevice, ctx->stream));   // (pageable 24 B: staged at once)
+  witness_group_kernel<<<(unsigned)((n_ops + 255) / 256), 256, 0, ctx->stream>>>(ops, (uint32_t)n_ops, cursor, idx);
+  ctx->launches++;
+  launch_expand<WOP_MULEQ>(ctx, ops, idx + off[WOP_MULEQ], counts[WOP_MULEQ], o);
+  launch_expand<WOP_REDUCE>(ctx, ops, idx + off[WOP_REDUCE], counts[WOP_REDUCE], o);
+  launch_expand<WOP_RAW128>(ctx, ops, idx + off[WOP_RAW128], counts[WOP_RAW128], o);
+  launch_expand<WOP_RAW256>(ctx, ops, idx + off[WOP_RAW256], counts[WOP_RAW256], o);
+  launch_expand<WOP_NATIVE>(ctx, ops, idx + off[WOP_NATIVE], counts[WOP_NATIVE], o);
   if (niz) {
-    witness_iszero_values_kernel<<<(unsigned)((niz + 127) / 128), 128, 0, ctx->stream>>>(seg[WOP_ISZERO], (uint32_t)niz, (Fr*)ctx->wit_ws.p);
+    witness_iszero_values_kernel<<<(unsigned)((niz + 127) / 128), 128, 0, ctx->stream>>>(ops, idx + off[WOP_ISZERO], (uint32_t)niz, vals);
     ctx->launches++;
-    int rc = batch_invert_dev(ctx, ctx->wit_ws.p, niz * 3);
+    rc = batch_invert_dev(ctx, vals, niz * 3);
     if (rc) return rc;
-    witness_iszero_rows_kernel<<<(unsigned)((niz + 127) / 128), 128, 0, ctx->stream>>>(seg[WOP_ISZERO], (uint32_t)niz, (const Fr*)ctx->wit_ws.p, o);
+    witness_iszero_rows_kernel<<<(unsigned)((niz + 127) / 128), 128, 0, ctx->stream>>>(ops, idx + off[WOP_ISZERO], (uint32_t)niz, vals, o);
     ctx->launches++;
   }
   H2AGG_CUDA(ctx, cudaGetLastError());

@@ -1,8 +1,8 @@
 // Op records exchanged between the host-side recorder (witness_recorder.cu) and the row-expansion
 // kernel (witness.cu).  One record = one fixed row recipe of halo2-ecc-circuit-lib
 // (SURVEY.md 8a rows W1-W5); `row` is the first advice row it owns, so records are independent
-// and the expansion is embarrassingly parallel.  The recorder keeps one store per opcode, so the device array is
-// grouped by opcode and every recipe runs as its own kernel (its own register budget, no divergence).
+// and the expansion is embarrassingly parallel.  The device groups the records by opcode (index array), so every
+// recipe runs as its own kernel (its own register budget, no divergence).
 #pragma once
 #include <cstdint>
 

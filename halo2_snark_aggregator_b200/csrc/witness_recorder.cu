@@ -274,7 +274,8 @@ static const int OVERFLOW_LIMIT = 64, OVERFLOW_THRESHOLD = 32;
 
 
 // ---- op-record storage: fixed-size chunks, page-locked when a device context exists ------------------------------
-// Records are only ever appended and later streamed to the GPU, so they live in 2 MiB chunks carved from page-locked
+// Records are only ever appended and later streamed to the GPU, so they live in 2 MiB chunks (one section of a
+// multi_exp recorded on its own thread is ~1.7 MB of records: one chunk) carved from page-locked
 // slabs (cudaHostAlloc, portable) once some h2agg_ctx exists in the process -- the H2D copy of a 2^21-row witness is
 // ~110 MB and runs at PCIe speed from pinned memory, at a fraction of it from pageable memory.  Without a device
 // (recording only: the CPU tests) chunks are plain heap memory.  Chunks go back to a process-wide pool.
@@ -344,19 +345,17 @@ struct OpChunk {
   uint32_t n = 0;
   bool pinned = false;
 };
-struct OpStore {  // one chunk list per opcode: the device array comes out grouped by recipe
-  std::vector<OpChunk> chunks[WOP_COUNT];
+struct OpStore {  // records in arrival order; only the per-opcode COUNTS are kept apart (the device groups the records)
+  std::vector<OpChunk> chunks;
   size_t count[WOP_COUNT] = {0, 0, 0, 0, 0, 0};
   OpStore() = default;
   OpStore(const OpStore&) = delete;
   OpStore& operator=(const OpStore&) = delete;
   ~OpStore() { clear(); }
   void clear() {
-    for (uint32_t k = 0; k < WOP_COUNT; k++) {
-      for (auto& c : chunks[k]) chunk_pool().put(c.p, c.pinned);
-      chunks[k].clear();
-      count[k] = 0;
-    }
+    for (auto& c : chunks) chunk_pool().put(c.p, c.pinned);
+    chunks.clear();
+    for (uint32_t k = 0; k < WOP_COUNT; k++) count[k] = 0;
   }
   size_t size() const {
     size_t t = 0;
@@ -364,26 +363,24 @@ struct OpStore {  // one chunk list per opcode: the device array comes out group
     return t;
   }
   void push_back(const WitnessOp& op) {
-    std::vector<OpChunk>& ch = chunks[op.opcode];
-    if (ch.empty() || ch.back().n == CHUNK_OPS) {
+    if (chunks.empty() || chunks.back().n == CHUNK_OPS) {
       OpChunk c;
       c.p = chunk_pool().get(&c.pinned);
-      ch.push_back(c);
+      chunks.push_back(c);
     }
-    OpChunk& c = ch.back();
+    OpChunk& c = chunks.back();
     c.p[c.n++] = op;
     count[op.opcode]++;
   }
   void add_to_rows(uint32_t delta) {  // rows recorded relative to a tag become absolute (mod 2^32 arithmetic)
-    for (uint32_t k = 0; k < WOP_COUNT; k++)
-      for (auto& c : chunks[k])
-        for (uint32_t i = 0; i < c.n; i++) c.p[i].row += delta;
+    for (auto& c : chunks)
+      for (uint32_t i = 0; i < c.n; i++) c.p[i].row += delta;
   }
   void absorb(OpStore& o) {  // take over the chunks of a child store (no copies)
+    for (auto& c : o.chunks) chunks.push_back(c);
+    o.chunks.clear();
     for (uint32_t k = 0; k < WOP_COUNT; k++) {
-      for (auto& c : o.chunks[k]) chunks[k].push_back(c);
       count[k] += o.count[k];
-      o.chunks[k].clear();
       o.count[k] = 0;
     }
   }
@@ -1541,15 +1538,15 @@ int h2agg_wit_point_value(h2agg_witness* w, int64_t h, uint64_t out_xy[8], int* 
 
 }  // extern "C"
 
-// record chunks -> one contiguous device array (the order of records is irrelevant: each names its own rows)
+// record chunks -> one contiguous device array in arrival order (each record names its own rows; the device groups
+// them by opcode through an index array, witness.cu)
 static int upload_ops(h2agg_ctx* ctx, const OpStore& ops) {
   size_t at = 0;
-  for (uint32_t k = 0; k < WOP_COUNT; k++)
-    for (const OpChunk& c : ops.chunks[k]) {
-      if (!c.n) continue;
-      H2AGG_CUDA(ctx, cudaMemcpyAsync((uint8_t*)ctx->io_a.p + at * sizeof(WitnessOp), c.p, (size_t)c.n * sizeof(WitnessOp), cudaMemcpyHostToDevice, ctx->stream));
-      at += c.n;
-    }
+  for (const OpChunk& c : ops.chunks) {
+    if (!c.n) continue;
+    H2AGG_CUDA(ctx, cudaMemcpyAsync((uint8_t*)ctx->io_a.p + at * sizeof(WitnessOp), c.p, (size_t)c.n * sizeof(WitnessOp), cudaMemcpyHostToDevice, ctx->stream));
+    at += c.n;
+  }
   return 0;
 }
 
