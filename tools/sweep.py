@@ -147,6 +147,23 @@ def main():
             out = ctx.d2h(d_o + 160, 40).reshape(2, 20)
             rec["msm_halves_add_up_to_the_sharded_result"] = bool(np.array_equal(ob.g1_sum(np.concatenate([out[0, 8:], out[1, 8:]])), got[8:]))
         rec["msm_ms"] = timed(msm_step, reps)
+        # ---- the same MSM on the witness-like mixture (a0..a3-like cells -- 70 % 17-bit, 10 % {0,1},
+        # 20 % zero -- ending in 6 full-width blinding rows as real halo2 columns do)
+        ctx.synth_scalars_dev(0xA770000 + k, 1, 0, n, d_s)
+        if n > 6:
+            ctx.synth_scalars_dev(0xA780000 + k, 0, 0, 6, d_s + 32 * (n - 6))
+        msm_step()
+        ctx.synchronize()
+        got_w = ctx.d2h(t_sum.data_ptr(), 20)
+        if use_oracle:
+            s_host, b_host = ctx.d2h(d_s, 4 * n), ctx.d2h(d_b, 8 * n)
+            t0 = time.perf_counter()
+            want = ob.best_multiexp(s_host, b_host, cores)
+            if k <= args.cpu_kmax:
+                rec["cpu_best_multiexp_witness_like_s"] = time.perf_counter() - t0
+            rec["msm_witness_like_equals_oracle"] = bool(np.array_equal(got_w[8:], want))
+            del s_host, b_host
+        rec["msm_witness_like_ms"] = timed(msm_step, reps)
         rec["msm_mode"] = {"table": bool(table), "window_bits": c, "windows": nwin, "my_windows": list(shard)}
         rec["msm_pairs_per_s"] = n / (rec["msm_ms"] * 1e-3)
         rec["msm_hbm_gbs"] = (96.0 * n + 96) / (rec["msm_ms"] * 1e-3) / 1e9
