@@ -62,6 +62,12 @@ class ResidentProver {
   ResidentProver(const ResidentProver&) = delete;
   ResidentProver& operator=(const ResidentProver&) = delete;
 
+  // Deferred transforms (h2agg_set_defer_transforms): the NTT passes of every commit round run on the context's
+  // background stream and fill the latency-bound stretches of the following rounds; they are joined where the quotient /
+  // the evaluation round / the opening first read a coefficient or extended form.  On by default, like the Python twin.
+  bool defer_transforms = true;
+  void join_transforms() { c_.check(h2agg_transforms_join(c_.raw())); }
+
   size_t usable_rows() const { return n_ - (s_.blinding_factors + 1); }
   void* lagrange(uint32_t id) { return slot(lag_, id, n_ * 32); }
   void* coeff(uint32_t id) { return slot(coeff_, id, n_ * 32); }
@@ -75,11 +81,12 @@ class ResidentProver {
     std::vector<void*> lo, co, eo;
     for (size_t i = 0; i < ids.size(); i++) {
       src.push_back(reinterpret_cast<const uint64_t*>(cols[i]));
-      lo.push_back(keep_lagrange ? lagrange(ids[i]) : nullptr);
+      lo.push_back((keep_lagrange || defer_transforms) ? lagrange(ids[i]) : nullptr);   // deferred passes read the column later
       co.push_back(coeff(ids[i]));
       eo.push_back(with_extended ? extended(ids[i]) : nullptr);
     }
     std::vector<G1Affine> out(ids.size());
+    Deferred scope(*this);
     c_.check(h2agg_commit_round_resident(c_.raw(), gl_, src.data(), ids.size(), s_.k, s_.omega_inv.l, s_.n_inv.l,
                                          reinterpret_cast<uint64_t*>(out.data()), lo.data(), co.data(), with_extended ? s_.ext_k : 0,
                                          with_extended ? s_.zeta.l : nullptr, with_extended ? s_.omega_ext.l : nullptr,
@@ -97,6 +104,7 @@ class ResidentProver {
       eo.push_back(extended(id));
     }
     std::vector<G1Affine> out(ids.size());
+    Deferred scope(*this);
     c_.check(h2agg_commit_round_dev(c_.raw(), gl_, src.data(), ids.size(), s_.k, s_.omega_inv.l, s_.n_inv.l,
                                     reinterpret_cast<uint64_t*>(out.data()), co.data(), s_.ext_k, s_.zeta.l, s_.omega_ext.l, eo.data()));
     return out;
@@ -187,6 +195,7 @@ class ResidentProver {
       if (it == ext_.end()) throw std::logic_error("quotient: column " + std::to_string(id) + " has no extended form yet");
       cols.push_back(it->second);
     }
+    join_transforms();
     void* h = scratch(KEY_H, ext_n_ * 32);
     h2agg_quotient_args a;
     memset(&a, 0, sizeof(a));
@@ -225,6 +234,7 @@ class ResidentProver {
 
   // points: rotation -> x * omega^rotation.  One batched call per opening point; results in query order
   std::vector<Fr> evaluate(const std::vector<Query>& queries, const std::map<int32_t, Fr>& points) {
+    join_transforms();
     void* d_ev = scratch(KEY_EVALS, 32 * std::max<size_t>(queries.size(), 1));
     std::map<int32_t, std::vector<size_t>> groups;
     for (size_t i = 0; i < queries.size(); i++) groups[queries[i].rotation].push_back(i);
@@ -247,6 +257,7 @@ class ResidentProver {
   // (The constant eval_batch halo2 subtracts only changes the remainder kate_division drops.)
   std::vector<G1Affine> open(const std::vector<Query>& queries, const std::map<int32_t, Fr>& points, const Fr& v,
                              std::vector<int32_t>* order_out = nullptr) {
+    join_transforms();
     std::vector<int32_t> order;
     std::map<int32_t, std::vector<const void*>> groups;
     for (const Query& q : queries) {
@@ -270,6 +281,16 @@ class ResidentProver {
   }
 
  private:
+  // scope of a commit round issued with deferred transforms (the setting is per context, so it is switched on only here)
+  struct Deferred {
+    ResidentProver& p;
+    explicit Deferred(ResidentProver& pr) : p(pr) {
+      if (p.defer_transforms) h2agg_set_defer_transforms(p.c_.raw(), 1);
+    }
+    ~Deferred() {
+      if (p.defer_transforms) h2agg_set_defer_transforms(p.c_.raw(), 0);
+    }
+  };
   enum : uint64_t { KEY_H = 1, KEY_H_FOLDED, KEY_EVALS, KEY_FOLD, KEY_PTS, KEY_W = 100, KEY_COMPRESSED = 1000 };
   static uint64_t key_compressed(size_t lookup, int side) { return KEY_COMPRESSED + 2 * lookup + side; }
 

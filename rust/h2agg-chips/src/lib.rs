@@ -29,6 +29,7 @@ pub struct h2agg_witness {
 
 extern "C" {
     fn h2agg_wit_new() -> *mut h2agg_witness;
+    fn h2agg_wit_set_threads(n: c_int) -> c_int; // host threads a multi_exp records its independent sections on
     fn h2agg_wit_free(w: *mut h2agg_witness);
     fn h2agg_wit_error(w: *mut h2agg_witness) -> *const c_char;
     fn h2agg_wit_rows(w: *mut h2agg_witness) -> u64;

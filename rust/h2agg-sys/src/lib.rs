@@ -29,6 +29,13 @@ extern "C" {
     pub fn h2agg_kate_division(ctx: *mut h2agg_ctx, a: *const u64, n: usize, b: *const u64, q: *mut u64) -> c_int;
     pub fn h2agg_permute_expression_pair(ctx: *mut h2agg_ctx, input: *const u64, table: *const u64, usable_rows: usize, permuted_input: *mut u64, permuted_table: *mut u64) -> c_int;
     pub fn h2agg_commit_round_resident(ctx: *mut h2agg_ctx, srs_id: u64, lagrange_cols: *const *const u64, n_cols: usize, k: u32, omega_inv: *const u64, n_inv: *const u64, out_affine: *mut u64, d_lagrange_out: *const *mut c_void, d_coeff_out: *const *mut c_void, ext_k: u32, zeta: *const u64, omega_ext: *const u64, d_ext_out: *const *mut c_void) -> c_int;
+    // deferred transforms: the NTT passes of a commit round on the background stream, joined before the quotient /
+    // evaluation round reads a coefficient or extended form (include/h2agg.h)
+    pub fn h2agg_set_defer_transforms(ctx: *mut h2agg_ctx, enable: c_int) -> c_int;
+    pub fn h2agg_transforms_join(ctx: *mut h2agg_ctx) -> c_int;
+    pub fn h2agg_transforms_dev(ctx: *mut h2agg_ctx, d_lagrange_cols: *const *const c_void, n_cols: usize, k: u32, omega_inv: *const u64, n_inv: *const u64, d_coeff_out: *const *mut c_void, ext_k: u32, zeta: *const u64, omega_ext: *const u64, d_ext_out: *const *mut c_void) -> c_int;
+    // multi-GPU: a window range per column in one batched call (window-sharded MSMs beside whole ones)
+    pub fn h2agg_msm_g1_batch_ranges_dev(ctx: *mut h2agg_ctx, srs_id: u64, d_bases: *const c_void, d_cols: *const *const c_void, n_cols: usize, n: usize, win_begins: *const c_int, win_ends: *const c_int, d_out160s: *mut c_void) -> c_int;
 }
 
 struct Ctx(*mut h2agg_ctx);
