@@ -71,26 +71,53 @@ __global__ void ntt_gen_tables(Fr omega, uint32_t lo_bits, uint32_t hi_bits, Fr*
   }
 }
 
+// ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) completing on an mbarrier: the tile load of the last pass ------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t arrivals) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(arrivals) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+
 template <bool LAST>
 __global__ void __launch_bounds__(NTT_THREADS, 3) ntt_pass_kernel(const __grid_constant__ NttPassArgs p) {
   extern __shared__ uint4 smem[];
   const uint32_t s = p.s, R = 1u << s, cbits = p.cbits, C = 1u << cbits, E = R << cbits;
-  const uint32_t rs = LAST ? 1u : C;
-  const uint32_t cs = LAST ? (R + 1) : 1u;
+  // Last pass of a multi-pass transform: every column of the tile is ONE contiguous run of R x 32 bytes in HBM, so the
+  // tile comes in as C bulk copies (cp.async.bulk -> UBLKCP, completion on an mbarrier) issued by one thread: no
+  // LDG -> register -> STS round trip, no address arithmetic per element.  The elements then sit in shared memory as
+  // they do in HBM (32-byte elements, lo half | hi half), column c at c * (2R + 1) 16-byte units: the odd pitch keeps
+  // the eight columns a quarter-warp reads on distinct bank groups.  Other passes keep two 16-byte planes.
+  const bool bulk = LAST && p.npass > 1;
+  const uint32_t rs = LAST ? (bulk ? 2u : 1u) : C;
+  const uint32_t cs = LAST ? (bulk ? 2 * R + 1 : R + 1) : 1u;
   const uint32_t plane = LAST ? C * (R + 1) : E;
   uint4* xl = smem;
-  uint4* xh = smem + plane;
+  uint4* xh = bulk ? smem + 1 : smem + plane;
   uint4* twl = smem + 2 * plane;  // stage twiddles w_R^m, m < R/2 (two 16-byte planes)
   uint4* twh = twl + (R >> 1);
+  __shared__ __align__(8) uint64_t tile_bar;
   const uint32_t tid = threadIdx.x;
   const unsigned long long tile = blockIdx.x;
-
-  // ---- stage twiddles: w_R^m = w_N^(m * N/R)
-  for (uint32_t m = tid; m < (R >> 1); m += NTT_THREADS) {
-    Fr w = get_tw(p.t_lo, p.t_hi, p.lo_bits, m << (p.log_n - s));
-    twl[m] = w.lo4();
-    twh[m] = w.hi4();
-  }
 
   // ---- tile coordinates
   unsigned long long base;  // position of (row 0, col 0)
@@ -115,6 +142,24 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) ntt_pass_kernel(const __grid_c
   // input): they are neither loaded nor computed -- after the bit reversal the first `zskip` DIT
   // stages degenerate to copies, so each loaded value is replicated 2^zskip times instead.
   const uint32_t zs = LAST ? 0u : p.zskip;
+  if (bulk && tid == 0) {   // the copies are in flight while the CTA stages its twiddles
+    mbar_init(&tile_bar, 1);
+    mbar_arrive_expect_tx(&tile_bar, E * 32);
+    for (uint32_t c = 0; c < C; c++) {
+      const unsigned long long pos0 = ((((unsigned long long)(j0 + c)) << log_q) + rest) << s;   // row 0 of column c
+      bulk_g2s(smem + (size_t)c * cs, p.src + 2 * pos0, R * 32, &tile_bar);
+    }
+  }
+  // ---- stage twiddles: w_R^m = w_N^(m * N/R)
+  for (uint32_t m = tid; m < (R >> 1); m += NTT_THREADS) {
+    Fr w = get_tw(p.t_lo, p.t_hi, p.lo_bits, m << (p.log_n - s));
+    twl[m] = w.lo4();
+    twh[m] = w.hi4();
+  }
+  if (bulk) {
+    __syncthreads();          // the barrier's initialisation is visible to every waiter
+    mbar_wait(&tile_bar, 0);
+  } else {
 #pragma unroll 4
   for (uint32_t idx = tid; idx < (E >> zs); idx += NTT_THREADS) {
     uint32_t r, c;
@@ -150,6 +195,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) ntt_pass_kernel(const __grid_c
       xl[si] = v.lo4();
       xh[si] = v.hi4();
     }
+  }
   }
 
   // ---- butterfly stages in shared memory, two at a time (radix-4 in registers): a thread owns the
