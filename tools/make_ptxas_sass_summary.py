@@ -1,0 +1,90 @@
+#!/usr/bin/env python3
+"""Static evidence table: ptxas resource usage (-Xptxas -v) + SASS instruction mix (cuobjdump -sass) of every kernel in
+libh2agg.so.  usage: python tools/make_ptxas_sass_summary.py <tag>  -> profiles/<tag>_ptxas_sass.md (run in the build
+container; recompiles every translation unit into a scratch directory, the in-tree objects are left alone)."""
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as g
+
+tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
+tmp = tempfile.mkdtemp(prefix="h2agg_ptxas_")
+rows = {}
+
+
+def demangle(names):
+    out = subprocess.check_output(["c++filt"], input="\n".join(names), text=True).split("\n")
+    return [re.sub(r"\(.*", "", o).replace("void ", "").replace("h2agg::", "") for o in out]
+
+
+for src in g.SOURCES:
+    obj = os.path.join(tmp, src[:-3] + ".o")
+    cmd = [os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")] + g.NVCC_FLAGS + ["-Xptxas", "-v", "-c", "-o", obj, os.path.join(g.CSRC, src)]
+    err = subprocess.run(cmd, cwd=g.CSRC, capture_output=True, text=True).stderr
+    cur = None
+    for line in err.split("\n"):
+        m = re.search(r"Compiling entry function '(\S+)'", line)
+        if m:
+            cur = m.group(1)
+            rows[cur] = {"file": src}
+            continue
+        if cur is None:
+            continue
+        m = re.search(r"(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads", line)
+        if m:
+            rows[cur].update(stack=int(m.group(1)), st=int(m.group(2)), ld=int(m.group(3)))
+        m = re.search(r"Used (\d+) registers", line)
+        if m:
+            rows[cur]["regs"] = int(m.group(1))
+    sass = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True).stdout
+    fn = None
+    for line in sass.split("\n"):
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            fn = m.group(1)
+            rows.setdefault(fn, {"file": src})
+            rows[fn].update(n=0, wide=0, imad=0, ldg=0, lds=0, tma=0, tc=0)
+            continue
+        if fn is None or "/*" not in line:
+            continue
+        m = re.search(r"\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
+        if not m:
+            continue
+        op = m.group(1)
+        r = rows[fn]
+        r["n"] += 1
+        if op.startswith("IMAD.WIDE"):
+            r["wide"] += 1
+        elif op.startswith("IMAD"):
+            r["imad"] += 1
+        elif op.startswith("LDG"):
+            r["ldg"] += 1
+        elif op.startswith(("LDS", "STS")):
+            r["lds"] += 1
+        elif op.startswith(("UBLKCP", "UTMA", "SYNCS")):
+            r["tma"] += 1
+        elif op.startswith(("HMMA", "UTCMMA", "UTCHMMA", "IMMA", "QMMA")):
+            r["tc"] += 1
+
+names = list(rows)
+nice = demangle(names)
+lines = ["# Static evidence, round 2: ptxas resource usage and SASS instruction mix (sm_100a, nvcc 12.9, `-O3 -lineinfo`)", "",
+         "Produced in the build container by `tools/make_ptxas_sass_summary.py %s` (`nvcc -Xptxas -v`, `cuobjdump -sass`) on the final sources of the round." % tag,
+         "TMA column = `UBLKCP` (cp.async.bulk) + `SYNCS.*` (mbarrier transaction arrive / try-wait) instructions; no tensor-core instruction anywhere:",
+         "the work is 256-bit modular integer arithmetic and `IMAD.WIDE.U32` on the fmaheavy pipe is the multiplier (DESIGN.md section 4).", ""]
+spilled = ["`%s` (%d B st / %d B ld)" % (nm, rows[k]["st"], rows[k]["ld"]) for k, nm in zip(names, nice) if rows[k].get("st") or rows[k].get("ld")]
+lines.append("Kernels with register spills: " + (", ".join(spilled) if spilled else "none") + ".")
+lines += ["", "| file | kernel | registers | stack B | spill st/ld B | SASS instrs | IMAD.WIDE | IMAD + IMAD.HI | LDG | LDS+STS | TMA (UBLKCP + SYNCS) | tensor core |", "|---|---|---|---|---|---|---|---|---|---|---|---|"]
+for k, nm in sorted(zip(names, nice), key=lambda kn: (rows[kn[0]]["file"], kn[1])):
+    r = rows[k]
+    lines.append("| %s | `%s` | %s | %s | %s / %s | %s | %s | %s | %s | %s | %s | %s |" % (
+        r["file"], nm, r.get("regs", ""), r.get("stack", ""), r.get("st", ""), r.get("ld", ""), r.get("n", ""), r.get("wide", ""), r.get("imad", ""),
+        r.get("ldg", ""), r.get("lds", ""), r.get("tma", ""), r.get("tc", "")))
+path = os.path.join(ROOT, "profiles", "%s_ptxas_sass.md" % tag)
+open(path, "w").write("\n".join(lines) + "\n")
+print("wrote", path, len(rows), "kernels")
