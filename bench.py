@@ -64,14 +64,14 @@ BLIND_ROWS = 6  # every committed halo2 column ends in blinding_factors + 1 full
 # k = 22, from the `ncu --set full --clock-control none` captures summarised under profiles/ (bench.py never runs under a
 # profiler; these are the committed numbers of the capture named in `note`).
 NCU = {
-    "msm_accumulate": {"dram_bytes": 7371500000, "fmaheavy_pct": 86.5,
-                       "note": "profiles/r01_ncu_summary.md (r01e capture): 7.246 GB read + 0.126 GB written per launch on a uniform 2^22 column in table mode vs 0.403 GB algorithmic -- the gather of 54.5 M precomputed 64-byte points is by design (HBM bytes traded for multiplier instructions); L2 serves 19.6 % of it"},
-    "ntt_pass_intt": {"dram_bytes": 290000000, "fmaheavy_pct": 74.2,
-                      "note": "profiles/r01_ncu_summary.md: iNTT 2^22 passes move 0.44 / 0.21 / 0.22 GB (avg 0.29) vs 0.27 GB algorithmic per pass; the first pass also streams the 128 MiB inter-pass twiddle table"},
-    "ntt_pass_coset": {"dram_bytes": 1387000000, "fmaheavy_pct": 78.7,
-                       "note": "profiles/r01_ncu_summary.md: coset NTT 2^22 -> 2^24 passes move 2.12 / 1.02 / 1.03 GB (avg 1.39) vs 0.94 GB algorithmic per pass; the first pass also streams the 512 MiB inter-pass twiddle table"},
-    "quot_evaluate_h": {"dram_bytes": 34766000000, "fmaheavy_pct": 82.5,
-                        "note": "profiles/r01_ncu_summary.md: 32.03 GB read + 2.74 GB written vs 30.1 GB algorithmic (55 columns + h, 512 MiB each): every column is read once, rotations hit L2"},
+    "msm_accumulate": {"dram_bytes": 7366000000, "fmaheavy_pct": 86.6,
+                       "note": "profiles/r02_ncu_summary.md (r02 capture): 7.243 GB read + 0.123 GB written per launch on a uniform 2^22 column in table mode vs 0.403 GB algorithmic -- the gather of 54.5 M precomputed 64-byte points is by design (HBM bytes traded for multiplier instructions); L2 serves 19.5 % of it"},
+    "ntt_pass_intt": {"dram_bytes": 291000000, "fmaheavy_pct": 74.5,
+                      "note": "profiles/r02_ncu_summary.md: iNTT 2^22 passes move 0.44 / 0.21 / 0.22 GB (avg 0.29) vs 0.27 GB algorithmic per pass; the first pass also streams the 128 MiB inter-pass twiddle table; fmaheavy 72.1 / 73.2 / 78.2 % (the last pass loads its tile with TMA bulk copies)"},
+    "ntt_pass_coset": {"dram_bytes": 1387000000, "fmaheavy_pct": 79.4,
+                       "note": "profiles/r02_ncu_summary.md: coset NTT 2^22 -> 2^24 passes move 2.12 / 1.02 / 1.02 GB (avg 1.39) vs 0.94 GB algorithmic per pass; the first pass also streams the 512 MiB inter-pass twiddle table (32-byte gathers); fmaheavy 80.0 / 78.4 / 79.8 %"},
+    "quot_evaluate_h": {"dram_bytes": 30561000000, "fmaheavy_pct": 82.4,
+                        "note": "profiles/r02_ncu_summary.md: 30.02 GB read + 0.54 GB written vs 30.1 GB algorithmic (55 columns + h, 512 MiB each): every column is read once, rotations hit L2; 126 registers, no spills"},
 }
 
 
