@@ -106,7 +106,7 @@ class DistributedProver:
 
     def _pool_msm(self, items):
         """items: [(device pointer of n scalars, srs id, n windows)] present on EVERY rank -> affine commitments (len, 8).
-        The window units of all items are cut into `world` contiguous ranges (parallel.window_units); everything this
+        The window units of all items are cut into `world` contiguous ranges (parallel.pooled_window_ranges); everything this
         rank owes goes out in ONE batched call per SRS with a window range per column (h2agg_msm_g1_batch_ranges_dev),
         so the latency-bound ends of one shard run beside the accumulation of the next; one all-gather + local add + one
         read-back for the whole list."""
@@ -117,14 +117,9 @@ class DistributedProver:
         d_part = self._buf(("pool_part", m), m * 160)
         self.tensor(d_part, m * 160).zero_()
         # the window units are laid out item after item; items may differ in their window count (two SRS forms)
-        total = sum(it[2] for it in items)
-        lo, hi = total * self.rank // self.world, total * (self.rank + 1) // self.world
-        by_srs, base = {}, 0
-        for i, (ptr, srs, nwin) in enumerate(items):
-            w0, w1 = max(lo, base) - base, min(hi, base + nwin) - base
-            if w1 > w0:
-                by_srs.setdefault(srs, []).append((i, w0, w1, nwin))
-            base += nwin
+        by_srs = {}
+        for (i, w0, w1) in par.pooled_window_ranges([it[2] for it in items], self.world, self.rank):
+            by_srs.setdefault(items[i][1], []).append((i, w0, w1, items[i][2]))
         d_stage = self._buf(("pool_stage", m), m * 160)
         for srs, mine in sorted(by_srs.items()):
             wins = [None if (w0 == 0 and w1 == nwin) else (w0, w1) for (_, w0, w1, nwin) in mine]

@@ -242,6 +242,22 @@ def window_units(n_items, n_windows, world):
     return out
 
 
+def pooled_window_ranges(item_windows, world, rank):
+    """The window units of a list of pooled MSMs (item i has item_windows[i] windows; the two SRS forms may differ) laid
+    out item after item and cut into `world` contiguous ranges: -> [(item, win_begin, win_end)] of `rank`.  Every window of
+    every item belongs to exactly one rank, ranks differ by at most one window, an item is cut at most
+    ceil(world / len(items)) + 1 times."""
+    total = sum(item_windows)
+    lo, hi = total * rank // world, total * (rank + 1) // world
+    out, base = [], 0
+    for i, nwin in enumerate(item_windows):
+        w0, w1 = max(lo, base) - base, min(hi, base + nwin) - base
+        if w1 > w0:
+            out.append((i, w0, w1))
+        base += nwin
+    return out
+
+
 def prover_plan(n_witness, n_lookups, n_perm_sets, world, cost=None):
     """Who does what in the column-parallel rounds of the multi-GPU prover.  Everything here is a pure function of the
     circuit shape and the world size, so every rank computes the same plan without talking.

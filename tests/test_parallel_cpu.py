@@ -237,3 +237,22 @@ def test_plan_phase_covers_every_window_once_and_uses_the_fixed_cost_model():
     # 4 MSMs on 8 ranks: two shards each, disjoint rank pairs
     plan = check([0] * 4, [], 8)
     assert sorted(r for u, r, w in plan) == list(range(8))
+
+
+def test_pooled_window_ranges_tile_every_item_exactly_once():
+    from halo2_snark_aggregator_b200 import parallel as par
+
+    for item_windows in ([13], [13, 13], [13, 13, 13, 13], [13, 13, 12], [16] * 9, [5]):
+        for world in (1, 2, 3, 4, 8):
+            cover = {i: [] for i in range(len(item_windows))}
+            sizes = []
+            for rank in range(world):
+                mine = par.pooled_window_ranges(item_windows, world, rank)
+                sizes.append(sum(w1 - w0 for _, w0, w1 in mine))
+                for i, w0, w1 in mine:
+                    assert 0 <= w0 < w1 <= item_windows[i]
+                    cover[i].append((w0, w1))
+            assert max(sizes) - min(sizes) <= 1
+            for i, ws in cover.items():
+                ws.sort()
+                assert ws[0][0] == 0 and ws[-1][1] == item_windows[i] and all(a[1] == b[0] for a, b in zip(ws, ws[1:]))
