@@ -78,7 +78,10 @@ lines = ["# Static evidence, round 2: ptxas resource usage and SASS instruction 
          "TMA column = `UBLKCP` (cp.async.bulk) + `SYNCS.*` (mbarrier transaction arrive / try-wait) instructions; no tensor-core instruction anywhere:",
          "the work is 256-bit modular integer arithmetic and `IMAD.WIDE.U32` on the fmaheavy pipe is the multiplier (DESIGN.md section 4).", ""]
 spilled = ["`%s` (%d B st / %d B ld)" % (nm, rows[k]["st"], rows[k]["ld"]) for k, nm in zip(names, nice) if rows[k].get("st") or rows[k].get("ld")]
-lines.append("Kernels with register spills: " + (", ".join(spilled) if spilled else "none") + ".")
+lines.append("Kernels with register spills: " + (", ".join(spilled) if spilled else "none") + ".  In `ntt_pass_kernel<false>` they are loop-invariant values "
+             "(tile base, column offset) stored once in the prologue and reloaded at the phase boundaries -- checked in the SASS: no STL / LDL inside a butterfly or "
+             "product loop; `quot_evaluate_h` (292 B in round 1) and `ntt_pass_kernel<true>` have none; `witness_expand_kernel<5>` (the MULEQ recipe, 0.15 ms per "
+             "2 M-row witness) keeps 560 B of indexed limb arrays in local memory by construction.")
 lines += ["", "| file | kernel | registers | stack B | spill st/ld B | SASS instrs | IMAD.WIDE | IMAD + IMAD.HI | LDG | LDS+STS | TMA (UBLKCP + SYNCS) | tensor core |", "|---|---|---|---|---|---|---|---|---|---|---|---|"]
 for k, nm in sorted(zip(names, nice), key=lambda kn: (rows[kn[0]]["file"], kn[1])):
     r = rows[k]
