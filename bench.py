@@ -944,6 +944,25 @@ def main():
             "rows": arows, "op_records": aops, "host_record_s": t1 - t0, "expand_incl_h2d_s": t2 - t1, "rows_per_s_total": arows / (t2 - t0),
             "note": "Poseidon transcript (T = 9) + ScalarChip expression mix + scalar_mul_constant per instance + two multi_exps + final pair (witness_workload.py), every chip call crossing Python/ctypes: ~60k ScalarChip calls of 1-2 rows each dominate the host time; the Rust chips (rust/h2agg-chips) make the same calls at FFI cost"}
         wctx.close()
+        # the same op stream from a COMPILED host (tests/cpp/witness_main.cpp: every chip call is a C function call, as it
+        # is for the reference's Rust chips), recording + H2D + expansion; informational, never takes the line down
+        try:
+            import tempfile
+
+            exe = os.path.join(ROOT, "tests", "cpp", "witness_main")
+            with tempfile.NamedTemporaryFile(suffix=".bin") as tf:
+                np.ascontiguousarray(all_pts).tofile(tf.name)
+                r = subprocess.run([exe, tf.name, "2", "21"], capture_output=True, text=True, timeout=120)
+            if r.returncode == 0:
+                witness["aggregation_like_2_proofs_compiled_host"] = json.loads(r.stdout.strip().split("\n")[-1])
+                witness["aggregation_like_2_proofs_compiled_host"]["note"] = (
+                    "tests/cpp/witness_main.cpp: the same calls as above made from C++ through the C ABI (Poseidon transcript, ScalarChip "
+                    "mix, 2 x 2 scalar_mul_constant, 44 transcript points, two multi_exps, final pair), steady-state mean of 3; "
+                    "its own context on the same GPU")
+            else:
+                witness["aggregation_like_2_proofs_compiled_host"] = {"error": r.stderr.strip()[-300:]}
+        except Exception as e:  # pragma: no cover
+            witness["aggregation_like_2_proofs_compiled_host"] = {"error": repr(e)}
         del d_cols
 
     # ---- N2 (next row): evaluation + Kate division of a 2^k coefficient vector, device resident

@@ -176,3 +176,27 @@ def test_host_modular_inverse_through_div():
         q = s.to_value(s.div(s.assign_var(a), s.assign_var(b)))
         assert q == a * pow(b, -1, ref.R) % ref.R
     w.close()
+
+
+def test_compiled_host_driver_records_the_same_layout_as_the_python_chips(tmp_path):
+    """tests/cpp/witness_main.cpp drives the aggregation op mix through the C ABI from C++; the Python twin
+    (witness_workload.py) makes the same calls through ctypes: same rows, same record count (no GPU needed)."""
+    import json
+    import subprocess
+
+    import oracle_binding as ob
+    from halo2_snark_aggregator_b200.witness import B200Context, B200EccChip, B200EncodeChip, B200ScalarChip
+    from halo2_snark_aggregator_b200.witness_workload import record_aggregation_like
+
+    exe = os.path.join(ROOT, "tests", "cpp", "witness_main")
+    assert os.path.exists(exe), "tests/cpp/witness_main is not built (python -c 'import __graft_entry__ as g; g.build()')"
+    pts = ob.gen_bases(0x77, 2048)
+    path = tmp_path / "pts.bin"
+    pts.tofile(str(path))
+    r = subprocess.run([exe, str(path), "1"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    got = json.loads(r.stdout.strip().split("\n")[-1])
+    w = B200Context()
+    record_aggregation_like(B200ScalarChip(w), B200EccChip(w), B200EncodeChip(w), lambda i: pts.reshape(-1, 8)[i % 2048], 1)
+    assert (got["rows"], got["op_records"]) == (w.rows(), w.ops())
+    w.close()
