@@ -1394,6 +1394,10 @@ int64_t h2agg_wit_ecc_mul(h2agg_witness* w, int64_t a, int64_t s) {
 }
 // ArithEccChip::multi_exp -> EccChipOps::shamir (halo2-snark-aggregator-circuit/src/chips/ecc_chip.rs:125-132)
 int64_t h2agg_wit_ecc_shamir(h2agg_witness* w, const int64_t* pts, const int64_t* scalars, size_t n) {
+  if (n == 0 || !pts || !scalars) {  // the reference indexes windows_in_be[0]: a multi_exp of nothing panics there
+    w->err = "multi_exp: no points";
+    return -1;
+  }
   WIT_TRY(w, {
     std::vector<HPoint> p;
     std::vector<HScalar> s;

@@ -200,3 +200,15 @@ def test_compiled_host_driver_records_the_same_layout_as_the_python_chips(tmp_pa
     record_aggregation_like(B200ScalarChip(w), B200EccChip(w), B200EncodeChip(w), lambda i: pts.reshape(-1, 8)[i % 2048], 1)
     assert (got["rows"], got["op_records"]) == (w.rows(), w.ops())
     w.close()
+
+
+def test_recorder_rejects_an_empty_multi_exp_and_bad_handles():
+    chip = h2.B200EccChip()
+    with pytest.raises(h2.H2aggError):
+        chip.multi_exp([], [])
+    p = chip.assign_var(ws.xy_mont(ref.G1_GEN))
+    with pytest.raises(h2.H2aggError):
+        chip.multi_exp([p], [12345])          # no such scalar handle
+    with pytest.raises(h2.H2aggError):
+        chip.add(p, 99)                       # no such point handle
+    chip.close()
