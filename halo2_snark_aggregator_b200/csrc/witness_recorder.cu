@@ -905,10 +905,11 @@ struct Recorder {
     p.has_curv = true;
     return p;
   }
-  HPoint assign_constant_point_with_curvature(bool identity, const Fq& x, const Fq& y) {  // :438-472
+  // `y_over_x`: the caller already holds y * x^-1 (constant_mul batches the inversions of its whole table)
+  HPoint assign_constant_point_with_curvature(bool identity, const Fq& x, const Fq& y, const Fq* y_over_x = nullptr) {  // :438-472
     Fq xv = identity ? q_zero() : x, yv = identity ? q_zero() : y;
     HPoint p;
-    p.curv.v = int_assign_constant(q_is_zero(xv) ? q_zero() : q_mul(yv, q_inv(xv)));
+    p.curv.v = int_assign_constant(q_is_zero(xv) ? q_zero() : (y_over_x ? *y_over_x : q_mul(yv, q_inv(xv))));
     p.curv.z = bg_assign_constant(q_is_zero(xv) ? 1 : 0);
     p.x = int_assign_constant(xv);
     p.y = int_assign_constant(yv);
@@ -1255,26 +1256,107 @@ struct Recorder {
   }
 };
 
-// native affine group law for constant_mul's table of constants (host, Fq Montgomery)
+// a constant point of constant_mul's table (host, Fq Montgomery)
 struct Aff {
   Fq x, y;
   bool inf;
 };
-static Aff aff_add(const Aff& p, const Aff& q) {
-  if (p.inf) return q;
-  if (q.inf) return p;
-  Fq lam;
-  if (memcmp(p.x.v, q.x.v, 32) == 0) {
-    Fq s = q_add(p.y, q.y);
-    if (q_is_zero(s)) return Aff{q_zero(), q_zero(), true};
-    Fq xx = q_mul(p.x, p.x);
-    lam = q_mul(q_add(q_add(xx, xx), xx), q_inv(q_add(p.y, p.y)));
-  } else {
-    lam = q_mul(q_sub(q.y, p.y), q_inv(q_sub(q.x, p.x)));
+// ---- the constant table of EccChipOps::constant_mul (chips/ecc_chip.rs:245-279) ---------------------------------
+// Per 2-bit window j the chip assigns the constants B_j, 2 B_j, 3 B_j with B_(j+1) = 4 B_j, each with its "curvature"
+// y / x.  Done with affine additions that is six field inversions per window on a sequential chain (127 windows); here the
+// chain runs in Jacobian coordinates and all 3 x 127 points are brought back with ONE inversion (Montgomery's trick), a
+// second batch gives every y / x.  Same field elements: affine coordinates are unique.
+struct Jac {
+  Fq X, Y, Z;
+};
+static Jac jac_dbl(const Jac& p) {  // a = 0: dbl-2009-l
+  Fq A = q_mul(p.X, p.X), B = q_mul(p.Y, p.Y), C = q_mul(B, B);
+  Fq t = q_add(p.X, B);
+  Fq D = q_sub(q_sub(q_mul(t, t), A), C);
+  D = q_add(D, D);
+  Fq E = q_add(q_add(A, A), A), F = q_mul(E, E);
+  Jac r;
+  r.X = q_sub(F, q_add(D, D));
+  Fq C8 = q_add(C, C);
+  C8 = q_add(C8, C8);
+  C8 = q_add(C8, C8);
+  r.Y = q_sub(q_mul(E, q_sub(D, r.X)), C8);
+  Fq yz = q_mul(p.Y, p.Z);
+  r.Z = q_add(yz, yz);
+  return r;
+}
+static Jac jac_add(const Jac& p, const Jac& q) {  // distinct, finite points: add-2007-bl
+  Fq Z1Z1 = q_mul(p.Z, p.Z), Z2Z2 = q_mul(q.Z, q.Z);
+  Fq U1 = q_mul(p.X, Z2Z2), U2 = q_mul(q.X, Z1Z1);
+  Fq S1 = q_mul(q_mul(p.Y, q.Z), Z2Z2), S2 = q_mul(q_mul(q.Y, p.Z), Z1Z1);
+  Fq H = q_sub(U2, U1);
+  Fq I = q_add(H, H);
+  I = q_mul(I, I);
+  Fq J = q_mul(H, I);
+  Fq rr = q_sub(S2, S1);
+  rr = q_add(rr, rr);
+  Fq V = q_mul(U1, I);
+  Jac r;
+  r.X = q_sub(q_sub(q_mul(rr, rr), J), q_add(V, V));
+  Fq S1J = q_mul(S1, J);
+  r.Y = q_sub(q_mul(rr, q_sub(V, r.X)), q_add(S1J, S1J));
+  Fq zs = q_add(p.Z, q.Z);
+  r.Z = q_mul(q_sub(q_sub(q_mul(zs, zs), Z1Z1), Z2Z2), H);
+  return r;
+}
+static void q_batch_inv(std::vector<Fq>& v) {  // in place; zeros stay zero
+  std::vector<Fq> pre(v.size());
+  Fq run = q_small(1);
+  for (size_t i = 0; i < v.size(); i++) {
+    pre[i] = run;
+    if (!q_is_zero(v[i])) run = q_mul(run, v[i]);
   }
-  Fq x3 = q_sub(q_sub(q_mul(lam, lam), p.x), q.x);
-  Fq y3 = q_sub(q_mul(lam, q_sub(p.x, x3)), p.y);
-  return Aff{x3, y3, false};
+  Fq inv = q_inv(run);
+  for (size_t i = v.size(); i-- > 0;) {
+    if (q_is_zero(v[i])) continue;
+    Fq t = q_mul(inv, pre[i]);
+    inv = q_mul(inv, v[i]);
+    v[i] = t;
+  }
+}
+struct ConstWindow {
+  Aff p[3];     // B, 2B, 3B
+  Fq lam[3];    // y / x of each (0 when x = 0)
+};
+static std::vector<ConstWindow> constant_mul_table(const Aff& base, size_t n_windows) {
+  std::vector<ConstWindow> out(n_windows);
+  if (base.inf || n_windows == 0) {
+    for (auto& w : out)
+      for (int t = 0; t < 3; t++) {
+        w.p[t] = Aff{q_zero(), q_zero(), true};
+        w.lam[t] = q_zero();
+      }
+    return out;
+  }
+  // BN254 G1 has prime order and no point with y = 0: k * B for k = 4^j * {1, 2, 3} is never the identity, and the
+  // operands of every addition below are distinct
+  std::vector<Jac> pts(3 * n_windows);
+  Jac b{base.x, base.y, q_small(1)};
+  for (size_t j = 0; j < n_windows; j++) {
+    Jac b2 = jac_dbl(b), b3 = jac_add(b2, b);
+    pts[3 * j] = b;
+    pts[3 * j + 1] = b2;
+    pts[3 * j + 2] = b3;
+    b = jac_dbl(b2);
+  }
+  std::vector<Fq> zi(pts.size());
+  for (size_t i = 0; i < pts.size(); i++) zi[i] = pts[i].Z;
+  q_batch_inv(zi);
+  std::vector<Fq> xi(pts.size());
+  for (size_t i = 0; i < pts.size(); i++) {
+    Fq z2 = q_mul(zi[i], zi[i]);
+    Aff a{q_mul(pts[i].X, z2), q_mul(pts[i].Y, q_mul(z2, zi[i])), false};
+    out[i / 3].p[i % 3] = a;
+    xi[i] = a.x;
+  }
+  q_batch_inv(xi);
+  for (size_t i = 0; i < pts.size(); i++) out[i / 3].lam[i % 3] = q_mul(out[i / 3].p[i % 3].y, xi[i]);
+  return out;
 }
 
 }  // namespace wit
@@ -1417,19 +1499,20 @@ int64_t h2agg_wit_ecc_constant_mul(h2agg_witness* w, const uint64_t base_xy[8], 
     auto bits_be = r.decompose_scalar(r.scalars.at(s), 2);
     HPoint identity = r.assign_constant_point_with_curvature(true, q_zero(), q_zero());
     Aff base{fq_from_mont_words(base_xy), fq_from_mont_words(base_xy + 4), is_identity_affine(base_xy)};
+    const std::vector<ConstWindow> table = constant_mul_table(base, bits_be.size());   // all inversions batched
     bool have = false;
     HPoint acc;
-    for (auto it = bits_be.rbegin(); it != bits_be.rend(); ++it) {
-      Aff b2 = aff_add(base, base), b3 = aff_add(b2, base);
-      HPoint c01 = r.assign_constant_point_with_curvature(b2.inf, b2.x, b2.y);
-      HPoint c10 = r.assign_constant_point_with_curvature(base.inf, base.x, base.y);
-      HPoint c11 = r.assign_constant_point_with_curvature(b3.inf, b3.x, b3.y);
+    size_t j = 0;
+    for (auto it = bits_be.rbegin(); it != bits_be.rend(); ++it, ++j) {
+      const ConstWindow& cw = table[j];   // B_j, 2 B_j, 3 B_j with B_(j+1) = 4 B_j
+      HPoint c01 = r.assign_constant_point_with_curvature(cw.p[1].inf, cw.p[1].x, cw.p[1].y, &cw.lam[1]);
+      HPoint c10 = r.assign_constant_point_with_curvature(cw.p[0].inf, cw.p[0].x, cw.p[0].y, &cw.lam[0]);
+      HPoint c11 = r.assign_constant_point_with_curvature(cw.p[2].inf, cw.p[2].x, cw.p[2].y, &cw.lam[2]);
       HPoint c0 = r.bisec_point_with_curvature((*it)[0], c10, identity);
       HPoint c1 = r.bisec_point_with_curvature((*it)[0], c11, c01);
       HPoint slot = r.bisec_point_with_curvature((*it)[1], c1, c0);
       if (!have) { acc = slot; have = true; }
       else acc = r.ecc_add(slot, acc);
-      base = aff_add(b3, base);
     }
     r.points.push_back(acc);
   });

@@ -215,3 +215,29 @@ def test_recorder_rejects_an_empty_multi_exp_and_bad_handles():
     with pytest.raises(h2.H2aggError):
         chip.add(p, 99)                       # no such point handle
     chip.close()
+
+
+def test_scalar_mul_constant_values_with_the_batched_constant_table():
+    """constant_mul builds its 127 x {B, 2B, 3B} table on a Jacobian chain with batched inversions: results equal s * B for
+    random and edge scalars, the identity base gives the identity, and the row count does not depend on the values."""
+    rng = random.Random(77)
+    rows = set()
+    for s in [0, 1, 2, 3, ref.R - 1, 1 << 200] + [rng.randrange(ref.R) for _ in range(4)]:
+        base = ref.g1_mul(rng.randrange(1, ref.R), ref.G1_GEN)
+        chip = h2.B200EccChip()
+        hs = chip.assign_scalar(s)
+        o = chip.rows()
+        h = chip.scalar_mul_constant(hs, ws.xy_mont(base))
+        rows.add(chip.rows() - o)
+        xy, ident = chip.to_value(h)
+        want = ref.g1_mul(s, base)
+        if want is None:
+            assert ident
+        else:
+            assert not ident and np.array_equal(xy, ws.xy_mont(want))
+        chip.close()
+    assert len(rows) == 1
+    chip = h2.B200EccChip()
+    h = chip.scalar_mul_constant(chip.assign_scalar(12345), np.zeros(8, dtype=np.uint64))   # identity base
+    assert chip.to_value(h)[1]
+    chip.close()
